@@ -1,0 +1,238 @@
+/*
+ * ttrl_b200.h -- C ABI of the B200-native batched simulator for the TopoTrafficRL per-step hot path.
+ *
+ * The reference (pure Python, /root/reference) has no FFI: its boundary is the gymnasium Env protocol
+ * (ttrl_env/envs/common/abstract.py:188-250) and the agent protocol (ttrl_agent/agents/deep_q_network/
+ * abstract.py:65-83).  This header is the C-ABI drop-in that sits directly under that Python boundary:
+ * the host package (topotrafficrl_b200/) mirrors the reference classes and binds these entry points
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types cross the ABI;
+ *  - every function returns 0 on success, non-zero on failure; ttrl_last_error() gives the message;
+ *  - "dev" pointers are device pointers on the sim's device (borrowed, never freed by the library);
+ *    "host" pointers are ordinary host memory;
+ *  - no internal threads; kernels are launched on the stream passed by the caller (0 = legacy default);
+ *  - E = number of env instances, V = vehicle slots per env (capacity), L = lanes.
+ *
+ * All simulation arithmetic is IEEE float64, like the reference (numpy float64 scalars throughout);
+ * observations and rewards are emitted as float32 like the reference's (observation.py:275).
+ */
+#ifndef TTRL_B200_H
+#define TTRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Road network: flat lane table in RoadNetwork.graph insertion order (road/road.py:55-71 iterates the
+ * dict in that order and np.argmin keeps the first minimum, so the order is part of the semantics).
+ * ---------------------------------------------------------------------------------------------- */
+enum { TTRL_LANE_STRAIGHT = 0, TTRL_LANE_CIRCULAR = 1, TTRL_LANE_SINE = 2 };
+
+typedef struct ttrl_lane {
+    int32_t kind;        /* TTRL_LANE_* (road/lane.py:159, :236, :311) */
+    int32_t road;        /* index into the road table: the (_from,_to) pair this lane belongs to */
+    int32_t lane_id;     /* index of the lane inside its road (third element of a LaneIndex) */
+    int32_t priority;    /* lane.priority (regulation.py:73-76) */
+    int32_t forbidden;   /* lane.forbidden (lane.py:111) */
+    int32_t is_exit;     /* "il" in _from and "o" in _to (intersection_env.py:352-353, :366-367) */
+    int32_t pad0, pad1;
+    double ax, ay;       /* straight/sine: start; circular: center */
+    double dx, dy;       /* straight/sine: unit direction (lane.py:190); lateral = (-dy, dx) */
+    double heading;      /* straight/sine: arctan2 of end-start (lane.py:185) */
+    double length;       /* lane.length */
+    double width;        /* lane.width */
+    double speed_limit;  /* lane.speed_limit */
+    double radius, start_phase, end_phase, cdir; /* circular: cdir = +1 clockwise / -1 (lane.py:333) */
+    double amplitude, pulsation, phase;          /* sine (lane.py:264-266) */
+    double pad2;
+} ttrl_lane;
+
+typedef struct ttrl_road {
+    int32_t from_node, to_node; /* node ids (strings in the reference, interned by the host) */
+    int32_t first_lane;         /* flat index of lane_id 0 of this road */
+    int32_t n_lanes;            /* len(graph[_from][_to]) */
+} ttrl_road;
+
+#define TTRL_MAX_LANES 64
+#define TTRL_MAX_ROADS 64
+#define TTRL_MAX_NODES 64
+#define TTRL_MAX_TARGET_SPEEDS 8
+#define TTRL_MAX_FEATURES 8
+#define TTRL_ROUTE_CAP 4
+
+/* Observation feature ids (vehicle/kinematics.py:237-261, the subset the hot configs use). */
+enum { TTRL_F_PRESENCE = 0, TTRL_F_X = 1, TTRL_F_Y = 2, TTRL_F_VX = 3, TTRL_F_VY = 4,
+       TTRL_F_COS_H = 5, TTRL_F_SIN_H = 6, TTRL_F_HEADING = 7, TTRL_F_ON_ROAD = 8 };
+enum { TTRL_OBS_KINEMATICS = 0, TTRL_OBS_GRID = 1 };
+enum { TTRL_ORDER_SORTED = 0, TTRL_ORDER_SHUFFLED = 1 };
+/* DiscreteMetaAction tables (envs/common/action.py:204-211) */
+enum { TTRL_ACT_ALL = 0 /* 0 LANE_LEFT 1 IDLE 2 LANE_RIGHT 3 FASTER 4 SLOWER */,
+       TTRL_ACT_LONGI = 1 /* 0 SLOWER 1 IDLE 2 FASTER */,
+       TTRL_ACT_LAT = 2 /* 0 LANE_LEFT 1 IDLE 2 LANE_RIGHT */ };
+enum { TTRL_REWARD_INTERSECTION = 0 /* intersection_env.py:78-104 */,
+       TTRL_REWARD_HIGHWAY = 1 /* u_turn_env.py:39-71 template on the synthetic highway */ };
+
+typedef struct ttrl_config {
+    /* network sizes */
+    int32_t n_lanes, n_roads, n_nodes, pad0;
+    /* timing (abstract.py:97-98, :252-256) */
+    double simulation_frequency, policy_frequency, duration;
+    /* RegulatedRoad (regulation.py:14-15, :28-32): regulated != 0 enables enforce_road_rules */
+    int32_t regulated, pad1;
+    /* IDM / MOBIL class constants (behavior.py:20-46; intersection_env.py:258-261 overrides) */
+    double acc_max, comfort_acc_max, comfort_acc_min, distance_wanted, time_wanted;
+    double politeness, lane_change_min_acc_gain, lane_change_max_braking_imposed, lane_change_delay;
+    /* MDPVehicle (controller.py:259, :317-344) + DiscreteMetaAction (action.py:199-260) */
+    int32_t n_target_speeds, action_mode;
+    double target_speeds[TTRL_MAX_TARGET_SPEEDS];
+    /* observation (observation.py:154-275 Kinematics, :278-498 OccupancyGrid) */
+    int32_t obs_type, obs_vehicles, n_features, absolute, order, see_behind, normalize, clip;
+    int32_t features[TTRL_MAX_FEATURES];
+    /* per-feature normalisation range; has_range[i]==0 -> feature i is not in features_range */
+    int32_t has_range[TTRL_MAX_FEATURES];
+    double range_lo[TTRL_MAX_FEATURES], range_hi[TTRL_MAX_FEATURES];
+    /* OccupancyGrid: features_range of "x"/"y" even when x/y are not observed features (observation.py:375-392) */
+    int32_t grid_has_xrange, grid_has_yrange, grid_w, grid_h, align_to_vehicle_axes, as_image, pad2, pad3;
+    double grid_xrange[2], grid_yrange[2];
+    double grid_min[2], grid_max[2], grid_step[2];
+    /* reward / termination */
+    int32_t reward_type, normalize_reward, offroad_terminal, pad4;
+    double collision_reward, high_speed_reward, arrived_reward, lane_reward;
+    double reward_speed_lo, reward_speed_hi;
+    /* IntersectionEnv spawn / clear (intersection_env.py:320-362) */
+    int32_t spawn_enabled, pad5;
+    double spawn_probability;
+} ttrl_config;
+
+/* ------------------------------------------------------------------------------------------------
+ * Vehicle state, struct-of-arrays.  Field f of slot s of env e lives at  buf[(f*E + e)*V + s].
+ * Slots 0..n_vehicles[e]-1 are live, in Road.vehicles list order (order is semantic: road.py:461-478).
+ * ---------------------------------------------------------------------------------------------- */
+enum { TTRL_D_X = 0, TTRL_D_Y, TTRL_D_HEADING, TTRL_D_SPEED, TTRL_D_STEERING, TTRL_D_ACCEL,
+       TTRL_D_TARGET_SPEED, TTRL_D_TIMER, TTRL_D_DELTA, TTRL_D_IMPACT_X, TTRL_D_IMPACT_Y, TTRL_ND = 11 };
+enum { TTRL_I_LANE = 0, TTRL_I_TARGET_LANE, TTRL_I_FLAGS, TTRL_I_SPEED_INDEX, TTRL_I_ROUTE_LEN,
+       TTRL_I_ROUTE_ROAD, TTRL_I_ROUTE_LANE, TTRL_I_YIELD_TIMER, TTRL_NI = 8 };
+/* TTRL_I_FLAGS bits */
+enum { TTRL_FL_MDP = 1 /* MDPVehicle (else IDMVehicle) */, TTRL_FL_CRASHED = 2, TTRL_FL_HAS_IMPACT = 4,
+       TTRL_FL_YIELDING = 8 /* is_yielding attribute is True */, TTRL_FL_CONTROLLED = 16 /* in env.controlled_vehicles */ };
+/* TTRL_I_ROUTE_LEN: -1 = route is None, else number of remaining entries (<= TTRL_ROUTE_CAP).
+ * TTRL_I_ROUTE_ROAD / TTRL_I_ROUTE_LANE: entry k in byte k (road index / lane id, 0xFF = None). */
+
+/* Per-env scalars: ibuf[f*E + e], dbuf[f*E + e] */
+enum { TTRL_EI_NVEH = 0, TTRL_EI_STEPS /* env.steps, abstract.py:273 */, TTRL_EI_ROAD_STEPS /* RegulatedRoad.steps */,
+       TTRL_EI_EGO /* slot of controlled_vehicles[0] */, TTRL_EI_EPISODE, TTRL_EI_DONE, TTRL_NEI = 6 };
+enum { TTRL_ED_TIME = 0 /* env.time, abstract.py:239 */, TTRL_ED_RETURN, TTRL_NED = 2 };
+
+/* Spawn draws injected for parity (the reference draws from numpy PCG64: intersection_env.py:328-346,
+ * behavior.py:66-69).  One record per env per step; u_spawn > spawn_probability means "no spawn". */
+typedef struct ttrl_spawn_draw {
+    double u_spawn;      /* np_random.uniform()                      (:328) */
+    int32_t entry, exit; /* np_random.choice(range(4), 2, False)      (:331) */
+    double n_pos, n_speed; /* np_random.normal() x2                   (:338, :340) */
+    double delta;        /* np_random.uniform(3.5, 4.5)               (behavior.py:67) */
+} ttrl_spawn_draw;
+
+/* Episode statistics accumulated on device (maps to Evaluation.after_all_episodes, trainer/evaluation.py:325-333) */
+typedef struct ttrl_episode_stats {
+    double episodes, total_return, total_length, crashes, arrivals, total_speed, vehicle_steps, env_steps;
+} ttrl_episode_stats;
+
+typedef struct ttrl_sim ttrl_sim;
+typedef struct ttrl_qnet ttrl_qnet;
+
+const char* ttrl_last_error(void);
+int ttrl_abi_version(void);
+
+/* Create E env instances with V vehicle slots each on CUDA device `device`.
+ * Replaces: AbstractEnv.__init__/configure (abstract.py:44-113) + _make_road (intersection_env.py:141-249,
+ * road.py:291-321) for a batch.  `node_roads`/`node_first`: CSR adjacency "roads starting at node n" in
+ * graph[_to].keys() order (road.py:126). */
+int ttrl_sim_create(const ttrl_config* cfg, const ttrl_lane* lanes, const ttrl_road* roads,
+                    const int32_t* node_first /* n_nodes+1 */, const int32_t* node_roads,
+                    int num_envs, int vcap, int device, ttrl_sim** out);
+int ttrl_sim_destroy(ttrl_sim* sim);
+int ttrl_sim_num_envs(const ttrl_sim* sim);
+int ttrl_sim_vcap(const ttrl_sim* sim);
+int ttrl_sim_obs_size(const ttrl_sim* sim); /* floats per env */
+
+/* Resync / golden capture (host buffers, layout above).  Replaces direct attribute access on
+ * Vehicle objects (kinematics.py:34-48, controller.py:35-48, behavior.py:48-64). */
+int ttrl_sim_set_state(ttrl_sim* sim, const double* veh_d, const int32_t* veh_i,
+                       const int32_t* env_i, const double* env_d);
+int ttrl_sim_get_state(ttrl_sim* sim, double* veh_d, int32_t* veh_i, int32_t* env_i, double* env_d);
+
+/* Store the current state as reset pool entry `slot` (autoreset source; reset itself stays on the host:
+ * AbstractEnv.reset, abstract.py:188-214).  Env e restarts from pool entry (e + k*E) mod pool_size at its k-th reset. */
+int ttrl_sim_set_reset_pool(ttrl_sim* sim, int pool_size, const double* veh_d, const int32_t* veh_i,
+                            const int32_t* env_i, const double* env_d);
+int ttrl_sim_set_autoreset(ttrl_sim* sim, int enabled);
+
+/* One simulation sub-step for every env: [ego meta-action if steps % F == 0] -> Road.act -> (regulation)
+ * -> Road.step.  Replaces one iteration of AbstractEnv._simulate (abstract.py:257-273).
+ * actions_dev: int32[E] or NULL (no action, like action=None). */
+int ttrl_sim_substep(ttrl_sim* sim, const int32_t* actions_dev, void* stream);
+
+/* One env.step() for every env.  Replaces AbstractEnv.step (abstract.py:224-250) +
+ * IntersectionEnv.step's clear/spawn (intersection_env.py:135-139).
+ * obs_dev float32[E*obs_size]; reward_dev float32[E]; terminated_dev/truncated_dev uint8[E]. */
+int ttrl_sim_step(ttrl_sim* sim, const int32_t* actions_dev, float* obs_dev, float* reward_dev,
+                  uint8_t* terminated_dev, uint8_t* truncated_dev, void* stream);
+
+/* Same call with HOST buffers: H2D of actions, the step, D2H of obs/reward/flags, synchronised on return.
+ * This is the reference-facing end-to-end form (one gym step for E envs from numpy arrays). */
+int ttrl_sim_step_host(ttrl_sim* sim, const int32_t* actions_host, float* obs_host, float* reward_host,
+                       uint8_t* terminated_host, uint8_t* truncated_host);
+
+/* Observation only (observation_type.observe() at reset: abstract.py:210). */
+int ttrl_sim_observe(ttrl_sim* sim, float* obs_dev, void* stream);
+
+/* Parity hooks: feed the oracle's RNG draws (spawn decisions; Kinematics "shuffled" permutations). */
+int ttrl_sim_inject_spawn(ttrl_sim* sim, const ttrl_spawn_draw* draws_host /* E records or NULL to clear */);
+int ttrl_sim_inject_shuffle(ttrl_sim* sim, const int32_t* perm_host /* E*(obs_vehicles-1) or NULL */);
+int ttrl_sim_seed(ttrl_sim* sim, uint64_t seed, int64_t first_global_env);
+
+int ttrl_sim_read_stats(ttrl_sim* sim, ttrl_episode_stats* out_host, int reset_after_read);
+/* number of kernel launches issued by this sim so far (bench.py's gpu_launches) */
+int64_t ttrl_sim_launch_count(const ttrl_sim* sim);
+
+/* ------------------------------------------------------------------------------------------------
+ * DQN Q-network rollout.  Replaces AbstractDQNAgent.act (deep_q_network/abstract.py:65-83) ->
+ * DQNAgent.get_batch_state_action_values (pytorch.py:79-80) -> EpsilonGreedy.update/sample
+ * (exploration/epsilon_greedy.py:32-48, exploration/abstract.py:20-25) for a batch of E observations.
+ * ---------------------------------------------------------------------------------------------- */
+enum { TTRL_QNET_MLP = 0 /* models.py:50-76 */, TTRL_QNET_EGO_ATTENTION = 1 /* models.py:237-312 */,
+       TTRL_QNET_DUELING = 2 /* models.py:79-104 */ };
+
+typedef struct ttrl_qnet_desc {
+    int32_t type;
+    int32_t n_entities, n_features;   /* observation (V, Fe) */
+    int32_t n_actions;
+    int32_t n_hidden;                 /* MLP / dueling base: number of hidden layers */
+    int32_t hidden[4];                /* their sizes */
+    int32_t embed_layers, embed[4];   /* ego-attention: embedding MLP sizes (ego and others share shapes) */
+    int32_t feature_size, heads;      /* EgoAttention */
+    int32_t out_layers, out_hidden[4];/* output_layer MLP */
+    int32_t presence_feature_idx;
+} ttrl_qnet_desc;
+
+/* weights_host: all parameters as one float32 blob in the order documented in INTEGRATION.md
+ * (reference state_dict order: models.py:56-59, :163-166, :249-255). */
+int ttrl_qnet_create(const ttrl_qnet_desc* desc, const float* weights_host, int64_t n_weights,
+                     int device, ttrl_qnet** out);
+int ttrl_qnet_destroy(ttrl_qnet* q);
+/* Q-values + epsilon-greedy action for E observations.  q_dev may be NULL.  epsilon<=0 -> Greedy. */
+int ttrl_qnet_act(ttrl_qnet* q, const float* obs_dev, int num_envs, double epsilon, uint64_t seed,
+                  uint64_t step, int32_t* actions_dev, float* q_dev, void* stream);
+/* tensor-core (tcgen05) variant of the forward: same outputs, bf16 operands / fp32 accumulate. */
+int ttrl_qnet_act_tc(ttrl_qnet* q, const float* obs_dev, int num_envs, double epsilon, uint64_t seed,
+                     uint64_t step, int32_t* actions_dev, float* q_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTRL_B200_H */

@@ -1,0 +1,318 @@
+"""Scene builders: road networks, device configs and initial traffic for the hot-path configurations.
+
+* intersection scene = ``IntersectionEnv._make_road`` (reference intersection_env.py:141-249): 4 corners x
+  (incoming straight 100 m, right-turn arc R=9, left-turn arc R=13, crossing straight, exit straight 100 m).
+* highway scene = ``RoadNetwork.straight_road_network`` (road.py:291-321) populated like
+  ``Vehicle.create_random`` (kinematics.py:50-104): the reference ships no HighwayEnv, so BASELINE
+  configs 2/3 are synthetic scenes composed from those reference primitives.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+from .road import AbstractLane, CircularLane, LineType, NetworkTable, RoadNetwork, StraightLane
+from .state import SimState
+
+# --------------------------------------------------------------------------------------------------
+# default configs (same keys as the reference: abstract.py:94-109, intersection_env.py:20-58)
+# --------------------------------------------------------------------------------------------------
+BASE_CONFIG = {
+    "observation": {"type": "Kinematics"},
+    "action": {"type": "DiscreteMetaAction"},
+    "simulation_frequency": 15,
+    "policy_frequency": 1,
+    "other_vehicles_type": "ttrl_env.vehicle.behavior.IDMVehicle",
+    "screen_width": 600, "screen_height": 150, "centering_position": [0.3, 0.5], "scaling": 5.5,
+    "show_trajectories": False, "render_agent": True, "offscreen_rendering": False,
+    "manual_control": False, "real_time_rendering": False,
+}
+
+INTERSECTION_CONFIG = dict(BASE_CONFIG, **{
+    "observation": {
+        "type": "Kinematics", "vehicles_count": 15,
+        "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+        "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]},
+        "absolute": True, "flatten": False, "observe_intentions": False,
+    },
+    "action": {"type": "DiscreteMetaAction", "longitudinal": True, "lateral": False, "target_speeds": [0, 4.5, 9]},
+    "duration": 13, "destination": "o1", "controlled_vehicles": 1, "initial_vehicle_count": 10,
+    "spawn_probability": 0.6, "screen_width": 600, "screen_height": 600, "centering_position": [0.5, 0.6],
+    "scaling": 5.5 * 1.3, "collision_reward": -5, "high_speed_reward": 1, "arrived_reward": 1,
+    "reward_speed_range": [7.0, 9.0], "normalize_reward": False, "offroad_terminal": False,
+})
+
+# Synthetic highway (BASELINE configs 2 and 3).  Reward template: u_turn_env.py:20-71.
+HIGHWAY_CONFIG = dict(BASE_CONFIG, **{
+    "observation": {
+        "type": "Kinematics", "vehicles_count": 15,
+        "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+        "absolute": False, "order": "sorted",
+    },
+    "action": {"type": "DiscreteMetaAction"},
+    "lanes_count": 4, "vehicles_count": 50, "vehicles_density": 2.0, "ego_spacing": 2.0,
+    "road_length": 10000, "speed_limit": 30,
+    "duration": 40, "collision_reward": -1.0, "left_lane_reward": 0.1, "high_speed_reward": 0.4,
+    "reward_speed_range": [20, 30], "normalize_reward": True, "offroad_terminal": False,
+})
+
+# IDM/MOBIL class constants: behavior.py:20-46; the intersection scene overrides three of them
+# process-wide (intersection_env.py:258-261) -- here they are per-scene constants.
+IDM_DEFAULT = dict(acc_max=6.0, comfort_acc_max=3.0, comfort_acc_min=-5.0, distance_wanted=5.0 + 5.0,
+                   time_wanted=1.5, politeness=0.0, lane_change_min_acc_gain=0.2,
+                   lane_change_max_braking_imposed=2.0, lane_change_delay=1.0)
+IDM_INTERSECTION = dict(IDM_DEFAULT, distance_wanted=7.0, comfort_acc_max=6.0, comfort_acc_min=-3.0)
+
+
+# --------------------------------------------------------------------------------------------------
+# networks
+# --------------------------------------------------------------------------------------------------
+def make_intersection_network() -> RoadNetwork:
+    """4-way intersection.  Node names: (o|ir|il)+corner, corner 0 south, 1 west, 2 north, 3 east."""
+    w = AbstractLane.DEFAULT_WIDTH
+    r_right = w + 5
+    r_left = r_right + w
+    outer = r_right + w / 2
+    access = 50 + 50
+    n, c, s = LineType.NONE, LineType.CONTINUOUS, LineType.STRIPED
+    net = RoadNetwork()
+    for k in range(4):
+        angle = np.radians(90 * k)
+        horizontal = k % 2
+        prio = 3 if horizontal else 1
+        rot = np.array([[np.cos(angle), -np.sin(angle)], [np.sin(angle), np.cos(angle)]])
+        o, ir = f"o{k}", f"ir{k}"
+        # incoming
+        net.add_lane(o, ir, StraightLane(rot @ np.array([w / 2, access + outer]), rot @ np.array([w / 2, outer]),
+                                         line_types=[s, c], priority=prio, speed_limit=10))
+        # right turn
+        net.add_lane(ir, f"il{(k - 1) % 4}",
+                     CircularLane(rot @ np.array([outer, outer]), r_right, angle + np.radians(180),
+                                  angle + np.radians(270), line_types=[n, c], priority=prio, speed_limit=10))
+        # left turn
+        net.add_lane(ir, f"il{(k + 1) % 4}",
+                     CircularLane(rot @ np.array([-r_left + w / 2, r_left - w / 2]), r_left, angle + np.radians(0),
+                                  angle + np.radians(-90), clockwise=False, line_types=[n, n],
+                                  priority=prio - 1, speed_limit=10))
+        # straight across
+        net.add_lane(ir, f"il{(k + 2) % 4}",
+                     StraightLane(rot @ np.array([w / 2, outer]), rot @ np.array([w / 2, -outer]),
+                                  line_types=[s, n], priority=prio, speed_limit=10))
+        # exit
+        ex_start = rot @ np.flip([w / 2, access + outer], axis=0)
+        ex_end = rot @ np.flip([w / 2, outer], axis=0)
+        net.add_lane(f"il{(k - 1) % 4}", f"o{(k - 1) % 4}",
+                     StraightLane(ex_end, ex_start, line_types=[n, c], priority=prio, speed_limit=10))
+    return net
+
+
+def intersection_exit_predicate(_from: str, _to: str) -> bool:
+    return "il" in _from and "o" in _to
+
+
+def make_highway_network(lanes: int = 4, length: float = 10000, speed_limit: float = 30) -> RoadNetwork:
+    return RoadNetwork.straight_road_network(lanes=lanes, length=length, speed_limit=speed_limit)
+
+
+def intersection_spawn_routes(net: RoadNetwork, table: NetworkTable):
+    """Route table for ``_spawn_vehicle`` (intersection_env.py:331-345): entry lane per corner and, per
+    (entry, exit) pair, the road indices that follow the entry lane in ``plan_route_to``'s BFS path."""
+    spawn_lane = np.zeros(4, np.int32)
+    rlen = np.zeros((4, 4), np.int32)
+    rroad = np.zeros((4, 4, abi.ROUTE_CAP), np.int32)
+    for a in range(4):
+        idx = (f"o{a}", f"ir{a}", 0)
+        spawn_lane[a] = table.flat(idx)
+        for b in range(4):
+            if a == b:
+                continue
+            route = net.plan_route(idx, f"o{b}")[1:]
+            rlen[a, b] = len(route)
+            for k, (f, t, _) in enumerate(route):
+                rroad[a, b, k] = table.road_index_of[(f, t)]
+    return spawn_lane, rlen, rroad
+
+
+# --------------------------------------------------------------------------------------------------
+# dict config -> device config
+# --------------------------------------------------------------------------------------------------
+def _resolve_observation(obs_cfg: dict) -> dict:
+    if obs_cfg["type"] == "MultiAgentObservation":
+        return obs_cfg["observation_config"]
+    return obs_cfg
+
+
+def build_config(table: NetworkTable, config: dict, scene: str, ego_lanes_count: int = 1) -> abi.Config:
+    """Translate a reference-style env config dict into the POD the device uses.
+
+    Unknown observation / action types raise ``ValueError`` like the reference factories
+    (observation.py:793, action.py:344)."""
+    cfg = abi.Config()
+    cfg.n_lanes, cfg.n_roads, cfg.n_nodes = table.n_lanes, table.n_roads, table.n_nodes
+    cfg.simulation_frequency = float(config["simulation_frequency"])
+    cfg.policy_frequency = float(config["policy_frequency"])
+    cfg.duration = float(config["duration"])
+    idm = IDM_INTERSECTION if scene == "intersection" else IDM_DEFAULT
+    for k, v in idm.items():
+        setattr(cfg, k, float(v))
+    cfg.regulated = 1 if scene == "intersection" else 0
+
+    # ---- action -------------------------------------------------------------------------------
+    act = config["action"]
+    if act["type"] == "MultiAgentAction":
+        act = act["action_config"]
+    if act["type"] != "DiscreteMetaAction":
+        if act["type"] in ("ContinuousAction", "DiscreteAction"):
+            raise NotImplementedError(f"action type {act['type']} is outside the B200 hot path (SURVEY.md section 2 row 14)")
+        raise ValueError("Unknown action type")
+    longitudinal, lateral = act.get("longitudinal", True), act.get("lateral", True)
+    if longitudinal and lateral:
+        cfg.action_mode = abi.ACT_ALL
+    elif longitudinal:
+        cfg.action_mode = abi.ACT_LONGI
+    elif lateral:
+        cfg.action_mode = abi.ACT_LAT
+    else:
+        raise ValueError("At least longitudinal or lateral actions must be included")
+    ts = act.get("target_speeds")
+    ts = np.linspace(20, 30, 3) if ts is None else np.asarray(ts, dtype=np.float64)
+    if len(ts) > abi.MAX_TARGET_SPEEDS:
+        raise ValueError("too many target speeds")
+    cfg.n_target_speeds = len(ts)
+    for k, v in enumerate(ts):
+        cfg.target_speeds[k] = float(v)
+
+    # ---- observation --------------------------------------------------------------------------
+    obs = _resolve_observation(config["observation"])
+    otype = obs["type"]
+    if otype == "Kinematics":
+        cfg.obs_type = abi.OBS_KINEMATICS
+        features = obs.get("features") or ["presence", "x", "y", "vx", "vy"]
+        cfg.obs_vehicles = int(obs.get("vehicles_count", 5))
+        cfg.absolute = int(bool(obs.get("absolute", False)))
+        order = obs.get("order", "sorted")
+        cfg.order = abi.ORDER_SHUFFLED if order == "shuffled" else abi.ORDER_SORTED
+        cfg.see_behind = int(bool(obs.get("see_behind", False)))
+        cfg.normalize = int(bool(obs.get("normalize", True)))
+        cfg.clip = int(bool(obs.get("clip", True)))
+        frange = obs.get("features_range")
+        if not frange:  # lazily derived from the ego's road in the reference (observation.py:213-225)
+            frange = {"x": [-5.0 * 40.0, 5.0 * 40.0],
+                      "y": [-AbstractLane.DEFAULT_WIDTH * ego_lanes_count, AbstractLane.DEFAULT_WIDTH * ego_lanes_count],
+                      "vx": [-2 * 40.0, 2 * 40.0], "vy": [-2 * 40.0, 2 * 40.0]}
+    elif otype == "OccupancyGrid":
+        cfg.obs_type = abi.OBS_GRID
+        features = obs.get("features")
+        if features is None:
+            features = ["presence", "vx", "vy", "on_road"]
+        if obs.get("absolute", False):
+            raise NotImplementedError()  # like the reference (observation.py:357-358)
+        grid_size = np.array(obs.get("grid_size") or [[-5.5 * 5, 5.5 * 5], [-5.5 * 5, 5.5 * 5]], dtype=np.float64)
+        grid_step = np.array(obs.get("grid_step") or [5, 5], dtype=np.float64)
+        shape = np.asarray(np.floor((grid_size[:, 1] - grid_size[:, 0]) / grid_step), dtype=np.uint8)
+        cfg.grid_w, cfg.grid_h = int(shape[0]), int(shape[1])
+        for k in range(2):
+            cfg.grid_min[k], cfg.grid_max[k], cfg.grid_step[k] = grid_size[k, 0], grid_size[k, 1], grid_step[k]
+        cfg.align_to_vehicle_axes = int(bool(obs.get("align_to_vehicle_axes", False)))
+        cfg.as_image = int(bool(obs.get("as_image", False)))
+        if cfg.as_image:
+            raise NotImplementedError("as_image grids are outside the B200 hot path")
+        cfg.clip = int(bool(obs.get("clip", True)))
+        cfg.obs_vehicles = 0
+        frange = obs.get("features_range")
+        if not frange:
+            frange = {"vx": [-2 * 40.0, 2 * 40.0], "vy": [-2 * 40.0, 2 * 40.0]}
+        if "x" in frange:
+            cfg.grid_has_xrange = 1
+            cfg.grid_xrange[0], cfg.grid_xrange[1] = float(frange["x"][0]), float(frange["x"][1])
+        if "y" in frange:
+            cfg.grid_has_yrange = 1
+            cfg.grid_yrange[0], cfg.grid_yrange[1] = float(frange["y"][0]), float(frange["y"][1])
+    else:
+        known = ("TimeToCollision", "KinematicsGoal", "GrayscaleObservation", "AttributesObservation",
+                 "MultiAgentObservation", "TupleObservation", "LidarObservation", "ExitObservation")
+        if otype in known:
+            raise NotImplementedError(f"observation type {otype} is outside the B200 hot path (SURVEY.md section 2 row 13)")
+        raise ValueError("Unknown observation type")
+    if len(features) > abi.MAX_FEATURES:
+        raise ValueError("too many observation features")
+    cfg.n_features = len(features)
+    for k, name in enumerate(features):
+        if name not in abi.FEATURES:
+            raise NotImplementedError(f"observation feature {name!r} is outside the B200 hot path")
+        cfg.features[k] = abi.FEATURES[name]
+        if name in frange:
+            cfg.has_range[k] = 1
+            cfg.range_lo[k], cfg.range_hi[k] = float(frange[name][0]), float(frange[name][1])
+
+    # ---- reward / termination -------------------------------------------------------------------
+    if scene == "intersection":
+        cfg.reward_type = abi.REWARD_INTERSECTION
+        cfg.arrived_reward = float(config.get("arrived_reward", 0))
+        cfg.spawn_enabled = 1
+        cfg.spawn_probability = float(config["spawn_probability"])
+    else:
+        cfg.reward_type = abi.REWARD_HIGHWAY
+        cfg.lane_reward = float(config.get("left_lane_reward", 0))
+    cfg.collision_reward = float(config.get("collision_reward", 0))
+    cfg.high_speed_reward = float(config.get("high_speed_reward", 0))
+    cfg.reward_speed_lo, cfg.reward_speed_hi = (float(x) for x in config["reward_speed_range"])
+    cfg.normalize_reward = int(bool(config.get("normalize_reward", False)))
+    cfg.offroad_terminal = int(bool(config.get("offroad_terminal", False)))
+    return cfg
+
+
+def merged_config(default: dict, overrides: Optional[dict]) -> dict:
+    """``AbstractEnv.configure`` semantics: a SHALLOW ``dict.update`` (abstract.py:111-113)."""
+    cfg = copy.deepcopy(default)
+    if overrides:
+        cfg.update(copy.deepcopy(overrides))
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------------
+# highway traffic generator (vectorised over envs)
+# --------------------------------------------------------------------------------------------------
+def make_highway_state(num_envs: int, config: dict, seed: int = 0, first_env: int = 0, vcap: Optional[int] = None) -> SimState:
+    """Initial traffic for the synthetic highway, following ``Vehicle.create_random``'s placement rule
+    (kinematics.py:91-103): each new vehicle goes ``offset * U[0.9, 1.1]`` ahead of the furthest vehicle,
+    ``offset = spacing * (12 + speed) * exp(-5/40 * lanes)``, on a uniformly random lane, at a speed
+    ``U[0.7, 0.8] * speed_limit``; slot 0 is the MDPVehicle ego (speed 25), the rest are IDMVehicles with
+    ``DELTA ~ U[3.5, 4.5]`` (behavior.py:66-69) and ``timer = (x + y) * pi mod 1`` (behavior.py:64).
+    The stream is keyed by the GLOBAL env index so a shard of envs is identical to the same envs of a
+    larger run."""
+    lanes = int(config["lanes_count"])
+    n = int(config["vehicles_count"])
+    vcap = vcap or n
+    st = SimState.zeros(num_envs, vcap)
+    speed_limit = float(config["speed_limit"])
+    density = float(config["vehicles_density"])
+    width = AbstractLane.DEFAULT_WIDTH
+    lane_factor = np.exp(-5 / 40 * lanes)
+    for e in range(num_envs):
+        rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence([seed, first_env + e])))
+        lane_ids = rng.integers(0, lanes, size=n)
+        speeds = rng.uniform(0.7 * speed_limit, 0.8 * speed_limit, size=n)
+        jitter = rng.uniform(0.9, 1.1, size=n)
+        deltas = rng.uniform(3.5, 4.5, size=n)
+        speeds[0] = 25.0
+        x_prev = 0.0
+        for s in range(n):
+            spacing = float(config["ego_spacing"]) if s == 0 else 1.0 / density
+            offset = spacing * (12 + 1.0 * speeds[s]) * lane_factor
+            x0 = 3 * offset if s == 0 else x_prev
+            x0 += offset * jitter[s]
+            x_prev = x0
+            y0 = lane_ids[s] * width
+            if s == 0:
+                st.set_vehicle(e, s, x=x0, y=y0, heading=0.0, speed=25.0, lane=int(lane_ids[s]), target_speed=25.0,
+                               speed_index=1, mdp=True, controlled=True)
+            else:
+                st.set_vehicle(e, s, x=x0, y=y0, heading=0.0, speed=speeds[s], lane=int(lane_ids[s]),
+                               timer=float(((x0 + y0) * np.pi) % 1.0), delta=float(deltas[s]))
+        st.env_i[abi.EI_NVEH, e] = n
+        st.env_i[abi.EI_EGO, e] = 0
+    return st

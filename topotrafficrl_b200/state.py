@@ -1,0 +1,104 @@
+"""Host-side container for the struct-of-arrays simulation state (layout of ``include/ttrl_b200.h``).
+
+Field ``f`` of slot ``s`` of env ``e`` is ``veh_d[f, e, s]`` / ``veh_i[f, e, s]``; slots ``0..n-1`` are live, in
+``Road.vehicles`` list order (the order is semantic in the reference: road.py:461-478).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+
+
+def pack_route(route: Optional[Sequence[Tuple[int, Optional[int]]]]) -> Tuple[int, int, int]:
+    """``route`` = list of (road index, lane id | None), or None.  Returns (len, road word, lane word)."""
+    if route is None:
+        return -1, 0, 0
+    if len(route) > abi.ROUTE_CAP:
+        raise ValueError(f"route longer than {abi.ROUTE_CAP} entries")
+    rr = rl = 0
+    for k, (road, lane) in enumerate(route):
+        rr |= (int(road) & 0xFF) << (8 * k)
+        rl |= (0xFF if lane is None else int(lane) & 0xFF) << (8 * k)
+    return len(route), _as_i32(rr), _as_i32(rl)
+
+
+def unpack_route(length: int, rr: int, rl: int) -> Optional[List[Tuple[int, Optional[int]]]]:
+    if length < 0:
+        return None
+    rr &= 0xFFFFFFFF
+    rl &= 0xFFFFFFFF
+    out = []
+    for k in range(length):
+        lane = (rl >> (8 * k)) & 0xFF
+        out.append(((rr >> (8 * k)) & 0xFF, None if lane == 0xFF else lane))
+    return out
+
+
+def _as_i32(x: int) -> int:
+    x &= 0xFFFFFFFF
+    return x - (1 << 32) if x & 0x80000000 else x
+
+
+@dataclass
+class SimState:
+    veh_d: np.ndarray  # float64 [ND, E, V]
+    veh_i: np.ndarray  # int32   [NI, E, V]
+    env_i: np.ndarray  # int32   [NEI, E]
+    env_d: np.ndarray  # float64 [NED, E]
+
+    @classmethod
+    def zeros(cls, num_envs: int, vcap: int) -> "SimState":
+        return cls(np.zeros((abi.ND, num_envs, vcap), np.float64), np.zeros((abi.NI, num_envs, vcap), np.int32),
+                   np.zeros((abi.NEI, num_envs), np.int32), np.zeros((abi.NED, num_envs), np.float64))
+
+    @property
+    def num_envs(self) -> int:
+        return self.veh_d.shape[1]
+
+    @property
+    def vcap(self) -> int:
+        return self.veh_d.shape[2]
+
+    def copy(self) -> "SimState":
+        return SimState(self.veh_d.copy(), self.veh_i.copy(), self.env_i.copy(), self.env_d.copy())
+
+    def contiguous(self) -> "SimState":
+        return SimState(*(np.ascontiguousarray(a) for a in (self.veh_d, self.veh_i, self.env_i, self.env_d)))
+
+    def slice_envs(self, lo: int, hi: int) -> "SimState":
+        return SimState(self.veh_d[:, lo:hi].copy(), self.veh_i[:, lo:hi].copy(),
+                        self.env_i[:, lo:hi].copy(), self.env_d[:, lo:hi].copy())
+
+    def n_vehicles(self) -> np.ndarray:
+        return self.env_i[abi.EI_NVEH]
+
+    def live_mask(self) -> np.ndarray:
+        return np.arange(self.vcap)[None, :] < self.env_i[abi.EI_NVEH][:, None]
+
+    def set_vehicle(self, e: int, s: int, *, x, y, heading, speed, lane, target_lane=None, target_speed=None,
+                    timer=0.0, delta=4.0, mdp=False, controlled=False, crashed=False, speed_index=0,
+                    route=None, steering=0.0, accel=0.0, impact=None, yielding=False, yield_timer=0) -> None:
+        d, i = self.veh_d, self.veh_i
+        d[abi.D_X, e, s], d[abi.D_Y, e, s] = x, y
+        d[abi.D_HEADING, e, s], d[abi.D_SPEED, e, s] = heading, speed
+        d[abi.D_STEERING, e, s], d[abi.D_ACCEL, e, s] = steering, accel
+        d[abi.D_TARGET_SPEED, e, s] = speed if target_speed is None else target_speed
+        d[abi.D_TIMER, e, s], d[abi.D_DELTA, e, s] = timer, delta
+        flags = (abi.FL_MDP if mdp else 0) | (abi.FL_CONTROLLED if controlled else 0) | (abi.FL_CRASHED if crashed else 0)
+        if impact is not None:
+            d[abi.D_IMPACT_X, e, s], d[abi.D_IMPACT_Y, e, s] = impact
+            flags |= abi.FL_HAS_IMPACT
+        else:
+            d[abi.D_IMPACT_X, e, s] = d[abi.D_IMPACT_Y, e, s] = 0.0
+        if yielding:
+            flags |= abi.FL_YIELDING
+        i[abi.I_LANE, e, s] = lane
+        i[abi.I_TARGET_LANE, e, s] = lane if target_lane is None else target_lane
+        i[abi.I_FLAGS, e, s] = flags
+        i[abi.I_SPEED_INDEX, e, s] = speed_index
+        i[abi.I_ROUTE_LEN, e, s], i[abi.I_ROUTE_ROAD, e, s], i[abi.I_ROUTE_LANE, e, s] = pack_route(route)
+        i[abi.I_YIELD_TIMER, e, s] = yield_timer
