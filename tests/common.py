@@ -1,0 +1,89 @@
+"""Shared helpers for the parity tests: golden fixtures -> SimState, scene construction, comparisons."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from topotrafficrl_b200 import abi, scenes
+from topotrafficrl_b200.state import SimState
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+GRID_DENSE = {"observation": {"type": "OccupancyGrid", "vehicles_count": 15,
+                              "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+                              "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]},
+                              "grid_size": [[-32, 32], [-32, 32]], "grid_step": [2, 2], "absolute": False}}
+GRID_ROAD = {"observation": {"type": "OccupancyGrid", "features": ["presence", "vx", "vy", "on_road"],
+                             "grid_size": [[-27.5, 27.5], [-27.5, 27.5]], "grid_step": [5, 5], "absolute": False}}
+HIGHWAY_GRID = {"observation": {"type": "OccupancyGrid", "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+                                "grid_size": [[-32, 32], [-32, 32]], "grid_step": [2, 2], "absolute": False}}
+
+# continuous-state tolerances of the parity tests.  The device computes in float64 like the reference, so
+# these are far inside the north-star tolerance (1e-4 m / 1e-5 rad per step): they only absorb last-ulp
+# differences between libm / numpy / CUDA transcendental functions.
+TOL_SUBSTEP = 1e-9
+TOL_STEP = 1e-6
+
+
+def golden(name: str):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def batch_state(g, prefix: str, sel=None) -> SimState:
+    """Stack S golden 1-env snapshots into one S-env SimState."""
+    vd, vi, ei, ed = (g[prefix + s] for s in ("_vd", "_vi", "_ei", "_ed"))
+    if sel is not None:
+        vd, vi, ei, ed = vd[sel], vi[sel], ei[sel], ed[sel]
+    return SimState(np.ascontiguousarray(vd.transpose(1, 0, 2)), np.ascontiguousarray(vi.transpose(1, 0, 2)),
+                    np.ascontiguousarray(ei.T), np.ascontiguousarray(ed.T))
+
+
+def intersection_scene(overrides=None):
+    net = scenes.make_intersection_network()
+    table = net.to_table(scenes.intersection_exit_predicate)
+    cfgd = scenes.merged_config(scenes.INTERSECTION_CONFIG, overrides)
+    cfg = scenes.build_config(table, cfgd, "intersection")
+    return net, table, cfg, scenes.intersection_spawn_routes(net, table)
+
+
+def highway_scene(n_vehicles=50, density=2.0, overrides=None):
+    net = scenes.make_highway_network(4)
+    table = net.to_table()
+    over = {"vehicles_count": n_vehicles, "vehicles_density": density}
+    if overrides:
+        over.update(overrides)
+    cfgd = scenes.merged_config(scenes.HIGHWAY_CONFIG, over)
+    cfg = scenes.build_config(table, cfgd, "highway", ego_lanes_count=4)
+    return net, table, cfg, cfgd
+
+
+def draws_array(draw_rows):
+    arr = (abi.SpawnDraw * len(draw_rows))()
+    for k, row in enumerate(draw_rows):
+        arr[k].u_spawn, arr[k].entry, arr[k].exit = float(row[0]), int(row[1]), int(row[2])
+        arr[k].n_pos, arr[k].n_speed, arr[k].delta = float(row[3]), float(row[4]), float(row[5])
+    return arr
+
+
+def compare_states(got: SimState, want: SimState, tol: float, what: str = "", check_action: bool = True):
+    """Discrete fields bit-exact on live slots, continuous within tol.  Returns max abs continuous diff."""
+    n_got, n_want = got.env_i[abi.EI_NVEH], want.env_i[abi.EI_NVEH]
+    assert (n_got == n_want).all(), f"{what}: vehicle counts differ at envs {np.nonzero(n_got != n_want)[0][:8]}"
+    live = want.live_mask()
+    for f, name in enumerate(["lane", "target_lane", "flags", "speed_index", "route_len", "route_road", "route_lane", "yield_timer"]):
+        bad = (got.veh_i[f] != want.veh_i[f]) & live
+        assert not bad.any(), (f"{what}: discrete field {name} differs at (env,slot) {np.argwhere(bad)[:8].tolist()} "
+                               f"got {got.veh_i[f][bad][:8]} want {want.veh_i[f][bad][:8]}")
+    for f in (abi.EI_STEPS, abi.EI_ROAD_STEPS, abi.EI_EGO):
+        assert (got.env_i[f] == want.env_i[f]).all(), f"{what}: env int field {f} differs"
+    worst = 0.0
+    for f in range(abi.ND):
+        if not check_action and f in (abi.D_STEERING, abi.D_ACCEL):
+            continue
+        d = np.abs(got.veh_d[f] - want.veh_d[f])[live]
+        if d.size:
+            m = float(d.max())
+            assert m <= tol, f"{what}: continuous field {f} differs by {m} (> {tol})"
+            worst = max(worst, m)
+    return worst
