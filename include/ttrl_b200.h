@@ -146,7 +146,10 @@ typedef struct ttrl_sim ttrl_sim;
 typedef struct ttrl_qnet ttrl_qnet;
 
 const char* ttrl_last_error(void);
+void ttrl_set_error(const char* msg);
 int ttrl_abi_version(void);
+/* sizeof of the POD structs as compiled (0 lane, 1 road, 2 config, 3 spawn_draw, 4 episode_stats, 5 qnet_desc): binding self-check */
+int ttrl_abi_sizeof(int which);
 
 /* Create E env instances with V vehicle slots each on CUDA device `device`.
  * Replaces: AbstractEnv.__init__/configure (abstract.py:44-113) + _make_road (intersection_env.py:141-249,
@@ -156,6 +159,10 @@ int ttrl_sim_create(const ttrl_config* cfg, const ttrl_lane* lanes, const ttrl_r
                     const int32_t* node_first /* n_nodes+1 */, const int32_t* node_roads,
                     int num_envs, int vcap, int device, ttrl_sim** out);
 int ttrl_sim_destroy(ttrl_sim* sim);
+/* IntersectionEnv spawn routes: entry lane per corner and, per (entry, exit), the roads that plan_route_to
+ * (controller.py:71-87, BFS of road.py:159-188 done on the host) appends after the entry lane. */
+int ttrl_sim_set_spawn_routes(ttrl_sim* sim, const int32_t* spawn_lane /*4*/, const int32_t* route_len /*16*/,
+                              const int32_t* route_road /*16*TTRL_ROUTE_CAP*/);
 int ttrl_sim_num_envs(const ttrl_sim* sim);
 int ttrl_sim_vcap(const ttrl_sim* sim);
 int ttrl_sim_obs_size(const ttrl_sim* sim); /* floats per env */
@@ -194,7 +201,14 @@ int ttrl_sim_observe(ttrl_sim* sim, float* obs_dev, void* stream);
 /* Parity hooks: feed the oracle's RNG draws (spawn decisions; Kinematics "shuffled" permutations). */
 int ttrl_sim_inject_spawn(ttrl_sim* sim, const ttrl_spawn_draw* draws_host /* E records or NULL to clear */);
 int ttrl_sim_inject_shuffle(ttrl_sim* sim, const int32_t* perm_host /* E*(obs_vehicles-1) or NULL */);
+/* seed != 0 enables device-side (Philox) spawn draws keyed by (seed, first_global_env + e, episode, step). */
 int ttrl_sim_seed(ttrl_sim* sim, uint64_t seed, int64_t first_global_env);
+/* spawn outcome of the last step (1 = a vehicle was appended), int32[E] to host */
+int ttrl_sim_spawn_accepted(ttrl_sim* sim, int32_t* accepted_host);
+/* Host-driven reset primitive: ONE _spawn_vehicle attempt with explicit arguments, as _make_vehicles calls it
+ * (intersection_env.py:265-283).  Synchronous. */
+int ttrl_sim_spawn(ttrl_sim* sim, const ttrl_spawn_draw* draws_host, double longitudinal, double position_deviation,
+                   double speed_deviation, double spawn_probability, int go_straight, int32_t* accepted_host);
 
 int ttrl_sim_read_stats(ttrl_sim* sim, ttrl_episode_stats* out_host, int reset_after_read);
 /* number of kernel launches issued by this sim so far (bench.py's gpu_launches) */
@@ -228,9 +242,10 @@ int ttrl_qnet_destroy(ttrl_qnet* q);
 /* Q-values + epsilon-greedy action for E observations.  q_dev may be NULL.  epsilon<=0 -> Greedy. */
 int ttrl_qnet_act(ttrl_qnet* q, const float* obs_dev, int num_envs, double epsilon, uint64_t seed,
                   uint64_t step, int32_t* actions_dev, float* q_dev, void* stream);
-/* tensor-core (tcgen05) variant of the forward: same outputs, bf16 operands / fp32 accumulate. */
-int ttrl_qnet_act_tc(ttrl_qnet* q, const float* obs_dev, int num_envs, double epsilon, uint64_t seed,
-                     uint64_t step, int32_t* actions_dev, float* q_dev, void* stream);
+/* Same with caller-supplied exploration uniforms u_dev double[E] (np_random.choice draws one U[0,1) per call). */
+int ttrl_qnet_act_injected(ttrl_qnet* q, const float* obs_dev, int num_envs, double epsilon, const double* u_dev,
+                           int32_t* actions_dev, float* q_dev, void* stream);
+int64_t ttrl_qnet_launch_count(const ttrl_qnet* q);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,142 @@
+// TEST-ONLY sequential emulation of the CUDA kernels' phases (no GPU in the build container).
+//
+// Compiles topotrafficrl_b200/csrc/ttrl_core.cuh -- the exact device logic -- for the host with an Exec
+// policy that runs the V "threads" of each phase one after the other (a __syncthreads() boundary becomes
+// the end of the loop).  Lets `pytest -m "not gpu"` check the device code against the CPU oracle and the
+// golden vectors before any GPU time is spent.  It is NOT reachable from the product package: the product
+// path has no CPU fallback and fails loudly without the CUDA library.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../topotrafficrl_b200/csrc/ttrl_core.cuh"
+
+using namespace ttrl;
+
+struct HostExec {
+    int T;
+    void sync() {}
+    template <class F> void par(F f) { for (int t = 0; t < T; ++t) f(t); }
+    template <class F> bool any(F f) { bool r = false; for (int t = 0; t < T; ++t) r = f(t) || r; return r; }
+    template <class F1, class F2> void par2(F1 f1, F2 f2) {
+        std::vector<SlotRegs> r(T);
+        std::vector<int> dst(T);
+        for (int t = 0; t < T; ++t) f1(t, r[t], dst[t]);
+        for (int t = 0; t < T; ++t) f2(t, r[t], dst[t]);
+    }
+    void atomic_min(int32_t* a, int32_t v) { if (v < *a) *a = v; }
+};
+
+template <int V>
+struct HostEnv {
+    EnvState<V> st;
+    std::vector<double> S, R, pred;
+    std::vector<float> obs_s;
+    std::vector<int32_t> cell;
+    EnvCtx<V> c;
+    HostEnv(const SceneDev* sc, int vcap) {
+        memset(&st, 0, sizeof st);
+        const ttrl_config& cfg = sc->cfg;
+        S.assign((size_t)V * cfg.n_lanes, 0.0); R.assign((size_t)V * cfg.n_lanes, 0.0);
+        pred.assign((size_t)3 * V * kPred, 0.0);
+        obs_s.assign((size_t)(cfg.obs_vehicles * cfg.n_features + 4), 0.f);
+        cell.assign((size_t)(cfg.grid_w * cfg.grid_h + 4), 0);
+        c.st = &st; c.sc = sc; c.lanes = sc->lanes; c.S = S.data(); c.R = R.data();
+        c.pred = cfg.regulated ? pred.data() : nullptr; c.obs_s = obs_s.data(); c.cell = cell.data();
+        c.L = cfg.n_lanes; c.vcap = vcap;
+    }
+};
+
+#define DISPATCH(vcap, EXPR)                                  \
+    do {                                                      \
+        if (vcap <= 32) { constexpr int V = 32; EXPR; }       \
+        else if (vcap <= 64) { constexpr int V = 64; EXPR; }  \
+        else if (vcap <= 128) { constexpr int V = 128; EXPR; }\
+        else { constexpr int V = 256; EXPR; }                 \
+    } while (0)
+
+extern "C" {
+
+SceneDev* emu_scene_create(const ttrl_config* cfg, const ttrl_lane* lanes, const ttrl_road* roads, const int32_t* node_first,
+                           const int32_t* node_roads) {
+    SceneDev* s = (SceneDev*)calloc(1, sizeof(SceneDev));
+    s->cfg = *cfg;
+    memcpy(s->lanes, lanes, sizeof(ttrl_lane) * cfg->n_lanes);
+    memcpy(s->roads, roads, sizeof(ttrl_road) * cfg->n_roads);
+    memcpy(s->node_first, node_first, sizeof(int32_t) * (cfg->n_nodes + 1));
+    memcpy(s->node_roads, node_roads, sizeof(int32_t) * node_first[cfg->n_nodes]);
+    s->F = (int)floor(cfg->simulation_frequency / cfg->policy_frequency);
+    s->dt = 1 / cfg->simulation_frequency;
+    s->reg_period = (int)(1 / s->dt / 2);
+    return s;
+}
+void emu_scene_destroy(SceneDev* s) { free(s); }
+void emu_scene_set_spawn_routes(SceneDev* s, const int32_t* spawn_lane, const int32_t* route_len, const int32_t* route_road) {
+    memcpy(s->spawn_lane, spawn_lane, sizeof(int32_t) * 4);
+    memcpy(s->spawn_route_len, route_len, sizeof(int32_t) * 16);
+    memcpy(s->spawn_route_road, route_road, sizeof(int32_t) * 16 * TTRL_ROUTE_CAP);
+}
+
+void emu_substep(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, const int32_t* actions) {
+    GlobalState g{vd, vi, ei, ed, E, Vs};
+    DISPATCH(Vs, {
+        HostEnv<V> env(sc, Vs);
+        HostExec ex{V};
+        for (int e = 0; e < E; ++e) {
+            load_env(env.c, ex, g, e);
+            env_substep(env.c, ex, actions ? actions[e] : -1);
+            store_env(env.c, ex, g, e);
+        }
+    });
+}
+
+void emu_observe(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, float* obs, int obs_size,
+                 const int32_t* inv_perm) {
+    GlobalState g{vd, vi, ei, ed, E, Vs};
+    DISPATCH(Vs, {
+        HostEnv<V> env(sc, Vs);
+        HostExec ex{V};
+        for (int e = 0; e < E; ++e) {
+            load_env(env.c, ex, g, e);
+            observe(env.c, ex, obs + (size_t)e * obs_size, inv_perm ? inv_perm + (size_t)e * (sc->cfg.obs_vehicles - 1) : nullptr);
+        }
+    });
+}
+
+void emu_step(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, const int32_t* actions,
+              float* obs, int obs_size, float* reward, uint8_t* terminated, uint8_t* truncated, const ttrl_spawn_draw* draws,
+              int32_t* accepted, const int32_t* inv_perm, double* stats, int pool_size, double* pvd, int32_t* pvi, int32_t* pei,
+              double* ped, int autoreset, uint64_t seed, int64_t first_global_env) {
+    GlobalState g{vd, vi, ei, ed, E, Vs};
+    StepIO io{};
+    io.actions = actions; io.obs = obs; io.reward = reward; io.terminated = terminated; io.truncated = truncated;
+    io.draws = draws; io.spawn_accepted = accepted; io.inv_perm = inv_perm; io.stats = stats;
+    io.pool = GlobalState{pvd, pvi, pei, ped, pool_size, Vs};
+    io.autoreset = autoreset; io.seed = seed; io.first_global_env = first_global_env; io.obs_size = obs_size;
+    DISPATCH(Vs, {
+        HostEnv<V> env(sc, Vs);
+        HostExec ex{V};
+        for (int e = 0; e < E; ++e) env_step(env.c, ex, g, io, e);
+    });
+}
+
+void emu_spawn(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, const ttrl_spawn_draw* draws,
+               double longitudinal, double position_deviation, double speed_deviation, double spawn_probability, int go_straight,
+               int32_t* accepted) {
+    GlobalState g{vd, vi, ei, ed, E, Vs};
+    SpawnParams sp{longitudinal, position_deviation, speed_deviation, spawn_probability, go_straight};
+    DISPATCH(Vs, {
+        HostEnv<V> env(sc, Vs);
+        HostExec ex{V};
+        for (int e = 0; e < E; ++e) {
+            load_env(env.c, ex, g, e);
+            spawn_vehicle(env.c, ex, draws[e], sp);
+            if (accepted) accepted[e] = env.st.flag0;
+            store_env(env.c, ex, g, e);
+        }
+    });
+}
+
+void emu_device_spawn_draw(uint64_t seed, int64_t env, uint64_t counter, ttrl_spawn_draw* out) { device_spawn_draw(seed, env, counter, *out); }
+}

@@ -1,0 +1,79 @@
+"""TEST-ONLY ctypes wrapper around tests/emu/libttrl_emu.so (host emulation of the CUDA phases)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+from topotrafficrl_b200 import abi
+from topotrafficrl_b200.state import SimState
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libttrl_emu.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
+        _lib = C.CDLL(_LIB)
+        _lib.emu_scene_create.restype = C.c_void_p
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Emulator:
+    def __init__(self, cfg: abi.Config, table, spawn_routes=None):
+        self.L = lib()
+        self.cfg = cfg
+        self.sc = C.c_void_p(self.L.emu_scene_create(C.byref(cfg), table.lanes, table.roads, _p(table.node_first), _p(table.node_roads)))
+        if spawn_routes is not None:
+            sl, rl, rr = (np.ascontiguousarray(a, dtype=np.int32) for a in spawn_routes)
+            self.L.emu_scene_set_spawn_routes(self.sc, _p(sl), _p(rl), _p(rr))
+        self.obs_size = (cfg.n_features * cfg.grid_w * cfg.grid_h) if cfg.obs_type == abi.OBS_GRID else cfg.obs_vehicles * cfg.n_features
+        self.pool = None
+        self.autoreset = False
+
+    def substep(self, st: SimState, actions=None):
+        a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32)
+        self.L.emu_substep(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(st.num_envs), C.c_int(st.vcap), _p(a))
+
+    def observe(self, st: SimState, inv_perm=None):
+        obs = np.zeros((st.num_envs, self.obs_size), np.float32)
+        self.L.emu_observe(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(st.num_envs), C.c_int(st.vcap),
+                           _p(obs), C.c_int(self.obs_size), _p(inv_perm))
+        return obs
+
+    def step(self, st: SimState, actions, draws=None, inv_perm=None, stats=None, seed=0, first_env=0):
+        E = st.num_envs
+        a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32)
+        obs = np.zeros((E, self.obs_size), np.float32)
+        reward = np.zeros(E, np.float32)
+        term = np.zeros(E, np.uint8)
+        trunc = np.zeros(E, np.uint8)
+        acc = np.zeros(E, np.int32)
+        pool = self.pool
+        self.L.emu_step(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(E), C.c_int(st.vcap), _p(a),
+                        _p(obs), C.c_int(self.obs_size), _p(reward), _p(term), _p(trunc), draws, _p(acc), _p(inv_perm), _p(stats),
+                        C.c_int(pool.num_envs if pool is not None else 0),
+                        _p(pool.veh_d) if pool is not None else None, _p(pool.veh_i) if pool is not None else None,
+                        _p(pool.env_i) if pool is not None else None, _p(pool.env_d) if pool is not None else None,
+                        C.c_int(int(self.autoreset)), C.c_uint64(seed), C.c_int64(first_env))
+        return obs, reward, term, trunc, acc
+
+    def spawn(self, st, draws, longitudinal, position_deviation=1.0, speed_deviation=1.0, spawn_probability=0.6, go_straight=False):
+        acc = np.zeros(st.num_envs, np.int32)
+        self.L.emu_spawn(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(st.num_envs), C.c_int(st.vcap), draws,
+                         C.c_double(longitudinal), C.c_double(position_deviation), C.c_double(speed_deviation),
+                         C.c_double(spawn_probability), C.c_int(int(go_straight)), _p(acc))
+        return acc

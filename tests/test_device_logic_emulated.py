@@ -1,0 +1,73 @@
+"""The CUDA kernels' device logic (topotrafficrl_b200/csrc/ttrl_core.cuh), compiled for the host and run
+phase by phase (tests/emu), against the reference-generated golden vectors and against the CPU oracle.
+CPU only; the same comparisons run on the real kernels in tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from topotrafficrl_b200 import abi, scenes
+from tests import common as T
+from tests.emu.emu import Emulator
+
+
+def _scene(scene, over=None):
+    if scene == "intersection":
+        _, table, cfg, routes = T.intersection_scene(over)
+        return cfg, table, routes
+    _, table, cfg, _ = T.highway_scene(int(scene[7:]), overrides=over)
+    return cfg, table, None
+
+
+@pytest.mark.parametrize("name,scene", [
+    ("intersection_substeps.npz", "intersection"),
+    ("highway_n8_substeps.npz", "highway8"),
+    ("highway_n50_substeps.npz", "highway50"),
+    ("highway_n200_substeps.npz", "highway200"),
+    ("highway_grid_n40_substeps.npz", "highway40"),
+])
+def test_substep_vs_golden(name, scene):
+    g = T.golden(name)
+    cfg, table, routes = _scene(scene)
+    emu = Emulator(cfg, table, routes)
+    st = T.batch_state(g, "before")
+    emu.substep(st, g["action"].astype(np.int32))
+    T.compare_states(st, T.batch_state(g, "after"), T.TOL_SUBSTEP, name)
+
+
+@pytest.mark.parametrize("name,scene,over", [
+    ("intersection_steps_kin.npz", "intersection", None),
+    ("intersection_steps_grid_dense.npz", "intersection", T.GRID_DENSE),
+    ("intersection_steps_grid_road.npz", "intersection", T.GRID_ROAD),
+    ("highway_n8_steps.npz", "highway8", None),
+    ("highway_n50_steps.npz", "highway50", None),
+    ("highway_grid_n40_steps.npz", "highway40", T.HIGHWAY_GRID),
+])
+def test_step_vs_golden(name, scene, over):
+    g = T.golden(name)
+    cfg, table, routes = _scene(scene, over)
+    emu = Emulator(cfg, table, routes)
+    st = T.batch_state(g, "before")
+    draws = T.draws_array(g["draw"]) if "draw" in g.files else None
+    obs, reward, term, trunc, _ = emu.step(st, g["action"].astype(np.int32), draws)
+    T.compare_states(st, T.batch_state(g, "after"), T.TOL_STEP, name)
+    np.testing.assert_allclose(obs.reshape(g["obs"].shape), g["obs"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(reward, g["reward"], rtol=0, atol=1e-6)
+    assert (term.astype(bool) == g["terminated"]).all() and (trunc.astype(bool) == g["truncated"]).all()
+
+
+@pytest.mark.parametrize("n,density,steps", [(50, 2.0, 12), (200, 4.0, 2)])
+def test_free_running_vs_oracle(n, density, steps):
+    """Free-running env-steps from the product's own scene generator: emulated device logic == oracle."""
+    _, table, cfg, cfgd = T.highway_scene(n, density)
+    emu, orc = Emulator(cfg, table), O.Oracle(cfg, table)
+    a = scenes.make_highway_state(6, cfgd, seed=3)
+    b = a.copy()
+    rng = np.random.default_rng(0)
+    for k in range(steps):
+        act = rng.integers(0, 5, size=6).astype(np.int32)
+        oa = emu.step(a, act)
+        ob = orc.step(b, act)
+        T.compare_states(a, b, 1e-7, f"step {k}")
+        np.testing.assert_allclose(oa[0], ob[0], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(oa[1], ob[1], rtol=0, atol=1e-6)
+        assert (oa[2] == ob[2]).all() and (oa[3] == ob[3]).all()

@@ -1,0 +1,138 @@
+"""Host-side logic (no GPU): ABI binding, config translation, lane tables, route planning, the host-driven
+reset (validated with the emulated device primitives against the reference's seeded resets), RNG mirroring."""
+import ctypes as C
+import re
+import os
+
+import numpy as np
+import pytest
+
+from topotrafficrl_b200 import abi, scenes
+from topotrafficrl_b200._gym import np_random
+from topotrafficrl_b200.reset import reset_intersection
+from topotrafficrl_b200.state import SimState, pack_route, unpack_route
+from tests import common as T
+from tests.emu.emu import Emulator
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports every function include/ttrl_b200.h declares (no compute calls)."""
+    from topotrafficrl_b200 import _lib
+    L = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "ttrl_b200.h")).read()
+    names = set(re.findall(r"\b(ttrl_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 25
+    for n in sorted(names):
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+    assert L.ttrl_abi_version() == 1
+    sizes = [C.sizeof(x) for x in (abi.Lane, abi.Road, abi.Config, abi.SpawnDraw, abi.EpisodeStats, abi.QnetDesc)]
+    assert [L.ttrl_abi_sizeof(i) for i in range(6)] == sizes
+
+
+def test_product_never_imports_oracle():
+    """The product package must not import, link or execute anything under oracle/ or tests/."""
+    pkg = os.path.join(ROOT, "topotrafficrl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in re.sub(r"#.*|//.*", "", src).replace("oracle-", ""), f
+                assert "tests.emu" not in src and "libttrl_emu" not in src, f
+
+
+def test_route_packing_roundtrip():
+    for route in (None, [], [(3, 0)], [(0, 0), (2, None), (19, None)], [(1, 3), (2, 2), (3, 1), (4, None)]):
+        assert unpack_route(*pack_route(route)) == route
+
+
+def test_intersection_table_matches_reference_layout():
+    net, table, cfg, (spawn_lane, rlen, rroad) = T.intersection_scene()
+    assert table.n_lanes == 20 and table.n_roads == 20
+    # insertion order per corner: incoming, right turn, left turn, straight, exit
+    assert table.lane_keys[:5] == [("o0", "ir0", 0), ("ir0", "il3", 0), ("ir0", "il1", 0), ("ir0", "il2", 0), ("il3", "o3", 0)]
+    lengths = [table.lanes[i].length for i in range(5)]
+    np.testing.assert_allclose(lengths, [100.0, 9 * np.pi / 2, 13 * np.pi / 2, 22.0, 100.0])
+    assert [table.lanes[i].priority for i in range(5)] == [1, 1, 0, 1, 1]
+    assert [table.lanes[5 + i].priority for i in range(5)] == [3, 3, 2, 3, 3]
+    assert [bool(table.lanes[i].is_exit) for i in range(5)] == [False, False, False, False, True]
+    assert list(spawn_lane) == [0, 5, 10, 15]
+    assert rlen[0, 1] == 2 and rlen[0, 0] == 0
+    assert net.plan_route(("o0", "ir0", 0), "o1") == [("o0", "ir0", 0), ("ir0", "il1", None), ("il1", "o1", None)]
+    assert cfg.regulated == 1 and cfg.distance_wanted == 7.0 and cfg.comfort_acc_max == 6.0 and cfg.comfort_acc_min == -3.0
+
+
+def test_config_translation_and_errors():
+    _, table, cfg, _ = T.highway_scene(50)
+    assert cfg.action_mode == abi.ACT_ALL and cfg.n_target_speeds == 3 and list(cfg.target_speeds)[:3] == [20.0, 25.0, 30.0]
+    assert cfg.obs_vehicles == 15 and cfg.n_features == 7 and cfg.absolute == 0
+    # default features_range derived from the 4-lane road (reference observation.py:213-225)
+    assert (cfg.range_lo[1], cfg.range_hi[1], cfg.range_lo[2], cfg.range_hi[2], cfg.range_hi[3]) == (-200.0, 200.0, -16.0, 16.0, 80.0)
+    with pytest.raises(ValueError):
+        scenes.build_config(table, scenes.merged_config(scenes.HIGHWAY_CONFIG, {"observation": {"type": "Nope"}}), "highway")
+    with pytest.raises(ValueError):
+        scenes.build_config(table, scenes.merged_config(scenes.HIGHWAY_CONFIG, {"action": {"type": "Nope"}}), "highway")
+    _, _, gcfg, _ = T.intersection_scene(T.GRID_DENSE)
+    assert (gcfg.grid_w, gcfg.grid_h) == (32, 32) and gcfg.grid_has_xrange == 1
+    # configure() is a SHALLOW update: a partial observation dict replaces the whole block
+    merged = scenes.merged_config(scenes.INTERSECTION_CONFIG, {"observation": {"type": "Kinematics"}})
+    assert merged["observation"] == {"type": "Kinematics"}
+
+
+def test_highway_generator_is_shard_invariant():
+    _, _, _, cfgd = T.highway_scene(50)
+    full = scenes.make_highway_state(8, cfgd, seed=5)
+    shard = scenes.make_highway_state(4, cfgd, seed=5, first_env=4)
+    np.testing.assert_array_equal(full.veh_d[:, 4:], shard.veh_d)
+    np.testing.assert_array_equal(full.veh_i[:, 4:], shard.veh_i)
+    assert (full.env_i[abi.EI_NVEH] == 50).all()
+    x = full.veh_d[abi.D_X]
+    assert (np.diff(x, axis=1) > 0).all()  # each vehicle is placed ahead of the previous one
+
+
+def test_numpy_shuffle_draws_depend_only_on_length():
+    """envs.py mirrors np_random.shuffle(obs[1:]) by shuffling an index vector with the same Generator."""
+    a, _ = np_random(11)
+    b, _ = np_random(11)
+    rows = np.arange(14 * 7, dtype=np.float64).reshape(14, 7)
+    ref = rows.copy()
+    a.shuffle(ref)
+    perm = np.arange(14)
+    b.shuffle(perm)
+    np.testing.assert_array_equal(ref, rows[perm])
+    assert a.uniform() == b.uniform()
+
+
+class _EmuBackend:
+    def __init__(self, emu, num_envs, vcap):
+        self.emu, self.num_envs = emu, num_envs
+        self.st = SimState.zeros(num_envs, vcap)
+
+    def spawn(self, draws, longitudinal, position_deviation, speed_deviation, spawn_probability, go_straight):
+        return self.emu.spawn(self.st, draws, longitudinal, position_deviation, speed_deviation, spawn_probability, go_straight)
+
+    def substep_none(self):
+        self.emu.substep(self.st, None)
+
+    def get_state(self):
+        return self.st.copy()
+
+    def set_state(self, st):
+        self.st = st.copy().contiguous()
+
+
+def test_host_driven_reset_reproduces_reference_resets():
+    """Seeded reset through (emulated) device primitives == IntersectionEnv.reset(seed) of the reference."""
+    g = T.golden("intersection_reset.npz")
+    net, table, cfg, routes = T.intersection_scene({"observation": dict(scenes.INTERSECTION_CONFIG["observation"], order="sorted")})
+    emu = Emulator(cfg, table, routes)
+    seeds = [int(s) for s in g["seed"]]
+    backend = _EmuBackend(emu, len(seeds), 32)
+    rngs = [np_random(s)[0] for s in seeds]
+    cfgd = scenes.merged_config(scenes.INTERSECTION_CONFIG, None)
+    st = reset_intersection(backend, rngs, net, table, cfgd, cfg)
+    want = T.batch_state(g, "state")
+    T.compare_states(st, want, 1e-9, "reset", check_action=True)
+    obs = emu.observe(backend.st)
+    np.testing.assert_allclose(obs.reshape(g["obs"].shape), g["obs"], rtol=0, atol=2e-6)

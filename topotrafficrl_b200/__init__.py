@@ -1,0 +1,31 @@
+"""B200-native batched simulator for the TopoTrafficRL per-step hot path.
+
+Public surface (mirrors the reference's ``ttrl_env`` / ``ttrl_agent`` names for the hot path):
+
+* :class:`TTRLVectorEnv` -- E envs in lockstep on one GPU (``vector_env.py``)
+* :class:`IntersectionEnv` -- single-env gymnasium-shaped front end (``envs.py``), id ``intersection-v0``
+* :class:`QNetRollout` -- batched DQN ``act`` (``agent.py``)
+* :class:`Sim` -- the C ABI as an object (``sim.py``)
+
+Importing the package does not load CUDA; the first use of any class above loads
+``csrc/libttrl_b200.so`` and raises if it (or a CUDA device) is missing -- there is no CPU fallback.
+"""
+from . import abi, road, scenes, state  # noqa: F401
+
+__version__ = "0.1.0"
+
+
+def __getattr__(name):
+    if name == "TTRLVectorEnv":
+        from .vector_env import TTRLVectorEnv
+        return TTRLVectorEnv
+    if name in ("IntersectionEnv", "AbstractEnv"):
+        from . import envs
+        return getattr(envs, name)
+    if name == "QNetRollout":
+        from .agent import QNetRollout
+        return QNetRollout
+    if name == "Sim":
+        from .sim import Sim
+        return Sim
+    raise AttributeError(name)

@@ -1,0 +1,1284 @@
+// ttrl_core.cuh -- device-side simulation logic of the B200 batched simulator.
+//
+// One CTA advances one env instance; thread t owns vehicle slot t.  The env's whole state lives in shared
+// memory for the F sub-steps of an env-step (one HBM round trip per env-step).  The logic is written as
+// barrier-separated PHASES behind an `Exec` policy (par / any / sync):
+//   * on the device Exec = one CTA:  par(f) -> f(threadIdx.x); __syncthreads();
+//   * in tests/emu a host Exec runs the threads of a phase one after the other, so the very same code is
+//     validated against the CPU oracle in a container without a GPU (it is NOT a product path).
+//
+// A per-env table S[v][l], R[v][l] of every vehicle's local coordinates in every lane is rebuilt after each
+// integration (it is the by-product of the closest-lane search, reference road.py:55-71) and serves all
+// neighbour scans, lane distances and controllers of the next sub-step from shared memory.
+//
+// Reference citations are relative to /root/reference.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "../../include/ttrl_b200.h"
+
+#if defined(__CUDACC__)
+#define TT_HD __host__ __device__ __forceinline__
+#define TT_HDN __host__ __device__ __noinline__
+#else
+#define TT_HD inline
+#define TT_HDN
+#endif
+
+namespace ttrl {
+
+constexpr double kPi = 3.141592653589793;
+constexpr int kPred = 11;            // regulation.py:87: np.arange(0.25, 3, 0.25)
+constexpr double kVehLength = 5.0;   // kinematics.py:21
+constexpr double kVehWidth = 2.0;    // kinematics.py:23
+constexpr int kStatFields = 8;       // ttrl_episode_stats
+
+// Read-only scene description, resident in global memory (L1/L2 hot: ~12 KB).
+struct SceneDev {
+    ttrl_config cfg;
+    ttrl_lane lanes[TTRL_MAX_LANES];
+    ttrl_road roads[TTRL_MAX_ROADS];
+    int32_t node_first[TTRL_MAX_NODES + 1];
+    int32_t node_roads[TTRL_MAX_ROADS];
+    int32_t spawn_lane[4];
+    int32_t spawn_route_len[16];
+    int32_t spawn_route_road[16 * TTRL_ROUTE_CAP];
+    int32_t F;           // sub-steps per env-step (abstract.py:254-256)
+    int32_t reg_period;  // int(1/dt/REGULATION_FREQUENCY) (regulation.py:30)
+    double dt;           // 1/simulation_frequency
+};
+
+// Per-env state in shared memory (struct of arrays over the V slots).
+template <int V>
+struct EnvState {
+    double x[V], y[V], h[V], v[V], ch[V], sh[V];
+    double steer[V], acc[V], tspeed[V], timer[V], delta[V], impx[V], impy[V];
+    int32_t lane[V], tlane[V], flags[V], sidx[V], rlen[V], ytimer[V];
+    uint32_t rroad[V], rlanew[V];
+    int32_t tl_old[V], mark[V];
+    int32_t n, steps, road_steps, ego, episode, done, flag0, flag1;
+    double time, ret;
+};
+
+template <int V_>
+struct EnvCtx {
+    static constexpr int V = V_;
+    EnvState<V_>* st;
+    const SceneDev* sc;
+    const ttrl_lane* lanes;  // lane table (shared-memory copy when it fits, else sc->lanes)
+    double* S;               // [V][L] longitudinal local coordinate of vehicle v in lane l
+    double* R;               // [V][L] lateral
+    double* pred;            // [3][V][kPred] regulation predictions (x, y, heading); null if not regulated
+    float* obs_s;            // staging for one Kinematics observation
+    int32_t* cell;           // OccupancyGrid per-cell winner (W*H ints)
+    int L;
+    int vcap;                // storage capacity (slots per env in HBM), <= V
+};
+
+// ------------------------------------------------------------------------------------------------
+// scalar helpers: ttrl_env/utils.py
+// ------------------------------------------------------------------------------------------------
+TT_HD double not_zero(double x) {  // utils.py:48-54
+    const double eps = 1e-2;
+    if (fabs(x) > eps) return x;
+    return x >= 0 ? eps : -eps;
+}
+// Python floored float modulo by 2*pi (utils.py:58).  Fast path for 0 <= a < 2pi (the common case); the
+// general path is the exact remainder through one fma.
+TT_HD double mod_2pi(double a) {
+    const double b = 2 * kPi;
+    if (a >= 0 && a < b) return a;
+    double q = floor(a / b);
+    double m = fma(-q, b, a);
+    if (m < 0) m += b;
+    else if (m >= b) m -= b;
+    return m;
+}
+TT_HD double wrap_to_pi(double x) { return mod_2pi(x + kPi) - kPi; }  // utils.py:57-58
+TT_HD double py_mod1(double a) {  // a % 1.0 for behavior.py:64
+    double m = a - floor(a);
+    return (m >= 1.0) ? 0.0 : m;
+}
+TT_HD double lmap(double v, double x0, double x1, double y0, double y1) {  // utils.py:29-31
+    return y0 + (v - x0) * (y1 - y0) / (x1 - x0);
+}
+TT_HD double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+
+// ------------------------------------------------------------------------------------------------
+// lane geometry: ttrl_env/road/lane.py
+// ------------------------------------------------------------------------------------------------
+TT_HD void lane_local(const ttrl_lane& l, double px, double py, double& s, double& r) {
+    double dx = px - l.ax, dy = py - l.ay;
+    if (l.kind == TTRL_LANE_CIRCULAR) {  // lane.py:355-362
+        double phi = atan2(dy, dx);
+        phi = l.start_phase + wrap_to_pi(phi - l.start_phase);
+        double rad = sqrt(dx * dx + dy * dy);
+        s = l.cdir * (phi - l.start_phase) * l.radius;
+        r = l.cdir * (l.radius - rad);
+    } else {  // lane.py:209-213, :282-286
+        double lon = dx * l.dx + dy * l.dy;
+        double lat = dx * (-l.dy) + dy * l.dx;
+        if (l.kind == TTRL_LANE_SINE) lat = lat - l.amplitude * sin(l.pulsation * lon + l.phase);
+        s = lon;
+        r = lat;
+    }
+}
+TT_HD void lane_position(const ttrl_lane& l, double s, double r, double& px, double& py) {
+    if (l.kind == TTRL_LANE_CIRCULAR) {  // lane.py:341-345
+        double phi = l.cdir * s / l.radius + l.start_phase;
+        double rr = l.radius - r * l.cdir;
+        px = l.ax + rr * cos(phi);
+        py = l.ay + rr * sin(phi);
+    } else {  // lane.py:196-201, :268-273
+        if (l.kind == TTRL_LANE_SINE) r = r + l.amplitude * sin(l.pulsation * s + l.phase);
+        px = l.ax + s * l.dx + r * (-l.dy);
+        py = l.ay + s * l.dy + r * l.dx;
+    }
+}
+TT_HD double lane_heading_at(const ttrl_lane& l, double s) {  // lane.py:203-204, :275-280, :347-350
+    if (l.kind == TTRL_LANE_CIRCULAR) {
+        double phi = l.cdir * s / l.radius + l.start_phase;
+        return phi + kPi / 2 * l.cdir;
+    }
+    if (l.kind == TTRL_LANE_SINE) return l.heading + atan(l.amplitude * l.pulsation * cos(l.pulsation * s + l.phase));
+    return l.heading;
+}
+TT_HD bool lane_on_lane(const ttrl_lane& l, double s, double r, double margin) {  // lane.py:80-102
+    return fabs(r) <= l.width / 2 + margin && -kVehLength <= s && s < l.length + kVehLength;
+}
+TT_HD bool lane_reachable(const ttrl_lane& l, double s, double r) {  // lane.py:104-118
+    if (l.forbidden) return false;
+    return fabs(r) <= 2 * l.width && 0 <= s && s < l.length + kVehLength;
+}
+TT_HD double lane_distance_sr(const ttrl_lane& l, double s, double r) {  // lane.py:127-130
+    return fabs(r) + fmax(s - l.length, 0.0) + fmax(0.0 - s, 0.0);
+}
+TT_HD double lane_distance(const ttrl_lane& l, double px, double py) {
+    double s, r;
+    lane_local(l, px, py, s, r);
+    return lane_distance_sr(l, s, r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// table access
+// ------------------------------------------------------------------------------------------------
+template <class C> TT_HD double& S_(C& c, int v, int l) { return c.S[v * c.L + l]; }
+template <class C> TT_HD double& R_(C& c, int v, int l) { return c.R[v * c.L + l]; }
+
+// Rebuild row v of the table and return the closest lane: RoadNetwork.get_closest_lane_index
+// (road.py:55-71, np.argmin keeps the FIRST minimum) over distance_with_heading (lane.py:132-147).
+template <class C>
+TT_HD int table_row_and_closest(C& c, int v) {
+    const double px = c.st->x[v], py = c.st->y[v], hd = c.st->h[v];
+    int best = 0;
+    double bd = 0;
+    for (int l = 0; l < c.L; ++l) {
+        const ttrl_lane& ln = c.lanes[l];
+        double s, r;
+        lane_local(ln, px, py, s, r);
+        S_(c, v, l) = s;
+        R_(c, v, l) = r;
+        double ang = fabs(wrap_to_pi(hd - lane_heading_at(ln, s)));
+        double d = lane_distance_sr(ln, s, r) + 1.0 * ang;
+        if (l == 0 || d < bd) { bd = d; best = l; }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// routes (packed: entry k in byte k; lane byte 0xFF = None)
+// ------------------------------------------------------------------------------------------------
+TT_HD int route_road_at(uint32_t w, int k) { return (w >> (8 * k)) & 0xFF; }
+TT_HD int route_lane_at(uint32_t w, int k) { int b = (w >> (8 * k)) & 0xFF; return b == 0xFF ? -1 : b; }
+
+// RoadNetwork.next_lane_given_next_road road.py:138-157 (next_id < 0 means None)
+template <class C>
+TT_HD int next_lane_given_next_road(C& c, int road, int id, int next_road, int next_id, double px, double py, double& dist) {
+    const ttrl_road& nr = c.sc->roads[next_road];
+    if (c.sc->roads[road].n_lanes == nr.n_lanes) {
+        if (next_id < 0) next_id = id;
+    } else {
+        double bd = 0;
+        int b = 0;
+        for (int l = 0; l < nr.n_lanes; ++l) {
+            double d = lane_distance(c.lanes[nr.first_lane + l], px, py);
+            if (l == 0 || d < bd) { bd = d; b = l; }
+        }
+        next_id = b;
+    }
+    dist = lane_distance(c.lanes[nr.first_lane + next_id], px, py);
+    return next_id;
+}
+
+// RoadNetwork.next_lane road.py:73-136; mutates the vehicle's route (route.pop(0), :100)
+template <class C>
+TT_HDN int next_lane(C& c, int i, int cur) {
+    auto* st = c.st;
+    const ttrl_lane& cl = c.lanes[cur];
+    const int road = cl.road, id = cl.lane_id;
+    const int to = c.sc->roads[road].to_node;
+    int next_road = -1, next_id = -1;
+    if (st->rlen[i] > 0) {
+        if (route_road_at(st->rroad[i], 0) == road) {
+            st->rroad[i] >>= 8;
+            st->rlanew[i] >>= 8;
+            st->rlen[i] -= 1;
+        }
+        if (st->rlen[i] > 0 && c.sc->roads[route_road_at(st->rroad[i], 0)].from_node == to) {
+            next_road = route_road_at(st->rroad[i], 0);
+            next_id = route_lane_at(st->rlanew[i], 0);
+        }
+    }
+    double lon = S_(c, i, cur), qx, qy;
+    lane_position(cl, lon, 0.0, qx, qy);
+    if (next_road < 0) {
+        const int a = c.sc->node_first[to], b = c.sc->node_first[to + 1];
+        if (a == b) return cur;  // KeyError branch (:129-130)
+        double bd = 0;
+        int br = -1, bid = 0;
+        for (int k = a; k < b; ++k) {
+            double d;
+            int nid = next_lane_given_next_road(c, road, id, c.sc->node_roads[k], -1, qx, qy, d);
+            if (k == a || d < bd) { bd = d; br = c.sc->node_roads[k]; bid = nid; }
+        }
+        next_road = br;
+        next_id = bid;
+    } else {
+        double d;
+        next_id = next_lane_given_next_road(c, road, id, next_road, next_id, qx, qy, d);
+    }
+    return c.sc->roads[next_road].first_lane + next_id;
+}
+
+// ControlledVehicle.follow_road controller.py:135-143 (+ after_end lane.py:120-125)
+template <class C>
+TT_HD void follow_road(C& c, int i) {
+    const int tl = c.st->tlane[i];
+    if (S_(c, i, tl) > c.lanes[tl].length - kVehLength / 2) c.st->tlane[i] = next_lane(c, i, tl);
+}
+
+// ControlledVehicle.steering_control controller.py:145-187
+template <class C>
+TT_HD double steering_control(C& c, int i, int target_lane) {
+    const double TAU_PURSUIT = 0.5 * 0.2, KP_LATERAL = 1 / 0.6, KP_HEADING = 1 / 0.2;
+    const double MAX_STEER = kPi / 3;
+    const ttrl_lane& tl = c.lanes[target_lane];
+    const double s = S_(c, i, target_lane), r = R_(c, i, target_lane);
+    const double speed = c.st->v[i];
+    double lane_next = s + speed * TAU_PURSUIT;
+    double lane_future_heading = lane_heading_at(tl, lane_next);
+    double lateral_speed_command = -KP_LATERAL * r;
+    double heading_command = asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
+    double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
+    double heading_rate_command = KP_HEADING * wrap_to_pi(heading_ref - c.st->h[i]);
+    double slip_angle = asin(clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0));
+    double steering_angle = atan(2 * tan(slip_angle));
+    return clipd(steering_angle, -MAX_STEER, MAX_STEER);
+}
+
+// MDPVehicle.speed_to_index controller.py:326-344 (np.round -> round half to even -> rint)
+TT_HD int speed_to_index(const ttrl_config& cfg, double speed) {
+    const int n = cfg.n_target_speeds;
+    double x = (speed - cfg.target_speeds[0]) / (cfg.target_speeds[n - 1] - cfg.target_speeds[0]);
+    return (int)clipd(rint(x * (n - 1)), 0.0, (double)(n - 1));
+}
+
+enum { A_NONE = 0, A_IDLE, A_LANE_LEFT, A_LANE_RIGHT, A_FASTER, A_SLOWER };
+TT_HD int decode_action(const ttrl_config& cfg, int a) {  // action.py:204-211
+    if (a < 0) return A_NONE;
+    if (cfg.action_mode == TTRL_ACT_ALL) return a == 0 ? A_LANE_LEFT : a == 1 ? A_IDLE : a == 2 ? A_LANE_RIGHT : a == 3 ? A_FASTER : A_SLOWER;
+    if (cfg.action_mode == TTRL_ACT_LONGI) return a == 0 ? A_SLOWER : a == 1 ? A_IDLE : A_FASTER;
+    return a == 0 ? A_LANE_LEFT : a == 1 ? A_IDLE : A_LANE_RIGHT;
+}
+
+// ControlledVehicle.act controller.py:89-133
+template <class C>
+TT_HDN void controlled_act(C& c, int i, int action) {
+    const double KP_A = 1 / 0.6, MAX_STEER = kPi / 3;
+    auto* st = c.st;
+    follow_road(c, i);
+    if (action == A_LANE_RIGHT || action == A_LANE_LEFT) {
+        const ttrl_lane& tl = c.lanes[st->tlane[i]];
+        const ttrl_road& rd = c.sc->roads[tl.road];
+        int id = tl.lane_id + (action == A_LANE_RIGHT ? 1 : -1);
+        id = id < 0 ? 0 : (id > rd.n_lanes - 1 ? rd.n_lanes - 1 : id);
+        const int cand = rd.first_lane + id;
+        if (lane_reachable(c.lanes[cand], S_(c, i, cand), R_(c, i, cand))) st->tlane[i] = cand;
+    }
+    double steering = steering_control(c, i, st->tlane[i]);
+    st->steer[i] = clipd(steering, -MAX_STEER, MAX_STEER);
+    st->acc[i] = KP_A * (st->tspeed[i] - st->v[i]);  // speed_control :189-198
+}
+
+// MDPVehicle.act controller.py:295-315
+template <class C>
+TT_HD void mdp_act(C& c, int i, int action) {
+    auto* st = c.st;
+    const ttrl_config& cfg = c.sc->cfg;
+    if (action == A_FASTER) st->sidx[i] = speed_to_index(cfg, st->v[i]) + 1;
+    else if (action == A_SLOWER) st->sidx[i] = speed_to_index(cfg, st->v[i]) - 1;
+    else { controlled_act(c, i, action); return; }
+    const int n = cfg.n_target_speeds;
+    st->sidx[i] = st->sidx[i] < 0 ? 0 : (st->sidx[i] > n - 1 ? n - 1 : st->sidx[i]);
+    st->tspeed[i] = cfg.target_speeds[st->sidx[i]];
+    controlled_act(c, i, A_NONE);
+}
+
+// ------------------------------------------------------------------------------------------------
+// IDM / MOBIL: ttrl_env/vehicle/behavior.py
+// ------------------------------------------------------------------------------------------------
+// Road.neighbour_vehicles road.py:480-513 served from the table
+template <class C>
+TT_HD void neighbours(C& c, int i, int lane, int& front, int& rear) {
+    const ttrl_lane& l = c.lanes[lane];
+    const double s = S_(c, i, lane);
+    const double half = l.width / 2 + 1.0, hi = l.length + kVehLength;
+    double sf = 0, sr = 0;
+    int f = -1, r = -1;
+    const int n = c.st->n;
+    for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        const double sv = S_(c, j, lane), lv = R_(c, j, lane);
+        if (!(fabs(lv) <= half && -kVehLength <= sv && sv < hi)) continue;
+        if (s <= sv && (f < 0 || sv <= sf)) { sf = sv; f = j; }
+        if (sv < s && (r < 0 || sv > sr)) { sr = sv; r = j; }
+    }
+    front = f;
+    rear = r;
+}
+// IDMVehicle.desired_gap behavior.py:192-217
+template <class C>
+TT_HD double desired_gap(C& c, int ego, int front) {
+    const ttrl_config& cfg = c.sc->cfg;
+    auto* st = c.st;
+    const double ab = -cfg.comfort_acc_max * cfg.comfort_acc_min;
+    const double ec = st->ch[ego], es = st->sh[ego];
+    const double dvx = st->v[ego] * ec - st->v[front] * st->ch[front], dvy = st->v[ego] * es - st->v[front] * st->sh[front];
+    const double dv = dvx * ec + dvy * es;
+    return cfg.distance_wanted + st->v[ego] * cfg.time_wanted + st->v[ego] * dv / (2 * sqrt(ab));
+}
+// IDMVehicle.acceleration behavior.py:150-190 (self_delta = SELF's DELTA, also when ego is another vehicle)
+template <class C>
+TT_HD double idm_acceleration(C& c, double self_delta, int ego, int front) {
+    if (ego < 0) return 0.0;
+    const ttrl_config& cfg = c.sc->cfg;
+    auto* st = c.st;
+    const int le = st->lane[ego];
+    const double ts = clipd(st->tspeed[ego], 0.0, c.lanes[le].speed_limit);
+    double acc = cfg.comfort_acc_max * (1 - pow(fmax(st->v[ego], 0.0) / fabs(not_zero(ts)), self_delta));
+    if (front >= 0) {
+        const double d = S_(c, front, le) - S_(c, ego, le);  // lane_distance_to objects.py:182-197
+        const double q = desired_gap(c, ego, front) / not_zero(d);
+        acc -= cfg.comfort_acc_max * (q * q);
+    }
+    return acc;
+}
+// IDMVehicle.mobil behavior.py:265-324
+template <class C>
+TT_HDN bool mobil(C& c, int i, int cand) {
+    const ttrl_config& cfg = c.sc->cfg;
+    auto* st = c.st;
+    const double dl = st->delta[i];
+    int new_prec, new_foll;
+    neighbours(c, i, cand, new_prec, new_foll);
+    const double new_following_a = idm_acceleration(c, dl, new_foll, new_prec);
+    const double new_following_pred_a = idm_acceleration(c, dl, new_foll, i);
+    if (new_following_pred_a < -cfg.lane_change_max_braking_imposed) return false;
+    int old_prec, old_foll;
+    neighbours(c, i, st->lane[i], old_prec, old_foll);
+    const double self_pred_a = idm_acceleration(c, dl, i, new_prec);
+    if (st->rlen[i] > 0 && route_lane_at(st->rlanew[i], 0) >= 0) {
+        const int cur_t = c.lanes[st->tlane[i]].lane_id;
+        const int want = route_lane_at(st->rlanew[i], 0) - cur_t, dir = c.lanes[cand].lane_id - cur_t;
+        const int sw = (want > 0) - (want < 0), sd = (dir > 0) - (dir < 0);
+        if (sd != sw) return false;
+        if (self_pred_a < -cfg.lane_change_max_braking_imposed) return false;
+    } else {
+        const double self_a = idm_acceleration(c, dl, i, old_prec);
+        const double old_following_a = idm_acceleration(c, dl, old_foll, i);
+        const double old_following_pred_a = idm_acceleration(c, dl, old_foll, old_prec);
+        const double jerk = self_pred_a - self_a +
+                            cfg.politeness * (new_following_pred_a - new_following_a + old_following_pred_a - old_following_a);
+        if (jerk < cfg.lane_change_min_acc_gain) return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ACT, split in three phases so that it is parallel over vehicles yet reproduces the reference's
+// sequential Road.act (road.py:461-464).  The only cross-vehicle write->read coupling inside act() is the
+// abort rule of change_lane_policy (behavior.py:229-244), which reads OTHER vehicles' target_lane_index:
+// vehicles earlier in the list have already acted (new value), later ones have not (old value).
+//   phase A  every vehicle: follow_road + (not changing lane) timer/MOBIL decision; ego: full controller
+//   phase B  vehicles in an ongoing lane change, in list order: abort test against the mixed old/new view
+//   phase C  every IDM vehicle: steering + IDM acceleration with its final target lane
+// ------------------------------------------------------------------------------------------------
+template <class C>
+TT_HD void act_phase_a(C& c, int i) {
+    auto* st = c.st;
+    st->tl_old[i] = st->tlane[i];
+    st->mark[i] = 0;
+    if (i >= st->n) return;
+    if (st->flags[i] & TTRL_FL_MDP) { mdp_act(c, i, A_NONE); return; }  // Road.act -> MDPVehicle.act(None)
+    if (st->flags[i] & TTRL_FL_CRASHED) return;                       // behavior.py:102-103
+    follow_road(c, i);
+    const int ln = st->lane[i];
+    if (ln != st->tlane[i]) {  // ongoing change: behavior.py:229-244, resolved in phase B
+        if (c.lanes[ln].road == c.lanes[st->tlane[i]].road) st->mark[i] = 1;
+        return;
+    }
+    if (!(c.sc->cfg.lane_change_delay < st->timer[i])) return;  // utils.do_every utils.py:25-26
+    st->timer[i] = 0;
+    const ttrl_lane& l = c.lanes[ln];
+    const int nl = c.sc->roads[l.road].n_lanes;
+    for (int k = 0; k < 2; ++k) {  // side_lanes road.py:200-211: id-1 then id+1
+        const int cand = k == 0 ? ln - 1 : ln + 1;
+        if (k == 0 ? !(l.lane_id > 0) : !(l.lane_id < nl - 1)) continue;
+        if (!lane_reachable(c.lanes[cand], S_(c, i, cand), R_(c, i, cand))) continue;
+        if (fabs(st->v[i]) < 1) continue;
+        if (mobil(c, i, cand)) st->tlane[i] = cand;
+    }
+}
+// abort predicate of vehicle i against vehicle j (behavior.py:232-243)
+template <class C>
+TT_HD bool abort_pred(C& c, int i, int j) {
+    auto* st = c.st;
+    if (j == i || j >= st->n) return false;
+    const int ti = st->tlane[i];
+    const int view = j < i ? st->tlane[j] : st->tl_old[j];
+    if (!(st->lane[j] != ti && view == ti)) return false;
+    const int li = st->lane[i];
+    const double d = S_(c, j, li) - S_(c, i, li);
+    const double d_star = desired_gap(c, i, j);
+    return 0 < d && d < d_star;
+}
+template <class C>
+TT_HD void act_phase_c(C& c, int i) {
+    auto* st = c.st;
+    if (i >= st->n) return;
+    if (st->flags[i] & (TTRL_FL_MDP | TTRL_FL_CRASHED)) return;
+    const double MAX_STEER = kPi / 3;
+    const int tl = st->tlane[i], ln = st->lane[i];
+    const double steering = clipd(steering_control(c, i, tl), -MAX_STEER, MAX_STEER);
+    int f, r;
+    neighbours(c, i, ln, f, r);
+    double acc = idm_acceleration(c, st->delta[i], i, f);
+    if (ln != tl) {
+        neighbours(c, i, tl, f, r);
+        acc = fmin(acc, idm_acceleration(c, st->delta[i], i, f));
+    }
+    st->steer[i] = steering;
+    st->acc[i] = clipd(acc, -c.sc->cfg.acc_max, c.sc->cfg.acc_max);
+}
+
+// ------------------------------------------------------------------------------------------------
+// INTEGRATE: IDMVehicle.step behavior.py:139-148 -> Vehicle.step kinematics.py:130-153, clip_actions :155-168,
+// on_state_update :170-177 (closest lane via the rebuilt table row)
+// ------------------------------------------------------------------------------------------------
+template <class C>
+TT_HD void integrate(C& c, int i) {
+    auto* st = c.st;
+    if (i >= st->n) return;
+    const double dt = c.sc->dt;
+    int fl = st->flags[i];
+    if (!(fl & TTRL_FL_MDP)) st->timer[i] += dt;
+    double steer = st->steer[i], acc = st->acc[i];
+    const double speed = st->v[i];
+    if (fl & TTRL_FL_CRASHED) { steer = 0; acc = -1.0 * speed; }
+    if (speed > 40.0) acc = fmin(acc, 1.0 * (40.0 - speed));
+    else if (speed < -40.0) acc = fmax(acc, 1.0 * (-40.0 - speed));
+    st->steer[i] = steer;
+    st->acc[i] = acc;
+    const double beta = atan(1.0 / 2 * tan(steer));
+    const double hd = st->h[i];
+    const double vx = speed * cos(hd + beta), vy = speed * sin(hd + beta);
+    double px = st->x[i] + vx * dt, py = st->y[i] + vy * dt;
+    if (fl & TTRL_FL_HAS_IMPACT) {
+        px += st->impx[i];
+        py += st->impy[i];
+        fl = (fl | TTRL_FL_CRASHED) & ~TTRL_FL_HAS_IMPACT;
+        st->impx[i] = 0;
+        st->impy[i] = 0;
+    }
+    const double nh = hd + speed * sin(beta) / (kVehLength / 2) * dt;
+    st->x[i] = px;
+    st->y[i] = py;
+    st->h[i] = nh;
+    st->v[i] = speed + acc * dt;
+    st->ch[i] = cos(nh);
+    st->sh[i] = sin(nh);
+    st->flags[i] = fl;
+    st->lane[i] = table_row_and_closest(c, i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// COLLIDE: Road.step's pair loop road.py:474-476 -> handle_collisions objects.py:91-137 -> SAT utils.py:175-239.
+// Thread k scans every partner p.  In the reference the pair (i<j) loop assigns `impact` to both members, so
+// for vehicle k the LAST assignment comes from its will-intersect partner with the largest index (pairs
+// involving k are visited in increasing partner order); `crashed` is an OR.
+// ------------------------------------------------------------------------------------------------
+struct Poly { double p[5][2]; };
+template <class C>
+TT_HD void vehicle_polygon(C& c, int i, Poly& o) {  // objects.py:168-180
+    const double cs = c.st->ch[i], sn = c.st->sh[i], px = c.st->x[i], py = c.st->y[i];
+    const double hx[4] = {-kVehLength / 2, -kVehLength / 2, +kVehLength / 2, +kVehLength / 2};
+    const double hy[4] = {-kVehWidth / 2, +kVehWidth / 2, +kVehWidth / 2, -kVehWidth / 2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        o.p[k][0] = (cs * hx[k] + (-sn) * hy[k]) + px;
+        o.p[k][1] = (sn * hx[k] + cs * hy[k]) + py;
+    }
+    o.p[4][0] = o.p[0][0];
+    o.p[4][1] = o.p[0][1];
+}
+TT_HD void project_polygon(const Poly& g, double nx, double ny, double& mn, double& mx) {  // utils.py:175-183
+    mn = mx = g.p[0][0] * nx + g.p[0][1] * ny;
+#pragma unroll
+    for (int k = 1; k < 5; ++k) {
+        const double pr = g.p[k][0] * nx + g.p[k][1] * ny;
+        if (pr < mn) mn = pr;
+        if (pr > mx) mx = pr;
+    }
+}
+TT_HD double interval_distance(double min_a, double max_a, double min_b, double max_b) {  // utils.py:186-191
+    return min_a < min_b ? min_b - max_a : min_a - max_b;
+}
+// utils.are_polygons_intersecting utils.py:194-239 (a = lower-index vehicle).  Returns bit0 intersecting, bit1 will.
+template <class C>
+TT_HDN int sat_pair(C& c, int ia, int ib, double& tx, double& ty) {
+    auto* st = c.st;
+    const double dt = c.sc->dt;
+    Poly a, b;
+    vehicle_polygon(c, ia, a);
+    vehicle_polygon(c, ib, b);
+    const double rvx = st->v[ia] * st->ch[ia] * dt - st->v[ib] * st->ch[ib] * dt;
+    const double rvy = st->v[ia] * st->sh[ia] * dt - st->v[ib] * st->sh[ib] * dt;
+    bool inter = true, will = true;
+    double min_distance = INFINITY, axx = 0, axy = 0;
+    for (int poly = 0; poly < 2; ++poly) {
+        const Poly& pg = poly == 0 ? a : b;
+        for (int k = 0; k < 4; ++k) {
+            double nx = -pg.p[k + 1][1] + pg.p[k][1], ny = pg.p[k + 1][0] - pg.p[k][0];
+            const double nn = sqrt(nx * nx + ny * ny);
+            nx /= nn;
+            ny /= nn;
+            double min_a, max_a, min_b, max_b;
+            project_polygon(a, nx, ny, min_a, max_a);
+            project_polygon(b, nx, ny, min_b, max_b);
+            if (interval_distance(min_a, max_a, min_b, max_b) > 0) inter = false;
+            const double vp = nx * rvx + ny * rvy;
+            if (vp < 0) min_a += vp; else max_a += vp;
+            const double distance = interval_distance(min_a, max_a, min_b, max_b);
+            if (distance > 0) will = false;
+            if (!inter && !will) break;
+            if (fabs(distance) < min_distance) {
+                min_distance = fabs(distance);
+                const double cax = (((a.p[0][0] + a.p[1][0]) + a.p[2][0]) + a.p[3][0]) / 4, cay = (((a.p[0][1] + a.p[1][1]) + a.p[2][1]) + a.p[3][1]) / 4;
+                const double cbx = (((b.p[0][0] + b.p[1][0]) + b.p[2][0]) + b.p[3][0]) / 4, cby = (((b.p[0][1] + b.p[1][1]) + b.p[2][1]) + b.p[3][1]) / 4;
+                if ((cax - cbx) * nx + (cay - cby) * ny > 0) { axx = nx; axy = ny; } else { axx = -nx; axy = -ny; }
+            }
+        }
+    }
+    if (will) { tx = min_distance * axx; ty = min_distance * axy; } else { tx = 0; ty = 0; }
+    return (inter ? 1 : 0) | (will ? 2 : 0);
+}
+template <class C>
+TT_HD void collide(C& c, int k) {
+    auto* st = c.st;
+    const int n = st->n;
+    if (k >= n) return;
+    const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
+    const double dt = c.sc->dt;
+    const double xk = st->x[k], yk = st->y[k], vk = st->v[k];
+    bool crashed = false, has_imp = false;
+    double ix = 0, iy = 0;
+    for (int p = 0; p < n; ++p) {
+        if (p == k) continue;
+        const int lo = k < p ? k : p;
+        const double dx = st->x[p] - xk, dy = st->y[p] - yk;  // |other - self| is symmetric up to sign
+        const double thr = (diag + diag) / 2 + (lo == k ? vk : st->v[p]) * dt;
+        const double d2 = dx * dx + dy * dy;
+        if (sqrt(d2) > thr) continue;  // objects.py:123-126 (self = the lower index)
+        double tx, ty;
+        const int res = sat_pair(c, lo, k < p ? p : k, tx, ty);
+        if (res & 2) {  // will_intersect: self.impact = +t/2, other.impact = -t/2 (objects.py:110-111)
+            has_imp = true;
+            ix = lo == k ? tx / 2 : -tx / 2;
+            iy = lo == k ? ty / 2 : -ty / 2;
+        }
+        if (res & 1) crashed = true;
+    }
+    if (has_imp) { st->impx[k] = ix; st->impy[k] = iy; st->flags[k] |= TTRL_FL_HAS_IMPACT; }
+    if (crashed) st->flags[k] |= TTRL_FL_CRASHED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// REGULATE: RegulatedRoad.enforce_road_rules regulation.py:34-103
+// ------------------------------------------------------------------------------------------------
+// RoadNetwork.position_heading_along_route road.py:323-362 with lateral 0
+template <class C>
+TT_HD void position_heading_along_route(C& c, uint32_t rroad, uint32_t rlanew, int rlen, double lon, int cur_lane,
+                                        double& px, double& py, double& ph) {
+    const int cur_id = c.lanes[cur_lane].lane_id;
+    int k = 0;
+    auto head = [&](int kk) {
+        const int lid = route_lane_at(rlanew, kk);
+        return c.sc->roads[route_road_at(rroad, kk)].first_lane + (lid < 0 ? cur_id : lid);
+    };
+    int li = head(k);
+    while (rlen - k > 1 && lon > c.lanes[li].length) {
+        lon -= c.lanes[li].length;
+        ++k;
+        li = head(k);
+    }
+    lane_position(c.lanes[li], lon, 0.0, px, py);
+    ph = lane_heading_at(c.lanes[li], lon);
+}
+// phase R1: un-yield (regulation.py:38-45) + ControlledVehicle.predict_trajectory_constant_speed (controller.py:236-253)
+template <class C>
+TT_HDN void regulate_predict(C& c, int i) {
+    auto* st = c.st;
+    if (i >= st->n) return;
+    st->mark[i] = 0;
+    if (st->flags[i] & TTRL_FL_YIELDING) {
+        if (st->ytimer[i] >= 0.0 * 2) {
+            st->tspeed[i] = c.lanes[st->lane[i]].speed_limit;
+            st->flags[i] &= ~TTRL_FL_YIELDING;
+        } else st->ytimer[i] += 1;
+    }
+    const int ln = st->lane[i];
+    const double s0 = S_(c, i, ln);
+    uint32_t rr = st->rroad[i], rl = st->rlanew[i];
+    int rlen = st->rlen[i];
+    if (rlen <= 0) {  // `self.route or [self.lane_index]`
+        rlen = 1;
+        rr = (uint32_t)c.lanes[ln].road;
+        rl = (uint32_t)c.lanes[ln].lane_id;
+    }
+    double* px = c.pred + (0 * C::V + i) * kPred;
+    double* py = c.pred + (1 * C::V + i) * kPred;
+    double* ph = c.pred + (2 * C::V + i) * kPred;
+    for (int k = 0; k < kPred; ++k) {
+        const double t = 0.25 + k * 0.25;
+        position_heading_along_route(c, rr, rl, rlen, s0 + st->v[i] * t, ln, px[k], py[k], ph[k]);
+    }
+}
+// utils.point_in_rotated_rectangle utils.py:75-91 with precomputed cos/sin of the rectangle angle
+TT_HD bool point_in_rotated_rectangle(double px, double py, double cx, double cy, double length, double width, double cs, double sn) {
+    const double dx = px - cx, dy = py - cy;
+    const double rx = cs * dx + (-sn) * dy, ry = sn * dx + cs * dy;
+    return -length / 2 <= rx && rx <= length / 2 && -width / 2 <= ry && ry <= width / 2;
+}
+// utils.has_corner_inside utils.py:158-172 (4 corners, centre, 4 edge midpoints: rect_corners :126-155)
+TT_HD bool has_corner_inside(double x1, double y1, double c1, double s1, double x2, double y2, double c2, double s2, double len, double wid) {
+    const double hl = len / 2, hw = wid / 2;
+    const double qx[9] = {-hl, -hl, +hl, +hl, 0, -hl, hl, 0, 0};
+    const double qy[9] = {-hw, +hw, +hw, -hw, 0, 0, 0, -hw, hw};
+    for (int k = 0; k < 9; ++k) {
+        const double px = (c1 * qx[k] + (-s1) * qy[k]) + x1;
+        const double py = (s1 * qx[k] + c1 * qy[k]) + y1;
+        if (point_in_rotated_rectangle(px, py, x2, y2, len, wid, c2, s2)) return true;
+    }
+    return false;
+}
+// RegulatedRoad.is_conflict_possible regulation.py:80-103
+template <class C>
+TT_HDN bool is_conflict_possible(C& c, int i, int j) {
+    const double* xi = c.pred + (0 * C::V + i) * kPred; const double* yi = c.pred + (1 * C::V + i) * kPred; const double* hi = c.pred + (2 * C::V + i) * kPred;
+    const double* xj = c.pred + (0 * C::V + j) * kPred; const double* yj = c.pred + (1 * C::V + j) * kPred; const double* hj = c.pred + (2 * C::V + j) * kPred;
+    const double len = 1.5 * kVehLength, wid = 0.9 * kVehWidth;
+    for (int k = 0; k < kPred; ++k) {
+        const double dx = xj[k] - xi[k], dy = yj[k] - yi[k];
+        if (sqrt(dx * dx + dy * dy) > kVehLength) continue;
+        const double c1 = cos(hi[k]), s1 = sin(hi[k]), c2 = cos(hj[k]), s2 = sin(hj[k]);
+        if (has_corner_inside(xi[k], yi[k], c1, s1, xj[k], yj[k], c2, s2, len, wid) ||
+            has_corner_inside(xj[k], yj[k], c2, s2, xi[k], yi[k], c1, s1, len, wid))
+            return true;
+    }
+    return false;
+}
+// phase R2: one (i<j) pair; marks the yielding vehicle (respect_priorities regulation.py:64-78).  The writes of
+// the reference (:59-62) are idempotent flags, so pair order is irrelevant; they are merged in phase R3.
+template <class C>
+TT_HD void regulate_pair(C& c, int i, int j) {
+    auto* st = c.st;
+    if (!is_conflict_possible(c, i, j)) return;
+    const int p1 = c.lanes[st->lane[i]].priority, p2 = c.lanes[st->lane[j]].priority;
+    int y;
+    if (p1 > p2) y = j;
+    else if (p1 < p2) y = i;
+    else {
+        const double f12 = st->ch[i] * (st->x[j] - st->x[i]) + st->sh[i] * (st->y[j] - st->y[i]);  // objects.py:204-205
+        const double f21 = st->ch[j] * (st->x[i] - st->x[j]) + st->sh[j] * (st->y[i] - st->y[j]);
+        y = f12 > f21 ? i : j;
+    }
+    if (!(st->flags[y] & TTRL_FL_MDP)) st->mark[y] = 1;  // benign same-value race
+}
+template <class C>
+TT_HD void regulate_apply(C& c, int i) {
+    auto* st = c.st;
+    if (i < st->n && st->mark[i]) {
+        st->tspeed[i] = 0;
+        st->flags[i] |= TTRL_FL_YIELDING;
+        st->ytimer[i] = 0;
+    }
+    st->mark[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one simulation sub-step (AbstractEnv._simulate body abstract.py:257-273)
+// ------------------------------------------------------------------------------------------------
+template <class C, class Exec>
+TT_HD void env_substep(C& c, Exec& ex, int raw_action) {
+    auto* st = c.st;
+    const SceneDev* sc = c.sc;
+    // ego meta-action on the first sub-step of an env-step: DiscreteMetaAction.act action.py:259-260
+    if (raw_action >= 0 && st->steps % sc->F == 0) {
+        ex.par([&](int t) { if (t == st->ego) mdp_act(c, t, decode_action(sc->cfg, raw_action)); });
+    }
+    ex.par([&](int t) { act_phase_a(c, t); });
+    {   // phase B (uniform loop: mark[] is in shared memory)
+        const int n = st->n;
+        for (int i = 0; i < n; ++i) {
+            if (!st->mark[i]) continue;
+            const bool ab = ex.any([&](int j) { return abort_pred(c, i, j); });
+            if (ab) ex.par([&](int t) { if (t == i) st->tlane[i] = st->lane[i]; });
+        }
+    }
+    ex.par([&](int t) { act_phase_c(c, t); });
+    if (sc->cfg.regulated) {  // RegulatedRoad.step regulation.py:28-32
+        const int rs = st->road_steps + 1;
+        if (rs % sc->reg_period == 0) {
+            ex.par([&](int t) { regulate_predict(c, t); });
+            ex.par([&](int t) {
+                const int n = st->n, pairs = n * (n - 1) / 2;
+                for (int q = t; q < pairs; q += ex.T) {
+                    // q -> (i<j): row-major over the strict upper triangle
+                    int i = 0, rem = q;
+                    while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+                    regulate_pair(c, i, i + 1 + rem);
+                }
+            });
+            ex.par([&](int t) { regulate_apply(c, t); });
+        }
+    }
+    ex.par([&](int t) { integrate(c, t); });
+    ex.par([&](int t) {
+        collide(c, t);
+        if (t == 0) { st->steps += 1; if (sc->cfg.regulated) st->road_steps += 1; }
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// observations: envs/common/observation.py
+// ------------------------------------------------------------------------------------------------
+template <class C>
+TT_HD double feature_of(C& c, int i, int f) {  // Vehicle.to_dict kinematics.py:237-261
+    auto* st = c.st;
+    switch (f) {
+        case TTRL_F_PRESENCE: return 1.0;
+        case TTRL_F_X: return st->x[i];
+        case TTRL_F_Y: return st->y[i];
+        case TTRL_F_VX: return st->v[i] * st->ch[i];
+        case TTRL_F_VY: return st->v[i] * st->sh[i];
+        case TTRL_F_COS_H: return st->ch[i];
+        case TTRL_F_SIN_H: return st->sh[i];
+        case TTRL_F_HEADING: return st->h[i];
+    }
+    return 0.0;
+}
+TT_HD bool is_relative_feature(int f) { return f == TTRL_F_X || f == TTRL_F_Y || f == TTRL_F_VX || f == TTRL_F_VY; }
+
+// KinematicObservation.observe observation.py:233-275 + Road.close_objects_to road.py:418-447.
+// Stable sort by rank counting: rank(j) = #{k : key_k < key_j or (key_k == key_j and k < j)}.
+// `inv_perm` (or null): row permutation for order == "shuffled" (np_random.shuffle(obs[1:]), :272-273).
+template <class C, class Exec>
+TT_HD void observe_kinematics(C& c, Exec& ex, float* out, const int32_t* inv_perm) {
+    auto* st = c.st;
+    const ttrl_config& cfg = c.sc->cfg;
+    const int Vo = cfg.obs_vehicles, Fe = cfg.n_features;
+    const int ego = st->ego, le = st->lane[ego];
+    ex.par([&](int t) {
+        for (int k = t; k < Vo * Fe; k += ex.T) c.obs_s[k] = 0.0f;
+        int cand = 0;
+        if (t < st->n && t != ego) {
+            const double dx = st->x[t] - st->x[ego], dy = st->y[t] - st->y[ego];
+            if (sqrt(dx * dx + dy * dy) < 5.0 * 40.0) {  // PERCEPTION_DISTANCE abstract.py:41
+                const double d = S_(c, t, le) - S_(c, ego, le);
+                if (cfg.see_behind || -2 * kVehLength < d) cand = 1;
+            }
+        }
+        st->mark[t] = cand;
+    });
+    ex.par([&](int t) {
+        int row = -1;
+        if (t == ego) row = 0;
+        else if (st->mark[t]) {
+            const double kt = fabs(S_(c, t, le) - S_(c, ego, le));
+            int rank = 0;
+            for (int k = 0; k < st->n; ++k) {
+                if (!st->mark[k] || k == t) continue;
+                if (cfg.order == TTRL_ORDER_SORTED) {
+                    const double kk = fabs(S_(c, k, le) - S_(c, ego, le));
+                    if (kk < kt || (kk == kt && k < t)) ++rank;
+                } else if (k < t) ++rank;
+            }
+            if (rank < Vo - 1) row = 1 + (inv_perm ? inv_perm[rank] : rank);
+        }
+        if (row >= 0) {
+            for (int k = 0; k < Fe; ++k) {
+                const int f = cfg.features[k];
+                double val = feature_of(c, t, f);
+                if (row > 0 && !cfg.absolute && is_relative_feature(f)) val -= feature_of(c, ego, f);
+                if (cfg.normalize && cfg.has_range[k]) {
+                    val = lmap(val, cfg.range_lo[k], cfg.range_hi[k], -1.0, 1.0);
+                    if (cfg.clip) val = clipd(val, -1.0, 1.0);
+                }
+                c.obs_s[row * Fe + k] = (float)val;
+            }
+        }
+    });
+    ex.par([&](int t) { for (int k = t; k < Vo * Fe; k += ex.T) out[k] = c.obs_s[k]; });
+}
+
+// OccupancyGridObservation.observe observation.py:353-412.  The reference writes vehicles in REVERSE list order
+// per layer, so the EARLIEST vehicle of a cell wins: per-cell winner = min slot index (atomicMin in smem).
+template <class C>
+TT_HD bool grid_cell_of(C& c, double px, double py, int& ci, int& cj) {  // pos_to_index :414-434 (already relative)
+    const ttrl_config& cfg = c.sc->cfg;
+    if (cfg.align_to_vehicle_axes) {
+        const double ca = c.st->ch[c.st->ego], sa = c.st->sh[c.st->ego];
+        const double qx = ca * px + sa * py, qy = -sa * px + ca * py;
+        px = qx;
+        py = qy;
+    }
+    const double fi = floor((px - cfg.grid_min[0]) / cfg.grid_step[0]);
+    const double fj = floor((py - cfg.grid_min[1]) / cfg.grid_step[1]);
+    if (!(fi >= 0 && fi < cfg.grid_w && fj >= 0 && fj < cfg.grid_h)) return false;
+    ci = (int)fi;
+    cj = (int)fj;
+    return true;
+}
+template <class C, class Exec>
+TT_HD void observe_grid(C& c, Exec& ex, float* out) {
+    auto* st = c.st;
+    const ttrl_config& cfg = c.sc->cfg;
+    const int W = cfg.grid_w, H = cfg.grid_h, Fe = cfg.n_features, ego = st->ego;
+    ex.par([&](int t) {
+        for (int k = t; k < W * H; k += ex.T) c.cell[k] = 0x7fffffff;
+        for (int k = t; k < Fe * W * H; k += ex.T) out[k] = 0.0f;
+    });
+    ex.par([&](int t) {
+        st->mark[t] = -1;
+        if (t < st->n) {
+            double x = st->x[t] - st->x[ego], y = st->y[t] - st->y[ego];
+            if (cfg.grid_has_xrange) { x = lmap(x, cfg.grid_xrange[0], cfg.grid_xrange[1], -1.0, 1.0); x = lmap(x, -1.0, 1.0, cfg.grid_xrange[0], cfg.grid_xrange[1]); }
+            if (cfg.grid_has_yrange) { y = lmap(y, cfg.grid_yrange[0], cfg.grid_yrange[1], -1.0, 1.0); y = lmap(y, -1.0, 1.0, cfg.grid_yrange[0], cfg.grid_yrange[1]); }
+            int ci, cj;
+            if (grid_cell_of(c, x, y, ci, cj)) {
+                st->mark[t] = ci * H + cj;
+                ex.atomic_min(&c.cell[ci * H + cj], t);
+            }
+        }
+    });
+    ex.par([&](int t) {
+        const int cellid = st->mark[t];
+        if (cellid >= 0 && c.cell[cellid] == t) {
+            for (int layer = 0; layer < Fe; ++layer) {
+                const int f = cfg.features[layer];
+                if (f == TTRL_F_ON_ROAD) continue;
+                double val = feature_of(c, t, f);
+                if (is_relative_feature(f)) val -= feature_of(c, ego, f);
+                if (cfg.has_range[layer]) val = lmap(val, cfg.range_lo[layer], cfg.range_hi[layer], -1.0, 1.0);
+                if (cfg.clip) val = clipd(val, -1.0, 1.0);
+                out[layer * W * H + cellid] = (float)val;
+            }
+        }
+        // on_road layer: fill_road_layer_by_lanes :453-483 (waypoints every min(grid_step) within +-100 m)
+        for (int layer = 0; layer < Fe; ++layer) {
+            if (cfg.features[layer] != TTRL_F_ON_ROAD) continue;
+            const double spacing = fmin(cfg.grid_step[0], cfg.grid_step[1]);
+            for (int li = 0; li < c.L; ++li) {
+                const ttrl_lane& l = c.lanes[li];
+                const double origin = S_(c, ego, li);
+                const double start = origin - 100.0, stop = origin + 100.0;
+                const int nw = (int)ceil((stop - start) / spacing);
+                for (int w = t; w < nw; w += ex.T) {
+                    const double wp = clipd(start + w * spacing, 0.0, l.length);
+                    double px, py;
+                    lane_position(l, wp, 0.0, px, py);
+                    int ci, cj;
+                    if (grid_cell_of(c, px - st->x[ego], py - st->y[ego], ci, cj)) out[layer * W * H + ci * H + cj] = 1.0f;
+                }
+            }
+        }
+    });
+}
+template <class C, class Exec>
+TT_HD void observe(C& c, Exec& ex, float* out, const int32_t* inv_perm) {
+    if (c.sc->cfg.obs_type == TTRL_OBS_GRID) observe_grid(c, ex, out);
+    else observe_kinematics(c, ex, out, inv_perm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// reward / termination (single controlled vehicle)
+// ------------------------------------------------------------------------------------------------
+template <class C>
+TT_HD bool has_arrived(C& c, int i) {  // intersection_env.py:364-369
+    const int ln = c.st->lane[i];
+    return c.lanes[ln].is_exit && S_(c, i, ln) >= 25;
+}
+template <class C>
+TT_HD bool on_road(C& c, int i) {  // objects.py:199-202
+    const int ln = c.st->lane[i];
+    return lane_on_lane(c.lanes[ln], S_(c, i, ln), R_(c, i, ln), 0.0);
+}
+template <class C>
+TT_HD double agent_reward(C& c, int i) {  // intersection_env.py:78-104 / u_turn_env.py:39-71
+    const ttrl_config& cfg = c.sc->cfg;
+    auto* st = c.st;
+    const double crashed = (st->flags[i] & TTRL_FL_CRASHED) ? 1.0 : 0.0;
+    const double hs = clipd(lmap(st->v[i], cfg.reward_speed_lo, cfg.reward_speed_hi, 0.0, 1.0), 0.0, 1.0);
+    const double onr = on_road(c, i) ? 1.0 : 0.0;
+    if (cfg.reward_type == TTRL_REWARD_INTERSECTION) {
+        const bool arrived = has_arrived(c, i);
+        double reward = 0 + cfg.collision_reward * crashed + cfg.high_speed_reward * hs + cfg.arrived_reward * (arrived ? 1.0 : 0.0) + 0 * onr;
+        reward = arrived ? cfg.arrived_reward : reward;
+        reward *= onr;
+        if (cfg.normalize_reward) reward = lmap(reward, cfg.collision_reward, cfg.arrived_reward, 0.0, 1.0);
+        return reward;
+    }
+    const ttrl_lane& l = c.lanes[st->lane[i]];
+    const int nl = c.sc->roads[l.road].n_lanes;
+    const double lane_term = (double)l.lane_id / (double)(nl - 1 > 1 ? nl - 1 : 1);
+    double reward = 0 + cfg.collision_reward * crashed + cfg.lane_reward * lane_term + cfg.high_speed_reward * hs + 0 * onr;
+    if (cfg.normalize_reward) reward = lmap(reward, cfg.collision_reward, cfg.high_speed_reward + cfg.lane_reward, 0.0, 1.0);
+    reward *= onr;
+    return reward;
+}
+template <class C>
+TT_HD bool is_terminated(C& c) {  // intersection_env.py:106-111 / u_turn_env.py:73-74
+    const int e = c.st->ego;
+    const bool crashed = (c.st->flags[e] & TTRL_FL_CRASHED) != 0;
+    const bool off = c.sc->cfg.offroad_terminal && !on_road(c, e);
+    if (c.sc->cfg.reward_type == TTRL_REWARD_INTERSECTION) return crashed || has_arrived(c, e) || off;
+    return crashed || off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// IntersectionEnv._clear_vehicles / _spawn_vehicle intersection_env.py:320-362
+// ------------------------------------------------------------------------------------------------
+struct SlotRegs {
+    double d[13];
+    int32_t i[6];
+    uint32_t u[2];
+};
+template <class C>
+TT_HD void slot_read(C& c, int t, SlotRegs& r) {
+    auto* st = c.st;
+    r.d[0] = st->x[t]; r.d[1] = st->y[t]; r.d[2] = st->h[t]; r.d[3] = st->v[t]; r.d[4] = st->ch[t]; r.d[5] = st->sh[t];
+    r.d[6] = st->steer[t]; r.d[7] = st->acc[t]; r.d[8] = st->tspeed[t]; r.d[9] = st->timer[t]; r.d[10] = st->delta[t];
+    r.d[11] = st->impx[t]; r.d[12] = st->impy[t];
+    r.i[0] = st->lane[t]; r.i[1] = st->tlane[t]; r.i[2] = st->flags[t]; r.i[3] = st->sidx[t]; r.i[4] = st->rlen[t]; r.i[5] = st->ytimer[t];
+    r.u[0] = st->rroad[t]; r.u[1] = st->rlanew[t];
+}
+template <class C>
+TT_HD void slot_write(C& c, int t, const SlotRegs& r) {
+    auto* st = c.st;
+    st->x[t] = r.d[0]; st->y[t] = r.d[1]; st->h[t] = r.d[2]; st->v[t] = r.d[3]; st->ch[t] = r.d[4]; st->sh[t] = r.d[5];
+    st->steer[t] = r.d[6]; st->acc[t] = r.d[7]; st->tspeed[t] = r.d[8]; st->timer[t] = r.d[9]; st->delta[t] = r.d[10];
+    st->impx[t] = r.d[11]; st->impy[t] = r.d[12];
+    st->lane[t] = r.i[0]; st->tlane[t] = r.i[1]; st->flags[t] = r.i[2]; st->sidx[t] = r.i[3]; st->rlen[t] = r.i[4]; st->ytimer[t] = r.i[5];
+    st->rroad[t] = r.u[0]; st->rlanew[t] = r.u[1];
+}
+
+// Stable compaction of the vehicle list (order preserved like the list comprehension at :357-362).
+// NB: table rows are NOT moved; callers rebuild the table before its next use.
+template <class C, class Exec>
+TT_HD void clear_vehicles(C& c, Exec& ex) {
+    auto* st = c.st;
+    ex.par([&](int t) {
+        int keep = 0;
+        if (t < st->n) {
+            keep = (st->flags[t] & TTRL_FL_CONTROLLED) != 0;
+            if (!keep) {
+                const int ln = st->lane[t];
+                const ttrl_lane& l = c.lanes[ln];
+                const bool leaving = l.is_exit && S_(c, t, ln) >= l.length - 4 * kVehLength;
+                keep = !(leaving || st->rlen[t] < 0);
+            }
+        }
+        st->mark[t] = keep;
+    });
+    ex.par2(
+        [&](int t, SlotRegs& r, int& dst) {
+            dst = -1;
+            if (st->mark[t]) {
+                dst = 0;
+                for (int k = 0; k < t; ++k) dst += st->mark[k];
+                slot_read(c, t, r);
+            }
+        },
+        [&](int t, SlotRegs& r, int& dst) {
+            if (dst >= 0) {
+                slot_write(c, dst, r);
+                if (t == st->ego) st->flag0 = dst;
+            }
+            if (t == 0) { int tot = 0; for (int k = 0; k < st->n; ++k) tot += st->mark[k]; st->flag1 = tot; }
+        });
+    ex.par([&](int t) { if (t == 0) { st->ego = st->flag0; st->n = st->flag1; } });
+}
+
+struct SpawnParams {
+    double longitudinal, position_deviation, speed_deviation, spawn_probability;
+    int go_straight;
+};
+// One spawn attempt (_spawn_vehicle :320-348 + make_on_lane objects.py:67-89 + IDMVehicle/ControlledVehicle
+// constructors + plan_route_to + randomize_behavior).  Sets st->flag0 = 1 if a vehicle was appended.
+template <class C, class Exec>
+TT_HD void spawn_vehicle(C& c, Exec& ex, const ttrl_spawn_draw& d, const SpawnParams& sp) {
+    auto* st = c.st;
+    const SceneDev* sc = c.sc;
+    ex.par([&](int t) { if (t == 0) st->flag0 = 0; });
+    if (d.u_spawn > sp.spawn_probability) return;  // uniform: d is per-env
+    const int entry = d.entry, exit_ = sp.go_straight ? (d.entry + 2) % 4 : d.exit;
+    const ttrl_lane& l = c.lanes[sc->spawn_lane[entry]];
+    const double lon = sp.longitudinal + 5 + d.n_pos * sp.position_deviation;
+    const double speed = 8 + d.n_speed * sp.speed_deviation;
+    double px, py;
+    lane_position(l, lon, 0.0, px, py);
+    const double hd = lane_heading_at(l, lon);
+    const bool too_close = ex.any([&](int t) {
+        if (t >= st->n) return false;
+        const double dx = st->x[t] - px, dy = st->y[t] - py;
+        return sqrt(dx * dx + dy * dy) < 15;
+    });
+    if (too_close || st->n >= c.vcap) return;
+    ex.par([&](int t) {
+        if (t != 0) return;
+        const int s = st->n;
+        st->x[s] = px; st->y[s] = py; st->h[s] = hd; st->v[s] = speed;
+        st->ch[s] = cos(hd); st->sh[s] = sin(hd);
+        st->steer[s] = 0; st->acc[s] = 0; st->impx[s] = 0; st->impy[s] = 0;
+        const int ln = table_row_and_closest(c, s);  // RoadObject.__init__ objects.py:45-50
+        st->lane[s] = ln; st->tlane[s] = ln;         // controller.py:46
+        st->tspeed[s] = speed;                       // controller.py:47
+        st->timer[s] = py_mod1((px + py) * kPi);     // behavior.py:64
+        st->delta[s] = d.delta;                      // behavior.py:66-69
+        st->flags[s] = 0; st->sidx[s] = 0; st->ytimer[s] = 0;
+        const int nr = sc->spawn_route_len[entry * 4 + exit_];
+        uint32_t rr = (uint32_t)c.lanes[ln].road, rl = (uint32_t)c.lanes[ln].lane_id;
+        for (int k = 0; k < nr; ++k) {
+            rr |= (uint32_t)(sc->spawn_route_road[(entry * 4 + exit_) * TTRL_ROUTE_CAP + k] & 0xFF) << (8 * (k + 1));
+            rl |= 0xFFu << (8 * (k + 1));
+        }
+        st->rlen[s] = 1 + nr; st->rroad[s] = rr; st->rlanew[s] = rl;
+        st->n = s + 1;
+        st->flag0 = 1;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// global <-> shared state movement (coalesced: thread t moves slot t of every field)
+// ------------------------------------------------------------------------------------------------
+struct GlobalState {
+    double* vd;   // [ND][E][V]
+    int32_t* vi;  // [NI][E][V]
+    int32_t* ei;  // [NEI][E]
+    double* ed;   // [NED][E]
+    int E;
+    int V;        // slots per env in this buffer
+};
+template <class C, class Exec>
+TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
+    auto* st = c.st;
+    const int V = g.V;
+    ex.par([&](int t) {
+        if (t == 0) {
+            st->n = g.ei[TTRL_EI_NVEH * g.E + e]; st->steps = g.ei[TTRL_EI_STEPS * g.E + e];
+            st->road_steps = g.ei[TTRL_EI_ROAD_STEPS * g.E + e]; st->ego = g.ei[TTRL_EI_EGO * g.E + e];
+            st->episode = g.ei[TTRL_EI_EPISODE * g.E + e]; st->done = g.ei[TTRL_EI_DONE * g.E + e];
+            st->time = g.ed[TTRL_ED_TIME * g.E + e]; st->ret = g.ed[TTRL_ED_RETURN * g.E + e];
+        }
+        if (t < V) {
+            const size_t o = (size_t)e * V + t, fs = (size_t)g.E * V;
+            st->x[t] = g.vd[TTRL_D_X * fs + o]; st->y[t] = g.vd[TTRL_D_Y * fs + o];
+            const double hd = g.vd[TTRL_D_HEADING * fs + o];
+            st->h[t] = hd; st->ch[t] = cos(hd); st->sh[t] = sin(hd);
+            st->v[t] = g.vd[TTRL_D_SPEED * fs + o];
+            st->steer[t] = g.vd[TTRL_D_STEERING * fs + o]; st->acc[t] = g.vd[TTRL_D_ACCEL * fs + o];
+            st->tspeed[t] = g.vd[TTRL_D_TARGET_SPEED * fs + o]; st->timer[t] = g.vd[TTRL_D_TIMER * fs + o];
+            st->delta[t] = g.vd[TTRL_D_DELTA * fs + o];
+            st->impx[t] = g.vd[TTRL_D_IMPACT_X * fs + o]; st->impy[t] = g.vd[TTRL_D_IMPACT_Y * fs + o];
+            st->lane[t] = g.vi[TTRL_I_LANE * fs + o]; st->tlane[t] = g.vi[TTRL_I_TARGET_LANE * fs + o];
+            st->flags[t] = g.vi[TTRL_I_FLAGS * fs + o]; st->sidx[t] = g.vi[TTRL_I_SPEED_INDEX * fs + o];
+            st->rlen[t] = g.vi[TTRL_I_ROUTE_LEN * fs + o];
+            st->rroad[t] = (uint32_t)g.vi[TTRL_I_ROUTE_ROAD * fs + o]; st->rlanew[t] = (uint32_t)g.vi[TTRL_I_ROUTE_LANE * fs + o];
+            st->ytimer[t] = g.vi[TTRL_I_YIELD_TIMER * fs + o];
+        } else {
+            st->x[t] = st->y[t] = st->h[t] = st->v[t] = st->sh[t] = st->steer[t] = st->acc[t] = 0; st->ch[t] = 1;
+            st->tspeed[t] = st->timer[t] = st->delta[t] = st->impx[t] = st->impy[t] = 0;
+            st->lane[t] = st->tlane[t] = st->flags[t] = st->sidx[t] = st->rlen[t] = st->ytimer[t] = 0;
+            st->rroad[t] = st->rlanew[t] = 0;
+        }
+        st->mark[t] = 0; st->tl_old[t] = 0;
+    });
+    // the table is a pure function of positions: rebuild it instead of storing it
+    ex.par([&](int t) { if (t < st->n) (void)table_row_and_closest(c, t); });
+}
+template <class C, class Exec>
+TT_HD void store_env(C& c, Exec& ex, const GlobalState& g, int e) {
+    auto* st = c.st;
+    const int V = g.V;
+    ex.par([&](int t) {
+        if (t == 0) {
+            g.ei[TTRL_EI_NVEH * g.E + e] = st->n; g.ei[TTRL_EI_STEPS * g.E + e] = st->steps;
+            g.ei[TTRL_EI_ROAD_STEPS * g.E + e] = st->road_steps; g.ei[TTRL_EI_EGO * g.E + e] = st->ego;
+            g.ei[TTRL_EI_EPISODE * g.E + e] = st->episode; g.ei[TTRL_EI_DONE * g.E + e] = st->done;
+            g.ed[TTRL_ED_TIME * g.E + e] = st->time; g.ed[TTRL_ED_RETURN * g.E + e] = st->ret;
+        }
+        if (t < V) {
+            const size_t o = (size_t)e * V + t, fs = (size_t)g.E * V;
+            const bool live = t < st->n;
+            const int rlen = live ? st->rlen[t] : 0;
+            // canonical form: dead slots zero, unused route bytes zero (keeps get_state comparable bit for bit)
+            const uint32_t keep = rlen >= 4 ? 0xFFFFFFFFu : (rlen <= 0 ? 0u : ((1u << (8 * rlen)) - 1u));
+            g.vd[TTRL_D_X * fs + o] = live ? st->x[t] : 0; g.vd[TTRL_D_Y * fs + o] = live ? st->y[t] : 0;
+            g.vd[TTRL_D_HEADING * fs + o] = live ? st->h[t] : 0; g.vd[TTRL_D_SPEED * fs + o] = live ? st->v[t] : 0;
+            g.vd[TTRL_D_STEERING * fs + o] = live ? st->steer[t] : 0; g.vd[TTRL_D_ACCEL * fs + o] = live ? st->acc[t] : 0;
+            g.vd[TTRL_D_TARGET_SPEED * fs + o] = live ? st->tspeed[t] : 0; g.vd[TTRL_D_TIMER * fs + o] = live ? st->timer[t] : 0;
+            g.vd[TTRL_D_DELTA * fs + o] = live ? st->delta[t] : 0;
+            g.vd[TTRL_D_IMPACT_X * fs + o] = live ? st->impx[t] : 0; g.vd[TTRL_D_IMPACT_Y * fs + o] = live ? st->impy[t] : 0;
+            g.vi[TTRL_I_LANE * fs + o] = live ? st->lane[t] : 0; g.vi[TTRL_I_TARGET_LANE * fs + o] = live ? st->tlane[t] : 0;
+            g.vi[TTRL_I_FLAGS * fs + o] = live ? st->flags[t] : 0; g.vi[TTRL_I_SPEED_INDEX * fs + o] = live ? st->sidx[t] : 0;
+            g.vi[TTRL_I_ROUTE_LEN * fs + o] = rlen;
+            g.vi[TTRL_I_ROUTE_ROAD * fs + o] = (int32_t)(live ? st->rroad[t] & keep : 0u);
+            g.vi[TTRL_I_ROUTE_LANE * fs + o] = (int32_t)(live ? st->rlanew[t] & keep : 0u);
+            g.vi[TTRL_I_YIELD_TIMER * fs + o] = live ? st->ytimer[t] : 0;
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// counter-based RNG for device-side spawn draws (Philox-4x32-10), keyed by (seed, global env, step, draw)
+// ------------------------------------------------------------------------------------------------
+TT_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+TT_HD void philox4x32(uint32_t ctr[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+        const uint32_t n0 = hi1 ^ ctr[1] ^ k0, n1 = lo1, n2 = hi0 ^ ctr[3] ^ k1, n3 = lo0;
+        ctr[0] = n0; ctr[1] = n1; ctr[2] = n2; ctr[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+TT_HD double u01(uint32_t hi, uint32_t lo) {  // 53-bit uniform in [0,1)
+    const uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
+    return (double)x * (1.0 / 9007199254740992.0);
+}
+TT_HD void device_spawn_draw(uint64_t seed, int64_t global_env, uint64_t counter, ttrl_spawn_draw& d) {
+    uint32_t a[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), (uint32_t)counter, 0u};
+    uint32_t b[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), (uint32_t)counter, 1u};
+    uint32_t e[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), (uint32_t)counter, 2u};
+    philox4x32(a, (uint32_t)seed, (uint32_t)(seed >> 32));
+    philox4x32(b, (uint32_t)seed, (uint32_t)(seed >> 32));
+    philox4x32(e, (uint32_t)seed, (uint32_t)(seed >> 32));
+    d.u_spawn = u01(a[0], a[1]);
+    const double ue = u01(a[2], a[3]);
+    d.entry = (int)(ue * 4.0) & 3;                       // choice(range(4), 2, replace=False): ordered pair,
+    d.exit = (d.entry + 1 + ((int)(u01(e[0], e[1]) * 3.0) % 3)) % 4;  // uniform over the 12 possibilities
+    const double u1 = 1.0 - u01(b[0], b[1]), u2 = u01(b[2], b[3]);    // Box-Muller
+    const double rad = sqrt(-2.0 * log(u1));
+    d.n_pos = rad * cos(2 * kPi * u2);
+    d.n_speed = rad * sin(2 * kPi * u2);
+    d.delta = 3.5 + u01(e[2], e[3]) * (4.5 - 3.5);       // behavior.py:66-69
+}
+
+// ------------------------------------------------------------------------------------------------
+// one env.step(): AbstractEnv.step abstract.py:224-250 + IntersectionEnv.step intersection_env.py:135-139
+// ------------------------------------------------------------------------------------------------
+struct StepIO {
+    const int32_t* actions;        // [E] or null
+    float* obs;                    // [E][obs_size] or null
+    float* reward;                 // [E] or null
+    uint8_t* terminated;           // [E] or null
+    uint8_t* truncated;            // [E] or null
+    const ttrl_spawn_draw* draws;  // [E] injected spawn draws or null (device Philox)
+    int32_t* spawn_accepted;       // [E] or null
+    const int32_t* inv_perm;       // [E][obs_vehicles-1] or null
+    double* stats;                 // [kStatFields][E] per-env accumulators
+    GlobalState pool;              // reset pool (pool.E == 0: none)
+    int autoreset;
+    uint64_t seed;
+    int64_t first_global_env;
+    int obs_size;
+};
+
+template <class C, class Exec>
+TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int e) {
+    auto* st = c.st;
+    const SceneDev* sc = c.sc;
+    const ttrl_config& cfg = sc->cfg;
+    load_env(c, ex, g, e);
+    const int action = io.actions ? io.actions[e] : -1;
+    ex.par([&](int t) { if (t == 0) st->time += 1 / cfg.policy_frequency; });
+    double veh_steps = 0;
+    for (int f = 0; f < sc->F; ++f) {
+        env_substep(c, ex, action);
+        veh_steps += st->n;
+    }
+    float* obs = io.obs ? io.obs + (size_t)e * io.obs_size : nullptr;
+    const int32_t* perm = io.inv_perm ? io.inv_perm + (size_t)e * (cfg.obs_vehicles - 1) : nullptr;
+    if (obs) observe(c, ex, obs, perm);
+    // reward / flags / episode accounting by thread 0
+    ex.par([&](int t) {
+        if (t != 0) return;
+        const int ego = st->ego;
+        const double r = agent_reward(c, ego);
+        const bool term = is_terminated(c), trunc = st->time >= cfg.duration;
+        if (io.reward) io.reward[e] = (float)r;
+        if (io.terminated) io.terminated[e] = term ? 1 : 0;
+        if (io.truncated) io.truncated[e] = trunc ? 1 : 0;
+        st->ret += r;
+        st->done = (term || trunc) ? 1 : 0;
+        if (io.stats) {
+            double* s = io.stats + e;
+            const int E = g.E;
+            s[5 * E] += st->v[ego];
+            s[6 * E] += veh_steps;
+            s[7 * E] += 1;
+            if (st->done) {
+                s[0 * E] += 1;
+                s[1 * E] += st->ret;
+                s[2 * E] += st->time * cfg.policy_frequency;
+                s[3 * E] += (st->flags[ego] & TTRL_FL_CRASHED) ? 1 : 0;
+                s[4 * E] += (cfg.reward_type == TTRL_REWARD_INTERSECTION && has_arrived(c, ego)) ? 1 : 0;
+            }
+        }
+    });
+    if (cfg.spawn_enabled) {
+        clear_vehicles(c, ex);
+        ttrl_spawn_draw d;
+        bool have = false;
+        if (io.draws) { d = io.draws[e]; have = true; }
+        else if (io.seed != 0) { device_spawn_draw(io.seed, io.first_global_env + e, (uint64_t)st->steps + ((uint64_t)st->episode << 32), d); have = true; }
+        if (have) {
+            SpawnParams sp{0.0, 1.0, 1.0, cfg.spawn_probability, 0};
+            spawn_vehicle(c, ex, d, sp);
+            if (io.spawn_accepted) ex.par([&](int t) { if (t == 0) io.spawn_accepted[e] = st->flag0; });
+        } else if (io.spawn_accepted) {
+            ex.par([&](int t) { if (t == 0) io.spawn_accepted[e] = 0; });
+        }
+    }
+    if (st->done && io.autoreset && io.pool.E > 0) {  // uniform: st->done is in shared memory
+        const int episode = st->episode + 1;
+        const int slot = (int)(((long long)e + (long long)episode * g.E) % io.pool.E);
+        load_env(c, ex, io.pool, slot);
+        ex.par([&](int t) { if (t == 0) { st->episode = episode; st->done = 0; } });
+        if (obs) observe(c, ex, obs, perm);
+    }
+    store_env(c, ex, g, e);
+}
+
+}  // namespace ttrl

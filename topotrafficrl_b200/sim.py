@@ -1,0 +1,123 @@
+"""Thin object wrapper over the C ABI (``include/ttrl_b200.h``): one :class:`Sim` = one ``ttrl_sim``.
+
+numpy in / numpy out for state resync and the host-buffer step; raw device pointers (e.g. from torch tensors)
+for the resident step.  No simulation logic lives here."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import abi
+from ._lib import check, lib
+from .road import NetworkTable
+from .state import SimState
+
+
+def _p(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Sim:
+    def __init__(self, cfg: abi.Config, table: NetworkTable, num_envs: int, vcap: int, device: int = 0,
+                 spawn_routes=None) -> None:
+        self._L = lib()
+        self.cfg, self.table = cfg, table
+        self.num_envs, self.vcap, self.device = int(num_envs), int(vcap), int(device)
+        h = C.c_void_p()
+        check(self._L.ttrl_sim_create(C.byref(cfg), C.cast(table.lanes, C.c_void_p), C.cast(table.roads, C.c_void_p),
+                                      _p(table.node_first), _p(table.node_roads), self.num_envs, self.vcap, self.device,
+                                      C.byref(h)))
+        self._h = h
+        self.obs_size = self._L.ttrl_sim_obs_size(self._h)
+        if spawn_routes is not None:
+            sl, rl, rr = (np.ascontiguousarray(a, dtype=np.int32) for a in spawn_routes)
+            check(self._L.ttrl_sim_set_spawn_routes(self._h, _p(sl), _p(rl), _p(rr)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.ttrl_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state ---------------------------------------------------------------------------------------
+    def set_state(self, st: SimState) -> None:
+        st = st.contiguous()
+        assert st.num_envs == self.num_envs and st.vcap == self.vcap, (st.num_envs, st.vcap, self.num_envs, self.vcap)
+        check(self._L.ttrl_sim_set_state(self._h, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d)))
+
+    def get_state(self) -> SimState:
+        st = SimState.zeros(self.num_envs, self.vcap)
+        check(self._L.ttrl_sim_get_state(self._h, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d)))
+        return st
+
+    def set_reset_pool(self, pool: SimState) -> None:
+        pool = pool.contiguous()
+        assert pool.vcap == self.vcap
+        check(self._L.ttrl_sim_set_reset_pool(self._h, pool.num_envs, _p(pool.veh_d), _p(pool.veh_i), _p(pool.env_i), _p(pool.env_d)))
+
+    def set_autoreset(self, on: bool) -> None:
+        check(self._L.ttrl_sim_set_autoreset(self._h, int(on)))
+
+    def seed(self, seed: int, first_global_env: int = 0) -> None:
+        check(self._L.ttrl_sim_seed(self._h, int(seed), int(first_global_env)))
+
+    # ---- parity hooks --------------------------------------------------------------------------------
+    def inject_spawn(self, draws) -> None:
+        check(self._L.ttrl_sim_inject_spawn(self._h, C.cast(draws, C.c_void_p) if draws is not None else None))
+
+    def inject_shuffle(self, inv_perm: Optional[np.ndarray]) -> None:
+        a = None if inv_perm is None else np.ascontiguousarray(inv_perm, dtype=np.int32)
+        check(self._L.ttrl_sim_inject_shuffle(self._h, _p(a)))
+
+    def spawn_accepted(self) -> np.ndarray:
+        out = np.zeros(self.num_envs, np.int32)
+        check(self._L.ttrl_sim_spawn_accepted(self._h, _p(out)))
+        return out
+
+    def spawn(self, draws, longitudinal: float, position_deviation: float = 1.0, speed_deviation: float = 1.0,
+              spawn_probability: float = 0.6, go_straight: bool = False) -> np.ndarray:
+        out = np.zeros(self.num_envs, np.int32)
+        check(self._L.ttrl_sim_spawn(self._h, C.cast(draws, C.c_void_p), longitudinal, position_deviation, speed_deviation,
+                                     spawn_probability, int(go_straight), _p(out)))
+        return out
+
+    # ---- stepping ------------------------------------------------------------------------------------
+    def substep_ptr(self, actions_ptr: Optional[int], stream: int = 0) -> None:
+        check(self._L.ttrl_sim_substep(self._h, actions_ptr, stream))
+
+    def step_ptr(self, actions_ptr, obs_ptr, reward_ptr, term_ptr, trunc_ptr, stream: int = 0) -> None:
+        check(self._L.ttrl_sim_step(self._h, actions_ptr, obs_ptr, reward_ptr, term_ptr, trunc_ptr, stream))
+
+    def observe_ptr(self, obs_ptr, stream: int = 0) -> None:
+        check(self._L.ttrl_sim_observe(self._h, obs_ptr, stream))
+
+    def step_host(self, actions: Optional[np.ndarray]):
+        """One env.step() for all envs from HOST buffers (H2D, kernel, D2H inside the call)."""
+        E = self.num_envs
+        a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32)
+        obs = np.empty((E, self.obs_size), np.float32)
+        reward = np.empty(E, np.float32)
+        term = np.empty(E, np.uint8)
+        trunc = np.empty(E, np.uint8)
+        check(self._L.ttrl_sim_step_host(self._h, _p(a), _p(obs), _p(reward), _p(term), _p(trunc)))
+        return obs, reward, term, trunc
+
+    def stats(self, reset: bool = False) -> abi.EpisodeStats:
+        out = abi.EpisodeStats()
+        check(self._L.ttrl_sim_read_stats(self._h, C.byref(out), int(reset)))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.ttrl_sim_launch_count(self._h))

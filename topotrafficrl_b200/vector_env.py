@@ -1,0 +1,148 @@
+"""``TTRLVectorEnv``: E env instances advanced in lockstep on one B200 (the vector form of the reference's
+gymnasium ``AbstractEnv`` API, abstract.py:188-250).  Observations, rewards and flags stay on the device as
+torch tensors (PyTorch is used for device memory and streams only); ``step_host`` is the numpy/host-buffer form.
+
+There is no CPU fallback: constructing the env without the CUDA library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import abi, scenes
+from ._gym import np_random as gym_np_random
+from ._gym import spaces
+from .reset import reset_intersection
+from .sim import Sim
+from .state import SimState
+
+
+class _SimResetBackend:
+    def __init__(self, sim: Sim):
+        self.sim, self.num_envs = sim, sim.num_envs
+
+    def spawn(self, draws, longitudinal, position_deviation, speed_deviation, spawn_probability, go_straight):
+        return self.sim.spawn(draws, longitudinal, position_deviation, speed_deviation, spawn_probability, go_straight)
+
+    def substep_none(self):
+        self.sim.substep_ptr(None, 0)
+
+    def get_state(self):
+        return self.sim.get_state()
+
+    def set_state(self, st):
+        self.sim.set_state(st)
+
+
+class TTRLVectorEnv:
+    """
+    :param num_envs: number of env instances on this device
+    :param scene: ``"highway"`` (synthetic multi-lane highway, BASELINE configs 2/3) or ``"intersection"``
+                  (``IntersectionEnv``, configs 1/4)
+    :param config: reference-style config dict, shallow-merged over the scene default (abstract.py:111-113)
+    :param device: CUDA device index or ``"cuda:N"``
+    :param seed: base seed; env e uses the stream keyed by ``first_env + e`` so shards reproduce a larger run
+    :param first_env: global index of this shard's first env (multi-GPU sharding)
+    """
+
+    def __init__(self, num_envs: int, scene: str = "highway", config: Optional[dict] = None, device=0, seed: int = 0,
+                 first_env: int = 0, vcap: Optional[int] = None, autoreset: bool = True) -> None:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("TTRLVectorEnv needs a CUDA device (there is no CPU fallback)")
+        self.torch = torch
+        self.num_envs = int(num_envs)
+        self.scene = scene
+        self.device_index = int(str(device).split(":")[-1]) if not isinstance(device, int) else device
+        self.device = torch.device("cuda", self.device_index)
+        self.seed_value, self.first_env = int(seed), int(first_env)
+        if scene == "highway":
+            self.config = scenes.merged_config(scenes.HIGHWAY_CONFIG, config)
+            self.net = scenes.make_highway_network(int(self.config["lanes_count"]), float(self.config["road_length"]),
+                                                   float(self.config["speed_limit"]))
+            self.table = self.net.to_table()
+            self.cfg = scenes.build_config(self.table, self.config, "highway", ego_lanes_count=int(self.config["lanes_count"]))
+            self.vcap = int(vcap or self.config["vehicles_count"])
+            routes = None
+        elif scene == "intersection":
+            self.config = scenes.merged_config(scenes.INTERSECTION_CONFIG, config)
+            self.net = scenes.make_intersection_network()
+            self.table = self.net.to_table(scenes.intersection_exit_predicate)
+            self.cfg = scenes.build_config(self.table, self.config, "intersection")
+            self.vcap = int(vcap or 32)
+            routes = scenes.intersection_spawn_routes(self.net, self.table)
+        else:
+            raise ValueError(f"unknown scene {scene!r}")
+        self.sim = Sim(self.cfg, self.table, self.num_envs, self.vcap, self.device_index, routes)
+        self.sim.set_autoreset(autoreset)
+        self.autoreset = autoreset
+        self.obs_shape = ((self.cfg.n_features, self.cfg.grid_w, self.cfg.grid_h) if self.cfg.obs_type == abi.OBS_GRID
+                          else (self.cfg.obs_vehicles, self.cfg.n_features))
+        n_actions = 5 if self.cfg.action_mode == abi.ACT_ALL else 3
+        self.single_observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=self.obs_shape, dtype=np.float32)
+        self.single_action_space = spaces.Discrete(n_actions)
+        E = self.num_envs
+        self._obs = torch.zeros((E,) + self.obs_shape, dtype=torch.float32, device=self.device)
+        self._reward = torch.zeros(E, dtype=torch.float32, device=self.device)
+        self._term = torch.zeros(E, dtype=torch.uint8, device=self.device)
+        self._trunc = torch.zeros(E, dtype=torch.uint8, device=self.device)
+        self._shuffle_rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence([self.seed_value, self.first_env, 7])))
+
+    # ------------------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return int(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, seed: Optional[int] = None):
+        if seed is not None:
+            self.seed_value = int(seed)
+        if self.scene == "highway":
+            st = scenes.make_highway_state(self.num_envs, self.config, seed=self.seed_value, first_env=self.first_env, vcap=self.vcap)
+            self.sim.set_state(st)
+        else:
+            rngs = [gym_np_random(self.seed_value + self.first_env + e)[0] for e in range(self.num_envs)]
+            st = reset_intersection(_SimResetBackend(self.sim), rngs, self.net, self.table, self.config, self.cfg)
+            self.sim.seed((self.seed_value << 1) | 1, self.first_env)  # device-side Philox spawn draws
+        self.sim.set_reset_pool(st)
+        self._maybe_shuffle()
+        self.sim.observe_ptr(self._obs.data_ptr(), self._stream())
+        return self._obs, {}
+
+    def _maybe_shuffle(self) -> None:
+        if self.cfg.obs_type == abi.OBS_KINEMATICS and self.cfg.order == abi.ORDER_SHUFFLED:
+            m = self.cfg.obs_vehicles - 1
+            perm = np.argsort(self._shuffle_rng.random((self.num_envs, m)), axis=1)
+            inv = np.empty_like(perm)
+            np.put_along_axis(inv, perm, np.broadcast_to(np.arange(m), perm.shape), axis=1)
+            self.sim.inject_shuffle(inv.astype(np.int32))
+
+    def step(self, actions):
+        """actions: int tensor [E] on this device (int32 preferred; int64 is converted)."""
+        torch = self.torch
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions), device=self.device)
+        if actions.dtype != torch.int32:
+            actions = actions.to(torch.int32)
+        actions = actions.contiguous()
+        self._maybe_shuffle()
+        self.sim.step_ptr(actions.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr(), self._term.data_ptr(),
+                          self._trunc.data_ptr(), self._stream())
+        return self._obs, self._reward, self._term.bool(), self._trunc.bool(), {}
+
+    def step_host(self, actions: np.ndarray):
+        obs, reward, term, trunc = self.sim.step_host(actions)
+        return obs.reshape((self.num_envs,) + self.obs_shape), reward, term.astype(bool), trunc.astype(bool), {}
+
+    def get_state(self) -> SimState:
+        return self.sim.get_state()
+
+    def set_state(self, st: SimState) -> None:
+        self.sim.set_state(st)
+
+    def stats(self, reset: bool = False) -> dict:
+        s = self.sim.stats(reset)
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def close(self) -> None:
+        self.sim.close()
