@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched env step on B200 (driver contract: see README / DESIGN.md section 7).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload highway50|...]
+
+One "step" = one env.step() of EVERY env of the workload (15 simulation sub-steps + observation + reward +
+termination [+ clear/spawn] [+ autoreset]).  At N=1 the workload is BASELINE.json configs[1]: 4096 highway envs x
+50 vehicles, Kinematics observation, random actions.  N>1 (torchrun, one rank per GPU): every rank owns its own
+4096 envs (global env ids rank*E .. rank*E+E-1), no collective on the step path ("weak" scaling); only the
+episode statistics are all-reduced (NCCL) after the timed region.
+
+Numbers on the JSON line
+  value      vehicle-steps/s, device-resident: actions already in HBM, obs/reward/flags written to HBM,
+             CUDA events around each step (L2 flushed between steps), max over ranks.
+  e2e        the same metric through the host-buffer C-ABI call (ttrl_sim_step_host): actions from host memory,
+             obs/reward/flags back to host memory every step, wall clock around the call.
+  roofline   k_step against the measured HBM copy bandwidth (MEASURED_PEAKS.json), algorithmic bytes per
+             env-step from SURVEY.md section 8d / DESIGN.md section 6.
+  cpu_baseline  the CPU oracle (C restatement of the reference algorithm, oracle/) on the host cores of this
+             box, bounded sample of the same workload.  Rank 0, N=1 only.
+
+`--impl reference` times the CPU oracle port alone (the Python reference itself cannot travel to the GPU box and
+runs at ~1.8e3 vehicle-steps/s/core; the C port is the faster, fairer CPU arm).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene, num_envs per GPU, vehicles, scene overrides, algorithmic bytes per env-step)
+    "highway50": dict(scene="highway", E=4096, n=50, over={"vehicles_count": 50, "vehicles_density": 2.0},
+                      label="configs[1]: highway 4096 envs x 50 vehicles, Kinematics obs, random actions",
+                      bytes_per_env_step=50 * 128 + 4 + 420 + 8, n_actions=5),
+    "dense200": dict(scene="highway", E=1024, n=200,
+                     over={"vehicles_count": 200, "vehicles_density": 4.0,
+                           "observation": {"type": "OccupancyGrid", "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+                                           "grid_size": [[-32, 32], [-32, 32]], "grid_step": [2, 2], "absolute": False}},
+                     label="configs[2]: dense highway 1024 envs x 200 vehicles, OccupancyGrid 7x32x32 obs",
+                     bytes_per_env_step=200 * 128 + 4 + 28672 + 8, n_actions=5),
+    "intersection": dict(scene="intersection", E=8192, n=32, over=None,
+                         label="configs[3]: intersection 8192 envs, regulated road, spawn, Kinematics obs",
+                         bytes_per_env_step=24 * 128 + 4 + 420 + 8, n_actions=3),
+}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(w):
+    from topotrafficrl_b200 import scenes
+    if w["scene"] == "highway":
+        cfgd = scenes.merged_config(scenes.HIGHWAY_CONFIG, w["over"])
+        net = scenes.make_highway_network(int(cfgd["lanes_count"]), float(cfgd["road_length"]), float(cfgd["speed_limit"]))
+        table = net.to_table()
+        cfg = scenes.build_config(table, cfgd, "highway", ego_lanes_count=int(cfgd["lanes_count"]))
+        return cfgd, net, table, cfg, None
+    cfgd = scenes.merged_config(scenes.INTERSECTION_CONFIG, w["over"])
+    net = scenes.make_intersection_network()
+    table = net.to_table(scenes.intersection_exit_predicate)
+    cfg = scenes.build_config(table, cfgd, "intersection")
+    return cfgd, net, table, cfg, scenes.intersection_spawn_routes(net, table)
+
+
+def cpu_oracle_throughput(w, seconds: float, seed: int = 0):
+    """CPU arm: the oracle port on all host cores, bounded sample of the workload.  Returns (veh-steps/s, env-steps/s, cores, sample)."""
+    from oracle import oracle as O
+    from topotrafficrl_b200 import scenes
+    if w["scene"] != "highway":
+        raise SystemExit("the CPU arm is implemented for the highway workloads")
+    cfgd, net, table, cfg, routes = build_scene(w)
+    cores = os.cpu_count() or 1
+    E = max(cores * 8, 64)
+    st = scenes.make_highway_state(E, cfgd, seed=seed)
+    orc = O.Oracle(cfg, table, threads=cores)
+    orc.set_reset_pool(st.copy())
+    orc.set_autoreset(True)
+    rng = np.random.default_rng(seed)
+    stats = np.zeros(8)
+    orc.step(st, rng.integers(0, w["n_actions"], size=E).astype(np.int32), stats=stats)  # warm-up
+    stats[:] = 0
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        orc.step(st, rng.integers(0, w["n_actions"], size=E).astype(np.int32), stats=stats)
+        steps += 1
+        if time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    return stats[6] / dt, stats[7] / dt, cores, f"{E} envs x {w['n']} vehicles x {steps} env-steps ({dt:.1f} s) of the same scene generator"
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step_seconds = 2.0
+    vals, evals = [], []
+    cores = sample = None
+    for k in range(args.warmup + args.steps):
+        v, ev, cores, sample = cpu_oracle_throughput(w, per_step_seconds, seed=k)
+        if k >= args.warmup:
+            vals.append(v); evals.append(ev)
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "vehicle_steps_per_sec", "value": value, "unit": "vehicle-steps/s",
+            "env_steps_per_sec": float(np.mean(evals)), "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_step_seconds * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": w["label"], "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": value, "unit": "vehicle-steps/s", "cores": cores, "kind": "port",
+                             "sample": "each step: " + sample},
+            "e2e": {"value": value, "unit": "vehicle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    from topotrafficrl_b200 import scenes
+    from topotrafficrl_b200.sim import Sim
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the simulator has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfgd, net, table, cfg, routes = build_scene(w)
+    E = args.envs or w["E"]
+    K, W = args.steps, args.warmup
+    first_env = rank * E
+    if w["scene"] == "highway":
+        st0 = scenes.make_highway_state(E, cfgd, seed=0, first_env=first_env, vcap=w["n"])
+        sim = Sim(cfg, table, E, w["n"], local_rank)
+        sim.set_state(st0)
+        sim.set_reset_pool(st0)
+        sim.set_autoreset(True)
+    else:
+        from topotrafficrl_b200.vector_env import TTRLVectorEnv
+        venv = TTRLVectorEnv(E, scene="intersection", device=local_rank, seed=0, first_env=first_env, vcap=w["n"])
+        venv.reset()
+        sim = venv.sim
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    actions = torch.randint(0, w["n_actions"], (W + K, E), dtype=torch.int32, device=dev, generator=gen)
+    obs = torch.zeros(E * sim.obs_size, dtype=torch.float32, device=dev)
+    rew = torch.zeros(E, dtype=torch.float32, device=dev)
+    term = torch.zeros(E, dtype=torch.uint8, device=dev)
+    trunc = torch.zeros(E, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = int(torch.cuda.current_stream(dev).cuda_stream)
+
+    def step(k):
+        sim.step_ptr(actions[k].data_ptr(), obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -------------------------------------------------------------------------
+    for k in range(W):
+        step(k)
+    sim.stats(reset=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = sim.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        flush.fill_(k & 0xFF)  # L2 flush between timed iterations (outside the event pair)
+        ev[k][0].record()
+        step(W + k)
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = sim.launch_count - launches0
+    clocks = sampler.stop()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(ms))
+    s = sim.stats(reset=True)  # one reduction kernel, outside the timed region
+    veh_steps, env_steps = s.vehicle_steps, s.env_steps
+    red = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([veh_steps, env_steps, s.episodes, s.crashes, s.total_return], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)  # episode statistics: the only collective of the workload
+    total_ms_max = float(red.item())
+    veh_all, env_all, episodes, crashes, ret = (float(x) for x in tot.tolist())
+
+    # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------------
+    acts_host = actions.cpu().numpy()
+    for k in range(min(W, 3)):
+        sim.step_host(acts_host[k])
+    sim.stats(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        o, r, t, u = sim.step_host(acts_host[W + k])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    s2 = sim.stats(reset=True)
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_v = torch.tensor([s2.vehicle_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_v, op=dist.ReduceOp.SUM)
+    h2d = E * 4
+    d2h = E * (sim.obs_size * 4 + 4 + 2)
+
+    if rank == 0:
+        hbm_peak, peak_kind = _peaks()
+        kernel_ms = statistics.mean(ms)
+        alg_bytes = w["bytes_per_env_step"] * E
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": "vehicle_steps_per_sec", "value": veh_all / (total_ms_max * 1e-3), "unit": "vehicle-steps/s",
+            "env_steps_per_sec": env_all / (total_ms_max * 1e-3),
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["label"], "envs_per_gpu": E, "vehicles_per_env": w["n"], "sub_steps_per_step": 15,
+                       "autoreset": True, "l2": "flushed between timed steps (256 MB fill)",
+                       "target": "1e8 vehicle-steps/s per B200 (BASELINE.json north_star)"},
+            "e2e": {"value": float(e2e_v.item()) / float(e2e_t.item()), "unit": "vehicle-steps/s",
+                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                    "ms_per_step": float(e2e_t.item()) / K * 1e3},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "kernel": "k_step", "kernel_ms": kernel_ms, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "clocks": clocks,
+            "episode_stats": {"episodes": episodes, "crashes": crashes, "mean_return": ret / episodes if episodes else None},
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline and w["scene"] == "highway":
+            v, evs, cores, sample = cpu_oracle_throughput(w, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": "vehicle-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                                    "env_steps_per_sec": evs}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="highway50", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()
