@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Map an ncu SASS source-page CSV onto CUDA source lines using nvdisasm line info.
+
+usage: ncu_lines.py <report.ncu-rep> <lib.so> <mangled-substring e.g. k_stepILi64> [top_n]
+Prints, per source line (file:line incl. the inlining function), the share of warp-stall samples, of executed
+warp instructions, and the average active threads.  (ncu's own --print-source cuda CSV carries no metrics.)
+"""
+import collections, csv, os, re, subprocess, sys, tempfile
+
+rep, so, kern = sys.argv[1:4]
+topn = int(sys.argv[4]) if len(sys.argv) > 4 else 50
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+# 1. per-function, per-instruction-index source line from nvdisasm
+line_of = {}  # (func, idx) -> "file:line"
+for cub in os.listdir(tmp):
+    txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+    func, cur, idx = None, "?", 0
+    for ln in txt.splitlines():
+        m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
+        if m:
+            func, idx, cur = m.group(1), 0, "?"
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', ln)
+        if m:
+            cur = f"{os.path.basename(m.group(1))}:{m.group(2)}"
+            continue
+        if func and re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", ln):
+            line_of[(func, idx)] = cur
+            idx += 1
+# 2. ncu sass page
+csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(csvtxt.splitlines()))
+agg = collections.defaultdict(lambda: [0, 0, 0])
+hdr = None
+func = None
+funcs = sorted({f for f, _ in line_of})
+k = 0
+done_first = False
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        if done_first:
+            break  # first profiled launch only
+        name = r[1]
+        func = None
+        if re.sub(r"I?Li\d+.*", "", kern) in name:
+            cands = [f for f in funcs if kern in f]
+            func = cands[0] if cands else None
+        k = 0
+        continue
+    if r and r[0] == "Address":
+        hdr = r
+        continue
+    if func is None or hdr is None or len(r) < len(hdr) - 2:
+        continue
+    done_first = True
+    i_s, i_i, i_t = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+    a = agg[line_of.get((func, k), "?")]
+    a[0] += int(r[i_s] or 0); a[1] += int(r[i_i] or 0); a[2] += int(r[i_t] or 0)
+    k += 1
+ts = sum(a[0] for a in agg.values()) or 1
+ti = sum(a[1] for a in agg.values()) or 1
+print(f"kernel {kern}: {k} SASS instructions, {ti} warp-inst executed, {ts} samples")
+src_cache = {}
+def src(loc):
+    f, _, n = loc.partition(":")
+    for d in ("topotrafficrl_b200/csrc", "include"):
+        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", d, f)
+        if os.path.exists(p):
+            if p not in src_cache:
+                src_cache[p] = open(p).read().splitlines()
+            try:
+                return src_cache[p][int(n) - 1].strip()[:100]
+            except Exception:
+                return ""
+    return ""
+for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:topn]:
+    print(f"{a[0]/ts*100:5.1f}% smp {a[1]/ti*100:5.1f}% inst thr/inst {a[2]/max(a[1],1):5.1f} | {loc:22s} {src(loc)}")
