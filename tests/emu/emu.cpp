@@ -15,36 +15,59 @@
 using namespace ttrl;
 
 struct HostExec {
-    int T;
+    int T;  // = V: every slot is a "thread"
+    bool first() const { return true; }  // single-thread sections run once
     void sync() {}
     template <class F> void par(F f) { for (int t = 0; t < T; ++t) f(t); }
-    template <class F> bool any(F f) { bool r = false; for (int t = 0; t < T; ++t) r = f(t) || r; return r; }
+    template <class F> void parn(int n, F f) { for (int t = 0; t < n; ++t) f(t); }
+    template <class F> bool any(int n, F f) { bool r = false; for (int t = 0; t < n; ++t) r = f(t) || r; return r; }
     template <class F1, class F2> void par2(F1 f1, F2 f2) {
         std::vector<SlotRegs> r(T);
         std::vector<int> dst(T);
         for (int t = 0; t < T; ++t) f1(t, r[t], dst[t]);
         for (int t = 0; t < T; ++t) f2(t, r[t], dst[t]);
     }
+    // same reduction the device does with shuffles: first axis of minimal absd wins
+    template <class FA, class FP> void sat_pairs(int np, FA fa, FP fp) {
+        for (int q = 0; q < np; ++q) {
+            bool inter = true, will = true;
+            double bd = INFINITY, nx = 0, ny = 0;
+            for (int axis = 0; axis < 8; ++axis) {
+                const AxisRes r = fa(q, axis);
+                if (r.fl & 1) inter = false;
+                if (r.fl & 2) will = false;
+                if (r.absd < bd) { bd = r.absd; nx = r.nx; ny = r.ny; }
+            }
+            fp(q, inter, will, bd, nx, ny);
+        }
+    }
     void atomic_min(int32_t* a, int32_t v) { if (v < *a) *a = v; }
+    void atomic_max(int32_t* a, int32_t v) { if (v > *a) *a = v; }
+    void atomic_or(uint32_t* a, uint32_t v) { *a |= v; }
+    int atomic_add(int32_t* a, int32_t v) { const int o = *a; *a += v; return o; }
 };
 
 template <int V>
 struct HostEnv {
     EnvState<V> st;
-    std::vector<double> S, R, pred;
+    std::vector<d2> SR;
+    std::vector<uint32_t> lmask;
+    std::vector<double> pred;
     std::vector<float> obs_s;
     std::vector<int32_t> cell;
     EnvCtx<V> c;
     HostEnv(const SceneDev* sc, int vcap) {
         memset(&st, 0, sizeof st);
         const ttrl_config& cfg = sc->cfg;
-        S.assign((size_t)V * cfg.n_lanes, 0.0); R.assign((size_t)V * cfg.n_lanes, 0.0);
+        SR.assign((size_t)V * cfg.n_lanes, d2{0.0, 0.0});
+        lmask.assign((size_t)((V + 31) / 32) * cfg.n_lanes, 0u);
         pred.assign((size_t)3 * V * kPred, 0.0);
         obs_s.assign((size_t)(cfg.obs_vehicles * cfg.n_features + 4), 0.f);
         cell.assign((size_t)(cfg.grid_w * cfg.grid_h + 4), 0);
-        c.st = &st; c.sc = sc; c.lanes = sc->lanes; c.S = S.data(); c.R = R.data();
+        c.st = &st; c.sc = sc; c.lanes = sc->lanes; c.SR = SR.data(); c.lmask = lmask.data();
         c.pred = cfg.regulated ? pred.data() : nullptr; c.obs_s = obs_s.data(); c.cell = cell.data();
         c.L = cfg.n_lanes; c.vcap = vcap;
+        c.gap_den = 2 * sqrt(-cfg.comfort_acc_max * cfg.comfort_acc_min);
     }
 };
 

@@ -1,15 +1,26 @@
 // ttrl_core.cuh -- device-side simulation logic of the B200 batched simulator.
 //
-// One CTA advances one env instance; thread t owns vehicle slot t.  The env's whole state lives in shared
-// memory for the F sub-steps of an env-step (one HBM round trip per env-step).  The logic is written as
-// barrier-separated PHASES behind an `Exec` policy (par / any / sync):
-//   * on the device Exec = one CTA:  par(f) -> f(threadIdx.x); __syncthreads();
-//   * in tests/emu a host Exec runs the threads of a phase one after the other, so the very same code is
-//     validated against the CPU oracle in a container without a GPU (it is NOT a product path).
+// One CTA ("team" of T threads, T = 32 for up to 64 vehicle slots) advances one env instance; the env's whole
+// state lives in shared memory for the F sub-steps of an env-step (one HBM round trip per env-step).  The logic
+// is written as barrier-separated PHASES over TASK LISTS behind an `Exec` policy:
+//   * ex.par(f)      f(slot) for every slot 0..V-1           (strided over the team) ; barrier
+//   * ex.parn(n, f)  f(task) for task 0..n-1                 (strided over the team) ; barrier
+//   * ex.any(n, f)   OR-reduction of f(task)
+//   * ex.sat_pairs   8 lanes per candidate pair, one SAT axis each, shuffle-reduced
+//   * on the device Exec = one CTA; in tests/emu a host Exec runs the tasks of a phase one after the other, so
+//     the very same code is validated against the CPU oracle in a container without a GPU (NOT a product path).
 //
-// A per-env table S[v][l], R[v][l] of every vehicle's local coordinates in every lane is rebuilt after each
-// integration (it is the by-product of the closest-lane search, reference road.py:55-71) and serves all
-// neighbour scans, lane distances and controllers of the next sub-step from shared memory.
+// Why task lists (ncu, profiles/r1a_*): the first version ran rare heavy work (MOBIL, SAT) inside per-vehicle
+// threads, so on average 10 of 32 lanes were active and 320 KB of SASS thrashed the instruction cache.  Here the
+// rare work is queued in shared memory and executed with full lanes: MOBIL = neighbour-query tasks + IDM
+// evaluation tasks + one decision task per vehicle; collisions = half-ring candidate scan with an exact
+// squared-distance guard -> pair queue -> 8 axis-lanes per pair.  Heavy math (pow, atan2, asin ...) exists ONCE
+// in the binary behind __noinline__ functions.
+//
+// A per-env table SR[v][l] = (s, r) of every vehicle's local coordinates in every lane is rebuilt after each
+// integration (it is the by-product of the closest-lane search, reference road.py:55-71) together with a
+// per-lane bitmask of the vehicles that are "on" the lane (lane.py:80-102, margin 1); they serve all neighbour
+// scans, lane distances and controllers of the next sub-step from shared memory.
 //
 // Reference citations are relative to /root/reference.
 #pragma once
@@ -33,6 +44,8 @@ constexpr double kVehLength = 5.0;   // kinematics.py:21
 constexpr double kVehWidth = 2.0;    // kinematics.py:23
 constexpr int kStatFields = 8;       // ttrl_episode_stats
 
+struct alignas(16) d2 { double x, y; };  // 16-byte pair (one LDS.128 on the device)
+
 // Read-only scene description, resident in global memory (L1/L2 hot: ~12 KB).
 struct SceneDev {
     ttrl_config cfg;
@@ -48,31 +61,51 @@ struct SceneDev {
     double dt;           // 1/simulation_frequency
 };
 
-// Per-env state in shared memory (struct of arrays over the V slots).
+// Per-env state in shared memory (struct of arrays over the V slots) + task scratch.
 template <int V>
-struct EnvState {
-    double x[V], y[V], h[V], v[V], ch[V], sh[V];
-    double steer[V], acc[V], tspeed[V], timer[V], delta[V], impx[V], impy[V];
+struct alignas(16) EnvState {
+    static constexpr int MB = V < 32 ? V : 32;  // MOBIL batch: vehicles whose lane-change timer fired, per round
+    static constexpr int PQ = 4 * V;            // collision candidate pair queue
+    static constexpr int WQ = V;                // will-intersect pair list
+    d2 pos[V];   // x, y
+    d2 cs[V];    // cos(heading), sin(heading)
+    d2 imp[V];   // pending impact
+    d2 wt[WQ];   // translation of will-intersect pairs
+    double h[V], v[V];
+    double steer[V], acc[V], tspeed[V], timer[V], delta[V];
+    double thr2[V];      // collision pre-check guard: (diag + v dt)^2 (1 + 1e-12), or -1 when diag + v dt < 0
+    double acc2[V];      // IDM acceleration w.r.t. the target lane (vehicles changing lane)
+    double mq_a[9 * MB];  // MOBIL IDM evaluations of the batch
     int32_t lane[V], tlane[V], flags[V], sidx[V], rlen[V], ytimer[V];
     uint32_t rroad[V], rlanew[V];
     int32_t tl_old[V], mark[V];
+    int32_t best[V];     // collision: largest will-intersect partner index
+    int32_t chg[V];      // vehicles in an ongoing lane change (IDM w.r.t. target lane too)
+    int32_t mob_veh[V];  // vehicles whose MOBIL timer fired this sub-step
+    int32_t pairq[PQ];   // lo | hi << 16
+    int32_t wpair[WQ];
+    int16_t fo[V];       // front neighbour on the own lane
+    int16_t mq_f[3 * MB], mq_r[3 * MB];  // MOBIL neighbour queries: own lane, left candidate, right candidate
     int32_t n, steps, road_steps, ego, episode, done, flag0, flag1;
+    int32_t n_chg, n_mob, n_pair, n_w, overflow, pad0;
     double time, ret;
 };
 
 template <int V_>
 struct EnvCtx {
     static constexpr int V = V_;
+    static constexpr int W = (V_ + 31) / 32;  // mask words per lane
     EnvState<V_>* st;
     const SceneDev* sc;
-    const ttrl_lane* lanes;  // lane table (shared-memory copy when it fits, else sc->lanes)
-    double* S;               // [V][L] longitudinal local coordinate of vehicle v in lane l
-    double* R;               // [V][L] lateral
+    const ttrl_lane* lanes;  // lane table (shared-memory copy)
+    d2* SR;                  // [V][L] (longitudinal, lateral) local coordinates of vehicle v in lane l
+    uint32_t* lmask;         // [L][W] bit v of lane l: vehicle v is on lane l with margin 1 (road.py:503)
     double* pred;            // [3][V][kPred] regulation predictions (x, y, heading); null if not regulated
     float* obs_s;            // staging for one Kinematics observation
     int32_t* cell;           // OccupancyGrid per-cell winner (W*H ints)
     int L;
     int vcap;                // storage capacity (slots per env in HBM), <= V
+    double gap_den;          // 2 sqrt(-COMFORT_ACC_MAX COMFORT_ACC_MIN) (behavior.py:214-216)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -105,9 +138,10 @@ TT_HD double lmap(double v, double x0, double x1, double y0, double y1) {  // ut
 TT_HD double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
 
 // ------------------------------------------------------------------------------------------------
-// lane geometry: ttrl_env/road/lane.py
+// lane geometry: ttrl_env/road/lane.py.  The curved kinds live behind __noinline__ functions so that
+// atan2 / sin / cos exist once in the binary.
 // ------------------------------------------------------------------------------------------------
-TT_HD void lane_local(const ttrl_lane& l, double px, double py, double& s, double& r) {
+TT_HDN void lane_local_curved(const ttrl_lane& l, double px, double py, double& s, double& r) {
     double dx = px - l.ax, dy = py - l.ay;
     if (l.kind == TTRL_LANE_CIRCULAR) {  // lane.py:355-362
         double phi = atan2(dy, dx);
@@ -115,32 +149,45 @@ TT_HD void lane_local(const ttrl_lane& l, double px, double py, double& s, doubl
         double rad = sqrt(dx * dx + dy * dy);
         s = l.cdir * (phi - l.start_phase) * l.radius;
         r = l.cdir * (l.radius - rad);
-    } else {  // lane.py:209-213, :282-286
+    } else {  // sine lane.py:282-286
         double lon = dx * l.dx + dy * l.dy;
         double lat = dx * (-l.dy) + dy * l.dx;
-        if (l.kind == TTRL_LANE_SINE) lat = lat - l.amplitude * sin(l.pulsation * lon + l.phase);
         s = lon;
-        r = lat;
+        r = lat - l.amplitude * sin(l.pulsation * lon + l.phase);
     }
 }
-TT_HD void lane_position(const ttrl_lane& l, double s, double r, double& px, double& py) {
+TT_HD void lane_local(const ttrl_lane& l, double px, double py, double& s, double& r) {
+    if (l.kind != TTRL_LANE_STRAIGHT) { lane_local_curved(l, px, py, s, r); return; }
+    double dx = px - l.ax, dy = py - l.ay;  // lane.py:209-213
+    s = dx * l.dx + dy * l.dy;
+    r = dx * (-l.dy) + dy * l.dx;
+}
+TT_HDN void lane_position_curved(const ttrl_lane& l, double s, double r, double& px, double& py) {
     if (l.kind == TTRL_LANE_CIRCULAR) {  // lane.py:341-345
         double phi = l.cdir * s / l.radius + l.start_phase;
         double rr = l.radius - r * l.cdir;
         px = l.ax + rr * cos(phi);
         py = l.ay + rr * sin(phi);
-    } else {  // lane.py:196-201, :268-273
-        if (l.kind == TTRL_LANE_SINE) r = r + l.amplitude * sin(l.pulsation * s + l.phase);
+    } else {  // sine lane.py:268-273
+        r = r + l.amplitude * sin(l.pulsation * s + l.phase);
         px = l.ax + s * l.dx + r * (-l.dy);
         py = l.ay + s * l.dy + r * l.dx;
     }
 }
-TT_HD double lane_heading_at(const ttrl_lane& l, double s) {  // lane.py:203-204, :275-280, :347-350
+TT_HD void lane_position(const ttrl_lane& l, double s, double r, double& px, double& py) {
+    if (l.kind != TTRL_LANE_STRAIGHT) { lane_position_curved(l, s, r, px, py); return; }
+    px = l.ax + s * l.dx + r * (-l.dy);  // lane.py:196-201
+    py = l.ay + s * l.dy + r * l.dx;
+}
+TT_HDN double lane_heading_sine(const ttrl_lane& l, double s) {  // lane.py:275-280
+    return l.heading + atan(l.amplitude * l.pulsation * cos(l.pulsation * s + l.phase));
+}
+TT_HD double lane_heading_at(const ttrl_lane& l, double s) {  // lane.py:203-204, :347-350
     if (l.kind == TTRL_LANE_CIRCULAR) {
         double phi = l.cdir * s / l.radius + l.start_phase;
         return phi + kPi / 2 * l.cdir;
     }
-    if (l.kind == TTRL_LANE_SINE) return l.heading + atan(l.amplitude * l.pulsation * cos(l.pulsation * s + l.phase));
+    if (l.kind == TTRL_LANE_SINE) return lane_heading_sine(l, s);
     return l.heading;
 }
 TT_HD bool lane_on_lane(const ttrl_lane& l, double s, double r, double margin) {  // lane.py:80-102
@@ -162,27 +209,52 @@ TT_HD double lane_distance(const ttrl_lane& l, double px, double py) {
 // ------------------------------------------------------------------------------------------------
 // table access
 // ------------------------------------------------------------------------------------------------
-template <class C> TT_HD double& S_(C& c, int v, int l) { return c.S[v * c.L + l]; }
-template <class C> TT_HD double& R_(C& c, int v, int l) { return c.R[v * c.L + l]; }
+template <class C> TT_HD double& S_(C& c, int v, int l) { return c.SR[v * c.L + l].x; }
+template <class C> TT_HD double& R_(C& c, int v, int l) { return c.SR[v * c.L + l].y; }
 
 // Rebuild row v of the table and return the closest lane: RoadNetwork.get_closest_lane_index
 // (road.py:55-71, np.argmin keeps the FIRST minimum) over distance_with_heading (lane.py:132-147).
+// Also returns the bitmask of the lanes the vehicle is "on" with margin 1 (neighbour_vehicles road.py:503).
 template <class C>
-TT_HD int table_row_and_closest(C& c, int v) {
-    const double px = c.st->x[v], py = c.st->y[v], hd = c.st->h[v];
+TT_HD int table_row_and_closest(C& c, int v, uint64_t& on_mask) {
+    const double px = c.st->pos[v].x, py = c.st->pos[v].y, hd = c.st->h[v];
     int best = 0;
     double bd = 0;
+    uint64_t m = 0;
     for (int l = 0; l < c.L; ++l) {
         const ttrl_lane& ln = c.lanes[l];
         double s, r;
         lane_local(ln, px, py, s, r);
-        S_(c, v, l) = s;
-        R_(c, v, l) = r;
+        c.SR[v * c.L + l] = d2{s, r};
+        if (lane_on_lane(ln, s, r, 1.0)) m |= 1ull << l;
         double ang = fabs(wrap_to_pi(hd - lane_heading_at(ln, s)));
         double d = lane_distance_sr(ln, s, r) + 1.0 * ang;
         if (l == 0 || d < bd) { bd = d; best = l; }
     }
+    on_mask = m;
     return best;
+}
+template <class C, class Exec>
+TT_HD void publish_on_mask(C& c, Exec& ex, int v, uint64_t m) {
+    while (m) {
+#if defined(__CUDA_ARCH__)
+        const int l = __ffsll((long long)m) - 1;
+#else
+        const int l = __builtin_ctzll(m);
+#endif
+        m &= m - 1;
+        ex.atomic_or(&c.lmask[l * C::W + (v >> 5)], 1u << (v & 31));
+    }
+}
+// Rebuild the whole table + lane masks from positions (after load / compaction).
+template <class C, class Exec>
+TT_HD void rebuild_tables(C& c, Exec& ex) {
+    ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; });
+    ex.parn(c.st->n, [&](int t) {
+        uint64_t m;
+        (void)table_row_and_closest(c, t, m);
+        publish_on_mask(c, ex, t, m);
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -259,15 +331,15 @@ TT_HD void follow_road(C& c, int i) {
 
 // ControlledVehicle.steering_control controller.py:145-187
 template <class C>
-TT_HD double steering_control(C& c, int i, int target_lane) {
+TT_HDN double steering_control(C& c, int i, int target_lane) {
     const double TAU_PURSUIT = 0.5 * 0.2, KP_LATERAL = 1 / 0.6, KP_HEADING = 1 / 0.2;
     const double MAX_STEER = kPi / 3;
     const ttrl_lane& tl = c.lanes[target_lane];
-    const double s = S_(c, i, target_lane), r = R_(c, i, target_lane);
+    const d2 sr = c.SR[i * c.L + target_lane];
     const double speed = c.st->v[i];
-    double lane_next = s + speed * TAU_PURSUIT;
+    double lane_next = sr.x + speed * TAU_PURSUIT;
     double lane_future_heading = lane_heading_at(tl, lane_next);
-    double lateral_speed_command = -KP_LATERAL * r;
+    double lateral_speed_command = -KP_LATERAL * sr.y;
     double heading_command = asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
     double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
     double heading_rate_command = KP_HEADING * wrap_to_pi(heading_ref - c.st->h[i]);
@@ -291,10 +363,11 @@ TT_HD int decode_action(const ttrl_config& cfg, int a) {  // action.py:204-211
     return a == 0 ? A_LANE_LEFT : a == 1 ? A_IDLE : A_LANE_RIGHT;
 }
 
-// ControlledVehicle.act controller.py:89-133
+// ControlledVehicle.act controller.py:89-133, WITHOUT its controller tail: the steering / speed commands of
+// an act() call are overwritten by the next call, so only the last call of a sub-step (Road.act) computes them
+// (controlled_commands, phase C).  The target-lane side effects of every call are kept.
 template <class C>
-TT_HDN void controlled_act(C& c, int i, int action) {
-    const double KP_A = 1 / 0.6, MAX_STEER = kPi / 3;
+TT_HD void controlled_act_lanes(C& c, int i, int action) {
     auto* st = c.st;
     follow_road(c, i);
     if (action == A_LANE_RIGHT || action == A_LANE_LEFT) {
@@ -305,43 +378,49 @@ TT_HDN void controlled_act(C& c, int i, int action) {
         const int cand = rd.first_lane + id;
         if (lane_reachable(c.lanes[cand], S_(c, i, cand), R_(c, i, cand))) st->tlane[i] = cand;
     }
-    double steering = steering_control(c, i, st->tlane[i]);
-    st->steer[i] = clipd(steering, -MAX_STEER, MAX_STEER);
-    st->acc[i] = KP_A * (st->tspeed[i] - st->v[i]);  // speed_control :189-198
 }
-
-// MDPVehicle.act controller.py:295-315
+// MDPVehicle.act controller.py:295-315 (lane / speed-index side effects)
 template <class C>
-TT_HD void mdp_act(C& c, int i, int action) {
+TT_HD void mdp_act_lanes(C& c, int i, int action) {
     auto* st = c.st;
     const ttrl_config& cfg = c.sc->cfg;
     if (action == A_FASTER) st->sidx[i] = speed_to_index(cfg, st->v[i]) + 1;
     else if (action == A_SLOWER) st->sidx[i] = speed_to_index(cfg, st->v[i]) - 1;
-    else { controlled_act(c, i, action); return; }
+    else { controlled_act_lanes(c, i, action); return; }
     const int n = cfg.n_target_speeds;
     st->sidx[i] = st->sidx[i] < 0 ? 0 : (st->sidx[i] > n - 1 ? n - 1 : st->sidx[i]);
     st->tspeed[i] = cfg.target_speeds[st->sidx[i]];
-    controlled_act(c, i, A_NONE);
+    controlled_act_lanes(c, i, A_NONE);
 }
 
 // ------------------------------------------------------------------------------------------------
 // IDM / MOBIL: ttrl_env/vehicle/behavior.py
 // ------------------------------------------------------------------------------------------------
-// Road.neighbour_vehicles road.py:480-513 served from the table
+// Road.neighbour_vehicles road.py:480-513 served from the table; candidates come from the lane's on-lane
+// bitmask in increasing index order, which keeps the reference's tie rules (front: a later vehicle with an
+// equal s replaces, `<=` :507; rear: the earlier one stays, `>` :510).
 template <class C>
 TT_HD void neighbours(C& c, int i, int lane, int& front, int& rear) {
-    const ttrl_lane& l = c.lanes[lane];
     const double s = S_(c, i, lane);
-    const double half = l.width / 2 + 1.0, hi = l.length + kVehLength;
     double sf = 0, sr = 0;
     int f = -1, r = -1;
-    const int n = c.st->n;
-    for (int j = 0; j < n; ++j) {
-        if (j == i) continue;
-        const double sv = S_(c, j, lane), lv = R_(c, j, lane);
-        if (!(fabs(lv) <= half && -kVehLength <= sv && sv < hi)) continue;
-        if (s <= sv && (f < 0 || sv <= sf)) { sf = sv; f = j; }
-        if (sv < s && (r < 0 || sv > sr)) { sr = sv; r = j; }
+    const int L = c.L;
+#pragma unroll 1
+    for (int w = 0; w < C::W; ++w) {
+        uint32_t m = c.lmask[lane * C::W + w];
+        if ((i >> 5) == w) m &= ~(1u << (i & 31));
+        while (m) {
+#if defined(__CUDA_ARCH__)
+            const int b = __ffs((int)m) - 1;
+#else
+            const int b = __builtin_ctz(m);
+#endif
+            m &= m - 1;
+            const int j = w * 32 + b;
+            const double sv = c.SR[j * L + lane].x;
+            if (s <= sv) { if (f < 0 || sv <= sf) { sf = sv; f = j; } }
+            else if (r < 0 || sv > sr) { sr = sv; r = j; }
+        }
     }
     front = f;
     rear = r;
@@ -351,15 +430,15 @@ template <class C>
 TT_HD double desired_gap(C& c, int ego, int front) {
     const ttrl_config& cfg = c.sc->cfg;
     auto* st = c.st;
-    const double ab = -cfg.comfort_acc_max * cfg.comfort_acc_min;
-    const double ec = st->ch[ego], es = st->sh[ego];
-    const double dvx = st->v[ego] * ec - st->v[front] * st->ch[front], dvy = st->v[ego] * es - st->v[front] * st->sh[front];
-    const double dv = dvx * ec + dvy * es;
-    return cfg.distance_wanted + st->v[ego] * cfg.time_wanted + st->v[ego] * dv / (2 * sqrt(ab));
+    const d2 e = st->cs[ego], f = st->cs[front];
+    const double ve = st->v[ego], vf = st->v[front];
+    const double dvx = ve * e.x - vf * f.x, dvy = ve * e.y - vf * f.y;
+    const double dv = dvx * e.x + dvy * e.y;
+    return cfg.distance_wanted + ve * cfg.time_wanted + ve * dv / c.gap_den;
 }
 // IDMVehicle.acceleration behavior.py:150-190 (self_delta = SELF's DELTA, also when ego is another vehicle)
 template <class C>
-TT_HD double idm_acceleration(C& c, double self_delta, int ego, int front) {
+TT_HDN double idm_acceleration(C& c, double self_delta, int ego, int front) {
     if (ego < 0) return 0.0;
     const ttrl_config& cfg = c.sc->cfg;
     auto* st = c.st;
@@ -373,54 +452,33 @@ TT_HD double idm_acceleration(C& c, double self_delta, int ego, int front) {
     }
     return acc;
 }
-// IDMVehicle.mobil behavior.py:265-324
-template <class C>
-TT_HDN bool mobil(C& c, int i, int cand) {
-    const ttrl_config& cfg = c.sc->cfg;
-    auto* st = c.st;
-    const double dl = st->delta[i];
-    int new_prec, new_foll;
-    neighbours(c, i, cand, new_prec, new_foll);
-    const double new_following_a = idm_acceleration(c, dl, new_foll, new_prec);
-    const double new_following_pred_a = idm_acceleration(c, dl, new_foll, i);
-    if (new_following_pred_a < -cfg.lane_change_max_braking_imposed) return false;
-    int old_prec, old_foll;
-    neighbours(c, i, st->lane[i], old_prec, old_foll);
-    const double self_pred_a = idm_acceleration(c, dl, i, new_prec);
-    if (st->rlen[i] > 0 && route_lane_at(st->rlanew[i], 0) >= 0) {
-        const int cur_t = c.lanes[st->tlane[i]].lane_id;
-        const int want = route_lane_at(st->rlanew[i], 0) - cur_t, dir = c.lanes[cand].lane_id - cur_t;
-        const int sw = (want > 0) - (want < 0), sd = (dir > 0) - (dir < 0);
-        if (sd != sw) return false;
-        if (self_pred_a < -cfg.lane_change_max_braking_imposed) return false;
-    } else {
-        const double self_a = idm_acceleration(c, dl, i, old_prec);
-        const double old_following_a = idm_acceleration(c, dl, old_foll, i);
-        const double old_following_pred_a = idm_acceleration(c, dl, old_foll, old_prec);
-        const double jerk = self_pred_a - self_a +
-                            cfg.politeness * (new_following_pred_a - new_following_a + old_following_pred_a - old_following_a);
-        if (jerk < cfg.lane_change_min_acc_gain) return false;
-    }
-    return true;
-}
 
 // ------------------------------------------------------------------------------------------------
-// ACT, split in three phases so that it is parallel over vehicles yet reproduces the reference's
-// sequential Road.act (road.py:461-464).  The only cross-vehicle write->read coupling inside act() is the
-// abort rule of change_lane_policy (behavior.py:229-244), which reads OTHER vehicles' target_lane_index:
-// vehicles earlier in the list have already acted (new value), later ones have not (old value).
-//   phase A  every vehicle: follow_road + (not changing lane) timer/MOBIL decision; ego: full controller
-//   phase B  vehicles in an ongoing lane change, in list order: abort test against the mixed old/new view
-//   phase C  every IDM vehicle: steering + IDM acceleration with its final target lane
+// ACT.  Reproduces the reference's sequential Road.act (road.py:461-464) with parallel phases.  The only
+// cross-vehicle write->read coupling inside act() is the abort rule of change_lane_policy
+// (behavior.py:229-244), which reads OTHER vehicles' target_lane_index: vehicles earlier in the list have
+// already acted (new value), later ones have not (old value).
+//   A   every vehicle: follow_road; ego: meta-action side effects; classify: ongoing lane change (-> phase B)
+//       or lane-change timer fired (-> MOBIL batch)
+//   M   MOBIL over the fired vehicles: neighbour-query tasks, IDM-evaluation tasks, one decision per vehicle
+//   B   vehicles in an ongoing lane change, in list order: abort test against the mixed old/new view
+//   C   every vehicle: steering + own-lane front neighbour; then IDM-evaluation tasks (own lane for all,
+//       target lane for the vehicles changing lane)
 // ------------------------------------------------------------------------------------------------
-template <class C>
-TT_HD void act_phase_a(C& c, int i) {
+template <class C, class Exec>
+TT_HD void act_phase_a(C& c, Exec& ex, int i, int first_action) {
     auto* st = c.st;
-    st->tl_old[i] = st->tlane[i];
     st->mark[i] = 0;
-    if (i >= st->n) return;
-    if (st->flags[i] & TTRL_FL_MDP) { mdp_act(c, i, A_NONE); return; }  // Road.act -> MDPVehicle.act(None)
-    if (st->flags[i] & TTRL_FL_CRASHED) return;                       // behavior.py:102-103
+    if (st->flags[i] & TTRL_FL_MDP) {
+        // DiscreteMetaAction.act (action.py:259-260) runs BEFORE Road.act: its target-lane change is the "old"
+        // value every other vehicle sees; then Road.act -> MDPVehicle.act(None)
+        if (first_action != A_NONE && i == st->ego) mdp_act_lanes(c, i, first_action);
+        st->tl_old[i] = st->tlane[i];
+        mdp_act_lanes(c, i, A_NONE);
+        return;
+    }
+    st->tl_old[i] = st->tlane[i];
+    if (st->flags[i] & TTRL_FL_CRASHED) return;  // behavior.py:102-103
     follow_road(c, i);
     const int ln = st->lane[i];
     if (ln != st->tlane[i]) {  // ongoing change: behavior.py:229-244, resolved in phase B
@@ -429,21 +487,83 @@ TT_HD void act_phase_a(C& c, int i) {
     }
     if (!(c.sc->cfg.lane_change_delay < st->timer[i])) return;  // utils.do_every utils.py:25-26
     st->timer[i] = 0;
+    // side_lanes road.py:200-211 (id-1 then id+1), reachable (lane.py:104-118), abs(speed) >= 1 (behavior.py:257)
     const ttrl_lane& l = c.lanes[ln];
     const int nl = c.sc->roads[l.road].n_lanes;
-    for (int k = 0; k < 2; ++k) {  // side_lanes road.py:200-211: id-1 then id+1
-        const int cand = k == 0 ? ln - 1 : ln + 1;
-        if (k == 0 ? !(l.lane_id > 0) : !(l.lane_id < nl - 1)) continue;
-        if (!lane_reachable(c.lanes[cand], S_(c, i, cand), R_(c, i, cand))) continue;
-        if (fabs(st->v[i]) < 1) continue;
-        if (mobil(c, i, cand)) st->tlane[i] = cand;
+    int valid = 0;
+    if (!(fabs(st->v[i]) < 1)) {
+        if (l.lane_id > 0 && lane_reachable(c.lanes[ln - 1], S_(c, i, ln - 1), R_(c, i, ln - 1))) valid |= 1;
+        if (l.lane_id < nl - 1 && lane_reachable(c.lanes[ln + 1], S_(c, i, ln + 1), R_(c, i, ln + 1))) valid |= 2;
     }
+    if (valid) st->mob_veh[ex.atomic_add(&st->n_mob, 1)] = i | (valid << 16);
 }
+
+// IDMVehicle.mobil behavior.py:265-324 for the vehicles of one batch (ranks base .. base+nb-1 of mob_veh).
+template <class C, class Exec>
+TT_HD void mobil_batch(C& c, Exec& ex, int base, int nb) {
+    auto* st = c.st;
+    const ttrl_config& cfg = c.sc->cfg;
+    // M1: neighbour queries: q = 0 own lane, 1 left candidate, 2 right candidate
+    ex.parn(3 * nb, [&](int k) {
+        const int b = k / 3, q = k - 3 * b;
+        const int rec = st->mob_veh[base + b], i = rec & 0xFFFF, valid = rec >> 16;
+        int f = -1, r = -1;
+        if (q == 0 || (valid >> (q - 1)) & 1) neighbours(c, i, st->lane[i] + (q == 0 ? 0 : q == 1 ? -1 : 1), f, r);
+        st->mq_f[k] = (int16_t)f;
+        st->mq_r[k] = (int16_t)r;
+    });
+    // M2: IDM evaluations.  e = 0 self_a, 1 old_following_a, 2 old_following_pred_a; 3+3k+{0,1,2} =
+    // new_following_a, new_following_pred_a, self_pred_a of candidate k
+    ex.parn(9 * nb, [&](int k) {
+        const int b = k / 9, e = k - 9 * b;
+        const int rec = st->mob_veh[base + b], i = rec & 0xFFFF, valid = rec >> 16;
+        const int old_prec = st->mq_f[3 * b], old_foll = st->mq_r[3 * b];
+        int ego = -1, front = -1;
+        if (e == 0) { ego = i; front = old_prec; }
+        else if (e == 1) { ego = old_foll; front = i; }
+        else if (e == 2) { ego = old_foll; front = old_prec; }
+        else {
+            const int kk = (e - 3) / 3, w = (e - 3) - 3 * kk;
+            if ((valid >> kk) & 1) {
+                const int new_prec = st->mq_f[3 * b + 1 + kk], new_foll = st->mq_r[3 * b + 1 + kk];
+                if (w == 0) { ego = new_foll; front = new_prec; }
+                else if (w == 1) { ego = new_foll; front = i; }
+                else { ego = i; front = new_prec; }
+            }
+        }
+        st->mq_a[k] = idm_acceleration(c, st->delta[i], ego, front);
+    });
+    // M3: decisions, candidates in side_lanes order; a later accepted candidate overwrites (behavior.py:250-263)
+    ex.parn(nb, [&](int b) {
+        const int rec = st->mob_veh[base + b], i = rec & 0xFFFF, valid = rec >> 16;
+        const double* a = st->mq_a + 9 * b;
+        const double self_a = a[0], old_following_a = a[1], old_following_pred_a = a[2];
+        for (int k = 0; k < 2; ++k) {
+            if (!((valid >> k) & 1)) continue;
+            const int cand = st->lane[i] + (k == 0 ? -1 : 1);
+            const double new_following_a = a[3 + 3 * k], new_following_pred_a = a[4 + 3 * k], self_pred_a = a[5 + 3 * k];
+            if (new_following_pred_a < -cfg.lane_change_max_braking_imposed) continue;
+            if (st->rlen[i] > 0 && route_lane_at(st->rlanew[i], 0) >= 0) {
+                const int cur_t = c.lanes[st->tlane[i]].lane_id;
+                const int want = route_lane_at(st->rlanew[i], 0) - cur_t, dir = c.lanes[cand].lane_id - cur_t;
+                const int sw = (want > 0) - (want < 0), sd = (dir > 0) - (dir < 0);
+                if (sd != sw) continue;
+                if (self_pred_a < -cfg.lane_change_max_braking_imposed) continue;
+            } else {
+                const double jerk = self_pred_a - self_a +
+                                    cfg.politeness * (new_following_pred_a - new_following_a + old_following_pred_a - old_following_a);
+                if (jerk < cfg.lane_change_min_acc_gain) continue;
+            }
+            st->tlane[i] = cand;
+        }
+    });
+}
+
 // abort predicate of vehicle i against vehicle j (behavior.py:232-243)
 template <class C>
 TT_HD bool abort_pred(C& c, int i, int j) {
     auto* st = c.st;
-    if (j == i || j >= st->n) return false;
+    if (j == i) return false;
     const int ti = st->tlane[i];
     const int view = j < i ? st->tlane[j] : st->tl_old[j];
     if (!(st->lane[j] != ti && view == ti)) return false;
@@ -452,37 +572,64 @@ TT_HD bool abort_pred(C& c, int i, int j) {
     const double d_star = desired_gap(c, i, j);
     return 0 < d && d < d_star;
 }
-template <class C>
-TT_HD void act_phase_c(C& c, int i) {
+
+// phase C1: steering for every vehicle (+ speed control for the ego), own-lane front neighbour
+template <class C, class Exec>
+TT_HD void act_phase_c1(C& c, Exec& ex, int i) {
     auto* st = c.st;
-    if (i >= st->n) return;
-    if (st->flags[i] & (TTRL_FL_MDP | TTRL_FL_CRASHED)) return;
     const double MAX_STEER = kPi / 3;
-    const int tl = st->tlane[i], ln = st->lane[i];
-    const double steering = clipd(steering_control(c, i, tl), -MAX_STEER, MAX_STEER);
-    int f, r;
-    neighbours(c, i, ln, f, r);
-    double acc = idm_acceleration(c, st->delta[i], i, f);
-    if (ln != tl) {
-        neighbours(c, i, tl, f, r);
-        acc = fmin(acc, idm_acceleration(c, st->delta[i], i, f));
-    }
+    const int fl = st->flags[i];
+    st->fo[i] = -1;
+    if (!(fl & TTRL_FL_MDP) && (fl & TTRL_FL_CRASHED)) return;  // IDMVehicle.act returns early when crashed
+    const int tl = st->tlane[i];
+    const double steering = clipd(steering_control(c, i, tl), -MAX_STEER, MAX_STEER);  // controller.py:131, behavior.py:114-116
     st->steer[i] = steering;
-    st->acc[i] = clipd(acc, -c.sc->cfg.acc_max, c.sc->cfg.acc_max);
+    if (fl & TTRL_FL_MDP) {
+        st->acc[i] = (1 / 0.6) * (st->tspeed[i] - st->v[i]);  // speed_control controller.py:189-198
+        return;
+    }
+    int f, r;
+    neighbours(c, i, st->lane[i], f, r);
+    st->fo[i] = (int16_t)f;
+    if (st->lane[i] != tl) st->chg[ex.atomic_add(&st->n_chg, 1)] = i;
+}
+// phase C2 task k: k < n -> IDM acceleration of vehicle k on its own lane; k >= n -> of a lane-changing vehicle
+// w.r.t. the front vehicle on its target lane (behavior.py:118-137)
+template <class C>
+TT_HD void act_phase_c2(C& c, int k) {
+    auto* st = c.st;
+    const int n = st->n;
+    int i, front;
+    if (k < n) {
+        i = k;
+        if (st->flags[i] & (TTRL_FL_MDP | TTRL_FL_CRASHED)) return;
+        front = st->fo[i];
+    } else {
+        i = st->chg[k - n];
+        int r;
+        neighbours(c, i, st->tlane[i], front, r);
+    }
+    const double a = idm_acceleration(c, st->delta[i], i, front);
+    if (k < n) st->acc[i] = a; else st->acc2[i] = a;
 }
 
 // ------------------------------------------------------------------------------------------------
 // INTEGRATE: IDMVehicle.step behavior.py:139-148 -> Vehicle.step kinematics.py:130-153, clip_actions :155-168,
 // on_state_update :170-177 (closest lane via the rebuilt table row)
 // ------------------------------------------------------------------------------------------------
-template <class C>
-TT_HD void integrate(C& c, int i) {
+template <class C, class Exec>
+TT_HD void integrate(C& c, Exec& ex, int i) {
     auto* st = c.st;
-    if (i >= st->n) return;
     const double dt = c.sc->dt;
     int fl = st->flags[i];
-    if (!(fl & TTRL_FL_MDP)) st->timer[i] += dt;
     double steer = st->steer[i], acc = st->acc[i];
+    if (!(fl & TTRL_FL_MDP)) {
+        st->timer[i] += dt;
+        if (!(fl & TTRL_FL_CRASHED)) {  // tail of IDMVehicle.act (behavior.py:130-137)
+            if (st->lane[i] != st->tlane[i]) acc = fmin(acc, st->acc2[i]);
+            acc = clipd(acc, -c.sc->cfg.acc_max, c.sc->cfg.acc_max);
+        }
+    }
     const double speed = st->v[i];
     if (fl & TTRL_FL_CRASHED) { steer = 0; acc = -1.0 * speed; }
     if (speed > 40.0) acc = fmin(acc, 1.0 * (40.0 - speed));
@@ -491,36 +638,51 @@ TT_HD void integrate(C& c, int i) {
     st->acc[i] = acc;
     const double beta = atan(1.0 / 2 * tan(steer));
     const double hd = st->h[i];
-    const double vx = speed * cos(hd + beta), vy = speed * sin(hd + beta);
-    double px = st->x[i] + vx * dt, py = st->y[i] + vy * dt;
+    double sb, cb;
+    sincos(hd + beta, &sb, &cb);
+    const double vx = speed * cb, vy = speed * sb;
+    double px = st->pos[i].x + vx * dt, py = st->pos[i].y + vy * dt;
     if (fl & TTRL_FL_HAS_IMPACT) {
-        px += st->impx[i];
-        py += st->impy[i];
+        px += st->imp[i].x;
+        py += st->imp[i].y;
         fl = (fl | TTRL_FL_CRASHED) & ~TTRL_FL_HAS_IMPACT;
-        st->impx[i] = 0;
-        st->impy[i] = 0;
+        st->imp[i] = d2{0, 0};
     }
     const double nh = hd + speed * sin(beta) / (kVehLength / 2) * dt;
-    st->x[i] = px;
-    st->y[i] = py;
+    const double nv = speed + acc * dt;
+    st->pos[i] = d2{px, py};
     st->h[i] = nh;
-    st->v[i] = speed + acc * dt;
-    st->ch[i] = cos(nh);
-    st->sh[i] = sin(nh);
+    st->v[i] = nv;
+    double sn, cn;
+    sincos(nh, &sn, &cn);
+    st->cs[i] = d2{cn, sn};
     st->flags[i] = fl;
-    st->lane[i] = table_row_and_closest(c, i);
+    uint64_t m;
+    st->lane[i] = table_row_and_closest(c, i, m);
+    publish_on_mask(c, ex, i, m);
+    // collision pre-check guard (objects.py:123-126): radius (diag_i + diag_j)/2 + speed dt of the LOWER index
+    const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
+    const double thr = (diag + diag) / 2 + nv * dt;
+    st->thr2[i] = thr < 0 ? -1.0 : thr * thr * (1.0 + 1e-12);
+    st->best[i] = -1;
 }
 
 // ------------------------------------------------------------------------------------------------
 // COLLIDE: Road.step's pair loop road.py:474-476 -> handle_collisions objects.py:91-137 -> SAT utils.py:175-239.
-// Thread k scans every partner p.  In the reference the pair (i<j) loop assigns `impact` to both members, so
-// for vehicle k the LAST assignment comes from its will-intersect partner with the largest index (pairs
-// involving k are visited in increasing partner order); `crashed` is an OR.
+// In the reference the pair (i<j) loop assigns `impact` to both members, so for vehicle k the LAST assignment
+// comes from its will-intersect partner with the largest index (pairs involving k are visited in increasing
+// partner order); `crashed` is an OR.
+//   K1  half-ring scan: vehicle k tests partners k+1 .. k+n/2 (mod n) -> candidate pair queue.  The exact test
+//       `norm(dp) > thr` is guarded by a squared-distance comparison that is conservative by 1e-12 relative.
+//   K2  8 lanes per candidate pair, one separating axis each (ex.sat_pairs); crashed flags OR-ed, will-intersect
+//       pairs appended to a list with their translation.
+//   K3  best[k] = max will-intersect partner;  K4  the winning pair writes the impact.
+// Queue overflow (pathological pile-ups) falls back to the plain per-vehicle loop `collide_serial`.
 // ------------------------------------------------------------------------------------------------
 struct Poly { double p[5][2]; };
 template <class C>
 TT_HD void vehicle_polygon(C& c, int i, Poly& o) {  // objects.py:168-180
-    const double cs = c.st->ch[i], sn = c.st->sh[i], px = c.st->x[i], py = c.st->y[i];
+    const double cs = c.st->cs[i].x, sn = c.st->cs[i].y, px = c.st->pos[i].x, py = c.st->pos[i].y;
     const double hx[4] = {-kVehLength / 2, -kVehLength / 2, +kVehLength / 2, +kVehLength / 2};
     const double hy[4] = {-kVehWidth / 2, +kVehWidth / 2, +kVehWidth / 2, -kVehWidth / 2};
 #pragma unroll
@@ -534,7 +696,7 @@ TT_HD void vehicle_polygon(C& c, int i, Poly& o) {  // objects.py:168-180
 TT_HD void project_polygon(const Poly& g, double nx, double ny, double& mn, double& mx) {  // utils.py:175-183
     mn = mx = g.p[0][0] * nx + g.p[0][1] * ny;
 #pragma unroll
-    for (int k = 1; k < 5; ++k) {
+    for (int k = 1; k < 4; ++k) {  // the closing 5th point repeats the first: it cannot change min / max
         const double pr = g.p[k][0] * nx + g.p[k][1] * ny;
         if (pr < mn) mn = pr;
         if (pr > mx) mx = pr;
@@ -543,73 +705,135 @@ TT_HD void project_polygon(const Poly& g, double nx, double ny, double& mn, doub
 TT_HD double interval_distance(double min_a, double max_a, double min_b, double max_b) {  // utils.py:186-191
     return min_a < min_b ? min_b - max_a : min_a - max_b;
 }
-// utils.are_polygons_intersecting utils.py:194-239 (a = lower-index vehicle).  Returns bit0 intersecting, bit1 will.
+// One separating-axis test of utils.are_polygons_intersecting (utils.py:194-239): axis = edge (axis & 3) of
+// polygon a (axis < 4) or b.  fl bit0: separated now, bit1: separated after the relative displacement.
+// The reference's early `break` only skips work once both flags are already false, and its running
+// `min_distance` matters only when will_intersect stays true (no break happened), so the 8 axes are independent:
+//   intersecting = no axis has bit0, will_intersect = no axis has bit1, translation = first axis of minimal absd.
+struct AxisRes { double absd, nx, ny; int fl; };
 template <class C>
-TT_HDN int sat_pair(C& c, int ia, int ib, double& tx, double& ty) {
+TT_HD AxisRes sat_axis(C& c, int ia, int ib, int axis) {
     auto* st = c.st;
     const double dt = c.sc->dt;
     Poly a, b;
     vehicle_polygon(c, ia, a);
     vehicle_polygon(c, ib, b);
-    const double rvx = st->v[ia] * st->ch[ia] * dt - st->v[ib] * st->ch[ib] * dt;
-    const double rvy = st->v[ia] * st->sh[ia] * dt - st->v[ib] * st->sh[ib] * dt;
-    bool inter = true, will = true;
-    double min_distance = INFINITY, axx = 0, axy = 0;
-    for (int poly = 0; poly < 2; ++poly) {
-        const Poly& pg = poly == 0 ? a : b;
-        for (int k = 0; k < 4; ++k) {
-            double nx = -pg.p[k + 1][1] + pg.p[k][1], ny = pg.p[k + 1][0] - pg.p[k][0];
-            const double nn = sqrt(nx * nx + ny * ny);
-            nx /= nn;
-            ny /= nn;
-            double min_a, max_a, min_b, max_b;
-            project_polygon(a, nx, ny, min_a, max_a);
-            project_polygon(b, nx, ny, min_b, max_b);
-            if (interval_distance(min_a, max_a, min_b, max_b) > 0) inter = false;
-            const double vp = nx * rvx + ny * rvy;
-            if (vp < 0) min_a += vp; else max_a += vp;
-            const double distance = interval_distance(min_a, max_a, min_b, max_b);
-            if (distance > 0) will = false;
-            if (!inter && !will) break;
-            if (fabs(distance) < min_distance) {
-                min_distance = fabs(distance);
-                const double cax = (((a.p[0][0] + a.p[1][0]) + a.p[2][0]) + a.p[3][0]) / 4, cay = (((a.p[0][1] + a.p[1][1]) + a.p[2][1]) + a.p[3][1]) / 4;
-                const double cbx = (((b.p[0][0] + b.p[1][0]) + b.p[2][0]) + b.p[3][0]) / 4, cby = (((b.p[0][1] + b.p[1][1]) + b.p[2][1]) + b.p[3][1]) / 4;
-                if ((cax - cbx) * nx + (cay - cby) * ny > 0) { axx = nx; axy = ny; } else { axx = -nx; axy = -ny; }
-            }
-        }
-    }
-    if (will) { tx = min_distance * axx; ty = min_distance * axy; } else { tx = 0; ty = 0; }
-    return (inter ? 1 : 0) | (will ? 2 : 0);
+    const double rvx = st->v[ia] * st->cs[ia].x * dt - st->v[ib] * st->cs[ib].x * dt;
+    const double rvy = st->v[ia] * st->cs[ia].y * dt - st->v[ib] * st->cs[ib].y * dt;
+    const Poly& pg = axis < 4 ? a : b;
+    const int k = axis & 3;
+    double nx = -pg.p[k + 1][1] + pg.p[k][1], ny = pg.p[k + 1][0] - pg.p[k][0];
+    const double nn = sqrt(nx * nx + ny * ny);
+    nx /= nn;
+    ny /= nn;
+    double min_a, max_a, min_b, max_b;
+    project_polygon(a, nx, ny, min_a, max_a);
+    project_polygon(b, nx, ny, min_b, max_b);
+    AxisRes res;
+    res.fl = interval_distance(min_a, max_a, min_b, max_b) > 0 ? 1 : 0;
+    const double vp = nx * rvx + ny * rvy;
+    if (vp < 0) min_a += vp; else max_a += vp;
+    const double distance = interval_distance(min_a, max_a, min_b, max_b);
+    if (distance > 0) res.fl |= 2;
+    res.absd = fabs(distance);
+    // orientation by the centre difference (utils.py:233-236)
+    const double cax = (((a.p[0][0] + a.p[1][0]) + a.p[2][0]) + a.p[3][0]) / 4, cay = (((a.p[0][1] + a.p[1][1]) + a.p[2][1]) + a.p[3][1]) / 4;
+    const double cbx = (((b.p[0][0] + b.p[1][0]) + b.p[2][0]) + b.p[3][0]) / 4, cby = (((b.p[0][1] + b.p[1][1]) + b.p[2][1]) + b.p[3][1]) / 4;
+    if ((cax - cbx) * nx + (cay - cby) * ny > 0) { res.nx = nx; res.ny = ny; } else { res.nx = -nx; res.ny = -ny; }
+    return res;
 }
+// exact pre-check objects.py:123-126 for the pair (lo < hi): true = the pair needs the SAT
 template <class C>
-TT_HD void collide(C& c, int k) {
+TT_HD bool collide_candidate(C& c, int lo, int hi) {
+    auto* st = c.st;
+    const d2 a = st->pos[lo], b = st->pos[hi];
+    const double dx = b.x - a.x, dy = b.y - a.y;
+    if (fma(dy, dy, dx * dx) > st->thr2[lo]) return false;  // conservative guard (fma only here)
+    const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
+    const double thr = (diag + diag) / 2 + st->v[lo] * c.sc->dt;
+    return !(sqrt(dx * dx + dy * dy) > thr);
+}
+// plain per-vehicle loop (fallback on queue overflow; same results)
+template <class C>
+TT_HDN void collide_serial(C& c, int k) {
     auto* st = c.st;
     const int n = st->n;
-    if (k >= n) return;
-    const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
-    const double dt = c.sc->dt;
-    const double xk = st->x[k], yk = st->y[k], vk = st->v[k];
     bool crashed = false, has_imp = false;
     double ix = 0, iy = 0;
     for (int p = 0; p < n; ++p) {
         if (p == k) continue;
-        const int lo = k < p ? k : p;
-        const double dx = st->x[p] - xk, dy = st->y[p] - yk;  // |other - self| is symmetric up to sign
-        const double thr = (diag + diag) / 2 + (lo == k ? vk : st->v[p]) * dt;
-        const double d2 = dx * dx + dy * dy;
-        if (sqrt(d2) > thr) continue;  // objects.py:123-126 (self = the lower index)
-        double tx, ty;
-        const int res = sat_pair(c, lo, k < p ? p : k, tx, ty);
-        if (res & 2) {  // will_intersect: self.impact = +t/2, other.impact = -t/2 (objects.py:110-111)
-            has_imp = true;
-            ix = lo == k ? tx / 2 : -tx / 2;
-            iy = lo == k ? ty / 2 : -ty / 2;
+        const int lo = k < p ? k : p, hi = k < p ? p : k;
+        if (!collide_candidate(c, lo, hi)) continue;
+        bool inter = true, will = true;
+        double best = INFINITY, tx = 0, ty = 0;
+        for (int ax = 0; ax < 8; ++ax) {
+            const AxisRes r = sat_axis(c, lo, hi, ax);
+            if (r.fl & 1) inter = false;
+            if (r.fl & 2) will = false;
+            if (r.absd < best) { best = r.absd; tx = r.nx; ty = r.ny; }
         }
-        if (res & 1) crashed = true;
+        if (will) {  // self.impact = +t/2, other.impact = -t/2 (objects.py:110-111)
+            has_imp = true;
+            ix = lo == k ? best * tx / 2 : -(best * tx) / 2;
+            iy = lo == k ? best * ty / 2 : -(best * ty) / 2;
+        }
+        if (inter) crashed = true;
     }
-    if (has_imp) { st->impx[k] = ix; st->impy[k] = iy; st->flags[k] |= TTRL_FL_HAS_IMPACT; }
+    if (has_imp) { st->imp[k] = d2{ix, iy}; st->flags[k] |= TTRL_FL_HAS_IMPACT; }
     if (crashed) st->flags[k] |= TTRL_FL_CRASHED;
+}
+template <class C, class Exec>
+TT_HD void collide_all(C& c, Exec& ex) {
+    auto* st = c.st;
+    const int n = st->n;
+    // K1
+    ex.parn(n, [&](int k) {
+        const int half = n / 2;
+        for (int m = 1; m <= half; ++m) {
+            int p = k + m;
+            if (p >= n) p -= n;
+            if (2 * m == n && k >= half) break;  // even n: the diametral pair is visited once
+            const int lo = k < p ? k : p, hi = k < p ? p : k;
+            if (!collide_candidate(c, lo, hi)) continue;
+            const int slot = ex.atomic_add(&st->n_pair, 1);
+            if (slot < EnvState<C::V>::PQ) st->pairq[slot] = lo | (hi << 16);
+            else st->overflow = 1;
+        }
+    });
+    const int np = st->n_pair;
+    if (np == 0) return;
+    if (!st->overflow) {
+        // K2
+        ex.sat_pairs(np,
+            [&](int q, int axis) { const int pr = st->pairq[q]; return sat_axis(c, pr & 0xFFFF, pr >> 16, axis); },
+            [&](int q, bool inter, bool will, double absd, double nx, double ny) {
+                const int pr = st->pairq[q], lo = pr & 0xFFFF, hi = pr >> 16;
+                if (inter) { ex.atomic_or((uint32_t*)&st->flags[lo], (uint32_t)TTRL_FL_CRASHED); ex.atomic_or((uint32_t*)&st->flags[hi], (uint32_t)TTRL_FL_CRASHED); }
+                if (will) {
+                    const int slot = ex.atomic_add(&st->n_w, 1);
+                    if (slot < EnvState<C::V>::WQ) { st->wpair[slot] = pr; st->wt[slot] = d2{absd * nx, absd * ny}; }
+                    else st->overflow = 1;
+                }
+            });
+    }
+    if (st->overflow) {  // uniform: shared memory
+        ex.parn(n, [&](int k) { collide_serial(c, k); });
+        return;
+    }
+    const int nw = st->n_w;
+    if (nw == 0) return;
+    // K3 / K4
+    ex.parn(nw, [&](int q) {
+        const int pr = st->wpair[q], lo = pr & 0xFFFF, hi = pr >> 16;
+        ex.atomic_max(&st->best[lo], hi);
+        ex.atomic_max(&st->best[hi], lo);
+    });
+    ex.parn(nw, [&](int q) {
+        const int pr = st->wpair[q], lo = pr & 0xFFFF, hi = pr >> 16;
+        const d2 t = st->wt[q];
+        if (st->best[lo] == hi) { st->imp[lo] = d2{t.x / 2, t.y / 2}; st->flags[lo] |= TTRL_FL_HAS_IMPACT; }
+        if (st->best[hi] == lo) { st->imp[hi] = d2{-t.x / 2, -t.y / 2}; st->flags[hi] |= TTRL_FL_HAS_IMPACT; }
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -638,7 +862,6 @@ TT_HD void position_heading_along_route(C& c, uint32_t rroad, uint32_t rlanew, i
 template <class C>
 TT_HDN void regulate_predict(C& c, int i) {
     auto* st = c.st;
-    if (i >= st->n) return;
     st->mark[i] = 0;
     if (st->flags[i] & TTRL_FL_YIELDING) {
         if (st->ytimer[i] >= 0.0 * 2) {
@@ -690,7 +913,9 @@ TT_HDN bool is_conflict_possible(C& c, int i, int j) {
     for (int k = 0; k < kPred; ++k) {
         const double dx = xj[k] - xi[k], dy = yj[k] - yi[k];
         if (sqrt(dx * dx + dy * dy) > kVehLength) continue;
-        const double c1 = cos(hi[k]), s1 = sin(hi[k]), c2 = cos(hj[k]), s2 = sin(hj[k]);
+        double s1, c1, s2, c2;
+        sincos(hi[k], &s1, &c1);
+        sincos(hj[k], &s2, &c2);
         if (has_corner_inside(xi[k], yi[k], c1, s1, xj[k], yj[k], c2, s2, len, wid) ||
             has_corner_inside(xj[k], yj[k], c2, s2, xi[k], yi[k], c1, s1, len, wid))
             return true;
@@ -708,8 +933,9 @@ TT_HD void regulate_pair(C& c, int i, int j) {
     if (p1 > p2) y = j;
     else if (p1 < p2) y = i;
     else {
-        const double f12 = st->ch[i] * (st->x[j] - st->x[i]) + st->sh[i] * (st->y[j] - st->y[i]);  // objects.py:204-205
-        const double f21 = st->ch[j] * (st->x[i] - st->x[j]) + st->sh[j] * (st->y[i] - st->y[j]);
+        const d2 pi_ = st->pos[i], pj = st->pos[j];
+        const double f12 = st->cs[i].x * (pj.x - pi_.x) + st->cs[i].y * (pj.y - pi_.y);  // objects.py:204-205
+        const double f21 = st->cs[j].x * (pi_.x - pj.x) + st->cs[j].y * (pi_.y - pj.y);
         y = f12 > f21 ? i : j;
     }
     if (!(st->flags[y] & TTRL_FL_MDP)) st->mark[y] = 1;  // benign same-value race
@@ -717,7 +943,7 @@ TT_HD void regulate_pair(C& c, int i, int j) {
 template <class C>
 TT_HD void regulate_apply(C& c, int i) {
     auto* st = c.st;
-    if (i < st->n && st->mark[i]) {
+    if (st->mark[i]) {
         st->tspeed[i] = 0;
         st->flags[i] |= TTRL_FL_YIELDING;
         st->ytimer[i] = 0;
@@ -732,41 +958,48 @@ template <class C, class Exec>
 TT_HD void env_substep(C& c, Exec& ex, int raw_action) {
     auto* st = c.st;
     const SceneDev* sc = c.sc;
+    using ES = EnvState<C::V>;
+    const int n = st->n;
     // ego meta-action on the first sub-step of an env-step: DiscreteMetaAction.act action.py:259-260
-    if (raw_action >= 0 && st->steps % sc->F == 0) {
-        ex.par([&](int t) { if (t == st->ego) mdp_act(c, t, decode_action(sc->cfg, raw_action)); });
+    const int first_action = (raw_action >= 0 && st->steps % sc->F == 0) ? decode_action(sc->cfg, raw_action) : A_NONE;
+    ex.parn(n, [&](int t) {
+        if (t == 0) { st->n_chg = 0; st->n_pair = 0; st->n_w = 0; st->overflow = 0; }
+        act_phase_a(c, ex, t, first_action);
+    });
+    {   // MOBIL over the vehicles whose timer fired (uniform: counters live in shared memory)
+        const int nm = st->n_mob;
+        for (int base = 0; base < nm; base += ES::MB) mobil_batch(c, ex, base, nm - base < ES::MB ? nm - base : ES::MB);
     }
-    ex.par([&](int t) { act_phase_a(c, t); });
-    {   // phase B (uniform loop: mark[] is in shared memory)
-        const int n = st->n;
+    {   // phase B, in list order
         for (int i = 0; i < n; ++i) {
             if (!st->mark[i]) continue;
-            const bool ab = ex.any([&](int j) { return abort_pred(c, i, j); });
-            if (ab) ex.par([&](int t) { if (t == i) st->tlane[i] = st->lane[i]; });
+            const bool ab = ex.any(n, [&](int j) { return abort_pred(c, i, j); });
+            if (ab) { if (ex.first()) st->tlane[i] = st->lane[i]; ex.sync(); }
         }
     }
-    ex.par([&](int t) { act_phase_c(c, t); });
+    ex.parn(n, [&](int t) {
+        if (t == 0) st->n_mob = 0;
+        act_phase_c1(c, ex, t);
+    });
+    ex.parn(n + st->n_chg, [&](int k) { act_phase_c2(c, k); });
     if (sc->cfg.regulated) {  // RegulatedRoad.step regulation.py:28-32
         const int rs = st->road_steps + 1;
         if (rs % sc->reg_period == 0) {
-            ex.par([&](int t) { regulate_predict(c, t); });
-            ex.par([&](int t) {
-                const int n = st->n, pairs = n * (n - 1) / 2;
-                for (int q = t; q < pairs; q += ex.T) {
-                    // q -> (i<j): row-major over the strict upper triangle
-                    int i = 0, rem = q;
-                    while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
-                    regulate_pair(c, i, i + 1 + rem);
-                }
+            ex.parn(n, [&](int t) { regulate_predict(c, t); });
+            ex.parn(n * (n - 1) / 2, [&](int q) {
+                // q -> (i<j): row-major over the strict upper triangle
+                int i = 0, rem = q;
+                while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+                regulate_pair(c, i, i + 1 + rem);
             });
-            ex.par([&](int t) { regulate_apply(c, t); });
+            ex.parn(n, [&](int t) { regulate_apply(c, t); });
         }
     }
-    ex.par([&](int t) { integrate(c, t); });
-    ex.par([&](int t) {
-        collide(c, t);
-        if (t == 0) { st->steps += 1; if (sc->cfg.regulated) st->road_steps += 1; }
-    });
+    ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; });
+    ex.parn(n, [&](int t) { integrate(c, ex, t); });
+    collide_all(c, ex);
+    if (ex.first()) { st->steps += 1; if (sc->cfg.regulated) st->road_steps += 1; }
+    ex.sync();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -777,12 +1010,12 @@ TT_HD double feature_of(C& c, int i, int f) {  // Vehicle.to_dict kinematics.py:
     auto* st = c.st;
     switch (f) {
         case TTRL_F_PRESENCE: return 1.0;
-        case TTRL_F_X: return st->x[i];
-        case TTRL_F_Y: return st->y[i];
-        case TTRL_F_VX: return st->v[i] * st->ch[i];
-        case TTRL_F_VY: return st->v[i] * st->sh[i];
-        case TTRL_F_COS_H: return st->ch[i];
-        case TTRL_F_SIN_H: return st->sh[i];
+        case TTRL_F_X: return st->pos[i].x;
+        case TTRL_F_Y: return st->pos[i].y;
+        case TTRL_F_VX: return st->v[i] * st->cs[i].x;
+        case TTRL_F_VY: return st->v[i] * st->cs[i].y;
+        case TTRL_F_COS_H: return st->cs[i].x;
+        case TTRL_F_SIN_H: return st->cs[i].y;
         case TTRL_F_HEADING: return st->h[i];
     }
     return 0.0;
@@ -798,11 +1031,11 @@ TT_HD void observe_kinematics(C& c, Exec& ex, float* out, const int32_t* inv_per
     const ttrl_config& cfg = c.sc->cfg;
     const int Vo = cfg.obs_vehicles, Fe = cfg.n_features;
     const int ego = st->ego, le = st->lane[ego];
+    ex.parn(Vo * Fe, [&](int k) { c.obs_s[k] = 0.0f; });
     ex.par([&](int t) {
-        for (int k = t; k < Vo * Fe; k += ex.T) c.obs_s[k] = 0.0f;
         int cand = 0;
         if (t < st->n && t != ego) {
-            const double dx = st->x[t] - st->x[ego], dy = st->y[t] - st->y[ego];
+            const double dx = st->pos[t].x - st->pos[ego].x, dy = st->pos[t].y - st->pos[ego].y;
             if (sqrt(dx * dx + dy * dy) < 5.0 * 40.0) {  // PERCEPTION_DISTANCE abstract.py:41
                 const double d = S_(c, t, le) - S_(c, ego, le);
                 if (cfg.see_behind || -2 * kVehLength < d) cand = 1;
@@ -810,7 +1043,7 @@ TT_HD void observe_kinematics(C& c, Exec& ex, float* out, const int32_t* inv_per
         }
         st->mark[t] = cand;
     });
-    ex.par([&](int t) {
+    ex.parn(st->n, [&](int t) {
         int row = -1;
         if (t == ego) row = 0;
         else if (st->mark[t]) {
@@ -838,7 +1071,7 @@ TT_HD void observe_kinematics(C& c, Exec& ex, float* out, const int32_t* inv_per
             }
         }
     });
-    ex.par([&](int t) { for (int k = t; k < Vo * Fe; k += ex.T) out[k] = c.obs_s[k]; });
+    ex.parn(Vo * Fe, [&](int k) { out[k] = c.obs_s[k]; });
 }
 
 // OccupancyGridObservation.observe observation.py:353-412.  The reference writes vehicles in REVERSE list order
@@ -847,7 +1080,7 @@ template <class C>
 TT_HD bool grid_cell_of(C& c, double px, double py, int& ci, int& cj) {  // pos_to_index :414-434 (already relative)
     const ttrl_config& cfg = c.sc->cfg;
     if (cfg.align_to_vehicle_axes) {
-        const double ca = c.st->ch[c.st->ego], sa = c.st->sh[c.st->ego];
+        const double ca = c.st->cs[c.st->ego].x, sa = c.st->cs[c.st->ego].y;
         const double qx = ca * px + sa * py, qy = -sa * px + ca * py;
         px = qx;
         py = qy;
@@ -864,14 +1097,12 @@ TT_HD void observe_grid(C& c, Exec& ex, float* out) {
     auto* st = c.st;
     const ttrl_config& cfg = c.sc->cfg;
     const int W = cfg.grid_w, H = cfg.grid_h, Fe = cfg.n_features, ego = st->ego;
-    ex.par([&](int t) {
-        for (int k = t; k < W * H; k += ex.T) c.cell[k] = 0x7fffffff;
-        for (int k = t; k < Fe * W * H; k += ex.T) out[k] = 0.0f;
-    });
+    ex.parn(W * H, [&](int k) { c.cell[k] = 0x7fffffff; });
+    ex.parn(Fe * W * H, [&](int k) { out[k] = 0.0f; });
     ex.par([&](int t) {
         st->mark[t] = -1;
         if (t < st->n) {
-            double x = st->x[t] - st->x[ego], y = st->y[t] - st->y[ego];
+            double x = st->pos[t].x - st->pos[ego].x, y = st->pos[t].y - st->pos[ego].y;
             if (cfg.grid_has_xrange) { x = lmap(x, cfg.grid_xrange[0], cfg.grid_xrange[1], -1.0, 1.0); x = lmap(x, -1.0, 1.0, cfg.grid_xrange[0], cfg.grid_xrange[1]); }
             if (cfg.grid_has_yrange) { y = lmap(y, cfg.grid_yrange[0], cfg.grid_yrange[1], -1.0, 1.0); y = lmap(y, -1.0, 1.0, cfg.grid_yrange[0], cfg.grid_yrange[1]); }
             int ci, cj;
@@ -881,7 +1112,7 @@ TT_HD void observe_grid(C& c, Exec& ex, float* out) {
             }
         }
     });
-    ex.par([&](int t) {
+    ex.parn(st->n, [&](int t) {
         const int cellid = st->mark[t];
         if (cellid >= 0 && c.cell[cellid] == t) {
             for (int layer = 0; layer < Fe; ++layer) {
@@ -894,25 +1125,25 @@ TT_HD void observe_grid(C& c, Exec& ex, float* out) {
                 out[layer * W * H + cellid] = (float)val;
             }
         }
-        // on_road layer: fill_road_layer_by_lanes :453-483 (waypoints every min(grid_step) within +-100 m)
-        for (int layer = 0; layer < Fe; ++layer) {
-            if (cfg.features[layer] != TTRL_F_ON_ROAD) continue;
-            const double spacing = fmin(cfg.grid_step[0], cfg.grid_step[1]);
-            for (int li = 0; li < c.L; ++li) {
-                const ttrl_lane& l = c.lanes[li];
-                const double origin = S_(c, ego, li);
-                const double start = origin - 100.0, stop = origin + 100.0;
-                const int nw = (int)ceil((stop - start) / spacing);
-                for (int w = t; w < nw; w += ex.T) {
-                    const double wp = clipd(start + w * spacing, 0.0, l.length);
-                    double px, py;
-                    lane_position(l, wp, 0.0, px, py);
-                    int ci, cj;
-                    if (grid_cell_of(c, px - st->x[ego], py - st->y[ego], ci, cj)) out[layer * W * H + ci * H + cj] = 1.0f;
-                }
-            }
-        }
     });
+    // on_road layer: fill_road_layer_by_lanes :453-483 (waypoints every min(grid_step) within +-100 m)
+    for (int layer = 0; layer < Fe; ++layer) {
+        if (cfg.features[layer] != TTRL_F_ON_ROAD) continue;
+        const double spacing = fmin(cfg.grid_step[0], cfg.grid_step[1]);
+        const int nw = (int)ceil(200.0 / spacing) + 1;  // task bound; the exact per-lane count is applied below
+        ex.parn(c.L * nw, [&](int k) {
+            const int li = k / nw, w = k - li * nw;
+            const ttrl_lane& l = c.lanes[li];
+            const double origin = S_(c, ego, li);
+            const double start = origin - 100.0, stop = origin + 100.0;
+            if (w >= (int)ceil((stop - start) / spacing)) return;
+            const double wp = clipd(start + w * spacing, 0.0, l.length);
+            double px, py;
+            lane_position(l, wp, 0.0, px, py);
+            int ci, cj;
+            if (grid_cell_of(c, px - st->pos[ego].x, py - st->pos[ego].y, ci, cj)) out[layer * W * H + ci * H + cj] = 1.0f;
+        });
+    }
 }
 template <class C, class Exec>
 TT_HD void observe(C& c, Exec& ex, float* out, const int32_t* inv_perm) {
@@ -976,24 +1207,24 @@ struct SlotRegs {
 template <class C>
 TT_HD void slot_read(C& c, int t, SlotRegs& r) {
     auto* st = c.st;
-    r.d[0] = st->x[t]; r.d[1] = st->y[t]; r.d[2] = st->h[t]; r.d[3] = st->v[t]; r.d[4] = st->ch[t]; r.d[5] = st->sh[t];
+    r.d[0] = st->pos[t].x; r.d[1] = st->pos[t].y; r.d[2] = st->h[t]; r.d[3] = st->v[t]; r.d[4] = st->cs[t].x; r.d[5] = st->cs[t].y;
     r.d[6] = st->steer[t]; r.d[7] = st->acc[t]; r.d[8] = st->tspeed[t]; r.d[9] = st->timer[t]; r.d[10] = st->delta[t];
-    r.d[11] = st->impx[t]; r.d[12] = st->impy[t];
+    r.d[11] = st->imp[t].x; r.d[12] = st->imp[t].y;
     r.i[0] = st->lane[t]; r.i[1] = st->tlane[t]; r.i[2] = st->flags[t]; r.i[3] = st->sidx[t]; r.i[4] = st->rlen[t]; r.i[5] = st->ytimer[t];
     r.u[0] = st->rroad[t]; r.u[1] = st->rlanew[t];
 }
 template <class C>
 TT_HD void slot_write(C& c, int t, const SlotRegs& r) {
     auto* st = c.st;
-    st->x[t] = r.d[0]; st->y[t] = r.d[1]; st->h[t] = r.d[2]; st->v[t] = r.d[3]; st->ch[t] = r.d[4]; st->sh[t] = r.d[5];
+    st->pos[t] = d2{r.d[0], r.d[1]}; st->h[t] = r.d[2]; st->v[t] = r.d[3]; st->cs[t] = d2{r.d[4], r.d[5]};
     st->steer[t] = r.d[6]; st->acc[t] = r.d[7]; st->tspeed[t] = r.d[8]; st->timer[t] = r.d[9]; st->delta[t] = r.d[10];
-    st->impx[t] = r.d[11]; st->impy[t] = r.d[12];
+    st->imp[t] = d2{r.d[11], r.d[12]};
     st->lane[t] = r.i[0]; st->tlane[t] = r.i[1]; st->flags[t] = r.i[2]; st->sidx[t] = r.i[3]; st->rlen[t] = r.i[4]; st->ytimer[t] = r.i[5];
     st->rroad[t] = r.u[0]; st->rlanew[t] = r.u[1];
 }
 
 // Stable compaction of the vehicle list (order preserved like the list comprehension at :357-362).
-// NB: table rows are NOT moved; callers rebuild the table before its next use.
+// NB: table rows / lane masks are NOT moved; callers rebuild them before their next use.
 template <class C, class Exec>
 TT_HD void clear_vehicles(C& c, Exec& ex) {
     auto* st = c.st;
@@ -1026,7 +1257,8 @@ TT_HD void clear_vehicles(C& c, Exec& ex) {
             }
             if (t == 0) { int tot = 0; for (int k = 0; k < st->n; ++k) tot += st->mark[k]; st->flag1 = tot; }
         });
-    ex.par([&](int t) { if (t == 0) { st->ego = st->flag0; st->n = st->flag1; } });
+    if (ex.first()) { st->ego = st->flag0; st->n = st->flag1; }
+    ex.sync();
 }
 
 struct SpawnParams {
@@ -1039,7 +1271,8 @@ template <class C, class Exec>
 TT_HD void spawn_vehicle(C& c, Exec& ex, const ttrl_spawn_draw& d, const SpawnParams& sp) {
     auto* st = c.st;
     const SceneDev* sc = c.sc;
-    ex.par([&](int t) { if (t == 0) st->flag0 = 0; });
+    if (ex.first()) st->flag0 = 0;
+    ex.sync();
     if (d.u_spawn > sp.spawn_probability) return;  // uniform: d is per-env
     const int entry = d.entry, exit_ = sp.go_straight ? (d.entry + 2) % 4 : d.exit;
     const ttrl_lane& l = c.lanes[sc->spawn_lane[entry]];
@@ -1048,19 +1281,18 @@ TT_HD void spawn_vehicle(C& c, Exec& ex, const ttrl_spawn_draw& d, const SpawnPa
     double px, py;
     lane_position(l, lon, 0.0, px, py);
     const double hd = lane_heading_at(l, lon);
-    const bool too_close = ex.any([&](int t) {
-        if (t >= st->n) return false;
-        const double dx = st->x[t] - px, dy = st->y[t] - py;
+    const bool too_close = ex.any(st->n, [&](int t) {
+        const double dx = st->pos[t].x - px, dy = st->pos[t].y - py;
         return sqrt(dx * dx + dy * dy) < 15;
     });
     if (too_close || st->n >= c.vcap) return;
-    ex.par([&](int t) {
-        if (t != 0) return;
+    if (ex.first()) {
         const int s = st->n;
-        st->x[s] = px; st->y[s] = py; st->h[s] = hd; st->v[s] = speed;
-        st->ch[s] = cos(hd); st->sh[s] = sin(hd);
-        st->steer[s] = 0; st->acc[s] = 0; st->impx[s] = 0; st->impy[s] = 0;
-        const int ln = table_row_and_closest(c, s);  // RoadObject.__init__ objects.py:45-50
+        st->pos[s] = d2{px, py}; st->h[s] = hd; st->v[s] = speed;
+        st->cs[s] = d2{cos(hd), sin(hd)};
+        st->steer[s] = 0; st->acc[s] = 0; st->imp[s] = d2{0, 0};
+        uint64_t m;
+        const int ln = table_row_and_closest(c, s, m);  // RoadObject.__init__ objects.py:45-50
         st->lane[s] = ln; st->tlane[s] = ln;         // controller.py:46
         st->tspeed[s] = speed;                       // controller.py:47
         st->timer[s] = py_mod1((px + py) * kPi);     // behavior.py:64
@@ -1075,11 +1307,12 @@ TT_HD void spawn_vehicle(C& c, Exec& ex, const ttrl_spawn_draw& d, const SpawnPa
         st->rlen[s] = 1 + nr; st->rroad[s] = rr; st->rlanew[s] = rl;
         st->n = s + 1;
         st->flag0 = 1;
-    });
+    }
+    ex.sync();
 }
 
 // ------------------------------------------------------------------------------------------------
-// global <-> shared state movement (coalesced: thread t moves slot t of every field)
+// global <-> shared state movement (coalesced: consecutive threads move consecutive slots of a field)
 // ------------------------------------------------------------------------------------------------
 struct GlobalState {
     double* vd;   // [ND][E][V]
@@ -1093,69 +1326,75 @@ template <class C, class Exec>
 TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
     auto* st = c.st;
     const int V = g.V;
+    if (ex.first()) {
+        st->n = g.ei[TTRL_EI_NVEH * g.E + e]; st->steps = g.ei[TTRL_EI_STEPS * g.E + e];
+        st->road_steps = g.ei[TTRL_EI_ROAD_STEPS * g.E + e]; st->ego = g.ei[TTRL_EI_EGO * g.E + e];
+        st->episode = g.ei[TTRL_EI_EPISODE * g.E + e]; st->done = g.ei[TTRL_EI_DONE * g.E + e];
+        st->time = g.ed[TTRL_ED_TIME * g.E + e]; st->ret = g.ed[TTRL_ED_RETURN * g.E + e];
+        st->n_chg = st->n_mob = st->n_pair = st->n_w = st->overflow = 0;
+    }
     ex.par([&](int t) {
-        if (t == 0) {
-            st->n = g.ei[TTRL_EI_NVEH * g.E + e]; st->steps = g.ei[TTRL_EI_STEPS * g.E + e];
-            st->road_steps = g.ei[TTRL_EI_ROAD_STEPS * g.E + e]; st->ego = g.ei[TTRL_EI_EGO * g.E + e];
-            st->episode = g.ei[TTRL_EI_EPISODE * g.E + e]; st->done = g.ei[TTRL_EI_DONE * g.E + e];
-            st->time = g.ed[TTRL_ED_TIME * g.E + e]; st->ret = g.ed[TTRL_ED_RETURN * g.E + e];
-        }
         if (t < V) {
             const size_t o = (size_t)e * V + t, fs = (size_t)g.E * V;
-            st->x[t] = g.vd[TTRL_D_X * fs + o]; st->y[t] = g.vd[TTRL_D_Y * fs + o];
+            st->pos[t] = d2{g.vd[TTRL_D_X * fs + o], g.vd[TTRL_D_Y * fs + o]};
             const double hd = g.vd[TTRL_D_HEADING * fs + o];
-            st->h[t] = hd; st->ch[t] = cos(hd); st->sh[t] = sin(hd);
+            double sn, cn;
+            sincos(hd, &sn, &cn);
+            st->h[t] = hd; st->cs[t] = d2{cn, sn};
             st->v[t] = g.vd[TTRL_D_SPEED * fs + o];
             st->steer[t] = g.vd[TTRL_D_STEERING * fs + o]; st->acc[t] = g.vd[TTRL_D_ACCEL * fs + o];
             st->tspeed[t] = g.vd[TTRL_D_TARGET_SPEED * fs + o]; st->timer[t] = g.vd[TTRL_D_TIMER * fs + o];
             st->delta[t] = g.vd[TTRL_D_DELTA * fs + o];
-            st->impx[t] = g.vd[TTRL_D_IMPACT_X * fs + o]; st->impy[t] = g.vd[TTRL_D_IMPACT_Y * fs + o];
+            st->imp[t] = d2{g.vd[TTRL_D_IMPACT_X * fs + o], g.vd[TTRL_D_IMPACT_Y * fs + o]};
             st->lane[t] = g.vi[TTRL_I_LANE * fs + o]; st->tlane[t] = g.vi[TTRL_I_TARGET_LANE * fs + o];
             st->flags[t] = g.vi[TTRL_I_FLAGS * fs + o]; st->sidx[t] = g.vi[TTRL_I_SPEED_INDEX * fs + o];
             st->rlen[t] = g.vi[TTRL_I_ROUTE_LEN * fs + o];
             st->rroad[t] = (uint32_t)g.vi[TTRL_I_ROUTE_ROAD * fs + o]; st->rlanew[t] = (uint32_t)g.vi[TTRL_I_ROUTE_LANE * fs + o];
             st->ytimer[t] = g.vi[TTRL_I_YIELD_TIMER * fs + o];
         } else {
-            st->x[t] = st->y[t] = st->h[t] = st->v[t] = st->sh[t] = st->steer[t] = st->acc[t] = 0; st->ch[t] = 1;
-            st->tspeed[t] = st->timer[t] = st->delta[t] = st->impx[t] = st->impy[t] = 0;
+            st->pos[t] = d2{0, 0}; st->cs[t] = d2{1, 0}; st->imp[t] = d2{0, 0};
+            st->h[t] = st->v[t] = st->steer[t] = st->acc[t] = 0;
+            st->tspeed[t] = st->timer[t] = st->delta[t] = 0;
             st->lane[t] = st->tlane[t] = st->flags[t] = st->sidx[t] = st->rlen[t] = st->ytimer[t] = 0;
             st->rroad[t] = st->rlanew[t] = 0;
         }
-        st->mark[t] = 0; st->tl_old[t] = 0;
+        st->mark[t] = 0; st->tl_old[t] = 0; st->acc2[t] = 0; st->best[t] = -1; st->fo[t] = -1;
+        // pre-check guard from the loaded speed (integrate refreshes it every sub-step)
+        const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
+        const double thr = (diag + diag) / 2 + st->v[t] * c.sc->dt;
+        st->thr2[t] = thr < 0 ? -1.0 : thr * thr * (1.0 + 1e-12);
     });
     // the table is a pure function of positions: rebuild it instead of storing it
-    ex.par([&](int t) { if (t < st->n) (void)table_row_and_closest(c, t); });
+    rebuild_tables(c, ex);
 }
 template <class C, class Exec>
 TT_HD void store_env(C& c, Exec& ex, const GlobalState& g, int e) {
     auto* st = c.st;
     const int V = g.V;
-    ex.par([&](int t) {
-        if (t == 0) {
-            g.ei[TTRL_EI_NVEH * g.E + e] = st->n; g.ei[TTRL_EI_STEPS * g.E + e] = st->steps;
-            g.ei[TTRL_EI_ROAD_STEPS * g.E + e] = st->road_steps; g.ei[TTRL_EI_EGO * g.E + e] = st->ego;
-            g.ei[TTRL_EI_EPISODE * g.E + e] = st->episode; g.ei[TTRL_EI_DONE * g.E + e] = st->done;
-            g.ed[TTRL_ED_TIME * g.E + e] = st->time; g.ed[TTRL_ED_RETURN * g.E + e] = st->ret;
-        }
-        if (t < V) {
-            const size_t o = (size_t)e * V + t, fs = (size_t)g.E * V;
-            const bool live = t < st->n;
-            const int rlen = live ? st->rlen[t] : 0;
-            // canonical form: dead slots zero, unused route bytes zero (keeps get_state comparable bit for bit)
-            const uint32_t keep = rlen >= 4 ? 0xFFFFFFFFu : (rlen <= 0 ? 0u : ((1u << (8 * rlen)) - 1u));
-            g.vd[TTRL_D_X * fs + o] = live ? st->x[t] : 0; g.vd[TTRL_D_Y * fs + o] = live ? st->y[t] : 0;
-            g.vd[TTRL_D_HEADING * fs + o] = live ? st->h[t] : 0; g.vd[TTRL_D_SPEED * fs + o] = live ? st->v[t] : 0;
-            g.vd[TTRL_D_STEERING * fs + o] = live ? st->steer[t] : 0; g.vd[TTRL_D_ACCEL * fs + o] = live ? st->acc[t] : 0;
-            g.vd[TTRL_D_TARGET_SPEED * fs + o] = live ? st->tspeed[t] : 0; g.vd[TTRL_D_TIMER * fs + o] = live ? st->timer[t] : 0;
-            g.vd[TTRL_D_DELTA * fs + o] = live ? st->delta[t] : 0;
-            g.vd[TTRL_D_IMPACT_X * fs + o] = live ? st->impx[t] : 0; g.vd[TTRL_D_IMPACT_Y * fs + o] = live ? st->impy[t] : 0;
-            g.vi[TTRL_I_LANE * fs + o] = live ? st->lane[t] : 0; g.vi[TTRL_I_TARGET_LANE * fs + o] = live ? st->tlane[t] : 0;
-            g.vi[TTRL_I_FLAGS * fs + o] = live ? st->flags[t] : 0; g.vi[TTRL_I_SPEED_INDEX * fs + o] = live ? st->sidx[t] : 0;
-            g.vi[TTRL_I_ROUTE_LEN * fs + o] = rlen;
-            g.vi[TTRL_I_ROUTE_ROAD * fs + o] = (int32_t)(live ? st->rroad[t] & keep : 0u);
-            g.vi[TTRL_I_ROUTE_LANE * fs + o] = (int32_t)(live ? st->rlanew[t] & keep : 0u);
-            g.vi[TTRL_I_YIELD_TIMER * fs + o] = live ? st->ytimer[t] : 0;
-        }
+    if (ex.first()) {
+        g.ei[TTRL_EI_NVEH * g.E + e] = st->n; g.ei[TTRL_EI_STEPS * g.E + e] = st->steps;
+        g.ei[TTRL_EI_ROAD_STEPS * g.E + e] = st->road_steps; g.ei[TTRL_EI_EGO * g.E + e] = st->ego;
+        g.ei[TTRL_EI_EPISODE * g.E + e] = st->episode; g.ei[TTRL_EI_DONE * g.E + e] = st->done;
+        g.ed[TTRL_ED_TIME * g.E + e] = st->time; g.ed[TTRL_ED_RETURN * g.E + e] = st->ret;
+    }
+    ex.parn(V, [&](int t) {
+        const size_t o = (size_t)e * V + t, fs = (size_t)g.E * V;
+        const bool live = t < st->n;
+        const int rlen = live ? st->rlen[t] : 0;
+        // canonical form: dead slots zero, unused route bytes zero (keeps get_state comparable bit for bit)
+        const uint32_t keep = rlen >= 4 ? 0xFFFFFFFFu : (rlen <= 0 ? 0u : ((1u << (8 * rlen)) - 1u));
+        g.vd[TTRL_D_X * fs + o] = live ? st->pos[t].x : 0; g.vd[TTRL_D_Y * fs + o] = live ? st->pos[t].y : 0;
+        g.vd[TTRL_D_HEADING * fs + o] = live ? st->h[t] : 0; g.vd[TTRL_D_SPEED * fs + o] = live ? st->v[t] : 0;
+        g.vd[TTRL_D_STEERING * fs + o] = live ? st->steer[t] : 0; g.vd[TTRL_D_ACCEL * fs + o] = live ? st->acc[t] : 0;
+        g.vd[TTRL_D_TARGET_SPEED * fs + o] = live ? st->tspeed[t] : 0; g.vd[TTRL_D_TIMER * fs + o] = live ? st->timer[t] : 0;
+        g.vd[TTRL_D_DELTA * fs + o] = live ? st->delta[t] : 0;
+        g.vd[TTRL_D_IMPACT_X * fs + o] = live ? st->imp[t].x : 0; g.vd[TTRL_D_IMPACT_Y * fs + o] = live ? st->imp[t].y : 0;
+        g.vi[TTRL_I_LANE * fs + o] = live ? st->lane[t] : 0; g.vi[TTRL_I_TARGET_LANE * fs + o] = live ? st->tlane[t] : 0;
+        g.vi[TTRL_I_FLAGS * fs + o] = live ? st->flags[t] : 0; g.vi[TTRL_I_SPEED_INDEX * fs + o] = live ? st->sidx[t] : 0;
+        g.vi[TTRL_I_ROUTE_LEN * fs + o] = rlen;
+        g.vi[TTRL_I_ROUTE_ROAD * fs + o] = (int32_t)(live ? st->rroad[t] & keep : 0u);
+        g.vi[TTRL_I_ROUTE_LANE * fs + o] = (int32_t)(live ? st->rlanew[t] & keep : 0u);
+        g.vi[TTRL_I_YIELD_TIMER * fs + o] = live ? st->ytimer[t] : 0;
     });
 }
 
@@ -1177,7 +1416,7 @@ TT_HD double u01(uint32_t hi, uint32_t lo) {  // 53-bit uniform in [0,1)
     const uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
     return (double)x * (1.0 / 9007199254740992.0);
 }
-TT_HD void device_spawn_draw(uint64_t seed, int64_t global_env, uint64_t counter, ttrl_spawn_draw& d) {
+TT_HDN void device_spawn_draw(uint64_t seed, int64_t global_env, uint64_t counter, ttrl_spawn_draw& d) {
     uint32_t a[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), (uint32_t)counter, 0u};
     uint32_t b[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), (uint32_t)counter, 1u};
     uint32_t e[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), (uint32_t)counter, 2u};
@@ -1222,7 +1461,8 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
     const ttrl_config& cfg = sc->cfg;
     load_env(c, ex, g, e);
     const int action = io.actions ? io.actions[e] : -1;
-    ex.par([&](int t) { if (t == 0) st->time += 1 / cfg.policy_frequency; });
+    if (ex.first()) st->time += 1 / cfg.policy_frequency;
+    ex.sync();
     double veh_steps = 0;
     for (int f = 0; f < sc->F; ++f) {
         env_substep(c, ex, action);
@@ -1231,9 +1471,8 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
     float* obs = io.obs ? io.obs + (size_t)e * io.obs_size : nullptr;
     const int32_t* perm = io.inv_perm ? io.inv_perm + (size_t)e * (cfg.obs_vehicles - 1) : nullptr;
     if (obs) observe(c, ex, obs, perm);
-    // reward / flags / episode accounting by thread 0
-    ex.par([&](int t) {
-        if (t != 0) return;
+    // reward / flags / episode accounting by the first thread
+    if (ex.first()) {
         const int ego = st->ego;
         const double r = agent_reward(c, ego);
         const bool term = is_terminated(c), trunc = st->time >= cfg.duration;
@@ -1256,7 +1495,8 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
                 s[4 * E] += (cfg.reward_type == TTRL_REWARD_INTERSECTION && has_arrived(c, ego)) ? 1 : 0;
             }
         }
-    });
+    }
+    ex.sync();
     if (cfg.spawn_enabled) {
         clear_vehicles(c, ex);
         ttrl_spawn_draw d;
@@ -1266,16 +1506,19 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
         if (have) {
             SpawnParams sp{0.0, 1.0, 1.0, cfg.spawn_probability, 0};
             spawn_vehicle(c, ex, d, sp);
-            if (io.spawn_accepted) ex.par([&](int t) { if (t == 0) io.spawn_accepted[e] = st->flag0; });
-        } else if (io.spawn_accepted) {
-            ex.par([&](int t) { if (t == 0) io.spawn_accepted[e] = 0; });
+            if (io.spawn_accepted && ex.first()) io.spawn_accepted[e] = st->flag0;
+        } else if (io.spawn_accepted && ex.first()) {
+            io.spawn_accepted[e] = 0;
         }
+        ex.sync();
     }
     if (st->done && io.autoreset && io.pool.E > 0) {  // uniform: st->done is in shared memory
         const int episode = st->episode + 1;
         const int slot = (int)(((long long)e + (long long)episode * g.E) % io.pool.E);
+        ex.sync();
         load_env(c, ex, io.pool, slot);
-        ex.par([&](int t) { if (t == 0) { st->episode = episode; st->done = 0; } });
+        if (ex.first()) { st->episode = episode; st->done = 0; }
+        ex.sync();
         if (obs) observe(c, ex, obs, perm);
     }
     store_env(c, ex, g, e);

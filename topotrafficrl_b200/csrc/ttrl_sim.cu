@@ -15,26 +15,84 @@
 using namespace ttrl;
 
 // ------------------------------------------------------------------------------------------------
-// device execution policy: one CTA
+// device execution policy: one CTA of T threads ("team") per env; slots / tasks are strided over the team.
+// T == 32: the team is one warp, barriers are __syncwarp().
 // ------------------------------------------------------------------------------------------------
+template <int V, int T>
 struct DevExec {
-    int tid, T;
-    __device__ __forceinline__ void sync() { __syncthreads(); }
-    template <class F> __device__ __forceinline__ void par(F f) { f(tid); __syncthreads(); }
-    template <class F> __device__ __forceinline__ bool any(F f) { return __syncthreads_or(f(tid) ? 1 : 0) != 0; }
+    int tid;
+    __device__ __forceinline__ bool first() const { return tid == 0; }
+    __device__ __forceinline__ void sync() {
+        if (T == 32) __syncwarp(); else __syncthreads();
+    }
+    template <class F> __device__ __forceinline__ void par(F f) {
+#pragma unroll 1
+        for (int t = tid; t < V; t += T) f(t);
+        sync();
+    }
+    template <class F> __device__ __forceinline__ void parn(int n, F f) {
+#pragma unroll 1
+        for (int t = tid; t < n; t += T) f(t);
+        sync();
+    }
+    template <class F> __device__ __forceinline__ bool any(int n, F f) {
+        int p = 0;
+#pragma unroll 1
+        for (int t = tid; t < n; t += T) p |= f(t) ? 1 : 0;
+        if (T == 32) return __any_sync(0xffffffffu, p) != 0;
+        return __syncthreads_or(p) != 0;
+    }
     template <class F1, class F2> __device__ __forceinline__ void par2(F1 f1, F2 f2) {
-        SlotRegs r;
-        int dst;
-        f1(tid, r, dst);
-        __syncthreads();
-        f2(tid, r, dst);
-        __syncthreads();
+        constexpr int R = (V + T - 1) / T;
+        SlotRegs r[R];
+        int dst[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) { dst[k] = -1; if (tid + k * T < V) f1(tid + k * T, r[k], dst[k]); }
+        sync();
+#pragma unroll
+        for (int k = 0; k < R; ++k) if (tid + k * T < V) f2(tid + k * T, r[k], dst[k]);
+        sync();
+    }
+    // 8 lanes per candidate pair, one separating axis each; the pair's result is reduced with shuffles:
+    // intersecting / will_intersect = no lane reports a separation, translation axis = first axis of minimal absd.
+    template <class FA, class FP> __device__ __forceinline__ void sat_pairs(int np, FA fa, FP fp) {
+        const int total = np * 8;
+#pragma unroll 1
+        for (int base = 0; base < total; base += T) {
+            const int idx = base + tid;
+            const bool act = idx < total;
+            const int q = idx >> 3, axis = idx & 7;
+            AxisRes r;
+            r.absd = INFINITY; r.nx = 0; r.ny = 0; r.fl = 0;
+            if (act) r = fa(q, axis);
+            const unsigned gbase = (unsigned)(tid & 31) & ~7u;
+            const unsigned sep_now = __ballot_sync(0xffffffffu, act && (r.fl & 1));
+            const unsigned sep_after = __ballot_sync(0xffffffffu, act && (r.fl & 2));
+            const bool inter = ((sep_now >> gbase) & 0xFFu) == 0, will = ((sep_after >> gbase) & 0xFFu) == 0;
+            double bd = r.absd;
+            int bi = axis;
+#pragma unroll
+            for (int off = 1; off < 8; off <<= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            const double nx = __shfl_sync(0xffffffffu, r.nx, (int)gbase + bi), ny = __shfl_sync(0xffffffffu, r.ny, (int)gbase + bi);
+            if (act && axis == 0) fp(q, inter, will, bd, nx, ny);
+        }
+        sync();
     }
     __device__ __forceinline__ void atomic_min(int32_t* a, int32_t v) { atomicMin(a, v); }
+    __device__ __forceinline__ void atomic_max(int32_t* a, int32_t v) { atomicMax(a, v); }
+    __device__ __forceinline__ void atomic_or(uint32_t* a, uint32_t v) { atomicOr(a, v); }
+    __device__ __forceinline__ int atomic_add(int32_t* a, int32_t v) { return atomicAdd(a, v); }
 };
 
+// threads per env for a slot capacity
+template <int V> struct TeamOf { static constexpr int T = V <= 64 ? 32 : V / 2; };
+
 struct SmemLayout {
-    int off_lanes, off_S, off_R, off_pred, off_obs, off_cell, total;
+    int off_lanes, off_SR, off_lmask, off_pred, off_obs, off_cell, total;
 };
 
 template <int V>
@@ -52,29 +110,31 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V>& c, unsigned char* smem, cons
         for (int k = threadIdx.x; k < n16; k += blockDim.x) dst[k] = __ldg(src + k);
     }
     c.lanes = lanes_s;
-    c.S = reinterpret_cast<double*>(smem + lay.off_S);
-    c.R = reinterpret_cast<double*>(smem + lay.off_R);
+    c.SR = reinterpret_cast<d2*>(smem + lay.off_SR);
+    c.lmask = reinterpret_cast<uint32_t*>(smem + lay.off_lmask);
     c.pred = lay.off_pred >= 0 ? reinterpret_cast<double*>(smem + lay.off_pred) : nullptr;
     c.obs_s = reinterpret_cast<float*>(smem + lay.off_obs);
     c.cell = reinterpret_cast<int32_t*>(smem + lay.off_cell);
+    c.gap_den = 2 * sqrt(-sc->cfg.comfort_acc_max * sc->cfg.comfort_acc_min);  // behavior.py:214-216
     __syncthreads();
 }
 
+#define TT_KERNEL_PROLOGUE                                     \
+    extern __shared__ __align__(16) unsigned char smem[];      \
+    constexpr int T = TeamOf<V>::T;                            \
+    EnvCtx<V> c;                                               \
+    make_ctx<V>(c, smem, sc, lay, g.V);                        \
+    DevExec<V, T> ex{(int)threadIdx.x};
+
 template <int V>
-__global__ void __launch_bounds__(V) k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    EnvCtx<V> c;
-    make_ctx<V>(c, smem, sc, lay, g.V);
-    DevExec ex{(int)threadIdx.x, V};
+__global__ void __launch_bounds__(TeamOf<V>::T) k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay) {
+    TT_KERNEL_PROLOGUE
     env_step(c, ex, g, io, (int)blockIdx.x);
 }
 
 template <int V>
-__global__ void __launch_bounds__(V) k_substep(const SceneDev* __restrict__ sc, GlobalState g, const int32_t* __restrict__ actions, SmemLayout lay) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    EnvCtx<V> c;
-    make_ctx<V>(c, smem, sc, lay, g.V);
-    DevExec ex{(int)threadIdx.x, V};
+__global__ void __launch_bounds__(TeamOf<V>::T) k_substep(const SceneDev* __restrict__ sc, GlobalState g, const int32_t* __restrict__ actions, SmemLayout lay) {
+    TT_KERNEL_PROLOGUE
     const int e = blockIdx.x;
     load_env(c, ex, g, e);
     env_substep(c, ex, actions ? actions[e] : -1);
@@ -82,29 +142,23 @@ __global__ void __launch_bounds__(V) k_substep(const SceneDev* __restrict__ sc, 
 }
 
 template <int V>
-__global__ void __launch_bounds__(V) k_observe(const SceneDev* __restrict__ sc, GlobalState g, float* __restrict__ obs, int obs_size,
-                                               const int32_t* __restrict__ inv_perm, SmemLayout lay) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    EnvCtx<V> c;
-    make_ctx<V>(c, smem, sc, lay, g.V);
-    DevExec ex{(int)threadIdx.x, V};
+__global__ void __launch_bounds__(TeamOf<V>::T) k_observe(const SceneDev* __restrict__ sc, GlobalState g, float* __restrict__ obs, int obs_size,
+                                                          const int32_t* __restrict__ inv_perm, SmemLayout lay) {
+    TT_KERNEL_PROLOGUE
     const int e = blockIdx.x;
     load_env(c, ex, g, e);
     observe(c, ex, obs + (size_t)e * obs_size, inv_perm ? inv_perm + (size_t)e * (sc->cfg.obs_vehicles - 1) : nullptr);
 }
 
 template <int V>
-__global__ void __launch_bounds__(V) k_spawn(const SceneDev* __restrict__ sc, GlobalState g, const ttrl_spawn_draw* __restrict__ draws,
-                                             SpawnParams sp, int32_t* __restrict__ accepted, SmemLayout lay) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    EnvCtx<V> c;
-    make_ctx<V>(c, smem, sc, lay, g.V);
-    DevExec ex{(int)threadIdx.x, V};
+__global__ void __launch_bounds__(TeamOf<V>::T) k_spawn(const SceneDev* __restrict__ sc, GlobalState g, const ttrl_spawn_draw* __restrict__ draws,
+                                                        SpawnParams sp, int32_t* __restrict__ accepted, SmemLayout lay) {
+    TT_KERNEL_PROLOGUE
     const int e = blockIdx.x;
     load_env(c, ex, g, e);
     spawn_vehicle(c, ex, draws[e], sp);
     if (accepted && threadIdx.x == 0) accepted[e] = c.st->flag0;
-    __syncthreads();
+    ex.sync();
     store_env(c, ex, g, e);
 }
 
@@ -165,8 +219,8 @@ static SmemLayout make_layout(const ttrl_config& cfg) {
     SmemLayout l{};
     size_t off = align_up(sizeof(EnvState<V>), 16);
     l.off_lanes = (int)off; off += align_up(sizeof(ttrl_lane) * cfg.n_lanes, 16);
-    l.off_S = (int)off; off += sizeof(double) * V * cfg.n_lanes;
-    l.off_R = (int)off; off += sizeof(double) * V * cfg.n_lanes;
+    l.off_SR = (int)off; off += sizeof(d2) * V * cfg.n_lanes;
+    l.off_lmask = (int)off; off += align_up(sizeof(uint32_t) * ((V + 31) / 32) * cfg.n_lanes, 16);
     if (cfg.regulated) { l.off_pred = (int)off; off += sizeof(double) * 3 * V * kPred; } else l.off_pred = -1;
     l.off_obs = (int)off; off += align_up(sizeof(float) * (cfg.obs_type == TTRL_OBS_KINEMATICS ? cfg.obs_vehicles * cfg.n_features : 4), 16);
     l.off_cell = (int)off; off += align_up(sizeof(int32_t) * (cfg.obs_type == TTRL_OBS_GRID ? cfg.grid_w * cfg.grid_h : 4), 16);
@@ -348,7 +402,7 @@ int ttrl_sim_spawn_accepted(ttrl_sim* s, int32_t* accepted_host) {
 int ttrl_sim_substep(ttrl_sim* s, const int32_t* actions_dev, void* stream) {
     CK(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_V(s, (k_substep<V><<<s->E, V, s->lay.total, st>>>(s->d_scene, s->g, actions_dev, s->lay)));
+    DISPATCH_V(s, (k_substep<V><<<s->E, TeamOf<V>::T, s->lay.total, st>>>(s->d_scene, s->g, actions_dev, s->lay)));
     s->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -365,7 +419,7 @@ static int launch_step(ttrl_sim* s, const int32_t* actions_dev, float* obs_dev, 
     io.autoreset = s->autoreset;
     io.seed = s->seed; io.first_global_env = s->first_global_env;
     io.obs_size = s->obs_size;
-    DISPATCH_V(s, (k_step<V><<<s->E, V, s->lay.total, st>>>(s->d_scene, s->g, io, s->lay)));
+    DISPATCH_V(s, (k_step<V><<<s->E, TeamOf<V>::T, s->lay.total, st>>>(s->d_scene, s->g, io, s->lay)));
     s->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -412,7 +466,7 @@ int ttrl_sim_observe(ttrl_sim* s, float* obs_dev, void* stream) {
     CK(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int32_t* perm = s->have_perm ? s->d_perm : nullptr;
-    DISPATCH_V(s, (k_observe<V><<<s->E, V, s->lay.total, st>>>(s->d_scene, s->g, obs_dev, s->obs_size, perm, s->lay)));
+    DISPATCH_V(s, (k_observe<V><<<s->E, TeamOf<V>::T, s->lay.total, st>>>(s->d_scene, s->g, obs_dev, s->obs_size, perm, s->lay)));
     s->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -424,7 +478,7 @@ int ttrl_sim_spawn(ttrl_sim* s, const ttrl_spawn_draw* draws_host, double longit
     CK(cudaSetDevice(s->device));
     CK(cudaMemcpy(s->d_draws, draws_host, sizeof(ttrl_spawn_draw) * s->E, cudaMemcpyHostToDevice));
     SpawnParams sp{longitudinal, position_deviation, speed_deviation, spawn_probability, go_straight};
-    DISPATCH_V(s, (k_spawn<V><<<s->E, V, s->lay.total, 0>>>(s->d_scene, s->g, s->d_draws, sp, s->d_accepted, s->lay)));
+    DISPATCH_V(s, (k_spawn<V><<<s->E, TeamOf<V>::T, s->lay.total, 0>>>(s->d_scene, s->g, s->d_draws, sp, s->d_accepted, s->lay)));
     s->launches++;
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
