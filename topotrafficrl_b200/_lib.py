@@ -11,7 +11,8 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libttrl_b200.so")
+# TTRL_B200_LIB selects an alternative build of the SAME CUDA library (kernel tuning experiments)
+LIB_PATH = os.environ.get("TTRL_B200_LIB") or os.path.join(_HERE, "csrc", "libttrl_b200.so")
 _lib = None
 
 

@@ -64,9 +64,9 @@ struct SceneDev {
 // Per-env state in shared memory (struct of arrays over the V slots) + task scratch.
 template <int V>
 struct alignas(16) EnvState {
-    static constexpr int MB = V < 32 ? V : 32;  // MOBIL batch: vehicles whose lane-change timer fired, per round
-    static constexpr int PQ = 4 * V;            // collision candidate pair queue
-    static constexpr int WQ = V;                // will-intersect pair list
+    static constexpr int MB = V < 16 ? V : 16;  // MOBIL batch: vehicles whose lane-change timer fired, per round
+    static constexpr int PQ = 2 * V;            // collision candidate pair queue
+    static constexpr int WQ = V / 2;            // will-intersect pair list
     d2 pos[V];   // x, y
     d2 cs[V];    // cos(heading), sin(heading)
     d2 imp[V];   // pending impact

@@ -89,7 +89,21 @@ struct DevExec {
 };
 
 // threads per env for a slot capacity
-template <int V> struct TeamOf { static constexpr int T = V <= 64 ? 32 : V / 2; };
+// Threads per env ("team") and minimum resident CTAs per SM (register cap) for a slot capacity.  Tuned on B200
+// (profiles/r1c_variants.txt): the kernel is latency-bound (fp64 dependency chains, instruction fetch), so
+// resident warps matter more than registers per thread; 2 warps per 64-slot env with >= 10 CTAs/SM is the best point.
+#ifndef TT_T64
+#define TT_T64 64
+#endif
+#ifndef TT_MINB64
+#define TT_MINB64 10
+#endif
+#ifndef TT_MINB32
+#define TT_MINB32 1
+#endif
+template <int V> struct TeamOf { static constexpr int T = V / 2, MINB = 1; };
+template <> struct TeamOf<32> { static constexpr int T = 32, MINB = TT_MINB32; };
+template <> struct TeamOf<64> { static constexpr int T = TT_T64, MINB = TT_MINB64; };
 
 struct SmemLayout {
     int off_lanes, off_SR, off_lmask, off_pred, off_obs, off_cell, total;
@@ -127,7 +141,7 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V>& c, unsigned char* smem, cons
     DevExec<V, T> ex{(int)threadIdx.x};
 
 template <int V>
-__global__ void __launch_bounds__(TeamOf<V>::T) k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay) {
+__global__ void __launch_bounds__(TeamOf<V>::T, TeamOf<V>::MINB) k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay) {
     TT_KERNEL_PROLOGUE
     env_step(c, ex, g, io, (int)blockIdx.x);
 }
