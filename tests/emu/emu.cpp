@@ -68,6 +68,7 @@ struct HostEnv {
         c.pred = cfg.regulated ? pred.data() : nullptr; c.obs_s = obs_s.data(); c.cell = cell.data();
         c.L = cfg.n_lanes; c.vcap = vcap;
         c.gap_den = 2 * sqrt(-cfg.comfort_acc_max * cfg.comfort_acc_min);
+        c.tan_max_steer = tan(kPi / 3);
     }
 };
 

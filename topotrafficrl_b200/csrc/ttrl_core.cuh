@@ -75,6 +75,7 @@ struct alignas(16) EnvState {
     double steer[V], acc[V], tspeed[V], timer[V], delta[V];
     double thr2[V];      // collision pre-check guard: (diag + v dt)^2 (1 + 1e-12), or -1 when diag + v dt < 0
     double acc2[V];      // IDM acceleration w.r.t. the target lane (vehicles changing lane)
+    double tsteer[V];    // tan(steering command) of this sub-step (by-product of steering_control, used by integrate)
     double mq_a[9 * MB];  // MOBIL IDM evaluations of the batch
     int32_t lane[V], tlane[V], flags[V], sidx[V], rlen[V], ytimer[V];
     uint32_t rroad[V], rlanew[V];
@@ -85,6 +86,7 @@ struct alignas(16) EnvState {
     int32_t pairq[PQ];   // lo | hi << 16
     int32_t wpair[WQ];
     int16_t fo[V];       // front neighbour on the own lane
+    uint32_t bmask[(V + 31) / 32];  // vehicles in an ongoing lane change on the same road (phase B), list order = bit order
     int16_t mq_f[3 * MB], mq_r[3 * MB];  // MOBIL neighbour queries: own lane, left candidate, right candidate
     int32_t n, steps, road_steps, ego, episode, done, flag0, flag1;
     int32_t n_chg, n_mob, n_pair, n_w, overflow, pad0;
@@ -106,6 +108,7 @@ struct EnvCtx {
     int L;
     int vcap;                // storage capacity (slots per env in HBM), <= V
     double gap_den;          // 2 sqrt(-COMFORT_ACC_MAX COMFORT_ACC_MIN) (behavior.py:214-216)
+    double tan_max_steer;    // tan(MAX_STEERING_ANGLE)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -329,9 +332,11 @@ TT_HD void follow_road(C& c, int i) {
     if (S_(c, i, tl) > c.lanes[tl].length - kVehLength / 2) c.st->tlane[i] = next_lane(c, i, tl);
 }
 
-// ControlledVehicle.steering_control controller.py:145-187
+// ControlledVehicle.steering_control controller.py:145-187, clipped to +-MAX_STEERING_ANGLE (controller.py:131).
+// tan(asin(w)) is evaluated as w / sqrt((1-w)(1+w)) (same value to a few ulp, no asin/tan pair), and the tangent of
+// the returned command comes out as a by-product for Vehicle.step's beta = atan(tan(delta) / 2).
 template <class C>
-TT_HDN double steering_control(C& c, int i, int target_lane) {
+TT_HDN double steering_control(C& c, int i, int target_lane, double& tan_steer) {
     const double TAU_PURSUIT = 0.5 * 0.2, KP_LATERAL = 1 / 0.6, KP_HEADING = 1 / 0.2;
     const double MAX_STEER = kPi / 3;
     const ttrl_lane& tl = c.lanes[target_lane];
@@ -343,9 +348,13 @@ TT_HDN double steering_control(C& c, int i, int target_lane) {
     double heading_command = asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
     double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
     double heading_rate_command = KP_HEADING * wrap_to_pi(heading_ref - c.st->h[i]);
-    double slip_angle = asin(clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0));
-    double steering_angle = atan(2 * tan(slip_angle));
-    return clipd(steering_angle, -MAX_STEER, MAX_STEER);
+    const double w = clipd(kVehLength / 2 / not_zero(speed) * heading_rate_command, -1.0, 1.0);  // sin(slip_angle)
+    const double tan2 = 2 * (w / sqrt((1 - w) * (1 + w)));                                      // 2 tan(slip_angle)
+    double steering_angle = atan(tan2);
+    if (steering_angle > MAX_STEER) { tan_steer = c.tan_max_steer; return MAX_STEER; }
+    if (steering_angle < -MAX_STEER) { tan_steer = -c.tan_max_steer; return -MAX_STEER; }
+    tan_steer = tan2;
+    return steering_angle;
 }
 
 // MDPVehicle.speed_to_index controller.py:326-344 (np.round -> round half to even -> rint)
@@ -444,7 +453,8 @@ TT_HDN double idm_acceleration(C& c, double self_delta, int ego, int front) {
     auto* st = c.st;
     const int le = st->lane[ego];
     const double ts = clipd(st->tspeed[ego], 0.0, c.lanes[le].speed_limit);
-    double acc = cfg.comfort_acc_max * (1 - pow(fmax(st->v[ego], 0.0) / fabs(not_zero(ts)), self_delta));
+    // np.power(x, delta) for x >= 0, delta in [3.5, 4.5] as exp(delta log x): a few ulp from pow, a third of its cost
+    double acc = cfg.comfort_acc_max * (1 - exp(self_delta * log(fmax(st->v[ego], 0.0) / fabs(not_zero(ts)))));
     if (front >= 0) {
         const double d = S_(c, front, le) - S_(c, ego, le);  // lane_distance_to objects.py:182-197
         const double q = desired_gap(c, ego, front) / not_zero(d);
@@ -482,7 +492,7 @@ TT_HD void act_phase_a(C& c, Exec& ex, int i, int first_action) {
     follow_road(c, i);
     const int ln = st->lane[i];
     if (ln != st->tlane[i]) {  // ongoing change: behavior.py:229-244, resolved in phase B
-        if (c.lanes[ln].road == c.lanes[st->tlane[i]].road) st->mark[i] = 1;
+        if (c.lanes[ln].road == c.lanes[st->tlane[i]].road) ex.atomic_or(&st->bmask[i >> 5], 1u << (i & 31));
         return;
     }
     if (!(c.sc->cfg.lane_change_delay < st->timer[i])) return;  // utils.do_every utils.py:25-26
@@ -577,13 +587,13 @@ TT_HD bool abort_pred(C& c, int i, int j) {
 template <class C, class Exec>
 TT_HD void act_phase_c1(C& c, Exec& ex, int i) {
     auto* st = c.st;
-    const double MAX_STEER = kPi / 3;
     const int fl = st->flags[i];
     st->fo[i] = -1;
     if (!(fl & TTRL_FL_MDP) && (fl & TTRL_FL_CRASHED)) return;  // IDMVehicle.act returns early when crashed
     const int tl = st->tlane[i];
-    const double steering = clipd(steering_control(c, i, tl), -MAX_STEER, MAX_STEER);  // controller.py:131, behavior.py:114-116
-    st->steer[i] = steering;
+    double tan_steer;
+    st->steer[i] = steering_control(c, i, tl, tan_steer);  // clipped: controller.py:131, behavior.py:114-116
+    st->tsteer[i] = tan_steer;
     if (fl & TTRL_FL_MDP) {
         st->acc[i] = (1 / 0.6) * (st->tspeed[i] - st->v[i]);  // speed_control controller.py:189-198
         return;
@@ -636,11 +646,12 @@ TT_HD void integrate(C& c, Exec& ex, int i) {
     else if (speed < -40.0) acc = fmax(acc, 1.0 * (-40.0 - speed));
     st->steer[i] = steer;
     st->acc[i] = acc;
-    const double beta = atan(1.0 / 2 * tan(steer));
+    // beta = arctan(1/2 tan(delta)) (kinematics.py:143): only cos/sin of beta and of heading+beta are needed
+    const double tb = (fl & TTRL_FL_CRASHED) ? 0.0 : 0.5 * st->tsteer[i];
+    const double cbeta = 1.0 / sqrt(1.0 + tb * tb), sbeta = tb * cbeta;
     const double hd = st->h[i];
-    double sb, cb;
-    sincos(hd + beta, &sb, &cb);
-    const double vx = speed * cb, vy = speed * sb;
+    const d2 hc = st->cs[i];
+    const double vx = speed * (hc.x * cbeta - hc.y * sbeta), vy = speed * (hc.y * cbeta + hc.x * sbeta);
     double px = st->pos[i].x + vx * dt, py = st->pos[i].y + vy * dt;
     if (fl & TTRL_FL_HAS_IMPACT) {
         px += st->imp[i].x;
@@ -648,7 +659,7 @@ TT_HD void integrate(C& c, Exec& ex, int i) {
         fl = (fl | TTRL_FL_CRASHED) & ~TTRL_FL_HAS_IMPACT;
         st->imp[i] = d2{0, 0};
     }
-    const double nh = hd + speed * sin(beta) / (kVehLength / 2) * dt;
+    const double nh = hd + speed * sbeta / (kVehLength / 2) * dt;
     const double nv = speed + acc * dt;
     st->pos[i] = d2{px, py};
     st->h[i] = nh;
@@ -970,15 +981,24 @@ TT_HD void env_substep(C& c, Exec& ex, int raw_action) {
         const int nm = st->n_mob;
         for (int base = 0; base < nm; base += ES::MB) mobil_batch(c, ex, base, nm - base < ES::MB ? nm - base : ES::MB);
     }
-    {   // phase B, in list order
-        for (int i = 0; i < n; ++i) {
-            if (!st->mark[i]) continue;
-            const bool ab = ex.any(n, [&](int j) { return abort_pred(c, i, j); });
-            if (ab) { if (ex.first()) st->tlane[i] = st->lane[i]; ex.sync(); }
+    {   // phase B, in list order (bit order of bmask)
+#pragma unroll 1
+        for (int w = 0; w < C::W; ++w) {
+            uint32_t m = st->bmask[w];
+            while (m) {
+#if defined(__CUDA_ARCH__)
+                const int i = w * 32 + __ffs((int)m) - 1;
+#else
+                const int i = w * 32 + __builtin_ctz(m);
+#endif
+                m &= m - 1;
+                const bool ab = ex.any(n, [&](int j) { return abort_pred(c, i, j); });
+                if (ab) { if (ex.first()) st->tlane[i] = st->lane[i]; ex.sync(); }
+            }
         }
     }
     ex.parn(n, [&](int t) {
-        if (t == 0) st->n_mob = 0;
+        if (t == 0) { st->n_mob = 0; for (int w = 0; w < C::W; ++w) st->bmask[w] = 0; }
         act_phase_c1(c, ex, t);
     });
     ex.parn(n + st->n_chg, [&](int k) { act_phase_c2(c, k); });
@@ -1332,6 +1352,7 @@ TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
         st->episode = g.ei[TTRL_EI_EPISODE * g.E + e]; st->done = g.ei[TTRL_EI_DONE * g.E + e];
         st->time = g.ed[TTRL_ED_TIME * g.E + e]; st->ret = g.ed[TTRL_ED_RETURN * g.E + e];
         st->n_chg = st->n_mob = st->n_pair = st->n_w = st->overflow = 0;
+        for (int w = 0; w < C::W; ++w) st->bmask[w] = 0;
     }
     ex.par([&](int t) {
         if (t < V) {
@@ -1358,7 +1379,7 @@ TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
             st->lane[t] = st->tlane[t] = st->flags[t] = st->sidx[t] = st->rlen[t] = st->ytimer[t] = 0;
             st->rroad[t] = st->rlanew[t] = 0;
         }
-        st->mark[t] = 0; st->tl_old[t] = 0; st->acc2[t] = 0; st->best[t] = -1; st->fo[t] = -1;
+        st->mark[t] = 0; st->tl_old[t] = 0; st->acc2[t] = 0; st->tsteer[t] = 0; st->best[t] = -1; st->fo[t] = -1;
         // pre-check guard from the loaded speed (integrate refreshes it every sub-step)
         const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
         const double thr = (diag + diag) / 2 + st->v[t] * c.sc->dt;

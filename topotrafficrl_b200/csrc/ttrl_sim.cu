@@ -130,6 +130,7 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V>& c, unsigned char* smem, cons
     c.obs_s = reinterpret_cast<float*>(smem + lay.off_obs);
     c.cell = reinterpret_cast<int32_t*>(smem + lay.off_cell);
     c.gap_den = 2 * sqrt(-sc->cfg.comfort_acc_max * sc->cfg.comfort_acc_min);  // behavior.py:214-216
+    c.tan_max_steer = tan(kPi / 3);
     __syncthreads();
 }
 
