@@ -30,10 +30,10 @@
 
 #if defined(__CUDACC__)
 #define TT_HD __host__ __device__ __forceinline__
-#define TT_HDN __host__ __device__ __noinline__
+#define TT_HDN inline __host__ __device__ __noinline__
 #else
 #define TT_HD inline
-#define TT_HDN
+#define TT_HDN inline
 #endif
 
 namespace ttrl {

@@ -1,0 +1,223 @@
+// ttrl_kern.cu -- the sm_100a kernels of the batched simulator for ONE slot capacity V (-DTT_V=<V>).
+//
+// Launch shape: one CTA ("team" of T threads) per env instance; slots and task lists are strided over the team.
+// k_step keeps the env's state in shared memory across the F sub-steps of an env-step: one coalesced HBM read
+// and one write of the state per env-step.  Shared-memory arrays are sized by V, so the
+// library carries one instantiation per common capacity (Makefile: TT_VS) and picks the smallest V >= vcap.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "ttrl_kernels.cuh"
+
+using namespace ttrl;
+
+// ------------------------------------------------------------------------------------------------
+// device execution policy: one CTA of T threads ("team") per env; slots / tasks are strided over the team.
+// T == 32: the team is one warp, barriers are __syncwarp().
+// ------------------------------------------------------------------------------------------------
+template <int V, int T>
+struct DevExec {
+    int tid;
+    __device__ __forceinline__ bool first() const { return tid == 0; }
+    __device__ __forceinline__ void sync() {
+        if (T == 32) __syncwarp(); else __syncthreads();
+    }
+    template <class F> __device__ __forceinline__ void par(F f) {
+#pragma unroll 1
+        for (int t = tid; t < V; t += T) f(t);
+        sync();
+    }
+    template <class F> __device__ __forceinline__ void parn(int n, F f) {
+#pragma unroll 1
+        for (int t = tid; t < n; t += T) f(t);
+        sync();
+    }
+    template <class F> __device__ __forceinline__ bool any(int n, F f) {
+        int p = 0;
+#pragma unroll 1
+        for (int t = tid; t < n; t += T) p |= f(t) ? 1 : 0;
+        if (T == 32) return __any_sync(0xffffffffu, p) != 0;
+        return __syncthreads_or(p) != 0;
+    }
+    template <class F1, class F2> __device__ __forceinline__ void par2(F1 f1, F2 f2) {
+        constexpr int R = (V + T - 1) / T;
+        SlotRegs r[R];
+        int dst[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) { dst[k] = -1; if (tid + k * T < V) f1(tid + k * T, r[k], dst[k]); }
+        sync();
+#pragma unroll
+        for (int k = 0; k < R; ++k) if (tid + k * T < V) f2(tid + k * T, r[k], dst[k]);
+        sync();
+    }
+    // 8 lanes per candidate pair, one separating axis each; the pair's result is reduced with shuffles:
+    // intersecting / will_intersect = no lane reports a separation, translation axis = first axis of minimal absd.
+    template <class FA, class FP> __device__ __forceinline__ void sat_pairs(int np, FA fa, FP fp) {
+        const int total = np * 8;
+#pragma unroll 1
+        for (int base = 0; base < total; base += T) {
+            const int idx = base + tid;
+            const bool act = idx < total;
+            const int q = idx >> 3, axis = idx & 7;
+            AxisRes r;
+            r.absd = INFINITY; r.nx = 0; r.ny = 0; r.fl = 0;
+            if (act) r = fa(q, axis);
+            const unsigned gbase = (unsigned)(tid & 31) & ~7u;
+            const unsigned sep_now = __ballot_sync(0xffffffffu, act && (r.fl & 1));
+            const unsigned sep_after = __ballot_sync(0xffffffffu, act && (r.fl & 2));
+            const bool inter = ((sep_now >> gbase) & 0xFFu) == 0, will = ((sep_after >> gbase) & 0xFFu) == 0;
+            double bd = r.absd;
+            int bi = axis;
+#pragma unroll
+            for (int off = 1; off < 8; off <<= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            const double nx = __shfl_sync(0xffffffffu, r.nx, (int)gbase + bi), ny = __shfl_sync(0xffffffffu, r.ny, (int)gbase + bi);
+            if (act && axis == 0) fp(q, inter, will, bd, nx, ny);
+        }
+        sync();
+    }
+    __device__ __forceinline__ void atomic_min(int32_t* a, int32_t v) { atomicMin(a, v); }
+    __device__ __forceinline__ void atomic_max(int32_t* a, int32_t v) { atomicMax(a, v); }
+    __device__ __forceinline__ void atomic_or(uint32_t* a, uint32_t v) { atomicOr(a, v); }
+    __device__ __forceinline__ int atomic_add(int32_t* a, int32_t v) { return atomicAdd(a, v); }
+};
+
+// threads per env for a slot capacity
+// Threads per env ("team") and minimum resident CTAs per SM (register cap) for a slot capacity.  Tuned on B200
+// (profiles/r1c_variants.txt): the kernel is latency-bound (fp64 dependency chains, instruction fetch), so
+// resident warps matter more than registers per thread.
+#ifndef TT_V
+#error "compile with -DTT_V=<slot capacity>"
+#endif
+#ifndef TT_T
+#define TT_T (TT_V <= 32 ? 32 : TT_V <= 64 ? 64 : 128)
+#endif
+#ifndef TT_MINB
+#define TT_MINB (TT_V <= 32 ? 1 : TT_V <= 64 ? 10 : 1)
+#endif
+template <int V> struct TeamOf { static constexpr int T = TT_T, MINB = TT_MINB; };
+
+template <int V>
+__device__ __forceinline__ void make_ctx(EnvCtx<V>& c, unsigned char* smem, const SceneDev* sc, const SmemLayout& lay, int vcap) {
+    c.st = reinterpret_cast<EnvState<V>*>(smem);
+    c.sc = sc;
+    c.L = sc->cfg.n_lanes;
+    c.vcap = vcap;
+    ttrl_lane* lanes_s = reinterpret_cast<ttrl_lane*>(smem + lay.off_lanes);
+    // copy the lane table into shared memory (n_lanes * 160 B) with 16-byte vector loads
+    {
+        const int4* src = reinterpret_cast<const int4*>(sc->lanes);
+        int4* dst = reinterpret_cast<int4*>(lanes_s);
+        const int n16 = c.L * (int)(sizeof(ttrl_lane) / 16);
+        for (int k = threadIdx.x; k < n16; k += blockDim.x) dst[k] = __ldg(src + k);
+    }
+    c.lanes = lanes_s;
+    c.SR = reinterpret_cast<d2*>(smem + lay.off_SR);
+    c.lmask = reinterpret_cast<uint32_t*>(smem + lay.off_lmask);
+    c.pred = lay.off_pred >= 0 ? reinterpret_cast<double*>(smem + lay.off_pred) : nullptr;
+    c.obs_s = reinterpret_cast<float*>(smem + lay.off_obs);
+    c.cell = reinterpret_cast<int32_t*>(smem + lay.off_cell);
+    c.gap_den = 2 * sqrt(-sc->cfg.comfort_acc_max * sc->cfg.comfort_acc_min);  // behavior.py:214-216
+    c.tan_max_steer = tan(kPi / 3);
+    __syncthreads();
+}
+
+#define TT_KERNEL_PROLOGUE                                     \
+    extern __shared__ __align__(16) unsigned char smem[];      \
+    constexpr int T = TeamOf<V>::T;                            \
+    EnvCtx<V> c;                                               \
+    make_ctx<V>(c, smem, sc, lay, g.V);                        \
+    DevExec<V, T> ex{(int)threadIdx.x};
+
+template <int V>
+__global__ void __launch_bounds__(TeamOf<V>::T, TeamOf<V>::MINB) k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay) {
+    TT_KERNEL_PROLOGUE
+    env_step(c, ex, g, io, (int)blockIdx.x);
+}
+
+template <int V>
+__global__ void __launch_bounds__(TeamOf<V>::T) k_substep(const SceneDev* __restrict__ sc, GlobalState g, const int32_t* __restrict__ actions, SmemLayout lay) {
+    TT_KERNEL_PROLOGUE
+    const int e = blockIdx.x;
+    load_env(c, ex, g, e);
+    env_substep(c, ex, actions ? actions[e] : -1);
+    store_env(c, ex, g, e);
+}
+
+template <int V>
+__global__ void __launch_bounds__(TeamOf<V>::T) k_observe(const SceneDev* __restrict__ sc, GlobalState g, float* __restrict__ obs, int obs_size,
+                                                          const int32_t* __restrict__ inv_perm, SmemLayout lay) {
+    TT_KERNEL_PROLOGUE
+    const int e = blockIdx.x;
+    load_env(c, ex, g, e);
+    observe(c, ex, obs + (size_t)e * obs_size, inv_perm ? inv_perm + (size_t)e * (sc->cfg.obs_vehicles - 1) : nullptr);
+}
+
+template <int V>
+__global__ void __launch_bounds__(TeamOf<V>::T) k_spawn(const SceneDev* __restrict__ sc, GlobalState g, const ttrl_spawn_draw* __restrict__ draws,
+                                                        SpawnParams sp, int32_t* __restrict__ accepted, SmemLayout lay) {
+    TT_KERNEL_PROLOGUE
+    const int e = blockIdx.x;
+    load_env(c, ex, g, e);
+    spawn_vehicle(c, ex, draws[e], sp);
+    if (accepted && threadIdx.x == 0) accepted[e] = c.st->flag0;
+    ex.sync();
+    store_env(c, ex, g, e);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// launch table
+// ------------------------------------------------------------------------------------------------
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <int V>
+static int configure(const ttrl_config& cfg, int vcap, SmemLayout* out) {
+    SmemLayout l{};
+    size_t off = align_up(sizeof(EnvState<V>), 16);
+    l.off_lanes = (int)off; off += align_up(sizeof(ttrl_lane) * cfg.n_lanes, 16);
+    l.off_SR = (int)off; off += sizeof(d2) * vcap * cfg.n_lanes;
+    l.off_lmask = (int)off; off += align_up(sizeof(uint32_t) * ((V + 31) / 32) * cfg.n_lanes, 16);
+    if (cfg.regulated) { l.off_pred = (int)off; off += sizeof(double) * 3 * V * kPred; } else l.off_pred = -1;
+    l.off_obs = (int)off; off += align_up(sizeof(float) * (cfg.obs_type == TTRL_OBS_KINEMATICS ? cfg.obs_vehicles * cfg.n_features : 4), 16);
+    l.off_cell = (int)off; off += align_up(sizeof(int32_t) * (cfg.obs_type == TTRL_OBS_GRID ? cfg.grid_w * cfg.grid_h : 4), 16);
+    l.total = (int)off;
+    *out = l;
+    if (l.total > 227 * 1024) return (int)cudaErrorInvalidValue;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_step<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_substep<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_observe<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_spawn<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
+    // all of the SM's unified L1/shared storage as shared memory: resident CTAs are what hides latency here
+    cudaFuncSetAttribute(k_step<V>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return 0;
+}
+template <int V>
+static void launch_step(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io) {
+    k_step<V><<<E, TeamOf<V>::T, lay.total, st>>>(sc, g, io, lay);
+}
+template <int V>
+static void launch_substep(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const int32_t* actions) {
+    k_substep<V><<<E, TeamOf<V>::T, lay.total, st>>>(sc, g, actions, lay);
+}
+template <int V>
+static void launch_observe(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, float* obs, int obs_size,
+                           const int32_t* inv_perm) {
+    k_observe<V><<<E, TeamOf<V>::T, lay.total, st>>>(sc, g, obs, obs_size, inv_perm, lay);
+}
+template <int V>
+static void launch_spawn(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const ttrl_spawn_draw* draws,
+                         SpawnParams sp, int32_t* accepted) {
+    k_spawn<V><<<E, TeamOf<V>::T, lay.total, st>>>(sc, g, draws, sp, accepted, lay);
+}
+
+#define TT_CAT_(a, b) a##b
+#define TT_CAT(a, b) TT_CAT_(a, b)
+extern "C" const KernelSet* TT_CAT(ttrl_kernel_set_, TT_V)(void) {
+    static const KernelSet ks = {TT_V, TeamOf<TT_V>::T, configure<TT_V>, launch_step<TT_V>, launch_substep<TT_V>, launch_observe<TT_V>, launch_spawn<TT_V>};
+    return &ks;
+}

@@ -1,0 +1,29 @@
+// ttrl_kernels.cuh -- interface between the host side of the C ABI (ttrl_sim.cu) and the per-capacity kernel
+// translation units (ttrl_kern.cu compiled once per slot capacity V with -DTT_V=<V>).
+#pragma once
+#include <cuda_runtime.h>
+#include "ttrl_core.cuh"
+
+namespace ttrl {
+
+struct SmemLayout {
+    int off_lanes, off_SR, off_lmask, off_pred, off_obs, off_cell, total;
+};
+
+// One set of launchers per compiled slot capacity.
+struct KernelSet {
+    int V;        // slot capacity the kernels were compiled for (arrays in shared memory are sized by it)
+    int T;        // threads per env
+    int (*configure)(const ttrl_config& cfg, int vcap, SmemLayout* lay);  // layout + shared-memory opt-in; cudaError_t as int
+    void (*step)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io);
+    void (*substep)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const int32_t* actions);
+    void (*observe)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, float* obs, int obs_size,
+                    const int32_t* inv_perm);
+    void (*spawn)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const ttrl_spawn_draw* draws,
+                  SpawnParams sp, int32_t* accepted);
+};
+
+}  // namespace ttrl
+
+// capacities compiled into the library (Makefile: TT_VS); ttrl_kernel_set_<V>() is defined by ttrl_kern.cu -DTT_V=<V>
+#define TT_DECLARE_KERNEL_SET(N_) extern "C" const ttrl::KernelSet* ttrl_kernel_set_##N_(void);
