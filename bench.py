@@ -201,7 +201,7 @@ def run_ours(args, w):
         sim.set_autoreset(True)
     else:
         from topotrafficrl_b200.vector_env import TTRLVectorEnv
-        venv = TTRLVectorEnv(E, scene="intersection", device=local_rank, seed=0, first_env=first_env, vcap=w["n"])
+        venv = TTRLVectorEnv(E, scene="intersection", device=local_rank, seed=0, first_env=first_env, vcap=args.vcap or w["n"])
         venv.reset()
         sim = venv.sim
 
@@ -316,6 +316,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="highway50", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--vcap", type=int, default=0, help="vehicle slots per env (intersection workload; default 32)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -9,25 +9,30 @@ import collections, csv, os, re, subprocess, sys, tempfile
 
 rep, so, kern = sys.argv[1:4]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 50
-tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-# 1. per-function, per-instruction-index source line from nvdisasm
+# <lib.so> may also be the build directory: every *.o holds one cubin (the .so holds several with the same name)
+inputs = [os.path.join(so, f) for f in sorted(os.listdir(so)) if f.endswith(".o")] if os.path.isdir(so) else [so]
 line_of = {}  # (func, idx) -> "file:line"
-for cub in os.listdir(tmp):
-    txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
-    func, cur, idx = None, "?", 0
-    for ln in txt.splitlines():
-        m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
-        if m:
-            func, idx, cur = m.group(1), 0, "?"
-            continue
-        m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', ln)
-        if m:
-            cur = f"{os.path.basename(m.group(1))}:{m.group(2)}"
-            continue
-        if func and re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", ln):
-            line_of[(func, idx)] = cur
-            idx += 1
+op_of = {}
+for inp in inputs:
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(inp)], cwd=tmp, check=False, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for cub in os.listdir(tmp):
+        txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+        func, cur, idx = None, "?", 0
+        for ln in txt.splitlines():
+            m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
+            if m:
+                func, idx, cur = m.group(1), 0, "?"
+                continue
+            m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', ln)
+            if m:
+                cur = f"{os.path.basename(m.group(1))}:{m.group(2)}"
+                continue
+            m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(\S+)", ln)
+            if func and m:
+                line_of[(func, idx)] = cur
+                op_of[(func, idx)] = m.group(1).split(".")[0].rstrip(";")
+                idx += 1
 # 2. ncu sass page
 csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(csvtxt.splitlines()))
@@ -36,6 +41,7 @@ hdr = None
 func = None
 funcs = sorted({f for f, _ in line_of})
 k = 0
+mismatch = 0
 done_first = False
 for r in rows:
     if r and r[0] == "Kernel Name":
@@ -55,12 +61,18 @@ for r in rows:
         continue
     done_first = True
     i_s, i_i, i_t = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+    sass_op = r[1].split()[0].split(".")[0] if r[1].split() and not r[1].split()[0].startswith("@") else (r[1].split()[1].split(".")[0] if len(r[1].split()) > 1 else "")
+    want_op = op_of.get((func, k), "")
+    if want_op and sass_op and want_op.lstrip("@!P0123456789UT ") != sass_op and not want_op.startswith("@"):
+        mismatch += 1
     a = agg[line_of.get((func, k), "?")]
     a[0] += int(r[i_s] or 0); a[1] += int(r[i_i] or 0); a[2] += int(r[i_t] or 0)
     k += 1
 ts = sum(a[0] for a in agg.values()) or 1
 ti = sum(a[1] for a in agg.values()) or 1
 print(f"kernel {kern}: {k} SASS instructions, {ti} warp-inst executed, {ts} samples")
+if k == 0 or mismatch > k // 20:
+    sys.exit(f"the library does not match the profiled binary ({mismatch} opcode mismatches over {k} instructions): rebuild the profiled revision first")
 src_cache = {}
 def src(loc):
     f, _, n = loc.partition(":")
