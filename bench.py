@@ -53,7 +53,42 @@ WORKLOADS = {
     "intersection": dict(scene="intersection", E=8192, n=32, over=None,
                          label="configs[3]: intersection 8192 envs, regulated road, spawn, Kinematics obs",
                          bytes_per_env_step=24 * 128 + 4 + 420 + 8, n_actions=3),
+    # BASELINE configs[3] proper: the DQN Q-network rollout (agent.act: forward + epsilon-greedy) in the loop
+    "intersection_qnet": dict(scene="intersection", E=8192, n=32, over=None, qnet="ego_attention_2h",
+                              label="configs[3]: intersection 8192 envs + DQN ego-attention (2 heads) Q-net rollout in the loop",
+                              bytes_per_env_step=24 * 128 + 4 + 420 + 8 + 420 + 4, n_actions=3),
+    "intersection_qnet_mlp": dict(scene="intersection", E=8192, n=32, over=None, qnet="mlp",
+                                  label="configs[3]: intersection 8192 envs + DQN MLP [128,128] Q-net rollout in the loop",
+                                  bytes_per_env_step=24 * 128 + 4 + 420 + 8 + 420 + 4, n_actions=3),
 }
+
+QNET_CONFIGS = {  # scripts/configs/IntersectionEnv/agents/DQNAgent/{ego_attention_2h,baseline}.json of the reference
+    "ego_attention_2h": {"type": "EgoAttentionNetwork", "embedding_layer": {"layers": [64, 64]}, "others_embedding_layer": {"layers": [64, 64]},
+                         "self_attention_layer": None, "attention_layer": {"feature_size": 64, "heads": 2}, "output_layer": {"layers": [64, 64]}},
+    "mlp": {"type": "MultiLayerPerceptron", "layers": [128, 128]},
+}
+
+
+def random_state_dict(kind: str, n_actions: int, seed: int = 0):
+    """Random-init weights of the reference architectures (torch.nn.Linear default init: U(-1/sqrt(fan_in), +))."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def lin(name, fan_in, fan_out, bias=True):
+        b = 1 / np.sqrt(fan_in)
+        sd[name + ".weight"] = rng.uniform(-b, b, size=(fan_out, fan_in)).astype(np.float32)
+        if bias:
+            sd[name + ".bias"] = rng.uniform(-b, b, size=fan_out).astype(np.float32)
+
+    if kind == "mlp":
+        lin("layers.0", 105, 128); lin("layers.1", 128, 128); lin("predict", 128, n_actions)
+    else:
+        for emb in ("ego_embedding", "others_embedding"):
+            lin(emb + ".layers.0", 7, 64); lin(emb + ".layers.1", 64, 64)
+        for name in ("key_all", "value_all", "query_ego", "attention_combine"):
+            lin("attention_layer." + name, 64, 64, bias=False)
+        lin("output_layer.layers.0", 64, 64); lin("output_layer.layers.1", 64, 64); lin("output_layer.predict", 64, n_actions)
+    return sd
 
 
 def _peaks():
@@ -215,8 +250,19 @@ def run_ours(args, w):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = int(torch.cuda.current_stream(dev).cuda_stream)
 
+    qnet = None
+    if w.get("qnet"):
+        from topotrafficrl_b200.agent import QNetRollout
+        qnet = QNetRollout(QNET_CONFIGS[w["qnet"]], random_state_dict(w["qnet"], w["n_actions"]), (15, 7), w["n_actions"], device=local_rank,
+                           exploration={"method": "EpsilonGreedy", "temperature": 0.05, "final_temperature": 0.05, "tau": 15000}, seed=7 + rank)
+        sim.observe_ptr(obs.data_ptr(), stream)
+    obs3 = obs.view(E, -1)
+
     def step(k):
-        sim.step_ptr(actions[k].data_ptr(), obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr(), stream)
+        a = actions[k]
+        if qnet is not None:  # agent.act on the observation the previous step left in HBM (no host round trip)
+            a = qnet.act(obs3)
+        sim.step_ptr(a.data_ptr(), obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr(), stream)
 
     def barrier():
         if world > 1:
@@ -230,7 +276,7 @@ def run_ours(args, w):
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    launches0 = sim.launch_count
+    launches0 = sim.launch_count + (qnet._L.ttrl_qnet_launch_count(qnet._h) if qnet is not None else 0)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     t_wall0 = time.perf_counter()
     for k in range(K):
@@ -240,7 +286,7 @@ def run_ours(args, w):
         ev[k][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = sim.launch_count - launches0
+    launches = sim.launch_count + (qnet._L.ttrl_qnet_launch_count(qnet._h) if qnet is not None else 0) - launches0
     clocks = sampler.stop()
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(ms))
@@ -261,8 +307,12 @@ def run_ours(args, w):
     sim.stats(reset=True)
     barrier()
     t0 = time.perf_counter()
+    o = obs3.cpu().numpy()
     for k in range(K):
-        o, r, t, u = sim.step_host(acts_host[W + k])
+        a_host = acts_host[W + k]
+        if qnet is not None:  # the reference's agent.act boundary: numpy observation in, numpy actions out
+            a_host = qnet.act(torch.from_numpy(o).to(dev, non_blocking=True).view(E, -1)).cpu().numpy()
+        o, r, t, u = sim.step_host(a_host)
     barrier()
     e2e_s = time.perf_counter() - t0
     s2 = sim.stats(reset=True)
@@ -271,7 +321,7 @@ def run_ours(args, w):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_v, op=dist.ReduceOp.SUM)
-    h2d = E * 4
+    h2d = E * 4 + (E * sim.obs_size * 4 if qnet is not None else 0)
     d2h = E * (sim.obs_size * 4 + 4 + 2)
 
     if rank == 0:

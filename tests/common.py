@@ -87,3 +87,35 @@ def compare_states(got: SimState, want: SimState, tol: float, what: str = "", ch
             assert m <= tol, f"{what}: continuous field {f} differs by {m} (> {tol})"
             worst = max(worst, m)
     return worst
+
+
+def stress_states(cfgd, E: int, n: int, seed: int = 0):
+    """Adversarial highway states for the task-queue paths of the kernel (tests only):
+    * env 0..E/3: a pile-up -- every vehicle within a few metres of one point, so every pair passes the collision
+      pre-check (n(n-1)/2 candidate pairs overflow the pair queue -> serial fallback) and most pairs intersect;
+    * next third: every lane-change timer already elapsed (all vehicles enter MOBIL in the same sub-step: several
+      MOBIL batches) in dense traffic with many ongoing lane changes (phase B);
+    * rest: ragged vehicle counts 1..n.
+    """
+    st = scenes.make_highway_state(E, cfgd, seed=seed)
+    rng = np.random.default_rng(seed + 99)
+    third = max(E // 3, 1)
+    for e in range(E):
+        if e < third:
+            st.veh_d[abi.D_X, e, :n] = 300.0 + rng.uniform(-4, 4, size=n)
+            st.veh_d[abi.D_Y, e, :n] = rng.integers(0, 4, size=n) * 4.0 + rng.uniform(-1.5, 1.5, size=n)
+            st.veh_d[abi.D_HEADING, e, :n] = rng.uniform(-0.3, 0.3, size=n)
+            st.veh_i[abi.I_LANE, e, :n] = np.clip(np.round(st.veh_d[abi.D_Y, e, :n] / 4.0), 0, 3).astype(np.int32)
+            st.veh_i[abi.I_TARGET_LANE, e, :n] = st.veh_i[abi.I_LANE, e, :n]
+        elif e < 2 * third:
+            st.veh_d[abi.D_TIMER, e, 1:n] = 1.0 + rng.uniform(0.01, 0.5, size=n - 1)
+            tl = np.clip(st.veh_i[abi.I_LANE, e, 1:n] + rng.integers(-1, 2, size=n - 1), 0, 3)
+            chg = rng.random(n - 1) < 0.4
+            st.veh_i[abi.I_TARGET_LANE, e, 1:n] = np.where(chg, tl, st.veh_i[abi.I_TARGET_LANE, e, 1:n])
+            st.veh_d[abi.D_TIMER, e, 1:n] = np.where(chg, 0.3, st.veh_d[abi.D_TIMER, e, 1:n])
+        else:
+            k = 1 + (e * 7) % n
+            st.veh_d[:, e, k:] = 0
+            st.veh_i[:, e, k:] = 0
+            st.env_i[abi.EI_NVEH, e] = k
+    return st

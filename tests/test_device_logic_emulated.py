@@ -71,3 +71,25 @@ def test_free_running_vs_oracle(n, density, steps):
         np.testing.assert_allclose(oa[0], ob[0], rtol=0, atol=1e-6)
         np.testing.assert_allclose(oa[1], ob[1], rtol=0, atol=1e-6)
         assert (oa[2] == ob[2]).all() and (oa[3] == ob[3]).all()
+
+
+@pytest.mark.parametrize("n,density", [(20, 2.0), (50, 3.0)])
+def test_task_queue_stress_vs_oracle(n, density):
+    """Pair-queue overflow (serial fallback), several MOBIL batches in one sub-step, many ongoing lane changes and
+    ragged vehicle counts: emulated device logic == oracle, per sub-step and per env-step."""
+    _, table, cfg, cfgd = T.highway_scene(n, density)
+    emu, orc = Emulator(cfg, table), O.Oracle(cfg, table)
+    a = T.stress_states(cfgd, 9, n, seed=4)
+    b = a.copy()
+    for k in range(4):
+        emu.substep(a, None)
+        orc.substep(b, None)
+        T.compare_states(a, b, 1e-9, f"stress sub-step {k}")
+    assert ((a.veh_i[abi.I_FLAGS] & abi.FL_CRASHED) != 0).sum() > n  # the pile-ups did crash
+    rng = np.random.default_rng(1)
+    for k in range(3):
+        act = rng.integers(0, 5, size=9).astype(np.int32)
+        oa, ob = emu.step(a, act), orc.step(b, act)
+        T.compare_states(a, b, 1e-7, f"stress step {k}")
+        np.testing.assert_allclose(oa[0], ob[0], rtol=0, atol=2e-6)
+        assert (oa[2] == ob[2]).all() and (oa[3] == ob[3]).all()

@@ -272,3 +272,32 @@ def test_missing_device_arguments_fail_loudly():
         _sim(cfg, table, 0, 50)
     with pytest.raises(TTRLError):
         _sim(cfg, table, 4, 1000)
+
+
+@pytest.mark.parametrize("n,density", [(20, 2.0), (50, 3.0), (200, 4.0)])
+def test_task_queue_stress_vs_oracle(n, density):
+    """Pair-queue overflow (serial fallback), several MOBIL batches in one sub-step, many ongoing lane changes and
+    ragged vehicle counts (1..n): device == oracle per resynced-free sub-step and per env-step."""
+    from oracle import oracle as O
+    torch = _torch()
+    E = 48
+    _, table, cfg, cfgd = T.highway_scene(n, density)
+    a = T.stress_states(cfgd, E, n, seed=4)
+    b = a.copy()
+    sim = _sim(cfg, table, E, n)
+    sim.set_state(a)
+    orc = O.Oracle(cfg, table, threads=8)
+    for k in range(4):
+        sim.substep_ptr(None, 0)
+        orc.substep(b, None)
+        T.compare_states(sim.get_state(), b, 1e-9, f"stress sub-step {k}")
+    assert ((b.veh_i[abi.I_FLAGS] & abi.FL_CRASHED) != 0).sum() > n
+    rng = np.random.default_rng(1)
+    for k in range(3):
+        act = rng.integers(0, 5, size=E).astype(np.int32)
+        obs, rew, term, trunc = _dev_step(sim, act)
+        oo, orr, ot, ou, _ = orc.step(b, act)
+        T.compare_states(sim.get_state(), b, 1e-7, f"stress step {k}")
+        np.testing.assert_allclose(obs, oo, rtol=0, atol=2e-6)
+        assert (term == ot).all() and (trunc == ou).all()
+    sim.close()
