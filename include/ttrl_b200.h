@@ -239,6 +239,12 @@ typedef struct ttrl_qnet_desc {
 int ttrl_qnet_create(const ttrl_qnet_desc* desc, const float* weights_host, int64_t n_weights,
                      int device, ttrl_qnet** out);
 int ttrl_qnet_destroy(ttrl_qnet* q);
+/* Arithmetic of the forward pass.  FP32 (default): CUDA-core fp32 FMA, the parity path (actions bit-exact vs the
+ * reference's torch CPU fp32 forward up to summation order).  TENSOR: the hidden GEMMs on the tcgen05 tensor cores
+ * with BF16x3 split operands and FP32 accumulation in TMEM (MultiLayerPerceptron, two hidden layers); Q-values agree
+ * to ~1e-5, the greedy action can differ on near-ties. */
+enum { TTRL_QNET_MODE_FP32 = 0, TTRL_QNET_MODE_TENSOR = 1 };
+int ttrl_qnet_set_mode(ttrl_qnet* q, int mode);
 /* Q-values + epsilon-greedy action for E observations.  q_dev may be NULL.  epsilon<=0 -> Greedy. */
 int ttrl_qnet_act(ttrl_qnet* q, const float* obs_dev, int num_envs, double epsilon, uint64_t seed,
                   uint64_t step, int32_t* actions_dev, float* q_dev, void* stream);

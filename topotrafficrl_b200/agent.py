@@ -95,8 +95,10 @@ def pack_weights(model_config: dict, state_dict: Dict[str, np.ndarray], obs_shap
 class QNetRollout:
     """Batched ``agent.act``: obs [E, V, Fe] float32 on the device -> actions int32 [E] (and Q-values)."""
 
+    MODES = {"fp32": 0, "tensor": 1}
+
     def __init__(self, model_config: dict, state_dict, obs_shape, n_actions: int, device: int = 0,
-                 exploration: Optional[dict] = None, seed: int = 0) -> None:
+                 exploration: Optional[dict] = None, seed: int = 0, mode: str = "fp32") -> None:
         import torch
 
         self.torch = torch
@@ -109,6 +111,7 @@ class QNetRollout:
                                        self.device_index, C.byref(h)))
         self._h = h
         self.n_actions = int(n_actions)
+        self.set_mode(mode)
         # EpsilonGreedy schedule (epsilon_greedy.py:26-30 defaults; baseline.json overrides tau/final_temperature)
         ex = dict(method="EpsilonGreedy", temperature=1.0, final_temperature=0.1, tau=5000)
         ex.update(exploration or {})
@@ -117,6 +120,15 @@ class QNetRollout:
         self.time = 0
         self.seed = int(seed)
         self.training = True
+
+    def set_mode(self, mode: str) -> None:
+        """``"fp32"``: CUDA-core fp32 forward, the parity path (default).  ``"tensor"``: hidden GEMMs on the tcgen05
+        tensor cores (BF16x3 split, FP32 accumulation in TMEM); MultiLayerPerceptron with two hidden layers only --
+        raises :class:`TTRLError` otherwise (no silent fallback)."""
+        if mode not in self.MODES:
+            raise ValueError(f"unknown mode {mode!r}")
+        check(self._L.ttrl_qnet_set_mode(self._h, self.MODES[mode]))
+        self.mode = mode
 
     def close(self):
         if getattr(self, "_h", None):

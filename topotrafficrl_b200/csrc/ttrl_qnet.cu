@@ -10,6 +10,7 @@
 // order; it is the parity path).  Persistent CTAs keep ALL weights in shared memory (<= ~137 KB for the
 // shipped configs); each warp forwards one env (ego-attention) or a group of 8 envs (MLP / dueling).
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -257,6 +258,215 @@ __global__ void __launch_bounds__(kWarps * 32) k_qnet_fp32(QnetDev net, const fl
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core path (throughput mode) for the MultiLayerPerceptron Q-network (models.py:50-76, the reference's
+// DQN baseline.json: 105 -> 128 -> 128 -> 3): the two hidden GEMMs run on the 5th-generation tensor cores.
+//
+//  * one CTA = one tile of 128 observations (UMMA M = 128), 128 threads; persistent over tiles;
+//  * operands live in shared memory in the canonical K-major, no-swizzle UMMA layout (8 x 16-byte core
+//    matrices): element (row, k) at (row/8)*SBO + (k/8)*128 + (row%8)*16 + (k%8)*2 bytes, SBO = K/8*128;
+//  * tcgen05.mma (kind::f16, BF16 inputs, FP32 accumulate) is issued by ONE thread, accumulators live in TMEM
+//    (128 lanes x N columns), completion is signalled with tcgen05.commit on an mbarrier, and the epilogue reads
+//    the accumulators back with tcgen05.ld (32x32b: thread t <-> TMEM lane t <-> observation t of the tile);
+//  * fp32 accuracy from BF16 tensor cores: every operand is split x = hi + lo (two BF16 values) and each product
+//    is accumulated as hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-16 relative), so Q-values agree with
+//    the fp32 path to ~1e-5 and the greedy action only differs on near-ties (tests/test_gpu_qnet.py);
+//  * bias + ReLU + re-split of the activations happen in the epilogue, straight into the next layer's A operand;
+//    the 3-wide head and the epsilon-greedy selection stay on the CUDA cores.
+// ------------------------------------------------------------------------------------------------
+struct TcMlp {
+    int nin, K1, H1, H2, A;                              // K1 = nin rounded up to 16
+    int w1, b1, w2, b2, w3, b3;                          // offsets into the fp32 blob ([in][out] matrices)
+    int off_w1hi, off_w1lo, off_w2hi, off_w2lo, off_ahi, off_alo, off_f32, off_bar, total;  // shared-memory bytes
+    int tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    // SmemDescriptor: start address [0,14), leading byte offset [16,30), stride byte offset [32,46) (all >> 4),
+    // version 1 (Blackwell) at [46,48), layout type SWIZZLE_NONE = 0 at [61,64)
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+}
+// canonical K-major no-swizzle offset (bytes) of element (row, k) in an operand with K columns
+__device__ __forceinline__ uint32_t canon_off(int row, int k, int K) {
+    return (uint32_t)((row >> 3) * (K >> 3) * 128 + (k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2);
+}
+
+// issue the 3-term split product D (+)= A * B^T for K columns; one thread
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int K, uint32_t idesc) {
+    const uint32_t sbo = (uint32_t)(K >> 3) * 128u;
+    uint32_t acc = 0;
+    for (int j = 0; j < K / 16; ++j) {
+        const uint32_t o = (uint32_t)j * 256u;  // two 128-byte core matrices per K = 16 step
+        umma_bf16(tmem_d, umma_desc(a_hi + o, 128, sbo), umma_desc(b_hi + o, 128, sbo), idesc, acc);
+        acc = 1;
+        umma_bf16(tmem_d, umma_desc(a_hi + o, 128, sbo), umma_desc(b_lo + o, 128, sbo), idesc, 1);
+        umma_bf16(tmem_d, umma_desc(a_lo + o, 128, sbo), umma_desc(b_hi + o, 128, sbo), idesc, 1);
+    }
+}
+
+__global__ void __launch_bounds__(128, 1) k_qnet_mlp_tc(TcMlp d, const float* __restrict__ weights, const float* __restrict__ obs, int E,
+                                                         double eps, uint64_t seed, uint64_t step, const double* __restrict__ u_inj,
+                                                         int32_t* __restrict__ actions, float* __restrict__ qout) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    float* f32 = reinterpret_cast<float*>(sm + d.off_f32);   // b1[H1] b2[H2] W3[A][H2] b3[A]
+    float* sb1 = f32; float* sb2 = sb1 + d.H1; float* sw3 = sb2 + d.H2; float* sb3 = sw3 + d.A * d.H2;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + d.off_bar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + d.off_bar + 8);
+
+    // ---- one-time setup: weights -> split BF16 canonical B operands; biases / head -> fp32 ----
+    for (int i = tid; i < d.H1 * d.K1; i += 128) {   // B1[n][k] = W1t[k][n]
+        const int n = i / d.K1, k = i - n * d.K1;
+        unsigned short hi, lo;
+        split_bf16(k < d.nin ? __ldg(weights + d.w1 + k * d.H1 + n) : 0.f, hi, lo);
+        const uint32_t o = canon_off(n, k, d.K1);
+        *reinterpret_cast<unsigned short*>(sm + d.off_w1hi + o) = hi;
+        *reinterpret_cast<unsigned short*>(sm + d.off_w1lo + o) = lo;
+    }
+    for (int i = tid; i < d.H2 * d.H1; i += 128) {   // B2[n][k] = W2t[k][n]
+        const int n = i / d.H1, k = i - n * d.H1;
+        unsigned short hi, lo;
+        split_bf16(__ldg(weights + d.w2 + k * d.H2 + n), hi, lo);
+        const uint32_t o = canon_off(n, k, d.H1);
+        *reinterpret_cast<unsigned short*>(sm + d.off_w2hi + o) = hi;
+        *reinterpret_cast<unsigned short*>(sm + d.off_w2lo + o) = lo;
+    }
+    for (int i = tid; i < d.H1; i += 128) sb1[i] = __ldg(weights + d.b1 + i);
+    for (int i = tid; i < d.H2; i += 128) sb2[i] = __ldg(weights + d.b2 + i);
+    for (int i = tid; i < d.A * d.H2; i += 128) { const int a = i / d.H2, k = i - a * d.H2; sw3[i] = __ldg(weights + d.w3 + k * d.A + a); }
+    for (int i = tid; i < d.A; i += 128) sb3[i] = __ldg(weights + d.b3 + i);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // TMEM allocation by one warp; the address lands in shared memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)d.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+    // instruction descriptor: D = F32 [4,6), A = B = BF16 [7,10) [10,13), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+    const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d.H1 >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d.H2 >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_hi = smem_u32(sm + d.off_ahi), a_lo = smem_u32(sm + d.off_alo);
+    uint32_t parity = 0;
+
+    const int tiles = (E + 127) / 128;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int e0 = tile * 128, rows = min(128, E - e0);
+        // ---- A1 = split(obs tile) in the K1 layout; coalesced reads of the contiguous rows ----
+        const float* src = obs + (size_t)e0 * d.nin;
+        for (int i = tid; i < 128 * d.K1; i += 128) {
+            const int r = i / d.K1, k = i - r * d.K1;
+            unsigned short hi, lo;
+            split_bf16((r < rows && k < d.nin) ? __ldg(src + r * d.nin + k) : 0.f, hi, lo);
+            const uint32_t o = canon_off(r, k, d.K1);
+            *reinterpret_cast<unsigned short*>(sm + d.off_ahi + o) = hi;
+            *reinterpret_cast<unsigned short*>(sm + d.off_alo + o) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {   // layer 1: [128 x K1] x [K1 x H1]
+            issue_layer(tmem, a_hi, a_lo, smem_u32(sm + d.off_w1hi), smem_u32(sm + d.off_w1lo), d.K1, idesc1);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+        }
+        mbar_wait(smem_u32(bar), parity);
+        parity ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue 1: h1 = relu(acc + b1) -> split -> A2 (K = H1 layout); thread t = row t ----
+        for (int c0 = 0; c0 < d.H1; c0 += 32) {
+            uint32_t v[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                         : "r"(tmem_row + (uint32_t)c0) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {  // 8 columns = one 16-byte row of a core matrix
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    unsigned short h0, l0, h1, l1;
+                    split_bf16(fmaxf(__uint_as_float(v[g * 8 + 2 * q]) + sb1[c0 + g * 8 + 2 * q], 0.f), h0, l0);
+                    split_bf16(fmaxf(__uint_as_float(v[g * 8 + 2 * q + 1]) + sb1[c0 + g * 8 + 2 * q + 1], 0.f), h1, l1);
+                    ph[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                    pl[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+                const uint32_t o = canon_off(tid, c0 + g * 8, d.H1);
+                *reinterpret_cast<uint4*>(sm + d.off_ahi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4*>(sm + d.off_alo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {   // layer 2: [128 x H1] x [H1 x H2]
+            issue_layer(tmem, a_hi, a_lo, smem_u32(sm + d.off_w2hi), smem_u32(sm + d.off_w2lo), d.H1, idesc2);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+        }
+        mbar_wait(smem_u32(bar), parity);
+        parity ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue 2: h2 = relu(acc + b2); head (A outputs) and action selection on the CUDA cores ----
+        float q[16];
+        for (int a = 0; a < d.A; ++a) q[a] = sb3[a];
+        for (int c0 = 0; c0 < d.H2; c0 += 32) {
+            uint32_t v[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                         : "r"(tmem_row + (uint32_t)c0) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float h = fmaxf(__uint_as_float(v[j]) + sb2[c0 + j], 0.f);
+                for (int a = 0; a < d.A; ++a) q[a] = fmaf(h, sw3[a * d.H2 + c0 + j], q[a]);
+            }
+        }
+        if (tid < rows) {
+            const int e = e0 + tid;
+            if (qout) for (int a = 0; a < d.A; ++a) qout[(size_t)e * d.A + a] = q[a];
+            actions[e] = select_action(q, d.A, eps, u_inj ? u_inj[e] : uniform_for(seed, step, e));
+        }
+        // all TMEM reads of this tile are done (wait::ld above) before the next tile's MMAs overwrite the accumulators
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)d.tmem_cols) : "memory");
+}
+
 }  // namespace
 
 struct ttrl_qnet {
@@ -266,6 +476,9 @@ struct ttrl_qnet {
     int smem_bytes = 0;
     int n_sms = 0;
     int64_t launches = 0;
+    int mode = 0;       // TTRL_QNET_MODE_FP32 (parity) | TTRL_QNET_MODE_TENSOR (tcgen05 BF16x3, MLP only)
+    bool tc_ok = false;
+    TcMlp tc{};
 };
 
 #define QCK(call)                                                                                  \
@@ -342,7 +555,41 @@ int ttrl_qnet_create(const ttrl_qnet_desc* desc, const float* weights_host, int6
     cudaDeviceProp prop;
     QCK(cudaGetDeviceProperties(&prop, device));
     q->n_sms = prop.multiProcessorCount;
+    // tensor-core path: MLP with two hidden layers whose widths are UMMA N sizes (multiples of 16, <= 256)
+    if (desc->type == TTRL_QNET_MLP && desc->n_hidden == 2 && desc->hidden[0] % 16 == 0 && desc->hidden[1] % 16 == 0 &&
+        desc->hidden[0] >= 16 && desc->hidden[1] >= 16 && desc->hidden[0] <= 256 && desc->hidden[1] <= 256) {
+        TcMlp& t = q->tc;
+        t.nin = nin; t.K1 = (nin + 15) / 16 * 16; t.H1 = desc->hidden[0]; t.H2 = desc->hidden[1]; t.A = desc->n_actions;
+        t.w1 = n.out[0].w_off; t.b1 = n.out[0].b_off; t.w2 = n.out[1].w_off; t.b2 = n.out[1].b_off; t.w3 = n.out[2].w_off; t.b3 = n.out[2].b_off;
+        auto up = [](int x) { return (x + 1023) / 1024 * 1024; };
+        int o = 0;
+        t.off_w1hi = o; o += up(t.H1 * t.K1 * 2);
+        t.off_w1lo = o; o += up(t.H1 * t.K1 * 2);
+        t.off_w2hi = o; o += up(t.H2 * t.H1 * 2);
+        t.off_w2lo = o; o += up(t.H2 * t.H1 * 2);
+        const int ka = t.K1 > t.H1 ? t.K1 : t.H1;
+        t.off_ahi = o; o += up(128 * ka * 2);
+        t.off_alo = o; o += up(128 * ka * 2);
+        t.off_f32 = o; o += up((int)sizeof(float) * (t.H1 + t.H2 + t.A * t.H2 + t.A));
+        t.off_bar = o; o += 16;
+        t.total = o;
+        const int mx = t.H1 > t.H2 ? t.H1 : t.H2;
+        t.tmem_cols = mx <= 32 ? 32 : mx <= 64 ? 64 : mx <= 128 ? 128 : 256;
+        if (t.total <= 227 * 1024 &&
+            cudaFuncSetAttribute(k_qnet_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, t.total) == cudaSuccess)
+            q->tc_ok = true;
+        (void)cudaGetLastError();
+    }
     *out = q;
+    return 0;
+}
+
+int ttrl_qnet_set_mode(ttrl_qnet* q, int mode) {
+    if (!q) return qfail("null argument");
+    if (mode == TTRL_QNET_MODE_FP32) { q->mode = mode; return 0; }
+    if (mode != TTRL_QNET_MODE_TENSOR) return qfail("unknown Q-network mode");
+    if (!q->tc_ok) return qfail("the tensor-core path supports MultiLayerPerceptron with two hidden layers of width 16..256 (multiples of 16) that fit in shared memory");
+    q->mode = mode;
     return 0;
 }
 
@@ -357,6 +604,15 @@ int ttrl_qnet_destroy(ttrl_qnet* q) {
 static int qnet_launch(ttrl_qnet* q, const float* obs_dev, int E, double eps, uint64_t seed, uint64_t step, const double* u_dev,
                        int32_t* actions_dev, float* q_dev, void* stream) {
     QCK(cudaSetDevice(q->device));
+    if (q->mode == TTRL_QNET_MODE_TENSOR) {
+        int grid = (E + 127) / 128;
+        if (grid > q->n_sms) grid = q->n_sms;
+        if (grid < 1) grid = 1;
+        k_qnet_mlp_tc<<<grid, 128, q->tc.total, (cudaStream_t)stream>>>(q->tc, q->d_weights, obs_dev, E, eps, seed, step, u_dev, actions_dev, q_dev);
+        q->launches++;
+        QCK(cudaGetLastError());
+        return 0;
+    }
     const int per = q->net.d.type == TTRL_QNET_EGO_ATTENTION ? 1 : 8;
     const int items = (E + per - 1) / per;
     int grid = (items + kWarps - 1) / kWarps;
