@@ -50,14 +50,14 @@ WORKLOADS = {
                                            "grid_size": [[-32, 32], [-32, 32]], "grid_step": [2, 2], "absolute": False}},
                      label="configs[2]: dense highway 1024 envs x 200 vehicles, OccupancyGrid 7x32x32 obs",
                      bytes_per_env_step=200 * 128 + 4 + 28672 + 8, n_actions=5),
-    "intersection": dict(scene="intersection", E=8192, n=32, over=None,
+    "intersection": dict(scene="intersection", E=8192, n=24, over=None,
                          label="configs[3]: intersection 8192 envs, regulated road, spawn, Kinematics obs",
                          bytes_per_env_step=24 * 128 + 4 + 420 + 8, n_actions=3),
     # BASELINE configs[3] proper: the DQN Q-network rollout (agent.act: forward + epsilon-greedy) in the loop
-    "intersection_qnet": dict(scene="intersection", E=8192, n=32, over=None, qnet="ego_attention_2h",
+    "intersection_qnet": dict(scene="intersection", E=8192, n=24, over=None, qnet="ego_attention_2h",
                               label="configs[3]: intersection 8192 envs + DQN ego-attention (2 heads) Q-net rollout in the loop",
                               bytes_per_env_step=24 * 128 + 4 + 420 + 8 + 420 + 4, n_actions=3),
-    "intersection_qnet_mlp": dict(scene="intersection", E=8192, n=32, over=None, qnet="mlp",
+    "intersection_qnet_mlp": dict(scene="intersection", E=8192, n=24, over=None, qnet="mlp",
                                   label="configs[3]: intersection 8192 envs + DQN MLP [128,128] Q-net rollout in the loop",
                                   bytes_per_env_step=24 * 128 + 4 + 420 + 8 + 420 + 4, n_actions=3),
 }
@@ -254,7 +254,8 @@ def run_ours(args, w):
     if w.get("qnet"):
         from topotrafficrl_b200.agent import QNetRollout
         qnet = QNetRollout(QNET_CONFIGS[w["qnet"]], random_state_dict(w["qnet"], w["n_actions"]), (15, 7), w["n_actions"], device=local_rank,
-                           exploration={"method": "EpsilonGreedy", "temperature": 0.05, "final_temperature": 0.05, "tau": 15000}, seed=7 + rank)
+                           exploration={"method": "EpsilonGreedy", "temperature": 0.05, "final_temperature": 0.05, "tau": 15000}, seed=7 + rank,
+                           mode=args.qnet_mode)
         sim.observe_ptr(obs.data_ptr(), stream)
     obs3 = obs.view(E, -1)
 
@@ -361,14 +362,15 @@ def run_ours(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="highway50", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
-    ap.add_argument("--vcap", type=int, default=0, help="vehicle slots per env (intersection workload; default 32)")
+    ap.add_argument("--vcap", type=int, default=0, help="vehicle slots per env (intersection workloads; default 24)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--qnet-mode", default="fp32", choices=["fp32", "tensor"], help="Q-net arithmetic for the *_qnet* workloads")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -28,10 +28,11 @@ for inp in inputs:
             if m:
                 cur = f"{os.path.basename(m.group(1))}:{m.group(2)}"
                 continue
-            m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(\S+)", ln)
+            m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*)", ln)
             if func and m:
                 line_of[(func, idx)] = cur
-                op_of[(func, idx)] = m.group(1).split(".")[0].rstrip(";")
+                toks = [t for t in m.group(1).replace("{", " ").split() if not t.startswith("@")]
+                op_of[(func, idx)] = toks[0].split(".")[0].rstrip(";") if toks else ""
                 idx += 1
 # 2. ncu sass page
 csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
@@ -61,9 +62,10 @@ for r in rows:
         continue
     done_first = True
     i_s, i_i, i_t = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
-    sass_op = r[1].split()[0].split(".")[0] if r[1].split() and not r[1].split()[0].startswith("@") else (r[1].split()[1].split(".")[0] if len(r[1].split()) > 1 else "")
+    toks = [t for t in r[1].replace("{", " ").split() if not t.startswith("@")]
+    sass_op = toks[0].split(".")[0].rstrip(";") if toks else ""
     want_op = op_of.get((func, k), "")
-    if want_op and sass_op and want_op.lstrip("@!P0123456789UT ") != sass_op and not want_op.startswith("@"):
+    if want_op and sass_op and want_op != sass_op:
         mismatch += 1
     a = agg[line_of.get((func, k), "?")]
     a[0] += int(r[i_s] or 0); a[1] += int(r[i_i] or 0); a[2] += int(r[i_t] or 0)

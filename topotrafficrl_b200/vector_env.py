@@ -71,7 +71,9 @@ class TTRLVectorEnv:
             self.net = scenes.make_intersection_network()
             self.table = self.net.to_table(scenes.intersection_exit_predicate)
             self.cfg = scenes.build_config(self.table, self.config, "intersection")
-            self.vcap = int(vcap or 32)
+            # slot capacity: the reference has no cap; its episodes peak at 15 vehicles, a spawn is
+            # rejected when all slots are taken
+            self.vcap = int(vcap or 24)
             routes = scenes.intersection_spawn_routes(self.net, self.table)
         else:
             raise ValueError(f"unknown scene {scene!r}")
