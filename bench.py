@@ -236,7 +236,8 @@ def run_ours(args, w):
         sim.set_autoreset(True)
     else:
         from topotrafficrl_b200.vector_env import TTRLVectorEnv
-        venv = TTRLVectorEnv(E, scene="intersection", device=local_rank, seed=0, first_env=first_env, vcap=args.vcap or w["n"])
+        venv = TTRLVectorEnv(E, scene="intersection", device=local_rank, seed=0, first_env=first_env, vcap=args.vcap or w["n"],
+                             reset_mode=args.reset_mode)
         venv.reset()
         sim = venv.sim
 
@@ -336,7 +337,7 @@ def run_ours(args, w):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["label"], "envs_per_gpu": E, "vehicles_per_env": w["n"], "sub_steps_per_step": 15,
-                       "autoreset": True, "l2": "flushed between timed steps (256 MB fill)",
+                       "autoreset": ("pool of initial states" if w["scene"] == "highway" or args.reset_mode == "host" else "device-side fresh reset"), "l2": "flushed between timed steps (256 MB fill)",
                        "target": "1e8 vehicle-steps/s per B200 (BASELINE.json north_star)"},
             "e2e": {"value": float(e2e_v.item()) / float(e2e_t.item()), "unit": "vehicle-steps/s",
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
@@ -370,6 +371,8 @@ def main():
     ap.add_argument("--vcap", type=int, default=0, help="vehicle slots per env (intersection workloads; default 24)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reset-mode", default="device", choices=["device", "host"],
+                    help="intersection workloads: device = fresh episodes generated on the GPU at every autoreset (the reference's _make_vehicles incl. its 45 warm-up sub-steps); host = replay a pool of host-generated initial states")
     ap.add_argument("--qnet-mode", default="fp32", choices=["fp32", "tensor"], help="Q-net arithmetic for the *_qnet* workloads")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -142,13 +142,32 @@ typedef struct ttrl_episode_stats {
     double episodes, total_return, total_length, crashes, arrivals, total_speed, vehicle_steps, env_steps;
 } ttrl_episode_stats;
 
+/* Device-side reset: fresh episodes generated on the GPU with counter-based (Philox) draws
+ * keyed by (seed, global env, episode, draw), following the reference's procedures:
+ *   scene 0: synthetic highway, Vehicle.create_random's placement rule (kinematics.py:50-104) + randomize_behavior;
+ *   scene 1: IntersectionEnv._make_vehicles (intersection_env.py:251-318): staggered spawn attempts, warm-up
+ *            sub-steps, challenger, MDPVehicle ego with its route, pruning of vehicles within 20 m of the ego. */
+#define TTRL_MAX_SPAWN_ATTEMPTS 32
+typedef struct ttrl_reset_params {
+    int32_t scene;            /* 0 highway, 1 intersection */
+    int32_t n_vehicles;       /* highway: vehicles per env incl. the ego; intersection: initial_vehicle_count */
+    int32_t lanes;            /* highway: lanes of road 0 */
+    int32_t ego_entry;        /* intersection: corner of the ego's start lane (o<k>, ir<k>, 0) */
+    int32_t destination;      /* intersection: exit corner 0..3, or -1 = drawn per episode ("destination": None) */
+    int32_t warmup_substeps;  /* intersection: 3 * simulation_frequency (intersection_env.py:267-274) */
+    int32_t pad0, pad1;
+    double speed_limit, density, ego_spacing, ego_speed;          /* highway */
+    double ego_longitudinal, ego_longitudinal_std;                /* intersection: 60 + 5 * N(1, 1) -> 60, 5 */
+    double spawn_longitudinal[TTRL_MAX_SPAWN_ATTEMPTS];           /* intersection: np.linspace(0, 80, n)[t] */
+} ttrl_reset_params;
+
 typedef struct ttrl_sim ttrl_sim;
 typedef struct ttrl_qnet ttrl_qnet;
 
 const char* ttrl_last_error(void);
 void ttrl_set_error(const char* msg);
 int ttrl_abi_version(void);
-/* sizeof of the POD structs as compiled (0 lane, 1 road, 2 config, 3 spawn_draw, 4 episode_stats, 5 qnet_desc): binding self-check */
+/* sizeof of the POD structs as compiled (0 lane, 1 road, 2 config, 3 spawn_draw, 4 episode_stats, 5 qnet_desc, 6 reset_params): binding self-check */
 int ttrl_abi_sizeof(int which);
 
 /* Create E env instances with V vehicle slots each on CUDA device `device`.
@@ -177,7 +196,14 @@ int ttrl_sim_get_state(ttrl_sim* sim, double* veh_d, int32_t* veh_i, int32_t* en
  * AbstractEnv.reset, abstract.py:188-214).  Env e restarts from pool entry (e + k*E) mod pool_size at its k-th reset. */
 int ttrl_sim_set_reset_pool(ttrl_sim* sim, int pool_size, const double* veh_d, const int32_t* veh_i,
                             const int32_t* env_i, const double* env_d);
-int ttrl_sim_set_autoreset(ttrl_sim* sim, int enabled);
+/* autoreset mode of ttrl_sim_step: 0 = off, 1 = restart finished envs from the reset pool, 2 = device-side reset
+ * (ttrl_sim_set_reset_params must have been called). */
+enum { TTRL_AUTORESET_OFF = 0, TTRL_AUTORESET_POOL = 1, TTRL_AUTORESET_DEVICE = 2 };
+int ttrl_sim_set_autoreset(ttrl_sim* sim, int mode);
+int ttrl_sim_set_reset_params(ttrl_sim* sim, const ttrl_reset_params* params);
+/* Device-side reset of every env (mask_dev == NULL) or of the envs with mask_dev[e] != 0; replaces
+ * AbstractEnv.reset (abstract.py:188-214) for a batch.  Uses the seed of ttrl_sim_seed. */
+int ttrl_sim_reset(ttrl_sim* sim, const uint8_t* mask_dev, void* stream);
 
 /* One simulation sub-step for every env: [ego meta-action if steps % F == 0] -> Road.act -> (regulation)
  * -> Road.step.  Replaces one iteration of AbstractEnv._simulate (abstract.py:257-273).

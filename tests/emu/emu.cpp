@@ -162,5 +162,21 @@ void emu_spawn(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double*
     });
 }
 
+void emu_scene_set_reset_params(SceneDev* s, const ttrl_reset_params* rp) { s->rp = *rp; s->have_rp = 1; }
+void emu_reset(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, uint64_t seed, int64_t first_global_env, int episode) {
+    GlobalState g{vd, vi, ei, ed, E, Vs};
+    DISPATCH(Vs, {
+        HostEnv<V> env(sc, Vs);
+        HostExec ex{V};
+        for (int e = 0; e < E; ++e) {
+            env_reset(env.c, ex, seed, first_global_env + e, episode);
+            store_env(env.c, ex, g, e);
+        }
+    });
+}
+void emu_reset_attempt_draw(uint64_t seed, int64_t env, int episode, int attempt, ttrl_spawn_draw* out) {
+    device_spawn_draw(seed, env, reset_attempt_counter(episode, attempt), *out);
+}
+void emu_reset_uniforms(uint64_t seed, int64_t env, int episode, uint32_t idx, double* out) { reset_uniforms(seed, env, episode, idx, out[0], out[1]); }
 void emu_device_spawn_draw(uint64_t seed, int64_t env, uint64_t counter, ttrl_spawn_draw* out) { device_spawn_draw(seed, env, counter, *out); }
 }

@@ -71,6 +71,23 @@ class Emulator:
                         C.c_int(int(self.autoreset)), C.c_uint64(seed), C.c_int64(first_env))
         return obs, reward, term, trunc, acc
 
+    def set_reset_params(self, rp):
+        self.L.emu_scene_set_reset_params(self.sc, C.byref(rp))
+
+    def reset(self, st: SimState, seed: int, first_env: int = 0, episode: int = 0):
+        self.L.emu_reset(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(st.num_envs), C.c_int(st.vcap),
+                         C.c_uint64(seed), C.c_int64(first_env), C.c_int(episode))
+
+    def reset_attempt_draw(self, seed: int, env: int, episode: int, attempt: int) -> abi.SpawnDraw:
+        d = abi.SpawnDraw()
+        self.L.emu_reset_attempt_draw(C.c_uint64(seed), C.c_int64(env), C.c_int(episode), C.c_int(attempt), C.byref(d))
+        return d
+
+    def reset_uniforms(self, seed: int, env: int, episode: int, idx: int):
+        out = (C.c_double * 2)()
+        self.L.emu_reset_uniforms(C.c_uint64(seed), C.c_int64(env), C.c_int(episode), C.c_uint32(idx), out)
+        return out[0], out[1]
+
     def spawn(self, st, draws, longitudinal, position_deviation=1.0, speed_deviation=1.0, spawn_probability=0.6, go_straight=False):
         acc = np.zeros(st.num_envs, np.int32)
         self.L.emu_spawn(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(st.num_envs), C.c_int(st.vcap), draws,

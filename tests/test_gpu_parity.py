@@ -301,3 +301,68 @@ def test_task_queue_stress_vs_oracle(n, density):
         np.testing.assert_allclose(obs, oo, rtol=0, atol=2e-6)
         assert (term == ot).all() and (trunc == ou).all()
     sim.close()
+
+
+def test_device_reset_equals_emulated_logic_and_autoreset_fresh_episodes():
+    """ttrl_sim_reset on the GPU == the same device logic run on the host (which tests/test_host_logic.py ties to the
+    reference's _make_vehicles); device autoreset gives every finished env a NEW episode; oracle agreement on the
+    dynamics that follow a device reset."""
+    from oracle import oracle as O
+    from tests.emu.emu import Emulator
+    from topotrafficrl_b200.state import SimState
+    torch = _torch()
+    # intersection
+    net, table, cfg, routes = T.intersection_scene()
+    cfgd = scenes.merged_config(scenes.INTERSECTION_CONFIG, None)
+    rp = scenes.intersection_reset_params(cfgd)
+    E = 64
+    sim = _sim(cfg, table, E, 24, routes)
+    sim.set_reset_params(rp)
+    sim.seed(12345, 500)
+    sim.reset_device()
+    got = sim.get_state()
+    emu = Emulator(cfg, table, routes)
+    emu.set_reset_params(rp)
+    want = SimState.zeros(E, 24)
+    emu.reset(want, 12345, 500, 0)
+    T.compare_states(got, want, 1e-9, "device reset (intersection)")
+    # masked reset: only the flagged envs restart, with episode + 1
+    mask = torch.zeros(E, dtype=torch.uint8, device="cuda")
+    mask[::3] = 1
+    sim.reset_device(mask.data_ptr())
+    after = sim.get_state()
+    keep = np.ones(E, bool)
+    keep[::3] = False
+    np.testing.assert_array_equal(after.veh_d[:, keep], got.veh_d[:, keep])
+    assert (after.env_i[abi.EI_EPISODE, ~keep] == 1).all() and (after.env_i[abi.EI_EPISODE, keep] == 0).all()
+    assert not np.array_equal(after.veh_d[:, ~keep], got.veh_d[:, ~keep])
+    sim.close()
+    # highway: device reset, then dynamics vs the oracle, then device autoreset inside the step kernel
+    _, table, cfg, cfgd = T.highway_scene(50, 2.0, overrides={"duration": 2})
+    sim = _sim(cfg, table, 96, 50)
+    sim.set_reset_params(scenes.highway_reset_params(cfgd))
+    sim.seed(99, 0)
+    sim.reset_device()
+    ref = sim.get_state()
+    first = ref.copy()
+    orc = O.Oracle(cfg, table, threads=8)
+    rng = np.random.default_rng(3)
+    act = rng.integers(0, 5, size=96).astype(np.int32)
+    obs, rew, term, trunc = _dev_step(sim, act)
+    oo, orr, ot, ou, _ = orc.step(ref, act)
+    T.compare_states(sim.get_state(), ref, 1e-7, "step after device reset")
+    np.testing.assert_allclose(obs, oo, rtol=0, atol=2e-6)
+    sim.set_autoreset("device")
+    obs, rew, term, trunc = _dev_step(sim, act)  # duration 2 -> every env is truncated here and restarts
+    assert (term | trunc).all()
+    st = sim.get_state()
+    assert (st.env_i[abi.EI_EPISODE] == 1).all() and (st.env_i[abi.EI_STEPS] == 0).all() and (st.env_d[abi.ED_TIME] == 0).all()
+    assert (st.env_i[abi.EI_NVEH] == 50).all()
+    assert not np.array_equal(st.veh_d[abi.D_X], first.veh_d[abi.D_X])  # a fresh scene, not the first one again
+    emu = Emulator(cfg, table)
+    emu.set_reset_params(scenes.highway_reset_params(cfgd))
+    want = SimState.zeros(96, 50)
+    emu.reset(want, 99, 0, 1)
+    T.compare_states(st, want, 1e-9, "device autoreset (highway)")
+    np.testing.assert_allclose(obs, emu.observe(want), rtol=0, atol=2e-6)
+    sim.close()

@@ -136,3 +136,84 @@ def test_host_driven_reset_reproduces_reference_resets():
     T.compare_states(st, want, 1e-9, "reset", check_action=True)
     obs = emu.observe(backend.st)
     np.testing.assert_allclose(obs.reshape(g["obs"].shape), g["obs"], rtol=0, atol=2e-6)
+
+
+class _DeviceDrawRng:
+    """Feeds ``reset_intersection`` (the host-driven reset, validated against the reference's resets above) with
+    the draws the DEVICE-side reset makes for one env, so both procedures can be compared state for state."""
+
+    class _BG:
+        state = None
+
+    def __init__(self, emu, seed, env, episode):
+        self.emu, self.seed, self.env, self.episode = emu, seed, env, episode
+        self.attempt, self.cur, self.normals = -1, None, 0
+        self.bit_generator = self._BG()
+
+    def uniform(self, low=None, high=None):
+        if low is None:  # u_spawn opens a new _spawn_vehicle call
+            self.attempt += 1
+            self.cur = self.emu.reset_attempt_draw(self.seed, self.env, self.episode, self.attempt)
+            self.normals = 0
+            return self.cur.u_spawn
+        return self.cur.delta
+
+    def choice(self, *a, **k):
+        return np.array([self.cur.entry, self.cur.exit])
+
+    def normal(self, loc=0.0):
+        if loc == 1:  # the ego's longitudinal draw: 5 * normal(1)
+            u0, u1 = self.emu.reset_uniforms(self.seed, self.env, self.episode, 0x100)
+            return 1.0 + np.sqrt(-2.0 * np.log(1.0 - u0)) * np.cos(2 * np.pi * u1)
+        self.normals += 1
+        return self.cur.n_pos if self.normals == 1 else self.cur.n_speed
+
+
+def test_device_reset_follows_make_vehicles():
+    """Device-side IntersectionEnv reset (emulated device logic) == the host-driven reset fed the same draws."""
+    net, table, cfg, routes = T.intersection_scene()
+    cfgd = scenes.merged_config(scenes.INTERSECTION_CONFIG, None)
+    emu = Emulator(cfg, table, routes)
+    emu.set_reset_params(scenes.intersection_reset_params(cfgd))
+    E, seed, first, episode = 12, 77, 1000, 3
+    got = SimState.zeros(E, 32)
+    emu.reset(got, seed, first, episode)
+    backend = _EmuBackend(emu, E, 32)
+    rngs = [_DeviceDrawRng(emu, seed, first + e, episode) for e in range(E)]
+    want = reset_intersection(backend, rngs, net, table, cfgd, cfg)
+    want.env_i[abi.EI_EPISODE] = episode
+    T.compare_states(got, want, 1e-12, "device reset")
+    assert (got.env_i[abi.EI_EPISODE] == episode).all() and (got.env_i[abi.EI_NVEH] >= 1).all()
+    egos = got.env_i[abi.EI_EGO]
+    assert all(got.veh_i[abi.I_FLAGS, e, egos[e]] & abi.FL_MDP for e in range(E))
+    assert len({tuple(np.round(got.veh_d[abi.D_Y, e, : got.env_i[abi.EI_NVEH, e]], 3)) for e in range(E)}) > E // 2  # envs differ
+
+
+def test_device_highway_reset_properties():
+    """Device-side highway reset: create_random's spacing rule, value ranges, determinism and shard invariance."""
+    _, table, cfg, cfgd = T.highway_scene(50, 2.0)
+    emu = Emulator(cfg, table)
+    emu.set_reset_params(scenes.highway_reset_params(cfgd))
+    a = SimState.zeros(6, 50)
+    emu.reset(a, 5, 0, 0)
+    b = SimState.zeros(3, 50)
+    emu.reset(b, 5, 3, 0)
+    np.testing.assert_array_equal(a.veh_d[:, 3:], b.veh_d)  # keyed by the GLOBAL env id
+    np.testing.assert_array_equal(a.veh_i[:, 3:], b.veh_i)
+    c = SimState.zeros(6, 50)
+    emu.reset(c, 5, 0, 1)
+    assert not np.array_equal(a.veh_d, c.veh_d)  # next episode, new draws
+    assert (a.env_i[abi.EI_NVEH] == 50).all() and (a.env_i[abi.EI_EGO] == 0).all()
+    x, y, v = a.veh_d[abi.D_X], a.veh_d[abi.D_Y], a.veh_d[abi.D_SPEED]
+    assert (np.diff(x, axis=1) > 0).all()
+    lane = a.veh_i[abi.I_LANE]
+    assert ((lane >= 0) & (lane < 4)).all() and np.array_equal(y, lane * 4.0)
+    assert (v[:, 0] == 25.0).all() and ((v[:, 1:] >= 21.0) & (v[:, 1:] <= 24.0)).all()
+    lf = np.exp(-5 / 40 * 4)
+    off = (1 / 2.0) * (12 + v[:, 1:]) * lf
+    gaps = np.diff(x, axis=1)
+    assert ((gaps >= 0.9 * off - 1e-9) & (gaps <= 1.1 * off + 1e-9)).all()
+    d = a.veh_d[abi.D_DELTA][:, 1:]
+    assert ((d >= 3.5) & (d <= 4.5)).all()
+    np.testing.assert_allclose(a.veh_d[abi.D_TIMER][:, 1:], ((x[:, 1:] + y[:, 1:]) * np.pi) % 1.0, atol=1e-9)
+    assert len(np.unique(lane[:, 1:])) == 4

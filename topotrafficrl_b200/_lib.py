@@ -51,6 +51,8 @@ def lib():
     L.ttrl_sim_get_state.argtypes = [vp, vp, vp, vp, vp]
     L.ttrl_sim_set_reset_pool.argtypes = [vp, i32, vp, vp, vp, vp]
     L.ttrl_sim_set_autoreset.argtypes = [vp, i32]
+    L.ttrl_sim_set_reset_params.argtypes = [vp, C.POINTER(abi.ResetParams)]
+    L.ttrl_sim_reset.argtypes = [vp, vp, vp]
     L.ttrl_sim_seed.argtypes = [vp, u64, i64]
     L.ttrl_sim_inject_spawn.argtypes = [vp, vp]
     L.ttrl_sim_inject_shuffle.argtypes = [vp, vp]

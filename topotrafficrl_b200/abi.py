@@ -85,6 +85,18 @@ class SpawnDraw(C.Structure):
                 ("n_pos", C.c_double), ("n_speed", C.c_double), ("delta", C.c_double)]
 
 
+MAX_SPAWN_ATTEMPTS = 32
+AUTORESET_OFF, AUTORESET_POOL, AUTORESET_DEVICE = 0, 1, 2
+
+
+class ResetParams(C.Structure):
+    _fields_ = [("scene", C.c_int32), ("n_vehicles", C.c_int32), ("lanes", C.c_int32), ("ego_entry", C.c_int32),
+                ("destination", C.c_int32), ("warmup_substeps", C.c_int32), ("pad0", C.c_int32), ("pad1", C.c_int32),
+                ("speed_limit", C.c_double), ("density", C.c_double), ("ego_spacing", C.c_double), ("ego_speed", C.c_double),
+                ("ego_longitudinal", C.c_double), ("ego_longitudinal_std", C.c_double),
+                ("spawn_longitudinal", C.c_double * MAX_SPAWN_ATTEMPTS)]
+
+
 class EpisodeStats(C.Structure):
     _fields_ = [("episodes", C.c_double), ("total_return", C.c_double), ("total_length", C.c_double),
                 ("crashes", C.c_double), ("arrivals", C.c_double), ("total_speed", C.c_double),

@@ -56,6 +56,8 @@ struct SceneDev {
     int32_t spawn_lane[4];
     int32_t spawn_route_len[16];
     int32_t spawn_route_road[16 * TTRL_ROUTE_CAP];
+    ttrl_reset_params rp;  // device-side reset parameters (have_rp != 0)
+    int32_t have_rp, pad_rp;
     int32_t F;           // sub-steps per env-step (abstract.py:254-256)
     int32_t reg_period;  // int(1/dt/REGULATION_FREQUENCY) (regulation.py:30)
     double dt;           // 1/simulation_frequency
@@ -966,7 +968,7 @@ TT_HD void regulate_apply(C& c, int i) {
 // one simulation sub-step (AbstractEnv._simulate body abstract.py:257-273)
 // ------------------------------------------------------------------------------------------------
 template <class C, class Exec>
-TT_HD void env_substep(C& c, Exec& ex, int raw_action) {
+TT_HD void env_substep(C& c, Exec& ex, int raw_action) {  // inlined on purpose: a call boundary here costs ~30 % (ctx spills)
     auto* st = c.st;
     const SceneDev* sc = c.sc;
     using ES = EnvState<C::V>;
@@ -1437,10 +1439,13 @@ TT_HD double u01(uint32_t hi, uint32_t lo) {  // 53-bit uniform in [0,1)
     const uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
     return (double)x * (1.0 / 9007199254740992.0);
 }
+// `counter` = steps | episode << 32 for the per-step spawn, (1 << 63) | episode << 8 | attempt for the reset attempts
 TT_HDN void device_spawn_draw(uint64_t seed, int64_t global_env, uint64_t counter, ttrl_spawn_draw& d) {
-    uint32_t a[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), (uint32_t)counter, 0u};
-    uint32_t b[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), (uint32_t)counter, 1u};
-    uint32_t e[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), (uint32_t)counter, 2u};
+    const uint32_t ctr = (uint32_t)counter ^ ((uint32_t)(counter >> 32) * 0x9E3779B1u);
+    const uint32_t dom = (uint32_t)(counter >> 63) << 4;
+    uint32_t a[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), ctr, dom | 0u};
+    uint32_t b[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), ctr, dom | 1u};
+    uint32_t e[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), ctr, dom | 2u};
     philox4x32(a, (uint32_t)seed, (uint32_t)(seed >> 32));
     philox4x32(b, (uint32_t)seed, (uint32_t)(seed >> 32));
     philox4x32(e, (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -1453,6 +1458,182 @@ TT_HDN void device_spawn_draw(uint64_t seed, int64_t global_env, uint64_t counte
     d.n_pos = rad * cos(2 * kPi * u2);
     d.n_speed = rad * sin(2 * kPi * u2);
     d.delta = 3.5 + u01(e[2], e[3]) * (4.5 - 3.5);       // behavior.py:66-69
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// device-side reset
+// ------------------------------------------------------------------------------------------------
+// two uniforms of the reset stream, keyed by (seed, global env, episode, index)
+TT_HD void reset_uniforms(uint64_t seed, int64_t genv, int episode, uint32_t idx, double& u0, double& u1) {
+    uint32_t c4[4] = {(uint32_t)genv, (uint32_t)((uint64_t)genv >> 32), (uint32_t)episode, 0x52000000u | idx};
+    philox4x32(c4, (uint32_t)seed, (uint32_t)(seed >> 32));
+    u0 = u01(c4[0], c4[1]);
+    u1 = u01(c4[2], c4[3]);
+}
+TT_HD uint64_t reset_attempt_counter(int episode, int attempt) { return (1ull << 63) | ((uint64_t)(uint32_t)episode << 8) | (uint64_t)attempt; }
+
+template <class C, class Exec>
+TT_HD void reset_scalars(C& c, Exec& ex, int episode) {
+    auto* st = c.st;
+    if (ex.first()) {
+        st->n = 0; st->steps = 0; st->road_steps = 0; st->ego = 0; st->episode = episode; st->done = 0;
+        st->time = 0; st->ret = 0;
+        st->n_chg = st->n_mob = st->n_pair = st->n_w = st->overflow = 0;
+        for (int w = 0; w < C::W; ++w) st->bmask[w] = 0;
+    }
+    ex.par([&](int t) {
+        st->pos[t] = d2{0, 0}; st->cs[t] = d2{1, 0}; st->imp[t] = d2{0, 0};
+        st->h[t] = st->v[t] = st->steer[t] = st->acc[t] = st->tspeed[t] = st->timer[t] = st->delta[t] = 0;
+        st->acc2[t] = st->tsteer[t] = 0; st->thr2[t] = 0;
+        st->lane[t] = st->tlane[t] = st->flags[t] = st->sidx[t] = st->rlen[t] = st->ytimer[t] = 0;
+        st->rroad[t] = st->rlanew[t] = 0;
+        st->mark[t] = 0; st->tl_old[t] = 0; st->best[t] = -1; st->fo[t] = -1;
+    });
+    ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; });
+}
+
+// Synthetic highway: Vehicle.create_random's rule (kinematics.py:91-103): every new vehicle goes
+// offset * U[0.9, 1.1] ahead of the furthest one, offset = spacing (12 + speed) exp(-5/40 lanes), on a uniformly
+// random lane at U[0.7, 0.8] speed_limit; slot 0 is the MDPVehicle ego; IDMVehicle DELTA ~ U[3.5, 4.5]
+// (behavior.py:66-69), timer = (x + y) pi mod 1 (behavior.py:64).  Same rule as scenes.make_highway_state.
+template <class C, class Exec>
+TT_HD void reset_highway(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) {
+    auto* st = c.st;
+    const ttrl_reset_params& rp = c.sc->rp;
+    const ttrl_config& cfg = c.sc->cfg;
+    reset_scalars(c, ex, episode);
+    const int n = rp.n_vehicles < c.vcap ? rp.n_vehicles : c.vcap;
+    const double lane_factor = exp(-5.0 / 40 * rp.lanes);
+    ex.parn(n, [&](int s) {
+        double u_lane, u_speed, u_jit, u_delta;
+        reset_uniforms(seed, genv, episode, 2u * s, u_lane, u_speed);
+        reset_uniforms(seed, genv, episode, 2u * s + 1u, u_jit, u_delta);
+        int lid = (int)(u_lane * rp.lanes);
+        if (lid > rp.lanes - 1) lid = rp.lanes - 1;
+        const double speed = s == 0 ? rp.ego_speed : (0.7 + 0.1 * u_speed) * rp.speed_limit;
+        const double spacing = s == 0 ? rp.ego_spacing : 1.0 / rp.density;
+        const double offset = spacing * (12 + 1.0 * speed) * lane_factor;
+        st->acc2[s] = offset * (0.9 + 0.2 * u_jit) + (s == 0 ? 3 * offset : 0.0);  // advance relative to the previous vehicle
+        st->v[s] = speed;
+        st->tspeed[s] = speed;
+        st->lane[s] = st->tlane[s] = c.sc->roads[0].first_lane + lid;
+        st->delta[s] = s == 0 ? 4.0 : 3.5 + u_delta;
+        st->rlen[s] = -1;  // route None
+        if (s == 0) {
+            st->flags[s] = TTRL_FL_MDP | TTRL_FL_CONTROLLED;
+            st->sidx[s] = speed_to_index(cfg, speed);
+            st->tspeed[s] = cfg.target_speeds[st->sidx[s]];
+        }
+    });
+    if (ex.first()) {  // positions: cumulative advances, in slot order
+        double x = 0;
+        for (int s = 0; s < n; ++s) {
+            x += st->acc2[s];
+            double px, py;
+            lane_position(c.lanes[st->lane[s]], x, 0.0, px, py);
+            st->pos[s] = d2{px, py};
+            st->h[s] = lane_heading_at(c.lanes[st->lane[s]], x);
+            st->cs[s] = d2{cos(st->h[s]), sin(st->h[s])};
+            st->timer[s] = s == 0 ? 0.0 : py_mod1((px + py) * kPi);
+            st->acc2[s] = 0;
+        }
+        st->n = n;
+        st->ego = 0;
+    }
+    ex.sync();
+    rebuild_tables(c, ex);
+}
+
+// IntersectionEnv._make_vehicles (intersection_env.py:251-318)
+template <class C, class Exec>
+TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) {
+    auto* st = c.st;
+    const SceneDev* sc = c.sc;
+    const ttrl_reset_params& rp = sc->rp;
+    const ttrl_config& cfg = sc->cfg;
+    reset_scalars(c, ex, episode);
+    // staggered spawn attempts (:265-266), default _spawn_vehicle arguments (spawn_probability 0.6)
+    for (int t = 0; t < rp.n_vehicles - 1; ++t) {
+        ttrl_spawn_draw d;
+        device_spawn_draw(seed, genv, reset_attempt_counter(episode, t), d);
+        SpawnParams sp{rp.spawn_longitudinal[t], 1.0, 1.0, 0.6, 0};
+        spawn_vehicle(c, ex, d, sp);
+    }
+    rebuild_tables(c, ex);
+    for (int k = 0; k < rp.warmup_substeps; ++k) env_substep(c, ex, -1);  // (:267-274) road.act(); road.step(1/sf)
+    {   // challenger vehicle (:276-277)
+        ttrl_spawn_draw d;
+        device_spawn_draw(seed, genv, reset_attempt_counter(episode, rp.n_vehicles - 1), d);
+        SpawnParams sp{60.0, 0.1, 0.0, 1.0, 1};
+        spawn_vehicle(c, ex, d, sp);
+    }
+    if (ex.first()) {
+        // ego MDPVehicle (:286-307) at ego_longitudinal + std * N(1, 1) on (o<k>, ir<k>, 0), speed = speed_limit
+        double u0, u1, ud, unused;
+        reset_uniforms(seed, genv, episode, 0x100u, u0, u1);
+        reset_uniforms(seed, genv, episode, 0x101u, ud, unused);
+        const double z = sqrt(-2.0 * log(1.0 - u0)) * cos(2 * kPi * u1);
+        const int entry = rp.ego_entry;
+        const ttrl_lane& el = c.lanes[sc->spawn_lane[entry]];
+        double px, py;
+        lane_position(el, rp.ego_longitudinal + rp.ego_longitudinal_std * (1.0 + z), 0.0, px, py);
+        int s = st->n;
+        if (s >= c.vcap) s = c.vcap - 1;  // full: the ego replaces the last vehicle
+        st->pos[s] = d2{px, py};
+        st->h[s] = lane_heading_at(el, rp.ego_longitudinal);
+        st->cs[s] = d2{cos(st->h[s]), sin(st->h[s])};
+        st->v[s] = el.speed_limit;
+        st->steer[s] = 0; st->acc[s] = 0; st->imp[s] = d2{0, 0}; st->timer[s] = 0; st->delta[s] = 4.0;
+        uint64_t m;
+        const int ln = table_row_and_closest(c, s, m);  // RoadObject.__init__ objects.py:45-50
+        st->lane[s] = ln; st->tlane[s] = ln;
+        st->sidx[s] = speed_to_index(cfg, st->v[s]);    // MDPVehicle.__init__ controller.py:283-293
+        st->tspeed[s] = cfg.target_speeds[st->sidx[s]];
+        st->flags[s] = TTRL_FL_MDP | TTRL_FL_CONTROLLED;
+        st->ytimer[s] = 0;
+        int dest = rp.destination;
+        if (dest < 0) { dest = 1 + (int)(ud * 3.0); if (dest > 3) dest = 3; dest = (entry + dest) % 4; }  // "o" + str(integers(1, 4))
+        const int nr = sc->spawn_route_len[entry * 4 + dest];
+        uint32_t rr = (uint32_t)c.lanes[ln].road, rl = (uint32_t)c.lanes[ln].lane_id;
+        for (int k = 0; k < nr; ++k) {
+            rr |= (uint32_t)(sc->spawn_route_road[(entry * 4 + dest) * TTRL_ROUTE_CAP + k] & 0xFF) << (8 * (k + 1));
+            rl |= 0xFFu << (8 * (k + 1));
+        }
+        st->rlen[s] = 1 + nr; st->rroad[s] = rr; st->rlanew[s] = rl;
+        const int n0 = s + 1;
+        // "prevent early collisions" (:313-318): list.remove() while iterating skips the element after each removal
+        int* order = st->chg;
+        int len = n0;
+        for (int k = 0; k < n0; ++k) order[k] = k;
+        for (int i = 0; i < len; ++i) {
+            const int v = order[i];
+            if (v == s) continue;
+            const double dx = st->pos[v].x - px, dy = st->pos[v].y - py;
+            if (sqrt(dx * dx + dy * dy) < 20) {
+                for (int k = i; k + 1 < len; ++k) order[k] = order[k + 1];
+                --len;
+            }
+        }
+        int ego = 0;
+        for (int dst = 0; dst < len; ++dst) {
+            const int src = order[dst];
+            if (src == s) ego = dst;
+            if (src != dst) { SlotRegs r; slot_read(c, src, r); slot_write(c, dst, r); }
+        }
+        st->n = len;
+        st->ego = ego;
+        st->steps = 0;
+        st->n_chg = 0;
+    }
+    ex.sync();
+    rebuild_tables(c, ex);
+}
+
+template <class C, class Exec>
+TT_HDN void env_reset(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) {  // cold path: keep it out of the step loop's code
+    if (c.sc->rp.scene == 1) reset_intersection(c, ex, seed, genv, episode);
+    else reset_highway(c, ex, seed, genv, episode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1533,7 +1714,12 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
         }
         ex.sync();
     }
-    if (st->done && io.autoreset && io.pool.E > 0) {  // uniform: st->done is in shared memory
+    if (st->done && io.autoreset == TTRL_AUTORESET_DEVICE && sc->have_rp) {  // uniform: st->done is in shared memory
+        const int episode = st->episode + 1;
+        ex.sync();
+        env_reset(c, ex, io.seed, io.first_global_env + e, episode);
+        if (obs) observe(c, ex, obs, perm);
+    } else if (st->done && io.autoreset == TTRL_AUTORESET_POOL && io.pool.E > 0) {
         const int episode = st->episode + 1;
         const int slot = (int)(((long long)e + (long long)episode * g.E) % io.pool.E);
         ex.sync();

@@ -93,10 +93,10 @@ struct DevExec {
 #error "compile with -DTT_V=<slot capacity>"
 #endif
 #ifndef TT_T
-#define TT_T (TT_V <= 32 ? 32 : TT_V <= 64 ? 64 : 128)
+#define TT_T (TT_V <= 32 ? 32 : TT_V <= 64 ? 64 : TT_V <= 128 ? 128 : 256)
 #endif
 #ifndef TT_MINB
-#define TT_MINB (TT_V <= 32 ? 1 : TT_V <= 64 ? 10 : 1)
+#define TT_MINB (TT_V <= 32 ? 1 : TT_V <= 64 ? 10 : TT_V <= 128 ? 5 : 3)
 #endif
 template <int V> struct TeamOf { static constexpr int T = TT_T, MINB = TT_MINB; };
 
@@ -169,6 +169,18 @@ __global__ void __launch_bounds__(TeamOf<V>::T) k_spawn(const SceneDev* __restri
 }
 
 
+// AbstractEnv.reset for every (masked) env: a fresh episode generated on the device (ttrl_core.cuh: env_reset)
+template <int V>
+__global__ void __launch_bounds__(TeamOf<V>::T) k_reset(const SceneDev* __restrict__ sc, GlobalState g, const uint8_t* __restrict__ mask, uint64_t seed,
+                                                        int64_t first_global_env, SmemLayout lay) {
+    TT_KERNEL_PROLOGUE
+    const int e = blockIdx.x;
+    if (mask && !mask[e]) return;  // uniform per CTA
+    const int episode = mask ? g.ei[TTRL_EI_EPISODE * g.E + e] + 1 : 0;
+    env_reset(c, ex, seed, first_global_env + e, episode);
+    store_env(c, ex, g, e);
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch table
 // ------------------------------------------------------------------------------------------------
@@ -192,6 +204,7 @@ static int configure(const ttrl_config& cfg, int vcap, SmemLayout* out) {
     if ((e = cudaFuncSetAttribute(k_substep<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_observe<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_spawn<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_reset<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     // all of the SM's unified L1/shared storage as shared memory: resident CTAs are what hides latency here
     cudaFuncSetAttribute(k_step<V>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return 0;
@@ -215,9 +228,15 @@ static void launch_spawn(int E, const SmemLayout& lay, cudaStream_t st, const Sc
     k_spawn<V><<<E, TeamOf<V>::T, lay.total, st>>>(sc, g, draws, sp, accepted, lay);
 }
 
+template <int V>
+static void launch_reset(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const uint8_t* mask, uint64_t seed,
+                         int64_t first_global_env) {
+    k_reset<V><<<E, TeamOf<V>::T, lay.total, st>>>(sc, g, mask, seed, first_global_env, lay);
+}
+
 #define TT_CAT_(a, b) a##b
 #define TT_CAT(a, b) TT_CAT_(a, b)
 extern "C" const KernelSet* TT_CAT(ttrl_kernel_set_, TT_V)(void) {
-    static const KernelSet ks = {TT_V, TeamOf<TT_V>::T, configure<TT_V>, launch_step<TT_V>, launch_substep<TT_V>, launch_observe<TT_V>, launch_spawn<TT_V>};
+    static const KernelSet ks = {TT_V, TeamOf<TT_V>::T, configure<TT_V>, launch_step<TT_V>, launch_substep<TT_V>, launch_observe<TT_V>, launch_spawn<TT_V>, launch_reset<TT_V>};
     return &ks;
 }

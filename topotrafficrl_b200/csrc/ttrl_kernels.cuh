@@ -21,6 +21,8 @@ struct KernelSet {
                     const int32_t* inv_perm);
     void (*spawn)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const ttrl_spawn_draw* draws,
                   SpawnParams sp, int32_t* accepted);
+    void (*reset)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const uint8_t* mask, uint64_t seed,
+                  int64_t first_global_env);
 };
 
 }  // namespace ttrl

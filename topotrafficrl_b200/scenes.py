@@ -316,3 +316,36 @@ def make_highway_state(num_envs: int, config: dict, seed: int = 0, first_env: in
         st.env_i[abi.EI_NVEH, e] = n
         st.env_i[abi.EI_EGO, e] = 0
     return st
+
+
+# --------------------------------------------------------------------------------------------------
+# device-side reset parameters (include/ttrl_b200.h: ttrl_reset_params)
+# --------------------------------------------------------------------------------------------------
+def highway_reset_params(config: dict) -> abi.ResetParams:
+    rp = abi.ResetParams()
+    rp.scene = 0
+    rp.n_vehicles = int(config["vehicles_count"])
+    rp.lanes = int(config["lanes_count"])
+    rp.speed_limit = float(config["speed_limit"])
+    rp.density = float(config["vehicles_density"])
+    rp.ego_spacing = float(config["ego_spacing"])
+    rp.ego_speed = 25.0
+    return rp
+
+
+def intersection_reset_params(config: dict) -> abi.ResetParams:
+    """``IntersectionEnv._make_vehicles`` constants (intersection_env.py:251-318)."""
+    rp = abi.ResetParams()
+    rp.scene = 1
+    n = int(config["initial_vehicle_count"])
+    if not 1 <= n <= abi.MAX_SPAWN_ATTEMPTS:
+        raise ValueError("initial_vehicle_count out of range")
+    rp.n_vehicles = n
+    for t, v in enumerate(np.linspace(0, 80, n)):
+        rp.spawn_longitudinal[t] = float(v)
+    rp.ego_entry = 0
+    dest = config.get("destination")
+    rp.destination = -1 if dest is None else int(str(dest)[1:])
+    rp.warmup_substeps = 3 * int(config["simulation_frequency"])
+    rp.ego_longitudinal, rp.ego_longitudinal_std = 60.0, 5.0
+    return rp

@@ -66,8 +66,18 @@ class Sim:
         assert pool.vcap == self.vcap
         check(self._L.ttrl_sim_set_reset_pool(self._h, pool.num_envs, _p(pool.veh_d), _p(pool.veh_i), _p(pool.env_i), _p(pool.env_d)))
 
-    def set_autoreset(self, on: bool) -> None:
-        check(self._L.ttrl_sim_set_autoreset(self._h, int(on)))
+    def set_autoreset(self, mode) -> None:
+        """``False``/0: off; ``True``/1: restart finished envs from the reset pool; 2 or ``"device"``: device-side reset."""
+        if mode == "device":
+            mode = abi.AUTORESET_DEVICE
+        check(self._L.ttrl_sim_set_autoreset(self._h, int(mode)))
+
+    def set_reset_params(self, params: abi.ResetParams) -> None:
+        check(self._L.ttrl_sim_set_reset_params(self._h, C.byref(params)))
+
+    def reset_device(self, mask_ptr: Optional[int] = None, stream: int = 0) -> None:
+        """Fresh episodes generated on the device for every env (or the envs of a uint8 device mask)."""
+        check(self._L.ttrl_sim_reset(self._h, mask_ptr, stream))
 
     def seed(self, seed: int, first_global_env: int = 0) -> None:
         check(self._L.ttrl_sim_seed(self._h, int(seed), int(first_global_env)))

@@ -44,10 +44,15 @@ class TTRLVectorEnv:
     :param device: CUDA device index or ``"cuda:N"``
     :param seed: base seed; env e uses the stream keyed by ``first_env + e`` so shards reproduce a larger run
     :param first_env: global index of this shard's first env (multi-GPU sharding)
+    :param reset_mode: ``"device"`` (default): episodes are generated on the GPU (``ttrl_sim_reset``; Philox draws keyed
+                  by (seed, global env, episode)) at ``reset()`` and, with ``autoreset``, inside the step kernel when an
+                  env finishes.  ``"host"``: the first reset is driven from the host with numpy ``Generator(PCG64)``
+                  streams seeded like gymnasium (the reference's own reset for the intersection scene) and finished
+                  envs restart from that pool of initial states.
     """
 
     def __init__(self, num_envs: int, scene: str = "highway", config: Optional[dict] = None, device=0, seed: int = 0,
-                 first_env: int = 0, vcap: Optional[int] = None, autoreset: bool = True) -> None:
+                 first_env: int = 0, vcap: Optional[int] = None, autoreset: bool = True, reset_mode: str = "device") -> None:
         import torch
 
         if not torch.cuda.is_available():
@@ -77,9 +82,14 @@ class TTRLVectorEnv:
             routes = scenes.intersection_spawn_routes(self.net, self.table)
         else:
             raise ValueError(f"unknown scene {scene!r}")
+        if reset_mode not in ("device", "host"):
+            raise ValueError(f"unknown reset_mode {reset_mode!r}")
+        self.reset_mode = reset_mode
         self.sim = Sim(self.cfg, self.table, self.num_envs, self.vcap, self.device_index, routes)
-        self.sim.set_autoreset(autoreset)
+        self.sim.set_reset_params(scenes.highway_reset_params(self.config) if scene == "highway"
+                                  else scenes.intersection_reset_params(self.config))
         self.autoreset = autoreset
+        self.sim.set_autoreset(0 if not autoreset else (abi.AUTORESET_DEVICE if reset_mode == "device" else abi.AUTORESET_POOL))
         self.obs_shape = ((self.cfg.n_features, self.cfg.grid_w, self.cfg.grid_h) if self.cfg.obs_type == abi.OBS_GRID
                           else (self.cfg.obs_vehicles, self.cfg.n_features))
         n_actions = 5 if self.cfg.action_mode == abi.ACT_ALL else 3
@@ -99,13 +109,18 @@ class TTRLVectorEnv:
     def reset(self, seed: Optional[int] = None):
         if seed is not None:
             self.seed_value = int(seed)
+        self.sim.seed((self.seed_value << 1) | 1, self.first_env)  # device-side Philox draws (spawns, resets)
+        if self.reset_mode == "device":
+            self.sim.reset_device(None, self._stream())
+            self._maybe_shuffle()
+            self.sim.observe_ptr(self._obs.data_ptr(), self._stream())
+            return self._obs, {}
         if self.scene == "highway":
             st = scenes.make_highway_state(self.num_envs, self.config, seed=self.seed_value, first_env=self.first_env, vcap=self.vcap)
             self.sim.set_state(st)
         else:
             rngs = [gym_np_random(self.seed_value + self.first_env + e)[0] for e in range(self.num_envs)]
             st = reset_intersection(_SimResetBackend(self.sim), rngs, self.net, self.table, self.config, self.cfg)
-            self.sim.seed((self.seed_value << 1) | 1, self.first_env)  # device-side Philox spawn draws
         self.sim.set_reset_pool(st)
         self._maybe_shuffle()
         self.sim.observe_ptr(self._obs.data_ptr(), self._stream())
