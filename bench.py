@@ -228,18 +228,11 @@ def run_ours(args, w):
     E = args.envs or w["E"]
     K, W = args.steps, args.warmup
     first_env = rank * E
-    if w["scene"] == "highway":
-        st0 = scenes.make_highway_state(E, cfgd, seed=0, first_env=first_env, vcap=w["n"])
-        sim = Sim(cfg, table, E, w["n"], local_rank)
-        sim.set_state(st0)
-        sim.set_reset_pool(st0)
-        sim.set_autoreset(True)
-    else:
-        from topotrafficrl_b200.vector_env import TTRLVectorEnv
-        venv = TTRLVectorEnv(E, scene="intersection", device=local_rank, seed=0, first_env=first_env, vcap=args.vcap or w["n"],
-                             reset_mode=args.reset_mode)
-        venv.reset()
-        sim = venv.sim
+    from topotrafficrl_b200.vector_env import TTRLVectorEnv
+    venv = TTRLVectorEnv(E, scene=w["scene"], config=w["over"], device=local_rank, seed=0, first_env=first_env,
+                         vcap=(args.vcap or w["n"]), reset_mode=args.reset_mode)
+    venv.reset()
+    sim = venv.sim
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -337,7 +330,7 @@ def run_ours(args, w):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["label"], "envs_per_gpu": E, "vehicles_per_env": w["n"], "sub_steps_per_step": 15,
-                       "autoreset": ("pool of initial states" if w["scene"] == "highway" or args.reset_mode == "host" else "device-side fresh reset"), "l2": "flushed between timed steps (256 MB fill)",
+                       "autoreset": ("pool of host-generated initial states" if args.reset_mode == "host" else "device-side fresh reset"), "l2": "flushed between timed steps (256 MB fill)",
                        "target": "1e8 vehicle-steps/s per B200 (BASELINE.json north_star)"},
             "e2e": {"value": float(e2e_v.item()) / float(e2e_t.item()), "unit": "vehicle-steps/s",
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
@@ -372,7 +365,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reset-mode", default="device", choices=["device", "host"],
-                    help="intersection workloads: device = fresh episodes generated on the GPU at every autoreset (the reference's _make_vehicles incl. its 45 warm-up sub-steps); host = replay a pool of host-generated initial states")
+                    help="device = fresh episodes generated on the GPU at every autoreset (the reference's _make_vehicles incl. its 45 warm-up sub-steps); host = replay a pool of host-generated initial states")
     ap.add_argument("--qnet-mode", default="fp32", choices=["fp32", "tensor"], help="Q-net arithmetic for the *_qnet* workloads")
     args = ap.parse_args()
     if args.warmup < 3:

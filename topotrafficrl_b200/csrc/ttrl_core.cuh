@@ -1526,22 +1526,23 @@ TT_HD void reset_highway(C& c, Exec& ex, uint64_t seed, int64_t genv, int episod
             st->tspeed[s] = cfg.target_speeds[st->sidx[s]];
         }
     });
-    if (ex.first()) {  // positions: cumulative advances, in slot order
+    if (ex.first()) {  // longitudinal positions: cumulative advances in slot order (the only serial part)
         double x = 0;
-        for (int s = 0; s < n; ++s) {
-            x += st->acc2[s];
-            double px, py;
-            lane_position(c.lanes[st->lane[s]], x, 0.0, px, py);
-            st->pos[s] = d2{px, py};
-            st->h[s] = lane_heading_at(c.lanes[st->lane[s]], x);
-            st->cs[s] = d2{cos(st->h[s]), sin(st->h[s])};
-            st->timer[s] = s == 0 ? 0.0 : py_mod1((px + py) * kPi);
-            st->acc2[s] = 0;
-        }
+        for (int s = 0; s < n; ++s) { x += st->acc2[s]; st->acc2[s] = x; }
         st->n = n;
         st->ego = 0;
     }
     ex.sync();
+    ex.parn(n, [&](int s) {
+        const double x = st->acc2[s];
+        double px, py;
+        lane_position(c.lanes[st->lane[s]], x, 0.0, px, py);
+        st->pos[s] = d2{px, py};
+        st->h[s] = lane_heading_at(c.lanes[st->lane[s]], x);
+        st->cs[s] = d2{cos(st->h[s]), sin(st->h[s])};
+        st->timer[s] = s == 0 ? 0.0 : py_mod1((px + py) * kPi);
+        st->acc2[s] = 0;
+    });
     rebuild_tables(c, ex);
 }
 
