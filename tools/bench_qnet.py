@@ -28,14 +28,13 @@ for E in [int(x) for x in sys.argv[1:]] or [8192, 131072]:
         out[kind + "_fp32_ms"] = timeit(lambda: net.act(obs))
         flops = {"mlp": 2 * (105 * 128 + 128 * 128 + 128 * 3), "ego_attention_2h": 419e3}[kind] * E
         out[kind + "_fp32_tflops"] = flops / out[kind + "_fp32_ms"] / 1e9
-        if kind == "mlp":
-            net.set_mode("tensor")
-            at, qt = net.act(obs, return_q=True)
-            out["mlp_tensor_ms"] = timeit(lambda: net.act(obs))
-            out["mlp_tensor_tflops_useful"] = flops / out["mlp_tensor_ms"] / 1e9
-            out["mlp_tensor_max_abs_dq"] = float((qt - q32).abs().max())
-            out["mlp_tensor_action_agreement"] = float((at == a32).float().mean())
-            gap = torch.sort(q32, dim=1).values
-            out["mlp_min_top2_gap_where_disagree"] = float((gap[:, -1] - gap[:, -2])[at != a32].max()) if (at != a32).any() else None
+        net.set_mode("tensor")
+        at, qt = net.act(obs, return_q=True)
+        out[kind + "_tensor_ms"] = timeit(lambda: net.act(obs))
+        out[kind + "_tensor_tflops_useful"] = flops / out[kind + "_tensor_ms"] / 1e9
+        out[kind + "_tensor_max_abs_dq"] = float((qt - q32).abs().max())
+        out[kind + "_tensor_action_agreement"] = float((at == a32).float().mean())
+        gap = torch.sort(q32, dim=1).values
+        out[kind + "_max_top2_gap_where_disagree"] = float((gap[:, -1] - gap[:, -2])[at != a32].max()) if (at != a32).any() else None
         net.close()
     print(json.dumps(out))

@@ -467,6 +467,302 @@ __global__ void __launch_bounds__(128, 1) k_qnet_mlp_tc(TcMlp d, const float* __
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)d.tmem_cols) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core path for the EgoAttentionNetwork (models.py:237-312; the reference's default DQN model,
+// ego_attention_2h.json): the embedding MLPs and the key / value / query projections -- 89 % of its FLOPs -- run
+// on tcgen05; attention, the combine layer and the 64-wide output MLP stay on the CUDA cores.
+//
+//  * tile = 8 observations = 128 rows: row r = 16 * env + entity (15 entities + 1 zero pad row), UMMA M = 128;
+//  * ego and others embeddings share each MMA: B = [W_others ; W_ego] stacked along N (N = 128), the epilogue of
+//    row r takes columns 0..63 (others) or 64..127 (ego row, entity 0);
+//  * K | V | Q come from ONE MMA with N = 192 ([W_k ; W_v ; W_q]); they are never written to shared memory:
+//    thread r keeps its K and V rows in registers (tcgen05.ld), scores are softmaxed across the 16 threads of an
+//    observation with shuffles, the p-weighted V rows are summed through a shared scratch;
+//  * BF16x3 split operands, FP32 accumulation, like the MLP path.
+// ------------------------------------------------------------------------------------------------
+struct TcEgo {
+    int NE, Fe, Fs, H, A, pidx;
+    int ego_w1, ego_b1, ego_w2, ego_b2, oth_w1, oth_b1, oth_w2, oth_b2, wk, wv, wq, wc, o_w1, o_b1, o_w2, o_b2, p_w, p_b;  // blob offsets
+    int off_b1hi, off_b1lo, off_b2hi, off_b2lo, off_b3hi, off_b3lo, off_ahi, off_alo, off_f32, off_x, off_small, off_bar, total;
+};
+
+#define TT_TMEM_LD32(v, addr)                                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                    \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), \
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),  \
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),  \
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                          \
+                 : "r"(addr) : "memory");                                                                                    \
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+
+__device__ __forceinline__ void tc_sync_before_mma() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// out[env][n] = act(bias[n] + sum_k in[env][k] * Wt[k][n]) for the 8 observations of a tile; thread = (env, 4 columns)
+__device__ __forceinline__ void tile_dense8(const float* in, const float* Wt, const float* bias, int K, int N, bool relu, float* out, int tid) {
+    const int env = tid >> 4, j = tid & 15;
+    if (N >= 64) {
+        float a0 = bias ? bias[4 * j] : 0.f, a1 = bias ? bias[4 * j + 1] : 0.f, a2 = bias ? bias[4 * j + 2] : 0.f, a3 = bias ? bias[4 * j + 3] : 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float x = in[env * 64 + k];
+            const float4 w = *reinterpret_cast<const float4*>(Wt + k * N + 4 * j);
+            a0 = fmaf(x, w.x, a0); a1 = fmaf(x, w.y, a1); a2 = fmaf(x, w.z, a2); a3 = fmaf(x, w.w, a3);
+        }
+        if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+        *reinterpret_cast<float4*>(out + env * 64 + 4 * j) = make_float4(a0, a1, a2, a3);
+    } else if (j < N) {
+        float a = bias ? bias[j] : 0.f;
+        for (int k = 0; k < K; ++k) a = fmaf(in[env * 64 + k], Wt[k * N + j], a);
+        out[env * 64 + j] = relu ? fmaxf(a, 0.f) : a;
+    }
+}
+
+__global__ void __launch_bounds__(128, 1) k_qnet_ego_tc(TcEgo d, const float* __restrict__ weights, const float* __restrict__ obs, int E,
+                                                         double eps, uint64_t seed, uint64_t step, const double* __restrict__ u_inj,
+                                                         int32_t* __restrict__ actions, float* __restrict__ qout) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int env = tid >> 4, ent = tid & 15;     // row tid of the tile = entity `ent` of observation `env`
+    const int Fs = d.Fs, nin = d.NE * d.Fe;
+    float* f32 = reinterpret_cast<float*>(sm + d.off_f32);
+    float* s_wc = f32; float* s_ow1 = s_wc + Fs * Fs; float* s_ow2 = s_ow1 + Fs * Fs; float* s_pw = s_ow2 + Fs * Fs;
+    float* s_b1o = s_pw + Fs * 4; float* s_b1e = s_b1o + Fs; float* s_b2o = s_b1e + Fs; float* s_b2e = s_b2o + Fs;
+    float* s_ob1 = s_b2e + Fs; float* s_ob2 = s_ob1 + Fs; float* s_pb = s_ob2 + Fs;
+    float* s_x = reinterpret_cast<float*>(sm + d.off_x);          // [8][nin]
+    float* s_q = reinterpret_cast<float*>(sm + d.off_small);      // [8][64] query of the ego
+    float* s_ego = s_q + 8 * 64; float* s_val = s_ego + 8 * 64; float* s_t0 = s_val + 8 * 64; float* s_t1 = s_t0 + 8 * 64;
+    float* scratch = reinterpret_cast<float*>(sm + d.off_ahi);    // [128][64] fp32, aliases the A operand (hi + lo)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + d.off_bar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + d.off_bar + 8);
+
+    // ---- one-time setup: stacked B operands (split BF16, canonical layout) and the fp32 tail weights ----
+    for (int i = tid; i < 128 * 16; i += 128) {            // B1[n][k], K = 16: n < 64 others layer 1, n >= 64 ego layer 1
+        const int n = i >> 4, k = i & 15;
+        float w = 0.f;
+        if (k < d.Fe) w = __ldg(weights + (n < 64 ? d.oth_w1 : d.ego_w1) + k * Fs + (n & 63));
+        unsigned short hi, lo; split_bf16(w, hi, lo);
+        const uint32_t o = canon_off(n, k, 16);
+        *reinterpret_cast<unsigned short*>(sm + d.off_b1hi + o) = hi; *reinterpret_cast<unsigned short*>(sm + d.off_b1lo + o) = lo;
+    }
+    for (int i = tid; i < 128 * 64; i += 128) {            // B2[n][k], K = 64
+        const int n = i >> 6, k = i & 63;
+        unsigned short hi, lo; split_bf16(__ldg(weights + (n < 64 ? d.oth_w2 : d.ego_w2) + k * Fs + (n & 63)), hi, lo);
+        const uint32_t o = canon_off(n, k, 64);
+        *reinterpret_cast<unsigned short*>(sm + d.off_b2hi + o) = hi; *reinterpret_cast<unsigned short*>(sm + d.off_b2lo + o) = lo;
+    }
+    for (int i = tid; i < 192 * 64; i += 128) {            // B3[n][k] = [W_k ; W_v ; W_q]
+        const int n = i >> 6, k = i & 63;
+        const int base = n < 64 ? d.wk : n < 128 ? d.wv : d.wq;
+        unsigned short hi, lo; split_bf16(__ldg(weights + base + k * Fs + (n & 63)), hi, lo);
+        const uint32_t o = canon_off(n, k, 64);
+        *reinterpret_cast<unsigned short*>(sm + d.off_b3hi + o) = hi; *reinterpret_cast<unsigned short*>(sm + d.off_b3lo + o) = lo;
+    }
+    for (int i = tid; i < Fs * Fs; i += 128) { s_wc[i] = __ldg(weights + d.wc + i); s_ow1[i] = __ldg(weights + d.o_w1 + i); s_ow2[i] = __ldg(weights + d.o_w2 + i); }
+    for (int i = tid; i < Fs * d.A; i += 128) s_pw[i] = __ldg(weights + d.p_w + i);
+    for (int i = tid; i < Fs; i += 128) {
+        s_b1o[i] = __ldg(weights + d.oth_b1 + i); s_b1e[i] = __ldg(weights + d.ego_b1 + i);
+        s_b2o[i] = __ldg(weights + d.oth_b2 + i); s_b2e[i] = __ldg(weights + d.ego_b2 + i);
+        s_ob1[i] = __ldg(weights + d.o_b1 + i); s_ob2[i] = __ldg(weights + d.o_b2 + i);
+    }
+    for (int i = tid; i < d.A; i += 128) s_pb[i] = __ldg(weights + d.p_b + i);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_sync_before_mma();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc192 = (1u << 4) | (1u << 7) | (1u << 10) | ((192u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_hi = smem_u32(sm + d.off_ahi), a_lo = smem_u32(sm + d.off_alo);
+    uint32_t parity = 0;
+    const int dk = Fs / d.H;
+    const float inv = 1.0f / sqrtf((float)dk);
+
+    const int tiles = (E + 7) / 8;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int e0 = tile * 8, nenv = min(8, E - e0);
+        // ---- observations of the tile (contiguous in HBM) ----
+        for (int i = tid; i < 8 * nin; i += 128) s_x[i] = i < nenv * nin ? __ldg(obs + (size_t)e0 * nin + i) : 0.f;
+        __syncthreads();
+        // ---- A1[r][k] (K = 16): features of entity `ent` of observation `env`, zero padded ----
+        {
+            uint32_t ph[8], pl[8];
+#pragma unroll
+            for (int q2 = 0; q2 < 8; ++q2) {
+                unsigned short h0, l0, h1, l1;
+                const int k0 = 2 * q2, k1 = 2 * q2 + 1;
+                split_bf16((ent < d.NE && k0 < d.Fe) ? s_x[env * nin + ent * d.Fe + k0] : 0.f, h0, l0);
+                split_bf16((ent < d.NE && k1 < d.Fe) ? s_x[env * nin + ent * d.Fe + k1] : 0.f, h1, l1);
+                ph[q2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                pl[q2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            const uint32_t o0 = canon_off(tid, 0, 16), o1 = canon_off(tid, 8, 16);
+            *reinterpret_cast<uint4*>(sm + d.off_ahi + o0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4*>(sm + d.off_ahi + o1) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+            *reinterpret_cast<uint4*>(sm + d.off_alo + o0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            *reinterpret_cast<uint4*>(sm + d.off_alo + o1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+        }
+        // ---- two embedding layers: MMA (N = 128: others | ego) + epilogue selecting the row's half ----
+        for (int layer = 0; layer < 2; ++layer) {
+            tc_sync_before_mma();
+            if (tid == 0) {
+                if (layer == 0) issue_layer(tmem, a_hi, a_lo, smem_u32(sm + d.off_b1hi), smem_u32(sm + d.off_b1lo), 16, idesc128);
+                else issue_layer(tmem, a_hi, a_lo, smem_u32(sm + d.off_b2hi), smem_u32(sm + d.off_b2lo), 64, idesc128);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+            }
+            mbar_wait(smem_u32(bar), parity);
+            parity ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float* bo = layer == 0 ? s_b1o : s_b2o;
+            const float* be = layer == 0 ? s_b1e : s_b2e;
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t vo[32], ve[32];
+                TT_TMEM_LD32(vo, tmem_row + (uint32_t)c0);
+                TT_TMEM_LD32(ve, tmem_row + (uint32_t)(64 + c0));
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t ph[4], pl[4];
+                    float hv[8];
+#pragma unroll
+                    for (int q2 = 0; q2 < 8; ++q2) {
+                        const int c = c0 + g * 8 + q2;
+                        const float acc = ent == 0 ? __uint_as_float(ve[g * 8 + q2]) + be[c] : __uint_as_float(vo[g * 8 + q2]) + bo[c];
+                        hv[q2] = fmaxf(acc, 0.f);
+                    }
+#pragma unroll
+                    for (int q2 = 0; q2 < 4; ++q2) {
+                        unsigned short h0, l0, h1, l1;
+                        split_bf16(hv[2 * q2], h0, l0);
+                        split_bf16(hv[2 * q2 + 1], h1, l1);
+                        ph[q2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                        pl[q2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                    }
+                    const uint32_t o = canon_off(tid, c0 + g * 8, 64);
+                    *reinterpret_cast<uint4*>(sm + d.off_ahi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                    *reinterpret_cast<uint4*>(sm + d.off_alo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    if (layer == 1 && ent == 0) {   // the ego's embedding: residual of the attention block
+#pragma unroll
+                        for (int q2 = 0; q2 < 8; ++q2) s_ego[env * 64 + c0 + g * 8 + q2] = hv[q2];
+                    }
+                }
+            }
+        }
+        // ---- K | V | Q = input_all x [W_k ; W_v ; W_q]^T ----
+        tc_sync_before_mma();
+        if (tid == 0) {
+            issue_layer(tmem, a_hi, a_lo, smem_u32(sm + d.off_b3hi), smem_u32(sm + d.off_b3lo), 64, idesc192);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+        }
+        mbar_wait(smem_u32(bar), parity);
+        parity ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {   // the ego rows publish their query
+            uint32_t v0[32], v1[32];
+            TT_TMEM_LD32(v0, tmem_row + 128u);
+            TT_TMEM_LD32(v1, tmem_row + 160u);
+            if (ent == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { s_q[env * 64 + j] = __uint_as_float(v0[j]); s_q[env * 64 + 32 + j] = __uint_as_float(v1[j]); }
+            }
+        }
+        __syncthreads();
+        // ---- attention (models.py:370-388): scores / sqrt(d_k), masked_fill(-1e9), softmax over the entities ----
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;  // per head probability of this row (H <= 4, d_k = 64 >> hshift... a power of two)
+        const int hshift = d.H == 1 ? 6 : d.H == 2 ? 5 : 4;
+        {
+            uint32_t k0[32], k1[32];
+            TT_TMEM_LD32(k0, tmem_row + 0u);
+            TT_TMEM_LD32(k1, tmem_row + 32u);
+            const bool masked = ent < d.NE ? s_x[env * nin + ent * d.Fe + d.pidx] < 0.5f : true;
+            float sc[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* qrow = s_q + env * 64;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {   // static register indices; the head of column c is c >> hshift
+                const float kv = __uint_as_float(c < 32 ? k0[c & 31] : k1[c & 31]);
+                const int h = c >> hshift;
+                const float qc = qrow[c];
+                sc[0] = h == 0 ? fmaf(qc, kv, sc[0]) : sc[0];
+                sc[1] = h == 1 ? fmaf(qc, kv, sc[1]) : sc[1];
+                sc[2] = h == 2 ? fmaf(qc, kv, sc[2]) : sc[2];
+                sc[3] = h == 3 ? fmaf(qc, kv, sc[3]) : sc[3];
+            }
+            float pr[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                float v = sc[h] * inv;
+                if (masked) v = -1e9f;
+                if (ent >= d.NE) v = -INFINITY;  // pad row: not an entity
+                float m = v;
+#pragma unroll
+                for (int off = 1; off < 16; off <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                const float ev = ent < d.NE ? expf(v - m) : 0.f;
+                float sum = ev;
+#pragma unroll
+                for (int off = 1; off < 16; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                pr[h] = ev / sum;
+            }
+            p0 = pr[0]; p1 = pr[1]; p2 = pr[2]; p3 = pr[3];
+        }
+        {   // p-weighted value rows -> scratch (the A operand is free: its MMA has completed)
+            uint32_t v0[32], v1[32];
+            TT_TMEM_LD32(v0, tmem_row + 64u);
+            TT_TMEM_LD32(v1, tmem_row + 96u);
+            float* row = scratch + tid * 64;
+#pragma unroll
+            for (int c = 0; c < 64; c += 4) {
+                float o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int h = (c + u) >> hshift;
+                    const float pw = h == 0 ? p0 : h == 1 ? p1 : h == 2 ? p2 : p3;
+                    o[u] = pw * __uint_as_float(c + u < 32 ? v0[(c + u) & 31] : v1[(c + u) & 31]);
+                }
+                *reinterpret_cast<float4*>(row + c) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        __syncthreads();
+        {   // value[env][c] = sum over the entities; thread = (env, 4 columns)
+            const int j = ent;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int n = 0; n < d.NE; ++n) {
+                const float4 t = *reinterpret_cast<const float4*>(scratch + (env * 16 + n) * 64 + 4 * j);
+                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+            }
+            *reinterpret_cast<float4*>(s_val + env * 64 + 4 * j) = a;
+        }
+        __syncthreads();
+        // ---- (attention_combine(value) + ego) / 2 (models.py:193), output MLP (models.py:69-76), action ----
+        tile_dense8(s_val, s_wc, nullptr, Fs, Fs, false, s_t0, tid);
+        __syncthreads();
+        for (int c = ent * 4; c < ent * 4 + 4; ++c) s_t0[env * 64 + c] = (s_t0[env * 64 + c] + s_ego[env * 64 + c]) / 2.f;
+        __syncthreads();
+        tile_dense8(s_t0, s_ow1, s_ob1, Fs, Fs, true, s_t1, tid);
+        __syncthreads();
+        tile_dense8(s_t1, s_ow2, s_ob2, Fs, Fs, true, s_t0, tid);
+        __syncthreads();
+        tile_dense8(s_t0, s_pw, s_pb, Fs, d.A, false, s_t1, tid);
+        __syncthreads();
+        if (ent == 0 && env < nenv) {
+            const int e = e0 + env;
+            const float* qv = s_t1 + env * 64;
+            if (qout) for (int a = 0; a < d.A; ++a) qout[(size_t)e * d.A + a] = qv[a];
+            actions[e] = select_action(qv, d.A, eps, u_inj ? u_inj[e] : uniform_for(seed, step, e));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256u) : "memory");
+}
+
 }  // namespace
 
 struct ttrl_qnet {
@@ -479,6 +775,7 @@ struct ttrl_qnet {
     int mode = 0;       // TTRL_QNET_MODE_FP32 (parity) | TTRL_QNET_MODE_TENSOR (tcgen05 BF16x3, MLP only)
     bool tc_ok = false;
     TcMlp tc{};
+    TcEgo tce{};
 };
 
 #define QCK(call)                                                                                  \
@@ -580,6 +877,38 @@ int ttrl_qnet_create(const ttrl_qnet_desc* desc, const float* weights_host, int6
             q->tc_ok = true;
         (void)cudaGetLastError();
     }
+    // tensor-core path for the EgoAttentionNetwork: the shipped shape family (two 64-wide embedding layers,
+    // feature_size 64, <= 4 heads, two 64-wide output layers, <= 15 entities x <= 16 features)
+    if (desc->type == TTRL_QNET_EGO_ATTENTION && desc->embed_layers == 2 && desc->embed[0] == 64 && desc->embed[1] == 64 &&
+        desc->feature_size == 64 && desc->heads >= 1 && desc->heads <= 4 && 64 % desc->heads == 0 && desc->out_layers == 2 &&
+        desc->out_hidden[0] == 64 && desc->out_hidden[1] == 64 && desc->n_entities <= 15 && desc->n_features <= 16 && desc->n_actions <= 4) {
+        TcEgo& t = q->tce;
+        t.NE = desc->n_entities; t.Fe = desc->n_features; t.Fs = 64; t.H = desc->heads; t.A = desc->n_actions; t.pidx = desc->presence_feature_idx;
+        t.ego_w1 = n.ego[0].w_off; t.ego_b1 = n.ego[0].b_off; t.ego_w2 = n.ego[1].w_off; t.ego_b2 = n.ego[1].b_off;
+        t.oth_w1 = n.oth[0].w_off; t.oth_b1 = n.oth[0].b_off; t.oth_w2 = n.oth[1].w_off; t.oth_b2 = n.oth[1].b_off;
+        t.wk = n.wk.w_off; t.wv = n.wv.w_off; t.wq = n.wq.w_off; t.wc = n.wc.w_off;
+        t.o_w1 = n.out[0].w_off; t.o_b1 = n.out[0].b_off; t.o_w2 = n.out[1].w_off; t.o_b2 = n.out[1].b_off;
+        t.p_w = n.out[2].w_off; t.p_b = n.out[2].b_off;
+        auto up = [](int x) { return (x + 1023) / 1024 * 1024; };
+        int o = 0;
+        t.off_b1hi = o; o += up(128 * 16 * 2);
+        t.off_b1lo = o; o += up(128 * 16 * 2);
+        t.off_b2hi = o; o += up(128 * 64 * 2);
+        t.off_b2lo = o; o += up(128 * 64 * 2);
+        t.off_b3hi = o; o += up(192 * 64 * 2);
+        t.off_b3lo = o; o += up(192 * 64 * 2);
+        t.off_ahi = o; o += 128 * 64 * 2;   // hi and lo contiguous: together they are the [128][64] fp32 scratch
+        t.off_alo = o; o += 128 * 64 * 2;
+        t.off_f32 = o; o += up((int)sizeof(float) * (3 * 64 * 64 + 64 * 4 + 6 * 64 + 16));
+        t.off_x = o; o += up((int)sizeof(float) * 8 * nin);
+        t.off_small = o; o += up((int)sizeof(float) * 5 * 8 * 64);
+        t.off_bar = o; o += 16;
+        t.total = o;
+        if (t.total <= 227 * 1024 &&
+            cudaFuncSetAttribute(k_qnet_ego_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, t.total) == cudaSuccess)
+            q->tc_ok = true;
+        (void)cudaGetLastError();
+    }
     *out = q;
     return 0;
 }
@@ -588,7 +917,8 @@ int ttrl_qnet_set_mode(ttrl_qnet* q, int mode) {
     if (!q) return qfail("null argument");
     if (mode == TTRL_QNET_MODE_FP32) { q->mode = mode; return 0; }
     if (mode != TTRL_QNET_MODE_TENSOR) return qfail("unknown Q-network mode");
-    if (!q->tc_ok) return qfail("the tensor-core path supports MultiLayerPerceptron with two hidden layers of width 16..256 (multiples of 16) that fit in shared memory");
+    if (!q->tc_ok) return qfail("the tensor-core path supports MultiLayerPerceptron with two hidden layers of width 16..256 (multiples of 16) and "
+                                "EgoAttentionNetwork with 64-wide embedding / attention / output layers (the shipped ego_attention*.json shapes)");
     q->mode = mode;
     return 0;
 }
@@ -604,6 +934,15 @@ int ttrl_qnet_destroy(ttrl_qnet* q) {
 static int qnet_launch(ttrl_qnet* q, const float* obs_dev, int E, double eps, uint64_t seed, uint64_t step, const double* u_dev,
                        int32_t* actions_dev, float* q_dev, void* stream) {
     QCK(cudaSetDevice(q->device));
+    if (q->mode == TTRL_QNET_MODE_TENSOR && q->net.d.type == TTRL_QNET_EGO_ATTENTION) {
+        int grid = (E + 7) / 8;
+        if (grid > q->n_sms) grid = q->n_sms;
+        if (grid < 1) grid = 1;
+        k_qnet_ego_tc<<<grid, 128, q->tce.total, (cudaStream_t)stream>>>(q->tce, q->d_weights, obs_dev, E, eps, seed, step, u_dev, actions_dev, q_dev);
+        q->launches++;
+        QCK(cudaGetLastError());
+        return 0;
+    }
     if (q->mode == TTRL_QNET_MODE_TENSOR) {
         int grid = (E + 127) / 128;
         if (grid > q->n_sms) grid = q->n_sms;
