@@ -366,7 +366,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reset-mode", default="device", choices=["device", "host"],
                     help="device = fresh episodes generated on the GPU at every autoreset (the reference's _make_vehicles incl. its 45 warm-up sub-steps); host = replay a pool of host-generated initial states")
-    ap.add_argument("--qnet-mode", default="fp32", choices=["fp32", "tensor"], help="Q-net arithmetic for the *_qnet* workloads")
+    ap.add_argument("--qnet-mode", default="tensor", choices=["fp32", "tensor"],
+                    help="Q-net arithmetic for the *_qnet* workloads: tcgen05 tensor cores (BF16x3, default) or fp32 CUDA cores")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
