@@ -12,8 +12,9 @@ episode statistics are all-reduced (NCCL) after the timed region.
 Numbers on the JSON line
   value      vehicle-steps/s, device-resident: actions already in HBM, obs/reward/flags written to HBM,
              CUDA events around each step (L2 flushed between steps), max over ranks.
-  e2e        the same metric through the host-buffer C-ABI call (ttrl_sim_step_host): actions from host memory,
-             obs/reward/flags back to host memory every step, wall clock around the call.
+  e2e        the same metric through the host-buffer C-ABI call (ttrl_sim_step_pinned / Sim.step_host): actions copied
+             from host memory to the GPU, obs/reward/flags copied back to (page-locked) host memory every step and
+             returned as numpy arrays, synchronous, wall clock around the call.
   roofline   k_step against the measured HBM copy bandwidth (MEASURED_PEAKS.json), algorithmic bytes per
              env-step from SURVEY.md section 8d / DESIGN.md section 6.
   cpu_baseline  the CPU oracle (C restatement of the reference algorithm, oracle/) on the host cores of this
@@ -343,7 +344,7 @@ def run_ours(args, w):
     # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------------
     acts_host = actions.cpu().numpy()
     for k in range(min(W, 3)):
-        sim.step_host(acts_host[k])
+        sim.step_host(acts_host[k], copy=False)
     sim.stats(reset=True)
     barrier()
     t0 = time.perf_counter()
@@ -352,7 +353,7 @@ def run_ours(args, w):
         a_host = acts_host[W + k]
         if qnet is not None:  # the reference's agent.act boundary: numpy observation in, numpy actions out
             a_host = qnet.act(torch.from_numpy(o).to(dev, non_blocking=True).view(E, -1)).cpu().numpy()
-        o, r, t, u = sim.step_host(a_host)
+        o, r, t, u = sim.step_host(a_host, copy=False)  # zero-copy views of the pinned staging buffers
     barrier()
     e2e_s = time.perf_counter() - t0
     s2 = sim.stats(reset=True)

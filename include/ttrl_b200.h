@@ -221,6 +221,13 @@ int ttrl_sim_step(ttrl_sim* sim, const int32_t* actions_dev, float* obs_dev, flo
 int ttrl_sim_step_host(ttrl_sim* sim, const int32_t* actions_host, float* obs_host, float* reward_host,
                        uint8_t* terminated_host, uint8_t* truncated_host);
 
+/* Zero-copy form of the host-buffer step: the library's own page-locked staging buffers (int32 actions[E], float
+ * obs[E*obs_size], float reward[E], uint8 terminated[E], uint8 truncated[E]; valid for the sim's lifetime) are
+ * handed to the caller, who writes the actions there, calls ttrl_sim_step_pinned and reads the results in place
+ * (they are overwritten by the next call). */
+int ttrl_sim_host_buffers(ttrl_sim* sim, int32_t** actions, float** obs, float** reward, uint8_t** terminated, uint8_t** truncated);
+int ttrl_sim_step_pinned(ttrl_sim* sim, int use_actions);
+
 /* Observation only (observation_type.observe() at reset: abstract.py:210). */
 int ttrl_sim_observe(ttrl_sim* sim, float* obs_dev, void* stream);
 

@@ -60,6 +60,8 @@ def lib():
     L.ttrl_sim_substep.argtypes = [vp, vp, vp]
     L.ttrl_sim_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.ttrl_sim_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.ttrl_sim_host_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
+    L.ttrl_sim_step_pinned.argtypes = [vp, i32]
     L.ttrl_sim_observe.argtypes = [vp, vp, vp]
     L.ttrl_sim_spawn.argtypes = [vp, vp, dbl, dbl, dbl, dbl, i32, vp]
     L.ttrl_sim_read_stats.argtypes = [vp, C.POINTER(abi.EpisodeStats), i32]

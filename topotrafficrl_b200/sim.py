@@ -112,15 +112,30 @@ class Sim:
     def observe_ptr(self, obs_ptr, stream: int = 0) -> None:
         check(self._L.ttrl_sim_observe(self._h, obs_ptr, stream))
 
-    def step_host(self, actions: Optional[np.ndarray]):
-        """One env.step() for all envs from HOST buffers (H2D, kernel, D2H inside the call)."""
-        E = self.num_envs
-        a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32)
-        obs = np.empty((E, self.obs_size), np.float32)
-        reward = np.empty(E, np.float32)
-        term = np.empty(E, np.uint8)
-        trunc = np.empty(E, np.uint8)
-        check(self._L.ttrl_sim_step_host(self._h, _p(a), _p(obs), _p(reward), _p(term), _p(trunc)))
+    def _pinned_views(self):
+        if getattr(self, "_pinned", None) is None:
+            ptrs = [C.c_void_p() for _ in range(5)]
+            check(self._L.ttrl_sim_host_buffers(self._h, *[C.byref(p) for p in ptrs]))
+            E = self.num_envs
+
+            def view(p, ctype, n, dtype):
+                return np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(n,)).view(dtype)
+
+            self._pinned = (view(ptrs[0], C.c_int32, E, np.int32), view(ptrs[1], C.c_float, E * self.obs_size, np.float32).reshape(E, self.obs_size),
+                            view(ptrs[2], C.c_float, E, np.float32), view(ptrs[3], C.c_uint8, E, np.uint8), view(ptrs[4], C.c_uint8, E, np.uint8))
+        return self._pinned
+
+    def step_host(self, actions: Optional[np.ndarray], copy: bool = True):
+        """One env.step() for all envs from HOST buffers (H2D, kernel, D2H inside the call).
+
+        ``copy=True`` returns fresh arrays (like the reference's ``step``).  ``copy=False`` returns views of the
+        library's page-locked staging buffers: no host copy at all, but the arrays are overwritten by the next call."""
+        a_pin, obs, reward, term, trunc = self._pinned_views()
+        if actions is not None:
+            a_pin[:] = actions
+        check(self._L.ttrl_sim_step_pinned(self._h, int(actions is not None)))
+        if copy:
+            return obs.copy(), reward.copy(), term.copy(), trunc.copy()
         return obs, reward, term, trunc
 
     def stats(self, reset: bool = False) -> abi.EpisodeStats:

@@ -147,9 +147,10 @@ class TTRLVectorEnv:
                           self._trunc.data_ptr(), self._stream())
         return self._obs, self._reward, self._term.bool(), self._trunc.bool(), {}
 
-    def step_host(self, actions: np.ndarray):
-        obs, reward, term, trunc = self.sim.step_host(actions)
-        return obs.reshape((self.num_envs,) + self.obs_shape), reward, term.astype(bool), trunc.astype(bool), {}
+    def step_host(self, actions: np.ndarray, copy: bool = True):
+        """numpy in / numpy out.  ``copy=False``: zero-copy views of the page-locked staging buffers (valid until the next call)."""
+        obs, reward, term, trunc = self.sim.step_host(actions, copy=copy)
+        return obs.reshape((self.num_envs,) + self.obs_shape), reward, term.view(np.bool_), trunc.view(np.bool_), {}
 
     def get_state(self) -> SimState:
         return self.sim.get_state()
