@@ -18,6 +18,7 @@ struct HostExec {
     int T;  // = V: every slot is a "thread"
     bool first() const { return true; }  // single-thread sections run once
     void sync() {}
+    void align() {}
     template <class F> void par(F f) { for (int t = 0; t < T; ++t) f(t); }
     template <class F> void parn(int n, F f) { for (int t = 0; t < n; ++t) f(t); }
     template <class F> bool any(int n, F f) { bool r = false; for (int t = 0; t < n; ++t) r = f(t) || r; return r; }
@@ -51,7 +52,7 @@ template <int V>
 struct HostEnv {
     EnvState<V> st;
     std::vector<d2> SR;
-    std::vector<uint32_t> lmask;
+    std::vector<uint32_t> lmask, pbits;
     std::vector<double> pred;
     std::vector<float> obs_s;
     std::vector<int32_t> cell;
@@ -61,11 +62,12 @@ struct HostEnv {
         const ttrl_config& cfg = sc->cfg;
         SR.assign((size_t)V * cfg.n_lanes, d2{0.0, 0.0});
         lmask.assign((size_t)((V + 31) / 32) * cfg.n_lanes, 0u);
-        pred.assign((size_t)3 * V * kPred, 0.0);
+        pred.assign((size_t)4 * V, 0.0);
+        pbits.assign((size_t)(V * (V - 1) / 2 + 31) / 32 + 1, 0u);
         obs_s.assign((size_t)(cfg.obs_vehicles * cfg.n_features + 4), 0.f);
         cell.assign((size_t)(cfg.grid_w * cfg.grid_h + 4), 0);
         c.st = &st; c.sc = sc; c.lanes = sc->lanes; c.SR = SR.data(); c.lmask = lmask.data();
-        c.pred = cfg.regulated ? pred.data() : nullptr; c.obs_s = obs_s.data(); c.cell = cell.data();
+        c.pred = cfg.regulated ? pred.data() : nullptr; c.pbits = cfg.regulated ? pbits.data() : nullptr; c.obs_s = obs_s.data(); c.cell = cell.data();
         c.L = cfg.n_lanes; c.vcap = vcap;
         c.gap_den = 2 * sqrt(-cfg.comfort_acc_max * cfg.comfort_acc_min);
         c.tan_max_steer = tan(kPi / 3);

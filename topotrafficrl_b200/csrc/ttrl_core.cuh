@@ -43,6 +43,13 @@ constexpr int kPred = 11;            // regulation.py:87: np.arange(0.25, 3, 0.2
 constexpr double kVehLength = 5.0;   // kinematics.py:21
 constexpr double kVehWidth = 2.0;    // kinematics.py:23
 constexpr int kStatFields = 8;       // ttrl_episode_stats
+// CTA-wide phase alignment points of an aligned env_substep (bit k = point k: 0 sub-step start, 1 before C1,
+// 2 before C2, 3 before integrate, 4 before collide); tuned per capacity in ttrl_kern.cu
+#ifndef TT_ALIGN_MASK
+#define TT_ALIGN_MASK 0x01
+#endif
+constexpr int kAlignMask = TT_ALIGN_MASK;
+constexpr int kAlignPerSubstep = ((kAlignMask >> 0) & 1) + ((kAlignMask >> 1) & 1) + ((kAlignMask >> 2) & 1) + ((kAlignMask >> 3) & 1) + ((kAlignMask >> 4) & 1);
 
 struct alignas(16) d2 { double x, y; };  // 16-byte pair (one LDS.128 on the device)
 
@@ -104,7 +111,8 @@ struct EnvCtx {
     const ttrl_lane* lanes;  // lane table (shared-memory copy)
     d2* SR;                  // [V][L] (longitudinal, lateral) local coordinates of vehicle v in lane l
     uint32_t* lmask;         // [L][W] bit v of lane l: vehicle v is on lane l with margin 1 (road.py:503)
-    double* pred;            // [3][V][kPred] regulation predictions (x, y, heading); null if not regulated
+    double* pred;            // [4][V] regulation predictions of one time slice (x, y, cos h, sin h); null if not regulated
+    uint32_t* pbits;         // [V (V - 1) / 2 bits] pairs in conflict (regulation); null if not regulated
     float* obs_s;            // staging for one Kinematics observation
     int32_t* cell;           // OccupancyGrid per-cell winner (W*H ints)
     int L;
@@ -871,9 +879,12 @@ TT_HD void position_heading_along_route(C& c, uint32_t rroad, uint32_t rlanew, i
     lane_position(c.lanes[li], lon, 0.0, px, py);
     ph = lane_heading_at(c.lanes[li], lon);
 }
-// phase R1: un-yield (regulation.py:38-45) + ControlledVehicle.predict_trajectory_constant_speed (controller.py:236-253)
+// Regulation runs as TIME SLICES: for each of the 11 prediction times, every vehicle's predicted pose is computed
+// once (5 doubles: x, y, heading's cos / sin ... per vehicle, instead of 33 for all times at once -- the shared-memory
+// footprint of an env decides how many envs an SM holds) and every pair not yet in conflict is tested at that time.
+// phase R0: un-yield (regulation.py:38-45)
 template <class C>
-TT_HDN void regulate_predict(C& c, int i) {
+TT_HD void regulate_unyield(C& c, int i) {
     auto* st = c.st;
     st->mark[i] = 0;
     if (st->flags[i] & TTRL_FL_YIELDING) {
@@ -882,6 +893,11 @@ TT_HDN void regulate_predict(C& c, int i) {
             st->flags[i] &= ~TTRL_FL_YIELDING;
         } else st->ytimer[i] += 1;
     }
+}
+// phase R1(k): ControlledVehicle.predict_trajectory_constant_speed (controller.py:236-253) at time 0.25 (k + 1)
+template <class C>
+TT_HDN void regulate_predict(C& c, int i, int k) {
+    auto* st = c.st;
     const int ln = st->lane[i];
     const double s0 = S_(c, i, ln);
     uint32_t rr = st->rroad[i], rl = st->rlanew[i];
@@ -891,13 +907,14 @@ TT_HDN void regulate_predict(C& c, int i) {
         rr = (uint32_t)c.lanes[ln].road;
         rl = (uint32_t)c.lanes[ln].lane_id;
     }
-    double* px = c.pred + (0 * C::V + i) * kPred;
-    double* py = c.pred + (1 * C::V + i) * kPred;
-    double* ph = c.pred + (2 * C::V + i) * kPred;
-    for (int k = 0; k < kPred; ++k) {
-        const double t = 0.25 + k * 0.25;
-        position_heading_along_route(c, rr, rl, rlen, s0 + st->v[i] * t, ln, px[k], py[k], ph[k]);
-    }
+    const double t = 0.25 + k * 0.25;
+    double px, py, ph, sn, cn;
+    position_heading_along_route(c, rr, rl, rlen, s0 + st->v[i] * t, ln, px, py, ph);
+    sincos(ph, &sn, &cn);
+    c.pred[0 * C::V + i] = px;
+    c.pred[1 * C::V + i] = py;
+    c.pred[2 * C::V + i] = cn;
+    c.pred[3 * C::V + i] = sn;
 }
 // utils.point_in_rotated_rectangle utils.py:75-91 with precomputed cos/sin of the rectangle angle
 TT_HD bool point_in_rotated_rectangle(double px, double py, double cx, double cy, double length, double width, double cs, double sn) {
@@ -917,30 +934,31 @@ TT_HD bool has_corner_inside(double x1, double y1, double c1, double s1, double 
     }
     return false;
 }
-// RegulatedRoad.is_conflict_possible regulation.py:80-103
+// one time slice of RegulatedRoad.is_conflict_possible (regulation.py:80-103) for the pair (i, j)
 template <class C>
-TT_HDN bool is_conflict_possible(C& c, int i, int j) {
-    const double* xi = c.pred + (0 * C::V + i) * kPred; const double* yi = c.pred + (1 * C::V + i) * kPred; const double* hi = c.pred + (2 * C::V + i) * kPred;
-    const double* xj = c.pred + (0 * C::V + j) * kPred; const double* yj = c.pred + (1 * C::V + j) * kPred; const double* hj = c.pred + (2 * C::V + j) * kPred;
+TT_HDN bool conflict_at_slice(C& c, int i, int j) {
+    const double xi = c.pred[0 * C::V + i], yi = c.pred[1 * C::V + i], c1 = c.pred[2 * C::V + i], s1 = c.pred[3 * C::V + i];
+    const double xj = c.pred[0 * C::V + j], yj = c.pred[1 * C::V + j], c2 = c.pred[2 * C::V + j], s2 = c.pred[3 * C::V + j];
     const double len = 1.5 * kVehLength, wid = 0.9 * kVehWidth;
-    for (int k = 0; k < kPred; ++k) {
-        const double dx = xj[k] - xi[k], dy = yj[k] - yi[k];
-        if (sqrt(dx * dx + dy * dy) > kVehLength) continue;
-        double s1, c1, s2, c2;
-        sincos(hi[k], &s1, &c1);
-        sincos(hj[k], &s2, &c2);
-        if (has_corner_inside(xi[k], yi[k], c1, s1, xj[k], yj[k], c2, s2, len, wid) ||
-            has_corner_inside(xj[k], yj[k], c2, s2, xi[k], yi[k], c1, s1, len, wid))
-            return true;
-    }
-    return false;
+    const double dx = xj - xi, dy = yj - yi;
+    if (sqrt(dx * dx + dy * dy) > kVehLength) return false;
+    return has_corner_inside(xi, yi, c1, s1, xj, yj, c2, s2, len, wid) || has_corner_inside(xj, yj, c2, s2, xi, yi, c1, s1, len, wid);
 }
-// phase R2: one (i<j) pair; marks the yielding vehicle (respect_priorities regulation.py:64-78).  The writes of
-// the reference (:59-62) are idempotent flags, so pair order is irrelevant; they are merged in phase R3.
+// pair index q -> (i < j), row-major over the strict upper triangle of an n x n matrix
+TT_HD void pair_of(int q, int n, int& i, int& j) {
+    int r = (int)((2.0f * n - 1.0f - sqrtf((2.0f * n - 1.0f) * (2.0f * n - 1.0f) - 8.0f * q)) * 0.5f);
+    if (r < 0) r = 0;
+    if (r > n - 2) r = n - 2;
+    while (r > 0 && r * (2 * n - r - 1) / 2 > q) --r;
+    while ((r + 1) * (2 * n - r - 2) / 2 <= q) ++r;
+    i = r;
+    j = r + 1 + (q - r * (2 * n - r - 1) / 2);
+}
+// phase R3: the yielding vehicle of a conflicting pair (respect_priorities regulation.py:64-78).  The writes of the
+// reference (:59-62) are idempotent flags, so pair order is irrelevant; they are merged in regulate_apply.
 template <class C>
-TT_HD void regulate_pair(C& c, int i, int j) {
+TT_HD void regulate_yield(C& c, int i, int j) {
     auto* st = c.st;
-    if (!is_conflict_possible(c, i, j)) return;
     const int p1 = c.lanes[st->lane[i]].priority, p2 = c.lanes[st->lane[j]].priority;
     int y;
     if (p1 > p2) y = j;
@@ -968,13 +986,15 @@ TT_HD void regulate_apply(C& c, int i) {
 // one simulation sub-step (AbstractEnv._simulate body abstract.py:257-273)
 // ------------------------------------------------------------------------------------------------
 template <class C, class Exec>
-TT_HD void env_substep(C& c, Exec& ex, int raw_action) {  // inlined on purpose: a call boundary here costs ~30 % (ctx spills)
+TT_HD void env_substep(C& c, Exec& ex, int raw_action, bool aligned = false) {  // inlined on purpose: a call boundary here costs ~30 % (ctx spills)
+    // `aligned`: the CTA-wide phase alignment points are active (k_step's main loop only; kAlignPerSubstep of them)
     auto* st = c.st;
     const SceneDev* sc = c.sc;
     using ES = EnvState<C::V>;
     const int n = st->n;
     // ego meta-action on the first sub-step of an env-step: DiscreteMetaAction.act action.py:259-260
     const int first_action = (raw_action >= 0 && st->steps % sc->F == 0) ? decode_action(sc->cfg, raw_action) : A_NONE;
+    if (aligned && (kAlignMask & 1)) ex.align();
     ex.parn(n, [&](int t) {
         if (t == 0) { st->n_chg = 0; st->n_pair = 0; st->n_w = 0; st->overflow = 0; }
         act_phase_a(c, ex, t, first_action);
@@ -999,26 +1019,41 @@ TT_HD void env_substep(C& c, Exec& ex, int raw_action) {  // inlined on purpose:
             }
         }
     }
+    if (aligned && (kAlignMask & 2)) ex.align();
     ex.parn(n, [&](int t) {
         if (t == 0) { st->n_mob = 0; for (int w = 0; w < C::W; ++w) st->bmask[w] = 0; }
         act_phase_c1(c, ex, t);
     });
+    if (aligned && (kAlignMask & 4)) ex.align();
     ex.parn(n + st->n_chg, [&](int k) { act_phase_c2(c, k); });
     if (sc->cfg.regulated) {  // RegulatedRoad.step regulation.py:28-32
         const int rs = st->road_steps + 1;
         if (rs % sc->reg_period == 0) {
-            ex.parn(n, [&](int t) { regulate_predict(c, t); });
-            ex.parn(n * (n - 1) / 2, [&](int q) {
-                // q -> (i<j): row-major over the strict upper triangle
-                int i = 0, rem = q;
-                while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
-                regulate_pair(c, i, i + 1 + rem);
+            const int np = n * (n - 1) / 2;
+            ex.parn(n, [&](int t) { regulate_unyield(c, t); });
+            ex.parn((np + 31) / 32, [&](int w) { c.pbits[w] = 0; });
+            for (int k = 0; k < kPred; ++k) {
+                ex.parn(n, [&](int t) { regulate_predict(c, t, k); });
+                ex.parn(np, [&](int q) {
+                    if ((c.pbits[q >> 5] >> (q & 31)) & 1) return;  // already in conflict at an earlier time
+                    int i, j;
+                    pair_of(q, n, i, j);
+                    if (conflict_at_slice(c, i, j)) ex.atomic_or(&c.pbits[q >> 5], 1u << (q & 31));
+                });
+            }
+            ex.parn(np, [&](int q) {
+                if (!((c.pbits[q >> 5] >> (q & 31)) & 1)) return;
+                int i, j;
+                pair_of(q, n, i, j);
+                regulate_yield(c, i, j);
             });
             ex.parn(n, [&](int t) { regulate_apply(c, t); });
         }
     }
+    if (aligned && (kAlignMask & 8)) ex.align();
     ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; });
     ex.parn(n, [&](int t) { integrate(c, ex, t); });
+    if (aligned && (kAlignMask & 16)) ex.align();
     collide_all(c, ex);
     if (ex.first()) { st->steps += 1; if (sc->cfg.regulated) st->road_steps += 1; }
     ex.sync();
@@ -1657,6 +1692,9 @@ struct StepIO {
     int obs_size;
 };
 
+// number of Exec::align() calls one env_step makes (teams without an env replay them)
+TT_HD int env_step_align_count(const SceneDev* sc) { return sc->F * kAlignPerSubstep; }
+
 template <class C, class Exec>
 TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int e) {
     auto* st = c.st;
@@ -1668,7 +1706,7 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
     ex.sync();
     double veh_steps = 0;
     for (int f = 0; f < sc->F; ++f) {
-        env_substep(c, ex, action);
+        env_substep(c, ex, action, true);
         veh_steps += st->n;
     }
     float* obs = io.obs ? io.obs + (size_t)e * io.obs_size : nullptr;

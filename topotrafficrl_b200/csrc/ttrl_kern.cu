@@ -12,15 +12,27 @@
 using namespace ttrl;
 
 // ------------------------------------------------------------------------------------------------
-// device execution policy: one CTA of T threads ("team") per env; slots / tasks are strided over the team.
-// T == 32: the team is one warp, barriers are __syncwarp().
+// device execution policy: a "team" of T threads per env; slots / tasks are strided over the team.
+//  * T > 32: one team per CTA, barriers are __syncthreads().
+//  * T == 32 (up to 32 vehicle slots): the team is one warp (barriers are __syncwarp()) and a CTA holds G teams.
+//    `align()` is a CTA-wide barrier at the phase boundaries of a sub-step: it keeps the warps of the CTA in the
+//    same code region, so an instruction-cache line fetched by one warp serves all of them.  The step kernel is
+//    bound by instruction-cache miss traffic (the GPC-level cache serves instruction requests at ~90 % of its peak
+//    rate and kernel time tracks the request count, profiles/r1f_icache.txt); for the intersection scene (few
+//    vehicles per env, long scalar phases) aligned multi-env CTAs are 23 % faster, for 2-warp and larger teams the
+//    barrier skew costs more than the fetch sharing saves (profiles/r1c_variants.txt).
 // ------------------------------------------------------------------------------------------------
 template <int V, int T>
 struct DevExec {
-    int tid;
+    int tid;    // thread within the team
+    int G;      // teams in this CTA (1 unless T == 32)
     __device__ __forceinline__ bool first() const { return tid == 0; }
     __device__ __forceinline__ void sync() {
         if (T == 32) __syncwarp(); else __syncthreads();
+    }
+    // CTA-wide phase alignment; every team of the CTA calls it the same number of times
+    __device__ __forceinline__ void align() {
+        if (T == 32 && G > 1) __syncthreads();
     }
     template <class F> __device__ __forceinline__ void par(F f) {
 #pragma unroll 1
@@ -98,26 +110,35 @@ struct DevExec {
 #ifndef TT_MINB
 #define TT_MINB (TT_V <= 32 ? 1 : TT_V <= 64 ? 10 : TT_V <= 128 ? 5 : 3)
 #endif
-template <int V> struct TeamOf { static constexpr int T = TT_T, MINB = TT_MINB; };
+// envs per CTA of k_step (1 = one env per CTA, no phase alignment)
+#ifndef TT_G
+#define TT_G (TT_V <= 32 ? 16 : 1)   /* upper bound; the launch uses as many as fit in shared memory */
+#endif
+template <int V> struct TeamOf {
+    static constexpr int T = TT_T, MINB = TT_MINB, G = TT_G;
+    static_assert(G == 1 || T == 32, "several envs per CTA need one-warp teams");
+};
 
 template <int V>
-__device__ __forceinline__ void make_ctx(EnvCtx<V>& c, unsigned char* smem, const SceneDev* sc, const SmemLayout& lay, int vcap) {
+__device__ __forceinline__ void make_ctx(EnvCtx<V>& c, unsigned char* smem_cta, int team, const SceneDev* sc, const SmemLayout& lay, int vcap) {
+    // the lane table (n_lanes * 160 B) is shared by the teams of the CTA: copied once with 16-byte vector loads
+    ttrl_lane* lanes_s = reinterpret_cast<ttrl_lane*>(smem_cta);
+    {
+        const int4* src = reinterpret_cast<const int4*>(sc->lanes);
+        int4* dst = reinterpret_cast<int4*>(lanes_s);
+        const int n16 = sc->cfg.n_lanes * (int)(sizeof(ttrl_lane) / 16);
+        for (int k = threadIdx.x; k < n16; k += blockDim.x) dst[k] = __ldg(src + k);
+    }
+    unsigned char* smem = smem_cta + lay.lanes_bytes + (size_t)team * lay.per_env;
     c.st = reinterpret_cast<EnvState<V>*>(smem);
     c.sc = sc;
     c.L = sc->cfg.n_lanes;
     c.vcap = vcap;
-    ttrl_lane* lanes_s = reinterpret_cast<ttrl_lane*>(smem + lay.off_lanes);
-    // copy the lane table into shared memory (n_lanes * 160 B) with 16-byte vector loads
-    {
-        const int4* src = reinterpret_cast<const int4*>(sc->lanes);
-        int4* dst = reinterpret_cast<int4*>(lanes_s);
-        const int n16 = c.L * (int)(sizeof(ttrl_lane) / 16);
-        for (int k = threadIdx.x; k < n16; k += blockDim.x) dst[k] = __ldg(src + k);
-    }
     c.lanes = lanes_s;
     c.SR = reinterpret_cast<d2*>(smem + lay.off_SR);
     c.lmask = reinterpret_cast<uint32_t*>(smem + lay.off_lmask);
     c.pred = lay.off_pred >= 0 ? reinterpret_cast<double*>(smem + lay.off_pred) : nullptr;
+    c.pbits = lay.off_pred >= 0 ? reinterpret_cast<uint32_t*>(smem + lay.off_pred + sizeof(double) * 4 * V) : nullptr;
     c.obs_s = reinterpret_cast<float*>(smem + lay.off_obs);
     c.cell = reinterpret_cast<int32_t*>(smem + lay.off_cell);
     c.gap_den = 2 * sqrt(-sc->cfg.comfort_acc_max * sc->cfg.comfort_acc_min);  // behavior.py:214-216
@@ -125,17 +146,32 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V>& c, unsigned char* smem, cons
     __syncthreads();
 }
 
+// single-team CTA (k_substep, k_observe, k_spawn, k_reset)
 #define TT_KERNEL_PROLOGUE                                     \
     extern __shared__ __align__(16) unsigned char smem[];      \
     constexpr int T = TeamOf<V>::T;                            \
     EnvCtx<V> c;                                               \
-    make_ctx<V>(c, smem, sc, lay, g.V);                        \
-    DevExec<V, T> ex{(int)threadIdx.x};
+    make_ctx<V>(c, smem, 0, sc, lay, g.V);                     \
+    DevExec<V, T> ex{(int)threadIdx.x, 1};
 
 template <int V>
-__global__ void __launch_bounds__(TeamOf<V>::T, TeamOf<V>::MINB) k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay) {
-    TT_KERNEL_PROLOGUE
-    env_step(c, ex, g, io, (int)blockIdx.x);
+__global__ void __launch_bounds__(TeamOf<V>::T * TeamOf<V>::G, TeamOf<V>::G > 1 ? 1 : TeamOf<V>::MINB)
+k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int T = TeamOf<V>::T;
+    const int G = (int)blockDim.x / T;
+    const int team = threadIdx.x / T;
+    EnvCtx<V> c;
+    make_ctx<V>(c, smem, team, sc, lay, g.V);
+    DevExec<V, T> ex{(int)threadIdx.x % T, G};
+    const int e = (int)blockIdx.x * G + team;
+    if (e < g.E) {
+        env_step(c, ex, g, io, e);
+    } else {
+        // a team without an env (last CTA) still takes part in the phase alignment of its CTA
+        const int n_align = env_step_align_count(sc);
+        for (int k = 0; k < n_align; ++k) ex.align();
+    }
 }
 
 template <int V>
@@ -189,18 +225,23 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 template <int V>
 static int configure(const ttrl_config& cfg, int vcap, SmemLayout* out) {
     SmemLayout l{};
+    l.lanes_bytes = (int)align_up(sizeof(ttrl_lane) * cfg.n_lanes, 128);
     size_t off = align_up(sizeof(EnvState<V>), 16);
-    l.off_lanes = (int)off; off += align_up(sizeof(ttrl_lane) * cfg.n_lanes, 16);
     l.off_SR = (int)off; off += sizeof(d2) * vcap * cfg.n_lanes;
     l.off_lmask = (int)off; off += align_up(sizeof(uint32_t) * ((V + 31) / 32) * cfg.n_lanes, 16);
-    if (cfg.regulated) { l.off_pred = (int)off; off += sizeof(double) * 3 * V * kPred; } else l.off_pred = -1;
+    if (cfg.regulated) { l.off_pred = (int)off; off += sizeof(double) * 4 * V + align_up(sizeof(uint32_t) * ((V * (V - 1) / 2 + 31) / 32), 16); } else l.off_pred = -1;
     l.off_obs = (int)off; off += align_up(sizeof(float) * (cfg.obs_type == TTRL_OBS_KINEMATICS ? cfg.obs_vehicles * cfg.n_features : 4), 16);
     l.off_cell = (int)off; off += align_up(sizeof(int32_t) * (cfg.obs_type == TTRL_OBS_GRID ? cfg.grid_w * cfg.grid_h : 4), 16);
-    l.total = (int)off;
+    l.per_env = (int)align_up(off, 128);
+    l.total = l.lanes_bytes + l.per_env;                       // single-team kernels
+    int G = TeamOf<V>::G;                                      // k_step: G envs per CTA, as many as fit
+    while (G > 1 && l.lanes_bytes + G * l.per_env > 227 * 1024) --G;
+    l.G = G;
+    l.total_step = l.lanes_bytes + G * l.per_env;
     *out = l;
-    if (l.total > 227 * 1024) return (int)cudaErrorInvalidValue;
+    if (l.total_step > 227 * 1024) return (int)cudaErrorInvalidValue;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_step<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_step<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_substep<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_observe<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_spawn<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
@@ -211,7 +252,8 @@ static int configure(const ttrl_config& cfg, int vcap, SmemLayout* out) {
 }
 template <int V>
 static void launch_step(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io) {
-    k_step<V><<<E, TeamOf<V>::T, lay.total, st>>>(sc, g, io, lay);
+    const int G = lay.G;
+    k_step<V><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
 }
 template <int V>
 static void launch_substep(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const int32_t* actions) {
