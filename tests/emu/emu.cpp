@@ -46,6 +46,7 @@ struct HostExec {
     void atomic_max(int32_t* a, int32_t v) { if (v > *a) *a = v; }
     void atomic_or(uint32_t* a, uint32_t v) { *a |= v; }
     int atomic_add(int32_t* a, int32_t v) { const int o = *a; *a += v; return o; }
+    int atomic_add_global(int32_t* a, int32_t v) { return atomic_add(a, v); }
 };
 
 template <int V>

@@ -366,3 +366,39 @@ def test_device_reset_equals_emulated_logic_and_autoreset_fresh_episodes():
     T.compare_states(st, want, 1e-9, "device autoreset (highway)")
     np.testing.assert_allclose(obs, emu.observe(want), rtol=0, atol=2e-6)
     sim.close()
+
+
+def test_batched_device_autoreset_intersection():
+    """Intersection scene, device autoreset: finished envs are queued by k_step and reset by the packed k_reset_list
+    pass; the result must equal the reset logic run on the host for (seed, global env, episode + 1)."""
+    from tests.emu.emu import Emulator
+    from topotrafficrl_b200.state import SimState
+    torch = _torch()
+    net, table, cfg, routes = T.intersection_scene({"duration": 2})
+    cfgd = scenes.merged_config(scenes.INTERSECTION_CONFIG, {"duration": 2})
+    rp = scenes.intersection_reset_params(cfgd)
+    E = 100  # not a multiple of the envs per CTA
+    sim = _sim(cfg, table, E, 24, routes)
+    sim.set_reset_params(rp)
+    sim.seed(4242, 7)
+    sim.reset_device()
+    sim.set_autoreset("device")
+    act = np.ones(E, np.int32)
+    _dev_step(sim, act)
+    assert (sim.get_state().env_i[abi.EI_EPISODE] == 0).sum() > 0  # not everybody crashed in the first second
+    obs, rew, term, trunc = _dev_step(sim, act)  # time 2 >= duration: every env is done here
+    assert (term | trunc).all()
+    st = sim.get_state()
+    emu = Emulator(cfg, table, routes)
+    emu.set_reset_params(rp)
+    for episode in (1, 2):
+        sel = np.nonzero(st.env_i[abi.EI_EPISODE] == episode)[0]
+        if sel.size == 0:
+            continue
+        want = SimState.zeros(E, 24)
+        emu.reset(want, 4242, 7, episode)
+        for e in sel:
+            T.compare_states(st.slice_envs(e, e + 1), want.slice_envs(e, e + 1), 1e-9, f"env {e} episode {episode}")
+        np.testing.assert_allclose(obs[sel], emu.observe(want)[sel], rtol=0, atol=2e-6)
+    assert (st.env_i[abi.EI_STEPS] == 0).all() and (st.env_i[abi.EI_DONE] == 0).all()
+    sim.close()

@@ -1583,7 +1583,7 @@ TT_HD void reset_highway(C& c, Exec& ex, uint64_t seed, int64_t genv, int episod
 
 // IntersectionEnv._make_vehicles (intersection_env.py:251-318)
 template <class C, class Exec>
-TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) {
+TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode, bool aligned) {
     auto* st = c.st;
     const SceneDev* sc = c.sc;
     const ttrl_reset_params& rp = sc->rp;
@@ -1597,7 +1597,7 @@ TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int e
         spawn_vehicle(c, ex, d, sp);
     }
     rebuild_tables(c, ex);
-    for (int k = 0; k < rp.warmup_substeps; ++k) env_substep(c, ex, -1);  // (:267-274) road.act(); road.step(1/sf)
+    for (int k = 0; k < rp.warmup_substeps; ++k) env_substep(c, ex, -1, aligned);  // (:267-274) road.act(); road.step(1/sf)
     {   // challenger vehicle (:276-277)
         ttrl_spawn_draw d;
         device_spawn_draw(seed, genv, reset_attempt_counter(episode, rp.n_vehicles - 1), d);
@@ -1667,8 +1667,8 @@ TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int e
 }
 
 template <class C, class Exec>
-TT_HDN void env_reset(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) {  // cold path: keep it out of the step loop's code
-    if (c.sc->rp.scene == 1) reset_intersection(c, ex, seed, genv, episode);
+TT_HDN void env_reset(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode, bool aligned = false) {  // cold path: keep it out of the step loop's code
+    if (c.sc->rp.scene == 1) reset_intersection(c, ex, seed, genv, episode, aligned);
     else reset_highway(c, ex, seed, genv, episode);
 }
 
@@ -1686,6 +1686,8 @@ struct StepIO {
     const int32_t* inv_perm;       // [E][obs_vehicles-1] or null
     double* stats;                 // [kStatFields][E] per-env accumulators
     GlobalState pool;              // reset pool (pool.E == 0: none)
+    int32_t* done_list;            // device autoreset with warm-up: finished envs are queued here (done_count) and reset by
+    int32_t* done_count;           //   k_reset_list right after the step, packed and phase-aligned; null: reset inside the step
     int autoreset;
     uint64_t seed;
     int64_t first_global_env;
@@ -1694,6 +1696,7 @@ struct StepIO {
 
 // number of Exec::align() calls one env_step makes (teams without an env replay them)
 TT_HD int env_step_align_count(const SceneDev* sc) { return sc->F * kAlignPerSubstep; }
+TT_HD int env_reset_align_count(const SceneDev* sc) { return sc->rp.scene == 1 ? sc->rp.warmup_substeps * kAlignPerSubstep : 0; }
 
 template <class C, class Exec>
 TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int e) {
@@ -1753,7 +1756,10 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
         }
         ex.sync();
     }
-    if (st->done && io.autoreset == TTRL_AUTORESET_DEVICE && sc->have_rp) {  // uniform: st->done is in shared memory
+    if (st->done && io.autoreset == TTRL_AUTORESET_DEVICE && sc->have_rp && io.done_list) {
+        // resets with warm-up sub-steps are batched: a lone resetting team would keep its whole CTA (and SM) waiting
+        if (ex.first()) io.done_list[ex.atomic_add_global(io.done_count, 1)] = e;
+    } else if (st->done && io.autoreset == TTRL_AUTORESET_DEVICE && sc->have_rp) {  // uniform: st->done is in shared memory
         const int episode = st->episode + 1;
         ex.sync();
         env_reset(c, ex, io.seed, io.first_global_env + e, episode);

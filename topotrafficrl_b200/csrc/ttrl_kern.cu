@@ -95,6 +95,7 @@ struct DevExec {
     __device__ __forceinline__ void atomic_max(int32_t* a, int32_t v) { atomicMax(a, v); }
     __device__ __forceinline__ void atomic_or(uint32_t* a, uint32_t v) { atomicOr(a, v); }
     __device__ __forceinline__ int atomic_add(int32_t* a, int32_t v) { return atomicAdd(a, v); }
+    __device__ __forceinline__ int atomic_add_global(int32_t* a, int32_t v) { return atomicAdd(a, v); }
 };
 
 // threads per env for a slot capacity
@@ -217,6 +218,36 @@ __global__ void __launch_bounds__(TeamOf<V>::T) k_reset(const SceneDev* __restri
     store_env(c, ex, g, e);
 }
 
+// Device autoreset of scenes whose reset has warm-up sub-steps (intersection): the envs k_step found finished are
+// listed in `done_list`; they are reset here PACKED (G per CTA, like k_step) and phase-aligned, and their first
+// observation replaces the terminal one (gymnasium autoreset semantics).  A reset inside k_step would leave one warp
+// running 45 sub-steps while the other teams of its CTA -- and the SM -- wait.
+template <int V>
+__global__ void __launch_bounds__(TeamOf<V>::T * TeamOf<V>::G, TeamOf<V>::G > 1 ? 1 : TeamOf<V>::MINB)
+k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int T = TeamOf<V>::T;
+    const int G = (int)blockDim.x / T;
+    const int team = threadIdx.x / T;
+    const int n_done = *io.done_count;
+    if ((int)blockIdx.x * G >= n_done) return;  // uniform per CTA
+    EnvCtx<V> c;
+    make_ctx<V>(c, smem, team, sc, lay, g.V);
+    DevExec<V, T> ex{(int)threadIdx.x % T, G};
+    const int k = (int)blockIdx.x * G + team;
+    if (k < n_done) {
+        const int e = io.done_list[k];
+        const int episode = g.ei[TTRL_EI_EPISODE * g.E + e] + 1;
+        env_reset(c, ex, io.seed, io.first_global_env + e, episode, true);
+        if (io.obs) observe(c, ex, io.obs + (size_t)e * io.obs_size,
+                            io.inv_perm ? io.inv_perm + (size_t)e * (sc->cfg.obs_vehicles - 1) : nullptr);
+        store_env(c, ex, g, e);
+    } else {
+        const int n_align = env_reset_align_count(sc);
+        for (int a = 0; a < n_align; ++a) ex.align();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch table
 // ------------------------------------------------------------------------------------------------
@@ -246,6 +277,7 @@ static int configure(const ttrl_config& cfg, int vcap, SmemLayout* out) {
     if ((e = cudaFuncSetAttribute(k_observe<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_spawn<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_reset<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_reset_list<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
     // all of the SM's unified L1/shared storage as shared memory: resident CTAs are what hides latency here
     cudaFuncSetAttribute(k_step<V>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return 0;
@@ -253,7 +285,10 @@ static int configure(const ttrl_config& cfg, int vcap, SmemLayout* out) {
 template <int V>
 static void launch_step(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io) {
     const int G = lay.G;
+    if (io.done_list) cudaMemsetAsync(io.done_count, 0, sizeof(int32_t), st);
     k_step<V><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    // CTAs beyond the number of finished envs exit at once
+    if (io.done_list) k_reset_list<V><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
 }
 template <int V>
 static void launch_substep(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const int32_t* actions) {
