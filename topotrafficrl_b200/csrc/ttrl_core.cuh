@@ -102,9 +102,13 @@ struct alignas(16) EnvState {
     double time, ret;
 };
 
-template <int V_>
+// P_ = 1 ("plain" scenes: straight lanes only, no regulation, no spawn / clear, highway reward -- BASELINE configs 1
+// and 2) compiles the curved-lane geometry, the regulation and the intersection reward out of the step loop: the kernel
+// is bound by instruction-cache miss traffic, so code that is never executed should not sit between code that is.
+template <int V_, int P_ = 0>
 struct EnvCtx {
     static constexpr int V = V_;
+    static constexpr bool kPlain = P_ == 1;
     static constexpr int W = (V_ + 31) / 32;  // mask words per lane
     EnvState<V_>* st;
     const SceneDev* sc;
@@ -219,6 +223,13 @@ TT_HD double lane_distance(const ttrl_lane& l, double px, double py) {
     return lane_distance_sr(l, s, r);
 }
 
+// scene-profile aware forms for the hot call sites
+template <class C> TT_HD void lane_local_c(const ttrl_lane& l, double px, double py, double& s, double& r) {
+    if (C::kPlain) { const double dx = px - l.ax, dy = py - l.ay; s = dx * l.dx + dy * l.dy; r = dx * (-l.dy) + dy * l.dx; }
+    else lane_local(l, px, py, s, r);
+}
+template <class C> TT_HD double lane_heading_at_c(const ttrl_lane& l, double s) { return C::kPlain ? l.heading : lane_heading_at(l, s); }
+
 // ------------------------------------------------------------------------------------------------
 // table access
 // ------------------------------------------------------------------------------------------------
@@ -237,10 +248,10 @@ TT_HD int table_row_and_closest(C& c, int v, uint64_t& on_mask) {
     for (int l = 0; l < c.L; ++l) {
         const ttrl_lane& ln = c.lanes[l];
         double s, r;
-        lane_local(ln, px, py, s, r);
+        lane_local_c<C>(ln, px, py, s, r);
         c.SR[v * c.L + l] = d2{s, r};
         if (lane_on_lane(ln, s, r, 1.0)) m |= 1ull << l;
-        double ang = fabs(wrap_to_pi(hd - lane_heading_at(ln, s)));
+        double ang = fabs(wrap_to_pi(hd - lane_heading_at_c<C>(ln, s)));
         double d = lane_distance_sr(ln, s, r) + 1.0 * ang;
         if (l == 0 || d < bd) { bd = d; best = l; }
     }
@@ -353,7 +364,7 @@ TT_HDN double steering_control(C& c, int i, int target_lane, double& tan_steer) 
     const d2 sr = c.SR[i * c.L + target_lane];
     const double speed = c.st->v[i];
     double lane_next = sr.x + speed * TAU_PURSUIT;
-    double lane_future_heading = lane_heading_at(tl, lane_next);
+    double lane_future_heading = lane_heading_at_c<C>(tl, lane_next);
     double lateral_speed_command = -KP_LATERAL * sr.y;
     double heading_command = asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
     double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
@@ -1026,7 +1037,7 @@ TT_HD void env_substep(C& c, Exec& ex, int raw_action, bool aligned = false) {  
     });
     if (aligned && (kAlignMask & 4)) ex.align();
     ex.parn(n + st->n_chg, [&](int k) { act_phase_c2(c, k); });
-    if (sc->cfg.regulated) {  // RegulatedRoad.step regulation.py:28-32
+    if (!C::kPlain && sc->cfg.regulated) {  // RegulatedRoad.step regulation.py:28-32
         const int rs = st->road_steps + 1;
         if (rs % sc->reg_period == 0) {
             const int np = n * (n - 1) / 2;
@@ -1055,7 +1066,7 @@ TT_HD void env_substep(C& c, Exec& ex, int raw_action, bool aligned = false) {  
     ex.parn(n, [&](int t) { integrate(c, ex, t); });
     if (aligned && (kAlignMask & 16)) ex.align();
     collide_all(c, ex);
-    if (ex.first()) { st->steps += 1; if (sc->cfg.regulated) st->road_steps += 1; }
+    if (ex.first()) { st->steps += 1; if (!C::kPlain && sc->cfg.regulated) st->road_steps += 1; }
     ex.sync();
 }
 
@@ -1228,7 +1239,7 @@ TT_HD double agent_reward(C& c, int i) {  // intersection_env.py:78-104 / u_turn
     const double crashed = (st->flags[i] & TTRL_FL_CRASHED) ? 1.0 : 0.0;
     const double hs = clipd(lmap(st->v[i], cfg.reward_speed_lo, cfg.reward_speed_hi, 0.0, 1.0), 0.0, 1.0);
     const double onr = on_road(c, i) ? 1.0 : 0.0;
-    if (cfg.reward_type == TTRL_REWARD_INTERSECTION) {
+    if (!C::kPlain && cfg.reward_type == TTRL_REWARD_INTERSECTION) {
         const bool arrived = has_arrived(c, i);
         double reward = 0 + cfg.collision_reward * crashed + cfg.high_speed_reward * hs + cfg.arrived_reward * (arrived ? 1.0 : 0.0) + 0 * onr;
         reward = arrived ? cfg.arrived_reward : reward;
@@ -1249,7 +1260,7 @@ TT_HD bool is_terminated(C& c) {  // intersection_env.py:106-111 / u_turn_env.py
     const int e = c.st->ego;
     const bool crashed = (c.st->flags[e] & TTRL_FL_CRASHED) != 0;
     const bool off = c.sc->cfg.offroad_terminal && !on_road(c, e);
-    if (c.sc->cfg.reward_type == TTRL_REWARD_INTERSECTION) return crashed || has_arrived(c, e) || off;
+    if (!C::kPlain && c.sc->cfg.reward_type == TTRL_REWARD_INTERSECTION) return crashed || has_arrived(c, e) || off;
     return crashed || off;
 }
 
@@ -1736,12 +1747,12 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
                 s[1 * E] += st->ret;
                 s[2 * E] += st->time * cfg.policy_frequency;
                 s[3 * E] += (st->flags[ego] & TTRL_FL_CRASHED) ? 1 : 0;
-                s[4 * E] += (cfg.reward_type == TTRL_REWARD_INTERSECTION && has_arrived(c, ego)) ? 1 : 0;
+                s[4 * E] += (!C::kPlain && cfg.reward_type == TTRL_REWARD_INTERSECTION && has_arrived(c, ego)) ? 1 : 0;
             }
         }
     }
     ex.sync();
-    if (cfg.spawn_enabled) {
+    if (!C::kPlain && cfg.spawn_enabled) {
         clear_vehicles(c, ex);
         ttrl_spawn_draw d;
         bool have = false;

@@ -120,8 +120,8 @@ template <int V> struct TeamOf {
     static_assert(G == 1 || T == 32, "several envs per CTA need one-warp teams");
 };
 
-template <int V>
-__device__ __forceinline__ void make_ctx(EnvCtx<V>& c, unsigned char* smem_cta, int team, const SceneDev* sc, const SmemLayout& lay, int vcap) {
+template <int V, int P>
+__device__ __forceinline__ void make_ctx(EnvCtx<V, P>& c, unsigned char* smem_cta, int team, const SceneDev* sc, const SmemLayout& lay, int vcap) {
     // the lane table (n_lanes * 160 B) is shared by the teams of the CTA: copied once with 16-byte vector loads
     ttrl_lane* lanes_s = reinterpret_cast<ttrl_lane*>(smem_cta);
     {
@@ -152,18 +152,18 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V>& c, unsigned char* smem_cta, 
     extern __shared__ __align__(16) unsigned char smem[];      \
     constexpr int T = TeamOf<V>::T;                            \
     EnvCtx<V> c;                                               \
-    make_ctx<V>(c, smem, 0, sc, lay, g.V);                     \
+    make_ctx<V, 0>(c, smem, 0, sc, lay, g.V);                  \
     DevExec<V, T> ex{(int)threadIdx.x, 1};
 
-template <int V>
+template <int V, int P>
 __global__ void __launch_bounds__(TeamOf<V>::T * TeamOf<V>::G, TeamOf<V>::G > 1 ? 1 : TeamOf<V>::MINB)
 k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int T = TeamOf<V>::T;
     const int G = (int)blockDim.x / T;
     const int team = threadIdx.x / T;
-    EnvCtx<V> c;
-    make_ctx<V>(c, smem, team, sc, lay, g.V);
+    EnvCtx<V, P> c;
+    make_ctx<V, P>(c, smem, team, sc, lay, g.V);
     DevExec<V, T> ex{(int)threadIdx.x % T, G};
     const int e = (int)blockIdx.x * G + team;
     if (e < g.E) {
@@ -231,8 +231,8 @@ k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayo
     const int team = threadIdx.x / T;
     const int n_done = *io.done_count;
     if ((int)blockIdx.x * G >= n_done) return;  // uniform per CTA
-    EnvCtx<V> c;
-    make_ctx<V>(c, smem, team, sc, lay, g.V);
+    EnvCtx<V, 0> c;
+    make_ctx<V, 0>(c, smem, team, sc, lay, g.V);
     DevExec<V, T> ex{(int)threadIdx.x % T, G};
     const int k = (int)blockIdx.x * G + team;
     if (k < n_done) {
@@ -254,7 +254,7 @@ k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayo
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <int V>
-static int configure(const ttrl_config& cfg, int vcap, SmemLayout* out) {
+static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, SmemLayout* out) {
     SmemLayout l{};
     l.lanes_bytes = (int)align_up(sizeof(ttrl_lane) * cfg.n_lanes, 128);
     size_t off = align_up(sizeof(EnvState<V>), 16);
@@ -272,21 +272,28 @@ static int configure(const ttrl_config& cfg, int vcap, SmemLayout* out) {
     *out = l;
     if (l.total_step > 227 * 1024) return (int)cudaErrorInvalidValue;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_step<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_step<V, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_step<V, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_substep<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_observe<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_spawn<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_reset<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_reset_list<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
     // all of the SM's unified L1/shared storage as shared memory: resident CTAs are what hides latency here
-    cudaFuncSetAttribute(k_step<V>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_step<V, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_step<V, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    // "plain" scene profile (EnvCtx::kPlain): straight lanes only, no regulation, no spawn / clear, highway reward
+    bool plain = !cfg.regulated && !cfg.spawn_enabled && cfg.reward_type == TTRL_REWARD_HIGHWAY;
+    for (int k = 0; k < cfg.n_lanes; ++k) plain = plain && lanes[k].kind == TTRL_LANE_STRAIGHT;
+    out->plain = plain ? 1 : 0;
     return 0;
 }
 template <int V>
 static void launch_step(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io) {
     const int G = lay.G;
     if (io.done_list) cudaMemsetAsync(io.done_count, 0, sizeof(int32_t), st);
-    k_step<V><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    if (lay.plain) k_step<V, 1><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    else k_step<V, 0><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
     // CTAs beyond the number of finished envs exit at once
     if (io.done_list) k_reset_list<V><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
 }

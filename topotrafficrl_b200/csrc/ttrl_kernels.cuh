@@ -8,14 +8,14 @@ namespace ttrl {
 
 struct SmemLayout {
     // offsets inside one env's region; a CTA's dynamic shared memory = lane table (lanes_bytes) + G env regions (per_env)
-    int off_SR, off_lmask, off_pred, off_obs, off_cell, lanes_bytes, per_env, total, total_step, G;
+    int off_SR, off_lmask, off_pred, off_obs, off_cell, lanes_bytes, per_env, total, total_step, G, plain;
 };
 
 // One set of launchers per compiled slot capacity.
 struct KernelSet {
     int V;        // slot capacity the kernels were compiled for (arrays in shared memory are sized by it)
     int T;        // threads per env
-    int (*configure)(const ttrl_config& cfg, int vcap, SmemLayout* lay);  // layout + shared-memory opt-in; cudaError_t as int
+    int (*configure)(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, SmemLayout* lay);  // layout + shared-memory opt-in; cudaError_t as int
     void (*step)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io);
     void (*substep)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const int32_t* actions);
     void (*observe)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, float* obs, int obs_size,
