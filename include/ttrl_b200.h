@@ -63,7 +63,9 @@ typedef struct ttrl_road {
 #define TTRL_MAX_NODES 64
 #define TTRL_MAX_TARGET_SPEEDS 8
 #define TTRL_MAX_FEATURES 8
-#define TTRL_ROUTE_CAP 4
+#define TTRL_ROUTE_CAP 12      /* route entries per vehicle: 3 words x 4 bytes (roundabout-v0 plans up to 10 roads, road.py:159-188) */
+#define TTRL_ROUTE_WORDS 3
+#define TTRL_MAX_CONTROLLED 4  /* controlled vehicles (agents) per env: MultiAgentIntersectionEnv places ego k on arm k % 4 */
 
 /* Observation feature ids (vehicle/kinematics.py:237-261, the subset the hot configs use). */
 enum { TTRL_F_PRESENCE = 0, TTRL_F_X = 1, TTRL_F_Y = 2, TTRL_F_VX = 3, TTRL_F_VY = 4,
@@ -74,8 +76,9 @@ enum { TTRL_ORDER_SORTED = 0, TTRL_ORDER_SHUFFLED = 1 };
 enum { TTRL_ACT_ALL = 0 /* 0 LANE_LEFT 1 IDLE 2 LANE_RIGHT 3 FASTER 4 SLOWER */,
        TTRL_ACT_LONGI = 1 /* 0 SLOWER 1 IDLE 2 FASTER */,
        TTRL_ACT_LAT = 2 /* 0 LANE_LEFT 1 IDLE 2 LANE_RIGHT */ };
-enum { TTRL_REWARD_INTERSECTION = 0 /* intersection_env.py:78-104 */,
-       TTRL_REWARD_HIGHWAY = 1 /* u_turn_env.py:39-71 template on the synthetic highway */ };
+enum { TTRL_REWARD_INTERSECTION = 0 /* intersection_env.py:61-104 (mean over the controlled vehicles) */,
+       TTRL_REWARD_HIGHWAY = 1 /* u_turn_env.py:39-71: UTurnEnv, and the same template on the synthetic highway */,
+       TTRL_REWARD_ROUNDABOUT = 2 /* roundabout_env.py:43-64: speed-index and lane-change terms */ };
 
 typedef struct ttrl_config {
     /* network sizes */
@@ -105,8 +108,15 @@ typedef struct ttrl_config {
     double collision_reward, high_speed_reward, arrived_reward, lane_reward;
     double reward_speed_lo, reward_speed_hi;
     /* IntersectionEnv spawn / clear (intersection_env.py:320-362) */
-    int32_t spawn_enabled, pad5;
+    int32_t spawn_enabled;
+    /* number of controlled vehicles K (config["controlled_vehicles"], intersection_env.py:285-307); 0 is read as 1.
+     * K > 1 = MultiAgentAction / MultiAgentObservation (action.py:301-331, observation.py:587-603): every per-env
+     * action / observation / shuffle-permutation array of this ABI holds K consecutive entries per env. */
+    int32_t controlled_vehicles;
     double spawn_probability;
+    /* RoundaboutEnv (roundabout_env.py:43-64): weight of `action in [0, 2]`, and the denominator of the speed-index
+     * term, MDPVehicle.DEFAULT_TARGET_SPEEDS.size - 1 (controller.py:259) */
+    double lane_change_reward, speed_index_den;
 } ttrl_config;
 
 /* ------------------------------------------------------------------------------------------------
@@ -116,16 +126,19 @@ typedef struct ttrl_config {
 enum { TTRL_D_X = 0, TTRL_D_Y, TTRL_D_HEADING, TTRL_D_SPEED, TTRL_D_STEERING, TTRL_D_ACCEL,
        TTRL_D_TARGET_SPEED, TTRL_D_TIMER, TTRL_D_DELTA, TTRL_D_IMPACT_X, TTRL_D_IMPACT_Y, TTRL_ND = 11 };
 enum { TTRL_I_LANE = 0, TTRL_I_TARGET_LANE, TTRL_I_FLAGS, TTRL_I_SPEED_INDEX, TTRL_I_ROUTE_LEN,
-       TTRL_I_ROUTE_ROAD, TTRL_I_ROUTE_LANE, TTRL_I_YIELD_TIMER, TTRL_NI = 8 };
+       TTRL_I_ROUTE_ROAD, TTRL_I_ROUTE_LANE, TTRL_I_YIELD_TIMER,
+       TTRL_I_ROUTE_ROAD1, TTRL_I_ROUTE_ROAD2, TTRL_I_ROUTE_LANE1, TTRL_I_ROUTE_LANE2, TTRL_NI = 12 };
 /* TTRL_I_FLAGS bits */
 enum { TTRL_FL_MDP = 1 /* MDPVehicle (else IDMVehicle) */, TTRL_FL_CRASHED = 2, TTRL_FL_HAS_IMPACT = 4,
-       TTRL_FL_YIELDING = 8 /* is_yielding attribute is True */, TTRL_FL_CONTROLLED = 16 /* in env.controlled_vehicles */ };
+       TTRL_FL_YIELDING = 8 /* is_yielding attribute is True */, TTRL_FL_CONTROLLED = 16 /* in env.controlled_vehicles */,
+       TTRL_FL_AGENT_SHIFT = 8, TTRL_FL_AGENT_MASK = 0x700 /* index of the vehicle in env.controlled_vehicles */ };
 /* TTRL_I_ROUTE_LEN: -1 = route is None, else number of remaining entries (<= TTRL_ROUTE_CAP).
- * TTRL_I_ROUTE_ROAD / TTRL_I_ROUTE_LANE: entry k in byte k (road index / lane id, 0xFF = None). */
+ * Route entry k (road index / lane id, 0xFF = None) is byte k % 4 of word k / 4; the words of the road bytes are
+ * TTRL_I_ROUTE_ROAD, _ROAD1, _ROAD2, those of the lane bytes TTRL_I_ROUTE_LANE, _LANE1, _LANE2. */
 
 /* Per-env scalars: ibuf[f*E + e], dbuf[f*E + e] */
 enum { TTRL_EI_NVEH = 0, TTRL_EI_STEPS /* env.steps, abstract.py:273 */, TTRL_EI_ROAD_STEPS /* RegulatedRoad.steps */,
-       TTRL_EI_EGO /* slot of controlled_vehicles[0] */, TTRL_EI_EPISODE, TTRL_EI_DONE, TTRL_NEI = 6 };
+       TTRL_EI_EGO /* slot of controlled_vehicles[0]; agents k >= 1 are found by their TTRL_FL_AGENT bits */, TTRL_EI_EPISODE, TTRL_EI_DONE, TTRL_NEI = 6 };
 enum { TTRL_ED_TIME = 0 /* env.time, abstract.py:239 */, TTRL_ED_RETURN, TTRL_NED = 2 };
 
 /* Spawn draws injected for parity (the reference draws from numpy PCG64: intersection_env.py:328-346,
@@ -152,7 +165,7 @@ typedef struct ttrl_reset_params {
     int32_t scene;            /* 0 highway, 1 intersection */
     int32_t n_vehicles;       /* highway: vehicles per env incl. the ego; intersection: initial_vehicle_count */
     int32_t lanes;            /* highway: lanes of road 0 */
-    int32_t ego_entry;        /* intersection: corner of the ego's start lane (o<k>, ir<k>, 0) */
+    int32_t ego_entry;        /* intersection: corner of ego 0's start lane (o<k>, ir<k>, 0); ego j starts on corner (k + j) % 4 */
     int32_t destination;      /* intersection: exit corner 0..3, or -1 = drawn per episode ("destination": None) */
     int32_t warmup_substeps;  /* intersection: 3 * simulation_frequency (intersection_env.py:267-274) */
     int32_t pad0, pad1;
@@ -184,7 +197,14 @@ int ttrl_sim_set_spawn_routes(ttrl_sim* sim, const int32_t* spawn_lane /*4*/, co
                               const int32_t* route_road /*16*TTRL_ROUTE_CAP*/);
 int ttrl_sim_num_envs(const ttrl_sim* sim);
 int ttrl_sim_vcap(const ttrl_sim* sim);
-int ttrl_sim_obs_size(const ttrl_sim* sim); /* floats per env */
+int ttrl_sim_obs_size(const ttrl_sim* sim); /* floats per env (K observations of the configured shape) */
+int ttrl_sim_num_agents(const ttrl_sim* sim); /* K = controlled vehicles per env */
+/* Per-agent results of the last ttrl_sim_step: info["agents_rewards"] / info["agents_terminated"]
+ * (IntersectionEnv._info intersection_env.py:121-129; what MultiAgentWrapper.step returns, abstract.py:432-441).
+ * float32[E*K] / uint8[E*K] device buffers owned by the library, valid for the sim's lifetime. */
+int ttrl_sim_agent_outputs(ttrl_sim* sim, const float** agent_reward_dev, const uint8_t** agent_terminated_dev);
+/* Redirect those per-agent results into caller-owned device buffers (borrowed; NULL = back to the library's own). */
+int ttrl_sim_set_agent_outputs(ttrl_sim* sim, float* agent_reward_dev, uint8_t* agent_terminated_dev);
 
 /* Resync / golden capture (host buffers, layout above).  Replaces direct attribute access on
  * Vehicle objects (kinematics.py:34-48, controller.py:35-48, behavior.py:48-64). */
@@ -208,11 +228,11 @@ int ttrl_sim_reset(ttrl_sim* sim, const uint8_t* mask_dev, void* stream);
 /* One simulation sub-step for every env: [ego meta-action if steps % F == 0] -> Road.act -> (regulation)
  * -> Road.step.  Replaces one iteration of AbstractEnv._simulate (abstract.py:257-273).
  * actions_dev: int32[E] or NULL (no action, like action=None). */
-int ttrl_sim_substep(ttrl_sim* sim, const int32_t* actions_dev, void* stream);
+int ttrl_sim_substep(ttrl_sim* sim, const int32_t* actions_dev /* int32[E*K] */, void* stream);
 
 /* One env.step() for every env.  Replaces AbstractEnv.step (abstract.py:224-250) +
  * IntersectionEnv.step's clear/spawn (intersection_env.py:135-139).
- * obs_dev float32[E*obs_size]; reward_dev float32[E]; terminated_dev/truncated_dev uint8[E]. */
+ * actions_dev int32[E*K]; obs_dev float32[E*obs_size]; reward_dev float32[E]; terminated_dev/truncated_dev uint8[E]. */
 int ttrl_sim_step(ttrl_sim* sim, const int32_t* actions_dev, float* obs_dev, float* reward_dev,
                   uint8_t* terminated_dev, uint8_t* truncated_dev, void* stream);
 
@@ -227,13 +247,15 @@ int ttrl_sim_step_host(ttrl_sim* sim, const int32_t* actions_host, float* obs_ho
  * (they are overwritten by the next call). */
 int ttrl_sim_host_buffers(ttrl_sim* sim, int32_t** actions, float** obs, float** reward, uint8_t** terminated, uint8_t** truncated);
 int ttrl_sim_step_pinned(ttrl_sim* sim, int use_actions);
+/* page-locked float agent_reward[E*K], uint8 agent_terminated[E*K]; filled by ttrl_sim_step_pinned when K > 1 */
+int ttrl_sim_host_agent_buffers(ttrl_sim* sim, float** agent_reward, uint8_t** agent_terminated);
 
 /* Observation only (observation_type.observe() at reset: abstract.py:210). */
 int ttrl_sim_observe(ttrl_sim* sim, float* obs_dev, void* stream);
 
 /* Parity hooks: feed the oracle's RNG draws (spawn decisions; Kinematics "shuffled" permutations). */
 int ttrl_sim_inject_spawn(ttrl_sim* sim, const ttrl_spawn_draw* draws_host /* E records or NULL to clear */);
-int ttrl_sim_inject_shuffle(ttrl_sim* sim, const int32_t* perm_host /* E*(obs_vehicles-1) or NULL */);
+int ttrl_sim_inject_shuffle(ttrl_sim* sim, const int32_t* perm_host /* E*K*(obs_vehicles-1) or NULL */);
 /* seed != 0 enables device-side (Philox) spawn draws keyed by (seed, first_global_env + e, episode, step). */
 int ttrl_sim_seed(ttrl_sim* sim, uint64_t seed, int64_t first_global_env);
 /* spawn outcome of the last step (1 = a vehicle was appended), int32[E] to host */

@@ -65,6 +65,8 @@ class Oracle:
             L.orc_scene_set_spawn_routes(self._sc, _p(sl), _p(rl), _p(rr))
         L.orc_obs_size.argtypes = [C.c_void_p]
         self.obs_size = L.orc_obs_size(self._sc)
+        self.K = max(1, int(cfg.controlled_vehicles))
+        self.agent_reward = self.agent_terminated = None  # per-agent outputs of the last step()
 
     def __del__(self):
         try:
@@ -99,9 +101,12 @@ class Oracle:
         term = np.zeros(E, np.uint8)
         trunc = np.zeros(E, np.uint8)
         accepted = np.zeros(E, np.int32)
-        self._L.orc_step(self._sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(E), C.c_int(st.vcap),
-                         _p(a), _p(obs), _p(reward), _p(term), _p(trunc),
-                         draws if draws is not None else None, _p(accepted), _p(stats), C.c_int(self.threads))
+        self.agent_reward = np.zeros((E, self.K), np.float32)
+        self.agent_terminated = np.zeros((E, self.K), np.uint8)
+        self._L.orc_step_agents(self._sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(E), C.c_int(st.vcap),
+                                _p(a), _p(obs), _p(reward), _p(term), _p(trunc),
+                                draws if draws is not None else None, _p(accepted), _p(stats), C.c_int(self.threads),
+                                _p(self.agent_reward), _p(self.agent_terminated))
         return obs, reward, term, trunc, accepted
 
     def spawn(self, st: SimState, draws, longitudinal: float, position_deviation: float = 1.0,

@@ -17,7 +17,9 @@ ref_shim.install()
 
 from ttrl_env import utils as ref_utils  # noqa: E402
 from ttrl_env.envs.common.abstract import AbstractEnv  # noqa: E402
-from ttrl_env.envs.intersection_env import IntersectionEnv  # noqa: E402
+from ttrl_env.envs.intersection_env import IntersectionEnv, MultiAgentIntersectionEnv  # noqa: E402
+from ttrl_env.envs.roundabout_env import RoundaboutEnv  # noqa: E402
+from ttrl_env.envs.u_turn_env import UTurnEnv  # noqa: E402
 from ttrl_env.road.road import Road, RoadNetwork  # noqa: E402
 from ttrl_env.vehicle.behavior import IDMVehicle  # noqa: E402
 from ttrl_env.vehicle.controller import MDPVehicle  # noqa: E402
@@ -114,6 +116,7 @@ def extract_state(env, table: NetworkTable, vcap: int) -> SimState:
             lane=table.flat(v.lane_index), target_lane=table.flat(v.target_lane_index),
             target_speed=float(v.target_speed), timer=float(getattr(v, "timer", 0.0)), delta=float(getattr(v, "DELTA", 4.0)),
             mdp=is_mdp, controlled=v in env.controlled_vehicles, crashed=bool(v.crashed),
+            agent=env.controlled_vehicles.index(v) if v in env.controlled_vehicles else 0,
             speed_index=int(getattr(v, "speed_index", 0)), route=route,
             steering=float(v.action["steering"]), accel=float(v.action["acceleration"]),
             impact=None if v.impact is None else (float(v.impact[0]), float(v.impact[1])),

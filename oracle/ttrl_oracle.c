@@ -29,6 +29,7 @@ typedef struct {
 
 typedef struct {
     int n, steps, road_steps, ego, episode, done;
+    int egos[TTRL_MAX_CONTROLLED]; /* slots of env.controlled_vehicles; egos[0] == ego */
     double time, ret;
     veh_t v[VMAX];
 } env_t;
@@ -667,12 +668,14 @@ static void enforce_road_rules(const orc_scene* sc, env_t* e) {
  * one simulation sub-step: AbstractEnv._simulate body abstract.py:257-273; Road.act road.py:461-464;
  * RegulatedRoad.step regulation.py:28-32; Road.step road.py:466-478
  * -------------------------------------------------------------------------------------------- */
-static void env_substep(const orc_scene* sc, env_t* e, int action /* raw id or -1 */) {
+static int n_agents(const orc_scene* sc) { return sc->cfg.controlled_vehicles < 1 ? 1 : sc->cfg.controlled_vehicles; }
+static void env_substep(const orc_scene* sc, env_t* e, const int32_t* actions /* K raw ids or NULL */) {
     int F = (int)floor(sc->cfg.simulation_frequency / sc->cfg.policy_frequency);
     double dt = 1 / sc->cfg.simulation_frequency;
-    if (action >= 0 && e->steps % F == 0) {
-        /* DiscreteMetaAction.act action.py:259-260 on controlled_vehicles[0] */
-        mdp_act(sc, &e->v[e->ego], decode_action(sc, action));
+    if (actions && e->steps % F == 0) {
+        /* DiscreteMetaAction.act action.py:259-260 on every controlled vehicle, in order (MultiAgentAction.act :320-323) */
+        for (int k = 0; k < n_agents(sc); ++k)
+            if (actions[k] >= 0) mdp_act(sc, &e->v[e->egos[k]], decode_action(sc, actions[k]));
     }
     for (int i = 0; i < e->n; ++i) {
         if (e->v[i].flags & TTRL_FL_MDP) mdp_act(sc, &e->v[i], A_NONE);
@@ -709,16 +712,16 @@ static int is_relative_feature(int f) { return f == TTRL_F_X || f == TTRL_F_Y ||
 
 /* KinematicObservation.observe observation.py:233-275 (+ normalize_obs :206-231, Road.close_objects_to road.py:418-447).
  * "shuffled" order is applied by the caller (host RNG); rows here are in sorted / list order. */
-static void observe_kinematics(const orc_scene* sc, const env_t* e, float* obs) {
+static void observe_kinematics(const orc_scene* sc, const env_t* e, int observer, float* obs) {
     const ttrl_config* c = &sc->cfg;
     int V = c->obs_vehicles, Fe = c->n_features;
-    const veh_t* ego = &e->v[e->ego];
+    const veh_t* ego = &e->v[observer];
     int idx[VMAX]; double key[VMAX]; int m = 0;
     for (int j = 0; j < e->n; ++j) {
         const veh_t* v = &e->v[j];
         double dx = v->x - ego->x, dy = v->y - ego->y;
         if (!(sqrt(dx * dx + dy * dy) < 200.0)) continue; /* PERCEPTION_DISTANCE abstract.py:41 */
-        if (j == e->ego) continue;
+        if (j == observer) continue;
         double d = lane_distance_to(sc, ego, v);
         if (!(c->see_behind || -2 * 5.0 < d)) continue;
         idx[m] = j; key[m] = fabs(d); m++;
@@ -751,10 +754,10 @@ static void observe_kinematics(const orc_scene* sc, const env_t* e, float* obs) 
 
 /* OccupancyGridObservation.observe observation.py:353-412 (+ normalize :336-351, pos_to_index :414-434,
  * fill_road_layer_by_lanes :453-483).  Relative (absolute=False) only, like the reference (:357-358). */
-static void observe_grid(const orc_scene* sc, const env_t* e, float* obs) {
+static void observe_grid(const orc_scene* sc, const env_t* e, int observer, float* obs) {
     const ttrl_config* c = &sc->cfg;
     int W = c->grid_w, H = c->grid_h, Fe = c->n_features;
-    const veh_t* ego = &e->v[e->ego];
+    const veh_t* ego = &e->v[observer];
     double* grid = (double*)malloc(sizeof(double) * Fe * W * H);
     for (int k = 0; k < Fe * W * H; ++k) grid[k] = NAN;
     double ca = cos(ego->heading), sa = sin(ego->heading);
@@ -805,14 +808,18 @@ static void observe_grid(const orc_scene* sc, const env_t* e, float* obs) {
     }
     free(grid);
 }
-static void observe(const orc_scene* sc, const env_t* e, float* obs) {
-    if (sc->cfg.obs_type == TTRL_OBS_GRID) observe_grid(sc, e, obs);
-    else observe_kinematics(sc, e, obs);
-}
-static int obs_size(const orc_scene* sc) {
+static int obs_single(const orc_scene* sc) {
     const ttrl_config* c = &sc->cfg;
     return c->obs_type == TTRL_OBS_GRID ? c->n_features * c->grid_w * c->grid_h : c->obs_vehicles * c->n_features;
 }
+/* observation_type.observe(); MultiAgentObservation.observe observation.py:602-603: one block per controlled vehicle */
+static void observe(const orc_scene* sc, const env_t* e, float* obs) {
+    for (int k = 0; k < n_agents(sc); ++k) {
+        if (sc->cfg.obs_type == TTRL_OBS_GRID) observe_grid(sc, e, e->egos[k], obs + (size_t)k * obs_single(sc));
+        else observe_kinematics(sc, e, e->egos[k], obs + (size_t)k * obs_single(sc));
+    }
+}
+static int obs_size(const orc_scene* sc) { return n_agents(sc) * obs_single(sc); }
 
 /* ----------------------------------------------------------------------------------------------
  * reward / termination
@@ -825,9 +832,18 @@ static int has_arrived(const orc_scene* sc, const veh_t* v) {
     return s >= 25;
 }
 /* IntersectionEnv._agent_reward(s) intersection_env.py:78-104; highway: u_turn_env.py:39-71 template */
-static double agent_reward(const orc_scene* sc, const veh_t* v) {
+static double agent_reward(const orc_scene* sc, const veh_t* v, int raw_action) {
     const ttrl_config* c = &sc->cfg;
     double crashed = (v->flags & TTRL_FL_CRASHED) ? 1 : 0;
+    if (c->reward_type == TTRL_REWARD_ROUNDABOUT) { /* RoundaboutEnv._reward / _rewards roundabout_env.py:43-64 */
+        double hs = (double)v->speed_index / c->speed_index_den; /* MDPVehicle.get_speed_index / (DEFAULT_TARGET_SPEEDS.size - 1) */
+        double lc = (raw_action == 0 || raw_action == 2) ? 1 : 0; /* action in [0, 2] */
+        double onr0 = on_road(sc, v);
+        double reward = 0 + c->collision_reward * crashed + c->high_speed_reward * hs + c->lane_change_reward * lc + 0 * onr0;
+        if (c->normalize_reward) reward = lmap(reward, c->collision_reward, c->high_speed_reward, 0, 1);
+        reward *= onr0;
+        return reward;
+    }
     double scaled = lmap(v->speed, c->reward_speed_lo, c->reward_speed_hi, 0, 1);
     double hs = clipd(scaled, 0, 1);
     double onr = on_road(sc, v);
@@ -852,9 +868,23 @@ static double agent_reward(const orc_scene* sc, const veh_t* v) {
 static int is_terminated(const orc_scene* sc, const env_t* e) {
     const veh_t* v = &e->v[e->ego];
     int crashed = (v->flags & TTRL_FL_CRASHED) != 0;
-    if (sc->cfg.reward_type == TTRL_REWARD_INTERSECTION)
-        return crashed || has_arrived(sc, v) || (sc->cfg.offroad_terminal && !on_road(sc, v));
+    if (sc->cfg.reward_type == TTRL_REWARD_ROUNDABOUT) return crashed; /* roundabout_env.py:66-67 */
+    if (sc->cfg.reward_type == TTRL_REWARD_INTERSECTION) {
+        /* any(crashed) or all(has_arrived) over controlled_vehicles or (offroad_terminal and not self.vehicle.on_road) */
+        int any_crashed = 0, all_arrived = 1;
+        for (int k = 0; k < n_agents(sc); ++k) {
+            const veh_t* a = &e->v[e->egos[k]];
+            if (a->flags & TTRL_FL_CRASHED) any_crashed = 1;
+            if (!has_arrived(sc, a)) all_arrived = 0;
+        }
+        return any_crashed || all_arrived || (sc->cfg.offroad_terminal && !on_road(sc, v));
+    }
     return crashed || (sc->cfg.offroad_terminal && !on_road(sc, v));
+}
+static void find_agents(env_t* e) {
+    for (int i = 0; i < e->n; ++i)
+        if ((e->v[i].flags & TTRL_FL_CONTROLLED) && (e->v[i].flags & TTRL_FL_AGENT_MASK))
+            e->egos[(e->v[i].flags & TTRL_FL_AGENT_MASK) >> TTRL_FL_AGENT_SHIFT] = i;
 }
 
 /* ----------------------------------------------------------------------------------------------
@@ -873,7 +903,8 @@ static void clear_vehicles(const orc_scene* sc, env_t* e) {
         }
         if (keep) { if (i == e->ego) new_ego = w; if (w != i) e->v[w] = e->v[i]; w++; }
     }
-    e->n = w; e->ego = new_ego;
+    e->n = w; e->ego = new_ego; e->egos[0] = new_ego;
+    find_agents(e);
 }
 /* returns 1 if a vehicle was appended.  longitudinal/deviations as in _spawn_vehicle's signature. */
 static int spawn_vehicle(const orc_scene* sc, env_t* e, const ttrl_spawn_draw* d, double longitudinal,
@@ -921,14 +952,17 @@ static void load_env(env_t* e, const double* vd, const int32_t* vi, const int32_
         v->timer = D(TTRL_D_TIMER); v->delta = D(TTRL_D_DELTA); v->impact_x = D(TTRL_D_IMPACT_X); v->impact_y = D(TTRL_D_IMPACT_Y);
         v->lane = I(TTRL_I_LANE); v->target_lane = I(TTRL_I_TARGET_LANE); v->flags = I(TTRL_I_FLAGS);
         v->speed_index = I(TTRL_I_SPEED_INDEX); v->route_len = I(TTRL_I_ROUTE_LEN); v->yield_timer = I(TTRL_I_YIELD_TIMER);
-        uint32_t rr = (uint32_t)I(TTRL_I_ROUTE_ROAD), rl = (uint32_t)I(TTRL_I_ROUTE_LANE);
+        const uint32_t rr[TTRL_ROUTE_WORDS] = {(uint32_t)I(TTRL_I_ROUTE_ROAD), (uint32_t)I(TTRL_I_ROUTE_ROAD1), (uint32_t)I(TTRL_I_ROUTE_ROAD2)};
+        const uint32_t rl[TTRL_ROUTE_WORDS] = {(uint32_t)I(TTRL_I_ROUTE_LANE), (uint32_t)I(TTRL_I_ROUTE_LANE1), (uint32_t)I(TTRL_I_ROUTE_LANE2)};
         for (int k = 0; k < TTRL_ROUTE_CAP; ++k) {
-            v->route_road[k] = (rr >> (8 * k)) & 0xFF;
-            int b = (rl >> (8 * k)) & 0xFF; v->route_lane[k] = b == 0xFF ? -1 : b;
+            v->route_road[k] = (rr[k >> 2] >> (8 * (k & 3))) & 0xFF;
+            int b = (rl[k >> 2] >> (8 * (k & 3))) & 0xFF; v->route_lane[k] = b == 0xFF ? -1 : b;
         }
 #undef D
 #undef I
     }
+    for (int k = 0; k < TTRL_MAX_CONTROLLED; ++k) e->egos[k] = e->ego;
+    find_agents(e);
 }
 static void store_env(const env_t* e, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int V, int ie) {
     ei[TTRL_EI_NVEH * E + ie] = e->n; ei[TTRL_EI_STEPS * E + ie] = e->steps; ei[TTRL_EI_ROAD_STEPS * E + ie] = e->road_steps;
@@ -944,13 +978,15 @@ static void store_env(const env_t* e, double* vd, int32_t* vi, int32_t* ei, doub
         D(TTRL_D_TIMER) = v->timer; D(TTRL_D_DELTA) = v->delta; D(TTRL_D_IMPACT_X) = v->impact_x; D(TTRL_D_IMPACT_Y) = v->impact_y;
         I(TTRL_I_LANE) = v->lane; I(TTRL_I_TARGET_LANE) = v->target_lane; I(TTRL_I_FLAGS) = v->flags;
         I(TTRL_I_SPEED_INDEX) = v->speed_index; I(TTRL_I_ROUTE_LEN) = s < e->n ? v->route_len : 0; I(TTRL_I_YIELD_TIMER) = v->yield_timer;
-        uint32_t rr = 0, rl = 0;
+        uint32_t rr[TTRL_ROUTE_WORDS] = {0, 0, 0}, rl[TTRL_ROUTE_WORDS] = {0, 0, 0};
         for (int k = 0; k < TTRL_ROUTE_CAP; ++k) {
             int on = s < e->n && k < v->route_len;
-            rr |= (uint32_t)((on ? v->route_road[k] : 0) & 0xFF) << (8 * k);
-            rl |= (uint32_t)((on ? (v->route_lane[k] < 0 ? 0xFF : v->route_lane[k]) : 0) & 0xFF) << (8 * k);
+            rr[k >> 2] |= (uint32_t)((on ? v->route_road[k] : 0) & 0xFF) << (8 * (k & 3));
+            rl[k >> 2] |= (uint32_t)((on ? (v->route_lane[k] < 0 ? 0xFF : v->route_lane[k]) : 0) & 0xFF) << (8 * (k & 3));
         }
-        I(TTRL_I_ROUTE_ROAD) = (int32_t)rr; I(TTRL_I_ROUTE_LANE) = (int32_t)rl;
+        I(TTRL_I_ROUTE_ROAD) = (int32_t)rr[0]; I(TTRL_I_ROUTE_LANE) = (int32_t)rl[0];
+        I(TTRL_I_ROUTE_ROAD1) = (int32_t)rr[1]; I(TTRL_I_ROUTE_LANE1) = (int32_t)rl[1];
+        I(TTRL_I_ROUTE_ROAD2) = (int32_t)rr[2]; I(TTRL_I_ROUTE_LANE2) = (int32_t)rl[2];
 #undef D
 #undef I
     }
@@ -1000,7 +1036,7 @@ void orc_substep(const orc_scene* sc, double* vd, int32_t* vi, int32_t* ei, doub
 #pragma omp parallel for num_threads(threads) schedule(dynamic, 4)
     for (int ie = 0; ie < E; ++ie) {
         env_t e; load_env(&e, vd, vi, ei, ed, E, V, ie);
-        env_substep(sc, &e, actions ? actions[ie] : -1);
+        env_substep(sc, &e, actions ? actions + (size_t)ie * n_agents(sc) : NULL);
         store_env(&e, vd, vi, ei, ed, E, V, ie);
     }
 }
@@ -1016,9 +1052,18 @@ void orc_observe(const orc_scene* sc, const double* vd, const int32_t* vi, const
 
 /* One env.step() for E envs: AbstractEnv.step abstract.py:224-250 then IntersectionEnv.step's clear + spawn
  * (intersection_env.py:135-139).  draws == NULL -> no spawn attempt.  stats[8] accumulates ttrl_episode_stats. */
+void orc_step_agents(const orc_scene* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int V, const int32_t* actions,
+              float* obs, float* reward, uint8_t* terminated, uint8_t* truncated, const ttrl_spawn_draw* draws,
+              int32_t* spawn_accepted, double* stats, int threads, float* agent_reward_out, uint8_t* agent_term_out);
 void orc_step(const orc_scene* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int V, const int32_t* actions,
               float* obs, float* reward, uint8_t* terminated, uint8_t* truncated, const ttrl_spawn_draw* draws,
               int32_t* spawn_accepted, double* stats, int threads) {
+    orc_step_agents(sc, vd, vi, ei, ed, E, V, actions, obs, reward, terminated, truncated, draws, spawn_accepted, stats, threads, NULL, NULL);
+}
+/* same + per-agent outputs: info["agents_rewards"], info["agents_terminated"] (intersection_env.py:121-129), [E][K] */
+void orc_step_agents(const orc_scene* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int V, const int32_t* actions,
+              float* obs, float* reward, uint8_t* terminated, uint8_t* truncated, const ttrl_spawn_draw* draws,
+              int32_t* spawn_accepted, double* stats, int threads, float* agent_reward_out, uint8_t* agent_term_out) {
     int F = (int)floor(sc->cfg.simulation_frequency / sc->cfg.policy_frequency);
     int osz = obs_size(sc);
     double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1026,9 +1071,20 @@ void orc_step(const orc_scene* sc, double* vd, int32_t* vi, int32_t* ei, double*
     for (int ie = 0; ie < E; ++ie) {
         env_t e; load_env(&e, vd, vi, ei, ed, E, V, ie);
         e.time += 1 / sc->cfg.policy_frequency;
-        for (int f = 0; f < F; ++f) { env_substep(sc, &e, actions ? actions[ie] : -1); st[6] += e.n; }
+        const int K = n_agents(sc);
+        const int32_t* act = actions ? actions + (size_t)ie * K : NULL;
+        for (int f = 0; f < F; ++f) { env_substep(sc, &e, act); st[6] += e.n; }
         observe(sc, &e, obs + (size_t)ie * osz);
-        double r = agent_reward(sc, &e.v[e.ego]);
+        /* IntersectionEnv._reward intersection_env.py:61-65: sum(agent rewards) / len(controlled_vehicles) */
+        double r = 0;
+        for (int k = 0; k < K; ++k) {
+            const veh_t* a = &e.v[e.egos[k]];
+            double rk = agent_reward(sc, a, act ? act[k] : -1);
+            r = r + rk;
+            if (agent_reward_out) agent_reward_out[(size_t)ie * K + k] = (float)rk;
+            if (agent_term_out) agent_term_out[(size_t)ie * K + k] = (uint8_t)(((a->flags & TTRL_FL_CRASHED) != 0) || has_arrived(sc, a)); /* :113-115 */
+        }
+        r = r / K;
         int term = is_terminated(sc, &e), trunc = e.time >= sc->cfg.duration;
         reward[ie] = (float)r; terminated[ie] = (uint8_t)term; truncated[ie] = (uint8_t)trunc;
         e.ret += r; st[7] += 1; st[5] += e.v[e.ego].speed;

@@ -35,6 +35,8 @@ def batch_state(g, prefix: str, sel=None) -> SimState:
     vd, vi, ei, ed = (g[prefix + s] for s in ("_vd", "_vi", "_ei", "_ed"))
     if sel is not None:
         vd, vi, ei, ed = vd[sel], vi[sel], ei[sel], ed[sel]
+    if vi.shape[1] < abi.NI:  # fixtures written before the route grew to 12 entries: words 1, 2 are zero (routes <= 4 entries)
+        vi = np.concatenate([vi, np.zeros((vi.shape[0], abi.NI - vi.shape[1], vi.shape[2]), vi.dtype)], axis=1)
     return SimState(np.ascontiguousarray(vd.transpose(1, 0, 2)), np.ascontiguousarray(vi.transpose(1, 0, 2)),
                     np.ascontiguousarray(ei.T), np.ascontiguousarray(ed.T))
 
@@ -71,7 +73,8 @@ def compare_states(got: SimState, want: SimState, tol: float, what: str = "", ch
     n_got, n_want = got.env_i[abi.EI_NVEH], want.env_i[abi.EI_NVEH]
     assert (n_got == n_want).all(), f"{what}: vehicle counts differ at envs {np.nonzero(n_got != n_want)[0][:8]}"
     live = want.live_mask()
-    for f, name in enumerate(["lane", "target_lane", "flags", "speed_index", "route_len", "route_road", "route_lane", "yield_timer"]):
+    for f, name in enumerate(["lane", "target_lane", "flags", "speed_index", "route_len", "route_road", "route_lane", "yield_timer",
+                              "route_road1", "route_road2", "route_lane1", "route_lane2"]):
         bad = (got.veh_i[f] != want.veh_i[f]) & live
         assert not bad.any(), (f"{what}: discrete field {name} differs at (env,slot) {np.argwhere(bad)[:8].tolist()} "
                                f"got {got.veh_i[f][bad][:8]} want {want.veh_i[f][bad][:8]}")
@@ -119,3 +122,38 @@ def stress_states(cfgd, E: int, n: int, seed: int = 0):
             st.veh_i[:, e, k:] = 0
             st.env_i[abi.EI_NVEH, e] = k
     return st
+
+
+# --------------------------------------------------------------------------------------------------
+# scenes of SURVEY.md section 8 rows A29 / N3: multi-agent intersection, roundabout, u-turn
+# --------------------------------------------------------------------------------------------------
+MULTI_AGENT = {"observation": {"type": "MultiAgentObservation",
+                               "observation_config": {"type": "Kinematics", "vehicles_count": 15,
+                                                      "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+                                                      "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]},
+                                                      "absolute": True, "order": "sorted"}},
+               "initial_vehicle_count": 5, "controlled_vehicles": 4}
+UTURN_KIN = {"observation": {"type": "Kinematics", "vehicles_count": 6, "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+                             "absolute": False, "order": "sorted"}}
+
+
+def multi_agent_scene(overrides=MULTI_AGENT):
+    net = scenes.make_intersection_network()
+    table = net.to_table(scenes.intersection_exit_predicate)
+    cfgd = scenes.merged_config(scenes.MULTI_AGENT_INTERSECTION_CONFIG, overrides)
+    cfg = scenes.build_config(table, cfgd, "intersection")
+    return net, table, cfg, cfgd, scenes.intersection_spawn_routes(net, table)
+
+
+def roundabout_scene(overrides=None):
+    net = scenes.make_roundabout_network()
+    table = net.to_table()
+    cfgd = scenes.merged_config(scenes.ROUNDABOUT_CONFIG, overrides)
+    return net, table, scenes.build_config(table, cfgd, "roundabout", ego_lanes_count=1), cfgd
+
+
+def uturn_scene(overrides=UTURN_KIN):
+    net = scenes.make_uturn_network()
+    table = net.to_table()
+    cfgd = scenes.merged_config(scenes.UTURN_CONFIG, overrides)
+    return net, table, scenes.build_config(table, cfgd, "u-turn", ego_lanes_count=2), cfgd

@@ -112,7 +112,7 @@ void emu_substep(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, doubl
         HostExec ex{V};
         for (int e = 0; e < E; ++e) {
             load_env(env.c, ex, g, e);
-            env_substep(env.c, ex, actions ? actions[e] : -1);
+            env_substep(env.c, ex, actions ? actions + (size_t)e * n_agents(env.c) : nullptr);
             store_env(env.c, ex, g, e);
         }
     });
@@ -126,7 +126,7 @@ void emu_observe(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, doubl
         HostExec ex{V};
         for (int e = 0; e < E; ++e) {
             load_env(env.c, ex, g, e);
-            observe(env.c, ex, obs + (size_t)e * obs_size, inv_perm ? inv_perm + (size_t)e * (sc->cfg.obs_vehicles - 1) : nullptr);
+            observe(env.c, ex, obs + (size_t)e * obs_size, inv_perm ? inv_perm + (size_t)e * n_agents(env.c) * (sc->cfg.obs_vehicles - 1) : nullptr);
         }
     });
 }
@@ -134,9 +134,10 @@ void emu_observe(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, doubl
 void emu_step(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, const int32_t* actions,
               float* obs, int obs_size, float* reward, uint8_t* terminated, uint8_t* truncated, const ttrl_spawn_draw* draws,
               int32_t* accepted, const int32_t* inv_perm, double* stats, int pool_size, double* pvd, int32_t* pvi, int32_t* pei,
-              double* ped, int autoreset, uint64_t seed, int64_t first_global_env) {
+              double* ped, int autoreset, uint64_t seed, int64_t first_global_env, float* agent_reward, uint8_t* agent_terminated) {
     GlobalState g{vd, vi, ei, ed, E, Vs};
     StepIO io{};
+    io.agent_reward = agent_reward; io.agent_terminated = agent_terminated;
     io.actions = actions; io.obs = obs; io.reward = reward; io.terminated = terminated; io.truncated = truncated;
     io.draws = draws; io.spawn_accepted = accepted; io.inv_perm = inv_perm; io.stats = stats;
     io.pool = GlobalState{pvd, pvi, pei, ped, pool_size, Vs};

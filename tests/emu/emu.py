@@ -40,7 +40,9 @@ class Emulator:
         if spawn_routes is not None:
             sl, rl, rr = (np.ascontiguousarray(a, dtype=np.int32) for a in spawn_routes)
             self.L.emu_scene_set_spawn_routes(self.sc, _p(sl), _p(rl), _p(rr))
-        self.obs_size = (cfg.n_features * cfg.grid_w * cfg.grid_h) if cfg.obs_type == abi.OBS_GRID else cfg.obs_vehicles * cfg.n_features
+        self.K = max(1, int(cfg.controlled_vehicles))
+        self.obs_size = self.K * ((cfg.n_features * cfg.grid_w * cfg.grid_h) if cfg.obs_type == abi.OBS_GRID else cfg.obs_vehicles * cfg.n_features)
+        self.agent_reward = self.agent_terminated = None  # per-agent outputs of the last step()
         self.pool = None
         self.autoreset = False
 
@@ -62,13 +64,15 @@ class Emulator:
         term = np.zeros(E, np.uint8)
         trunc = np.zeros(E, np.uint8)
         acc = np.zeros(E, np.int32)
+        self.agent_reward = np.zeros((E, self.K), np.float32)
+        self.agent_terminated = np.zeros((E, self.K), np.uint8)
         pool = self.pool
         self.L.emu_step(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(E), C.c_int(st.vcap), _p(a),
                         _p(obs), C.c_int(self.obs_size), _p(reward), _p(term), _p(trunc), draws, _p(acc), _p(inv_perm), _p(stats),
                         C.c_int(pool.num_envs if pool is not None else 0),
                         _p(pool.veh_d) if pool is not None else None, _p(pool.veh_i) if pool is not None else None,
                         _p(pool.env_i) if pool is not None else None, _p(pool.env_d) if pool is not None else None,
-                        C.c_int(int(self.autoreset)), C.c_uint64(seed), C.c_int64(first_env))
+                        C.c_int(int(self.autoreset)), C.c_uint64(seed), C.c_int64(first_env), _p(self.agent_reward), _p(self.agent_terminated))
         return obs, reward, term, trunc, acc
 
     def set_reset_params(self, rp):

@@ -151,6 +151,81 @@ def highway(n_vehicles, density, seeds, n_substeps, name, obs_overrides=None, wi
     rec.save(name + "_steps.npz")
 
 
+MULTI_AGENT = {"observation": {"type": "MultiAgentObservation",
+                               "observation_config": {"type": "Kinematics", "vehicles_count": 15,
+                                                      "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+                                                      "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]},
+                                                      "absolute": True, "order": "sorted"}},
+               "initial_vehicle_count": 5, "controlled_vehicles": 4}
+UTURN_KIN = {"observation": {"type": "Kinematics", "vehicles_count": 6, "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+                             "absolute": False, "order": "sorted"}}
+
+
+def multi_agent_steps(seeds, overrides, name, vcap=32):
+    """MultiAgentIntersectionEnv (intersection_env.py:372-394; scripts/configs/IntersectionEnv/env_multi_agent.json with a
+    sorted observation order): post-reset states, full steps with tuple actions, per-agent rewards / terminal flags."""
+    net = scenes.make_intersection_network()
+    table = net.to_table(scenes.intersection_exit_predicate)
+    env = H.MultiAgentIntersectionEnv(config=overrides)
+    K = env.config["controlled_vehicles"]
+    rec = Rec()
+    rng = np.random.default_rng(77)
+    for seed in seeds:
+        obs, _ = env.reset(seed=seed)
+        rec.add_state("reset", H.extract_state(env, table, vcap))
+        rec.add(reset_seed=seed, reset_obs=np.stack(obs).astype(np.float32))
+        proxy = H.RecordingRng(env.np_random)
+        env.np_random = proxy
+        env.road.np_random = proxy
+        done = False
+        while not done:
+            a = tuple(int(x) for x in rng.integers(0, 3, size=K))
+            rec.add_state("before", H.extract_state(env, table, vcap))
+            proxy.log.clear()
+            obs, reward, term, trunc, info = env.step(a)
+            rec.add(action=np.array(a, np.int32), draw=draw_array(H.draws_from_log(proxy.log)), obs=np.stack(obs).astype(np.float32),
+                    reward=np.float64(reward), terminated=bool(term), truncated=bool(trunc),
+                    agents_rewards=np.array(info["agents_rewards"], np.float64),
+                    agents_terminated=np.array(info["agents_terminated"], bool))
+            rec.add_state("after", H.extract_state(env, table, vcap))
+            done = term or trunc
+    rec.save(name)
+
+
+def scripted_scene(env_cls, net, overrides, seeds, name, n_actions, vcap=16):
+    """RoundaboutEnv / UTurnEnv: post-reset states per seed, per-sub-step and per-step snapshots under random actions."""
+    H.restore_idm_class_constants()  # IntersectionEnv mutates the IDMVehicle class constants process-wide
+    table = net.to_table()
+    env = env_cls(config=overrides)
+    rec, sub = Rec(), Rec()
+    rng = np.random.default_rng(555)
+    for seed in seeds:
+        obs, _ = env.reset(seed=seed)
+        rec.add_state("reset", H.extract_state(env, table, vcap))
+        rec.add(reset_seed=seed, reset_obs=np.asarray(obs, np.float32))
+        done = False
+        k = 0
+        while not done:
+            a = int(rng.integers(0, n_actions))
+            if k % 3 == 2:  # every third env-step sub-step by sub-step (same transition; finer resync for the parity tests)
+                env.time += 1 / env.config["policy_frequency"]
+                for _ in range(15):
+                    sub.add_state("before", H.extract_state(env, table, vcap))
+                    sub.add(action=a)
+                    H.ref_substep(env, a)
+                    sub.add_state("after", H.extract_state(env, table, vcap))
+                done = env._is_terminated() or env._is_truncated()
+            else:
+                rec.add_state("before", H.extract_state(env, table, vcap))
+                obs, reward, term, trunc, info = env.step(a)
+                rec.add(action=a, obs=np.asarray(obs, np.float32), reward=np.float64(reward), terminated=bool(term), truncated=bool(trunc))
+                rec.add_state("after", H.extract_state(env, table, vcap))
+                done = term or trunc
+            k += 1
+    rec.save(name + "_steps.npz")
+    sub.save(name + "_substeps.npz")
+
+
 def function_kats():
     """Function-level known answers: reference function outputs on random inputs."""
     from ttrl_env import utils as U
@@ -290,7 +365,7 @@ def qnet_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kat", "int_sub", "int_steps", "int_reset", "hw", "qnet"]
+    which = sys.argv[1:] or ["kat", "int_sub", "int_steps", "int_reset", "hw", "qnet", "multi", "scripted"]
     if "kat" in which:
         function_kats()
     if "int_sub" in which:
@@ -310,3 +385,8 @@ if __name__ == "__main__":
                                                "grid_size": [[-32, 32], [-32, 32]], "grid_step": [2, 2], "absolute": False}})
     if "qnet" in which:
         qnet_vectors()
+    if "multi" in which:
+        multi_agent_steps(range(400, 406), MULTI_AGENT, "multiagent_steps.npz")
+    if "scripted" in which:
+        scripted_scene(H.RoundaboutEnv, scenes.make_roundabout_network(), None, range(500, 508), "roundabout", 5)
+        scripted_scene(H.UTurnEnv, scenes.make_uturn_network(), UTURN_KIN, range(600, 606), "uturn", 5)

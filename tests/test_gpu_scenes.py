@@ -1,0 +1,197 @@
+"""CUDA path, through the C ABI, for SURVEY.md section 8 rows A29 (K controlled vehicles: MultiAgentIntersectionEnv) and N3
+(RoundaboutEnv, UTurnEnv), against golden vectors of the unmodified reference and against the CPU oracle.  Same bars as
+tests/test_gpu_parity.py: discrete fields bit-exact, continuous state within 1e-9 per resynced sub-step / 1e-6 per env-step.
+"""
+import numpy as np
+import pytest
+
+from topotrafficrl_b200 import abi, scenes
+from tests import common as T
+from tests.test_gpu_parity import _dev_step, _sim, _torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_multi_agent_step_vs_reference_golden():
+    torch = _torch()
+    g = T.golden("multiagent_steps.npz")
+    _, table, cfg, _, routes = T.multi_agent_scene()
+    st = T.batch_state(g, "before")
+    sim = _sim(cfg, table, st.num_envs, st.vcap, routes)
+    assert sim.num_agents == 4 and sim.obs_size == 4 * 15 * 7
+    sim.set_state(st)
+    sim.inject_spawn(T.draws_array(g["draw"]))
+    E, K = st.num_envs, 4
+    ar = torch.zeros(E * K, dtype=torch.float32, device="cuda")
+    at = torch.zeros(E * K, dtype=torch.uint8, device="cuda")
+    sim.set_agent_outputs_ptr(ar.data_ptr(), at.data_ptr())  # per-agent outputs into caller-owned device buffers
+    assert sim.agent_outputs_ptr() == (ar.data_ptr(), at.data_ptr())
+    obs, reward, term, trunc = _dev_step(sim, g["action"])
+    T.compare_states(sim.get_state(), T.batch_state(g, "after"), T.TOL_STEP, "multi-agent step")
+    np.testing.assert_allclose(obs.reshape(g["obs"].shape), g["obs"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(reward, g["reward"], rtol=0, atol=1e-6)
+    assert (term.astype(bool) == g["terminated"]).all() and (trunc.astype(bool) == g["truncated"]).all()
+    np.testing.assert_allclose(ar.cpu().numpy().reshape(E, K), g["agents_rewards"], rtol=0, atol=1e-6)
+    assert (at.cpu().numpy().reshape(E, K).astype(bool) == g["agents_terminated"]).all()
+    # the host-buffer form reports the same through the library's page-locked buffers
+    sim.set_state(st)
+    sim.inject_spawn(T.draws_array(g["draw"]))
+    h_obs, h_rew, h_term, h_trunc = sim.step_host(g["action"].astype(np.int32))
+    h_ar, h_at = sim.agent_outputs_host()
+    np.testing.assert_array_equal(h_obs.reshape(-1), obs.reshape(-1))
+    np.testing.assert_array_equal(h_ar, ar.cpu().numpy().reshape(E, K))
+    np.testing.assert_array_equal(h_at, at.cpu().numpy().reshape(E, K))
+    sim.close()
+
+
+def test_multi_agent_env_episodes_match_reference():
+    """MultiAgentIntersectionEnv front end: seeded reset + tuple actions reproduce the reference's episodes
+    (state at reset, K observations, aggregated reward, per-agent info) with the env's own numpy RNG stream."""
+    from topotrafficrl_b200._gym import make
+    import topotrafficrl_b200.envs  # noqa: F401  (registers the ids)
+    g = T.golden("multiagent_steps.npz")
+    env = make("intersection-multi-agent-v0", config=T.MULTI_AGENT)
+    k = 0
+    for r, seed in enumerate(g["reset_seed"]):
+        obs, _ = env.reset(seed=int(seed))
+        assert isinstance(obs, tuple) and len(obs) == 4
+        np.testing.assert_allclose(np.stack(obs), g["reset_obs"][r], rtol=0, atol=2e-6)
+        T.compare_states(env.sim.get_state(), T.batch_state(g, "reset", slice(r, r + 1)), 1e-9, f"reset seed {seed}")
+        done = False
+        while not done:
+            obs, reward, term, trunc, info = env.step(tuple(int(a) for a in g["action"][k]))
+            np.testing.assert_allclose(np.stack(obs), g["obs"][k], rtol=0, atol=1e-5, err_msg=f"seed {seed} k {k}")
+            assert abs(reward - g["reward"][k]) <= 1e-6
+            assert term == bool(g["terminated"][k]) and trunc == bool(g["truncated"][k])
+            np.testing.assert_allclose(info["agents_rewards"], g["agents_rewards"][k], rtol=0, atol=1e-6)
+            assert info["agents_terminated"] == tuple(bool(x) for x in g["agents_terminated"][k])
+            done = term or trunc
+            k += 1
+    assert k == len(g["action"])
+    env.close()
+    # -v1 = the same env behind MultiAgentWrapper: per-agent rewards / terminal flags in the step tuple
+    env = make("intersection-multi-agent-v1", config=T.MULTI_AGENT)
+    env.reset(seed=int(g["reset_seed"][0]))
+    obs, reward, term, trunc, info = env.step(tuple(int(a) for a in g["action"][0]))
+    np.testing.assert_allclose(reward, g["agents_rewards"][0], rtol=0, atol=1e-6)
+    assert term == tuple(bool(x) for x in g["agents_terminated"][0])
+    env.close()
+
+
+def test_multi_agent_vector_env_vs_oracle():
+    """Throughput form: 512 multi-agent envs, device-side resets, [E, K] actions; the oracle replays the device's states."""
+    torch = _torch()
+    from oracle import oracle as O
+    from topotrafficrl_b200 import TTRLVectorEnv
+    E, K = 512, 4
+    env = TTRLVectorEnv(E, "intersection", config=dict(T.MULTI_AGENT, **{"action": scenes.MULTI_AGENT_INTERSECTION_CONFIG["action"]}),
+                        seed=3, autoreset=False)
+    assert env.num_agents == K and env.obs_shape == (K, 15, 7)
+    obs, _ = env.reset()
+    orc = O.Oracle(env.cfg, env.table, scenes.intersection_spawn_routes(env.net, env.table), threads=8)
+    rng = np.random.default_rng(1)
+    for step in range(4):
+        st = env.get_state()
+        n = st.env_i[abi.EI_NVEH]
+        assert (n >= K).all()
+        act = rng.integers(0, 3, size=(E, K)).astype(np.int32)
+        env.sim.inject_spawn(None)
+        obs, reward, term, trunc, info = env.step(torch.as_tensor(act, device="cuda"))
+        torch.cuda.synchronize()
+        # the oracle cannot reproduce the device's Philox spawn draws: compare everything before clear / spawn
+        o_obs, o_rew, o_term, o_trunc, _ = orc.step(st, act, None)
+        np.testing.assert_allclose(obs.cpu().numpy().reshape(E, -1), o_obs, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(reward.cpu().numpy(), o_rew, rtol=0, atol=1e-6)
+        assert (term.cpu().numpy() == o_term.astype(bool)).all() and (trunc.cpu().numpy() == o_trunc.astype(bool)).all()
+        np.testing.assert_allclose(info["agents_rewards"].cpu().numpy(), orc.agent_reward, rtol=0, atol=1e-6)
+        assert (info["agents_terminated"].cpu().numpy() == orc.agent_terminated.astype(bool)).all()
+    env.close()
+
+
+@pytest.mark.parametrize("scene", ["roundabout", "uturn"])
+def test_scripted_scene_vs_reference_golden(scene):
+    torch = _torch()
+    _, table, cfg, _ = T.roundabout_scene() if scene == "roundabout" else T.uturn_scene()
+    gs, g = T.golden(f"{scene}_substeps.npz"), T.golden(f"{scene}_steps.npz")
+    st = T.batch_state(gs, "before")
+    sim = _sim(cfg, table, st.num_envs, st.vcap)
+    sim.set_state(st)
+    a = torch.as_tensor(gs["action"].astype(np.int32), device="cuda")
+    sim.substep_ptr(a.data_ptr(), 0)
+    T.compare_states(sim.get_state(), T.batch_state(gs, "after"), T.TOL_SUBSTEP, f"{scene} sub-step")
+    sim.close()
+    st = T.batch_state(g, "before")
+    sim = _sim(cfg, table, st.num_envs, st.vcap)
+    sim.set_state(st)
+    obs, reward, term, trunc = _dev_step(sim, g["action"])
+    T.compare_states(sim.get_state(), T.batch_state(g, "after"), T.TOL_STEP, f"{scene} step")
+    np.testing.assert_allclose(obs.reshape(g["obs"].shape), g["obs"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(reward, g["reward"], rtol=0, atol=1e-6)
+    assert (term.astype(bool) == g["terminated"]).all() and (trunc.astype(bool) == g["truncated"]).all()
+    sim.close()
+
+
+@pytest.mark.parametrize("scene,env_id,over", [("roundabout", "roundabout-v0", None), ("uturn", "u-turn-v0", T.UTURN_KIN)])
+def test_scripted_env_episodes_match_reference(scene, env_id, over):
+    """RoundaboutEnv / UTurnEnv front ends: reset(seed) == the reference's reset; stepping the golden actions from the
+    golden 'before' states reproduces obs / reward / flags."""
+    from topotrafficrl_b200._gym import make
+    import topotrafficrl_b200.envs  # noqa: F401
+    g = T.golden(f"{scene}_steps.npz")
+    env = make(env_id, config=over)
+    for r, seed in enumerate(g["reset_seed"]):
+        obs, info = env.reset(seed=int(seed))
+        np.testing.assert_allclose(obs, g["reset_obs"][r], rtol=0, atol=2e-6)
+        T.compare_states(env.sim.get_state(), T.batch_state(g, "reset", slice(r, r + 1)), 1e-12, f"{scene} reset {seed}")
+    for k in range(min(12, len(g["action"]))):
+        env.sim.set_state(T.batch_state(g, "before", slice(k, k + 1)))
+        obs, reward, term, trunc, info = env.step(int(g["action"][k]))
+        np.testing.assert_allclose(obs, g["obs"][k], rtol=0, atol=2e-6)
+        assert abs(reward - g["reward"][k]) <= 1e-6 and term == bool(g["terminated"][k])
+    env.close()
+    if scene == "uturn":
+        with pytest.raises(NotImplementedError):  # the default TimeToCollision observation is outside the hot path
+            make(env_id)
+
+
+@pytest.mark.parametrize("scene", ["roundabout", "u-turn"])
+def test_scripted_vector_env_vs_oracle(scene):
+    """1024 envs from the host-generated pool, free-running with autoreset from the pool: device == oracle."""
+    torch = _torch()
+    from oracle import oracle as O
+    from topotrafficrl_b200 import TTRLVectorEnv
+    E = 1024
+    env = TTRLVectorEnv(E, scene, config=T.UTURN_KIN if scene == "u-turn" else None, seed=11, pool_factor=2)
+    obs, _ = env.reset()
+    orc = O.Oracle(env.cfg, env.table, threads=8)
+    st = env.get_state()
+    rng = np.random.default_rng(2)
+    crashed = 0
+    for step in range(14):  # longer than one episode (duration 11 / 10): exercises the pool autoreset on both sides
+        act = rng.integers(0, 5, size=E).astype(np.int32)
+        before = env.get_state()
+        obs, reward, term, trunc, _ = env.step(torch.as_tensor(act, device="cuda"))
+        torch.cuda.synchronize()
+        o_obs, o_rew, o_term, o_trunc, _ = orc.step(before, act, None)
+        done = o_term.astype(bool) | o_trunc.astype(bool)
+        keep = ~done  # finished envs carry the first observation of their next episode on the device
+        np.testing.assert_allclose(obs.cpu().numpy().reshape(E, -1)[keep], o_obs[keep], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(reward.cpu().numpy(), o_rew, rtol=0, atol=1e-6)
+        assert (term.cpu().numpy() == o_term.astype(bool)).all() and (trunc.cpu().numpy() == o_trunc.astype(bool)).all()
+        crashed += int(o_term.sum())
+        after = env.get_state()
+        sel = np.nonzero(keep)[0]
+        T.compare_states(after.slice_envs(0, E) if len(sel) == E else _take(after, sel), _take(before, sel), 1e-6, f"{scene} step {step}")
+        if done.any():
+            d = np.nonzero(done)[0]
+            assert (after.env_i[abi.EI_EPISODE, d] == before.env_i[abi.EI_EPISODE, d] + 1).all()
+            assert (after.env_d[abi.ED_TIME, d] == 0).all()
+    s = env.stats()
+    assert s["episodes"] >= E and s["env_steps"] == 14 * E
+    assert crashed > 0
+    env.close()
+
+
+def _take(st, sel):
+    from topotrafficrl_b200.state import SimState
+    return SimState(st.veh_d[:, sel].copy(), st.veh_i[:, sel].copy(), st.env_i[:, sel].copy(), st.env_d[:, sel].copy())

@@ -43,7 +43,8 @@ def test_product_never_imports_oracle():
 
 
 def test_route_packing_roundtrip():
-    for route in (None, [], [(3, 0)], [(0, 0), (2, None), (19, None)], [(1, 3), (2, 2), (3, 1), (4, None)]):
+    for route in (None, [], [(3, 0)], [(0, 0), (2, None), (19, None)], [(1, 3), (2, 2), (3, 1), (4, None)],
+                  [(k, None if k % 3 else k % 4) for k in range(9)], [(23 - k, None) for k in range(12)]):
         assert unpack_route(*pack_route(route)) == route
 
 
@@ -58,7 +59,7 @@ def test_intersection_table_matches_reference_layout():
     assert [table.lanes[5 + i].priority for i in range(5)] == [3, 3, 2, 3, 3]
     assert [bool(table.lanes[i].is_exit) for i in range(5)] == [False, False, False, False, True]
     assert list(spawn_lane) == [0, 5, 10, 15]
-    assert rlen[0, 1] == 2 and rlen[0, 0] == 0
+    assert rlen[0, 1] == 2 and rlen[0, 0] == 5  # own arm (multi-agent egos): around the block, 1 + 5 route entries
     assert net.plan_route(("o0", "ir0", 0), "o1") == [("o0", "ir0", 0), ("ir0", "il1", None), ("il1", "o1", None)]
     assert cfg.regulated == 1 and cfg.distance_wanted == 7.0 and cfg.comfort_acc_max == 6.0 and cfg.comfort_acc_min == -3.0
 

@@ -3,7 +3,9 @@
 Public surface (mirrors the reference's ``ttrl_env`` / ``ttrl_agent`` names for the hot path):
 
 * :class:`TTRLVectorEnv` -- E envs in lockstep on one GPU (``vector_env.py``)
-* :class:`IntersectionEnv` -- single-env gymnasium-shaped front end (``envs.py``), id ``intersection-v0``
+* :class:`IntersectionEnv`, :class:`MultiAgentIntersectionEnv`, :class:`RoundaboutEnv`, :class:`UTurnEnv` -- single-env
+  gymnasium-shaped front ends (``envs.py``), ids ``intersection-v0``, ``intersection-multi-agent-v0/-v1``, ``roundabout-v0``,
+  ``u-turn-v0``
 * :class:`QNetRollout` -- batched DQN ``act`` (``agent.py``)
 * :class:`Sim` -- the C ABI as an object (``sim.py``)
 
@@ -19,7 +21,7 @@ def __getattr__(name):
     if name == "TTRLVectorEnv":
         from .vector_env import TTRLVectorEnv
         return TTRLVectorEnv
-    if name in ("IntersectionEnv", "AbstractEnv"):
+    if name in ("IntersectionEnv", "AbstractEnv", "MultiAgentIntersectionEnv", "RoundaboutEnv", "UTurnEnv", "MultiAgentWrapper"):
         from . import envs
         return getattr(envs, name)
     if name == "QNetRollout":

@@ -15,6 +15,7 @@ try:  # pragma: no cover - depends on the environment
     register = gym.register
     make = gym.make
     np_random = seeding.np_random
+    Wrapper = gym.Wrapper
 except ImportError:
     HAVE_GYMNASIUM = False
 
@@ -66,9 +67,30 @@ except ImportError:
         def __repr__(self):
             return f"Discrete({self.n})"
 
+    class Tuple(_Space):
+        def __init__(self, spaces_):
+            super().__init__(None, None)
+            self.spaces = tuple(spaces_)
+
+        def sample(self):
+            return tuple(s.sample() for s in self.spaces)
+
+        def contains(self, x):
+            return len(x) == len(self.spaces) and all(s.contains(v) for s, v in zip(self.spaces, x))
+
+        def __len__(self):
+            return len(self.spaces)
+
+        def __getitem__(self, k):
+            return self.spaces[k]
+
+        def __repr__(self):
+            return "Tuple(" + ", ".join(repr(s) for s in self.spaces) + ")"
+
     class _Spaces:
         Box = Box
         Discrete = Discrete
+        Tuple = Tuple
         Space = _Space
 
     spaces = _Spaces()
@@ -100,6 +122,28 @@ except ImportError:
         def close(self):
             pass
 
+    class Wrapper(Env):
+        def __init__(self, env):
+            self.env = env
+
+        def __getattr__(self, name):
+            if name.startswith("_"):
+                raise AttributeError(name)
+            return getattr(self.env, name)
+
+        @property
+        def unwrapped(self):
+            return self.env.unwrapped
+
+        def reset(self, *, seed=None, options=None):
+            return self.env.reset(seed=seed, options=options)
+
+        def step(self, action):
+            return self.env.step(action)
+
+        def close(self):
+            return self.env.close()
+
     _registry = {}
 
     def register(id, entry_point=None, **kwargs):
@@ -112,4 +156,7 @@ except ImportError:
         if isinstance(entry, str):
             mod, cls = entry.split(":")
             entry = getattr(importlib.import_module(mod), cls)
-        return entry(**dict(extra.get("kwargs", {}), **kwargs))
+        env = entry(**dict(extra.get("kwargs", {}), **kwargs))
+        for wrapper in extra.get("additional_wrappers", ()):  # classes here; WrapperSpec objects under gymnasium
+            env = wrapper(env)
+        return env

@@ -42,7 +42,7 @@ def lib():
     L.ttrl_abi_sizeof.argtypes = [i32]
     L.ttrl_sim_create.argtypes = [C.POINTER(abi.Config), vp, vp, vp, vp, i32, i32, i32, C.POINTER(vp)]
     L.ttrl_sim_destroy.argtypes = [vp]
-    for name in ("ttrl_sim_num_envs", "ttrl_sim_vcap", "ttrl_sim_obs_size"):
+    for name in ("ttrl_sim_num_envs", "ttrl_sim_vcap", "ttrl_sim_obs_size", "ttrl_sim_num_agents"):
         getattr(L, name).argtypes = [vp]
     L.ttrl_sim_launch_count.argtypes = [vp]
     L.ttrl_sim_launch_count.restype = i64
@@ -62,6 +62,9 @@ def lib():
     L.ttrl_sim_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.ttrl_sim_host_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
     L.ttrl_sim_step_pinned.argtypes = [vp, i32]
+    L.ttrl_sim_host_agent_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.ttrl_sim_agent_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.ttrl_sim_set_agent_outputs.argtypes = [vp, vp, vp]
     L.ttrl_sim_observe.argtypes = [vp, vp, vp]
     L.ttrl_sim_spawn.argtypes = [vp, vp, dbl, dbl, dbl, dbl, i32, vp]
     L.ttrl_sim_read_stats.argtypes = [vp, C.POINTER(abi.EpisodeStats), i32]

@@ -12,7 +12,9 @@ MAX_ROADS = 64
 MAX_NODES = 64
 MAX_TARGET_SPEEDS = 8
 MAX_FEATURES = 8
-ROUTE_CAP = 4
+ROUTE_CAP = 12
+ROUTE_WORDS = 3
+MAX_CONTROLLED = 4
 
 LANE_STRAIGHT, LANE_CIRCULAR, LANE_SINE = 0, 1, 2
 
@@ -21,14 +23,18 @@ FEATURES = {"presence": 0, "x": 1, "y": 2, "vx": 3, "vy": 4, "cos_h": 5, "sin_h"
 OBS_KINEMATICS, OBS_GRID = 0, 1
 ORDER_SORTED, ORDER_SHUFFLED = 0, 1
 ACT_ALL, ACT_LONGI, ACT_LAT = 0, 1, 2
-REWARD_INTERSECTION, REWARD_HIGHWAY = 0, 1
+REWARD_INTERSECTION, REWARD_HIGHWAY, REWARD_ROUNDABOUT = 0, 1, 2
 
 # vehicle SoA fields
 D_X, D_Y, D_HEADING, D_SPEED, D_STEERING, D_ACCEL, D_TARGET_SPEED, D_TIMER, D_DELTA, D_IMPACT_X, D_IMPACT_Y = range(11)
 ND = 11
-I_LANE, I_TARGET_LANE, I_FLAGS, I_SPEED_INDEX, I_ROUTE_LEN, I_ROUTE_ROAD, I_ROUTE_LANE, I_YIELD_TIMER = range(8)
-NI = 8
+(I_LANE, I_TARGET_LANE, I_FLAGS, I_SPEED_INDEX, I_ROUTE_LEN, I_ROUTE_ROAD, I_ROUTE_LANE, I_YIELD_TIMER,
+ I_ROUTE_ROAD1, I_ROUTE_ROAD2, I_ROUTE_LANE1, I_ROUTE_LANE2) = range(12)
+NI = 12
+I_ROUTE_ROAD_WORDS = (I_ROUTE_ROAD, I_ROUTE_ROAD1, I_ROUTE_ROAD2)  # route entry k: byte k % 4 of word k // 4
+I_ROUTE_LANE_WORDS = (I_ROUTE_LANE, I_ROUTE_LANE1, I_ROUTE_LANE2)
 FL_MDP, FL_CRASHED, FL_HAS_IMPACT, FL_YIELDING, FL_CONTROLLED = 1, 2, 4, 8, 16
+FL_AGENT_SHIFT, FL_AGENT_MASK = 8, 0x700  # index of the vehicle in env.controlled_vehicles
 EI_NVEH, EI_STEPS, EI_ROAD_STEPS, EI_EGO, EI_EPISODE, EI_DONE = range(6)
 NEI = 6
 ED_TIME, ED_RETURN = range(2)
@@ -75,8 +81,9 @@ class Config(C.Structure):
         ("reward_type", C.c_int32), ("normalize_reward", C.c_int32), ("offroad_terminal", C.c_int32), ("pad4", C.c_int32),
         ("collision_reward", C.c_double), ("high_speed_reward", C.c_double), ("arrived_reward", C.c_double),
         ("lane_reward", C.c_double), ("reward_speed_lo", C.c_double), ("reward_speed_hi", C.c_double),
-        ("spawn_enabled", C.c_int32), ("pad5", C.c_int32),
+        ("spawn_enabled", C.c_int32), ("controlled_vehicles", C.c_int32),
         ("spawn_probability", C.c_double),
+        ("lane_change_reward", C.c_double), ("speed_index_den", C.c_double),
     ]
 
 

@@ -87,7 +87,7 @@ struct alignas(16) EnvState {
     double tsteer[V];    // tan(steering command) of this sub-step (by-product of steering_control, used by integrate)
     double mq_a[9 * MB];  // MOBIL IDM evaluations of the batch
     int32_t lane[V], tlane[V], flags[V], sidx[V], rlen[V], ytimer[V];
-    uint32_t rroad[V], rlanew[V];
+    uint32_t rroad[TTRL_ROUTE_WORDS][V], rlanew[TTRL_ROUTE_WORDS][V];  // route entry k: byte k % 4 of word k / 4 (road index / lane id)
     int32_t tl_old[V], mark[V];
     int32_t best[V];     // collision: largest will-intersect partner index
     int32_t chg[V];      // vehicles in an ongoing lane change (IDM w.r.t. target lane too)
@@ -98,6 +98,7 @@ struct alignas(16) EnvState {
     uint32_t bmask[(V + 31) / 32];  // vehicles in an ongoing lane change on the same road (phase B), list order = bit order
     int16_t mq_f[3 * MB], mq_r[3 * MB];  // MOBIL neighbour queries: own lane, left candidate, right candidate
     int32_t n, steps, road_steps, ego, episode, done, flag0, flag1;
+    int32_t egos[TTRL_MAX_CONTROLLED];  // slots of env.controlled_vehicles (egos[0] == ego)
     int32_t n_chg, n_mob, n_pair, n_w, overflow, pad0;
     double time, ret;
 };
@@ -286,6 +287,32 @@ TT_HD void rebuild_tables(C& c, Exec& ex) {
 // ------------------------------------------------------------------------------------------------
 TT_HD int route_road_at(uint32_t w, int k) { return (w >> (8 * k)) & 0xFF; }
 TT_HD int route_lane_at(uint32_t w, int k) { int b = (w >> (8 * k)) & 0xFF; return b == 0xFF ? -1 : b; }
+// a whole route in registers (up to TTRL_ROUTE_CAP entries)
+struct Route { uint32_t r[TTRL_ROUTE_WORDS], l[TTRL_ROUTE_WORDS]; };
+TT_HD int route_road_at(const Route& q, int k) { return route_road_at(k < 4 ? q.r[0] : k < 8 ? q.r[1] : q.r[2], k & 3); }
+TT_HD int route_lane_at(const Route& q, int k) { return route_lane_at(k < 4 ? q.l[0] : k < 8 ? q.l[1] : q.l[2], k & 3); }
+template <class S> TT_HD Route route_of(const S* st, int i) {
+    Route q;
+    for (int w = 0; w < TTRL_ROUTE_WORDS; ++w) { q.r[w] = st->rroad[w][i]; q.l[w] = st->rlanew[w][i]; }
+    return q;
+}
+template <class S> TT_HD void route_store(S* st, int i, const Route& q) {
+    for (int w = 0; w < TTRL_ROUTE_WORDS; ++w) { st->rroad[w][i] = q.r[w]; st->rlanew[w][i] = q.l[w]; }
+}
+TT_HD void route_set(Route& q, int k, int road, int lane /* < 0: None */) {
+    q.r[k >> 2] |= (uint32_t)(road & 0xFF) << (8 * (k & 3));
+    q.l[k >> 2] |= (uint32_t)(lane < 0 ? 0xFF : lane & 0xFF) << (8 * (k & 3));
+}
+// route.pop(0) (road.py:100)
+template <class S> TT_HD void route_pop(S* st, int i) {
+    st->rroad[0][i] = (st->rroad[0][i] >> 8) | (st->rroad[1][i] << 24);
+    st->rroad[1][i] = (st->rroad[1][i] >> 8) | (st->rroad[2][i] << 24);
+    st->rroad[2][i] >>= 8;
+    st->rlanew[0][i] = (st->rlanew[0][i] >> 8) | (st->rlanew[1][i] << 24);
+    st->rlanew[1][i] = (st->rlanew[1][i] >> 8) | (st->rlanew[2][i] << 24);
+    st->rlanew[2][i] >>= 8;
+    st->rlen[i] -= 1;
+}
 
 // RoadNetwork.next_lane_given_next_road road.py:138-157 (next_id < 0 means None)
 template <class C>
@@ -315,14 +342,10 @@ TT_HDN int next_lane(C& c, int i, int cur) {
     const int to = c.sc->roads[road].to_node;
     int next_road = -1, next_id = -1;
     if (st->rlen[i] > 0) {
-        if (route_road_at(st->rroad[i], 0) == road) {
-            st->rroad[i] >>= 8;
-            st->rlanew[i] >>= 8;
-            st->rlen[i] -= 1;
-        }
-        if (st->rlen[i] > 0 && c.sc->roads[route_road_at(st->rroad[i], 0)].from_node == to) {
-            next_road = route_road_at(st->rroad[i], 0);
-            next_id = route_lane_at(st->rlanew[i], 0);
+        if (route_road_at(st->rroad[0][i], 0) == road) route_pop(st, i);
+        if (st->rlen[i] > 0 && c.sc->roads[route_road_at(st->rroad[0][i], 0)].from_node == to) {
+            next_road = route_road_at(st->rroad[0][i], 0);
+            next_id = route_lane_at(st->rlanew[0][i], 0);
         }
     }
     double lon = S_(c, i, cur), qx, qy;
@@ -386,6 +409,13 @@ TT_HD int speed_to_index(const ttrl_config& cfg, double speed) {
 }
 
 enum { A_NONE = 0, A_IDLE, A_LANE_LEFT, A_LANE_RIGHT, A_FASTER, A_SLOWER };
+// number of controlled vehicles (plain scenes: always one)
+template <class C> TT_HD int n_agents(const C& c) {
+    if (C::kPlain) return 1;
+    const int k = c.sc->cfg.controlled_vehicles;
+    return k < 1 ? 1 : (k > TTRL_MAX_CONTROLLED ? TTRL_MAX_CONTROLLED : k);
+}
+TT_HD int agent_of(int flags) { return (flags & TTRL_FL_AGENT_MASK) >> TTRL_FL_AGENT_SHIFT; }
 TT_HD int decode_action(const ttrl_config& cfg, int a) {  // action.py:204-211
     if (a < 0) return A_NONE;
     if (cfg.action_mode == TTRL_ACT_ALL) return a == 0 ? A_LANE_LEFT : a == 1 ? A_IDLE : a == 2 ? A_LANE_RIGHT : a == 3 ? A_FASTER : A_SLOWER;
@@ -497,13 +527,18 @@ TT_HDN double idm_acceleration(C& c, double self_delta, int ego, int front) {
 //       target lane for the vehicles changing lane)
 // ------------------------------------------------------------------------------------------------
 template <class C, class Exec>
-TT_HD void act_phase_a(C& c, Exec& ex, int i, int first_action) {
+TT_HD void act_phase_a(C& c, Exec& ex, int i, const int32_t* actions) {
     auto* st = c.st;
     st->mark[i] = 0;
     if (st->flags[i] & TTRL_FL_MDP) {
-        // DiscreteMetaAction.act (action.py:259-260) runs BEFORE Road.act: its target-lane change is the "old"
-        // value every other vehicle sees; then Road.act -> MDPVehicle.act(None)
-        if (first_action != A_NONE && i == st->ego) mdp_act_lanes(c, i, first_action);
+        // DiscreteMetaAction.act (action.py:259-260; MultiAgentAction.act :320-323 for K agents) runs BEFORE Road.act:
+        // its target-lane change is the "old" value every other vehicle sees; then Road.act -> MDPVehicle.act(None)
+        int first_action = A_NONE;
+        if (actions) {  // non-null on the first sub-step of an env-step only
+            if (n_agents(c) == 1) { if (i == st->ego) first_action = decode_action(c.sc->cfg, actions[0]); }
+            else if (st->flags[i] & TTRL_FL_CONTROLLED) first_action = decode_action(c.sc->cfg, actions[agent_of(st->flags[i])]);
+        }
+        if (first_action != A_NONE) mdp_act_lanes(c, i, first_action);
         st->tl_old[i] = st->tlane[i];
         mdp_act_lanes(c, i, A_NONE);
         return;
@@ -574,9 +609,9 @@ TT_HD void mobil_batch(C& c, Exec& ex, int base, int nb) {
             const int cand = st->lane[i] + (k == 0 ? -1 : 1);
             const double new_following_a = a[3 + 3 * k], new_following_pred_a = a[4 + 3 * k], self_pred_a = a[5 + 3 * k];
             if (new_following_pred_a < -cfg.lane_change_max_braking_imposed) continue;
-            if (st->rlen[i] > 0 && route_lane_at(st->rlanew[i], 0) >= 0) {
+            if (st->rlen[i] > 0 && route_lane_at(st->rlanew[0][i], 0) >= 0) {
                 const int cur_t = c.lanes[st->tlane[i]].lane_id;
-                const int want = route_lane_at(st->rlanew[i], 0) - cur_t, dir = c.lanes[cand].lane_id - cur_t;
+                const int want = route_lane_at(st->rlanew[0][i], 0) - cur_t, dir = c.lanes[cand].lane_id - cur_t;
                 const int sw = (want > 0) - (want < 0), sd = (dir > 0) - (dir < 0);
                 if (sd != sw) continue;
                 if (self_pred_a < -cfg.lane_change_max_braking_imposed) continue;
@@ -873,13 +908,13 @@ TT_HD void collide_all(C& c, Exec& ex) {
 // ------------------------------------------------------------------------------------------------
 // RoadNetwork.position_heading_along_route road.py:323-362 with lateral 0
 template <class C>
-TT_HD void position_heading_along_route(C& c, uint32_t rroad, uint32_t rlanew, int rlen, double lon, int cur_lane,
+TT_HD void position_heading_along_route(C& c, const Route& rt, int rlen, double lon, int cur_lane,
                                         double& px, double& py, double& ph) {
     const int cur_id = c.lanes[cur_lane].lane_id;
     int k = 0;
     auto head = [&](int kk) {
-        const int lid = route_lane_at(rlanew, kk);
-        return c.sc->roads[route_road_at(rroad, kk)].first_lane + (lid < 0 ? cur_id : lid);
+        const int lid = route_lane_at(rt, kk);
+        return c.sc->roads[route_road_at(rt, kk)].first_lane + (lid < 0 ? cur_id : lid);
     };
     int li = head(k);
     while (rlen - k > 1 && lon > c.lanes[li].length) {
@@ -911,16 +946,16 @@ TT_HDN void regulate_predict(C& c, int i, int k) {
     auto* st = c.st;
     const int ln = st->lane[i];
     const double s0 = S_(c, i, ln);
-    uint32_t rr = st->rroad[i], rl = st->rlanew[i];
+    Route rt = route_of(st, i);
     int rlen = st->rlen[i];
     if (rlen <= 0) {  // `self.route or [self.lane_index]`
         rlen = 1;
-        rr = (uint32_t)c.lanes[ln].road;
-        rl = (uint32_t)c.lanes[ln].lane_id;
+        rt.r[0] = (uint32_t)c.lanes[ln].road;
+        rt.l[0] = (uint32_t)c.lanes[ln].lane_id;
     }
     const double t = 0.25 + k * 0.25;
     double px, py, ph, sn, cn;
-    position_heading_along_route(c, rr, rl, rlen, s0 + st->v[i] * t, ln, px, py, ph);
+    position_heading_along_route(c, rt, rlen, s0 + st->v[i] * t, ln, px, py, ph);
     sincos(ph, &sn, &cn);
     c.pred[0 * C::V + i] = px;
     c.pred[1 * C::V + i] = py;
@@ -997,18 +1032,19 @@ TT_HD void regulate_apply(C& c, int i) {
 // one simulation sub-step (AbstractEnv._simulate body abstract.py:257-273)
 // ------------------------------------------------------------------------------------------------
 template <class C, class Exec>
-TT_HD void env_substep(C& c, Exec& ex, int raw_action, bool aligned = false) {  // inlined on purpose: a call boundary here costs ~30 % (ctx spills)
+TT_HD void env_substep(C& c, Exec& ex, const int32_t* actions, bool aligned = false) {  // inlined on purpose: a call boundary here costs ~30 % (ctx spills)
+    // `actions`: this env's raw action ids (one per controlled vehicle) or null (action=None)
     // `aligned`: the CTA-wide phase alignment points are active (k_step's main loop only; kAlignPerSubstep of them)
     auto* st = c.st;
     const SceneDev* sc = c.sc;
     using ES = EnvState<C::V>;
     const int n = st->n;
     // ego meta-action on the first sub-step of an env-step: DiscreteMetaAction.act action.py:259-260
-    const int first_action = (raw_action >= 0 && st->steps % sc->F == 0) ? decode_action(sc->cfg, raw_action) : A_NONE;
+    const int32_t* first_actions = (actions && st->steps % sc->F == 0) ? actions : nullptr;
     if (aligned && (kAlignMask & 1)) ex.align();
     ex.parn(n, [&](int t) {
         if (t == 0) { st->n_chg = 0; st->n_pair = 0; st->n_w = 0; st->overflow = 0; }
-        act_phase_a(c, ex, t, first_action);
+        act_phase_a(c, ex, t, first_actions);
     });
     {   // MOBIL over the vehicles whose timer fired (uniform: counters live in shared memory)
         const int nm = st->n_mob;
@@ -1094,11 +1130,11 @@ TT_HD bool is_relative_feature(int f) { return f == TTRL_F_X || f == TTRL_F_Y ||
 // Stable sort by rank counting: rank(j) = #{k : key_k < key_j or (key_k == key_j and k < j)}.
 // `inv_perm` (or null): row permutation for order == "shuffled" (np_random.shuffle(obs[1:]), :272-273).
 template <class C, class Exec>
-TT_HD void observe_kinematics(C& c, Exec& ex, float* out, const int32_t* inv_perm) {
+TT_HD void observe_kinematics(C& c, Exec& ex, float* out, const int32_t* inv_perm, int ego) {
     auto* st = c.st;
     const ttrl_config& cfg = c.sc->cfg;
     const int Vo = cfg.obs_vehicles, Fe = cfg.n_features;
-    const int ego = st->ego, le = st->lane[ego];
+    const int le = st->lane[ego];
     ex.parn(Vo * Fe, [&](int k) { c.obs_s[k] = 0.0f; });
     ex.par([&](int t) {
         int cand = 0;
@@ -1145,10 +1181,10 @@ TT_HD void observe_kinematics(C& c, Exec& ex, float* out, const int32_t* inv_per
 // OccupancyGridObservation.observe observation.py:353-412.  The reference writes vehicles in REVERSE list order
 // per layer, so the EARLIEST vehicle of a cell wins: per-cell winner = min slot index (atomicMin in smem).
 template <class C>
-TT_HD bool grid_cell_of(C& c, double px, double py, int& ci, int& cj) {  // pos_to_index :414-434 (already relative)
+TT_HD bool grid_cell_of(C& c, int ego, double px, double py, int& ci, int& cj) {  // pos_to_index :414-434 (already relative)
     const ttrl_config& cfg = c.sc->cfg;
     if (cfg.align_to_vehicle_axes) {
-        const double ca = c.st->cs[c.st->ego].x, sa = c.st->cs[c.st->ego].y;
+        const double ca = c.st->cs[ego].x, sa = c.st->cs[ego].y;
         const double qx = ca * px + sa * py, qy = -sa * px + ca * py;
         px = qx;
         py = qy;
@@ -1161,10 +1197,10 @@ TT_HD bool grid_cell_of(C& c, double px, double py, int& ci, int& cj) {  // pos_
     return true;
 }
 template <class C, class Exec>
-TT_HD void observe_grid(C& c, Exec& ex, float* out) {
+TT_HD void observe_grid(C& c, Exec& ex, float* out, int ego) {
     auto* st = c.st;
     const ttrl_config& cfg = c.sc->cfg;
-    const int W = cfg.grid_w, H = cfg.grid_h, Fe = cfg.n_features, ego = st->ego;
+    const int W = cfg.grid_w, H = cfg.grid_h, Fe = cfg.n_features;
     ex.parn(W * H, [&](int k) { c.cell[k] = 0x7fffffff; });
     ex.parn(Fe * W * H, [&](int k) { out[k] = 0.0f; });
     ex.par([&](int t) {
@@ -1174,7 +1210,7 @@ TT_HD void observe_grid(C& c, Exec& ex, float* out) {
             if (cfg.grid_has_xrange) { x = lmap(x, cfg.grid_xrange[0], cfg.grid_xrange[1], -1.0, 1.0); x = lmap(x, -1.0, 1.0, cfg.grid_xrange[0], cfg.grid_xrange[1]); }
             if (cfg.grid_has_yrange) { y = lmap(y, cfg.grid_yrange[0], cfg.grid_yrange[1], -1.0, 1.0); y = lmap(y, -1.0, 1.0, cfg.grid_yrange[0], cfg.grid_yrange[1]); }
             int ci, cj;
-            if (grid_cell_of(c, x, y, ci, cj)) {
+            if (grid_cell_of(c, ego, x, y, ci, cj)) {
                 st->mark[t] = ci * H + cj;
                 ex.atomic_min(&c.cell[ci * H + cj], t);
             }
@@ -1209,14 +1245,24 @@ TT_HD void observe_grid(C& c, Exec& ex, float* out) {
             double px, py;
             lane_position(l, wp, 0.0, px, py);
             int ci, cj;
-            if (grid_cell_of(c, px - st->pos[ego].x, py - st->pos[ego].y, ci, cj)) out[layer * W * H + ci * H + cj] = 1.0f;
+            if (grid_cell_of(c, ego, px - st->pos[ego].x, py - st->pos[ego].y, ci, cj)) out[layer * W * H + ci * H + cj] = 1.0f;
         });
     }
 }
+TT_HD int obs_single_size(const ttrl_config& cfg) {  // floats of ONE controlled vehicle's observation
+    return cfg.obs_type == TTRL_OBS_GRID ? cfg.n_features * cfg.grid_w * cfg.grid_h : cfg.obs_vehicles * cfg.n_features;
+}
+// observation_type.observe(): one observation per controlled vehicle (MultiAgentObservation observation.py:587-603),
+// K consecutive blocks in `out`; `inv_perm` (or null) holds K consecutive row permutations.
 template <class C, class Exec>
 TT_HD void observe(C& c, Exec& ex, float* out, const int32_t* inv_perm) {
-    if (c.sc->cfg.obs_type == TTRL_OBS_GRID) observe_grid(c, ex, out);
-    else observe_kinematics(c, ex, out, inv_perm);
+    const ttrl_config& cfg = c.sc->cfg;
+    const int K = n_agents(c);
+    for (int k = 0; k < K; ++k) {
+        const int ego = K == 1 ? c.st->ego : c.st->egos[k];
+        if (cfg.obs_type == TTRL_OBS_GRID) observe_grid(c, ex, out + (size_t)k * obs_single_size(cfg), ego);
+        else observe_kinematics(c, ex, out + (size_t)k * obs_single_size(cfg), inv_perm ? inv_perm + k * (cfg.obs_vehicles - 1) : nullptr, ego);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1233,10 +1279,20 @@ TT_HD bool on_road(C& c, int i) {  // objects.py:199-202
     return lane_on_lane(c.lanes[ln], S_(c, i, ln), R_(c, i, ln), 0.0);
 }
 template <class C>
-TT_HD double agent_reward(C& c, int i) {  // intersection_env.py:78-104 / u_turn_env.py:39-71
+TT_HD double agent_reward(C& c, int i, int raw_action) {  // intersection_env.py:78-104 / u_turn_env.py:39-71 / roundabout_env.py:43-64
     const ttrl_config& cfg = c.sc->cfg;
     auto* st = c.st;
     const double crashed = (st->flags[i] & TTRL_FL_CRASHED) ? 1.0 : 0.0;
+    if (!C::kPlain && cfg.reward_type == TTRL_REWARD_ROUNDABOUT) {
+        // MDPVehicle.get_speed_index(vehicle) / (DEFAULT_TARGET_SPEEDS.size - 1); `action in [0, 2]`
+        const double hs = (double)st->sidx[i] / cfg.speed_index_den;
+        const double lc = (raw_action == 0 || raw_action == 2) ? 1.0 : 0.0;
+        const double onr = on_road(c, i) ? 1.0 : 0.0;
+        double reward = 0 + cfg.collision_reward * crashed + cfg.high_speed_reward * hs + cfg.lane_change_reward * lc + 0 * onr;
+        if (cfg.normalize_reward) reward = lmap(reward, cfg.collision_reward, cfg.high_speed_reward, 0.0, 1.0);
+        reward *= onr;
+        return reward;
+    }
     const double hs = clipd(lmap(st->v[i], cfg.reward_speed_lo, cfg.reward_speed_hi, 0.0, 1.0), 0.0, 1.0);
     const double onr = on_road(c, i) ? 1.0 : 0.0;
     if (!C::kPlain && cfg.reward_type == TTRL_REWARD_INTERSECTION) {
@@ -1256,11 +1312,21 @@ TT_HD double agent_reward(C& c, int i) {  // intersection_env.py:78-104 / u_turn
     return reward;
 }
 template <class C>
-TT_HD bool is_terminated(C& c) {  // intersection_env.py:106-111 / u_turn_env.py:73-74
+TT_HD bool is_terminated(C& c) {  // intersection_env.py:106-111 / u_turn_env.py:73-74 / roundabout_env.py:66-67
     const int e = c.st->ego;
     const bool crashed = (c.st->flags[e] & TTRL_FL_CRASHED) != 0;
-    const bool off = c.sc->cfg.offroad_terminal && !on_road(c, e);
-    if (!C::kPlain && c.sc->cfg.reward_type == TTRL_REWARD_INTERSECTION) return crashed || has_arrived(c, e) || off;
+    if (!C::kPlain && c.sc->cfg.reward_type == TTRL_REWARD_ROUNDABOUT) return crashed;
+    const bool off = c.sc->cfg.offroad_terminal && !on_road(c, e);  // self.vehicle = controlled_vehicles[0]
+    if (!C::kPlain && c.sc->cfg.reward_type == TTRL_REWARD_INTERSECTION) {
+        const int K = n_agents(c);
+        if (K == 1) return crashed || has_arrived(c, e) || off;
+        bool any_crashed = false, all_arrived = true;  // any(crashed) or all(has_arrived) over the controlled vehicles
+        for (int k = 0; k < K; ++k) {
+            any_crashed = any_crashed || (c.st->flags[c.st->egos[k]] & TTRL_FL_CRASHED) != 0;
+            all_arrived = all_arrived && has_arrived(c, c.st->egos[k]);
+        }
+        return any_crashed || all_arrived || off;
+    }
     return crashed || off;
 }
 
@@ -1270,7 +1336,7 @@ TT_HD bool is_terminated(C& c) {  // intersection_env.py:106-111 / u_turn_env.py
 struct SlotRegs {
     double d[13];
     int32_t i[6];
-    uint32_t u[2];
+    Route rt;
 };
 template <class C>
 TT_HD void slot_read(C& c, int t, SlotRegs& r) {
@@ -1279,7 +1345,7 @@ TT_HD void slot_read(C& c, int t, SlotRegs& r) {
     r.d[6] = st->steer[t]; r.d[7] = st->acc[t]; r.d[8] = st->tspeed[t]; r.d[9] = st->timer[t]; r.d[10] = st->delta[t];
     r.d[11] = st->imp[t].x; r.d[12] = st->imp[t].y;
     r.i[0] = st->lane[t]; r.i[1] = st->tlane[t]; r.i[2] = st->flags[t]; r.i[3] = st->sidx[t]; r.i[4] = st->rlen[t]; r.i[5] = st->ytimer[t];
-    r.u[0] = st->rroad[t]; r.u[1] = st->rlanew[t];
+    r.rt = route_of(st, t);
 }
 template <class C>
 TT_HD void slot_write(C& c, int t, const SlotRegs& r) {
@@ -1288,7 +1354,18 @@ TT_HD void slot_write(C& c, int t, const SlotRegs& r) {
     st->steer[t] = r.d[6]; st->acc[t] = r.d[7]; st->tspeed[t] = r.d[8]; st->timer[t] = r.d[9]; st->delta[t] = r.d[10];
     st->imp[t] = d2{r.d[11], r.d[12]};
     st->lane[t] = r.i[0]; st->tlane[t] = r.i[1]; st->flags[t] = r.i[2]; st->sidx[t] = r.i[3]; st->rlen[t] = r.i[4]; st->ytimer[t] = r.i[5];
-    st->rroad[t] = r.u[0]; st->rlanew[t] = r.u[1];
+    route_store(st, t, r.rt);
+}
+
+// slots of the controlled vehicles from their agent bits (after a compaction / reset of a multi-agent env)
+template <class C, class Exec>
+TT_HD void find_agents(C& c, Exec& ex) {
+    auto* st = c.st;
+    ex.parn(st->n, [&](int t) {
+        if (st->flags[t] & TTRL_FL_CONTROLLED) st->egos[agent_of(st->flags[t])] = t;
+    });
+    if (ex.first()) st->ego = st->egos[0];
+    ex.sync();
 }
 
 // Stable compaction of the vehicle list (order preserved like the list comprehension at :357-362).
@@ -1325,8 +1402,22 @@ TT_HD void clear_vehicles(C& c, Exec& ex) {
             }
             if (t == 0) { int tot = 0; for (int k = 0; k < st->n; ++k) tot += st->mark[k]; st->flag1 = tot; }
         });
-    if (ex.first()) { st->ego = st->flag0; st->n = st->flag1; }
+    if (ex.first()) { st->ego = st->flag0; st->egos[0] = st->flag0; st->n = st->flag1; }
     ex.sync();
+    if (n_agents(c) > 1) find_agents(c, ex);
+}
+
+// ControlledVehicle.plan_route_to (controller.py:71-87): [lane_index] + the roads of the host's BFS path (road.py:159-188)
+// from the entry corner to exit node o<exit_>; written to slot s, returns the route length.
+template <class C>
+TT_HD int planned_route(C& c, int ln, int entry, int exit_, int s) {
+    const SceneDev* sc = c.sc;
+    const int nr = sc->spawn_route_len[entry * 4 + exit_];
+    Route q{};
+    route_set(q, 0, c.lanes[ln].road, c.lanes[ln].lane_id);
+    for (int k = 0; k < nr && k + 1 < TTRL_ROUTE_CAP; ++k) route_set(q, k + 1, sc->spawn_route_road[(entry * 4 + exit_) * TTRL_ROUTE_CAP + k], -1);
+    route_store(c.st, s, q);
+    return 1 + nr;
 }
 
 struct SpawnParams {
@@ -1366,13 +1457,7 @@ TT_HD void spawn_vehicle(C& c, Exec& ex, const ttrl_spawn_draw& d, const SpawnPa
         st->timer[s] = py_mod1((px + py) * kPi);     // behavior.py:64
         st->delta[s] = d.delta;                      // behavior.py:66-69
         st->flags[s] = 0; st->sidx[s] = 0; st->ytimer[s] = 0;
-        const int nr = sc->spawn_route_len[entry * 4 + exit_];
-        uint32_t rr = (uint32_t)c.lanes[ln].road, rl = (uint32_t)c.lanes[ln].lane_id;
-        for (int k = 0; k < nr; ++k) {
-            rr |= (uint32_t)(sc->spawn_route_road[(entry * 4 + exit_) * TTRL_ROUTE_CAP + k] & 0xFF) << (8 * (k + 1));
-            rl |= 0xFFu << (8 * (k + 1));
-        }
-        st->rlen[s] = 1 + nr; st->rroad[s] = rr; st->rlanew[s] = rl;
+        st->rlen[s] = planned_route(c, ln, entry, exit_, s);
         st->n = s + 1;
         st->flag0 = 1;
     }
@@ -1401,7 +1486,11 @@ TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
         st->time = g.ed[TTRL_ED_TIME * g.E + e]; st->ret = g.ed[TTRL_ED_RETURN * g.E + e];
         st->n_chg = st->n_mob = st->n_pair = st->n_w = st->overflow = 0;
         for (int w = 0; w < C::W; ++w) st->bmask[w] = 0;
+        st->egos[0] = st->ego;
+        for (int k = 1; k < TTRL_MAX_CONTROLLED; ++k) st->egos[k] = st->ego;
     }
+    ex.sync();
+    const int st_n = g.ei[TTRL_EI_NVEH * g.E + e];
     ex.par([&](int t) {
         if (t < V) {
             const size_t o = (size_t)e * V + t, fs = (size_t)g.E * V;
@@ -1418,14 +1507,18 @@ TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
             st->lane[t] = g.vi[TTRL_I_LANE * fs + o]; st->tlane[t] = g.vi[TTRL_I_TARGET_LANE * fs + o];
             st->flags[t] = g.vi[TTRL_I_FLAGS * fs + o]; st->sidx[t] = g.vi[TTRL_I_SPEED_INDEX * fs + o];
             st->rlen[t] = g.vi[TTRL_I_ROUTE_LEN * fs + o];
-            st->rroad[t] = (uint32_t)g.vi[TTRL_I_ROUTE_ROAD * fs + o]; st->rlanew[t] = (uint32_t)g.vi[TTRL_I_ROUTE_LANE * fs + o];
+            st->rroad[0][t] = (uint32_t)g.vi[TTRL_I_ROUTE_ROAD * fs + o]; st->rlanew[0][t] = (uint32_t)g.vi[TTRL_I_ROUTE_LANE * fs + o];
+            st->rroad[1][t] = (uint32_t)g.vi[TTRL_I_ROUTE_ROAD1 * fs + o]; st->rlanew[1][t] = (uint32_t)g.vi[TTRL_I_ROUTE_LANE1 * fs + o];
+            st->rroad[2][t] = (uint32_t)g.vi[TTRL_I_ROUTE_ROAD2 * fs + o]; st->rlanew[2][t] = (uint32_t)g.vi[TTRL_I_ROUTE_LANE2 * fs + o];
             st->ytimer[t] = g.vi[TTRL_I_YIELD_TIMER * fs + o];
+            if (t < st_n && (st->flags[t] & TTRL_FL_CONTROLLED) && (st->flags[t] & TTRL_FL_AGENT_MASK))
+                st->egos[(st->flags[t] & TTRL_FL_AGENT_MASK) >> TTRL_FL_AGENT_SHIFT] = t;  // agents k >= 1 (distinct slots: no race)
         } else {
             st->pos[t] = d2{0, 0}; st->cs[t] = d2{1, 0}; st->imp[t] = d2{0, 0};
             st->h[t] = st->v[t] = st->steer[t] = st->acc[t] = 0;
             st->tspeed[t] = st->timer[t] = st->delta[t] = 0;
             st->lane[t] = st->tlane[t] = st->flags[t] = st->sidx[t] = st->rlen[t] = st->ytimer[t] = 0;
-            st->rroad[t] = st->rlanew[t] = 0;
+            for (int w = 0; w < TTRL_ROUTE_WORDS; ++w) st->rroad[w][t] = st->rlanew[w][t] = 0;
         }
         st->mark[t] = 0; st->tl_old[t] = 0; st->acc2[t] = 0; st->tsteer[t] = 0; st->best[t] = -1; st->fo[t] = -1;
         // pre-check guard from the loaded speed (integrate refreshes it every sub-step)
@@ -1451,7 +1544,8 @@ TT_HD void store_env(C& c, Exec& ex, const GlobalState& g, int e) {
         const bool live = t < st->n;
         const int rlen = live ? st->rlen[t] : 0;
         // canonical form: dead slots zero, unused route bytes zero (keeps get_state comparable bit for bit)
-        const uint32_t keep = rlen >= 4 ? 0xFFFFFFFFu : (rlen <= 0 ? 0u : ((1u << (8 * rlen)) - 1u));
+        auto keep_of = [](int n) { return n >= 4 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << (8 * n)) - 1u)); };
+        const uint32_t keep = live ? keep_of(rlen) : 0u, keep1 = live ? keep_of(rlen - 4) : 0u, keep2 = live ? keep_of(rlen - 8) : 0u;
         g.vd[TTRL_D_X * fs + o] = live ? st->pos[t].x : 0; g.vd[TTRL_D_Y * fs + o] = live ? st->pos[t].y : 0;
         g.vd[TTRL_D_HEADING * fs + o] = live ? st->h[t] : 0; g.vd[TTRL_D_SPEED * fs + o] = live ? st->v[t] : 0;
         g.vd[TTRL_D_STEERING * fs + o] = live ? st->steer[t] : 0; g.vd[TTRL_D_ACCEL * fs + o] = live ? st->acc[t] : 0;
@@ -1461,8 +1555,12 @@ TT_HD void store_env(C& c, Exec& ex, const GlobalState& g, int e) {
         g.vi[TTRL_I_LANE * fs + o] = live ? st->lane[t] : 0; g.vi[TTRL_I_TARGET_LANE * fs + o] = live ? st->tlane[t] : 0;
         g.vi[TTRL_I_FLAGS * fs + o] = live ? st->flags[t] : 0; g.vi[TTRL_I_SPEED_INDEX * fs + o] = live ? st->sidx[t] : 0;
         g.vi[TTRL_I_ROUTE_LEN * fs + o] = rlen;
-        g.vi[TTRL_I_ROUTE_ROAD * fs + o] = (int32_t)(live ? st->rroad[t] & keep : 0u);
-        g.vi[TTRL_I_ROUTE_LANE * fs + o] = (int32_t)(live ? st->rlanew[t] & keep : 0u);
+        g.vi[TTRL_I_ROUTE_ROAD * fs + o] = (int32_t)(st->rroad[0][t] & keep);
+        g.vi[TTRL_I_ROUTE_LANE * fs + o] = (int32_t)(st->rlanew[0][t] & keep);
+        g.vi[TTRL_I_ROUTE_ROAD1 * fs + o] = (int32_t)(st->rroad[1][t] & keep1);
+        g.vi[TTRL_I_ROUTE_LANE1 * fs + o] = (int32_t)(st->rlanew[1][t] & keep1);
+        g.vi[TTRL_I_ROUTE_ROAD2 * fs + o] = (int32_t)(st->rroad[2][t] & keep2);
+        g.vi[TTRL_I_ROUTE_LANE2 * fs + o] = (int32_t)(st->rlanew[2][t] & keep2);
         g.vi[TTRL_I_YIELD_TIMER * fs + o] = live ? st->ytimer[t] : 0;
     });
 }
@@ -1524,6 +1622,7 @@ TT_HD void reset_scalars(C& c, Exec& ex, int episode) {
     auto* st = c.st;
     if (ex.first()) {
         st->n = 0; st->steps = 0; st->road_steps = 0; st->ego = 0; st->episode = episode; st->done = 0;
+        for (int k = 0; k < TTRL_MAX_CONTROLLED; ++k) st->egos[k] = 0;
         st->time = 0; st->ret = 0;
         st->n_chg = st->n_mob = st->n_pair = st->n_w = st->overflow = 0;
         for (int w = 0; w < C::W; ++w) st->bmask[w] = 0;
@@ -1533,7 +1632,7 @@ TT_HD void reset_scalars(C& c, Exec& ex, int episode) {
         st->h[t] = st->v[t] = st->steer[t] = st->acc[t] = st->tspeed[t] = st->timer[t] = st->delta[t] = 0;
         st->acc2[t] = st->tsteer[t] = 0; st->thr2[t] = 0;
         st->lane[t] = st->tlane[t] = st->flags[t] = st->sidx[t] = st->rlen[t] = st->ytimer[t] = 0;
-        st->rroad[t] = st->rlanew[t] = 0;
+        for (int w = 0; w < TTRL_ROUTE_WORDS; ++w) st->rroad[w][t] = st->rlanew[w][t] = 0;
         st->mark[t] = 0; st->tl_old[t] = 0; st->best[t] = -1; st->fo[t] = -1;
     });
     ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; });
@@ -1608,7 +1707,7 @@ TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int e
         spawn_vehicle(c, ex, d, sp);
     }
     rebuild_tables(c, ex);
-    for (int k = 0; k < rp.warmup_substeps; ++k) env_substep(c, ex, -1, aligned);  // (:267-274) road.act(); road.step(1/sf)
+    for (int k = 0; k < rp.warmup_substeps; ++k) env_substep(c, ex, nullptr, aligned);  // (:267-274) road.act(); road.step(1/sf)
     {   // challenger vehicle (:276-277)
         ttrl_spawn_draw d;
         device_spawn_draw(seed, genv, reset_attempt_counter(episode, rp.n_vehicles - 1), d);
@@ -1616,60 +1715,57 @@ TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int e
         spawn_vehicle(c, ex, d, sp);
     }
     if (ex.first()) {
-        // ego MDPVehicle (:286-307) at ego_longitudinal + std * N(1, 1) on (o<k>, ir<k>, 0), speed = speed_limit
-        double u0, u1, ud, unused;
-        reset_uniforms(seed, genv, episode, 0x100u, u0, u1);
-        reset_uniforms(seed, genv, episode, 0x101u, ud, unused);
-        const double z = sqrt(-2.0 * log(1.0 - u0)) * cos(2 * kPi * u1);
-        const int entry = rp.ego_entry;
-        const ttrl_lane& el = c.lanes[sc->spawn_lane[entry]];
-        double px, py;
-        lane_position(el, rp.ego_longitudinal + rp.ego_longitudinal_std * (1.0 + z), 0.0, px, py);
-        int s = st->n;
-        if (s >= c.vcap) s = c.vcap - 1;  // full: the ego replaces the last vehicle
-        st->pos[s] = d2{px, py};
-        st->h[s] = lane_heading_at(el, rp.ego_longitudinal);
-        st->cs[s] = d2{cos(st->h[s]), sin(st->h[s])};
-        st->v[s] = el.speed_limit;
-        st->steer[s] = 0; st->acc[s] = 0; st->imp[s] = d2{0, 0}; st->timer[s] = 0; st->delta[s] = 4.0;
-        uint64_t m;
-        const int ln = table_row_and_closest(c, s, m);  // RoadObject.__init__ objects.py:45-50
-        st->lane[s] = ln; st->tlane[s] = ln;
-        st->sidx[s] = speed_to_index(cfg, st->v[s]);    // MDPVehicle.__init__ controller.py:283-293
-        st->tspeed[s] = cfg.target_speeds[st->sidx[s]];
-        st->flags[s] = TTRL_FL_MDP | TTRL_FL_CONTROLLED;
-        st->ytimer[s] = 0;
-        int dest = rp.destination;
-        if (dest < 0) { dest = 1 + (int)(ud * 3.0); if (dest > 3) dest = 3; dest = (entry + dest) % 4; }  // "o" + str(integers(1, 4))
-        const int nr = sc->spawn_route_len[entry * 4 + dest];
-        uint32_t rr = (uint32_t)c.lanes[ln].road, rl = (uint32_t)c.lanes[ln].lane_id;
-        for (int k = 0; k < nr; ++k) {
-            rr |= (uint32_t)(sc->spawn_route_road[(entry * 4 + dest) * TTRL_ROUTE_CAP + k] & 0xFF) << (8 * (k + 1));
-            rl |= 0xFFu << (8 * (k + 1));
-        }
-        st->rlen[s] = 1 + nr; st->rroad[s] = rr; st->rlanew[s] = rl;
-        const int n0 = s + 1;
-        // "prevent early collisions" (:313-318): list.remove() while iterating skips the element after each removal
-        int* order = st->chg;
-        int len = n0;
-        for (int k = 0; k < n0; ++k) order[k] = k;
-        for (int i = 0; i < len; ++i) {
-            const int v = order[i];
-            if (v == s) continue;
-            const double dx = st->pos[v].x - px, dy = st->pos[v].y - py;
-            if (sqrt(dx * dx + dy * dy) < 20) {
-                for (int k = i; k + 1 < len; ++k) order[k] = order[k + 1];
-                --len;
+        const int K = n_agents(c);
+        for (int a = 0; a < K; ++a) {
+            // ego MDPVehicle a (:286-307) at ego_longitudinal + std * N(1, 1) on (o<k>, ir<k>, 0), k = a % 4, speed = speed_limit
+            double u0, u1, ud, unused;
+            reset_uniforms(seed, genv, episode, 0x100u + 2u * a, u0, u1);
+            reset_uniforms(seed, genv, episode, 0x101u + 2u * a, ud, unused);
+            const double z = sqrt(-2.0 * log(1.0 - u0)) * cos(2 * kPi * u1);
+            const int entry = (rp.ego_entry + a) % 4;
+            const ttrl_lane& el = c.lanes[sc->spawn_lane[entry]];
+            double px, py;
+            lane_position(el, rp.ego_longitudinal + rp.ego_longitudinal_std * (1.0 + z), 0.0, px, py);
+            int s = st->n;
+            if (s >= c.vcap) s = c.vcap - 1;  // full: the ego replaces the last vehicle
+            st->pos[s] = d2{px, py};
+            st->h[s] = lane_heading_at(el, rp.ego_longitudinal);
+            st->cs[s] = d2{cos(st->h[s]), sin(st->h[s])};
+            st->v[s] = el.speed_limit;
+            st->steer[s] = 0; st->acc[s] = 0; st->imp[s] = d2{0, 0}; st->timer[s] = 0; st->delta[s] = 4.0;
+            uint64_t m;
+            const int ln = table_row_and_closest(c, s, m);  // RoadObject.__init__ objects.py:45-50
+            st->lane[s] = ln; st->tlane[s] = ln;
+            st->sidx[s] = speed_to_index(cfg, st->v[s]);    // MDPVehicle.__init__ controller.py:283-293
+            st->tspeed[s] = cfg.target_speeds[st->sidx[s]];
+            st->flags[s] = TTRL_FL_MDP | TTRL_FL_CONTROLLED | (a << TTRL_FL_AGENT_SHIFT);
+            st->ytimer[s] = 0;
+            int dest = rp.destination;
+            if (dest < 0) { dest = 1 + (int)(ud * 3.0); if (dest > 3) dest = 3; }  // "o" + str(integers(1, 4))
+            st->rlen[s] = planned_route(c, ln, entry, dest, s);
+            const int n0 = s + 1;
+            // "prevent early collisions" (:313-318): list.remove() while iterating skips the element after each removal
+            int* order = st->chg;
+            int len = n0;
+            for (int k = 0; k < n0; ++k) order[k] = k;
+            for (int i = 0; i < len; ++i) {
+                const int v = order[i];
+                if (v == s) continue;
+                const double dx = st->pos[v].x - px, dy = st->pos[v].y - py;
+                if (sqrt(dx * dx + dy * dy) < 20) {
+                    for (int k = i; k + 1 < len; ++k) order[k] = order[k + 1];
+                    --len;
+                }
             }
+            for (int dst = 0; dst < len; ++dst) {
+                const int src = order[dst];
+                if (src != dst) { SlotRegs r; slot_read(c, src, r); slot_write(c, dst, r); }
+            }
+            st->n = len;
         }
-        int ego = 0;
-        for (int dst = 0; dst < len; ++dst) {
-            const int src = order[dst];
-            if (src == s) ego = dst;
-            if (src != dst) { SlotRegs r; slot_read(c, src, r); slot_write(c, dst, r); }
-        }
-        st->n = len;
-        st->ego = ego;
+        for (int t = 0; t < st->n; ++t)
+            if (st->flags[t] & TTRL_FL_CONTROLLED) st->egos[agent_of(st->flags[t])] = t;
+        st->ego = st->egos[0];
         st->steps = 0;
         st->n_chg = 0;
     }
@@ -1687,14 +1783,16 @@ TT_HDN void env_reset(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode, 
 // one env.step(): AbstractEnv.step abstract.py:224-250 + IntersectionEnv.step intersection_env.py:135-139
 // ------------------------------------------------------------------------------------------------
 struct StepIO {
-    const int32_t* actions;        // [E] or null
-    float* obs;                    // [E][obs_size] or null
+    const int32_t* actions;        // [E][K] or null (K = controlled vehicles per env)
+    float* agent_reward;           // [E][K] or null: info["agents_rewards"] (intersection_env.py:121-129)
+    uint8_t* agent_terminated;     // [E][K] or null: info["agents_terminated"]
+    float* obs;                    // [E][obs_size] or null (obs_size = K observations)
     float* reward;                 // [E] or null
     uint8_t* terminated;           // [E] or null
     uint8_t* truncated;            // [E] or null
     const ttrl_spawn_draw* draws;  // [E] injected spawn draws or null (device Philox)
     int32_t* spawn_accepted;       // [E] or null
-    const int32_t* inv_perm;       // [E][obs_vehicles-1] or null
+    const int32_t* inv_perm;       // [E][K][obs_vehicles-1] or null
     double* stats;                 // [kStatFields][E] per-env accumulators
     GlobalState pool;              // reset pool (pool.E == 0: none)
     int32_t* done_list;            // device autoreset with warm-up: finished envs are queued here (done_count) and reset by
@@ -1715,21 +1813,37 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
     const SceneDev* sc = c.sc;
     const ttrl_config& cfg = sc->cfg;
     load_env(c, ex, g, e);
-    const int action = io.actions ? io.actions[e] : -1;
+    const int K = n_agents(c);
+    const int32_t* actions = io.actions ? io.actions + (size_t)e * K : nullptr;
     if (ex.first()) st->time += 1 / cfg.policy_frequency;
     ex.sync();
     double veh_steps = 0;
     for (int f = 0; f < sc->F; ++f) {
-        env_substep(c, ex, action, true);
+        env_substep(c, ex, actions, true);
         veh_steps += st->n;
     }
     float* obs = io.obs ? io.obs + (size_t)e * io.obs_size : nullptr;
-    const int32_t* perm = io.inv_perm ? io.inv_perm + (size_t)e * (cfg.obs_vehicles - 1) : nullptr;
+    const int32_t* perm = io.inv_perm ? io.inv_perm + (size_t)e * K * (cfg.obs_vehicles - 1) : nullptr;
     if (obs) observe(c, ex, obs, perm);
     // reward / flags / episode accounting by the first thread
     if (ex.first()) {
         const int ego = st->ego;
-        const double r = agent_reward(c, ego);
+        double r;
+        if (K == 1) {
+            r = agent_reward(c, ego, actions ? actions[0] : -1);
+            if (io.agent_reward) io.agent_reward[e] = (float)r;
+            if (io.agent_terminated) io.agent_terminated[e] = ((st->flags[ego] & TTRL_FL_CRASHED) || (!C::kPlain && has_arrived(c, ego))) ? 1 : 0;
+        } else {  // sum(agent rewards) / len(controlled_vehicles) (intersection_env.py:61-65)
+            double sum = 0;
+            for (int k = 0; k < K; ++k) {
+                const int v = st->egos[k];
+                const double rk = agent_reward(c, v, actions ? actions[k] : -1);
+                sum = sum + rk;
+                if (io.agent_reward) io.agent_reward[(size_t)e * K + k] = (float)rk;
+                if (io.agent_terminated) io.agent_terminated[(size_t)e * K + k] = ((st->flags[v] & TTRL_FL_CRASHED) || has_arrived(c, v)) ? 1 : 0;  // _agent_is_terminal :113-115
+            }
+            r = sum / K;
+        }
         const bool term = is_terminated(c), trunc = st->time >= cfg.duration;
         if (io.reward) io.reward[e] = (float)r;
         if (io.terminated) io.terminated[e] = term ? 1 : 0;

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(TeamOf<V>::T) k_substep(const SceneDev* __rest
     TT_KERNEL_PROLOGUE
     const int e = blockIdx.x;
     load_env(c, ex, g, e);
-    env_substep(c, ex, actions ? actions[e] : -1);
+    env_substep(c, ex, actions ? actions + (size_t)e * n_agents(c) : nullptr);
     store_env(c, ex, g, e);
 }
 
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(TeamOf<V>::T) k_observe(const SceneDev* __rest
     TT_KERNEL_PROLOGUE
     const int e = blockIdx.x;
     load_env(c, ex, g, e);
-    observe(c, ex, obs + (size_t)e * obs_size, inv_perm ? inv_perm + (size_t)e * (sc->cfg.obs_vehicles - 1) : nullptr);
+    observe(c, ex, obs + (size_t)e * obs_size, inv_perm ? inv_perm + (size_t)e * n_agents(c) * (sc->cfg.obs_vehicles - 1) : nullptr);
 }
 
 template <int V>
@@ -240,7 +240,7 @@ k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayo
         const int episode = g.ei[TTRL_EI_EPISODE * g.E + e] + 1;
         env_reset(c, ex, io.seed, io.first_global_env + e, episode, true);
         if (io.obs) observe(c, ex, io.obs + (size_t)e * io.obs_size,
-                            io.inv_perm ? io.inv_perm + (size_t)e * (sc->cfg.obs_vehicles - 1) : nullptr);
+                            io.inv_perm ? io.inv_perm + (size_t)e * n_agents(c) * (sc->cfg.obs_vehicles - 1) : nullptr);
         store_env(c, ex, g, e);
     } else {
         const int n_align = env_reset_align_count(sc);
@@ -283,7 +283,7 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
     cudaFuncSetAttribute(k_step<V, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_step<V, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     // "plain" scene profile (EnvCtx::kPlain): straight lanes only, no regulation, no spawn / clear, highway reward
-    bool plain = !cfg.regulated && !cfg.spawn_enabled && cfg.reward_type == TTRL_REWARD_HIGHWAY;
+    bool plain = !cfg.regulated && !cfg.spawn_enabled && cfg.reward_type == TTRL_REWARD_HIGHWAY && cfg.controlled_vehicles <= 1;
     for (int k = 0; k < cfg.n_lanes; ++k) plain = plain && lanes[k].kind == TTRL_LANE_STRAIGHT;
     out->plain = plain ? 1 : 0;
     return 0;

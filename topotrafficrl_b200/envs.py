@@ -1,9 +1,10 @@
 """Single-env, gymnasium-shaped front ends over the batched simulator, with the reference's ids, class names,
 config keys, return tuple and RNG stream (``ttrl_env/__init__.py:22-56``, ``envs/common/abstract.py:188-250``,
-``envs/intersection_env.py:17-139``).  ``scripts/example.py``-style code runs unchanged apart from the import.
+``envs/intersection_env.py:17-139``, ``envs/roundabout_env.py``, ``envs/u_turn_env.py``).  ``scripts/example.py``-style
+code runs unchanged apart from the import.
 
-The env's ``np_random`` is a numpy ``Generator(PCG64)`` seeded like gymnasium; spawn draws and the
-"shuffled" observation permutation are taken from it in the reference's order (observe -> shuffle, then
+The env's ``np_random`` is a numpy ``Generator(PCG64)`` seeded like gymnasium; reset draws, spawn draws and the
+"shuffled" observation permutations are taken from it in the reference's order (observe -> shuffle per agent, then
 clear -> spawn), so a seeded episode reproduces the reference episode.
 """
 from __future__ import annotations
@@ -13,18 +14,20 @@ from typing import Optional
 import numpy as np
 
 from . import abi, scenes
-from ._gym import Env, register, spaces
-from .reset import draw_spawn, reset_intersection
+from ._gym import HAVE_GYMNASIUM, Env, Wrapper, register, spaces
+from .reset import draw_spawn, reset_intersection, reset_roundabout, reset_uturn
 from .sim import Sim
 from .vector_env import _SimResetBackend
 
 
 class AbstractEnv(Env):
-    """Common part: config handling, spaces, the step/reset tuple."""
+    """Common part: config handling, spaces, the step/reset tuple (abstract.py:25-250)."""
 
     metadata = {"render_modes": ["human", "rgb_array"]}
     PERCEPTION_DISTANCE = 5.0 * 40.0
     SCENE = "intersection"
+    VCAP = 32
+    EGO_LANES = 1  # lanes of the ego's road at reset: default ``features_range`` of Kinematics (observation.py:213-225)
 
     def __init__(self, config: Optional[dict] = None, render_mode: Optional[str] = None, device: int = 0) -> None:
         super().__init__()
@@ -46,12 +49,119 @@ class AbstractEnv(Env):
         if config:
             self.config.update(config)  # shallow, like the reference (abstract.py:111-113)
 
-    # ---- to be provided by the scene ---------------------------------------------------------------
-    def _build(self) -> None:
+    # ---- provided by the scene -------------------------------------------------------------------------
+    def _make_network(self):
         raise NotImplementedError
 
-    def _reset(self) -> None:
+    def _exit_predicate(self):
+        return None
+
+    def _spawn_routes(self):
+        return None
+
+    def _reset_state(self) -> None:
+        """Place the vehicles of a new episode on the device, drawing from ``self.np_random`` like the reference's ``_reset``."""
         raise NotImplementedError
+
+    # ---- generic -----------------------------------------------------------------------------------------
+    def _build(self) -> None:
+        if self.sim is not None:
+            self.sim.close()
+        self.net = self._make_network()
+        self.table = self.net.to_table(self._exit_predicate())
+        self.cfg = scenes.build_config(self.table, self.config, self.SCENE, ego_lanes_count=self.EGO_LANES)
+        self.sim = Sim(self.cfg, self.table, 1, self.VCAP, self.device_index, self._spawn_routes())
+        self.sim.set_autoreset(False)
+        self.num_agents = K = self.sim.num_agents
+        shape = ((self.cfg.n_features, self.cfg.grid_w, self.cfg.grid_h) if self.cfg.obs_type == abi.OBS_GRID
+                 else (self.cfg.obs_vehicles, self.cfg.n_features))
+        self._obs_shape = shape
+        box = spaces.Box(low=-np.inf, high=np.inf, shape=shape, dtype=np.float32)
+        act = spaces.Discrete(5 if self.cfg.action_mode == abi.ACT_ALL else 3)
+        multi = self.config["observation"]["type"] == "MultiAgentObservation"
+        self._multi = multi
+        self.observation_space = spaces.Tuple([box] * K) if multi else box       # observation.py:597-600
+        self.action_space = spaces.Tuple([act] * K) if self.config["action"]["type"] == "MultiAgentAction" else act  # action.py:311-314
+        self._built_for = repr(self.config)
+
+    def _shuffled(self) -> bool:
+        return self.cfg.obs_type == abi.OBS_KINEMATICS and self.cfg.order == abi.ORDER_SHUFFLED
+
+    def _format_obs(self, flat: np.ndarray, perms=None):
+        obs = flat.reshape((self.num_agents,) + self._obs_shape)
+        if perms is not None:
+            for k, perm in enumerate(perms):
+                obs[k, 1:] = obs[k, 1:][perm]
+        return tuple(np.array(o) for o in obs) if self._multi else obs[0]
+
+    def _draw_perms(self):
+        """``np_random.shuffle(obs[1:])`` per agent observation (observation.py:272-273): the permutation depends on the
+        row count only, so it is drawn on an index vector and applied to the device's rows."""
+        if not self._shuffled():
+            return None
+        perms = []
+        for _ in range(self.num_agents):
+            perm = np.arange(self.cfg.obs_vehicles - 1)
+            self.np_random.shuffle(perm)
+            perms.append(perm)
+        return perms
+
+    def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
+        super().reset(seed=seed, options=options)
+        if options and "config" in options:
+            self.configure(options["config"])
+        if repr(self.config) != self._built_for:
+            self._build()
+        self.time = self.steps = 0
+        self.done = False
+        self._reset_state()
+        flat = self._observe()
+        return self._format_obs(flat, self._draw_perms()), self._info(None)
+
+    def _observe(self) -> np.ndarray:
+        import torch
+
+        buf = torch.zeros(self.sim.obs_size, dtype=torch.float32, device=f"cuda:{self.device_index}")
+        self.sim.observe_ptr(buf.data_ptr(), int(torch.cuda.current_stream().cuda_stream))
+        return buf.cpu().numpy()
+
+    def _info(self, action) -> dict:
+        st = self.sim.get_state()
+        ego = int(st.env_i[abi.EI_EGO, 0])
+        return {"speed": float(st.veh_d[abi.D_SPEED, 0, ego]),
+                "crashed": bool(st.veh_i[abi.I_FLAGS, 0, ego] & abi.FL_CRASHED), "action": action}
+
+    def step(self, action):
+        if self.sim is None:
+            raise NotImplementedError("The road and vehicle must be initialized in the environment implementation")
+        K = self.num_agents
+        if self.config["action"]["type"] == "MultiAgentAction":
+            assert isinstance(action, tuple)  # action.py:321
+            acts = np.array([int(a) for a in action], np.int32)
+        else:
+            acts = np.array([int(action)], np.int32)
+        # RNG order of the reference: observe() shuffles first, then _spawn_vehicle draws (intersection_env.py:135-139)
+        perms = self._draw_perms()
+        saved = None
+        if self.cfg.spawn_enabled:
+            draws = (abi.SpawnDraw * 1)()
+            saved = draw_spawn(self.np_random, float(self.config["spawn_probability"]), draws[0])
+            self.sim.inject_spawn(draws)
+        obs, reward, term, trunc = self.sim.step_host(acts.reshape(1, K))
+        if saved is not None and not self.sim.spawn_accepted()[0]:
+            self.np_random.bit_generator.state = saved
+        self.time += 1 / self.config["policy_frequency"]
+        self.steps += int(self.config["simulation_frequency"] // self.config["policy_frequency"])
+        info = self._info(action)
+        if self.SCENE == "intersection":  # IntersectionEnv._info (intersection_env.py:121-129)
+            if K > 1:
+                ar, at = self.sim.agent_outputs_host()
+                info["agents_rewards"] = tuple(float(x) for x in ar[0])
+                info["agents_terminated"] = tuple(bool(x) for x in at[0])
+            else:
+                info["agents_rewards"] = (float(reward[0]),)
+                info["agents_terminated"] = (bool(term[0]),)
+        return self._format_obs(obs, perms), float(reward[0]), bool(term[0]), bool(trunc[0]), info
 
     def render(self):
         raise NotImplementedError("rendering (pygame) is outside the B200 hot path (SURVEY.md section 2 row 20)")
@@ -71,79 +181,81 @@ class IntersectionEnv(AbstractEnv):
     def default_config(cls) -> dict:
         return scenes.merged_config(scenes.INTERSECTION_CONFIG, None)
 
-    def _build(self) -> None:
-        if self.sim is not None:
-            self.sim.close()
-        self.net = scenes.make_intersection_network()
-        self.table = self.net.to_table(scenes.intersection_exit_predicate)
-        self.cfg = scenes.build_config(self.table, self.config, "intersection")
-        self.sim = Sim(self.cfg, self.table, 1, 32, self.device_index, scenes.intersection_spawn_routes(self.net, self.table))
-        self.sim.set_autoreset(False)
-        shape = ((self.cfg.n_features, self.cfg.grid_w, self.cfg.grid_h) if self.cfg.obs_type == abi.OBS_GRID
-                 else (self.cfg.obs_vehicles, self.cfg.n_features))
-        self._obs_shape = shape
-        self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=shape, dtype=np.float32)
-        self.action_space = spaces.Discrete(5 if self.cfg.action_mode == abi.ACT_ALL else 3)
-        self._built_for = repr(self.config)
+    def _make_network(self):
+        return scenes.make_intersection_network()
 
-    def _shuffle(self, obs: np.ndarray) -> np.ndarray:
-        if self.cfg.obs_type == abi.OBS_KINEMATICS and self.cfg.order == abi.ORDER_SHUFFLED:
-            self.np_random.shuffle(obs[1:])  # observation.py:272-273
-        return obs
+    def _exit_predicate(self):
+        return scenes.intersection_exit_predicate
 
-    def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
-        super().reset(seed=seed, options=options)
-        if options and "config" in options:
-            self.configure(options["config"])
-        if repr(self.config) != self._built_for:
-            self._build()
-        self.time = self.steps = 0
-        self.done = False
+    def _spawn_routes(self):
+        return scenes.intersection_spawn_routes(self.net, self.table)
+
+    def _reset_state(self) -> None:
         reset_intersection(_SimResetBackend(self.sim), [self.np_random], self.net, self.table, self.config, self.cfg)
-        obs = self._observe()
-        return self._shuffle(obs), self._info(None)
 
-    def _observe(self) -> np.ndarray:
-        import torch
 
-        buf = torch.zeros(self.sim.obs_size, dtype=torch.float32, device=f"cuda:{self.device_index}")
-        self.sim.observe_ptr(buf.data_ptr(), int(torch.cuda.current_stream().cuda_stream))
-        return buf.cpu().numpy().reshape(self._obs_shape)
+class MultiAgentIntersectionEnv(IntersectionEnv):
+    """intersection_env.py:372-394: K controlled vehicles, tuple actions and tuple observations."""
 
-    def _info(self, action) -> dict:
-        st = self.sim.get_state()
-        ego = int(st.env_i[abi.EI_EGO, 0])
-        return {"speed": float(st.veh_d[abi.D_SPEED, 0, ego]),
-                "crashed": bool(st.veh_i[abi.I_FLAGS, 0, ego] & abi.FL_CRASHED), "action": action}
+    @classmethod
+    def default_config(cls) -> dict:
+        return scenes.merged_config(scenes.MULTI_AGENT_INTERSECTION_CONFIG, None)
 
-    def step(self, action: int):
-        if self.sim is None:
-            raise NotImplementedError("The road and vehicle must be initialized in the environment implementation")
-        # RNG order of the reference: observe() shuffles first, then _spawn_vehicle draws (intersection_env.py:135-139)
-        shuffled = self.cfg.obs_type == abi.OBS_KINEMATICS and self.cfg.order == abi.ORDER_SHUFFLED
-        perm = None
-        if shuffled:
-            perm = np.arange(self.cfg.obs_vehicles - 1)
-            self.np_random.shuffle(perm)
-        draws = (abi.SpawnDraw * 1)()
-        saved = draw_spawn(self.np_random, float(self.config["spawn_probability"]), draws[0])
-        self.sim.inject_spawn(draws)
-        obs, reward, term, trunc = self.sim.step_host(np.array([int(action)], np.int32))
-        if saved is not None and not self.sim.spawn_accepted()[0]:
-            self.np_random.bit_generator.state = saved
-        obs = obs.reshape(self._obs_shape)
-        if perm is not None:
-            obs[1:] = obs[1:][perm]
-        self.time += 1 / self.config["policy_frequency"]
-        self.steps += int(self.config["simulation_frequency"] // self.config["policy_frequency"])
-        info = self._info(action)
-        info["agents_rewards"] = (float(reward[0]),)
-        info["agents_terminated"] = (bool(term[0]),)
-        return obs, float(reward[0]), bool(term[0]), bool(trunc[0]), info
+
+class RoundaboutEnv(AbstractEnv):
+    SCENE = "roundabout"
+    VCAP = 16
+
+    @classmethod
+    def default_config(cls) -> dict:
+        return scenes.merged_config(scenes.ROUNDABOUT_CONFIG, None)
+
+    def _make_network(self):
+        return scenes.make_roundabout_network()
+
+    def _reset_state(self) -> None:
+        self.sim.set_state(reset_roundabout([self.np_random], self.net, self.table, self.config, self.cfg, self.VCAP))
+
+
+class UTurnEnv(AbstractEnv):
+    """u_turn_env.py.  Its default ``TimeToCollision`` observation is outside the hot path:
+    pass a Kinematics / OccupancyGrid observation config."""
+    SCENE = "u-turn"
+    VCAP = 16
+    EGO_LANES = 2
+
+    @classmethod
+    def default_config(cls) -> dict:
+        return scenes.merged_config(scenes.UTURN_CONFIG, None)
+
+    def _make_network(self):
+        return scenes.make_uturn_network()
+
+    def _reset_state(self) -> None:
+        self.sim.set_state(reset_uturn([self.np_random], self.net, self.table, self.config, self.cfg, self.VCAP))
+
+
+class MultiAgentWrapper(Wrapper):
+    """abstract.py:432-441: per-agent rewards and terminal flags instead of the aggregated ones."""
+
+    def step(self, action):
+        obs, _, _, truncated, info = self.env.step(action)
+        return obs, info["agents_rewards"], info["agents_terminated"], truncated, info
 
 
 def _register_ttrl_envs() -> None:
+    """Same ids as ``ttrl_env/__init__.py:22-56`` (``intersection-v1`` = ContinuousAction: outside the hot path)."""
     register(id="intersection-v0", entry_point="topotrafficrl_b200.envs:IntersectionEnv")
+    register(id="intersection-multi-agent-v0", entry_point="topotrafficrl_b200.envs:MultiAgentIntersectionEnv")
+    if HAVE_GYMNASIUM:  # pragma: no cover - gymnasium is not in this image
+        from gymnasium.envs.registration import WrapperSpec
+        wrappers = (WrapperSpec("MultiAgentWrapper", "topotrafficrl_b200.envs:MultiAgentWrapper", None),)
+    else:
+        wrappers = (MultiAgentWrapper,)
+    register(id="intersection-multi-agent-v1", entry_point="topotrafficrl_b200.envs:MultiAgentIntersectionEnv",
+             additional_wrappers=wrappers)
+    register(id="roundabout-v0", entry_point="topotrafficrl_b200.envs:RoundaboutEnv")
+    register(id="u-turn-v0", entry_point="topotrafficrl_b200.envs:UTurnEnv")
 
 
 _register_ttrl_envs()

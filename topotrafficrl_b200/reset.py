@@ -53,8 +53,9 @@ def draw_spawn(rng: np.random.Generator, spawn_probability: float, rec: abi.Spaw
 def reset_intersection(backend: ResetBackend, rngs: Sequence[np.random.Generator], net: RoadNetwork, table: NetworkTable,
                        config: dict, cfg: abi.Config) -> SimState:
     E = backend.num_envs
-    if int(config.get("controlled_vehicles", 1)) != 1:
-        raise NotImplementedError("multi-agent intersection is outside the round-1 hot path (SURVEY.md section 8f, N3)")
+    n_controlled = int(config.get("controlled_vehicles", 1))
+    if not 1 <= n_controlled <= abi.MAX_CONTROLLED:
+        raise NotImplementedError(f"controlled_vehicles must be in 1..{abi.MAX_CONTROLLED}")
     n_vehicles = int(config["initial_vehicle_count"])
     sim_freq = int(config["simulation_frequency"])
     st0 = SimState.zeros(E, backend.get_state().vcap)
@@ -74,43 +75,144 @@ def reset_intersection(backend: ResetBackend, rngs: Sequence[np.random.Generator
         backend.substep_none()
     attempt(60, 0.1, 0.0, 1.0, True)  # challenger vehicle
 
-    # ego: MDPVehicle on (o0, ir0, 0) at s = 60 + 5 N(1, 1), speed = speed_limit, route to the destination
+    # controlled vehicles: MDPVehicle k on (o<k%4>, ir<k%4>, 0) at s = 60 + 5 N(1, 1), speed = speed_limit, route to the destination
     st = backend.get_state()
-    ego_key = ("o0", "ir0", 0)
-    ego_lane = net.get_lane(ego_key)
-    lane_flat = table.flat(ego_key)
     ts = np.array([cfg.target_speeds[k] for k in range(cfg.n_target_speeds)])
     for e in range(E):
-        destination = config["destination"] or "o" + str(rngs[e].integers(1, 4))
-        pos = ego_lane.position(60 + 5 * rngs[e].normal(1), 0)
-        speed = float(ego_lane.speed_limit)
-        x = (speed - ts[0]) / (ts[-1] - ts[0])
-        sidx = int(np.clip(np.round(x * (ts.size - 1)), 0, ts.size - 1))  # MDPVehicle.speed_to_index
-        route = [(table.road_index_of[(f, t_)], i) for f, t_, i in net.plan_route(ego_key, destination)]
-        n = int(st.env_i[abi.EI_NVEH, e])
-        if n >= st.vcap:
-            raise RuntimeError("vehicle capacity exceeded during reset")
-        st.set_vehicle(e, n, x=float(pos[0]), y=float(pos[1]), heading=float(ego_lane.heading_at(60)), speed=speed,
-                       lane=lane_flat, target_speed=float(ts[sidx]), speed_index=sidx, mdp=True, controlled=True, route=route)
-        # "prevent early collisions": list.remove() while iterating skips the element after each removal (:313-318)
-        order: List[int] = list(range(n + 1))
-        ego_slot = n
-        i = 0
-        while i < len(order):
-            s = order[i]
-            if s != ego_slot:
-                d = np.linalg.norm(np.array([st.veh_d[abi.D_X, e, s] - pos[0], st.veh_d[abi.D_Y, e, s] - pos[1]]))
-                if d < 20:
-                    order.pop(i)
-            i += 1
-        _compact(st, e, order)
-        st.env_i[abi.EI_NVEH, e] = len(order)
-        st.env_i[abi.EI_EGO, e] = order.index(ego_slot)
+        for ego_id in range(n_controlled):
+            ego_key = (f"o{ego_id % 4}", f"ir{ego_id % 4}", 0)
+            ego_lane = net.get_lane(ego_key)
+            destination = config["destination"] or "o" + str(rngs[e].integers(1, 4))
+            pos = ego_lane.position(60 + 5 * rngs[e].normal(1), 0)
+            heading = float(ego_lane.heading_at(60))
+            speed = float(ego_lane.speed_limit)
+            x = (speed - ts[0]) / (ts[-1] - ts[0])
+            sidx = int(np.clip(np.round(x * (ts.size - 1)), 0, ts.size - 1))  # MDPVehicle.speed_to_index
+            lane_key = net.get_closest_lane_index(pos, heading)                # RoadObject.__init__ objects.py:45-50
+            route = [(table.road_index_of[(f, t_)], i) for f, t_, i in net.plan_route(lane_key, destination)]
+            n = int(st.env_i[abi.EI_NVEH, e])
+            if n >= st.vcap:
+                raise RuntimeError("vehicle capacity exceeded during reset")
+            st.set_vehicle(e, n, x=float(pos[0]), y=float(pos[1]), heading=heading, speed=speed,
+                           lane=table.flat(lane_key), target_speed=float(ts[sidx]), speed_index=sidx, mdp=True, controlled=True,
+                           route=route, agent=ego_id)
+            # "prevent early collisions": list.remove() while iterating skips the element after each removal (:313-318)
+            order: List[int] = list(range(n + 1))
+            ego_slot = n
+            i = 0
+            while i < len(order):
+                s = order[i]
+                if s != ego_slot:
+                    d = np.linalg.norm(np.array([st.veh_d[abi.D_X, e, s] - pos[0], st.veh_d[abi.D_Y, e, s] - pos[1]]))
+                    if d < 20:
+                        order.pop(i)
+                i += 1
+            _compact(st, e, order)
+            st.env_i[abi.EI_NVEH, e] = len(order)
+        flags = st.veh_i[abi.I_FLAGS, e, :int(st.env_i[abi.EI_NVEH, e])]
+        first = np.nonzero((flags & abi.FL_CONTROLLED) != 0)[0]
+        first = [int(k) for k in first if ((int(flags[k]) & abi.FL_AGENT_MASK) >> abi.FL_AGENT_SHIFT) == 0]
+        st.env_i[abi.EI_EGO, e] = first[0]
         st.env_i[abi.EI_STEPS, e] = 0
         st.env_d[abi.ED_TIME, e] = 0.0
         st.env_d[abi.ED_RETURN, e] = 0.0
         st.env_i[abi.EI_DONE, e] = 0
     backend.set_state(st)
+    return st
+
+
+# --------------------------------------------------------------------------------------------------
+# scripted scenes: RoundaboutEnv / UTurnEnv place a fixed cast of vehicles with a few random draws
+# --------------------------------------------------------------------------------------------------
+class _Cast:
+    """Builds one env's vehicle list the way the reference constructors do (``RoadObject.make_on_lane`` objects.py:67-89,
+    ``RoadObject.__init__`` :45-50 closest-lane lookup, ``ControlledVehicle.__init__`` controller.py:35-48,
+    ``MDPVehicle.__init__`` :262-293, ``IDMVehicle.__init__`` behavior.py:48-64, ``plan_route_to`` controller.py:71-87)."""
+
+    def __init__(self, st: SimState, e: int, net: RoadNetwork, table: NetworkTable, cfg: abi.Config) -> None:
+        self.st, self.e, self.net, self.table = st, e, net, table
+        self.ts = np.array([cfg.target_speeds[k] for k in range(cfg.n_target_speeds)])
+        self.n = 0
+
+    def _route(self, lane_key, destination):
+        if destination is None:
+            return None
+        return [(self.table.road_index_of[(f, t)], i) for f, t, i in self.net.plan_route(lane_key, destination)]
+
+    def ego(self, position, heading: float, speed: float, destination) -> None:
+        lane_key = self.net.get_closest_lane_index(position, heading)
+        ts = self.ts
+        x = (speed - ts[0]) / (ts[-1] - ts[0])
+        sidx = int(np.clip(np.round(x * (ts.size - 1)), 0, ts.size - 1))
+        self.st.set_vehicle(self.e, self.n, x=float(position[0]), y=float(position[1]), heading=float(heading), speed=float(speed),
+                            lane=self.table.flat(lane_key), target_speed=float(ts[sidx]), speed_index=sidx, mdp=True,
+                            controlled=True, route=self._route(lane_key, destination))
+        self.st.env_i[abi.EI_EGO, self.e] = self.n
+        self.n += 1
+
+    def idm_on_lane(self, lane_index, longitudinal: float, speed: float, destination, delta: float = 4.0) -> None:
+        lane = self.net.get_lane(lane_index)
+        position, heading = lane.position(longitudinal, 0), float(lane.heading_at(longitudinal))
+        lane_key = self.net.get_closest_lane_index(position, heading)
+        self.st.set_vehicle(self.e, self.n, x=float(position[0]), y=float(position[1]), heading=heading, speed=float(speed),
+                            lane=self.table.flat(lane_key), timer=float((np.sum(position) * np.pi) % 1.0), delta=float(delta),
+                            route=self._route(lane_key, destination))
+        self.n += 1
+
+    def done(self) -> None:
+        self.st.env_i[abi.EI_NVEH, self.e] = self.n
+
+
+def reset_roundabout(rngs: Sequence[np.random.Generator], net: RoadNetwork, table: NetworkTable, config: dict, cfg: abi.Config,
+                     vcap: int) -> SimState:
+    """``RoundaboutEnv._make_vehicles`` (roundabout_env.py:326-387) for one Generator per env, draws in the reference's order."""
+    st = SimState.zeros(len(rngs), vcap)
+    position_deviation = speed_deviation = 2
+    destinations = ["exr", "sxr", "nxr"]
+    for e, rng in enumerate(rngs):
+        cast = _Cast(st, e, net, table, cfg)
+        ego_lane = net.get_lane(("ser", "ses", 0))
+        cast.ego(ego_lane.position(125, 0), ego_lane.heading_at(140), 8, "nxs")
+        # incoming vehicle
+        lon = 5 + rng.normal() * position_deviation
+        speed = 16 + rng.normal() * speed_deviation
+        if config["incoming_vehicle_destination"] is not None:
+            destination = destinations[config["incoming_vehicle_destination"]]
+        else:
+            destination = str(rng.choice(destinations))
+        cast.idm_on_lane(("we", "sx", 1), lon, speed, destination, delta=rng.uniform(low=3.5, high=4.5))
+        # other vehicles
+        for i in list(range(1, 2)) + list(range(-1, 0)):
+            lon = 20 * i + rng.normal() * position_deviation
+            speed = 16 + rng.normal() * speed_deviation
+            destination = str(rng.choice(destinations))
+            cast.idm_on_lane(("we", "sx", 0), lon, speed, destination, delta=rng.uniform(low=3.5, high=4.5))
+        # entering vehicle
+        lon = 50 + rng.normal() * position_deviation
+        speed = 16 + rng.normal() * speed_deviation
+        destination = str(rng.choice(destinations))
+        cast.idm_on_lane(("eer", "ees", 0), lon, speed, destination, delta=rng.uniform(low=3.5, high=4.5))
+        cast.done()
+    return st
+
+
+def reset_uturn(rngs: Sequence[np.random.Generator], net: RoadNetwork, table: NetworkTable, config: dict, cfg: abi.Config,
+                vcap: int) -> SimState:
+    """``UTurnEnv._make_vehicles`` (u_turn_env.py:173-271)."""
+    st = SimState.zeros(len(rngs), vcap)
+    position_deviation = speed_deviation = 2
+    for e, rng in enumerate(rngs):
+        cast = _Cast(st, e, net, table, cfg)
+        ego_lane = net.get_lane(("a", "b", 0))
+        cast.ego(ego_lane.position(0, 0), 0.0, 16, "d")
+        script = [(("a", "b", 0), 25, 13.5, True), (("a", "b", 1), 56, 14.5, False), (("b", "c", 1), 0.5, 4.5, False),
+                  (("b", "c", 0), 17.5, 5.5, False), (("c", "d", 0), 1, 3.5, False), (("c", "d", 1), 30, 5.5, False)]
+        for lane_index, lon0, speed0, randomize in script:
+            lon = lon0 + rng.normal() * position_deviation
+            speed = speed0 + rng.normal() * speed_deviation
+            delta = rng.uniform(low=3.5, high=4.5) if randomize else 4.0  # randomize_behavior (behavior.py:66-69)
+            cast.idm_on_lane(lane_index, lon, speed, "d", delta=delta)
+        cast.done()
     return st
 
 

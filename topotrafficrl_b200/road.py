@@ -29,6 +29,10 @@ class LineType:
     CONTINUOUS_LINE = 3
 
 
+def wrap_to_pi(x: float) -> float:
+    return ((x + np.pi) % (2 * np.pi)) - np.pi  # utils.py:57-58
+
+
 class AbstractLane:
     DEFAULT_WIDTH: float = 4
     VEHICLE_LENGTH: float = 5
@@ -36,6 +40,16 @@ class AbstractLane:
 
     def _record(self) -> abi.Lane:  # pragma: no cover - abstract
         raise NotImplementedError
+
+    # Scene-construction helpers (host-driven resets place vehicles like RoadObject.__init__, objects.py:45-50, which
+    # looks up the closest lane of the new vehicle); never on the step path.
+    def local_coordinates(self, position) -> Tuple[float, float]:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def distance_with_heading(self, position, heading: float, heading_weight: float = 1.0) -> float:  # lane.py:132-147
+        s, r = self.local_coordinates(position)
+        angle = np.abs(wrap_to_pi(heading - self.heading_at(s)))
+        return abs(r) + max(s - self.length, 0) + max(0 - s, 0) + heading_weight * angle
 
 
 class StraightLane(AbstractLane):
@@ -70,6 +84,10 @@ class StraightLane(AbstractLane):
     def heading_at(self, longitudinal: float) -> float:
         return self.heading
 
+    def local_coordinates(self, position) -> Tuple[float, float]:  # lane.py:209-213
+        delta = np.asarray(position, dtype=np.float64) - self.start
+        return float(np.dot(delta, self.direction)), float(np.dot(delta, self.direction_lateral))
+
 
 class SineLane(StraightLane):
     def __init__(self, start, end, amplitude: float, pulsation: float, phase: float,
@@ -91,6 +109,10 @@ class SineLane(StraightLane):
 
     def heading_at(self, longitudinal: float) -> float:
         return self.heading + np.arctan(self.amplitude * self.pulsation * np.cos(self.pulsation * longitudinal + self.phase))
+
+    def local_coordinates(self, position) -> Tuple[float, float]:  # lane.py:282-286
+        longitudinal, lateral = super().local_coordinates(position)
+        return longitudinal, lateral - self.amplitude * np.sin(self.pulsation * longitudinal + self.phase)
 
 
 class CircularLane(AbstractLane):
@@ -127,6 +149,13 @@ class CircularLane(AbstractLane):
     def heading_at(self, longitudinal: float) -> float:
         phi = self.direction * longitudinal / self.radius + self.start_phase
         return phi + np.pi / 2 * self.direction
+
+    def local_coordinates(self, position) -> Tuple[float, float]:  # lane.py:355-362
+        delta = np.asarray(position, dtype=np.float64) - self.center
+        phi = np.arctan2(delta[1], delta[0])
+        phi = self.start_phase + wrap_to_pi(phi - self.start_phase)
+        r = np.linalg.norm(delta)
+        return float(self.direction * (phi - self.start_phase) * self.radius), float(self.direction * (self.radius - r))
 
 
 @dataclass
@@ -178,6 +207,16 @@ class RoadNetwork:
 
     def lanes_list(self) -> List[AbstractLane]:
         return [lane for tos in self.graph.values() for lanes in tos.values() for lane in lanes]
+
+    def get_closest_lane_index(self, position, heading: float) -> LaneIndex:
+        """road.py:55-71: argmin of ``distance_with_heading`` in dict order (the first minimum wins)."""
+        indexes, distances = [], []
+        for _from, tos in self.graph.items():
+            for _to, lanes in tos.items():
+                for _id, lane in enumerate(lanes):
+                    distances.append(lane.distance_with_heading(position, heading))
+                    indexes.append((_from, _to, _id))
+        return indexes[int(np.argmin(distances))]
 
     # ---- route planning (host side; the device receives finished route tables) --------------------
     def bfs_paths(self, start: str, goal: str):

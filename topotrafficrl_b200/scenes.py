@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import abi
-from .road import AbstractLane, CircularLane, LineType, NetworkTable, RoadNetwork, StraightLane
+from .road import AbstractLane, CircularLane, LineType, NetworkTable, RoadNetwork, SineLane, StraightLane
 from .state import SimState
 
 # --------------------------------------------------------------------------------------------------
@@ -57,6 +57,32 @@ HIGHWAY_CONFIG = dict(BASE_CONFIG, **{
     "road_length": 10000, "speed_limit": 30,
     "duration": 40, "collision_reward": -1.0, "left_lane_reward": 0.1, "high_speed_reward": 0.4,
     "reward_speed_range": [20, 30], "normalize_reward": True, "offroad_terminal": False,
+})
+
+# MultiAgentIntersectionEnv.default_config (intersection_env.py:372-394)
+MULTI_AGENT_INTERSECTION_CONFIG = dict(INTERSECTION_CONFIG, **{
+    "action": {"type": "MultiAgentAction",
+               "action_config": {"type": "DiscreteMetaAction", "lateral": False, "longitudinal": True}},
+    "observation": {"type": "MultiAgentObservation", "observation_config": {"type": "Kinematics"}},
+    "controlled_vehicles": 2,
+})
+
+# RoundaboutEnv.default_config (roundabout_env.py:13-41)
+ROUNDABOUT_CONFIG = dict(BASE_CONFIG, **{
+    "observation": {"type": "Kinematics", "absolute": True,
+                    "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-15, 15], "vy": [-15, 15]}},
+    "action": {"type": "DiscreteMetaAction", "target_speeds": [0, 8, 16]},
+    "incoming_vehicle_destination": None, "collision_reward": -1, "high_speed_reward": 0.2, "right_lane_reward": 0,
+    "lane_change_reward": -0.05, "screen_width": 600, "screen_height": 600, "centering_position": [0.5, 0.6],
+    "duration": 11, "normalize_reward": True,
+})
+
+# UTurnEnv.default_config (u_turn_env.py:18-37)
+UTURN_CONFIG = dict(BASE_CONFIG, **{
+    "observation": {"type": "TimeToCollision", "horizon": 16},
+    "action": {"type": "DiscreteMetaAction", "target_speeds": [8, 16, 24]},
+    "screen_width": 789, "screen_height": 289, "duration": 10, "collision_reward": -1.0, "left_lane_reward": 0.1,
+    "high_speed_reward": 0.4, "reward_speed_range": [8, 24], "normalize_reward": True, "offroad_terminal": False,
 })
 
 # IDM/MOBIL class constants: behavior.py:20-46; the intersection scene overrides three of them
@@ -109,6 +135,67 @@ def make_intersection_network() -> RoadNetwork:
     return net
 
 
+def make_roundabout_network() -> RoadNetwork:
+    """``RoundaboutEnv._make_road`` (roundabout_env.py:76-324): two-lane ring of 8 arcs (radii 20 / 24 m) and four
+    access roads, each a straight lane joined to the ring by a sine lane.  Nodes: (s)outh/(e)ast/(n)orth/(w)est,
+    (e)ntry/e(x)it, (r)oad/(s)ine."""
+    center, radius, alpha = [0, 0], 20, 24
+    net = RoadNetwork()
+    radii = [radius, radius + 4]
+    n, c, s = LineType.NONE, LineType.CONTINUOUS, LineType.STRIPED
+    line = [[c, s], [n, c]]
+    ring = [("se", "ex", 90 - alpha, alpha), ("ex", "ee", alpha, -alpha), ("ee", "nx", -alpha, -90 + alpha),
+            ("nx", "ne", -90 + alpha, -90 - alpha), ("ne", "wx", -90 - alpha, -180 + alpha),
+            ("wx", "we", -180 + alpha, -180 - alpha), ("we", "sx", 180 - alpha, 90 + alpha), ("sx", "se", 90 + alpha, 90 - alpha)]
+    for lane in [0, 1]:
+        for _from, _to, a0, a1 in ring:
+            net.add_lane(_from, _to, CircularLane(center, radii[lane], np.deg2rad(a0), np.deg2rad(a1), clockwise=False,
+                                                  line_types=line[lane]))
+    access, dev, a = 170, 85, 5
+    delta_st = 0.2 * dev
+    delta_en = dev - delta_st
+    w = 2 * np.pi / dev
+    net.add_lane("ser", "ses", StraightLane([2, access], [2, dev / 2], line_types=(s, c)))
+    net.add_lane("ses", "se", SineLane([2 + a, dev / 2], [2 + a, dev / 2 - delta_st], a, w, -np.pi / 2, line_types=(c, c)))
+    net.add_lane("sx", "sxs", SineLane([-2 - a, -dev / 2 + delta_en], [-2 - a, dev / 2], a, w, -np.pi / 2 + w * delta_en, line_types=(c, c)))
+    net.add_lane("sxs", "sxr", StraightLane([-2, dev / 2], [-2, access], line_types=(n, c)))
+    net.add_lane("eer", "ees", StraightLane([access, -2], [dev / 2, -2], line_types=(s, c)))
+    net.add_lane("ees", "ee", SineLane([dev / 2, -2 - a], [dev / 2 - delta_st, -2 - a], a, w, -np.pi / 2, line_types=(c, c)))
+    net.add_lane("ex", "exs", SineLane([-dev / 2 + delta_en, 2 + a], [dev / 2, 2 + a], a, w, -np.pi / 2 + w * delta_en, line_types=(c, c)))
+    net.add_lane("exs", "exr", StraightLane([dev / 2, 2], [access, 2], line_types=(n, c)))
+    net.add_lane("ner", "nes", StraightLane([-2, -access], [-2, -dev / 2], line_types=(s, c)))
+    net.add_lane("nes", "ne", SineLane([-2 - a, -dev / 2], [-2 - a, -dev / 2 + delta_st], a, w, -np.pi / 2, line_types=(c, c)))
+    net.add_lane("nx", "nxs", SineLane([2 + a, dev / 2 - delta_en], [2 + a, -dev / 2], a, w, -np.pi / 2 + w * delta_en, line_types=(c, c)))
+    net.add_lane("nxs", "nxr", StraightLane([2, -dev / 2], [2, -access], line_types=(n, c)))
+    net.add_lane("wer", "wes", StraightLane([-access, 2], [-dev / 2, 2], line_types=(s, c)))
+    net.add_lane("wes", "we", SineLane([-dev / 2, 2 + a], [-dev / 2 + delta_st, 2 + a], a, w, -np.pi / 2, line_types=(c, c)))
+    net.add_lane("wx", "wxs", SineLane([dev / 2 - delta_en, -2 - a], [-dev / 2, -2 - a], a, w, -np.pi / 2 + w * delta_en, line_types=(c, c)))
+    net.add_lane("wxs", "wxr", StraightLane([-dev / 2, -2], [-access, -2], line_types=(n, c)))
+    return net
+
+
+def make_uturn_network(length: float = 128) -> RoadNetwork:
+    """``UTurnEnv._make_road`` (u_turn_env.py:83-171): two lanes a->b, a counter-clockwise half circle b->c, two lanes c->d."""
+    net = RoadNetwork()
+    w = StraightLane.DEFAULT_WIDTH
+    net.add_lane("c", "d", StraightLane([length, w], [0, w], line_types=(LineType.CONTINUOUS_LINE, LineType.STRIPED)))
+    net.add_lane("c", "d", StraightLane([length, 0], [0, 0], line_types=(LineType.NONE, LineType.CONTINUOUS_LINE)))
+    center = [length, w + 20]
+    radius, alpha = 20, 0
+    radii = [radius, radius + w]
+    n, c, s = LineType.NONE, LineType.CONTINUOUS, LineType.STRIPED
+    line = [[c, s], [n, c]]
+    for lane in [0, 1]:
+        net.add_lane("b", "c", CircularLane(center, radii[lane], np.deg2rad(90 - alpha), np.deg2rad(-90 + alpha),
+                                            clockwise=False, line_types=line[lane]))
+    offset = 2 * radius
+    net.add_lane("a", "b", StraightLane([0, ((2 * w + offset) - w)], [length, ((2 * w + offset) - w)],
+                                        line_types=(LineType.CONTINUOUS_LINE, LineType.STRIPED)))
+    net.add_lane("a", "b", StraightLane([0, (2 * w + offset)], [length, (2 * w + offset)],
+                                        line_types=(LineType.NONE, LineType.CONTINUOUS_LINE)))
+    return net
+
+
 def intersection_exit_predicate(_from: str, _to: str) -> bool:
     return "il" in _from and "o" in _to
 
@@ -127,9 +214,10 @@ def intersection_spawn_routes(net: RoadNetwork, table: NetworkTable):
         idx = (f"o{a}", f"ir{a}", 0)
         spawn_lane[a] = table.flat(idx)
         for b in range(4):
-            if a == b:
-                continue
+            # a == b (a controlled vehicle of the multi-agent env whose destination is its own arm): 5 roads
             route = net.plan_route(idx, f"o{b}")[1:]
+            if len(route) + 1 > abi.ROUTE_CAP:
+                raise ValueError("planned route exceeds the device route capacity")
             rlen[a, b] = len(route)
             for k, (f, t, _) in enumerate(route):
                 rroad[a, b, k] = table.road_index_of[(f, t)]
@@ -155,10 +243,18 @@ def build_config(table: NetworkTable, config: dict, scene: str, ego_lanes_count:
     cfg.simulation_frequency = float(config["simulation_frequency"])
     cfg.policy_frequency = float(config["policy_frequency"])
     cfg.duration = float(config["duration"])
+    if scene not in ("intersection", "highway", "roundabout", "u-turn"):
+        raise ValueError(f"unknown scene {scene!r}")
     idm = IDM_INTERSECTION if scene == "intersection" else IDM_DEFAULT
     for k, v in idm.items():
         setattr(cfg, k, float(v))
     cfg.regulated = 1 if scene == "intersection" else 0
+    cfg.controlled_vehicles = int(config.get("controlled_vehicles", 1))
+    if not 1 <= cfg.controlled_vehicles <= abi.MAX_CONTROLLED:
+        # ego k starts on arm k % 4 (intersection_env.py:287-289): a fifth ego would be placed onto the first one
+        raise NotImplementedError(f"controlled_vehicles must be in 1..{abi.MAX_CONTROLLED}")
+    if cfg.controlled_vehicles > 1 and scene != "intersection":
+        raise NotImplementedError("several controlled vehicles exist in the intersection scene only (intersection_env.py:372)")
 
     # ---- action -------------------------------------------------------------------------------
     act = config["action"]
@@ -249,17 +345,22 @@ def build_config(table: NetworkTable, config: dict, scene: str, ego_lanes_count:
             cfg.range_lo[k], cfg.range_hi[k] = float(frange[name][0]), float(frange[name][1])
 
     # ---- reward / termination -------------------------------------------------------------------
+    cfg.speed_index_den = 1.0
     if scene == "intersection":
         cfg.reward_type = abi.REWARD_INTERSECTION
         cfg.arrived_reward = float(config.get("arrived_reward", 0))
         cfg.spawn_enabled = 1
         cfg.spawn_probability = float(config["spawn_probability"])
+    elif scene == "roundabout":
+        cfg.reward_type = abi.REWARD_ROUNDABOUT
+        cfg.lane_change_reward = float(config.get("lane_change_reward", 0))
+        cfg.speed_index_den = float(np.linspace(20, 30, 3).size - 1)  # MDPVehicle.DEFAULT_TARGET_SPEEDS.size - 1 (controller.py:259)
     else:
         cfg.reward_type = abi.REWARD_HIGHWAY
         cfg.lane_reward = float(config.get("left_lane_reward", 0))
     cfg.collision_reward = float(config.get("collision_reward", 0))
     cfg.high_speed_reward = float(config.get("high_speed_reward", 0))
-    cfg.reward_speed_lo, cfg.reward_speed_hi = (float(x) for x in config["reward_speed_range"])
+    cfg.reward_speed_lo, cfg.reward_speed_hi = (float(x) for x in config.get("reward_speed_range", [0.0, 1.0]))
     cfg.normalize_reward = int(bool(config.get("normalize_reward", False)))
     cfg.offroad_terminal = int(bool(config.get("offroad_terminal", False)))
     return cfg

@@ -34,7 +34,8 @@ class Sim:
                                       _p(table.node_first), _p(table.node_roads), self.num_envs, self.vcap, self.device,
                                       C.byref(h)))
         self._h = h
-        self.obs_size = self._L.ttrl_sim_obs_size(self._h)
+        self.obs_size = self._L.ttrl_sim_obs_size(self._h)       # floats per env: K observations
+        self.num_agents = self._L.ttrl_sim_num_agents(self._h)  # K = controlled vehicles per env
         if spawn_routes is not None:
             sl, rl, rr = (np.ascontiguousarray(a, dtype=np.int32) for a in spawn_routes)
             check(self._L.ttrl_sim_set_spawn_routes(self._h, _p(sl), _p(rl), _p(rr)))
@@ -116,12 +117,15 @@ class Sim:
         if getattr(self, "_pinned", None) is None:
             ptrs = [C.c_void_p() for _ in range(5)]
             check(self._L.ttrl_sim_host_buffers(self._h, *[C.byref(p) for p in ptrs]))
-            E = self.num_envs
+            E, K = self.num_envs, self.num_agents
 
             def view(p, ctype, n, dtype):
                 return np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(n,)).view(dtype)
 
-            self._pinned = (view(ptrs[0], C.c_int32, E, np.int32), view(ptrs[1], C.c_float, E * self.obs_size, np.float32).reshape(E, self.obs_size),
+            ar, at = C.c_void_p(), C.c_void_p()
+            check(self._L.ttrl_sim_host_agent_buffers(self._h, C.byref(ar), C.byref(at)))
+            self._pinned_agents = (view(ar, C.c_float, E * K, np.float32).reshape(E, K), view(at, C.c_uint8, E * K, np.uint8).reshape(E, K))
+            self._pinned = (view(ptrs[0], C.c_int32, E * K, np.int32), view(ptrs[1], C.c_float, E * self.obs_size, np.float32).reshape(E, self.obs_size),
                             view(ptrs[2], C.c_float, E, np.float32), view(ptrs[3], C.c_uint8, E, np.uint8), view(ptrs[4], C.c_uint8, E, np.uint8))
         return self._pinned
 
@@ -132,11 +136,29 @@ class Sim:
         library's page-locked staging buffers: no host copy at all, but the arrays are overwritten by the next call."""
         a_pin, obs, reward, term, trunc = self._pinned_views()
         if actions is not None:
-            a_pin[:] = actions
+            a_pin[:] = np.asarray(actions, dtype=np.int32).reshape(-1)
         check(self._L.ttrl_sim_step_pinned(self._h, int(actions is not None)))
         if copy:
             return obs.copy(), reward.copy(), term.copy(), trunc.copy()
         return obs, reward, term, trunc
+
+    def agent_outputs_host(self, copy: bool = True):
+        """info["agents_rewards"] / info["agents_terminated"] of the last ``step_host`` call: float32 [E, K], uint8 [E, K]
+        (filled by the library when K > 1)."""
+        self._pinned_views()
+        r, t = self._pinned_agents
+        return (r.copy(), t.copy()) if copy else (r, t)
+
+    def agent_outputs_ptr(self):
+        """Device pointers (agent_reward float32[E*K], agent_terminated uint8[E*K]) of the last ``step_ptr`` call."""
+        r, t = C.c_void_p(), C.c_void_p()
+        check(self._L.ttrl_sim_agent_outputs(self._h, C.byref(r), C.byref(t)))
+        return r.value, t.value
+
+    def set_agent_outputs_ptr(self, agent_reward_ptr, agent_terminated_ptr) -> None:
+        """Let ``step_ptr`` write info["agents_rewards"] / ["agents_terminated"] into caller-owned device buffers
+        (float32[E*K], uint8[E*K])."""
+        check(self._L.ttrl_sim_set_agent_outputs(self._h, agent_reward_ptr, agent_terminated_ptr))
 
     def stats(self, reset: bool = False) -> abi.EpisodeStats:
         out = abi.EpisodeStats()

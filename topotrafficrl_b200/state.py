@@ -13,28 +13,33 @@ import numpy as np
 from . import abi
 
 
-def pack_route(route: Optional[Sequence[Tuple[int, Optional[int]]]]) -> Tuple[int, int, int]:
-    """``route`` = list of (road index, lane id | None), or None.  Returns (len, road word, lane word)."""
+def pack_route(route: Optional[Sequence[Tuple[int, Optional[int]]]]) -> Tuple[int, Tuple[int, ...], Tuple[int, ...]]:
+    """``route`` = list of (road index, lane id | None), or None.  Returns (len, road words, lane words): entry k is
+    byte ``k % 4`` of word ``k // 4`` (``abi.ROUTE_WORDS`` int32 words each)."""
     if route is None:
-        return -1, 0, 0
+        return -1, (0,) * abi.ROUTE_WORDS, (0,) * abi.ROUTE_WORDS
     if len(route) > abi.ROUTE_CAP:
         raise ValueError(f"route longer than {abi.ROUTE_CAP} entries")
-    rr = rl = 0
+    rr = [0] * abi.ROUTE_WORDS
+    rl = [0] * abi.ROUTE_WORDS
     for k, (road, lane) in enumerate(route):
-        rr |= (int(road) & 0xFF) << (8 * k)
-        rl |= (0xFF if lane is None else int(lane) & 0xFF) << (8 * k)
-    return len(route), _as_i32(rr), _as_i32(rl)
+        rr[k // 4] |= (int(road) & 0xFF) << (8 * (k % 4))
+        rl[k // 4] |= (0xFF if lane is None else int(lane) & 0xFF) << (8 * (k % 4))
+    return len(route), tuple(_as_i32(w) for w in rr), tuple(_as_i32(w) for w in rl)
 
 
-def unpack_route(length: int, rr: int, rl: int) -> Optional[List[Tuple[int, Optional[int]]]]:
+def unpack_route(length: int, rr: Sequence[int], rl: Sequence[int]) -> Optional[List[Tuple[int, Optional[int]]]]:
+    """Inverse of :func:`pack_route`; ``rr`` / ``rl`` are the road / lane words (a single int = word 0 only)."""
     if length < 0:
         return None
-    rr &= 0xFFFFFFFF
-    rl &= 0xFFFFFFFF
+    if isinstance(rr, (int, np.integer)):
+        rr, rl = (rr,), (rl,)
+    rr = [int(w) & 0xFFFFFFFF for w in rr]
+    rl = [int(w) & 0xFFFFFFFF for w in rl]
     out = []
     for k in range(length):
-        lane = (rl >> (8 * k)) & 0xFF
-        out.append(((rr >> (8 * k)) & 0xFF, None if lane == 0xFF else lane))
+        lane = (rl[k // 4] >> (8 * (k % 4))) & 0xFF
+        out.append(((rr[k // 4] >> (8 * (k % 4))) & 0xFF, None if lane == 0xFF else lane))
     return out
 
 
@@ -81,7 +86,7 @@ class SimState:
 
     def set_vehicle(self, e: int, s: int, *, x, y, heading, speed, lane, target_lane=None, target_speed=None,
                     timer=0.0, delta=4.0, mdp=False, controlled=False, crashed=False, speed_index=0,
-                    route=None, steering=0.0, accel=0.0, impact=None, yielding=False, yield_timer=0) -> None:
+                    route=None, steering=0.0, accel=0.0, impact=None, yielding=False, yield_timer=0, agent=0) -> None:
         d, i = self.veh_d, self.veh_i
         d[abi.D_X, e, s], d[abi.D_Y, e, s] = x, y
         d[abi.D_HEADING, e, s], d[abi.D_SPEED, e, s] = heading, speed
@@ -89,6 +94,7 @@ class SimState:
         d[abi.D_TARGET_SPEED, e, s] = speed if target_speed is None else target_speed
         d[abi.D_TIMER, e, s], d[abi.D_DELTA, e, s] = timer, delta
         flags = (abi.FL_MDP if mdp else 0) | (abi.FL_CONTROLLED if controlled else 0) | (abi.FL_CRASHED if crashed else 0)
+        flags |= (int(agent) << abi.FL_AGENT_SHIFT) & abi.FL_AGENT_MASK
         if impact is not None:
             d[abi.D_IMPACT_X, e, s], d[abi.D_IMPACT_Y, e, s] = impact
             flags |= abi.FL_HAS_IMPACT
@@ -100,5 +106,7 @@ class SimState:
         i[abi.I_TARGET_LANE, e, s] = lane if target_lane is None else target_lane
         i[abi.I_FLAGS, e, s] = flags
         i[abi.I_SPEED_INDEX, e, s] = speed_index
-        i[abi.I_ROUTE_LEN, e, s], i[abi.I_ROUTE_ROAD, e, s], i[abi.I_ROUTE_LANE, e, s] = pack_route(route)
+        i[abi.I_ROUTE_LEN, e, s], rr, rl = pack_route(route)
+        for w in range(abi.ROUTE_WORDS):
+            i[abi.I_ROUTE_ROAD_WORDS[w], e, s], i[abi.I_ROUTE_LANE_WORDS[w], e, s] = rr[w], rl[w]
         i[abi.I_YIELD_TIMER, e, s] = yield_timer

@@ -13,7 +13,7 @@ import numpy as np
 from . import abi, scenes
 from ._gym import np_random as gym_np_random
 from ._gym import spaces
-from .reset import reset_intersection
+from .reset import reset_intersection, reset_roundabout, reset_uturn
 from .sim import Sim
 from .state import SimState
 
@@ -38,8 +38,10 @@ class _SimResetBackend:
 class TTRLVectorEnv:
     """
     :param num_envs: number of env instances on this device
-    :param scene: ``"highway"`` (synthetic multi-lane highway, BASELINE configs 2/3) or ``"intersection"``
-                  (``IntersectionEnv``, configs 1/4)
+    :param scene: ``"highway"`` (synthetic multi-lane highway, BASELINE configs 2/3), ``"intersection"``
+                  (``IntersectionEnv``, configs 1/4; ``config["controlled_vehicles"] = K > 1`` gives the multi-agent form:
+                  actions ``[E, K]``, observations ``[E, K, ...]``, ``info["agents_rewards"]`` / ``["agents_terminated"]``
+                  ``[E, K]``), ``"roundabout"`` (``RoundaboutEnv``) or ``"u-turn"`` (``UTurnEnv``)
     :param config: reference-style config dict, shallow-merged over the scene default (abstract.py:111-113)
     :param device: CUDA device index or ``"cuda:N"``
     :param seed: base seed; env e uses the stream keyed by ``first_env + e`` so shards reproduce a larger run
@@ -48,11 +50,14 @@ class TTRLVectorEnv:
                   by (seed, global env, episode)) at ``reset()`` and, with ``autoreset``, inside the step kernel when an
                   env finishes.  ``"host"``: the first reset is driven from the host with numpy ``Generator(PCG64)``
                   streams seeded like gymnasium (the reference's own reset for the intersection scene) and finished
-                  envs restart from that pool of initial states.
+                  envs restart from that pool of initial states.  Default: ``"device"`` for the highway and the
+                  intersection, ``"host"`` for the roundabout and the u-turn (their cast of vehicles is scripted on the
+                  host; the pool holds ``pool_factor`` initial states per env).
     """
 
     def __init__(self, num_envs: int, scene: str = "highway", config: Optional[dict] = None, device=0, seed: int = 0,
-                 first_env: int = 0, vcap: Optional[int] = None, autoreset: bool = True, reset_mode: str = "device") -> None:
+                 first_env: int = 0, vcap: Optional[int] = None, autoreset: bool = True, reset_mode: Optional[str] = None,
+                 pool_factor: int = 4) -> None:
         import torch
 
         if not torch.cuda.is_available():
@@ -80,14 +85,29 @@ class TTRLVectorEnv:
             # rejected when all slots are taken
             self.vcap = int(vcap or 24)
             routes = scenes.intersection_spawn_routes(self.net, self.table)
+        elif scene in ("roundabout", "u-turn"):
+            self.config = scenes.merged_config(scenes.ROUNDABOUT_CONFIG if scene == "roundabout" else scenes.UTURN_CONFIG, config)
+            self.net = scenes.make_roundabout_network() if scene == "roundabout" else scenes.make_uturn_network()
+            self.table = self.net.to_table()
+            self.cfg = scenes.build_config(self.table, self.config, scene, ego_lanes_count=1 if scene == "roundabout" else 2)
+            self.vcap = int(vcap or 16)
+            routes = None
         else:
             raise ValueError(f"unknown scene {scene!r}")
+        scripted = scene in ("roundabout", "u-turn")
+        if reset_mode is None:
+            reset_mode = "host" if scripted else "device"
         if reset_mode not in ("device", "host"):
             raise ValueError(f"unknown reset_mode {reset_mode!r}")
+        if scripted and reset_mode == "device":
+            raise NotImplementedError(f"the {scene} scene is reset from the host (reset_mode='host')")
         self.reset_mode = reset_mode
+        self.pool_factor = max(1, int(pool_factor))
         self.sim = Sim(self.cfg, self.table, self.num_envs, self.vcap, self.device_index, routes)
-        self.sim.set_reset_params(scenes.highway_reset_params(self.config) if scene == "highway"
-                                  else scenes.intersection_reset_params(self.config))
+        self.num_agents = self.sim.num_agents
+        if not scripted:
+            self.sim.set_reset_params(scenes.highway_reset_params(self.config) if scene == "highway"
+                                      else scenes.intersection_reset_params(self.config))
         self.autoreset = autoreset
         self.sim.set_autoreset(0 if not autoreset else (abi.AUTORESET_DEVICE if reset_mode == "device" else abi.AUTORESET_POOL))
         self.obs_shape = ((self.cfg.n_features, self.cfg.grid_w, self.cfg.grid_h) if self.cfg.obs_type == abi.OBS_GRID
@@ -95,7 +115,12 @@ class TTRLVectorEnv:
         n_actions = 5 if self.cfg.action_mode == abi.ACT_ALL else 3
         self.single_observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=self.obs_shape, dtype=np.float32)
         self.single_action_space = spaces.Discrete(n_actions)
-        E = self.num_envs
+        E, K = self.num_envs, self.num_agents
+        if K > 1:  # MultiAgentObservation: one observation per controlled vehicle
+            self.obs_shape = (K,) + self.obs_shape
+        self._agent_reward = torch.zeros((E, K), dtype=torch.float32, device=self.device)
+        self._agent_term = torch.zeros((E, K), dtype=torch.uint8, device=self.device)
+        self.sim.set_agent_outputs_ptr(self._agent_reward.data_ptr(), self._agent_term.data_ptr())
         self._obs = torch.zeros((E,) + self.obs_shape, dtype=torch.float32, device=self.device)
         self._reward = torch.zeros(E, dtype=torch.float32, device=self.device)
         self._term = torch.zeros(E, dtype=torch.uint8, device=self.device)
@@ -118,6 +143,18 @@ class TTRLVectorEnv:
         if self.scene == "highway":
             st = scenes.make_highway_state(self.num_envs, self.config, seed=self.seed_value, first_env=self.first_env, vcap=self.vcap)
             self.sim.set_state(st)
+        elif self.scene in ("roundabout", "u-turn"):
+            # pool entry p of this shard = the reference's reset(seed = seed + global index p); env e starts from entry e
+            n_pool = self.num_envs * self.pool_factor
+            rngs = [gym_np_random(self.seed_value + self.first_env * self.pool_factor + p)[0] for p in range(n_pool)]
+            make = reset_roundabout if self.scene == "roundabout" else reset_uturn
+            pool = make(rngs, self.net, self.table, self.config, self.cfg, self.vcap)
+            st = pool.slice_envs(0, self.num_envs)
+            self.sim.set_state(st)
+            self.sim.set_reset_pool(pool)
+            self._maybe_shuffle()
+            self.sim.observe_ptr(self._obs.data_ptr(), self._stream())
+            return self._obs, {}
         else:
             rngs = [gym_np_random(self.seed_value + self.first_env + e)[0] for e in range(self.num_envs)]
             st = reset_intersection(_SimResetBackend(self.sim), rngs, self.net, self.table, self.config, self.cfg)
@@ -129,13 +166,13 @@ class TTRLVectorEnv:
     def _maybe_shuffle(self) -> None:
         if self.cfg.obs_type == abi.OBS_KINEMATICS and self.cfg.order == abi.ORDER_SHUFFLED:
             m = self.cfg.obs_vehicles - 1
-            perm = np.argsort(self._shuffle_rng.random((self.num_envs, m)), axis=1)
+            perm = np.argsort(self._shuffle_rng.random((self.num_envs * self.num_agents, m)), axis=1)
             inv = np.empty_like(perm)
             np.put_along_axis(inv, perm, np.broadcast_to(np.arange(m), perm.shape), axis=1)
             self.sim.inject_shuffle(inv.astype(np.int32))
 
     def step(self, actions):
-        """actions: int tensor [E] on this device (int32 preferred; int64 is converted)."""
+        """actions: int tensor [E] (``[E, K]`` with K controlled vehicles) on this device (int32 preferred; int64 is converted)."""
         torch = self.torch
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions), device=self.device)
@@ -145,12 +182,21 @@ class TTRLVectorEnv:
         self._maybe_shuffle()
         self.sim.step_ptr(actions.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr(), self._term.data_ptr(),
                           self._trunc.data_ptr(), self._stream())
-        return self._obs, self._reward, self._term.bool(), self._trunc.bool(), {}
+        return self._obs, self._reward, self._term.bool(), self._trunc.bool(), self._info()
+
+    def _info(self) -> dict:
+        if self.num_agents == 1:
+            return {}
+        return {"agents_rewards": self._agent_reward, "agents_terminated": self._agent_term.bool()}
 
     def step_host(self, actions: np.ndarray, copy: bool = True):
         """numpy in / numpy out.  ``copy=False``: zero-copy views of the page-locked staging buffers (valid until the next call)."""
         obs, reward, term, trunc = self.sim.step_host(actions, copy=copy)
-        return obs.reshape((self.num_envs,) + self.obs_shape), reward, term.view(np.bool_), trunc.view(np.bool_), {}
+        info = {}
+        if self.num_agents > 1:
+            ar, at = self.sim.agent_outputs_host(copy=copy)
+            info = {"agents_rewards": ar, "agents_terminated": at.view(np.bool_)}
+        return obs.reshape((self.num_envs,) + self.obs_shape), reward, term.view(np.bool_), trunc.view(np.bool_), info
 
     def get_state(self) -> SimState:
         return self.sim.get_state()
