@@ -294,6 +294,10 @@ typedef struct ttrl_qnet_desc {
 int ttrl_qnet_create(const ttrl_qnet_desc* desc, const float* weights_host, int64_t n_weights,
                      int device, ttrl_qnet** out);
 int ttrl_qnet_destroy(ttrl_qnet* q);
+/* Replace all parameters (same blob layout as ttrl_qnet_create): the training driver refreshes the rollout network after
+ * optimiser steps (value_net of DQNAgent, pytorch.py:15-31).  on_device != 0: `weights` is a device pointer and the copy
+ * is enqueued on `stream`, ordered before later ttrl_qnet_act calls on that stream. */
+int ttrl_qnet_set_weights(ttrl_qnet* q, const float* weights, int64_t n_weights, int on_device, void* stream);
 /* Arithmetic of the forward pass.  FP32 (default): CUDA-core fp32 FMA, the parity path (actions bit-exact vs the
  * reference's torch CPU fp32 forward up to summation order).  TENSOR: the hidden GEMMs on the tcgen05 tensor cores
  * with BF16x3 split operands and FP32 accumulation in TMEM (MultiLayerPerceptron, two hidden layers); Q-values agree

@@ -1,0 +1,105 @@
+"""Batched DQN training driver and the JSON loaders on the GPU."""
+import json
+
+import numpy as np
+import pytest
+
+from topotrafficrl_b200 import factory
+from tests import common as T
+from tests.test_gpu_parity import _torch
+from tests.test_training_host import CONFIGS
+
+pytestmark = pytest.mark.gpu
+
+ENV_JSON = {  # scripts/configs/IntersectionEnv/env.json of the reference
+    "id": "intersection-v0", "import_module": "ttrl_env",
+    "observation": {"type": "Kinematics", "vehicles_count": 15, "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+                    "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]},
+                    "absolute": True, "order": "shuffled"},
+    "destination": "o1"}
+AGENT = {"__class__": "<class 'ttrl_agent.agents.deep_q_network.pytorch.DQNAgent'>", "gamma": 0.95, "n_steps": 1, "batch_size": 64,
+         "memory_capacity": 15000, "target_update": 16,
+         "exploration": {"method": "EpsilonGreedy", "tau": 15000, "temperature": 1.0, "final_temperature": 0.05}}
+
+
+def test_load_environment_single_env_from_reference_json(tmp_path):
+    """load_environment(path) -> a configured, reset single env whose seeded episode is the reference's (shuffled order:
+    the env's own numpy stream draws the row permutation, then the spawn)."""
+    p = tmp_path / "env.json"
+    p.write_text(json.dumps(ENV_JSON))
+    env = factory.load_environment(str(p))
+    assert env.import_module == "ttrl_env" and env.config["destination"] == "o1" and env.config["id"] == "intersection-v0"
+    assert env.observation_space.shape == (15, 7) and env.action_space.n == 3
+    g = T.golden("intersection_steps_kin.npz")  # generated with the default config == env.json
+    env.reset(seed=100)
+    for k in range(3):
+        obs, reward, term, trunc, info = env.step(int(g["action"][k]))
+        np.testing.assert_allclose(obs, g["obs"][k], rtol=0, atol=1e-5)
+        assert abs(reward - g["reward"][k]) <= 1e-6
+    env.close()
+
+
+@pytest.mark.parametrize("model", ["mlp", "ego2h", "dueling"])
+def test_batched_dqn_training_step_by_step(model, tmp_path):
+    torch = _torch()
+    env = factory.load_environment(ENV_JSON, num_envs=256, seed=5)
+    agent = factory.load_agent(dict(AGENT, model=CONFIGS[model]), env, seed=3)
+    assert agent.obs_shape == (15, 7) and agent.n_actions == 3 and agent.rollout.epsilon == 1.0
+    obs, _ = env.reset()
+    before = {k: v.clone() for k, v in agent.value_net.state_dict().items()}
+    for step in range(24):
+        prev = obs.clone()
+        actions = agent.act(prev)
+        assert actions.shape == (256,) and actions.dtype == torch.int32 and int(actions.min()) >= 0 and int(actions.max()) <= 2
+        obs, reward, term, trunc, _ = env.step(actions)
+        agent.record(prev, actions, reward, obs, term, trunc)
+    assert agent.steps == 24 and torch.isfinite(agent.last_loss)
+    assert agent.rollout.time == 24 * 256 and agent.rollout.epsilon < 1.0
+    assert len(agent.memory) > 20 * 256
+    changed = [k for k, v in agent.value_net.state_dict().items() if not torch.equal(v, before[k])]
+    assert len(changed) == len(before)
+    # the target network lags: copied at optimiser steps 16 (target_update), not since
+    assert any(not torch.equal(a, b) for a, b in zip(agent.target_net.state_dict().values(), agent.value_net.state_dict().values()))
+    # the rollout kernels carry the CURRENT value network: their Q-values == the torch forward of value_net
+    agent.eval()
+    a, q = agent.rollout.act(obs.reshape(-1, 15, 7), step_exploration_time=False, return_q=True)
+    with torch.no_grad():
+        want = agent.value_net(obs.reshape(-1, 15, 7))
+    np.testing.assert_allclose(q.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=5e-5)
+    gap = want.sort(dim=1, descending=True)[0]
+    clear = (gap[:, 0] - gap[:, 1]) > 1e-4
+    assert (a.long()[clear] == want.argmax(1)[clear]).all()
+    # checkpoint round trip in the reference's format
+    path = agent.save(str(tmp_path / "checkpoint.tar"))
+    ck = torch.load(path, map_location="cpu")
+    assert set(ck) == {"state_dict", "optimizer"} and set(ck["state_dict"]) == set(before)
+    other = factory.load_agent(dict(AGENT, model=CONFIGS[model]), env, seed=99)
+    other.load(path)
+    _, q2 = other.rollout.act(obs.reshape(-1, 15, 7), step_exploration_time=False, return_q=True)
+    np.testing.assert_allclose(q2.cpu().numpy(), q.cpu().numpy(), rtol=0, atol=1e-6)
+    agent.close(); other.close(); env.close()
+
+
+def test_batched_evaluation_multi_agent_and_learning_signal():
+    """BatchedEvaluation over the multi-agent intersection (K = 2 agents share one network, abstract.py:53-55) trains, logs
+    and then tests greedily; training lowers the Bellman loss on a fixed probe batch."""
+    torch = _torch()
+    from topotrafficrl_b200.trainer import BatchedEvaluation
+    env = factory.load_environment({"id": "intersection-multi-agent-v0", "import_module": "ttrl_env",
+                                    "observation": T.MULTI_AGENT["observation"], "controlled_vehicles": 2}, num_envs=512, seed=1)
+    assert env.num_agents == 2 and env.obs_shape == (2, 15, 7)
+    agent = factory.load_agent(dict(AGENT, model=CONFIGS["mlp"], batch_size=256), env, seed=0, updates_per_step=4)
+    ev = BatchedEvaluation(env, agent, num_steps=60)
+    out = ev.train(log_every=20)
+    assert out["env_steps"] == 60 * 512 and out["episodes"] > 512 and len(ev.history) == 3
+    assert agent.steps == 60 * 4 - 0 or agent.steps > 200
+    probe = agent.memory.sample(2048)
+    with torch.no_grad():
+        trained = float(agent.compute_bellman_residual(probe))
+    fresh = factory.load_agent(dict(AGENT, model=CONFIGS["mlp"], batch_size=256), env, seed=7)
+    with torch.no_grad():
+        untrained = float(fresh.compute_bellman_residual(probe))
+    assert trained < untrained
+    res = BatchedEvaluation(env, agent, num_steps=15).test()
+    assert agent.rollout.epsilon == 0.0 and res["episodes"] > 0 and np.isfinite(res["mean_return"])
+    agent.close(); fresh.close(); env.close()

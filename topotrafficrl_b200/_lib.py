@@ -70,6 +70,7 @@ def lib():
     L.ttrl_sim_read_stats.argtypes = [vp, C.POINTER(abi.EpisodeStats), i32]
     L.ttrl_qnet_create.argtypes = [C.POINTER(abi.QnetDesc), vp, i64, i32, C.POINTER(vp)]
     L.ttrl_qnet_destroy.argtypes = [vp]
+    L.ttrl_qnet_set_weights.argtypes = [vp, vp, i64, i32, vp]
     L.ttrl_qnet_set_mode.argtypes = [vp, i32]
     L.ttrl_qnet_act.argtypes = [vp, vp, i32, dbl, u64, u64, vp, vp, vp]
     L.ttrl_qnet_act_injected.argtypes = [vp, vp, i32, dbl, vp, vp, vp, vp]

@@ -92,6 +92,42 @@ def pack_weights(model_config: dict, state_dict: Dict[str, np.ndarray], obs_shap
     return d, blob
 
 
+def blob_keys(model_config: dict):
+    """State-dict keys in the order of the weight blob (``pack_weights``); ``*.weight`` entries are stored transposed
+    ([in][out]).  Used to rebuild the blob on the device from live torch parameters (``QNetRollout.load_parameters``)."""
+    mtype = model_config["type"]
+    keys = []
+
+    def dense(prefix, bias=True):
+        keys.append(prefix + ".weight")
+        if bias:
+            keys.append(prefix + ".bias")
+
+    if mtype == "MultiLayerPerceptron":
+        for k in range(len(model_config.get("layers", [64, 64]))):
+            dense(f"layers.{k}")
+        dense("predict")
+    elif mtype == "EgoAttentionNetwork":
+        n_emb = len(model_config["embedding_layer"].get("layers", [64, 64]))
+        for k in range(n_emb):
+            dense(f"ego_embedding.layers.{k}")
+        for k in range(n_emb):
+            dense(f"others_embedding.layers.{k}")
+        for name in ("key_all", "value_all", "query_ego", "attention_combine"):
+            dense(f"attention_layer.{name}", bias=False)
+        for k in range(len(model_config["output_layer"].get("layers", [64, 64]))):
+            dense(f"output_layer.layers.{k}")
+        dense("output_layer.predict")
+    elif mtype == "DuelingNetwork":
+        for k in range(len((model_config.get("base_module") or {}).get("layers", [64, 64]))):
+            dense(f"base_module.layers.{k}")
+        dense("value.predict")
+        dense("advantage.predict")
+    else:
+        raise ValueError("Unknown model type")
+    return keys
+
+
 class QNetRollout:
     """Batched ``agent.act``: obs [E, V, Fe] float32 on the device -> actions int32 [E] (and Q-values)."""
 
@@ -129,6 +165,20 @@ class QNetRollout:
             raise ValueError(f"unknown mode {mode!r}")
         check(self._L.ttrl_qnet_set_mode(self._h, self.MODES[mode]))
         self.mode = mode
+
+    def load_parameters(self, module, model_config: dict) -> None:
+        """Refresh the rollout network from a live torch module ON THE DEVICE (no host round trip): the blob is rebuilt with
+        torch ops on the current stream and copied into the library's weight buffer (``ttrl_qnet_set_weights``)."""
+        torch = self.torch
+        sd = dict(module.named_parameters())
+        parts = []
+        for key in blob_keys(model_config):
+            p = sd[key].detach()
+            parts.append((p.t().contiguous() if key.endswith(".weight") else p).reshape(-1))
+        blob = torch.cat(parts).to(dtype=torch.float32, device=self.device).contiguous()
+        stream = int(torch.cuda.current_stream(self.device).cuda_stream)
+        check(self._L.ttrl_qnet_set_weights(self._h, blob.data_ptr(), blob.numel(), 1, stream))
+        self._blob_keepalive = blob  # until the enqueued copy has run
 
     def close(self):
         if getattr(self, "_h", None):

@@ -923,6 +923,16 @@ int ttrl_qnet_set_mode(ttrl_qnet* q, int mode) {
     return 0;
 }
 
+int ttrl_qnet_set_weights(ttrl_qnet* q, const float* weights, int64_t n_weights, int on_device, void* stream) {
+    if (!q || !weights) return qfail("null argument");
+    if (n_weights != q->net.n_weights) return qfail("weight blob size does not match the network description");
+    QCK(cudaSetDevice(q->device));
+    QCK(cudaMemcpyAsync(q->d_weights, weights, sizeof(float) * n_weights, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                        (cudaStream_t)stream));
+    if (!on_device) QCK(cudaStreamSynchronize((cudaStream_t)stream));  // the host buffer may be reused by the caller
+    return 0;
+}
+
 int ttrl_qnet_destroy(ttrl_qnet* q) {
     if (!q) return 0;
     cudaSetDevice(q->device);

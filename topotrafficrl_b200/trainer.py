@@ -1,0 +1,258 @@
+"""Batched rollout / training driver: DQN over E lockstep envs on one B200.
+
+Replaces the reference's ``Evaluation.run_episodes`` loop (``ttrl_agent/trainer/evaluation.py:139-194``) and the training
+half of ``DQNAgent`` (``deep_q_network/abstract.py:37-63, 85-94``, ``deep_q_network/pytorch.py:32-93``) for a vector env:
+
+* acting: the CUDA Q-network kernels (``agent.QNetRollout``; epsilon-greedy on the device), never the torch modules;
+* stepping: ``TTRLVectorEnv.step`` (one launch per env-step of all E envs);
+* replay memory: a ring buffer of device tensors (``ReplayMemory.push`` / ``sample`` semantics, memory.py:25-52, n_steps = 1);
+* learning: double-DQN Bellman residual, loss per ``loss_function_factory``, gradient clamp to [-1, 1], Adam / RMSprop per
+  ``optimizer_factory`` (optimizers.py:152-173), target network copied every ``target_update`` optimiser steps -- torch
+  autograd on the modules of ``models.py``; with ``torch.distributed`` initialised the gradients are averaged over the
+  ranks (NCCL all-reduce: the one data-path collective of the whole system, as SURVEY.md section 8e anticipates);
+* checkpoints: ``{"state_dict", "optimizer"}`` like ``DQNAgent.save`` (pytorch.py:82-93), interchangeable with the reference.
+
+Differences from the reference, all forced by batching and stated here:
+* one ``record`` call pushes E (x K agents) transitions and performs ``updates_per_step`` optimiser steps (the reference
+  performs one per transition);
+* the exploration clock advances by E per vector step (one tick per collected env-step, like the reference);
+* finished envs are restarted inside the step kernel, so the observation after a TRUNCATED step belongs to the next
+  episode: such transitions (time-limit only; terminated ones do not bootstrap) are not stored.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Optional
+
+import numpy as np
+
+from .agent import QNetRollout
+from .factory import rec_update
+from .models import model_factory, size_model_config
+
+
+class DeviceReplayMemory:
+    """Ring buffer of transitions on the device: ``push`` appends a batch, ``sample`` draws uniformly without replacement
+    (``random.sample``, memory.py:47)."""
+
+    def __init__(self, capacity: int, obs_shape, device, generator) -> None:
+        import torch
+
+        self.torch, self.capacity, self.gen = torch, int(capacity), generator
+        self.state = torch.zeros((self.capacity,) + tuple(obs_shape), dtype=torch.float32, device=device)
+        self.next_state = torch.zeros_like(self.state)
+        self.action = torch.zeros(self.capacity, dtype=torch.int64, device=device)
+        self.reward = torch.zeros(self.capacity, dtype=torch.float32, device=device)
+        self.terminal = torch.zeros(self.capacity, dtype=torch.bool, device=device)
+        self.position = 0
+        self.size = 0
+
+    def __len__(self) -> int:
+        return self.size
+
+    def push(self, state, action, reward, next_state, terminal) -> None:
+        torch = self.torch
+        n = int(state.shape[0])
+        if n == 0:
+            return
+        if n > self.capacity:  # keep the newest
+            state, action, reward, next_state, terminal = (t[-self.capacity:] for t in (state, action, reward, next_state, terminal))
+            n = self.capacity
+        idx = (self.position + torch.arange(n, device=state.device)) % self.capacity
+        self.state[idx], self.next_state[idx] = state, next_state
+        self.action[idx], self.reward[idx], self.terminal[idx] = action.to(torch.int64), reward, terminal
+        self.position = (self.position + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def sample(self, batch_size: int):
+        idx = self.torch.randperm(self.size, device=self.state.device, generator=self.gen)[:batch_size]
+        return self.state[idx], self.action[idx], self.reward[idx], self.next_state[idx], self.terminal[idx]
+
+
+class BatchedDQNAgent:
+    """``DQNAgent`` for a vector env.  ``env``: a :class:`TTRLVectorEnv` (or anything with ``num_envs``, ``obs_shape``,
+    ``num_agents``, ``single_action_space``, ``device``)."""
+
+    @classmethod
+    def default_config(cls) -> dict:  # deep_q_network/abstract.py:21-35
+        return dict(model=dict(type="DuelingNetwork"), optimizer=dict(type="ADAM", lr=5e-4, weight_decay=0, k=5),
+                    loss_function="l2", memory_capacity=50000, batch_size=100, gamma=0.99, device="cuda:best",
+                    exploration=dict(method="EpsilonGreedy"), target_update=1, double=True, n_steps=1)
+
+    def __init__(self, env, config: Optional[dict] = None, seed: int = 0, rollout_mode: str = "fp32",
+                 updates_per_step: int = 1, refresh_every: int = 1) -> None:
+        import torch
+        from torch.nn import functional as F
+
+        self.torch, self.env = torch, env
+        self.config = rec_update(self.default_config(), copy.deepcopy(config or {}))
+        if int(self.config.get("n_steps", 1)) != 1:
+            raise NotImplementedError("n-step returns are not used by the shipped agent configs (n_steps: 1)")
+        self.device = env.device
+        self.num_envs, self.K = int(env.num_envs), int(getattr(env, "num_agents", 1))
+        self.obs_shape = tuple(env.obs_shape[1:]) if self.K > 1 else tuple(env.obs_shape)
+        self.n_actions = int(env.single_action_space.n)
+        self.model_config = size_model_config(self.obs_shape, self.n_actions, self.config["model"])
+        torch.manual_seed(seed)
+        self.value_net = model_factory(self.model_config).to(self.device)
+        self.target_net = model_factory(self.model_config).to(self.device)
+        self.target_net.load_state_dict(self.value_net.state_dict())
+        self.target_net.eval()
+        losses = {"l2": F.mse_loss, "l1": F.l1_loss, "smooth_l1": F.smooth_l1_loss, "bce": F.binary_cross_entropy}
+        if self.config["loss_function"] not in losses:
+            raise ValueError("Unknown loss function : {}".format(self.config["loss_function"]))
+        self.loss_function = losses[self.config["loss_function"]]
+        opt = self.config["optimizer"]
+        if opt["type"] == "ADAM":
+            self.optimizer = torch.optim.Adam(self.value_net.parameters(), lr=opt["lr"], weight_decay=opt["weight_decay"])
+        elif opt["type"] == "RMS_PROP":
+            self.optimizer = torch.optim.RMSprop(self.value_net.parameters(), weight_decay=opt["weight_decay"])
+        elif opt["type"] == "RANGER":
+            raise NotImplementedError("the RANGER optimiser is not used by the shipped agent configs")
+        else:
+            raise ValueError("Unknown optimizer type: {}".format(opt["type"]))
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(seed)
+        self.memory = DeviceReplayMemory(self.config["memory_capacity"], self.obs_shape, self.device, self.gen)
+        self.rollout = QNetRollout(self.model_config, self.value_net.state_dict(), self.obs_shape, self.n_actions,
+                                   device=self.device.index or 0, exploration=self.config["exploration"], seed=seed, mode=rollout_mode)
+        self.updates_per_step, self.refresh_every = int(updates_per_step), int(refresh_every)
+        self.steps = 0          # optimiser steps (update_target_network's counter, abstract.py:91-94)
+        self.training = True
+        self.last_loss = None
+
+    # ---- acting ---------------------------------------------------------------------------------------------
+    def act(self, obs, step_exploration_time: bool = True):
+        """obs ``[E, (K,) V, F]`` on the device -> int32 actions ``[E]`` / ``[E, K]`` (abstract.py:65-83: every agent of a
+        multi-agent observation acts with the same network; the exploration clock ticks once per env-step)."""
+        if step_exploration_time:
+            self.rollout.time += self.num_envs
+        flat = obs.reshape((-1,) + self.obs_shape)
+        a = self.rollout.act(flat, step_exploration_time=False)
+        return a.view(self.num_envs, self.K) if self.K > 1 else a
+
+    def eval(self) -> None:
+        self.training = False
+        self.rollout.eval()
+
+    # ---- learning -------------------------------------------------------------------------------------------
+    def record(self, state, action, reward, next_state, terminated, truncated=None) -> None:
+        """``AbstractDQNAgent.record`` (abstract.py:37-63) for a batch of E transitions."""
+        if not self.training:
+            return
+        torch = self.torch
+        keep = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
+        if truncated is not None:
+            keep = ~(truncated.bool() & ~terminated.bool())  # next_state of a time-limit end belongs to the next episode
+        K = self.K
+        s = state.reshape((self.num_envs, K) + self.obs_shape)[keep].reshape((-1,) + self.obs_shape)
+        ns = next_state.reshape((self.num_envs, K) + self.obs_shape)[keep].reshape((-1,) + self.obs_shape)
+        a = action.reshape(self.num_envs, K)[keep].reshape(-1)
+        r = reward[keep].repeat_interleave(K)               # the aggregated reward is shared by the agents (abstract.py:53-55)
+        t = terminated.bool()[keep].repeat_interleave(K)
+        self.memory.push(s, a, r, ns, t)
+        for _ in range(self.updates_per_step):
+            if len(self.memory) < self.config["batch_size"]:
+                return
+            loss = self.compute_bellman_residual(self.memory.sample(self.config["batch_size"]))
+            self.step_optimizer(loss)
+            self.update_target_network()
+            self.last_loss = loss.detach()
+        if self.steps % self.refresh_every == 0:
+            self.rollout.load_parameters(self.value_net, self.model_config)
+
+    def compute_bellman_residual(self, batch):
+        """pytorch.py:41-73: double-DQN target from the target network, terminal states do not bootstrap."""
+        torch = self.torch
+        state, action, reward, next_state, terminal = batch
+        q = self.value_net(state).gather(1, action.unsqueeze(1)).squeeze(1)
+        with torch.no_grad():
+            next_values = torch.zeros_like(reward)
+            if self.config["double"]:
+                best_actions = self.value_net(next_state).max(1)[1]
+                best_values = self.target_net(next_state).gather(1, best_actions.unsqueeze(1)).squeeze(1)
+            else:
+                best_values = self.target_net(next_state).max(1)[0]
+            next_values[~terminal] = best_values[~terminal]
+            target = reward + self.config["gamma"] * next_values
+        return self.loss_function(q, target)
+
+    def step_optimizer(self, loss) -> None:
+        """pytorch.py:32-39 (+ gradient averaging over the ranks when torch.distributed is initialised)."""
+        torch = self.torch
+        self.optimizer.zero_grad()
+        loss.backward()
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            grads = [p.grad for p in self.value_net.parameters() if p.grad is not None]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat)
+            flat /= dist.get_world_size()
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        for p in self.value_net.parameters():
+            if p.grad is not None:
+                p.grad.data.clamp_(-1, 1)
+        self.optimizer.step()
+
+    def update_target_network(self) -> None:
+        self.steps += 1
+        if self.steps % self.config["target_update"] == 0:
+            self.target_net.load_state_dict(self.value_net.state_dict())
+
+    # ---- checkpoints (pytorch.py:82-93) -------------------------------------------------------------------------
+    def save(self, filename):
+        self.torch.save({"state_dict": self.value_net.state_dict(), "optimizer": self.optimizer.state_dict()}, filename)
+        return filename
+
+    def load(self, filename):
+        checkpoint = self.torch.load(filename, map_location=self.device)
+        self.value_net.load_state_dict(checkpoint["state_dict"])
+        self.target_net.load_state_dict(checkpoint["state_dict"])
+        self.optimizer.load_state_dict(checkpoint["optimizer"])
+        self.rollout.load_parameters(self.value_net, self.model_config)
+        return filename
+
+    def close(self) -> None:
+        self.rollout.close()
+
+
+class BatchedEvaluation:
+    """The ``Evaluation.train`` / ``test`` loop (evaluation.py:115-161) for a vector env: no per-episode Python loop -- the
+    envs restart on the device and episode statistics are accumulated there (``TTRLVectorEnv.stats``)."""
+
+    def __init__(self, env, agent: BatchedDQNAgent, num_steps: int = 1000, training: bool = True) -> None:
+        self.env, self.agent, self.num_steps, self.training = env, agent, int(num_steps), training
+        self.observation = None
+        self.history = []
+
+    def train(self, log_every: int = 0) -> dict:
+        self.training = True
+        return self._run(log_every)
+
+    def test(self) -> dict:
+        self.training = False
+        self.agent.eval()
+        return self._run(0)
+
+    def _run(self, log_every: int) -> dict:
+        env, agent = self.env, self.agent
+        obs, _ = env.reset()
+        env.stats(reset=True)
+        for step in range(self.num_steps):
+            prev = obs.clone()
+            actions = agent.act(prev)
+            obs, reward, terminated, truncated, info = env.step(actions)
+            if self.training:
+                agent.record(prev, actions, reward, obs, terminated, truncated)
+            if log_every and (step + 1) % log_every == 0:
+                s = env.stats()
+                self.history.append(dict(step=step + 1, episodes=s["episodes"], mean_return=s["total_return"] / max(s["episodes"], 1),
+                                         crash_rate=s["crashes"] / max(s["episodes"], 1), epsilon=agent.rollout.epsilon,
+                                         loss=None if agent.last_loss is None else float(agent.last_loss)))
+        s = env.stats()
+        n = max(s["episodes"], 1)
+        return dict(episodes=s["episodes"], mean_return=s["total_return"] / n, mean_length=s["total_length"] / n,
+                    crash_rate=s["crashes"] / n, arrival_rate=s["arrivals"] / n, env_steps=s["env_steps"])
