@@ -61,6 +61,21 @@ WORKLOADS = {
     "intersection_qnet_mlp": dict(scene="intersection", E=8192, n=24, over=None, qnet="mlp",
                                   label="configs[3]: intersection 8192 envs + DQN MLP [128,128] Q-net rollout in the loop",
                                   bytes_per_env_step=24 * 128 + 4 + 420 + 8 + 420 + 4, n_actions=3),
+    # SURVEY.md section 8 rows A29 / N3 (not BASELINE configs; parity cases with a throughput line)
+    "multiagent": dict(scene="intersection", E=8192, n=24, agents=4,
+                       over={"controlled_vehicles": 4, "initial_vehicle_count": 5,
+                             "action": {"type": "MultiAgentAction", "action_config": {"type": "DiscreteMetaAction", "lateral": False, "longitudinal": True}},
+                             "observation": {"type": "MultiAgentObservation", "observation_config": {
+                                 "type": "Kinematics", "vehicles_count": 15, "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+                                 "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]}, "absolute": True}}},
+                       label="multi-agent intersection (env_multi_agent.json): 8192 envs x 4 controlled vehicles, 4 Kinematics obs per env",
+                       bytes_per_env_step=24 * 128 + 4 * 4 + 4 * 420 + 8 + 4 * 5, n_actions=3),
+    "roundabout": dict(scene="roundabout", E=8192, n=16, over=None, scripted=True,
+                       label="roundabout-v0: 8192 envs x 5 vehicles, 32-lane network (arcs + sine lanes), Kinematics 5x5 obs",
+                       bytes_per_env_step=5 * 128 + 4 + 100 + 8, n_actions=5),
+    "uturn": dict(scene="u-turn", E=8192, n=16, scripted=True,
+                  over={"observation": {"type": "Kinematics", "vehicles_count": 6, "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"]}},
+                  label="u-turn-v0: 8192 envs x 7 vehicles, Kinematics 6x7 obs", bytes_per_env_step=7 * 128 + 4 + 168 + 8, n_actions=5),
 }
 
 QNET_CONFIGS = {  # scripts/configs/IntersectionEnv/agents/DQNAgent/{ego_attention_2h,baseline}.json of the reference
@@ -279,10 +294,11 @@ def run_ours(args, w):
                          vcap=(args.vcap or w["n"]), reset_mode=args.reset_mode)
     venv.reset()
     sim = venv.sim
+    A = sim.num_agents  # controlled vehicles per env: actions are [E, A]
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    actions = torch.randint(0, w["n_actions"], (W + K, E), dtype=torch.int32, device=dev, generator=gen)
+    actions = torch.randint(0, w["n_actions"], (W + K, E * A), dtype=torch.int32, device=dev, generator=gen)
     obs = torch.zeros(E * sim.obs_size, dtype=torch.float32, device=dev)
     rew = torch.zeros(E, dtype=torch.float32, device=dev)
     term = torch.zeros(E, dtype=torch.uint8, device=dev)
@@ -362,8 +378,8 @@ def run_ours(args, w):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_v, op=dist.ReduceOp.SUM)
-    h2d = E * 4 + (E * sim.obs_size * 4 if qnet is not None else 0)
-    d2h = E * (sim.obs_size * 4 + 4 + 2)
+    h2d = E * A * 4 + (E * sim.obs_size * 4 if qnet is not None else 0)
+    d2h = E * (sim.obs_size * 4 + 4 + 2) + (E * A * 5 if A > 1 else 0)  # + per-agent rewards / terminal flags
 
     if rank == 0:
         hbm_peak, peak_kind = _peaks()

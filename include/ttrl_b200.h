@@ -159,10 +159,25 @@ typedef struct ttrl_episode_stats {
  * keyed by (seed, global env, episode, draw), following the reference's procedures:
  *   scene 0: synthetic highway, Vehicle.create_random's placement rule (kinematics.py:50-104) + randomize_behavior;
  *   scene 1: IntersectionEnv._make_vehicles (intersection_env.py:251-318): staggered spawn attempts, warm-up
- *            sub-steps, challenger, MDPVehicle ego with its route, pruning of vehicles within 20 m of the ego. */
+ *            sub-steps, challenger, MDPVehicle ego with its route, pruning of vehicles within 20 m of the ego;
+ *   scene 2: a scripted cast -- RoundaboutEnv._make_vehicles (roundabout_env.py:326-387), UTurnEnv._make_vehicles
+ *            (u_turn_env.py:173-271): every member is made on a lane at longitudinal + N(0, 1) * std with speed + N(0, 1) *
+ *            std (RoadObject.make_on_lane objects.py:67-89), takes the closest lane at that pose (objects.py:45-50), plans
+ *            a route to a fixed or uniformly drawn destination (controller.py:71-87) and optionally draws its DELTA. */
 #define TTRL_MAX_SPAWN_ATTEMPTS 32
+#define TTRL_MAX_CAST 8
+#define TTRL_CAST_DEST 4
+typedef struct ttrl_cast_member {
+    int32_t lane;        /* flat index of the lane the member is made on */
+    int32_t mdp;         /* 1: the controlled MDPVehicle (no draws); 0: IDMVehicle */
+    int32_t n_dest;      /* 0: route None; 1: dest[0]; > 1: np_random.choice over dest[0..n_dest-1] */
+    int32_t randomize;   /* randomize_behavior(): DELTA ~ U[3.5, 4.5] (behavior.py:66-69), else the class default 4.0 */
+    int32_t dest[TTRL_CAST_DEST];  /* destination ids = columns of cast_route_* */
+    double longitudinal, longitudinal_std, speed, speed_std;
+    double heading_longitudinal;   /* heading = lane.heading_at(this) (the roundabout's ego: position at 125, heading at 140) */
+} ttrl_cast_member;
 typedef struct ttrl_reset_params {
-    int32_t scene;            /* 0 highway, 1 intersection */
+    int32_t scene;            /* 0 highway, 1 intersection, 2 scripted cast (roundabout, u-turn) */
     int32_t n_vehicles;       /* highway: vehicles per env incl. the ego; intersection: initial_vehicle_count */
     int32_t lanes;            /* highway: lanes of road 0 */
     int32_t ego_entry;        /* intersection: corner of ego 0's start lane (o<k>, ir<k>, 0); ego j starts on corner (k + j) % 4 */
@@ -172,6 +187,11 @@ typedef struct ttrl_reset_params {
     double speed_limit, density, ego_spacing, ego_speed;          /* highway */
     double ego_longitudinal, ego_longitudinal_std;                /* intersection: 60 + 5 * N(1, 1) -> 60, 5 */
     double spawn_longitudinal[TTRL_MAX_SPAWN_ATTEMPTS];           /* intersection: np.linspace(0, 80, n)[t] */
+    /* scene 2: the cast (n_vehicles members, list order) and, per (road of the member's closest lane, destination id), the
+     * roads plan_route_to appends after the member's own lane (BFS of road.py:159-188 done on the host) */
+    ttrl_cast_member cast[TTRL_MAX_CAST];
+    uint8_t cast_route_len[TTRL_MAX_ROADS][TTRL_CAST_DEST];
+    uint8_t cast_route_road[TTRL_MAX_ROADS][TTRL_CAST_DEST][TTRL_ROUTE_CAP];
 } ttrl_reset_params;
 
 typedef struct ttrl_sim ttrl_sim;

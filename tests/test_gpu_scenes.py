@@ -174,14 +174,13 @@ def test_scripted_env_episodes_match_reference(scene, env_id, over):
             make(env_id)
 
 
-@pytest.mark.parametrize("scene", ["roundabout", "u-turn"])
-def test_scripted_vector_env_vs_oracle(scene):
-    """1024 envs from the host-generated pool, free-running with autoreset from the pool: device == oracle."""
+@pytest.mark.parametrize("scene,reset_mode,E", [("roundabout", "device", 1024), ("u-turn", "device", 1024), ("roundabout", "host", 256)])
+def test_scripted_vector_env_vs_oracle(scene, reset_mode, E):
+    """Free-running envs with autoreset (fresh device-side episodes, or the host-generated pool): device == oracle."""
     torch = _torch()
     from oracle import oracle as O
     from topotrafficrl_b200 import TTRLVectorEnv
-    E = 1024
-    env = TTRLVectorEnv(E, scene, config=T.UTURN_KIN if scene == "u-turn" else None, seed=11, pool_factor=2)
+    env = TTRLVectorEnv(E, scene, config=T.UTURN_KIN if scene == "u-turn" else None, seed=11, pool_factor=2, reset_mode=reset_mode)
     obs, _ = env.reset()
     orc = O.Oracle(env.cfg, env.table, threads=8)
     st = env.get_state()

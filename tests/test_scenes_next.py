@@ -112,3 +112,56 @@ def test_scripted_scene_reset_vs_reference(scene):
     np.testing.assert_allclose(obs.reshape(g["reset_obs"].shape), g["reset_obs"], rtol=0, atol=2e-6)
     if scene == "roundabout":
         assert g["reset_vi"][:, abi.I_ROUTE_LEN].max() > 4  # routes beyond one 4-entry word
+
+
+class _CastDrawRng:
+    """Feeds ``reset_roundabout`` / ``reset_uturn`` (validated against the reference's resets above) with the draws the
+    DEVICE-side scripted reset makes for one env (ttrl_core.cuh: reset_cast), member by member."""
+
+    def __init__(self, emu, seed, env, episode):
+        self.emu, self.seed, self.env, self.episode = emu, seed, env, episode
+        self.member, self.calls = 0, 0
+
+    def _u(self, which):
+        return self.emu.reset_uniforms(self.seed, self.env, self.episode, 0x200 + which + 2 * self.member)
+
+    def normal(self):
+        if self.calls % 2 == 0:
+            self.member += 1  # a new cast member: its longitudinal draw comes first (member 0 is the ego: no draws)
+        self.calls += 1
+        u0, u1 = self._u(0)
+        rad = np.sqrt(-2.0 * np.log(1.0 - u0))
+        return rad * np.cos(2 * np.pi * u1) if self.calls % 2 == 1 else rad * np.sin(2 * np.pi * u1)
+
+    def choice(self, seq):
+        ud, _ = self._u(1)
+        return seq[min(int(ud * len(seq)), len(seq) - 1)]
+
+    def uniform(self, low, high):
+        _, ue = self._u(1)
+        return low + ue * (high - low)
+
+
+@pytest.mark.parametrize("scene", ["roundabout", "u-turn"])
+def test_device_cast_reset_follows_make_vehicles(scene):
+    """Device-side scripted reset (emulated device logic) == the host reset fed the same draws; keyed by the global env."""
+    net, table, cfg, cfgd = T.roundabout_scene() if scene == "roundabout" else T.uturn_scene()
+    emu = Emulator(cfg, table)
+    emu.set_reset_params(scenes.cast_reset_params(scene, net, table, cfgd))
+    E, seed, first, episode = 24, 41, 500, 2
+    got = SimState.zeros(E, 16)
+    emu.reset(got, seed, first, episode)
+    rngs = [_CastDrawRng(emu, seed, first + e, episode) for e in range(E)]
+    want = (reset_roundabout if scene == "roundabout" else reset_uturn)(rngs, net, table, cfgd, cfg, 16)
+    want.env_i[abi.EI_EPISODE] = episode
+    T.compare_states(got, want, 1e-12, f"{scene} device reset")
+    assert (got.env_i[abi.EI_NVEH] == (5 if scene == "roundabout" else 7)).all() and (got.env_i[abi.EI_EGO] == 0).all()
+    half = SimState.zeros(E // 2, 16)
+    emu.reset(half, seed, first + E // 2, episode)
+    np.testing.assert_array_equal(half.veh_d, got.veh_d[:, E // 2:])      # shard invariance
+    if scene == "roundabout":
+        dests = {table.road_keys[unpack_route(got.veh_i[abi.I_ROUTE_LEN, e, 1], [got.veh_i[w, e, 1] for w in abi.I_ROUTE_ROAD_WORDS],
+                                              [got.veh_i[w, e, 1] for w in abi.I_ROUTE_LANE_WORDS])[-1][0]][1] for e in range(E)}
+        assert dests == {"exr", "sxr", "nxr"}                                 # the destination draw covers all three exits
+        fixed = scenes.cast_reset_params(scene, net, table, dict(cfgd, incoming_vehicle_destination=1))
+        assert fixed.cast[1].n_dest == 1 and fixed.cast[1].dest[0] == 1

@@ -93,7 +93,16 @@ class SpawnDraw(C.Structure):
 
 
 MAX_SPAWN_ATTEMPTS = 32
+MAX_CAST = 8
+CAST_DEST = 4
 AUTORESET_OFF, AUTORESET_POOL, AUTORESET_DEVICE = 0, 1, 2
+
+
+class CastMember(C.Structure):
+    _fields_ = [("lane", C.c_int32), ("mdp", C.c_int32), ("n_dest", C.c_int32), ("randomize", C.c_int32),
+                ("dest", C.c_int32 * CAST_DEST),
+                ("longitudinal", C.c_double), ("longitudinal_std", C.c_double), ("speed", C.c_double), ("speed_std", C.c_double),
+                ("heading_longitudinal", C.c_double)]
 
 
 class ResetParams(C.Structure):
@@ -101,7 +110,10 @@ class ResetParams(C.Structure):
                 ("destination", C.c_int32), ("warmup_substeps", C.c_int32), ("pad0", C.c_int32), ("pad1", C.c_int32),
                 ("speed_limit", C.c_double), ("density", C.c_double), ("ego_spacing", C.c_double), ("ego_speed", C.c_double),
                 ("ego_longitudinal", C.c_double), ("ego_longitudinal_std", C.c_double),
-                ("spawn_longitudinal", C.c_double * MAX_SPAWN_ATTEMPTS)]
+                ("spawn_longitudinal", C.c_double * MAX_SPAWN_ATTEMPTS),
+                ("cast", CastMember * MAX_CAST),
+                ("cast_route_len", (C.c_uint8 * CAST_DEST) * MAX_ROADS),
+                ("cast_route_road", ((C.c_uint8 * ROUTE_CAP) * CAST_DEST) * MAX_ROADS)]
 
 
 class EpisodeStats(C.Structure):

@@ -1773,9 +1773,68 @@ TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int e
     rebuild_tables(c, ex);
 }
 
+// Scripted cast: RoundaboutEnv._make_vehicles (roundabout_env.py:326-387), UTurnEnv._make_vehicles (u_turn_env.py:173-271).
+// The members are independent of each other, one task each.  Draws of member m: stream index 0x200 + 2m -> the two normals
+// (Box-Muller pair: longitudinal, speed), 0x201 + 2m -> destination choice and DELTA.
+template <class C, class Exec>
+TT_HD void reset_cast(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) {
+    auto* st = c.st;
+    const SceneDev* sc = c.sc;
+    const ttrl_reset_params& rp = sc->rp;
+    const ttrl_config& cfg = sc->cfg;
+    reset_scalars(c, ex, episode);
+    const int n = rp.n_vehicles < c.vcap ? rp.n_vehicles : c.vcap;
+    ex.parn(n, [&](int s) {
+        const ttrl_cast_member& m = rp.cast[s];
+        double u0, u1, ud, ue;
+        reset_uniforms(seed, genv, episode, 0x200u + 2u * s, u0, u1);
+        reset_uniforms(seed, genv, episode, 0x201u + 2u * s, ud, ue);
+        const double rad = sqrt(-2.0 * log(1.0 - u0));
+        const double z_lon = rad * cos(2 * kPi * u1), z_speed = rad * sin(2 * kPi * u1);
+        const ttrl_lane& l = c.lanes[m.lane];
+        const double lon = m.mdp ? m.longitudinal : m.longitudinal + z_lon * m.longitudinal_std;
+        const double speed = m.mdp ? m.speed : m.speed + z_speed * m.speed_std;
+        double px, py;
+        lane_position(l, lon, 0.0, px, py);                                   // make_on_lane objects.py:67-89
+        const double hd = lane_heading_at(l, m.mdp ? m.heading_longitudinal : lon);
+        st->pos[s] = d2{px, py}; st->h[s] = hd; st->v[s] = speed;
+        st->cs[s] = d2{cos(hd), sin(hd)};
+        uint64_t mask;
+        const int ln = table_row_and_closest(c, s, mask);                     // RoadObject.__init__ objects.py:45-50
+        st->lane[s] = ln; st->tlane[s] = ln;
+        st->tspeed[s] = speed;                                                // controller.py:47
+        if (m.mdp) {                                                          // MDPVehicle.__init__ controller.py:283-293
+            st->flags[s] = TTRL_FL_MDP | TTRL_FL_CONTROLLED;
+            st->sidx[s] = speed_to_index(cfg, speed);
+            st->tspeed[s] = cfg.target_speeds[st->sidx[s]];
+            st->delta[s] = 4.0;
+        } else {
+            st->timer[s] = py_mod1((px + py) * kPi);                          // behavior.py:64
+            st->delta[s] = m.randomize ? 3.5 + ue * (4.5 - 3.5) : 4.0;        // behavior.py:66-69
+        }
+        if (m.n_dest <= 0) { st->rlen[s] = -1; return; }                      // route None
+        int k = m.n_dest == 1 ? 0 : (int)(ud * m.n_dest);                     // np_random.choice(destinations)
+        if (k > m.n_dest - 1) k = m.n_dest - 1;
+        const int dest = m.dest[k], road = c.lanes[ln].road;
+        const int nr = rp.cast_route_len[road][dest];                         // plan_route_to controller.py:71-87
+        Route q{};
+        route_set(q, 0, road, c.lanes[ln].lane_id);
+        for (int j = 0; j < nr && j + 1 < TTRL_ROUTE_CAP; ++j) route_set(q, j + 1, rp.cast_route_road[road][dest][j], -1);
+        route_store(st, s, q);
+        st->rlen[s] = 1 + nr;
+    });
+    if (ex.first()) {
+        st->n = n;
+        for (int s = 0; s < n; ++s) if (rp.cast[s].mdp) { st->ego = s; st->egos[0] = s; }
+    }
+    ex.sync();
+    rebuild_tables(c, ex);
+}
+
 template <class C, class Exec>
 TT_HDN void env_reset(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode, bool aligned = false) {  // cold path: keep it out of the step loop's code
     if (c.sc->rp.scene == 1) reset_intersection(c, ex, seed, genv, episode, aligned);
+    else if (c.sc->rp.scene == 2) reset_cast(c, ex, seed, genv, episode);
     else reset_highway(c, ex, seed, genv, episode);
 }
 

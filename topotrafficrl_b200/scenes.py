@@ -450,3 +450,54 @@ def intersection_reset_params(config: dict) -> abi.ResetParams:
     rp.warmup_substeps = 3 * int(config["simulation_frequency"])
     rp.ego_longitudinal, rp.ego_longitudinal_std = 60.0, 5.0
     return rp
+
+
+# (lane the member is made on, longitudinal, speed, randomize_behavior, destinations) -- roundabout_env.py:326-387
+_ROUNDABOUT_DESTINATIONS = ["exr", "sxr", "nxr"]
+_ROUNDABOUT_CAST = [(("we", "sx", 1), 5, 16, True), (("we", "sx", 0), 20 * 1, 16, True), (("we", "sx", 0), 20 * -1, 16, True),
+                    (("eer", "ees", 0), 50, 16, True)]
+# u_turn_env.py:173-271 (only vehicle 1 randomises its behaviour)
+_UTURN_CAST = [(("a", "b", 0), 25, 13.5, True), (("a", "b", 1), 56, 14.5, False), (("b", "c", 1), 0.5, 4.5, False),
+               (("b", "c", 0), 17.5, 5.5, False), (("c", "d", 0), 1, 3.5, False), (("c", "d", 1), 30, 5.5, False)]
+
+
+def cast_reset_params(scene: str, net: RoadNetwork, table: NetworkTable, config: dict) -> abi.ResetParams:
+    """Device-side reset of the scripted scenes (``ttrl_reset_params.scene == 2``): the cast of ``RoundaboutEnv._make_vehicles``
+    / ``UTurnEnv._make_vehicles`` and the route table ``plan_route_to`` would produce from any road to each destination."""
+    rp = abi.ResetParams()
+    rp.scene = 2
+    if scene == "roundabout":
+        destinations = list(_ROUNDABOUT_DESTINATIONS) + ["nxs"]
+        ego = (("ser", "ses", 0), 125.0, 8.0, 140.0, destinations.index("nxs"))
+        fixed = config.get("incoming_vehicle_destination")
+        members = []
+        for k, (lane, lon, speed, rnd) in enumerate(_ROUNDABOUT_CAST):
+            dest = [fixed] if (k == 0 and fixed is not None) else [0, 1, 2]
+            members.append((lane, lon, 2.0, speed, 2.0, rnd, dest))
+    elif scene == "u-turn":
+        destinations = ["d"]
+        ego = (("a", "b", 0), 0.0, 16.0, 0.0, 0)
+        members = [(lane, lon, 2.0, speed, 2.0, rnd, [0]) for lane, lon, speed, rnd in _UTURN_CAST]
+    else:
+        raise ValueError(f"no scripted cast for scene {scene!r}")
+    assert len(destinations) <= abi.CAST_DEST and 1 + len(members) <= abi.MAX_CAST
+    m = rp.cast[0]
+    m.lane, m.mdp, m.n_dest, m.randomize = table.flat(ego[0]), 1, 1, 0
+    m.dest[0] = ego[4]
+    m.longitudinal, m.speed, m.heading_longitudinal = ego[1], ego[2], ego[3]
+    for k, (lane, lon, lon_std, speed, speed_std, rnd, dest) in enumerate(members, start=1):
+        m = rp.cast[k]
+        m.lane, m.mdp, m.n_dest, m.randomize = table.flat(lane), 0, len(dest), int(rnd)
+        for j, d in enumerate(dest):
+            m.dest[j] = int(d)
+        m.longitudinal, m.longitudinal_std, m.speed, m.speed_std = float(lon), float(lon_std), float(speed), float(speed_std)
+    rp.n_vehicles = 1 + len(members)
+    for r, (_from, _to) in enumerate(table.road_keys):
+        for d, name in enumerate(destinations):
+            route = net.plan_route((_from, _to, 0), name)[1:]
+            if len(route) + 1 > abi.ROUTE_CAP:
+                raise ValueError("planned route exceeds the device route capacity")
+            rp.cast_route_len[r][d] = len(route)
+            for j, (f, t, _) in enumerate(route):
+                rp.cast_route_road[r][d][j] = table.road_index_of[(f, t)]
+    return rp

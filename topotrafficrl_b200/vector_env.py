@@ -50,9 +50,8 @@ class TTRLVectorEnv:
                   by (seed, global env, episode)) at ``reset()`` and, with ``autoreset``, inside the step kernel when an
                   env finishes.  ``"host"``: the first reset is driven from the host with numpy ``Generator(PCG64)``
                   streams seeded like gymnasium (the reference's own reset for the intersection scene) and finished
-                  envs restart from that pool of initial states.  Default: ``"device"`` for the highway and the
-                  intersection, ``"host"`` for the roundabout and the u-turn (their cast of vehicles is scripted on the
-                  host; the pool holds ``pool_factor`` initial states per env).
+                  envs restart from that pool of initial states (roundabout / u-turn: ``pool_factor`` initial states
+                  per env, entry p = the reference's ``reset(seed + p)``).
     """
 
     def __init__(self, num_envs: int, scene: str = "highway", config: Optional[dict] = None, device=0, seed: int = 0,
@@ -96,16 +95,16 @@ class TTRLVectorEnv:
             raise ValueError(f"unknown scene {scene!r}")
         scripted = scene in ("roundabout", "u-turn")
         if reset_mode is None:
-            reset_mode = "host" if scripted else "device"
+            reset_mode = "device"
         if reset_mode not in ("device", "host"):
             raise ValueError(f"unknown reset_mode {reset_mode!r}")
-        if scripted and reset_mode == "device":
-            raise NotImplementedError(f"the {scene} scene is reset from the host (reset_mode='host')")
         self.reset_mode = reset_mode
         self.pool_factor = max(1, int(pool_factor))
         self.sim = Sim(self.cfg, self.table, self.num_envs, self.vcap, self.device_index, routes)
         self.num_agents = self.sim.num_agents
-        if not scripted:
+        if scripted:
+            self.sim.set_reset_params(scenes.cast_reset_params(scene, self.net, self.table, self.config))
+        else:
             self.sim.set_reset_params(scenes.highway_reset_params(self.config) if scene == "highway"
                                       else scenes.intersection_reset_params(self.config))
         self.autoreset = autoreset
