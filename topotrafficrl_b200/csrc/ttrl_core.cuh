@@ -908,19 +908,21 @@ TT_HD void collide_all(C& c, Exec& ex) {
 // ------------------------------------------------------------------------------------------------
 // RoadNetwork.position_heading_along_route road.py:323-362 with lateral 0
 template <class C>
-TT_HD void position_heading_along_route(C& c, const Route& rt, int rlen, double lon, int cur_lane,
+TT_HD void position_heading_along_route(C& c, Route rt, int rlen, double lon, int cur_lane,
                                         double& px, double& py, double& ph) {
     const int cur_id = c.lanes[cur_lane].lane_id;
     int k = 0;
-    auto head = [&](int kk) {
-        const int lid = route_lane_at(rt, kk);
-        return c.sc->roads[route_road_at(rt, kk)].first_lane + (lid < 0 ? cur_id : lid);
+    auto head = [&]() {  // the walk consumes the local copy of the route: its head is always entry 0
+        const int lid = route_lane_at(rt.l[0], 0);
+        return c.sc->roads[route_road_at(rt.r[0], 0)].first_lane + (lid < 0 ? cur_id : lid);
     };
-    int li = head(k);
+    int li = head();
     while (rlen - k > 1 && lon > c.lanes[li].length) {
         lon -= c.lanes[li].length;
         ++k;
-        li = head(k);
+        rt.r[0] = (rt.r[0] >> 8) | (rt.r[1] << 24); rt.r[1] = (rt.r[1] >> 8) | (rt.r[2] << 24); rt.r[2] >>= 8;
+        rt.l[0] = (rt.l[0] >> 8) | (rt.l[1] << 24); rt.l[1] = (rt.l[1] >> 8) | (rt.l[2] << 24); rt.l[2] >>= 8;
+        li = head();
     }
     lane_position(c.lanes[li], lon, 0.0, px, py);
     ph = lane_heading_at(c.lanes[li], lon);
@@ -1258,6 +1260,7 @@ template <class C, class Exec>
 TT_HD void observe(C& c, Exec& ex, float* out, const int32_t* inv_perm) {
     const ttrl_config& cfg = c.sc->cfg;
     const int K = n_agents(c);
+#pragma unroll 1
     for (int k = 0; k < K; ++k) {
         const int ego = K == 1 ? c.st->ego : c.st->egos[k];
         if (cfg.obs_type == TTRL_OBS_GRID) observe_grid(c, ex, out + (size_t)k * obs_single_size(cfg), ego);
@@ -1716,6 +1719,7 @@ TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int e
     }
     if (ex.first()) {
         const int K = n_agents(c);
+#pragma unroll 1
         for (int a = 0; a < K; ++a) {
             // ego MDPVehicle a (:286-307) at ego_longitudinal + std * N(1, 1) on (o<k>, ir<k>, 0), k = a % 4, speed = speed_limit
             double u0, u1, ud, unused;
@@ -1894,6 +1898,7 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
             if (io.agent_terminated) io.agent_terminated[e] = ((st->flags[ego] & TTRL_FL_CRASHED) || (!C::kPlain && has_arrived(c, ego))) ? 1 : 0;
         } else {  // sum(agent rewards) / len(controlled_vehicles) (intersection_env.py:61-65)
             double sum = 0;
+#pragma unroll 1
             for (int k = 0; k < K; ++k) {
                 const int v = st->egos[k];
                 const double rk = agent_reward(c, v, actions ? actions[k] : -1);
