@@ -49,7 +49,7 @@ struct HostExec {
     int atomic_add_global(int32_t* a, int32_t v) { return atomic_add(a, v); }
 };
 
-template <int V>
+template <int V, int P>
 struct HostEnv {
     EnvState<V> st;
     std::vector<d2> SR;
@@ -57,7 +57,7 @@ struct HostEnv {
     std::vector<double> pred;
     std::vector<float> obs_s;
     std::vector<int32_t> cell;
-    EnvCtx<V> c;
+    EnvCtx<V, P> c;
     HostEnv(const SceneDev* sc, int vcap) {
         memset(&st, 0, sizeof st);
         const ttrl_config& cfg = sc->cfg;
@@ -75,12 +75,19 @@ struct HostEnv {
     }
 };
 
-#define DISPATCH(vcap, EXPR)                                  \
-    do {                                                      \
-        if (vcap <= 32) { constexpr int V = 32; EXPR; }       \
-        else if (vcap <= 64) { constexpr int V = 64; EXPR; }  \
-        else if (vcap <= 128) { constexpr int V = 128; EXPR; }\
-        else { constexpr int V = 256; EXPR; }                 \
+// scene profile like the library's (ttrl_kern.cu configure): 2 = several controlled vehicles, 0 = general single-agent
+// (the "plain" profile 1 only removes code paths that plain scenes never take)
+#define DISPATCH_V(vcap, ...)                                        \
+    do {                                                             \
+        if (vcap <= 32) { constexpr int V = 32; __VA_ARGS__; }       \
+        else if (vcap <= 64) { constexpr int V = 64; __VA_ARGS__; }  \
+        else if (vcap <= 128) { constexpr int V = 128; __VA_ARGS__; }\
+        else { constexpr int V = 256; __VA_ARGS__; }                 \
+    } while (0)
+#define DISPATCH(vcap, ...)                                                                    \
+    do {                                                                                       \
+        if (sc->cfg.controlled_vehicles > 1) { constexpr int P = 2; DISPATCH_V(vcap, __VA_ARGS__); } \
+        else { constexpr int P = 0; DISPATCH_V(vcap, __VA_ARGS__); }                           \
     } while (0)
 
 extern "C" {
@@ -108,7 +115,7 @@ void emu_scene_set_spawn_routes(SceneDev* s, const int32_t* spawn_lane, const in
 void emu_substep(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, const int32_t* actions) {
     GlobalState g{vd, vi, ei, ed, E, Vs};
     DISPATCH(Vs, {
-        HostEnv<V> env(sc, Vs);
+        HostEnv<V, P> env(sc, Vs);
         HostExec ex{V};
         for (int e = 0; e < E; ++e) {
             load_env(env.c, ex, g, e);
@@ -122,7 +129,7 @@ void emu_observe(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, doubl
                  const int32_t* inv_perm) {
     GlobalState g{vd, vi, ei, ed, E, Vs};
     DISPATCH(Vs, {
-        HostEnv<V> env(sc, Vs);
+        HostEnv<V, P> env(sc, Vs);
         HostExec ex{V};
         for (int e = 0; e < E; ++e) {
             load_env(env.c, ex, g, e);
@@ -143,7 +150,7 @@ void emu_step(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* 
     io.pool = GlobalState{pvd, pvi, pei, ped, pool_size, Vs};
     io.autoreset = autoreset; io.seed = seed; io.first_global_env = first_global_env; io.obs_size = obs_size;
     DISPATCH(Vs, {
-        HostEnv<V> env(sc, Vs);
+        HostEnv<V, P> env(sc, Vs);
         HostExec ex{V};
         for (int e = 0; e < E; ++e) env_step(env.c, ex, g, io, e);
     });
@@ -155,7 +162,7 @@ void emu_spawn(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double*
     GlobalState g{vd, vi, ei, ed, E, Vs};
     SpawnParams sp{longitudinal, position_deviation, speed_deviation, spawn_probability, go_straight};
     DISPATCH(Vs, {
-        HostEnv<V> env(sc, Vs);
+        HostEnv<V, P> env(sc, Vs);
         HostExec ex{V};
         for (int e = 0; e < E; ++e) {
             load_env(env.c, ex, g, e);
@@ -170,7 +177,7 @@ void emu_scene_set_reset_params(SceneDev* s, const ttrl_reset_params* rp) { s->r
 void emu_reset(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, uint64_t seed, int64_t first_global_env, int episode) {
     GlobalState g{vd, vi, ei, ed, E, Vs};
     DISPATCH(Vs, {
-        HostEnv<V> env(sc, Vs);
+        HostEnv<V, P> env(sc, Vs);
         HostExec ex{V};
         for (int e = 0; e < E; ++e) {
             env_reset(env.c, ex, seed, first_global_env + e, episode);

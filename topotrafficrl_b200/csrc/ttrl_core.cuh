@@ -106,10 +106,13 @@ struct alignas(16) EnvState {
 // P_ = 1 ("plain" scenes: straight lanes only, no regulation, no spawn / clear, highway reward -- BASELINE configs 1
 // and 2) compiles the curved-lane geometry, the regulation and the intersection reward out of the step loop: the kernel
 // is bound by instruction-cache miss traffic, so code that is never executed should not sit between code that is.
+// P_ = 2 ("multi"): the number of controlled vehicles is read from the config at run time (MultiAgentIntersectionEnv); the
+// single-agent profiles 0 / 1 compile the per-agent loops and lookups out for the same reason.
 template <int V_, int P_ = 0>
 struct EnvCtx {
     static constexpr int V = V_;
     static constexpr bool kPlain = P_ == 1;
+    static constexpr bool kMulti = P_ == 2;
     static constexpr int W = (V_ + 31) / 32;  // mask words per lane
     EnvState<V_>* st;
     const SceneDev* sc;
@@ -411,7 +414,7 @@ TT_HD int speed_to_index(const ttrl_config& cfg, double speed) {
 enum { A_NONE = 0, A_IDLE, A_LANE_LEFT, A_LANE_RIGHT, A_FASTER, A_SLOWER };
 // number of controlled vehicles (plain scenes: always one)
 template <class C> TT_HD int n_agents(const C& c) {
-    if (C::kPlain) return 1;
+    if (!C::kMulti) return 1;
     const int k = c.sc->cfg.controlled_vehicles;
     return k < 1 ? 1 : (k > TTRL_MAX_CONTROLLED ? TTRL_MAX_CONTROLLED : k);
 }
@@ -1514,7 +1517,7 @@ TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
             st->rroad[1][t] = (uint32_t)g.vi[TTRL_I_ROUTE_ROAD1 * fs + o]; st->rlanew[1][t] = (uint32_t)g.vi[TTRL_I_ROUTE_LANE1 * fs + o];
             st->rroad[2][t] = (uint32_t)g.vi[TTRL_I_ROUTE_ROAD2 * fs + o]; st->rlanew[2][t] = (uint32_t)g.vi[TTRL_I_ROUTE_LANE2 * fs + o];
             st->ytimer[t] = g.vi[TTRL_I_YIELD_TIMER * fs + o];
-            if (t < st_n && (st->flags[t] & TTRL_FL_CONTROLLED) && (st->flags[t] & TTRL_FL_AGENT_MASK))
+            if (C::kMulti && t < st_n && (st->flags[t] & TTRL_FL_CONTROLLED) && (st->flags[t] & TTRL_FL_AGENT_MASK))
                 st->egos[(st->flags[t] & TTRL_FL_AGENT_MASK) >> TTRL_FL_AGENT_SHIFT] = t;  // agents k >= 1 (distinct slots: no race)
         } else {
             st->pos[t] = d2{0, 0}; st->cs[t] = d2{1, 0}; st->imp[t] = d2{0, 0};

@@ -147,12 +147,12 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V, P>& c, unsigned char* smem_ct
     __syncthreads();
 }
 
-// single-team CTA (k_substep, k_observe, k_spawn, k_reset)
+// single-team CTA (k_substep, k_observe, k_spawn, k_reset): the general profile (any number of controlled vehicles)
 #define TT_KERNEL_PROLOGUE                                     \
     extern __shared__ __align__(16) unsigned char smem[];      \
     constexpr int T = TeamOf<V>::T;                            \
-    EnvCtx<V> c;                                               \
-    make_ctx<V, 0>(c, smem, 0, sc, lay, g.V);                  \
+    EnvCtx<V, 2> c;                                            \
+    make_ctx<V, 2>(c, smem, 0, sc, lay, g.V);                  \
     DevExec<V, T> ex{(int)threadIdx.x, 1};
 
 template <int V, int P>
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(TeamOf<V>::T) k_reset(const SceneDev* __restri
 // listed in `done_list`; they are reset here PACKED (G per CTA, like k_step) and phase-aligned, and their first
 // observation replaces the terminal one (gymnasium autoreset semantics).  A reset inside k_step would leave one warp
 // running 45 sub-steps while the other teams of its CTA -- and the SM -- wait.
-template <int V>
+template <int V, int P>
 __global__ void __launch_bounds__(TeamOf<V>::T * TeamOf<V>::G, TeamOf<V>::G > 1 ? 1 : TeamOf<V>::MINB)
 k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -231,8 +231,8 @@ k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayo
     const int team = threadIdx.x / T;
     const int n_done = *io.done_count;
     if ((int)blockIdx.x * G >= n_done) return;  // uniform per CTA
-    EnvCtx<V, 0> c;
-    make_ctx<V, 0>(c, smem, team, sc, lay, g.V);
+    EnvCtx<V, P> c;
+    make_ctx<V, P>(c, smem, team, sc, lay, g.V);
     DevExec<V, T> ex{(int)threadIdx.x % T, G};
     const int k = (int)blockIdx.x * G + team;
     if (k < n_done) {
@@ -274,28 +274,33 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_step<V, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_step<V, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_step<V, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_substep<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_observe<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_spawn<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_reset<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
-    if ((e = cudaFuncSetAttribute(k_reset_list<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_reset_list<V, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_reset_list<V, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
     // all of the SM's unified L1/shared storage as shared memory: resident CTAs are what hides latency here
     cudaFuncSetAttribute(k_step<V, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_step<V, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_step<V, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     // "plain" scene profile (EnvCtx::kPlain): straight lanes only, no regulation, no spawn / clear, highway reward
     bool plain = !cfg.regulated && !cfg.spawn_enabled && cfg.reward_type == TTRL_REWARD_HIGHWAY && cfg.controlled_vehicles <= 1;
     for (int k = 0; k < cfg.n_lanes; ++k) plain = plain && lanes[k].kind == TTRL_LANE_STRAIGHT;
-    out->plain = plain ? 1 : 0;
+    out->plain = plain ? 1 : (cfg.controlled_vehicles > 1 ? 2 : 0);  // scene profile: 0 general single-agent, 1 plain, 2 multi-agent
     return 0;
 }
 template <int V>
 static void launch_step(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io) {
     const int G = lay.G;
     if (io.done_list) cudaMemsetAsync(io.done_count, 0, sizeof(int32_t), st);
-    if (lay.plain) k_step<V, 1><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    if (lay.plain == 1) k_step<V, 1><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    else if (lay.plain == 2) k_step<V, 2><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
     else k_step<V, 0><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
     // CTAs beyond the number of finished envs exit at once
-    if (io.done_list) k_reset_list<V><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    if (io.done_list && lay.plain == 2) k_reset_list<V, 2><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    else if (io.done_list) k_reset_list<V, 0><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
 }
 template <int V>
 static void launch_substep(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const int32_t* actions) {
