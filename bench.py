@@ -107,6 +107,16 @@ def random_state_dict(kind: str, n_actions: int, seed: int = 0):
     return sd
 
 
+def _dram_traffic(workload: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/dram_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)[workload]["bytes"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -399,7 +409,7 @@ def run_ours(args, w):
                     "ms_per_step": float(e2e_t.item()) / K * 1e3},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "kernel": "k_step", "kernel_ms": kernel_ms, "peak_kind": peak_kind,
+                         "traffic": _dram_traffic(args.workload) if E == w["E"] else None, "kernel": "k_step", "kernel_ms": kernel_ms, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks,
             "episode_stats": {"episodes": episodes, "crashes": crashes, "mean_return": ret / episodes if episodes else None},
