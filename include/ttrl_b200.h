@@ -70,7 +70,9 @@ typedef struct ttrl_road {
 /* Observation feature ids (vehicle/kinematics.py:237-261, the subset the hot configs use). */
 enum { TTRL_F_PRESENCE = 0, TTRL_F_X = 1, TTRL_F_Y = 2, TTRL_F_VX = 3, TTRL_F_VY = 4,
        TTRL_F_COS_H = 5, TTRL_F_SIN_H = 6, TTRL_F_HEADING = 7, TTRL_F_ON_ROAD = 8 };
-enum { TTRL_OBS_KINEMATICS = 0, TTRL_OBS_GRID = 1 };
+enum { TTRL_OBS_KINEMATICS = 0, TTRL_OBS_GRID = 1,
+       TTRL_OBS_TTC = 2 /* TimeToCollisionObservation (observation.py:114-151 over finite_mdp.compute_ttc_grid :104-163): 3 x 3 x ttc_steps */ };
+#define TTRL_MAX_TTC_CELLS 2048  /* target speeds x lanes of the ego's road x ttc_steps */
 enum { TTRL_ORDER_SORTED = 0, TTRL_ORDER_SHUFFLED = 1 };
 /* DiscreteMetaAction tables (envs/common/action.py:204-211) */
 enum { TTRL_ACT_ALL = 0 /* 0 LANE_LEFT 1 IDLE 2 LANE_RIGHT 3 FASTER 4 SLOWER */,
@@ -100,7 +102,9 @@ typedef struct ttrl_config {
     int32_t has_range[TTRL_MAX_FEATURES];
     double range_lo[TTRL_MAX_FEATURES], range_hi[TTRL_MAX_FEATURES];
     /* OccupancyGrid: features_range of "x"/"y" even when x/y are not observed features (observation.py:375-392) */
-    int32_t grid_has_xrange, grid_has_yrange, grid_w, grid_h, align_to_vehicle_axes, as_image, pad2, pad3;
+    int32_t grid_has_xrange, grid_has_yrange, grid_w, grid_h, align_to_vehicle_axes, as_image;
+    int32_t ttc_steps;   /* TimeToCollision: int(horizon * policy_frequency) time cells of 1 / policy_frequency seconds */
+    int32_t pad3;
     double grid_xrange[2], grid_yrange[2];
     double grid_min[2], grid_max[2], grid_step[2];
     /* reward / termination */

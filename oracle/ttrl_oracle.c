@@ -808,14 +808,86 @@ static void observe_grid(const orc_scene* sc, const env_t* e, int observer, floa
     }
     free(grid);
 }
+/* RoadNetwork.is_connected_road road.py:231-276 (same_lane = False: roads only).  route = (road)[rlen] from position k. */
+static int is_connected_road(const orc_scene* sc, int r1, int r2, const int* rroad, int rlen, int depth) {
+    /* is_same_road(lane 2, lane 1) or is_leading_to_road(lane 2, lane 1) */
+    if (r2 == r1 || sc->roads[r2].to_node == sc->roads[r1].from_node) return 1;
+    if (depth > 0) {
+        if (rlen > 0 && rroad[0] == r1) return is_connected_road(sc, r1, r2, rroad + 1, rlen - 1, depth);
+        else if (rlen > 0 && sc->roads[rroad[0]].from_node == sc->roads[r1].to_node)
+            return is_connected_road(sc, rroad[0], r2, rroad + 1, rlen - 1, depth - 1);
+        else {
+            int to = sc->roads[r1].to_node, any = 0;
+            for (int k = sc->node_first[to]; k < sc->node_first[to + 1]; ++k)
+                if (is_connected_road(sc, sc->node_roads[k], r2, rroad, rlen, depth - 1)) any = 1;
+            return any;
+        }
+    }
+    return 0;
+}
+/* compute_ttc_grid finite_mdp.py:104-163 + TimeToCollisionObservation.observe observation.py:114-151 */
+static void observe_ttc(const orc_scene* sc, const env_t* e, int observer, float* obs) {
+    const ttrl_config* c = &sc->cfg;
+    const veh_t* ego = &e->v[observer];
+    int S = c->n_target_speeds, H = c->ttc_steps;
+    int re = sc->lanes[ego->lane].road, L = sc->roads[re].n_lanes;
+    double tq = 1 / c->policy_frequency;
+    double* grid = (double*)calloc((size_t)S * L * H, sizeof(double));
+    for (int si = 0; si < S; ++si) {
+        double ego_speed = c->target_speeds[si];
+        for (int j = 0; j < e->n; ++j) {
+            const veh_t* other = &e->v[j];
+            if (j == observer || ego_speed == other->speed) continue;
+            double margin = 5.0 / 2 + 5.0 / 2;
+            double ms[3] = {0, -margin, margin}, costs[3] = {1, 0.5, 0.5};
+            for (int mi = 0; mi < 3; ++mi) {
+                double distance = lane_distance_to(sc, ego, other) + ms[mi];
+                double other_projected_speed = other->speed * (cos(other->heading) * cos(ego->heading) + sin(other->heading) * sin(ego->heading));
+                double ttc = distance / not_zero(ego_speed - other_projected_speed);
+                if (ttc < 0) continue;
+                int ro = sc->lanes[other->lane].road;
+                if (!is_connected_road(sc, re, ro, ego->route_road, ego->route_len < 0 ? 0 : ego->route_len, 3)) continue;
+                int lane_lo, lane_hi;
+                if (sc->roads[ro].n_lanes == L) { lane_lo = lane_hi = sc->lanes[other->lane].lane_id; }
+                else { lane_lo = 0; lane_hi = L - 1; }
+                double q = ttc / tq;
+                if (!(q < (double)H)) continue; /* int(q) >= H: outside the grid (also keeps the casts defined) */
+                int times[2] = {(int)q, (int)ceil(q)};
+                for (int w = 0; w < 2; ++w) {
+                    int time = times[w];
+                    if (!(0 <= time && time < H)) continue;
+                    for (int l = lane_lo; l <= lane_hi; ++l) {
+                        double* g = &grid[((size_t)si * L + l) * H + time];
+                        if (costs[mi] > *g) *g = costs[mi];
+                    }
+                }
+            }
+        }
+    }
+    /* padding with ones across lanes, repeated first / last rows across speeds, 3 x 3 window (observation.py:137-151) */
+    int lid = sc->lanes[ego->lane].lane_id;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+            for (int t = 0; t < H; ++t) {
+                int so = ego->speed_index - 1 + a;
+                if (so < 0) so = 0;
+                if (so > S - 1) so = S - 1;
+                int lo = lid - 1 + b;
+                double v = (lo >= 0 && lo < L) ? grid[((size_t)so * L + lo) * H + t] : 1.0;
+                obs[(a * 3 + b) * H + t] = (float)v;
+            }
+    free(grid);
+}
 static int obs_single(const orc_scene* sc) {
     const ttrl_config* c = &sc->cfg;
+    if (c->obs_type == TTRL_OBS_TTC) return 9 * c->ttc_steps;
     return c->obs_type == TTRL_OBS_GRID ? c->n_features * c->grid_w * c->grid_h : c->obs_vehicles * c->n_features;
 }
 /* observation_type.observe(); MultiAgentObservation.observe observation.py:602-603: one block per controlled vehicle */
 static void observe(const orc_scene* sc, const env_t* e, float* obs) {
     for (int k = 0; k < n_agents(sc); ++k) {
-        if (sc->cfg.obs_type == TTRL_OBS_GRID) observe_grid(sc, e, e->egos[k], obs + (size_t)k * obs_single(sc));
+        if (sc->cfg.obs_type == TTRL_OBS_TTC) observe_ttc(sc, e, e->egos[k], obs + (size_t)k * obs_single(sc));
+        else if (sc->cfg.obs_type == TTRL_OBS_GRID) observe_grid(sc, e, e->egos[k], obs + (size_t)k * obs_single(sc));
         else observe_kinematics(sc, e, e->egos[k], obs + (size_t)k * obs_single(sc));
     }
 }

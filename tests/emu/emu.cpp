@@ -66,7 +66,7 @@ struct HostEnv {
         pred.assign((size_t)4 * V, 0.0);
         pbits.assign((size_t)(V * (V - 1) / 2 + 31) / 32 + 1, 0u);
         obs_s.assign((size_t)(cfg.obs_vehicles * cfg.n_features + 4), 0.f);
-        cell.assign((size_t)(cfg.grid_w * cfg.grid_h + 4), 0);
+        cell.assign((size_t)(cfg.grid_w * cfg.grid_h + 4 + TTRL_MAX_TTC_CELLS), 0);
         c.st = &st; c.sc = sc; c.lanes = sc->lanes; c.SR = SR.data(); c.lmask = lmask.data();
         c.pred = cfg.regulated ? pred.data() : nullptr; c.pbits = cfg.regulated ? pbits.data() : nullptr; c.obs_s = obs_s.data(); c.cell = cell.data();
         c.L = cfg.n_lanes; c.vcap = vcap;

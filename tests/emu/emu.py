@@ -41,7 +41,8 @@ class Emulator:
             sl, rl, rr = (np.ascontiguousarray(a, dtype=np.int32) for a in spawn_routes)
             self.L.emu_scene_set_spawn_routes(self.sc, _p(sl), _p(rl), _p(rr))
         self.K = max(1, int(cfg.controlled_vehicles))
-        self.obs_size = self.K * ((cfg.n_features * cfg.grid_w * cfg.grid_h) if cfg.obs_type == abi.OBS_GRID else cfg.obs_vehicles * cfg.n_features)
+        from topotrafficrl_b200 import scenes
+        self.obs_size = self.K * int(np.prod(scenes.obs_shape(cfg)))
         self.agent_reward = self.agent_terminated = None  # per-agent outputs of the last step()
         self.pool = None
         self.autoreset = False

@@ -114,7 +114,7 @@ def intersection_reset(seeds, vcap=32):
     rec.save("intersection_reset.npz")
 
 
-def highway(n_vehicles, density, seeds, n_substeps, name, obs_overrides=None, with_steps=True):
+def highway(n_vehicles, density, seeds, n_substeps, name, obs_overrides=None, with_steps=True, with_substeps=True):
     net = scenes.make_highway_network(4)
     table = net.to_table()
     cfg = {"vehicles_count": n_vehicles, "vehicles_density": density}
@@ -133,7 +133,8 @@ def highway(n_vehicles, density, seeds, n_substeps, name, obs_overrides=None, wi
             rec.add(action=a)
             H.ref_substep(env, a)
             rec.add_state("after", H.extract_state(env, table, n_vehicles))
-    rec.save(name + "_substeps.npz")
+    if with_substeps:
+        rec.save(name + "_substeps.npz")
     if not with_steps:
         return
     rec = Rec()
@@ -192,7 +193,7 @@ def multi_agent_steps(seeds, overrides, name, vcap=32):
     rec.save(name)
 
 
-def scripted_scene(env_cls, net, overrides, seeds, name, n_actions, vcap=16):
+def scripted_scene(env_cls, net, overrides, seeds, name, n_actions, vcap=16, substeps=True):
     """RoundaboutEnv / UTurnEnv: post-reset states per seed, per-sub-step and per-step snapshots under random actions."""
     H.restore_idm_class_constants()  # IntersectionEnv mutates the IDMVehicle class constants process-wide
     table = net.to_table()
@@ -207,7 +208,7 @@ def scripted_scene(env_cls, net, overrides, seeds, name, n_actions, vcap=16):
         k = 0
         while not done:
             a = int(rng.integers(0, n_actions))
-            if k % 3 == 2:  # every third env-step sub-step by sub-step (same transition; finer resync for the parity tests)
+            if substeps and k % 3 == 2:  # every third env-step sub-step by sub-step (same transition; finer resync for the parity tests)
                 env.time += 1 / env.config["policy_frequency"]
                 for _ in range(15):
                     sub.add_state("before", H.extract_state(env, table, vcap))
@@ -223,7 +224,8 @@ def scripted_scene(env_cls, net, overrides, seeds, name, n_actions, vcap=16):
                 done = term or trunc
             k += 1
     rec.save(name + "_steps.npz")
-    sub.save(name + "_substeps.npz")
+    if substeps:
+        sub.save(name + "_substeps.npz")
 
 
 def function_kats():
@@ -365,7 +367,7 @@ def qnet_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kat", "int_sub", "int_steps", "int_reset", "hw", "qnet", "multi", "scripted"]
+    which = sys.argv[1:] or ["kat", "int_sub", "int_steps", "int_reset", "hw", "qnet", "multi", "scripted", "ttc"]
     if "kat" in which:
         function_kats()
     if "int_sub" in which:
@@ -385,6 +387,10 @@ if __name__ == "__main__":
                                                "grid_size": [[-32, 32], [-32, 32]], "grid_step": [2, 2], "absolute": False}})
     if "qnet" in which:
         qnet_vectors()
+    if "ttc" in which:  # TimeToCollisionObservation (observation.py:114-151): UTurnEnv's default config, and a 4-lane highway
+        scripted_scene(H.UTurnEnv, scenes.make_uturn_network(), None, range(700, 708), "uturn_ttc", 5, substeps=False)
+        highway(30, 2.0, range(3), 150, "highway_ttc_n30", with_substeps=False,
+                obs_overrides={"observation": {"type": "TimeToCollision", "horizon": 10}})
     if "multi" in which:
         multi_agent_steps(range(400, 406), MULTI_AGENT, "multiagent_steps.npz")
     if "scripted" in which:

@@ -169,9 +169,14 @@ def test_scripted_env_episodes_match_reference(scene, env_id, over):
         np.testing.assert_allclose(obs, g["obs"][k], rtol=0, atol=2e-6)
         assert abs(reward - g["reward"][k]) <= 1e-6 and term == bool(g["terminated"][k])
     env.close()
-    if scene == "uturn":
-        with pytest.raises(NotImplementedError):  # the default TimeToCollision observation is outside the hot path
-            make(env_id)
+    if scene == "uturn":  # the DEFAULT config: TimeToCollision observation, horizon 16
+        g = T.golden("uturn_ttc_steps.npz")
+        env = make(env_id)
+        assert env.observation_space.shape == (3, 3, 16)
+        for r, seed in enumerate(g["reset_seed"][:4]):
+            obs, _ = env.reset(seed=int(seed))
+            np.testing.assert_array_equal(obs, g["reset_obs"][r])
+        env.close()
 
 
 @pytest.mark.parametrize("scene,reset_mode,E", [("roundabout", "device", 1024), ("u-turn", "device", 1024), ("roundabout", "host", 256)])
@@ -221,3 +226,20 @@ def test_scripted_vector_env_vs_oracle(scene, reset_mode, E):
 def _take(st, sel):
     from topotrafficrl_b200.state import SimState
     return SimState(st.veh_d[:, sel].copy(), st.veh_i[:, sel].copy(), st.env_i[:, sel].copy(), st.env_d[:, sel].copy())
+
+
+@pytest.mark.parametrize("name", ["uturn_ttc_steps.npz", "highway_ttc_n30_steps.npz"])
+def test_time_to_collision_observation_vs_reference_golden(name):
+    g = T.golden(name)
+    if name.startswith("uturn"):
+        _, table, cfg, _ = T.uturn_scene(None)
+    else:
+        _, table, cfg, _ = T.highway_scene(30, 2.0, overrides={"observation": {"type": "TimeToCollision", "horizon": 10}})
+    st = T.batch_state(g, "before")
+    sim = _sim(cfg, table, st.num_envs, st.vcap)
+    sim.set_state(st)
+    obs, reward, term, trunc = _dev_step(sim, g["action"])
+    T.compare_states(sim.get_state(), T.batch_state(g, "after"), T.TOL_STEP, name)
+    np.testing.assert_array_equal(obs.reshape(g["obs"].shape), g["obs"])
+    np.testing.assert_allclose(reward, g["reward"], rtol=0, atol=1e-6)
+    sim.close()

@@ -165,3 +165,24 @@ def test_device_cast_reset_follows_make_vehicles(scene):
         assert dests == {"exr", "sxr", "nxr"}                                 # the destination draw covers all three exits
         fixed = scenes.cast_reset_params(scene, net, table, dict(cfgd, incoming_vehicle_destination=1))
         assert fixed.cast[1].n_dest == 1 and fixed.cast[1].dest[0] == 1
+
+
+@pytest.mark.parametrize("name", ["uturn_ttc_steps.npz", "highway_ttc_n30_steps.npz"])
+def test_time_to_collision_observation_vs_reference(name):
+    """TimeToCollisionObservation (observation.py:114-151, finite_mdp.compute_ttc_grid): UTurnEnv's DEFAULT config, and a
+    4-lane highway (lane padding on both sides, every speed row)."""
+    g = T.golden(name)
+    if name.startswith("uturn"):
+        _, table, cfg, _ = T.uturn_scene(None)
+    else:
+        _, table, cfg, _ = T.highway_scene(30, 2.0, overrides={"observation": {"type": "TimeToCollision", "horizon": 10}})
+    assert cfg.obs_type == abi.OBS_TTC and scenes.obs_shape(cfg) == g["obs"].shape[1:]
+    for what, eng in _engines(cfg, table):
+        st = T.batch_state(g, "before")
+        obs, reward, term, trunc, _ = eng.step(st, g["action"].astype(np.int32))
+        T.compare_states(st, T.batch_state(g, "after"), T.TOL_STEP, f"{name}, {what}")
+        np.testing.assert_array_equal(obs.reshape(g["obs"].shape), g["obs"], err_msg=what)  # costs 0 / 0.5 / 1: exact
+        np.testing.assert_allclose(reward, g["reward"], rtol=0, atol=1e-6)
+        if "reset_obs" in g.files:
+            np.testing.assert_array_equal(eng.observe(T.batch_state(g, "reset")).reshape(g["reset_obs"].shape), g["reset_obs"])
+    assert 0 < (g["obs"] == 0.5).mean() and 0 < (g["obs"] == 1.0).mean() < 1  # both cost levels and free cells occur

@@ -20,7 +20,8 @@ LANE_STRAIGHT, LANE_CIRCULAR, LANE_SINE = 0, 1, 2
 
 # observation features (vehicle/kinematics.py:237-261 of the reference)
 FEATURES = {"presence": 0, "x": 1, "y": 2, "vx": 3, "vy": 4, "cos_h": 5, "sin_h": 6, "heading": 7, "on_road": 8}
-OBS_KINEMATICS, OBS_GRID = 0, 1
+OBS_KINEMATICS, OBS_GRID, OBS_TTC = 0, 1, 2
+MAX_TTC_CELLS = 2048
 ORDER_SORTED, ORDER_SHUFFLED = 0, 1
 ACT_ALL, ACT_LONGI, ACT_LAT = 0, 1, 2
 REWARD_INTERSECTION, REWARD_HIGHWAY, REWARD_ROUNDABOUT = 0, 1, 2
@@ -75,7 +76,7 @@ class Config(C.Structure):
         ("has_range", C.c_int32 * MAX_FEATURES),
         ("range_lo", C.c_double * MAX_FEATURES), ("range_hi", C.c_double * MAX_FEATURES),
         ("grid_has_xrange", C.c_int32), ("grid_has_yrange", C.c_int32), ("grid_w", C.c_int32), ("grid_h", C.c_int32),
-        ("align_to_vehicle_axes", C.c_int32), ("as_image", C.c_int32), ("pad2", C.c_int32), ("pad3", C.c_int32),
+        ("align_to_vehicle_axes", C.c_int32), ("as_image", C.c_int32), ("ttc_steps", C.c_int32), ("pad3", C.c_int32),
         ("grid_xrange", C.c_double * 2), ("grid_yrange", C.c_double * 2),
         ("grid_min", C.c_double * 2), ("grid_max", C.c_double * 2), ("grid_step", C.c_double * 2),
         ("reward_type", C.c_int32), ("normalize_reward", C.c_int32), ("offroad_terminal", C.c_int32), ("pad4", C.c_int32),

@@ -1254,7 +1254,92 @@ TT_HD void observe_grid(C& c, Exec& ex, float* out, int ego) {
         });
     }
 }
+// RoadNetwork.is_connected_road road.py:231-276 with same_lane = False: only the ROADS of the two lanes matter.  D = remaining
+// search depth; the "route starts at the current road" case keeps the depth and consumes the route, so it is a loop.
+template <int D, class C>
+TT_HDN bool is_connected_road(C& c, int r1, int r2, Route rt, int rlen) {
+    const SceneDev* sc = c.sc;
+    for (;;) {
+        if (r2 == r1 || sc->roads[r2].to_node == sc->roads[r1].from_node) return true;  // is_same_road / is_leading_to_road(lane 2, lane 1)
+        if (D == 0) return false;
+        if (rlen > 0 && route_road_at(rt.r[0], 0) == r1) {  // route starts at the current road: skip it (:255-259)
+            rt.r[0] = (rt.r[0] >> 8) | (rt.r[1] << 24); rt.r[1] = (rt.r[1] >> 8) | (rt.r[2] << 24); rt.r[2] >>= 8;
+            --rlen;
+            continue;
+        }
+        break;
+    }
+    if (D > 0) {
+        constexpr int D1 = D > 0 ? D - 1 : 0;
+        if (rlen > 0 && sc->roads[route_road_at(rt.r[0], 0)].from_node == sc->roads[r1].to_node) {  // follow the route (:260-264)
+            const int nr = route_road_at(rt.r[0], 0);
+            rt.r[0] = (rt.r[0] >> 8) | (rt.r[1] << 24); rt.r[1] = (rt.r[1] >> 8) | (rt.r[2] << 24); rt.r[2] >>= 8;
+            return is_connected_road<D1>(c, nr, r2, rt, rlen - 1);
+        }
+        const int to = sc->roads[r1].to_node;  // every road leaving the end node (:265-275)
+        for (int k = sc->node_first[to]; k < sc->node_first[to + 1]; ++k)
+            if (is_connected_road<D1>(c, sc->node_roads[k], r2, rt, rlen)) return true;
+    }
+    return false;
+}
+
+// TimeToCollisionObservation.observe observation.py:114-151 over compute_ttc_grid finite_mdp.py:104-163.  The grid
+// [speeds][lanes of the ego's road][time] only holds the costs 0 / 0.5 / 1 and is a running maximum: kept as 0 / 1 / 2
+// in shared-memory ints (`cell`) under atomicMax.  Then the 3 x 3 x T window around the ego's speed index and lane is cut
+// out of the grid padded with ones across the lanes and with repeated first / last rows across the speeds.
+template <class C, class Exec>
+TT_HD void observe_ttc(C& c, Exec& ex, float* out, int ego) {
+    auto* st = c.st;
+    const ttrl_config& cfg = c.sc->cfg;
+    const int S = cfg.n_target_speeds, H = cfg.ttc_steps, n = st->n;
+    const int le = st->lane[ego], re = c.lanes[le].road, L = c.sc->roads[re].n_lanes;
+    const double tq = 1 / cfg.policy_frequency;
+    ex.parn(S * L * H, [&](int k) { c.cell[k] = 0; });
+    ex.parn(n, [&](int t) {  // connectivity of every other vehicle's road: independent of the speed row and the margin
+        int m = -2;          // -2 not connected, -1 every lane, else the lane id
+        if (t != ego) {
+            const int ro = c.lanes[st->lane[t]].road;
+            if (is_connected_road<3>(c, re, ro, route_of(st, ego), st->rlen[ego] < 0 ? 0 : st->rlen[ego]))
+                m = c.sc->roads[ro].n_lanes == L ? c.lanes[st->lane[t]].lane_id : -1;
+        }
+        st->mark[t] = m;
+    });
+    ex.parn(S * n * 3, [&](int k) {
+        const int si = k / (n * 3), rem = k - si * n * 3, t = rem / 3, mi = rem - 3 * t;
+        if (t == ego || st->mark[t] == -2) return;
+        const double ego_speed = cfg.target_speeds[si];  // index_to_speed controller.py:317-324
+        if (ego_speed == st->v[t]) return;
+        const double margin = kVehLength / 2 + kVehLength / 2;
+        const double mm = mi == 0 ? 0.0 : (mi == 1 ? -margin : margin);
+        const double distance = (S_(c, t, le) - S_(c, ego, le)) + mm;
+        const double other_projected_speed = st->v[t] * (st->cs[t].x * st->cs[ego].x + st->cs[t].y * st->cs[ego].y);
+        const double ttc = distance / not_zero(ego_speed - other_projected_speed);
+        if (ttc < 0) return;
+        const double q = ttc / tq;
+        if (!(q < (double)H)) return;  // both time cells are beyond the horizon
+        const int cost = mi == 0 ? 2 : 1;
+        const int times[2] = {(int)q, (int)ceil(q)};
+        for (int w = 0; w < 2; ++w) {
+            const int time = times[w];
+            if (time < 0 || time >= H) continue;
+            if (st->mark[t] >= 0) ex.atomic_max(&c.cell[(si * L + st->mark[t]) * H + time], cost);
+            else for (int l = 0; l < L; ++l) ex.atomic_max(&c.cell[(si * L + l) * H + time], cost);
+        }
+    });
+    const int sidx = st->sidx[ego], lid = c.lanes[le].lane_id;
+    ex.parn(9 * H, [&](int k) {
+        const int a = k / (3 * H), b = (k / H) % 3, time = k % H;
+        int so = sidx - 1 + a;
+        so = so < 0 ? 0 : (so > S - 1 ? S - 1 : so);
+        const int lo = lid - 1 + b;
+        float val = 1.0f;
+        if (lo >= 0 && lo < L) val = 0.5f * (float)c.cell[(so * L + lo) * H + time];
+        out[k] = val;
+    });
+}
+
 TT_HD int obs_single_size(const ttrl_config& cfg) {  // floats of ONE controlled vehicle's observation
+    if (cfg.obs_type == TTRL_OBS_TTC) return 9 * cfg.ttc_steps;
     return cfg.obs_type == TTRL_OBS_GRID ? cfg.n_features * cfg.grid_w * cfg.grid_h : cfg.obs_vehicles * cfg.n_features;
 }
 // observation_type.observe(): one observation per controlled vehicle (MultiAgentObservation observation.py:587-603),
@@ -1266,7 +1351,8 @@ TT_HD void observe(C& c, Exec& ex, float* out, const int32_t* inv_perm) {
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
         const int ego = K == 1 ? c.st->ego : c.st->egos[k];
-        if (cfg.obs_type == TTRL_OBS_GRID) observe_grid(c, ex, out + (size_t)k * obs_single_size(cfg), ego);
+        if (!C::kPlain && cfg.obs_type == TTRL_OBS_TTC) observe_ttc(c, ex, out + (size_t)k * obs_single_size(cfg), ego);
+        else if (cfg.obs_type == TTRL_OBS_GRID) observe_grid(c, ex, out + (size_t)k * obs_single_size(cfg), ego);
         else observe_kinematics(c, ex, out + (size_t)k * obs_single_size(cfg), inv_perm ? inv_perm + k * (cfg.obs_vehicles - 1) : nullptr, ego);
     }
 }

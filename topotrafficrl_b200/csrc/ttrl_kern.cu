@@ -262,7 +262,8 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
     l.off_lmask = (int)off; off += align_up(sizeof(uint32_t) * ((V + 31) / 32) * cfg.n_lanes, 16);
     if (cfg.regulated) { l.off_pred = (int)off; off += sizeof(double) * 4 * V + align_up(sizeof(uint32_t) * ((V * (V - 1) / 2 + 31) / 32), 16); } else l.off_pred = -1;
     l.off_obs = (int)off; off += align_up(sizeof(float) * (cfg.obs_type == TTRL_OBS_KINEMATICS ? cfg.obs_vehicles * cfg.n_features : 4), 16);
-    l.off_cell = (int)off; off += align_up(sizeof(int32_t) * (cfg.obs_type == TTRL_OBS_GRID ? cfg.grid_w * cfg.grid_h : 4), 16);
+    l.off_cell = (int)off; off += align_up(sizeof(int32_t) * (cfg.obs_type == TTRL_OBS_GRID ? cfg.grid_w * cfg.grid_h :
+                                                                cfg.obs_type == TTRL_OBS_TTC ? TTRL_MAX_TTC_CELLS : 4), 16);
     l.per_env = (int)align_up(off, 128);
     l.total = l.lanes_bytes + l.per_env;                       // single-team kernels
     int G = TeamOf<V>::G;                                      // k_step: G envs per CTA, as many as fit
@@ -286,7 +287,8 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
     cudaFuncSetAttribute(k_step<V, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_step<V, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     // "plain" scene profile (EnvCtx::kPlain): straight lanes only, no regulation, no spawn / clear, highway reward
-    bool plain = !cfg.regulated && !cfg.spawn_enabled && cfg.reward_type == TTRL_REWARD_HIGHWAY && cfg.controlled_vehicles <= 1;
+    bool plain = !cfg.regulated && !cfg.spawn_enabled && cfg.reward_type == TTRL_REWARD_HIGHWAY && cfg.controlled_vehicles <= 1 &&
+                 cfg.obs_type != TTRL_OBS_TTC;
     for (int k = 0; k < cfg.n_lanes; ++k) plain = plain && lanes[k].kind == TTRL_LANE_STRAIGHT;
     out->plain = plain ? 1 : (cfg.controlled_vehicles > 1 ? 2 : 0);  // scene profile: 0 general single-agent, 1 plain, 2 multi-agent
     return 0;

@@ -73,8 +73,7 @@ class AbstractEnv(Env):
         self.sim = Sim(self.cfg, self.table, 1, self.VCAP, self.device_index, self._spawn_routes())
         self.sim.set_autoreset(False)
         self.num_agents = K = self.sim.num_agents
-        shape = ((self.cfg.n_features, self.cfg.grid_w, self.cfg.grid_h) if self.cfg.obs_type == abi.OBS_GRID
-                 else (self.cfg.obs_vehicles, self.cfg.n_features))
+        shape = scenes.obs_shape(self.cfg)
         self._obs_shape = shape
         box = spaces.Box(low=-np.inf, high=np.inf, shape=shape, dtype=np.float32)
         act = spaces.Discrete(5 if self.cfg.action_mode == abi.ACT_ALL else 3)
@@ -218,8 +217,7 @@ class RoundaboutEnv(AbstractEnv):
 
 
 class UTurnEnv(AbstractEnv):
-    """u_turn_env.py.  Its default ``TimeToCollision`` observation is outside the hot path:
-    pass a Kinematics / OccupancyGrid observation config."""
+    """u_turn_env.py (default observation: ``TimeToCollision`` with a 16 s horizon)."""
     SCENE = "u-turn"
     VCAP = 16
     EGO_LANES = 2

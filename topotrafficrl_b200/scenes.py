@@ -327,8 +327,16 @@ def build_config(table: NetworkTable, config: dict, scene: str, ego_lanes_count:
         if "y" in frange:
             cfg.grid_has_yrange = 1
             cfg.grid_yrange[0], cfg.grid_yrange[1] = float(frange["y"][0]), float(frange["y"][1])
+    elif otype == "TimeToCollision":  # observation.py:114-151; horizon in seconds, one time cell per policy step
+        cfg.obs_type = abi.OBS_TTC
+        cfg.ttc_steps = int(obs.get("horizon", 10) * config["policy_frequency"])
+        max_lanes = max(int(table.roads[r].n_lanes) for r in range(table.n_roads))
+        if cfg.ttc_steps < 1 or cfg.n_target_speeds * max_lanes * cfg.ttc_steps > abi.MAX_TTC_CELLS:
+            raise ValueError("TimeToCollision grid too large for the device scratch")
+        cfg.obs_vehicles = 0
+        features, frange = [], {}
     else:
-        known = ("TimeToCollision", "KinematicsGoal", "GrayscaleObservation", "AttributesObservation",
+        known = ("KinematicsGoal", "GrayscaleObservation", "AttributesObservation",
                  "MultiAgentObservation", "TupleObservation", "LidarObservation", "ExitObservation")
         if otype in known:
             raise NotImplementedError(f"observation type {otype} is outside the B200 hot path (SURVEY.md section 2 row 13)")
@@ -364,6 +372,15 @@ def build_config(table: NetworkTable, config: dict, scene: str, ego_lanes_count:
     cfg.normalize_reward = int(bool(config.get("normalize_reward", False)))
     cfg.offroad_terminal = int(bool(config.get("offroad_terminal", False)))
     return cfg
+
+
+def obs_shape(cfg: abi.Config) -> tuple:
+    """Shape of ONE controlled vehicle's observation (the ``space()`` of the reference's observation types)."""
+    if cfg.obs_type == abi.OBS_GRID:
+        return (cfg.n_features, cfg.grid_w, cfg.grid_h)
+    if cfg.obs_type == abi.OBS_TTC:
+        return (3, 3, cfg.ttc_steps)
+    return (cfg.obs_vehicles, cfg.n_features)
 
 
 def merged_config(default: dict, overrides: Optional[dict]) -> dict:

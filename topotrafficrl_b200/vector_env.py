@@ -109,8 +109,7 @@ class TTRLVectorEnv:
                                       else scenes.intersection_reset_params(self.config))
         self.autoreset = autoreset
         self.sim.set_autoreset(0 if not autoreset else (abi.AUTORESET_DEVICE if reset_mode == "device" else abi.AUTORESET_POOL))
-        self.obs_shape = ((self.cfg.n_features, self.cfg.grid_w, self.cfg.grid_h) if self.cfg.obs_type == abi.OBS_GRID
-                          else (self.cfg.obs_vehicles, self.cfg.n_features))
+        self.obs_shape = scenes.obs_shape(self.cfg)
         n_actions = 5 if self.cfg.action_mode == abi.ACT_ALL else 3
         self.single_observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=self.obs_shape, dtype=np.float32)
         self.single_action_space = spaces.Discrete(n_actions)
