@@ -61,6 +61,11 @@ WORKLOADS = {
     "intersection_qnet_mlp": dict(scene="intersection", E=8192, n=24, over=None, qnet="mlp",
                                   label="configs[3]: intersection 8192 envs + DQN MLP [128,128] Q-net rollout in the loop",
                                   bytes_per_env_step=24 * 128 + 4 + 420 + 8 + 420 + 4, n_actions=3),
+    # the whole DQN training iteration (CUDA Q-net act -> env step -> replay push -> double-DQN
+    # update with torch autograd -> rollout weights refreshed on the device), one optimiser step of batch 64 per vector step
+    "train_intersection": dict(scene="intersection", E=8192, n=24, over=None, train="mlp",
+                               label="training: intersection 8192 envs, DQN MLP [128,128] (baseline.json), act + step + record per iteration",
+                               bytes_per_env_step=24 * 128 + 4 + 420 + 8 + 420 + 4, n_actions=3),
     # SURVEY.md section 8 rows A29 / N3 (not BASELINE configs; parity cases with a throughput line)
     "multiagent": dict(scene="intersection", E=8192, n=24, agents=4,
                        over={"controlled_vehicles": 4, "initial_vehicle_count": 5,
@@ -324,9 +329,23 @@ def run_ours(args, w):
                            mode=args.qnet_mode)
         sim.observe_ptr(obs.data_ptr(), stream)
     obs3 = obs.view(E, -1)
+    trainer = None
+    if w.get("train"):
+        from topotrafficrl_b200.trainer import BatchedDQNAgent
+        trainer = BatchedDQNAgent(venv, {"model": QNET_CONFIGS[w["train"]], "gamma": 0.95, "batch_size": 64, "memory_capacity": 15000,
+                                         "target_update": 512, "exploration": {"method": "EpsilonGreedy", "tau": 15000, "temperature": 1.0,
+                                                                               "final_temperature": 0.05}}, seed=rank, rollout_mode=args.qnet_mode)
+        sim.observe_ptr(obs.data_ptr(), stream)
+        obs_t = obs.view((E,) + venv.obs_shape)
 
     def step(k):
         a = actions[k]
+        if trainer is not None:  # one full training iteration (trainer.BatchedDQNAgent: act / record)
+            prev = obs_t.clone()
+            a = trainer.act(prev)
+            sim.step_ptr(a.data_ptr(), obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr(), stream)
+            trainer.record(prev, a, rew, obs_t, term, trunc)
+            return
         if qnet is not None:  # agent.act on the observation the previous step left in HBM (no host round trip)
             a = qnet.act(obs3)
         sim.step_ptr(a.data_ptr(), obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr(), stream)
@@ -343,7 +362,8 @@ def run_ours(args, w):
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    launches0 = sim.launch_count + (qnet._L.ttrl_qnet_launch_count(qnet._h) if qnet is not None else 0)
+    counted = qnet if qnet is not None else (trainer.rollout if trainer is not None else None)  # OUR kernels only (not torch's)
+    launches0 = sim.launch_count + (counted._L.ttrl_qnet_launch_count(counted._h) if counted is not None else 0)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     t_wall0 = time.perf_counter()
     for k in range(K):
@@ -353,7 +373,7 @@ def run_ours(args, w):
         ev[k][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = sim.launch_count + (qnet._L.ttrl_qnet_launch_count(qnet._h) if qnet is not None else 0) - launches0
+    launches = sim.launch_count + (counted._L.ttrl_qnet_launch_count(counted._h) if counted is not None else 0) - launches0
     clocks = sampler.stop()
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(ms))
