@@ -204,7 +204,8 @@ typedef struct ttrl_qnet ttrl_qnet;
 const char* ttrl_last_error(void);
 void ttrl_set_error(const char* msg);
 int ttrl_abi_version(void);
-/* sizeof of the POD structs as compiled (0 lane, 1 road, 2 config, 3 spawn_draw, 4 episode_stats, 5 qnet_desc, 6 reset_params): binding self-check */
+/* sizeof of the POD structs as compiled (0 lane, 1 road, 2 config, 3 spawn_draw, 4 episode_stats, 5 qnet_desc, 6 reset_params,
+ * 7 cast_member): binding self-check */
 int ttrl_abi_sizeof(int which);
 
 /* Create E env instances with V vehicle slots each on CUDA device `device`.
