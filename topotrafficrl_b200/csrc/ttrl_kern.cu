@@ -230,21 +230,29 @@ k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayo
     const int G = (int)blockDim.x / T;
     const int team = threadIdx.x / T;
     const int n_done = *io.done_count;
-    if ((int)blockIdx.x * G >= n_done) return;  // uniform per CTA
+    const int nb = (int)gridDim.x, b = (int)blockIdx.x;
+    if (b >= n_done) return;  // uniform per CTA
     EnvCtx<V, P> c;
     make_ctx<V, P>(c, smem, team, sc, lay, g.V);
     DevExec<V, T> ex{(int)threadIdx.x % T, G};
-    const int k = (int)blockIdx.x * G + team;
-    if (k < n_done) {
-        const int e = io.done_list[k];
-        const int episode = g.ei[TTRL_EI_EPISODE * g.E + e] + 1;
-        env_reset(c, ex, io.seed, io.first_global_env + e, episode, true);
-        if (io.obs) observe(c, ex, io.obs + (size_t)e * io.obs_size,
-                            io.inv_perm ? io.inv_perm + (size_t)e * n_agents(c) * (sc->cfg.obs_vehicles - 1) : nullptr);
-        store_env(c, ex, g, e);
-    } else {
-        const int n_align = env_reset_align_count(sc);
-        for (int a = 0; a < n_align; ++a) ex.align();
+    // The finished envs are dealt ROUND-ROBIN over the CTAs (one CTA per SM), team by team: a typical step finishes ~1/13 of
+    // the envs, and a few teams on every SM run faster than 14 teams on a third of the SMs (a team's speed is set by
+    // dependency latency and by its share of the SM's instruction fetch).  With more finished envs than teams the CTA
+    // makes several passes; a team without an env in a pass only takes part in the phase alignment.
+    const int passes = (n_done + G * nb - 1) / (G * nb);
+    for (int pass = 0; pass < passes; ++pass) {
+        const int k = (pass * G + team) * nb + b;
+        if (k < n_done) {
+            const int e = io.done_list[k];
+            const int episode = g.ei[TTRL_EI_EPISODE * g.E + e] + 1;
+            env_reset(c, ex, io.seed, io.first_global_env + e, episode, true);
+            if (io.obs) observe(c, ex, io.obs + (size_t)e * io.obs_size,
+                                io.inv_perm ? io.inv_perm + (size_t)e * n_agents(c) * (sc->cfg.obs_vehicles - 1) : nullptr);
+            store_env(c, ex, g, e);
+        } else {
+            const int n_align = env_reset_align_count(sc);
+            for (int a = 0; a < n_align; ++a) ex.align();
+        }
     }
 }
 
@@ -291,6 +299,9 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
                  cfg.obs_type != TTRL_OBS_TTC;
     for (int k = 0; k < cfg.n_lanes; ++k) plain = plain && lanes[k].kind == TTRL_LANE_STRAIGHT;
     out->plain = plain ? 1 : (cfg.controlled_vehicles > 1 ? 2 : 0);  // scene profile: 0 general single-agent, 1 plain, 2 multi-agent
+    int dev = 0, n_sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    out->n_sms = n_sms > 0 ? n_sms : 148;
     return 0;
 }
 template <int V>
@@ -300,9 +311,10 @@ static void launch_step(int E, const SmemLayout& lay, cudaStream_t st, const Sce
     if (lay.plain == 1) k_step<V, 1><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
     else if (lay.plain == 2) k_step<V, 2><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
     else k_step<V, 0><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
-    // CTAs beyond the number of finished envs exit at once
-    if (io.done_list && lay.plain == 2) k_reset_list<V, 2><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
-    else if (io.done_list) k_reset_list<V, 0><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    // one CTA per SM (fewer for tiny batches); CTAs beyond the number of finished envs exit at once
+    const int nb_reset = (E + G - 1) / G < lay.n_sms ? (E + G - 1) / G : lay.n_sms;
+    if (io.done_list && lay.plain == 2) k_reset_list<V, 2><<<nb_reset, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    else if (io.done_list) k_reset_list<V, 0><<<nb_reset, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
 }
 template <int V>
 static void launch_substep(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const int32_t* actions) {
