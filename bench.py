@@ -306,7 +306,7 @@ def run_ours(args, w):
     first_env = rank * E
     from topotrafficrl_b200.vector_env import TTRLVectorEnv
     venv = TTRLVectorEnv(E, scene=w["scene"], config=w["over"], device=local_rank, seed=0, first_env=first_env,
-                         vcap=(args.vcap or w["n"]), reset_mode=args.reset_mode)
+                         vcap=(args.vcap or w["n"]), reset_mode=args.reset_mode, async_reset=not args.sync_reset)
     venv.reset()
     sim = venv.sim
     A = sim.num_agents  # controlled vehicles per env: actions are [E, A]
@@ -456,6 +456,7 @@ def main():
     ap.add_argument("--vcap", type=int, default=0, help="vehicle slots per env (intersection workloads; default 24)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-reset", action="store_true", help="device resets right after the step that finished the env (no side-stream regeneration)")
     ap.add_argument("--reset-mode", default="device", choices=["device", "host"],
                     help="device = fresh episodes generated on the GPU at every autoreset (the reference's _make_vehicles incl. its 45 warm-up sub-steps); host = replay a pool of host-generated initial states")
     ap.add_argument("--qnet-mode", default="tensor", choices=["fp32", "tensor"],

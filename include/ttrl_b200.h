@@ -243,7 +243,12 @@ int ttrl_sim_set_reset_pool(ttrl_sim* sim, int pool_size, const double* veh_d, c
                             const int32_t* env_i, const double* env_d);
 /* autoreset mode of ttrl_sim_step: 0 = off, 1 = restart finished envs from the reset pool, 2 = device-side reset
  * (ttrl_sim_set_reset_params must have been called). */
-enum { TTRL_AUTORESET_OFF = 0, TTRL_AUTORESET_POOL = 1, TTRL_AUTORESET_DEVICE = 2 };
+enum { TTRL_AUTORESET_OFF = 0, TTRL_AUTORESET_POOL = 1, TTRL_AUTORESET_DEVICE = 2,
+       /* same episodes as TTRL_AUTORESET_DEVICE, bit for bit (the draws are keyed by (seed, global env, episode)), but for scenes
+        * whose reset runs warm-up sub-steps (intersection: 45) every env's NEXT episode is generated ahead of time into a shadow
+        * buffer by a kernel on a side stream, overlapping the following env-steps; a finished env restarts from its shadow inside
+        * the step kernel.  Envs that finish again before their shadow is ready take the synchronous path. */
+       TTRL_AUTORESET_DEVICE_ASYNC = 3 };
 int ttrl_sim_set_autoreset(ttrl_sim* sim, int mode);
 int ttrl_sim_set_reset_params(ttrl_sim* sim, const ttrl_reset_params* params);
 /* Device-side reset of every env (mask_dev == NULL) or of the envs with mask_dev[e] != 0; replaces

@@ -47,6 +47,7 @@ struct HostExec {
     void atomic_or(uint32_t* a, uint32_t v) { *a |= v; }
     int atomic_add(int32_t* a, int32_t v) { const int o = *a; *a += v; return o; }
     int atomic_add_global(int32_t* a, int32_t v) { return atomic_add(a, v); }
+    int load_acquire(const int32_t* a) { return *a; }
 };
 
 template <int V, int P>

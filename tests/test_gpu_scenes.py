@@ -243,3 +243,41 @@ def test_time_to_collision_observation_vs_reference_golden(name):
     np.testing.assert_array_equal(obs.reshape(g["obs"].shape), g["obs"])
     np.testing.assert_allclose(reward, g["reward"], rtol=0, atol=1e-6)
     sim.close()
+
+
+@pytest.mark.parametrize("K", [1, 2])
+def test_async_device_reset_equals_synchronous_device_reset(K):
+    """TTRL_AUTORESET_DEVICE_ASYNC (next episodes generated ahead of time on a side stream, consumed from the shadow buffers
+    inside the step kernel) produces the same episodes as TTRL_AUTORESET_DEVICE, bit for bit, over many episode ends -- including
+    envs that finish again before their shadow is ready (synchronous path) -- and across host resyncs."""
+    torch = _torch()
+    from topotrafficrl_b200 import TTRLVectorEnv
+    E = 2048
+    cfg = {"controlled_vehicles": K} if K > 1 else None
+    envs = [TTRLVectorEnv(E, "intersection", config=cfg, seed=21, async_reset=a) for a in (True, False)]
+    assert envs[0].sim._L.ttrl_sim_set_autoreset is not None
+    for env in envs:
+        env.reset()
+    rng = np.random.default_rng(5)
+    n_actions = 3
+    for step in range(45):
+        act = torch.as_tensor(rng.integers(0, n_actions, size=(E, K) if K > 1 else E).astype(np.int32), device="cuda")
+        outs = [env.step(act) for env in envs]
+        torch.cuda.synchronize()
+        for a, b in zip(outs[0][:4], outs[1][:4]):
+            assert torch.equal(a, b), f"step {step}"
+        if step in (10, 30):  # a host resync in the middle (get_state / set_state) drops the shadows: still identical
+            sa, sb = envs[0].get_state(), envs[1].get_state()
+            np.testing.assert_array_equal(sa.veh_d, sb.veh_d)
+            np.testing.assert_array_equal(sa.veh_i, sb.veh_i)
+            np.testing.assert_array_equal(sa.env_i, sb.env_i)
+            if step == 30:
+                envs[0].set_state(sa)
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    np.testing.assert_array_equal(sa.veh_d, sb.veh_d)
+    np.testing.assert_array_equal(sa.env_i, sb.env_i)
+    s0, s1 = envs[0].stats(), envs[1].stats()
+    assert s0 == s1 and s0["episodes"] > 3 * E
+    assert int(sa.env_i[abi.EI_EPISODE].max()) >= 5
+    for env in envs:
+        env.close()

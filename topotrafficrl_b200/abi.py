@@ -96,7 +96,7 @@ class SpawnDraw(C.Structure):
 MAX_SPAWN_ATTEMPTS = 32
 MAX_CAST = 8
 CAST_DEST = 4
-AUTORESET_OFF, AUTORESET_POOL, AUTORESET_DEVICE = 0, 1, 2
+AUTORESET_OFF, AUTORESET_POOL, AUTORESET_DEVICE, AUTORESET_DEVICE_ASYNC = 0, 1, 2, 3
 
 
 class CastMember(C.Structure):

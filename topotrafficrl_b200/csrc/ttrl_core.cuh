@@ -1567,42 +1567,51 @@ struct GlobalState {
     int E;
     int V;        // slots per env in this buffer
 };
-template <class C, class Exec>
+// CG = true: every load bypasses L1 (ld.global.cg).  Used for the shadow buffers of the asynchronous device reset, which
+// another kernel may have written while this one was already running (L1 is not coherent; a neighbouring env's earlier
+// load can have cached a line that also holds part of this env's record).
+template <bool CG, class T_> TT_HD T_ gload(const T_* p) {
+#if defined(__CUDA_ARCH__)
+    if (CG) return __ldcg(p);
+#endif
+    return *p;
+}
+template <bool CG = false, class C, class Exec>
 TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
     auto* st = c.st;
     const int V = g.V;
     if (ex.first()) {
-        st->n = g.ei[TTRL_EI_NVEH * g.E + e]; st->steps = g.ei[TTRL_EI_STEPS * g.E + e];
-        st->road_steps = g.ei[TTRL_EI_ROAD_STEPS * g.E + e]; st->ego = g.ei[TTRL_EI_EGO * g.E + e];
-        st->episode = g.ei[TTRL_EI_EPISODE * g.E + e]; st->done = g.ei[TTRL_EI_DONE * g.E + e];
-        st->time = g.ed[TTRL_ED_TIME * g.E + e]; st->ret = g.ed[TTRL_ED_RETURN * g.E + e];
+        st->n = gload<CG>(&g.ei[TTRL_EI_NVEH * g.E + e]); st->steps = gload<CG>(&g.ei[TTRL_EI_STEPS * g.E + e]);
+        st->road_steps = gload<CG>(&g.ei[TTRL_EI_ROAD_STEPS * g.E + e]); st->ego = gload<CG>(&g.ei[TTRL_EI_EGO * g.E + e]);
+        st->episode = gload<CG>(&g.ei[TTRL_EI_EPISODE * g.E + e]); st->done = gload<CG>(&g.ei[TTRL_EI_DONE * g.E + e]);
+        st->time = gload<CG>(&g.ed[TTRL_ED_TIME * g.E + e]); st->ret = gload<CG>(&g.ed[TTRL_ED_RETURN * g.E + e]);
         st->n_chg = st->n_mob = st->n_pair = st->n_w = st->overflow = 0;
         for (int w = 0; w < C::W; ++w) st->bmask[w] = 0;
         st->egos[0] = st->ego;
         for (int k = 1; k < TTRL_MAX_CONTROLLED; ++k) st->egos[k] = st->ego;
     }
     ex.sync();
-    const int st_n = g.ei[TTRL_EI_NVEH * g.E + e];
+    const int st_n = gload<CG>(&g.ei[TTRL_EI_NVEH * g.E + e]);
     ex.par([&](int t) {
         if (t < V) {
             const size_t o = (size_t)e * V + t, fs = (size_t)g.E * V;
-            st->pos[t] = d2{g.vd[TTRL_D_X * fs + o], g.vd[TTRL_D_Y * fs + o]};
-            const double hd = g.vd[TTRL_D_HEADING * fs + o];
+            st->pos[t] = d2{gload<CG>(&g.vd[TTRL_D_X * fs + o]), gload<CG>(&g.vd[TTRL_D_Y * fs + o])};
+            const double hd = gload<CG>(&g.vd[TTRL_D_HEADING * fs + o]);
             double sn, cn;
             sincos(hd, &sn, &cn);
             st->h[t] = hd; st->cs[t] = d2{cn, sn};
-            st->v[t] = g.vd[TTRL_D_SPEED * fs + o];
-            st->steer[t] = g.vd[TTRL_D_STEERING * fs + o]; st->acc[t] = g.vd[TTRL_D_ACCEL * fs + o];
-            st->tspeed[t] = g.vd[TTRL_D_TARGET_SPEED * fs + o]; st->timer[t] = g.vd[TTRL_D_TIMER * fs + o];
-            st->delta[t] = g.vd[TTRL_D_DELTA * fs + o];
-            st->imp[t] = d2{g.vd[TTRL_D_IMPACT_X * fs + o], g.vd[TTRL_D_IMPACT_Y * fs + o]};
-            st->lane[t] = g.vi[TTRL_I_LANE * fs + o]; st->tlane[t] = g.vi[TTRL_I_TARGET_LANE * fs + o];
-            st->flags[t] = g.vi[TTRL_I_FLAGS * fs + o]; st->sidx[t] = g.vi[TTRL_I_SPEED_INDEX * fs + o];
-            st->rlen[t] = g.vi[TTRL_I_ROUTE_LEN * fs + o];
-            st->rroad[0][t] = (uint32_t)g.vi[TTRL_I_ROUTE_ROAD * fs + o]; st->rlanew[0][t] = (uint32_t)g.vi[TTRL_I_ROUTE_LANE * fs + o];
-            st->rroad[1][t] = (uint32_t)g.vi[TTRL_I_ROUTE_ROAD1 * fs + o]; st->rlanew[1][t] = (uint32_t)g.vi[TTRL_I_ROUTE_LANE1 * fs + o];
-            st->rroad[2][t] = (uint32_t)g.vi[TTRL_I_ROUTE_ROAD2 * fs + o]; st->rlanew[2][t] = (uint32_t)g.vi[TTRL_I_ROUTE_LANE2 * fs + o];
-            st->ytimer[t] = g.vi[TTRL_I_YIELD_TIMER * fs + o];
+            st->v[t] = gload<CG>(&g.vd[TTRL_D_SPEED * fs + o]);
+            st->steer[t] = gload<CG>(&g.vd[TTRL_D_STEERING * fs + o]); st->acc[t] = gload<CG>(&g.vd[TTRL_D_ACCEL * fs + o]);
+            st->tspeed[t] = gload<CG>(&g.vd[TTRL_D_TARGET_SPEED * fs + o]); st->timer[t] = gload<CG>(&g.vd[TTRL_D_TIMER * fs + o]);
+            st->delta[t] = gload<CG>(&g.vd[TTRL_D_DELTA * fs + o]);
+            st->imp[t] = d2{gload<CG>(&g.vd[TTRL_D_IMPACT_X * fs + o]), gload<CG>(&g.vd[TTRL_D_IMPACT_Y * fs + o])};
+            st->lane[t] = gload<CG>(&g.vi[TTRL_I_LANE * fs + o]); st->tlane[t] = gload<CG>(&g.vi[TTRL_I_TARGET_LANE * fs + o]);
+            st->flags[t] = gload<CG>(&g.vi[TTRL_I_FLAGS * fs + o]); st->sidx[t] = gload<CG>(&g.vi[TTRL_I_SPEED_INDEX * fs + o]);
+            st->rlen[t] = gload<CG>(&g.vi[TTRL_I_ROUTE_LEN * fs + o]);
+            st->rroad[0][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_ROAD * fs + o]); st->rlanew[0][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_LANE * fs + o]);
+            st->rroad[1][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_ROAD1 * fs + o]); st->rlanew[1][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_LANE1 * fs + o]);
+            st->rroad[2][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_ROAD2 * fs + o]); st->rlanew[2][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_LANE2 * fs + o]);
+            st->ytimer[t] = gload<CG>(&g.vi[TTRL_I_YIELD_TIMER * fs + o]);
             if (C::kMulti && t < st_n && (st->flags[t] & TTRL_FL_CONTROLLED) && (st->flags[t] & TTRL_FL_AGENT_MASK))
                 st->egos[(st->flags[t] & TTRL_FL_AGENT_MASK) >> TTRL_FL_AGENT_SHIFT] = t;  // agents k >= 1 (distinct slots: no race)
         } else {
@@ -1949,6 +1958,14 @@ struct StepIO {
     GlobalState pool;              // reset pool (pool.E == 0: none)
     int32_t* done_list;            // device autoreset with warm-up: finished envs are queued here (done_count) and reset by
     int32_t* done_count;           //   k_reset_list right after the step, packed and phase-aligned; null: reset inside the step
+    // asynchronous device reset (TTRL_AUTORESET_DEVICE_ASYNC): the NEXT episode of every env is generated ahead of time into
+    // `shadow` by k_regen_list on a side stream; shadow_ready[e] = episode number held by the shadow of env e (-1: none),
+    // written after the record (release) and read before it (acquire).  A finished env whose shadow holds episode + 1
+    // restarts from it inside the step; otherwise it takes the done_list path.  Either way (e, episode + 2) is queued.
+    GlobalState shadow;            // shadow.E == 0: off
+    int32_t* shadow_ready;         // [E]
+    int32_t* regen_list;           // [2 E]: (env, episode to generate) pairs
+    int32_t* regen_count;
     int autoreset;
     uint64_t seed;
     int64_t first_global_env;
@@ -2036,7 +2053,28 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
     }
     if (st->done && io.autoreset == TTRL_AUTORESET_DEVICE && sc->have_rp && io.done_list) {
         // resets with warm-up sub-steps are batched: a lone resetting team would keep its whole CTA (and SM) waiting
-        if (ex.first()) io.done_list[ex.atomic_add_global(io.done_count, 1)] = e;
+        const int next_episode = st->episode + 1;
+        bool from_shadow = false;
+        if (io.shadow.E > 0) {
+            if (ex.first()) st->flag0 = ex.load_acquire(&io.shadow_ready[e]) == next_episode ? 1 : 0;
+            ex.sync();
+            from_shadow = st->flag0 != 0;  // uniform: shared memory
+            ex.sync();
+        }
+        if (from_shadow) {
+            load_env<true>(c, ex, io.shadow, e);  // episode, time, counters come with the record (env_reset wrote them)
+            if (obs) observe(c, ex, obs, perm);
+        }
+        if (ex.first()) {
+            if (!from_shadow) io.done_list[ex.atomic_add_global(io.done_count, 1)] = e;
+            if (io.shadow.E > 0) {
+                io.shadow_ready[e] = -1;  // consumed, or stale: invalid until the queued regeneration has finished
+                const int k = ex.atomic_add_global(io.regen_count, 1);
+                io.regen_list[2 * k] = e;
+                io.regen_list[2 * k + 1] = next_episode + 1;
+            }
+        }
+        ex.sync();
     } else if (st->done && io.autoreset == TTRL_AUTORESET_DEVICE && sc->have_rp) {  // uniform: st->done is in shared memory
         const int episode = st->episode + 1;
         ex.sync();

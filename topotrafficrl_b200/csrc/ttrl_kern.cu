@@ -96,6 +96,12 @@ struct DevExec {
     __device__ __forceinline__ void atomic_or(uint32_t* a, uint32_t v) { atomicOr(a, v); }
     __device__ __forceinline__ int atomic_add(int32_t* a, int32_t v) { return atomicAdd(a, v); }
     __device__ __forceinline__ int atomic_add_global(int32_t* a, int32_t v) { return atomicAdd(a, v); }
+    // acquire load (gpu scope): pairs with the release in k_regen_list
+    __device__ __forceinline__ int load_acquire(const int32_t* a) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+        return v;
+    }
 };
 
 // threads per env for a slot capacity
@@ -256,6 +262,39 @@ k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayo
     }
 }
 
+// Asynchronous device reset: generate the episodes queued in io.regen_list = (env, episode) pairs into the SHADOW buffers,
+// on a side stream, while the next env-steps run.  Same dealing of the work as k_reset_list.  The record is published with
+// a release store of its episode number after every thread's writes have been fenced.
+template <int V, int P>
+__global__ void __launch_bounds__(TeamOf<V>::T * TeamOf<V>::G, TeamOf<V>::G > 1 ? 1 : TeamOf<V>::MINB)
+k_regen_list(const SceneDev* __restrict__ sc, StepIO io, SmemLayout lay) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int T = TeamOf<V>::T;
+    const int G = (int)blockDim.x / T;
+    const int team = threadIdx.x / T;
+    const int n_regen = *io.regen_count;
+    const int nb = (int)gridDim.x, b = (int)blockIdx.x;
+    if (b >= n_regen) return;  // uniform per CTA
+    EnvCtx<V, P> c;
+    make_ctx<V, P>(c, smem, team, sc, lay, io.shadow.V);
+    DevExec<V, T> ex{(int)threadIdx.x % T, G};
+    const int passes = (n_regen + G * nb - 1) / (G * nb);
+    for (int pass = 0; pass < passes; ++pass) {
+        const int k = (pass * G + team) * nb + b;
+        if (k < n_regen) {
+            const int e = io.regen_list[2 * k], episode = io.regen_list[2 * k + 1];
+            env_reset(c, ex, io.seed, io.first_global_env + e, episode, true);
+            store_env(c, ex, io.shadow, e);
+            __threadfence();
+            ex.sync();
+            if (ex.first()) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(io.shadow_ready + e), "r"(episode) : "memory");
+        } else {
+            const int n_align = env_reset_align_count(sc);
+            for (int a = 0; a < n_align; ++a) ex.align();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch table
 // ------------------------------------------------------------------------------------------------
@@ -290,6 +329,8 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
     if ((e = cudaFuncSetAttribute(k_reset<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_reset_list<V, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_reset_list<V, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_regen_list<V, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_regen_list<V, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
     // all of the SM's unified L1/shared storage as shared memory: resident CTAs are what hides latency here
     cudaFuncSetAttribute(k_step<V, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_step<V, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -316,6 +357,17 @@ static void launch_step(int E, const SmemLayout& lay, cudaStream_t st, const Sce
     if (io.done_list && lay.plain == 2) k_reset_list<V, 2><<<nb_reset, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
     else if (io.done_list) k_reset_list<V, 0><<<nb_reset, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
 }
+// the regeneration of the episodes queued by the last step, on the side stream
+template <int V>
+static void launch_regen(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const StepIO& io) {
+    const int G = lay.G;
+    // One CTA per SM, default stream priority: the regeneration CTAs (4-5 busy teams each) slot into the ragged tail of the
+    // step kernel's last wave and the next step's CTAs follow as they drain.  Measured alternatives (profiles/r1k_async_reset.txt):
+    // a third of the SMs at the lowest priority starves the regeneration (5.02 vs 3.45 ms/step).
+    const int nb = (E + G - 1) / G < lay.n_sms ? (E + G - 1) / G : lay.n_sms;
+    if (lay.plain == 2) k_regen_list<V, 2><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay);
+    else k_regen_list<V, 0><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay);
+}
 template <int V>
 static void launch_substep(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const int32_t* actions) {
     k_substep<V><<<E, TeamOf<V>::T, lay.total, st>>>(sc, g, actions, lay);
@@ -340,6 +392,7 @@ static void launch_reset(int E, const SmemLayout& lay, cudaStream_t st, const Sc
 #define TT_CAT_(a, b) a##b
 #define TT_CAT(a, b) TT_CAT_(a, b)
 extern "C" const KernelSet* TT_CAT(ttrl_kernel_set_, TT_V)(void) {
-    static const KernelSet ks = {TT_V, TeamOf<TT_V>::T, configure<TT_V>, launch_step<TT_V>, launch_substep<TT_V>, launch_observe<TT_V>, launch_spawn<TT_V>, launch_reset<TT_V>};
+    static const KernelSet ks = {TT_V, TeamOf<TT_V>::T, configure<TT_V>, launch_step<TT_V>, launch_substep<TT_V>, launch_observe<TT_V>, launch_spawn<TT_V>, launch_reset<TT_V>,
+                                 launch_regen<TT_V>};
     return &ks;
 }

@@ -71,6 +71,8 @@ class Sim:
         """``False``/0: off; ``True``/1: restart finished envs from the reset pool; 2 or ``"device"``: device-side reset."""
         if mode == "device":
             mode = abi.AUTORESET_DEVICE
+        elif mode == "device-async":
+            mode = abi.AUTORESET_DEVICE_ASYNC
         check(self._L.ttrl_sim_set_autoreset(self._h, int(mode)))
 
     def set_reset_params(self, params: abi.ResetParams) -> None:

@@ -46,6 +46,9 @@ class TTRLVectorEnv:
     :param device: CUDA device index or ``"cuda:N"``
     :param seed: base seed; env e uses the stream keyed by ``first_env + e`` so shards reproduce a larger run
     :param first_env: global index of this shard's first env (multi-GPU sharding)
+    :param async_reset: with ``reset_mode="device"`` and a scene whose reset has warm-up sub-steps (the intersection: 45),
+                  generate every env's next episode ahead of time on a side stream (``TTRL_AUTORESET_DEVICE_ASYNC``) instead of
+                  right after the step that finished it; the episodes are the same bit for bit.
     :param reset_mode: ``"device"`` (default): episodes are generated on the GPU (``ttrl_sim_reset``; Philox draws keyed
                   by (seed, global env, episode)) at ``reset()`` and, with ``autoreset``, inside the step kernel when an
                   env finishes.  ``"host"``: the first reset is driven from the host with numpy ``Generator(PCG64)``
@@ -56,7 +59,7 @@ class TTRLVectorEnv:
 
     def __init__(self, num_envs: int, scene: str = "highway", config: Optional[dict] = None, device=0, seed: int = 0,
                  first_env: int = 0, vcap: Optional[int] = None, autoreset: bool = True, reset_mode: Optional[str] = None,
-                 pool_factor: int = 4) -> None:
+                 pool_factor: int = 4, async_reset: bool = True) -> None:
         import torch
 
         if not torch.cuda.is_available():
@@ -108,7 +111,9 @@ class TTRLVectorEnv:
             self.sim.set_reset_params(scenes.highway_reset_params(self.config) if scene == "highway"
                                       else scenes.intersection_reset_params(self.config))
         self.autoreset = autoreset
-        self.sim.set_autoreset(0 if not autoreset else (abi.AUTORESET_DEVICE if reset_mode == "device" else abi.AUTORESET_POOL))
+        # scenes whose reset runs warm-up sub-steps regenerate the next episodes on a side stream (same episodes, bit for bit)
+        device_mode = abi.AUTORESET_DEVICE_ASYNC if (async_reset and scene == "intersection") else abi.AUTORESET_DEVICE
+        self.sim.set_autoreset(0 if not autoreset else (device_mode if reset_mode == "device" else abi.AUTORESET_POOL))
         self.obs_shape = scenes.obs_shape(self.cfg)
         n_actions = 5 if self.cfg.action_mode == abi.ACT_ALL else 3
         self.single_observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=self.obs_shape, dtype=np.float32)
