@@ -6,6 +6,7 @@
 // library carries one instantiation per common capacity (Makefile: TT_VS) and picks the smallest V >= vcap.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "ttrl_kernels.cuh"
 
@@ -364,7 +365,9 @@ static void launch_regen(int E, const SmemLayout& lay, cudaStream_t st, const Sc
     // One CTA per SM, default stream priority: the regeneration CTAs (4-5 busy teams each) slot into the ragged tail of the
     // step kernel's last wave and the next step's CTAs follow as they drain.  Measured alternatives (profiles/r1k_async_reset.txt):
     // a third of the SMs at the lowest priority starves the regeneration (5.02 vs 3.45 ms/step).
-    const int nb = (E + G - 1) / G < lay.n_sms ? (E + G - 1) / G : lay.n_sms;
+    static const int div = [] { const char* v = getenv("TTRL_REGEN_SM_DIV"); const int d = v ? atoi(v) : 1; return d > 0 ? d : 1; }();  // tuning experiments
+    const int cap = lay.n_sms / div > 0 ? lay.n_sms / div : 1;
+    const int nb = (E + G - 1) / G < cap ? (E + G - 1) / G : cap;
     if (lay.plain == 2) k_regen_list<V, 2><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay);
     else k_regen_list<V, 0><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay);
 }
