@@ -334,7 +334,7 @@ def run_ours(args, w):
         from topotrafficrl_b200.trainer import BatchedDQNAgent
         trainer = BatchedDQNAgent(venv, {"model": QNET_CONFIGS[w["train"]], "gamma": 0.95, "batch_size": 64, "memory_capacity": 15000,
                                          "target_update": 512, "exploration": {"method": "EpsilonGreedy", "tau": 15000, "temperature": 1.0,
-                                                                               "final_temperature": 0.05}}, seed=rank, rollout_mode=args.qnet_mode)
+                                                                               "final_temperature": 0.05}}, seed=rank, rollout_mode=args.qnet_mode, cuda_graph=(world == 1))
         sim.observe_ptr(obs.data_ptr(), stream)
         obs_t = obs.view((E,) + venv.obs_shape)
 

@@ -80,7 +80,7 @@ class BatchedDQNAgent:
                     exploration=dict(method="EpsilonGreedy"), target_update=1, double=True, n_steps=1)
 
     def __init__(self, env, config: Optional[dict] = None, seed: int = 0, rollout_mode: str = "fp32",
-                 updates_per_step: int = 1, refresh_every: int = 1) -> None:
+                 updates_per_step: int = 1, refresh_every: int = 1, cuda_graph: bool = False) -> None:
         import torch
         from torch.nn import functional as F
 
@@ -103,8 +103,14 @@ class BatchedDQNAgent:
             raise ValueError("Unknown loss function : {}".format(self.config["loss_function"]))
         self.loss_function = losses[self.config["loss_function"]]
         opt = self.config["optimizer"]
+        # cuda_graph: the whole update (minibatch gather, both forwards, the double-DQN target, backward, gradient clamp, Adam
+        # step) is captured once in a CUDA graph and replayed: the update is ~150 small launches and otherwise launch-bound
+        self.cuda_graph = bool(cuda_graph)
+        if self.cuda_graph and opt["type"] != "ADAM":
+            raise NotImplementedError("cuda_graph=True is implemented for the ADAM optimiser")
         if opt["type"] == "ADAM":
-            self.optimizer = torch.optim.Adam(self.value_net.parameters(), lr=opt["lr"], weight_decay=opt["weight_decay"])
+            self.optimizer = torch.optim.Adam(self.value_net.parameters(), lr=opt["lr"], weight_decay=opt["weight_decay"],
+                                              capturable=self.cuda_graph)
         elif opt["type"] == "RMS_PROP":
             self.optimizer = torch.optim.RMSprop(self.value_net.parameters(), weight_decay=opt["weight_decay"])
         elif opt["type"] == "RANGER":
@@ -120,6 +126,7 @@ class BatchedDQNAgent:
         self.steps = 0          # optimiser steps (update_target_network's counter, abstract.py:91-94)
         self.training = True
         self.last_loss = None
+        self._graph = None
 
     # ---- acting ---------------------------------------------------------------------------------------------
     def act(self, obs, step_exploration_time: bool = True):
@@ -154,10 +161,13 @@ class BatchedDQNAgent:
         for _ in range(self.updates_per_step):
             if len(self.memory) < self.config["batch_size"]:
                 return
-            loss = self.compute_bellman_residual(self.memory.sample(self.config["batch_size"]))
-            self.step_optimizer(loss)
+            if self.cuda_graph:
+                self._graph_update()
+            else:
+                loss = self.compute_bellman_residual(self.memory.sample(self.config["batch_size"]))
+                self.step_optimizer(loss)
+                self.last_loss = loss.detach()
             self.update_target_network()
-            self.last_loss = loss.detach()
         if self.steps % self.refresh_every == 0:
             self.rollout.load_parameters(self.value_net, self.model_config)
 
@@ -167,15 +177,61 @@ class BatchedDQNAgent:
         state, action, reward, next_state, terminal = batch
         q = self.value_net(state).gather(1, action.unsqueeze(1)).squeeze(1)
         with torch.no_grad():
-            next_values = torch.zeros_like(reward)
             if self.config["double"]:
                 best_actions = self.value_net(next_state).max(1)[1]
                 best_values = self.target_net(next_state).gather(1, best_actions.unsqueeze(1)).squeeze(1)
             else:
                 best_values = self.target_net(next_state).max(1)[0]
-            next_values[~terminal] = best_values[~terminal]
+            next_values = torch.where(terminal, torch.zeros_like(reward), best_values)  # static shapes: capturable in a CUDA graph
             target = reward + self.config["gamma"] * next_values
         return self.loss_function(q, target)
+
+    # ---- the update as one CUDA graph ----------------------------------------------------------------------------
+    def _update_from_indices(self):
+        m, idx = self.memory, self._graph_idx
+        loss = self.compute_bellman_residual((m.state[idx], m.action[idx], m.reward[idx], m.next_state[idx], m.terminal[idx]))
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        for p in self.value_net.parameters():
+            p.grad.clamp_(-1, 1)
+        self.optimizer.step()
+        return loss.detach()
+
+    def _build_graph(self) -> None:
+        """Capture one update.  The warm-up iterations that torch needs before a capture (lazy optimiser state, cuBLAS
+        workspaces) are undone afterwards: parameters and Adam moments are restored in place, so training is unaffected."""
+        torch = self.torch
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            raise NotImplementedError("cuda_graph=True with several ranks: the gradient all-reduce is not captured")
+        B = int(self.config["batch_size"])
+        self._graph_idx = torch.zeros(B, dtype=torch.int64, device=self.device)
+        saved = [p.detach().clone() for p in self.value_net.parameters()]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._update_from_indices()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self._graph):
+            self._graph_loss = self._update_from_indices()
+        with torch.no_grad():
+            for p, v in zip(self.value_net.parameters(), saved):
+                p.copy_(v)
+            for state in self.optimizer.state.values():
+                for v in state.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+
+    def _graph_update(self) -> None:
+        if self._graph is None:
+            self._build_graph()
+        B = int(self.config["batch_size"])
+        self._graph_idx.copy_(self.torch.randperm(self.memory.size, device=self.device, generator=self.gen)[:B])
+        self._graph.replay()
+        self.last_loss = self._graph_loss
 
     def step_optimizer(self, loss) -> None:
         """pytorch.py:32-39 (+ gradient averaging over the ranks when torch.distributed is initialised)."""
