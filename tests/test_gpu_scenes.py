@@ -281,3 +281,32 @@ def test_async_device_reset_equals_synchronous_device_reset(K):
     assert int(sa.env_i[abi.EI_EPISODE].max()) >= 5
     for env in envs:
         env.close()
+
+
+@pytest.mark.parametrize("scene", ["intersection", "roundabout"])
+def test_shard_invariance_with_device_resets(scene):
+    """One sim of E envs == two sims of E / 2 envs keyed by the global env index (what each rank of a multi-GPU run holds), bit
+    for bit, through device-side resets, spawns and (intersection) the asynchronous regeneration."""
+    torch = _torch()
+    from topotrafficrl_b200 import TTRLVectorEnv
+    E = 1024
+    whole = TTRLVectorEnv(E, scene, seed=13)
+    halves = [TTRLVectorEnv(E // 2, scene, seed=13, first_env=k * E // 2) for k in range(2)]
+    for env in [whole] + halves:
+        env.reset()
+    rng = np.random.default_rng(8)
+    n_actions = whole.single_action_space.n
+    for step in range(25):
+        act = rng.integers(0, n_actions, size=E).astype(np.int32)
+        o = whole.step(torch.as_tensor(act, device="cuda"))
+        parts = [h.step(torch.as_tensor(act[k * E // 2:(k + 1) * E // 2], device="cuda")) for k, h in enumerate(halves)]
+        torch.cuda.synchronize()
+        for j in range(4):
+            assert torch.equal(o[j], torch.cat([p[j] for p in parts])), f"output {j} differs at step {step}"
+    sw = whole.get_state()
+    sh = [h.get_state() for h in halves]
+    np.testing.assert_array_equal(sw.veh_d, np.concatenate([s.veh_d for s in sh], axis=1))
+    np.testing.assert_array_equal(sw.veh_i, np.concatenate([s.veh_i for s in sh], axis=1))
+    assert int(sw.env_i[abi.EI_EPISODE].max()) >= 2
+    for env in [whole] + halves:
+        env.close()
