@@ -162,7 +162,16 @@ TT_HD double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi
 // lane geometry: ttrl_env/road/lane.py.  The curved kinds live behind __noinline__ functions so that
 // atan2 / sin / cos exist once in the binary.
 // ------------------------------------------------------------------------------------------------
-TT_HDN void lane_local_curved(const ttrl_lane& l, double px, double py, double& s, double& r) {
+// The curved-lane projection exists twice: inlined into the closest-lane loop (table_row_and_closest: every vehicle x every
+// lane x every sub-step; without the call the compiler overlaps the atan2 / sqrt chain with the neighbouring lanes' work:
+// intersection -5 %, multi-agent -8 %, roundabout -16 %, profiles/r1l_lane_loop.txt) and as ONE out-of-line copy for the rare
+// call sites.  TT_LANE_UNROLL > 1 unrolls that loop (measured slower: 2 -> +1 %, 4 -> +6 .. +17 %).
+#ifndef TT_LANE_UNROLL
+#define TT_LANE_UNROLL 1
+#endif
+#define TT_PRAGMA_(x) _Pragma(#x)
+#define TT_PRAGMA(x) TT_PRAGMA_(x)
+TT_HD void lane_local_curved_inl(const ttrl_lane& l, double px, double py, double& s, double& r) {
     double dx = px - l.ax, dy = py - l.ay;
     if (l.kind == TTRL_LANE_CIRCULAR) {  // lane.py:355-362
         double phi = atan2(dy, dx);
@@ -177,6 +186,7 @@ TT_HDN void lane_local_curved(const ttrl_lane& l, double px, double py, double& 
         r = lat - l.amplitude * sin(l.pulsation * lon + l.phase);
     }
 }
+TT_HDN void lane_local_curved(const ttrl_lane& l, double px, double py, double& s, double& r) { lane_local_curved_inl(l, px, py, s, r); }
 TT_HD void lane_local(const ttrl_lane& l, double px, double py, double& s, double& r) {
     if (l.kind != TTRL_LANE_STRAIGHT) { lane_local_curved(l, px, py, s, r); return; }
     double dx = px - l.ax, dy = py - l.ay;  // lane.py:209-213
@@ -249,10 +259,12 @@ TT_HD int table_row_and_closest(C& c, int v, uint64_t& on_mask) {
     int best = 0;
     double bd = 0;
     uint64_t m = 0;
+    TT_PRAGMA(unroll TT_LANE_UNROLL)
     for (int l = 0; l < c.L; ++l) {
         const ttrl_lane& ln = c.lanes[l];
         double s, r;
-        lane_local_c<C>(ln, px, py, s, r);
+        if (C::kPlain || ln.kind == TTRL_LANE_STRAIGHT) { const double dx = px - ln.ax, dy = py - ln.ay; s = dx * ln.dx + dy * ln.dy; r = dx * (-ln.dy) + dy * ln.dx; }
+        else lane_local_curved_inl(ln, px, py, s, r);
         c.SR[v * c.L + l] = d2{s, r};
         if (lane_on_lane(ln, s, r, 1.0)) m |= 1ull << l;
         double ang = fabs(wrap_to_pi(hd - lane_heading_at_c<C>(ln, s)));
