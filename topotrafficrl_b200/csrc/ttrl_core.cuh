@@ -169,6 +169,30 @@ TT_HD double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi
 #ifndef TT_LANE_UNROLL
 #define TT_LANE_UNROLL 1
 #endif
+// Call boundaries (profiles/r1m_inline.txt).  A __noinline__ function exists once in the binary (less instruction fetch, what
+// the first kernels needed most) but is a scheduling barrier for the code around the call.  With the fetch traffic down, inlining
+// the controllers pays: steering + IDM inlined: highway 1.188 -> 1.120 ms/step; + the regulation predictions / pair tests:
+// intersection 3.29 -> 2.97.  -DTT_NOINL_STEER / _IDM / _REG restore the calls; -DTT_INL_POS inlines the curved-lane position too.
+#if defined(TT_NOINL_STEER)
+#define TT_STEER TT_HDN
+#else
+#define TT_STEER TT_HD
+#endif
+#if defined(TT_NOINL_IDM)
+#define TT_IDM TT_HDN
+#else
+#define TT_IDM TT_HD
+#endif
+#if defined(TT_NOINL_REG)
+#define TT_REG TT_HDN
+#else
+#define TT_REG TT_HD
+#endif
+#if defined(TT_INL_POS)
+#define TT_POS TT_HD
+#else
+#define TT_POS TT_HDN
+#endif
 #define TT_PRAGMA_(x) _Pragma(#x)
 #define TT_PRAGMA(x) TT_PRAGMA_(x)
 TT_HD void lane_local_curved_inl(const ttrl_lane& l, double px, double py, double& s, double& r) {
@@ -193,7 +217,7 @@ TT_HD void lane_local(const ttrl_lane& l, double px, double py, double& s, doubl
     s = dx * l.dx + dy * l.dy;
     r = dx * (-l.dy) + dy * l.dx;
 }
-TT_HDN void lane_position_curved(const ttrl_lane& l, double s, double r, double& px, double& py) {
+TT_POS void lane_position_curved(const ttrl_lane& l, double s, double r, double& px, double& py) {
     if (l.kind == TTRL_LANE_CIRCULAR) {  // lane.py:341-345
         double phi = l.cdir * s / l.radius + l.start_phase;
         double rr = l.radius - r * l.cdir;
@@ -210,7 +234,7 @@ TT_HD void lane_position(const ttrl_lane& l, double s, double r, double& px, dou
     px = l.ax + s * l.dx + r * (-l.dy);  // lane.py:196-201
     py = l.ay + s * l.dy + r * l.dx;
 }
-TT_HDN double lane_heading_sine(const ttrl_lane& l, double s) {  // lane.py:275-280
+TT_POS double lane_heading_sine(const ttrl_lane& l, double s) {  // lane.py:275-280
     return l.heading + atan(l.amplitude * l.pulsation * cos(l.pulsation * s + l.phase));
 }
 TT_HD double lane_heading_at(const ttrl_lane& l, double s) {  // lane.py:203-204, :347-350
@@ -395,7 +419,7 @@ TT_HD void follow_road(C& c, int i) {
 // tan(asin(w)) is evaluated as w / sqrt((1-w)(1+w)) (same value to a few ulp, no asin/tan pair), and the tangent of
 // the returned command comes out as a by-product for Vehicle.step's beta = atan(tan(delta) / 2).
 template <class C>
-TT_HDN double steering_control(C& c, int i, int target_lane, double& tan_steer) {
+TT_STEER double steering_control(C& c, int i, int target_lane, double& tan_steer) {
     const double TAU_PURSUIT = 0.5 * 0.2, KP_LATERAL = 1 / 0.6, KP_HEADING = 1 / 0.2;
     const double MAX_STEER = kPi / 3;
     const ttrl_lane& tl = c.lanes[target_lane];
@@ -513,7 +537,7 @@ TT_HD double desired_gap(C& c, int ego, int front) {
 }
 // IDMVehicle.acceleration behavior.py:150-190 (self_delta = SELF's DELTA, also when ego is another vehicle)
 template <class C>
-TT_HDN double idm_acceleration(C& c, double self_delta, int ego, int front) {
+TT_IDM double idm_acceleration(C& c, double self_delta, int ego, int front) {
     if (ego < 0) return 0.0;
     const ttrl_config& cfg = c.sc->cfg;
     auto* st = c.st;
@@ -959,7 +983,7 @@ TT_HD void regulate_unyield(C& c, int i) {
 }
 // phase R1(k): ControlledVehicle.predict_trajectory_constant_speed (controller.py:236-253) at time 0.25 (k + 1)
 template <class C>
-TT_HDN void regulate_predict(C& c, int i, int k) {
+TT_REG void regulate_predict(C& c, int i, int k) {
     auto* st = c.st;
     const int ln = st->lane[i];
     const double s0 = S_(c, i, ln);
@@ -999,7 +1023,7 @@ TT_HD bool has_corner_inside(double x1, double y1, double c1, double s1, double 
 }
 // one time slice of RegulatedRoad.is_conflict_possible (regulation.py:80-103) for the pair (i, j)
 template <class C>
-TT_HDN bool conflict_at_slice(C& c, int i, int j) {
+TT_REG bool conflict_at_slice(C& c, int i, int j) {
     const double xi = c.pred[0 * C::V + i], yi = c.pred[1 * C::V + i], c1 = c.pred[2 * C::V + i], s1 = c.pred[3 * C::V + i];
     const double xj = c.pred[0 * C::V + j], yj = c.pred[1 * C::V + j], c2 = c.pred[2 * C::V + j], s2 = c.pred[3 * C::V + j];
     const double len = 1.5 * kVehLength, wid = 0.9 * kVehWidth;
