@@ -172,7 +172,7 @@ TT_HD double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi
 // Call boundaries (profiles/r1m_inline.txt).  A __noinline__ function exists once in the binary (less instruction fetch, what
 // the first kernels needed most) but is a scheduling barrier for the code around the call.  With the fetch traffic down, inlining
 // the controllers pays: steering + IDM inlined: highway 1.188 -> 1.120 ms/step; + the regulation predictions / pair tests:
-// intersection 3.29 -> 2.97.  -DTT_NOINL_STEER / _IDM / _REG restore the calls; -DTT_INL_POS inlines the curved-lane position too.
+// intersection 3.29 -> 2.97.  the curved-lane position / sine heading: another 1.3 %.  -DTT_NOINL_STEER / _IDM / _REG / _POS restore the calls.
 #if defined(TT_NOINL_STEER)
 #define TT_STEER TT_HDN
 #else
@@ -188,10 +188,10 @@ TT_HD double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi
 #else
 #define TT_REG TT_HD
 #endif
-#if defined(TT_INL_POS)
-#define TT_POS TT_HD
-#else
+#if defined(TT_NOINL_POS)
 #define TT_POS TT_HDN
+#else
+#define TT_POS TT_HD
 #endif
 #define TT_PRAGMA_(x) _Pragma(#x)
 #define TT_PRAGMA(x) TT_PRAGMA_(x)
