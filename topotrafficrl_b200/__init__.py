@@ -7,6 +7,8 @@ Public surface (mirrors the reference's ``ttrl_env`` / ``ttrl_agent`` names for 
   gymnasium-shaped front ends (``envs.py``), ids ``intersection-v0``, ``intersection-multi-agent-v0/-v1``, ``roundabout-v0``,
   ``u-turn-v0``
 * :class:`QNetRollout` -- batched DQN ``act`` (``agent.py``)
+* ``factory.load_environment / load_agent_config / load_agent`` -- the reference's JSON configuration format (``factory.py``)
+* ``trainer.BatchedDQNAgent / BatchedEvaluation`` -- batched DQN rollout / training driver (``trainer.py``, ``models.py``)
 * :class:`Sim` -- the C ABI as an object (``sim.py``)
 
 Importing the package does not load CUDA; the first use of any class above loads
