@@ -1971,8 +1971,10 @@ TT_HD void reset_cast(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) 
 
 template <class C, class Exec>
 TT_HDN void env_reset(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode, bool aligned = false) {  // cold path: keep it out of the step loop's code
-    if (c.sc->rp.scene == 1) reset_intersection(c, ex, seed, genv, episode, aligned);
-    else if (c.sc->rp.scene == 2) reset_cast(c, ex, seed, genv, episode);
+    // the plain profile only ever resets highways (ttrl_sim_set_reset_params moves a sim with another reset scene to the general
+    // profile): the intersection reset would drag a second copy of the whole sub-step into its kernel
+    if (!C::kPlain && c.sc->rp.scene == 1) reset_intersection(c, ex, seed, genv, episode, aligned);
+    else if (!C::kPlain && c.sc->rp.scene == 2) reset_cast(c, ex, seed, genv, episode);
     else reset_highway(c, ex, seed, genv, episode);
 }
 
