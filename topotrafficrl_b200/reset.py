@@ -137,7 +137,11 @@ class _Cast:
     def _route(self, lane_key, destination):
         if destination is None:
             return None
-        return [(self.table.road_index_of[(f, t)], i) for f, t, i in self.net.plan_route(lane_key, destination)]
+        cache = self.net.__dict__.setdefault("_planned_routes", {})  # the BFS result depends on (lane, destination) only
+        key = (lane_key, destination)
+        if key not in cache:
+            cache[key] = [(self.table.road_index_of[(f, t)], i) for f, t, i in self.net.plan_route(lane_key, destination)]
+        return cache[key]
 
     def ego(self, position, heading: float, speed: float, destination) -> None:
         lane_key = self.net.get_closest_lane_index(position, heading)
