@@ -409,7 +409,7 @@ def run_ours(args, w):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_v, op=dist.ReduceOp.SUM)
     h2d = E * A * 4 + (E * sim.obs_size * 4 if qnet is not None else 0)
-    d2h = E * (sim.obs_size * 4 + 4 + 2) + (E * A * 5 if A > 1 else 0)  # + per-agent rewards / terminal flags
+    d2h = E * (sim.obs_size * 4 + 4 + 2) + E * A * 5  # + per-agent rewards / terminal flags
 
     if rank == 0:
         hbm_peak, peak_kind = _peaks()

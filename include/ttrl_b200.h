@@ -157,6 +157,10 @@ typedef struct ttrl_spawn_draw {
 /* Episode statistics accumulated on device (maps to Evaluation.after_all_episodes, trainer/evaluation.py:325-333) */
 typedef struct ttrl_episode_stats {
     double episodes, total_return, total_length, crashes, arrivals, total_speed, vehicle_steps, env_steps;
+    /* spawn attempts that found a free place on the road but no free vehicle slot (the reference's vehicle list has no
+     * capacity): non-zero means the slot capacity `vcap` is too small for the workload and the episodes DIFFER from the
+     * reference's from that point on */
+    double spawn_capacity_rejects;
 } ttrl_episode_stats;
 
 /* Device-side reset: fresh episodes generated on the GPU with counter-based (Philox) draws
@@ -231,6 +235,25 @@ int ttrl_sim_agent_outputs(ttrl_sim* sim, const float** agent_reward_dev, const 
 /* Redirect those per-agent results into caller-owned device buffers (borrowed; NULL = back to the library's own). */
 int ttrl_sim_set_agent_outputs(ttrl_sim* sim, float* agent_reward_dev, uint8_t* agent_terminated_dev);
 
+/* The step's `info` dict for a batch (AbstractEnv._info abstract.py:169-186, evaluated like the reference right after the
+ * reward and BEFORE IntersectionEnv.step's clear / spawn and before any autoreset), one value per key per env, float64:
+ *   info_dev[TTRL_INFO_SPEED * E + e]     info["speed"]    = self.vehicle.speed (controlled_vehicles[0])
+ *   info_dev[TTRL_INFO_CRASHED * E + e]   info["crashed"]  = self.vehicle.crashed (0 / 1)
+ *   info_dev[(TTRL_INFO_REWARDS + k) * E + e], k = 0..3: info["rewards"], the dict of _rewards(action) in its own key order
+ *     (mean over the controlled vehicles, intersection_env.py:67-76):
+ *       TTRL_REWARD_INTERSECTION: collision_reward, high_speed_reward, arrived_reward, on_road_reward (intersection_env.py:94-104)
+ *       TTRL_REWARD_HIGHWAY:      collision_reward, left_lane_reward, high_speed_reward, on_road_reward (u_turn_env.py:60-71)
+ *       TTRL_REWARD_ROUNDABOUT:   collision_reward, high_speed_reward, lane_change_reward, on_road_reward (roundabout_env.py:57-64)
+ * final_obs_dev float32[E * obs_size]: gymnasium's info["final_observation"] -- with autoreset on, an env that finished in this
+ * step has its first observation of the NEXT episode in obs_dev and its terminal observation (what the reference's step()
+ * returned) here; rows of envs that did not finish are left untouched.  Either pointer may be NULL (= not wanted).
+ * Borrowed device buffers, used by ttrl_sim_step on any stream (the host-buffer step has its own: ttrl_sim_host_info_buffers). */
+enum { TTRL_INFO_SPEED = 0, TTRL_INFO_CRASHED = 1, TTRL_INFO_REWARDS = 2, TTRL_NINFO = 6 };
+int ttrl_sim_set_info_outputs(ttrl_sim* sim, double* info_dev /* [TTRL_NINFO][E] */, float* final_obs_dev /* [E][obs_size] */);
+/* page-locked double info[TTRL_NINFO][E] and float final_obs[E][obs_size], filled by every ttrl_sim_step_pinned /
+ * ttrl_sim_step_host call after ttrl_sim_host_info_buffers was called once (it switches the two outputs on for the host path) */
+int ttrl_sim_host_info_buffers(ttrl_sim* sim, double** info, float** final_obs);
+
 /* Resync / golden capture (host buffers, layout above).  Replaces direct attribute access on
  * Vehicle objects (kinematics.py:34-48, controller.py:35-48, behavior.py:48-64). */
 int ttrl_sim_set_state(ttrl_sim* sim, const double* veh_d, const int32_t* veh_i,
@@ -277,16 +300,22 @@ int ttrl_sim_step_host(ttrl_sim* sim, const int32_t* actions_host, float* obs_ho
  * (they are overwritten by the next call). */
 int ttrl_sim_host_buffers(ttrl_sim* sim, int32_t** actions, float** obs, float** reward, uint8_t** terminated, uint8_t** truncated);
 int ttrl_sim_step_pinned(ttrl_sim* sim, int use_actions);
-/* page-locked float agent_reward[E*K], uint8 agent_terminated[E*K]; filled by ttrl_sim_step_pinned when K > 1 */
+/* page-locked float agent_reward[E*K], uint8 agent_terminated[E*K]; filled by every ttrl_sim_step_pinned call */
 int ttrl_sim_host_agent_buffers(ttrl_sim* sim, float** agent_reward, uint8_t** agent_terminated);
 
-/* Observation only (observation_type.observe() at reset: abstract.py:210). */
+/* Observation only (observation_type.observe() at reset: abstract.py:210); also fills the info buffer of
+ * ttrl_sim_set_info_outputs (speed, crashed, _rewards with no action: the reset's info dict, abstract.py:211). */
 int ttrl_sim_observe(ttrl_sim* sim, float* obs_dev, void* stream);
 
 /* Parity hooks: feed the oracle's RNG draws (spawn decisions; Kinematics "shuffled" permutations). */
 int ttrl_sim_inject_spawn(ttrl_sim* sim, const ttrl_spawn_draw* draws_host /* E records or NULL to clear */);
 int ttrl_sim_inject_shuffle(ttrl_sim* sim, const int32_t* perm_host /* E*K*(obs_vehicles-1) or NULL */);
-/* seed != 0 enables device-side (Philox) spawn draws keyed by (seed, first_global_env + e, episode, step). */
+/* seed != 0 enables device-side (Philox) draws keyed by (seed, first_global_env + e, episode, step): the spawn draws and, for
+ * Kinematics order == "shuffled" without an injected permutation, the row shuffle of every observation (a Fisher-Yates
+ * permutation per (env, agent, step), np_random.shuffle(obs[1:]) observation.py:272-273).  Without a seed and without an
+ * injected permutation the rows of a "shuffled" observation come out in the pre-shuffle order (Road.vehicles list order,
+ * road.py:418-447 with sort=False) and the caller applies its own permutation (the single-env front end does, from the
+ * env's numpy stream). */
 int ttrl_sim_seed(ttrl_sim* sim, uint64_t seed, int64_t first_global_env);
 /* spawn outcome of the last step (1 = a vehicle was appended), int32[E] to host */
 int ttrl_sim_spawn_accepted(ttrl_sim* sim, int32_t* accepted_host);

@@ -146,6 +146,15 @@ class RecordingRng:
     def __init__(self, rng):
         self._rng = rng
         self.log: List[tuple] = []
+        self.perms: List[np.ndarray] = []  # np_random.shuffle(obs[1:]) (observation.py:272-273): new row i = old row perm[i]
+
+    def shuffle(self, x, *a, **k):
+        twin = np.random.Generator(np.random.PCG64())
+        twin.bit_generator.state = self._rng.bit_generator.state
+        idx = np.arange(len(x))
+        twin.shuffle(idx)  # the permutation depends on the stream and the row count only
+        self.perms.append(idx)
+        return self._rng.shuffle(x, *a, **k)
 
     def uniform(self, *a, **k):
         v = self._rng.uniform(*a, **k)

@@ -26,6 +26,25 @@ TOL_SUBSTEP = 1e-9
 TOL_STEP = 1e-6
 
 
+# Reference-shipped env configs (scripts/configs/IntersectionEnv/*.json) pinned as whole seeded episodes
+# (tests/golden/intersection_ep_<name>.npz, written by make_golden.py `episodes`): name -> (config overrides, seeds)
+_KIN_OBS = {"type": "Kinematics", "vehicles_count": 15, "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
+            "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]}, "absolute": True}
+EPISODE_CONFIGS = {
+    # env.json as shipped: "order": "shuffled" (BASELINE configs[0])
+    "envjson": ({"observation": dict(_KIN_OBS, order="shuffled"), "destination": "o1"}, list(range(100, 112))),
+    # env_5fps.json: policy_frequency 5 -> 3 sub-steps per step, regulation ticks not aligned to steps, 75-step episodes
+    "5fps": ({"policy_frequency": 5, "show_history": False, "destination": "o1", "duration": 15,
+              "observation": dict(_KIN_OBS, order="sorted")}, [120, 121, 122]),
+    # env_linear.json / env_multi_model.json with the IDM traffic class: normalize_reward, destination None (drawn per
+    # episode), un-normalised shuffled observation, 9 initial vehicles, spawn probability 0.3
+    "normdest": ({"initial_vehicle_count": 9, "spawn_probability": 0.3, "observation": dict(_KIN_OBS, normalize=False, order="shuffled"),
+                  "normalize_reward": True, "destination": None}, list(range(130, 136))),
+    "straight": ({"destination": "o2"}, [140, 141, 142, 143]),   # env_straight.json
+    "right": ({"destination": "o3"}, [150, 151, 152, 153]),      # env_right.json
+}
+
+
 def golden(name: str):
     return np.load(os.path.join(GOLDEN, name))
 

@@ -57,6 +57,7 @@ struct HostEnv {
     std::vector<uint32_t> lmask, pbits;
     std::vector<double> pred;
     std::vector<float> obs_s;
+    std::vector<uint32_t> perm_s;
     std::vector<int32_t> cell;
     EnvCtx<V, P> c;
     HostEnv(const SceneDev* sc, int vcap) {
@@ -67,9 +68,10 @@ struct HostEnv {
         pred.assign((size_t)4 * V, 0.0);
         pbits.assign((size_t)(V * (V - 1) / 2 + 31) / 32 + 1, 0u);
         obs_s.assign((size_t)(cfg.obs_vehicles * cfg.n_features + 4), 0.f);
+        perm_s.assign((size_t)(2 * cfg.obs_vehicles + 4), 0u);
         cell.assign((size_t)(cfg.grid_w * cfg.grid_h + 4 + TTRL_MAX_TTC_CELLS), 0);
         c.st = &st; c.sc = sc; c.lanes = sc->lanes; c.SR = SR.data(); c.lmask = lmask.data();
-        c.pred = cfg.regulated ? pred.data() : nullptr; c.pbits = cfg.regulated ? pbits.data() : nullptr; c.obs_s = obs_s.data(); c.cell = cell.data();
+        c.pred = cfg.regulated ? pred.data() : nullptr; c.pbits = cfg.regulated ? pbits.data() : nullptr; c.obs_s = obs_s.data(); c.perm_s = perm_s.data(); c.cell = cell.data();
         c.L = cfg.n_lanes; c.vcap = vcap;
         c.gap_den = 2 * sqrt(-cfg.comfort_acc_max * cfg.comfort_acc_min);
         c.tan_max_steer = tan(kPi / 3);
@@ -142,10 +144,12 @@ void emu_observe(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, doubl
 void emu_step(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, const int32_t* actions,
               float* obs, int obs_size, float* reward, uint8_t* terminated, uint8_t* truncated, const ttrl_spawn_draw* draws,
               int32_t* accepted, const int32_t* inv_perm, double* stats, int pool_size, double* pvd, int32_t* pvi, int32_t* pei,
-              double* ped, int autoreset, uint64_t seed, int64_t first_global_env, float* agent_reward, uint8_t* agent_terminated) {
+              double* ped, int autoreset, uint64_t seed, int64_t first_global_env, float* agent_reward, uint8_t* agent_terminated,
+              double* info, float* final_obs) {
     GlobalState g{vd, vi, ei, ed, E, Vs};
     StepIO io{};
     io.agent_reward = agent_reward; io.agent_terminated = agent_terminated;
+    io.info = info; io.final_obs = final_obs;
     io.actions = actions; io.obs = obs; io.reward = reward; io.terminated = terminated; io.truncated = truncated;
     io.draws = draws; io.spawn_accepted = accepted; io.inv_perm = inv_perm; io.stats = stats;
     io.pool = GlobalState{pvd, pvi, pei, ped, pool_size, Vs};

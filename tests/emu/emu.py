@@ -67,13 +67,16 @@ class Emulator:
         acc = np.zeros(E, np.int32)
         self.agent_reward = np.zeros((E, self.K), np.float32)
         self.agent_terminated = np.zeros((E, self.K), np.uint8)
+        self.info = np.zeros((abi.NINFO, E), np.float64)          # ttrl_sim_set_info_outputs
+        self.final_obs = np.zeros((E, self.obs_size), np.float32)
         pool = self.pool
         self.L.emu_step(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(E), C.c_int(st.vcap), _p(a),
                         _p(obs), C.c_int(self.obs_size), _p(reward), _p(term), _p(trunc), draws, _p(acc), _p(inv_perm), _p(stats),
                         C.c_int(pool.num_envs if pool is not None else 0),
                         _p(pool.veh_d) if pool is not None else None, _p(pool.veh_i) if pool is not None else None,
                         _p(pool.env_i) if pool is not None else None, _p(pool.env_d) if pool is not None else None,
-                        C.c_int(int(self.autoreset)), C.c_uint64(seed), C.c_int64(first_env), _p(self.agent_reward), _p(self.agent_terminated))
+                        C.c_int(int(self.autoreset)), C.c_uint64(seed), C.c_int64(first_env), _p(self.agent_reward), _p(self.agent_terminated),
+                        _p(self.info), _p(self.final_obs))
         return obs, reward, term, trunc, acc
 
     def set_reset_params(self, rp):

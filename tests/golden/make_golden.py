@@ -101,6 +101,44 @@ def intersection_steps(seeds, overrides, name, vcap=32):
     rec.save(name)
 
 
+def intersection_episodes(name, overrides, seeds, vcap=32):
+    """Whole seeded episodes of a reference-shipped config through the public API (reset(seed) then step until done):
+    the (s, a, r, s', done) stream incl. the truncated last step, the info dict, the spawn draws and the row
+    permutation np_random.shuffle applied to the observation -- plus the state after reset and after every step."""
+    net = scenes.make_intersection_network()
+    table = net.to_table(scenes.intersection_exit_predicate)
+    env = H.IntersectionEnv(config=overrides)
+    m = env.config["observation"]["vehicles_count"] - 1
+    keys = ("collision_reward", "high_speed_reward", "arrived_reward", "on_road_reward")
+    rec = Rec()
+    rng = np.random.default_rng(2718)
+
+    def info_row(info):
+        return np.array([float(info["speed"]), float(info["crashed"])] + [float(info["rewards"][k]) for k in keys], np.float64)
+
+    for seed in seeds:
+        obs, info = env.reset(seed=seed)
+        proxy = H.RecordingRng(env.np_random)
+        env.np_random = proxy
+        env.road.np_random = proxy
+        rec.add(ep_seed=seed, ep_first=len(rec.d.get("action", [])), reset_obs=np.asarray(obs, np.float32), reset_info=info_row(info))
+        rec.add_state("reset", H.extract_state(env, table, vcap))
+        done = False
+        while not done:
+            a = int(rng.integers(0, 3))
+            proxy.log.clear()
+            proxy.perms.clear()
+            obs, reward, term, trunc, info = env.step(a)
+            perm = proxy.perms[0] if proxy.perms else np.arange(m)
+            rec.add(action=a, draw=draw_array(H.draws_from_log(proxy.log)), perm=np.asarray(perm, np.int32), obs=np.asarray(obs, np.float32),
+                    reward=np.float64(reward), terminated=bool(term), truncated=bool(trunc), info=info_row(info),
+                    agents_rewards=np.array(info["agents_rewards"], np.float64), agents_terminated=np.array(info["agents_terminated"], bool))
+            rec.add_state("after", H.extract_state(env, table, vcap))
+            done = term or trunc
+    rec.add(n_steps=len(rec.d["action"]))
+    rec.save("intersection_ep_%s.npz" % name)
+
+
 def intersection_reset(seeds, vcap=32):
     """Post-reset states + first observation for seeded resets (anchors the host-driven reset)."""
     net = scenes.make_intersection_network()
@@ -367,7 +405,7 @@ def qnet_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kat", "int_sub", "int_steps", "int_reset", "hw", "qnet", "multi", "scripted", "ttc"]
+    which = sys.argv[1:] or ["kat", "int_sub", "int_steps", "int_reset", "hw", "qnet", "multi", "scripted", "ttc", "episodes"]
     if "kat" in which:
         function_kats()
     if "int_sub" in which:
@@ -376,6 +414,10 @@ if __name__ == "__main__":
         intersection_steps(range(100, 112), None, "intersection_steps_kin.npz")
         intersection_steps(range(200, 204), GRID_DENSE, "intersection_steps_grid_dense.npz")
         intersection_steps(range(300, 304), GRID_ROAD, "intersection_steps_grid_road.npz")
+    if "episodes" in which:
+        from tests.common import EPISODE_CONFIGS
+        for name, (over, seeds) in EPISODE_CONFIGS.items():
+            intersection_episodes(name, over, seeds)
     if "int_reset" in which:
         intersection_reset(range(8))
     if "hw" in which:

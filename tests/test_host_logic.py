@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     for n in sorted(names):
         assert hasattr(L, n), f"{n} declared in the header but not exported"
-    assert L.ttrl_abi_version() == 1
+    assert L.ttrl_abi_version() == abi.ABI_VERSION == 2
     sizes = [C.sizeof(x) for x in (abi.Lane, abi.Road, abi.Config, abi.SpawnDraw, abi.EpisodeStats, abi.QnetDesc, abi.ResetParams,
                                    abi.CastMember)]
     assert [L.ttrl_abi_sizeof(i) for i in range(8)] == sizes

@@ -19,7 +19,7 @@ def _run_shard(first, last, seed_actions=0):
     emu = Emulator(cfg, table)
     st = scenes.make_highway_state(last - first, cfgd, seed=5, first_env=first)
     emu.pool, emu.autoreset = st.copy(), True
-    stats = np.zeros((8, last - first))  # per-env accumulators [field][env], like the device buffer
+    stats = np.zeros((len(shard.STAT_FIELDS), last - first))  # per-env accumulators [field][env], like the device buffer
     acts = np.random.default_rng(seed_actions).integers(0, 5, size=(STEPS, E_TOTAL)).astype(np.int32)
     obs = []
     for k in range(STEPS):

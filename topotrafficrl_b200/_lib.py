@@ -65,6 +65,8 @@ def lib():
     L.ttrl_sim_host_agent_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.ttrl_sim_agent_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.ttrl_sim_set_agent_outputs.argtypes = [vp, vp, vp]
+    L.ttrl_sim_set_info_outputs.argtypes = [vp, vp, vp]
+    L.ttrl_sim_host_info_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.ttrl_sim_observe.argtypes = [vp, vp, vp]
     L.ttrl_sim_spawn.argtypes = [vp, vp, dbl, dbl, dbl, dbl, i32, vp]
     L.ttrl_sim_read_stats.argtypes = [vp, C.POINTER(abi.EpisodeStats), i32]
@@ -76,6 +78,8 @@ def lib():
     L.ttrl_qnet_act_injected.argtypes = [vp, vp, i32, dbl, vp, vp, vp, vp]
     L.ttrl_qnet_launch_count.argtypes = [vp]
     L.ttrl_qnet_launch_count.restype = i64
+    if L.ttrl_abi_version() != abi.ABI_VERSION:
+        raise TTRLError(f"{LIB_PATH} has ABI version {L.ttrl_abi_version()}, this package binds version {abi.ABI_VERSION}: rebuild it")
     _lib = L
     return L
 

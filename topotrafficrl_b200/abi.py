@@ -120,7 +120,18 @@ class ResetParams(C.Structure):
 class EpisodeStats(C.Structure):
     _fields_ = [("episodes", C.c_double), ("total_return", C.c_double), ("total_length", C.c_double),
                 ("crashes", C.c_double), ("arrivals", C.c_double), ("total_speed", C.c_double),
-                ("vehicle_steps", C.c_double), ("env_steps", C.c_double)]
+                ("vehicle_steps", C.c_double), ("env_steps", C.c_double), ("spawn_capacity_rejects", C.c_double)]
+
+
+ABI_VERSION = 2
+# ttrl_sim_set_info_outputs: float64 [NINFO][E]
+INFO_SPEED, INFO_CRASHED, INFO_REWARDS, NINFO = 0, 1, 2, 6
+# keys of info["rewards"] per reward type, in the reference's dict order
+REWARD_KEYS = {
+    REWARD_INTERSECTION: ("collision_reward", "high_speed_reward", "arrived_reward", "on_road_reward"),   # intersection_env.py:94-104
+    REWARD_HIGHWAY: ("collision_reward", "left_lane_reward", "high_speed_reward", "on_road_reward"),       # u_turn_env.py:60-71
+    REWARD_ROUNDABOUT: ("collision_reward", "high_speed_reward", "lane_change_reward", "on_road_reward"),  # roundabout_env.py:57-64
+}
 
 
 class QnetDesc(C.Structure):

@@ -42,7 +42,7 @@ constexpr double kPi = 3.141592653589793;
 constexpr int kPred = 11;            // regulation.py:87: np.arange(0.25, 3, 0.25)
 constexpr double kVehLength = 5.0;   // kinematics.py:21
 constexpr double kVehWidth = 2.0;    // kinematics.py:23
-constexpr int kStatFields = 8;       // ttrl_episode_stats
+constexpr int kStatFields = 9;       // ttrl_episode_stats
 // CTA-wide phase alignment points of an aligned env_substep (bit k = point k: 0 sub-step start, 1 before C1,
 // 2 before C2, 3 before integrate, 4 before collide); tuned per capacity in ttrl_kern.cu
 #ifndef TT_ALIGN_MASK
@@ -122,6 +122,7 @@ struct EnvCtx {
     double* pred;            // [4][V] regulation predictions of one time slice (x, y, cos h, sin h); null if not regulated
     uint32_t* pbits;         // [V (V - 1) / 2 bits] pairs in conflict (regulation); null if not regulated
     float* obs_s;            // staging for one Kinematics observation
+    uint32_t* perm_s;        // [2 (obs_vehicles - 1)] device-drawn row shuffle: random keys, then their ranks
     int32_t* cell;           // OccupancyGrid per-cell winner (W*H ints)
     int L;
     int vcap;                // storage capacity (slots per env in HBM), <= V
@@ -157,6 +158,23 @@ TT_HD double lmap(double v, double x0, double x1, double y0, double y1) {  // ut
     return y0 + (v - x0) * (y1 - y0) / (x1 - x0);
 }
 TT_HD double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+
+// counter-based RNG (Philox-4x32-10) of every device-side draw: spawns, resets, observation shuffles
+TT_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+TT_HD void philox4x32(uint32_t ctr[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+        const uint32_t n0 = hi1 ^ ctr[1] ^ k0, n1 = lo1, n2 = hi0 ^ ctr[3] ^ k1, n3 = lo0;
+        ctr[0] = n0; ctr[1] = n1; ctr[2] = n2; ctr[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+TT_HD double u01(uint32_t hi, uint32_t lo) {  // 53-bit uniform in [0,1)
+    const uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
+    return (double)x * (1.0 / 9007199254740992.0);
+}
 
 // ------------------------------------------------------------------------------------------------
 // lane geometry: ttrl_env/road/lane.py.  The curved kinds live behind __noinline__ functions so that
@@ -1380,8 +1398,33 @@ TT_HD int obs_single_size(const ttrl_config& cfg) {  // floats of ONE controlled
 }
 // observation_type.observe(): one observation per controlled vehicle (MultiAgentObservation observation.py:587-603),
 // K consecutive blocks in `out`; `inv_perm` (or null) holds K consecutive row permutations.
+// np_random.shuffle(obs[1:]) (observation.py:272-273) with device draws: row k of the unshuffled observation gets a 32-bit
+// Philox key keyed by (seed, global env, episode, env.steps, agent, k); its rank among the keys is its new row -- a uniform
+// random permutation, the same for any team size.  Result: inv_perm[k] in c.perm_s[m ..].
 template <class C, class Exec>
-TT_HD void observe(C& c, Exec& ex, float* out, const int32_t* inv_perm) {
+TT_HD const int32_t* draw_shuffle(C& c, Exec& ex, uint64_t seed, int64_t genv, int agent) {
+    const int m = c.sc->cfg.obs_vehicles - 1;
+    auto* st = c.st;
+    ex.parn(m, [&](int k) {
+        uint32_t c4[4] = {(uint32_t)genv, (uint32_t)((uint64_t)genv >> 32), (uint32_t)st->episode ^ ((uint32_t)st->steps * 0x9E3779B1u),
+                          0x53000000u | ((uint32_t)agent << 16) | (uint32_t)k};
+        philox4x32(c4, (uint32_t)seed, (uint32_t)(seed >> 32));
+        c.perm_s[k] = c4[0];
+    });
+    ex.parn(m, [&](int k) {
+        const uint32_t key = c.perm_s[k];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) { const uint32_t kj = c.perm_s[j]; rank += (kj < key || (kj == key && j < k)) ? 1 : 0; }
+        c.perm_s[m + k] = (uint32_t)rank;
+    });
+    return reinterpret_cast<const int32_t*>(c.perm_s + m);
+}
+
+// observation_type.observe(): one observation per controlled vehicle (MultiAgentObservation observation.py:587-603),
+// K consecutive blocks in `out`; `inv_perm` (or null) holds K consecutive row permutations; without one, seed != 0 draws
+// the "shuffled" order on the device.
+template <class C, class Exec>
+TT_HD void observe(C& c, Exec& ex, float* out, const int32_t* inv_perm, uint64_t seed = 0, int64_t genv = 0) {
     const ttrl_config& cfg = c.sc->cfg;
     const int K = n_agents(c);
 #pragma unroll 1
@@ -1389,7 +1432,11 @@ TT_HD void observe(C& c, Exec& ex, float* out, const int32_t* inv_perm) {
         const int ego = K == 1 ? c.st->ego : c.st->egos[k];
         if (!C::kPlain && cfg.obs_type == TTRL_OBS_TTC) observe_ttc(c, ex, out + (size_t)k * obs_single_size(cfg), ego);
         else if (cfg.obs_type == TTRL_OBS_GRID) observe_grid(c, ex, out + (size_t)k * obs_single_size(cfg), ego);
-        else observe_kinematics(c, ex, out + (size_t)k * obs_single_size(cfg), inv_perm ? inv_perm + k * (cfg.obs_vehicles - 1) : nullptr, ego);
+        else {
+            const int32_t* perm = inv_perm ? inv_perm + k * (cfg.obs_vehicles - 1) : nullptr;
+            if (!perm && seed != 0 && cfg.order == TTRL_ORDER_SHUFFLED && cfg.obs_vehicles > 1) perm = draw_shuffle(c, ex, seed, genv, k);
+            observe_kinematics(c, ex, out + (size_t)k * obs_single_size(cfg), perm, ego);
+        }
     }
 }
 
@@ -1406,8 +1453,9 @@ TT_HD bool on_road(C& c, int i) {  // objects.py:199-202
     const int ln = c.st->lane[i];
     return lane_on_lane(c.lanes[ln], S_(c, i, ln), R_(c, i, ln), 0.0);
 }
+// `rc` (or null): the four entries of _agent_rewards / _rewards in the reference's key order (include/ttrl_b200.h: TTRL_INFO_REWARDS)
 template <class C>
-TT_HD double agent_reward(C& c, int i, int raw_action) {  // intersection_env.py:78-104 / u_turn_env.py:39-71 / roundabout_env.py:43-64
+TT_HD double agent_reward(C& c, int i, int raw_action, double* rc = nullptr) {  // intersection_env.py:78-104 / u_turn_env.py:39-71 / roundabout_env.py:43-64
     const ttrl_config& cfg = c.sc->cfg;
     auto* st = c.st;
     const double crashed = (st->flags[i] & TTRL_FL_CRASHED) ? 1.0 : 0.0;
@@ -1416,6 +1464,7 @@ TT_HD double agent_reward(C& c, int i, int raw_action) {  // intersection_env.py
         const double hs = (double)st->sidx[i] / cfg.speed_index_den;
         const double lc = (raw_action == 0 || raw_action == 2) ? 1.0 : 0.0;
         const double onr = on_road(c, i) ? 1.0 : 0.0;
+        if (rc) { rc[0] = crashed; rc[1] = hs; rc[2] = lc; rc[3] = onr; }
         double reward = 0 + cfg.collision_reward * crashed + cfg.high_speed_reward * hs + cfg.lane_change_reward * lc + 0 * onr;
         if (cfg.normalize_reward) reward = lmap(reward, cfg.collision_reward, cfg.high_speed_reward, 0.0, 1.0);
         reward *= onr;
@@ -1425,6 +1474,7 @@ TT_HD double agent_reward(C& c, int i, int raw_action) {  // intersection_env.py
     const double onr = on_road(c, i) ? 1.0 : 0.0;
     if (!C::kPlain && cfg.reward_type == TTRL_REWARD_INTERSECTION) {
         const bool arrived = has_arrived(c, i);
+        if (rc) { rc[0] = crashed; rc[1] = hs; rc[2] = arrived ? 1.0 : 0.0; rc[3] = onr; }
         double reward = 0 + cfg.collision_reward * crashed + cfg.high_speed_reward * hs + cfg.arrived_reward * (arrived ? 1.0 : 0.0) + 0 * onr;
         reward = arrived ? cfg.arrived_reward : reward;
         reward *= onr;
@@ -1434,6 +1484,7 @@ TT_HD double agent_reward(C& c, int i, int raw_action) {  // intersection_env.py
     const ttrl_lane& l = c.lanes[st->lane[i]];
     const int nl = c.sc->roads[l.road].n_lanes;
     const double lane_term = (double)l.lane_id / (double)(nl - 1 > 1 ? nl - 1 : 1);
+    if (rc) { rc[0] = crashed; rc[1] = lane_term; rc[2] = hs; rc[3] = onr; }
     double reward = 0 + cfg.collision_reward * crashed + cfg.lane_reward * lane_term + cfg.high_speed_reward * hs + 0 * onr;
     if (cfg.normalize_reward) reward = lmap(reward, cfg.collision_reward, cfg.high_speed_reward + cfg.lane_reward, 0.0, 1.0);
     reward *= onr;
@@ -1456,6 +1507,23 @@ TT_HD bool is_terminated(C& c) {  // intersection_env.py:106-111 / u_turn_env.py
         return any_crashed || all_arrived || off;
     }
     return crashed || off;
+}
+
+// AbstractEnv._info (abstract.py:169-186) of the current state without a step (reset: abstract.py:211): speed, crashed and
+// _rewards(action) with `raw_actions` (or null: no action) -- by one thread
+template <class C>
+TT_HD void write_info(C& c, double* info, int E, int e, const int32_t* raw_actions) {
+    auto* st = c.st;
+    const int K = n_agents(c), ego = st->ego;
+    double rc[4] = {0, 0, 0, 0};
+    for (int k = 0; k < K; ++k) {
+        double rk4[4];
+        (void)agent_reward(c, K == 1 ? ego : st->egos[k], raw_actions ? raw_actions[k] : -1, rk4);
+        for (int q = 0; q < 4; ++q) rc[q] = rc[q] + rk4[q];
+    }
+    info[(size_t)TTRL_INFO_SPEED * E + e] = st->v[ego];
+    info[(size_t)TTRL_INFO_CRASHED * E + e] = (st->flags[ego] & TTRL_FL_CRASHED) ? 1.0 : 0.0;
+    for (int q = 0; q < 4; ++q) info[(size_t)(TTRL_INFO_REWARDS + q) * E + e] = rc[q] / K;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1558,7 +1626,7 @@ template <class C, class Exec>
 TT_HD void spawn_vehicle(C& c, Exec& ex, const ttrl_spawn_draw& d, const SpawnParams& sp) {
     auto* st = c.st;
     const SceneDev* sc = c.sc;
-    if (ex.first()) st->flag0 = 0;
+    if (ex.first()) { st->flag0 = 0; st->flag1 = 0; }  // flag0: a vehicle was appended; flag1: no free slot (capacity reject)
     ex.sync();
     if (d.u_spawn > sp.spawn_probability) return;  // uniform: d is per-env
     const int entry = d.entry, exit_ = sp.go_straight ? (d.entry + 2) % 4 : d.exit;
@@ -1572,7 +1640,12 @@ TT_HD void spawn_vehicle(C& c, Exec& ex, const ttrl_spawn_draw& d, const SpawnPa
         const double dx = st->pos[t].x - px, dy = st->pos[t].y - py;
         return sqrt(dx * dx + dy * dy) < 15;
     });
-    if (too_close || st->n >= c.vcap) return;
+    if (too_close) return;
+    if (st->n >= c.vcap) {  // uniform (shared memory).  The reference's list has no capacity: counted in ttrl_episode_stats
+        if (ex.first()) st->flag1 = 1;
+        ex.sync();
+        return;
+    }
     if (ex.first()) {
         const int s = st->n;
         st->pos[s] = d2{px, py}; st->h[s] = hd; st->v[s] = speed;
@@ -1705,21 +1778,6 @@ TT_HD void store_env(C& c, Exec& ex, const GlobalState& g, int e) {
 // ------------------------------------------------------------------------------------------------
 // counter-based RNG for device-side spawn draws (Philox-4x32-10), keyed by (seed, global env, step, draw)
 // ------------------------------------------------------------------------------------------------
-TT_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
-TT_HD void philox4x32(uint32_t ctr[4], uint32_t k0, uint32_t k1) {
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = mulhi32(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
-        const uint32_t hi1 = mulhi32(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
-        const uint32_t n0 = hi1 ^ ctr[1] ^ k0, n1 = lo1, n2 = hi0 ^ ctr[3] ^ k1, n3 = lo0;
-        ctr[0] = n0; ctr[1] = n1; ctr[2] = n2; ctr[3] = n3;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-}
-TT_HD double u01(uint32_t hi, uint32_t lo) {  // 53-bit uniform in [0,1)
-    const uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
-    return (double)x * (1.0 / 9007199254740992.0);
-}
 // `counter` = steps | episode << 32 for the per-step spawn, (1 << 63) | episode << 8 | attempt for the reset attempts
 TT_HDN void device_spawn_draw(uint64_t seed, int64_t global_env, uint64_t counter, ttrl_spawn_draw& d) {
     const uint32_t ctr = (uint32_t)counter ^ ((uint32_t)(counter >> 32) * 0x9E3779B1u);
@@ -1993,6 +2051,8 @@ struct StepIO {
     int32_t* spawn_accepted;       // [E] or null
     const int32_t* inv_perm;       // [E][K][obs_vehicles-1] or null
     double* stats;                 // [kStatFields][E] per-env accumulators
+    double* info;                  // [TTRL_NINFO][E] or null: info["speed"], ["crashed"], ["rewards"] (abstract.py:169-186)
+    float* final_obs;              // [E][obs_size] or null: terminal observation of the envs that finish in this step
     GlobalState pool;              // reset pool (pool.E == 0: none)
     int32_t* done_list;            // device autoreset with warm-up: finished envs are queued here (done_count) and reset by
     int32_t* done_count;           //   k_reset_list right after the step, packed and phase-aligned; null: reset inside the step
@@ -2031,13 +2091,14 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
     }
     float* obs = io.obs ? io.obs + (size_t)e * io.obs_size : nullptr;
     const int32_t* perm = io.inv_perm ? io.inv_perm + (size_t)e * K * (cfg.obs_vehicles - 1) : nullptr;
-    if (obs) observe(c, ex, obs, perm);
+    if (obs) observe(c, ex, obs, perm, io.seed, io.first_global_env + e);
     // reward / flags / episode accounting by the first thread
     if (ex.first()) {
         const int ego = st->ego;
         double r;
+        double rc[4] = {0, 0, 0, 0};  // info["rewards"] (mean over the controlled vehicles, intersection_env.py:67-76)
         if (K == 1) {
-            r = agent_reward(c, ego, actions ? actions[0] : -1);
+            r = agent_reward(c, ego, actions ? actions[0] : -1, io.info ? rc : nullptr);
             if (io.agent_reward) io.agent_reward[e] = (float)r;
             if (io.agent_terminated) io.agent_terminated[e] = ((st->flags[ego] & TTRL_FL_CRASHED) || (!C::kPlain && has_arrived(c, ego))) ? 1 : 0;
         } else {  // sum(agent rewards) / len(controlled_vehicles) (intersection_env.py:61-65)
@@ -2045,12 +2106,21 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
 #pragma unroll 1
             for (int k = 0; k < K; ++k) {
                 const int v = st->egos[k];
-                const double rk = agent_reward(c, v, actions ? actions[k] : -1);
+                double rk4[4];
+                const double rk = agent_reward(c, v, actions ? actions[k] : -1, rk4);
                 sum = sum + rk;
+                for (int q = 0; q < 4; ++q) rc[q] = rc[q] + rk4[q];
                 if (io.agent_reward) io.agent_reward[(size_t)e * K + k] = (float)rk;
                 if (io.agent_terminated) io.agent_terminated[(size_t)e * K + k] = ((st->flags[v] & TTRL_FL_CRASHED) || has_arrived(c, v)) ? 1 : 0;  // _agent_is_terminal :113-115
             }
             r = sum / K;
+            for (int q = 0; q < 4; ++q) rc[q] = rc[q] / K;
+        }
+        if (io.info) {  // AbstractEnv._info abstract.py:169-186: self.vehicle = controlled_vehicles[0]
+            const size_t E = (size_t)g.E;
+            io.info[TTRL_INFO_SPEED * E + e] = st->v[ego];
+            io.info[TTRL_INFO_CRASHED * E + e] = (st->flags[ego] & TTRL_FL_CRASHED) ? 1.0 : 0.0;
+            for (int q = 0; q < 4; ++q) io.info[(TTRL_INFO_REWARDS + q) * E + e] = rc[q];
         }
         const bool term = is_terminated(c), trunc = st->time >= cfg.duration;
         if (io.reward) io.reward[e] = (float)r;
@@ -2074,6 +2144,11 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
         }
     }
     ex.sync();
+    // gymnasium's info["final_observation"]: the autoreset below replaces the terminal observation in `obs`
+    if (io.final_obs && obs && st->done && io.autoreset != TTRL_AUTORESET_OFF) {  // uniform: st->done is in shared memory
+        float* fo = io.final_obs + (size_t)e * io.obs_size;
+        ex.parn(io.obs_size, [&](int k) { fo[k] = obs[k]; });  // written by this team above, barrier since
+    }
     if (!C::kPlain && cfg.spawn_enabled) {
         clear_vehicles(c, ex);
         ttrl_spawn_draw d;
@@ -2084,6 +2159,7 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
             SpawnParams sp{0.0, 1.0, 1.0, cfg.spawn_probability, 0};
             spawn_vehicle(c, ex, d, sp);
             if (io.spawn_accepted && ex.first()) io.spawn_accepted[e] = st->flag0;
+            if (io.stats && ex.first() && st->flag1) io.stats[(size_t)8 * g.E + e] += 1;  // spawn_capacity_rejects
         } else if (io.spawn_accepted && ex.first()) {
             io.spawn_accepted[e] = 0;
         }
@@ -2101,7 +2177,7 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
         }
         if (from_shadow) {
             load_env<true>(c, ex, io.shadow, e);  // episode, time, counters come with the record (env_reset wrote them)
-            if (obs) observe(c, ex, obs, perm);
+            if (obs) observe(c, ex, obs, perm, io.seed, io.first_global_env + e);
         }
         if (ex.first()) {
             if (!from_shadow) io.done_list[ex.atomic_add_global(io.done_count, 1)] = e;
@@ -2117,7 +2193,7 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
         const int episode = st->episode + 1;
         ex.sync();
         env_reset(c, ex, io.seed, io.first_global_env + e, episode);
-        if (obs) observe(c, ex, obs, perm);
+        if (obs) observe(c, ex, obs, perm, io.seed, io.first_global_env + e);
     } else if (st->done && io.autoreset == TTRL_AUTORESET_POOL && io.pool.E > 0) {
         const int episode = st->episode + 1;
         const int slot = (int)(((long long)e + (long long)episode * g.E) % io.pool.E);
@@ -2125,7 +2201,7 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
         load_env(c, ex, io.pool, slot);
         if (ex.first()) { st->episode = episode; st->done = 0; }
         ex.sync();
-        if (obs) observe(c, ex, obs, perm);
+        if (obs) observe(c, ex, obs, perm, io.seed, io.first_global_env + e);
     }
     store_env(c, ex, g, e);
 }

@@ -148,6 +148,7 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V, P>& c, unsigned char* smem_ct
     c.pred = lay.off_pred >= 0 ? reinterpret_cast<double*>(smem + lay.off_pred) : nullptr;
     c.pbits = lay.off_pred >= 0 ? reinterpret_cast<uint32_t*>(smem + lay.off_pred + sizeof(double) * 4 * V) : nullptr;
     c.obs_s = reinterpret_cast<float*>(smem + lay.off_obs);
+    c.perm_s = reinterpret_cast<uint32_t*>(smem + lay.off_perm);
     c.cell = reinterpret_cast<int32_t*>(smem + lay.off_cell);
     c.gap_den = 2 * sqrt(-sc->cfg.comfort_acc_max * sc->cfg.comfort_acc_min);  // behavior.py:214-216
     c.tan_max_steer = tan(kPi / 3);
@@ -193,11 +194,14 @@ __global__ void __launch_bounds__(TeamOf<V>::T) k_substep(const SceneDev* __rest
 
 template <int V>
 __global__ void __launch_bounds__(TeamOf<V>::T) k_observe(const SceneDev* __restrict__ sc, GlobalState g, float* __restrict__ obs, int obs_size,
-                                                          const int32_t* __restrict__ inv_perm, SmemLayout lay) {
+                                                          const int32_t* __restrict__ inv_perm, uint64_t seed, int64_t first_global_env,
+                                                          double* __restrict__ info, SmemLayout lay) {
     TT_KERNEL_PROLOGUE
     const int e = blockIdx.x;
     load_env(c, ex, g, e);
-    observe(c, ex, obs + (size_t)e * obs_size, inv_perm ? inv_perm + (size_t)e * n_agents(c) * (sc->cfg.obs_vehicles - 1) : nullptr);
+    observe(c, ex, obs + (size_t)e * obs_size, inv_perm ? inv_perm + (size_t)e * n_agents(c) * (sc->cfg.obs_vehicles - 1) : nullptr,
+            seed, first_global_env + e);
+    if (info && ex.first()) write_info(c, info, g.E, e, nullptr);
 }
 
 template <int V>
@@ -254,7 +258,8 @@ k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayo
             const int episode = g.ei[TTRL_EI_EPISODE * g.E + e] + 1;
             env_reset(c, ex, io.seed, io.first_global_env + e, episode, true);
             if (io.obs) observe(c, ex, io.obs + (size_t)e * io.obs_size,
-                                io.inv_perm ? io.inv_perm + (size_t)e * n_agents(c) * (sc->cfg.obs_vehicles - 1) : nullptr);
+                                io.inv_perm ? io.inv_perm + (size_t)e * n_agents(c) * (sc->cfg.obs_vehicles - 1) : nullptr,
+                                io.seed, io.first_global_env + e);
             store_env(c, ex, g, e);
         } else {
             const int n_align = env_reset_align_count(sc);
@@ -310,6 +315,7 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
     l.off_lmask = (int)off; off += align_up(sizeof(uint32_t) * ((V + 31) / 32) * cfg.n_lanes, 16);
     if (cfg.regulated) { l.off_pred = (int)off; off += sizeof(double) * 4 * V + align_up(sizeof(uint32_t) * ((V * (V - 1) / 2 + 31) / 32), 16); } else l.off_pred = -1;
     l.off_obs = (int)off; off += align_up(sizeof(float) * (cfg.obs_type == TTRL_OBS_KINEMATICS ? cfg.obs_vehicles * cfg.n_features : 4), 16);
+    l.off_perm = (int)off; off += align_up(sizeof(uint32_t) * 2 * (cfg.obs_type == TTRL_OBS_KINEMATICS && cfg.order == TTRL_ORDER_SHUFFLED && cfg.obs_vehicles > 1 ? cfg.obs_vehicles - 1 : 0), 16);
     l.off_cell = (int)off; off += align_up(sizeof(int32_t) * (cfg.obs_type == TTRL_OBS_GRID ? cfg.grid_w * cfg.grid_h :
                                                                 cfg.obs_type == TTRL_OBS_TTC ? TTRL_MAX_TTC_CELLS : 4), 16);
     l.per_env = (int)align_up(off, 128);
@@ -377,8 +383,8 @@ static void launch_substep(int E, const SmemLayout& lay, cudaStream_t st, const 
 }
 template <int V>
 static void launch_observe(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, float* obs, int obs_size,
-                           const int32_t* inv_perm) {
-    k_observe<V><<<E, TeamOf<V>::T, lay.total, st>>>(sc, g, obs, obs_size, inv_perm, lay);
+                           const int32_t* inv_perm, uint64_t seed, int64_t first_global_env, double* info) {
+    k_observe<V><<<E, TeamOf<V>::T, lay.total, st>>>(sc, g, obs, obs_size, inv_perm, seed, first_global_env, info, lay);
 }
 template <int V>
 static void launch_spawn(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const ttrl_spawn_draw* draws,

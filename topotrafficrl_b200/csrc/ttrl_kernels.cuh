@@ -8,7 +8,7 @@ namespace ttrl {
 
 struct SmemLayout {
     // offsets inside one env's region; a CTA's dynamic shared memory = lane table (lanes_bytes) + G env regions (per_env)
-    int off_SR, off_lmask, off_pred, off_obs, off_cell, lanes_bytes, per_env, total, total_step, G, plain, n_sms;
+    int off_SR, off_lmask, off_pred, off_obs, off_perm, off_cell, lanes_bytes, per_env, total, total_step, G, plain, n_sms;
 };
 
 // One set of launchers per compiled slot capacity.
@@ -19,7 +19,7 @@ struct KernelSet {
     void (*step)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io);
     void (*substep)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const int32_t* actions);
     void (*observe)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, float* obs, int obs_size,
-                    const int32_t* inv_perm);
+                    const int32_t* inv_perm, uint64_t seed, int64_t first_global_env, double* info);
     void (*spawn)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const ttrl_spawn_draw* draws,
                   SpawnParams sp, int32_t* accepted);
     void (*reset)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const uint8_t* mask, uint64_t seed,

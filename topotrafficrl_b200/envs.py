@@ -72,6 +72,8 @@ class AbstractEnv(Env):
         self.cfg = scenes.build_config(self.table, self.config, self.SCENE, ego_lanes_count=self.EGO_LANES)
         self.sim = Sim(self.cfg, self.table, 1, self.VCAP, self.device_index, self._spawn_routes())
         self.sim.set_autoreset(False)
+        self.sim.host_info(copy=False)  # info["speed"], ["crashed"], ["rewards"] of every step_host call
+        self._info_dev = None
         self.num_agents = K = self.sim.num_agents
         shape = scenes.obs_shape(self.cfg)
         self._obs_shape = shape
@@ -121,14 +123,18 @@ class AbstractEnv(Env):
         import torch
 
         buf = torch.zeros(self.sim.obs_size, dtype=torch.float32, device=f"cuda:{self.device_index}")
+        if self._info_dev is None:
+            self._info_dev = torch.zeros((abi.NINFO, 1), dtype=torch.float64, device=f"cuda:{self.device_index}")
+            self.sim.set_info_outputs_ptr(self._info_dev.data_ptr(), None)
         self.sim.observe_ptr(buf.data_ptr(), int(torch.cuda.current_stream().cuda_stream))
         return buf.cpu().numpy()
 
-    def _info(self, action) -> dict:
-        st = self.sim.get_state()
-        ego = int(st.env_i[abi.EI_EGO, 0])
-        return {"speed": float(st.veh_d[abi.D_SPEED, 0, ego]),
-                "crashed": bool(st.veh_i[abi.I_FLAGS, 0, ego] & abi.FL_CRASHED), "action": action}
+    def _info(self, action, after_step: bool = False) -> dict:
+        """``AbstractEnv._info`` (abstract.py:169-186): evaluated on the device together with the reward (before the
+        clear / spawn of ``IntersectionEnv.step``); at reset by the observation kernel, with no action."""
+        buf = self.sim.host_info(copy=False)[0][:, 0] if after_step else self._info_dev.cpu().numpy()[:, 0]
+        return {"speed": float(buf[abi.INFO_SPEED]), "crashed": bool(buf[abi.INFO_CRASHED]), "action": action,
+                "rewards": {k: float(buf[abi.INFO_REWARDS + i]) for i, k in enumerate(abi.REWARD_KEYS[self.cfg.reward_type])}}
 
     def step(self, action):
         if self.sim is None:
@@ -151,7 +157,7 @@ class AbstractEnv(Env):
             self.np_random.bit_generator.state = saved
         self.time += 1 / self.config["policy_frequency"]
         self.steps += int(self.config["simulation_frequency"] // self.config["policy_frequency"])
-        info = self._info(action)
+        info = self._info(action, after_step=True)
         if self.SCENE == "intersection":  # IntersectionEnv._info (intersection_env.py:121-129)
             if K > 1:
                 ar, at = self.sim.agent_outputs_host()

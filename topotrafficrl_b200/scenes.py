@@ -249,6 +249,11 @@ def build_config(table: NetworkTable, config: dict, scene: str, ego_lanes_count:
     for k, v in idm.items():
         setattr(cfg, k, float(v))
     cfg.regulated = 1 if scene == "intersection" else 0
+    # the class of the surrounding traffic (intersection_env.py:257, roundabout_env.py:337, u_turn_env.py:203)
+    ovt = str(config.get("other_vehicles_type", "ttrl_env.vehicle.behavior.IDMVehicle")).rsplit(".", 1)[-1]
+    if ovt != "IDMVehicle":
+        raise NotImplementedError(f"other_vehicles_type {ovt!r}: only IDMVehicle traffic runs on the device "
+                                  "(LinearVehicle / MultipleModelVehicle would silently change the dynamics)")
     cfg.controlled_vehicles = int(config.get("controlled_vehicles", 1))
     if not 1 <= cfg.controlled_vehicles <= abi.MAX_CONTROLLED:
         # ego k starts on arm k % 4 (intersection_env.py:287-289): a fifth ego would be placed onto the first one

@@ -6,7 +6,8 @@ from __future__ import annotations
 
 from typing import Dict, Tuple
 
-STAT_FIELDS = ("episodes", "total_return", "total_length", "crashes", "arrivals", "total_speed", "vehicle_steps", "env_steps")
+STAT_FIELDS = ("episodes", "total_return", "total_length", "crashes", "arrivals", "total_speed", "vehicle_steps", "env_steps",
+               "spawn_capacity_rejects")
 
 
 def shard_range(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:

@@ -146,7 +146,7 @@ class Sim:
 
     def agent_outputs_host(self, copy: bool = True):
         """info["agents_rewards"] / info["agents_terminated"] of the last ``step_host`` call: float32 [E, K], uint8 [E, K]
-        (filled by the library when K > 1)."""
+        (filled by the library at every ``step_host`` call)."""
         self._pinned_views()
         r, t = self._pinned_agents
         return (r.copy(), t.copy()) if copy else (r, t)
@@ -161,6 +161,25 @@ class Sim:
         """Let ``step_ptr`` write info["agents_rewards"] / ["agents_terminated"] into caller-owned device buffers
         (float32[E*K], uint8[E*K])."""
         check(self._L.ttrl_sim_set_agent_outputs(self._h, agent_reward_ptr, agent_terminated_ptr))
+
+    def set_info_outputs_ptr(self, info_ptr, final_obs_ptr) -> None:
+        """Let ``step_ptr`` write the batched ``info`` (float64 ``[abi.NINFO, E]``: speed, crashed, the four ``rewards`` entries)
+        and gymnasium's ``final_observation`` (float32 ``[E, obs_size]``, rows of the envs that finished) into caller-owned
+        device buffers; ``None`` switches an output off."""
+        check(self._L.ttrl_sim_set_info_outputs(self._h, info_ptr, final_obs_ptr))
+
+    def host_info(self, copy: bool = True):
+        """``(info float64 [abi.NINFO, E], final_obs float32 [E, obs_size])`` of the last ``step_host`` call (page-locked
+        staging buffers; the first call switches the two outputs on for the host-buffer path)."""
+        if getattr(self, "_pinned_info", None) is None:
+            a, b = C.c_void_p(), C.c_void_p()
+            check(self._L.ttrl_sim_host_info_buffers(self._h, C.byref(a), C.byref(b)))
+            E = self.num_envs
+            info = np.ctypeslib.as_array(C.cast(a, C.POINTER(C.c_double)), shape=(abi.NINFO * E,)).reshape(abi.NINFO, E)
+            fo = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_float)), shape=(E * self.obs_size,)).reshape(E, self.obs_size)
+            self._pinned_info = (info, fo)
+        info, fo = self._pinned_info
+        return (info.copy(), fo.copy()) if copy else (info, fo)
 
     def stats(self, reset: bool = False) -> abi.EpisodeStats:
         out = abi.EpisodeStats()

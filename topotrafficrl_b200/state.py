@@ -78,6 +78,10 @@ class SimState:
         return SimState(self.veh_d[:, lo:hi].copy(), self.veh_i[:, lo:hi].copy(),
                         self.env_i[:, lo:hi].copy(), self.env_d[:, lo:hi].copy())
 
+    def select_envs(self, idx) -> "SimState":
+        idx = np.asarray(idx)
+        return SimState(self.veh_d[:, idx].copy(), self.veh_i[:, idx].copy(), self.env_i[:, idx].copy(), self.env_d[:, idx].copy())
+
     def n_vehicles(self) -> np.ndarray:
         return self.env_i[abi.EI_NVEH]
 

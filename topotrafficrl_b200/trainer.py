@@ -12,12 +12,18 @@ half of ``DQNAgent`` (``deep_q_network/abstract.py:37-63, 85-94``, ``deep_q_netw
   ranks (NCCL all-reduce: the one data-path collective of the whole system, as SURVEY.md section 8e anticipates);
 * checkpoints: ``{"state_dict", "optimizer"}`` like ``DQNAgent.save`` (pytorch.py:82-93), interchangeable with the reference.
 
+Every transition is stored like the reference does (``evaluation.py:176-190``, ``abstract.py:37-63``): ``done`` is the
+``terminated`` flag only, so an episode that ends by the time limit is stored with ``terminal=False`` and its REAL next
+state -- the vector env restarts finished envs inside the step kernel and hands their terminal observation back as
+``info["final_observation"]`` (gymnasium autoreset), which ``record`` uses as ``next_state`` for those rows.
+
 Differences from the reference, all forced by batching and stated here:
-* one ``record`` call pushes E (x K agents) transitions and performs ``updates_per_step`` optimiser steps (the reference
-  performs one per transition);
-* the exploration clock advances by E per vector step (one tick per collected env-step, like the reference);
-* finished envs are restarted inside the step kernel, so the observation after a TRUNCATED step belongs to the next
-  episode: such transitions (time-limit only; terminated ones do not bootstrap) are not stored.
+* one ``record`` call pushes E (x K agents) transitions and performs ``updates_per_step`` optimiser steps of ``batch_size``
+  samples (the reference performs one optimiser step per transition): the update-to-data ratio is
+  ``updates_per_step / (E K)`` instead of 1;
+* the replay memory holds at least ``min_memory_steps`` vector steps (``max(memory_capacity, min_memory_steps E K)``
+  transitions): the reference's 15 000 entries are ~1150 episodes, two vector steps of 8192 envs would overwrite them;
+* the exploration clock advances by E per vector step (one tick per collected env-step, like the reference).
 """
 from __future__ import annotations
 
@@ -80,7 +86,7 @@ class BatchedDQNAgent:
                     exploration=dict(method="EpsilonGreedy"), target_update=1, double=True, n_steps=1)
 
     def __init__(self, env, config: Optional[dict] = None, seed: int = 0, rollout_mode: str = "fp32",
-                 updates_per_step: int = 1, refresh_every: int = 1, cuda_graph: bool = False) -> None:
+                 updates_per_step: int = 1, refresh_every: int = 1, cuda_graph: bool = False, min_memory_steps: int = 8) -> None:
         import torch
         from torch.nn import functional as F
 
@@ -105,7 +111,10 @@ class BatchedDQNAgent:
         opt = self.config["optimizer"]
         # cuda_graph: the whole update (minibatch gather, both forwards, the double-DQN target, backward, gradient clamp, Adam
         # step) is captured once in a CUDA graph and replayed: the update is ~150 small launches and otherwise launch-bound
-        self.cuda_graph = bool(cuda_graph)
+        dist = torch.distributed
+        self._world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        # several ranks: the gradient all-reduce sits between backward and the optimiser step, the update runs eagerly
+        self.cuda_graph = bool(cuda_graph) and self._world == 1
         if self.cuda_graph and opt["type"] != "ADAM":
             raise NotImplementedError("cuda_graph=True is implemented for the ADAM optimiser")
         if opt["type"] == "ADAM":
@@ -119,9 +128,18 @@ class BatchedDQNAgent:
             raise ValueError("Unknown optimizer type: {}".format(opt["type"]))
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(seed)
-        self.memory = DeviceReplayMemory(self.config["memory_capacity"], self.obs_shape, self.device, self.gen)
+        capacity = max(int(self.config["memory_capacity"]), int(min_memory_steps) * self.num_envs * self.K)
+        self.memory = DeviceReplayMemory(capacity, self.obs_shape, self.device, self.gen)
+        if self._world > 1:  # every rank starts from rank 0's parameters whatever its seed
+            for p in self.value_net.parameters():
+                dist.broadcast(p.data, src=0)
+            self.target_net.load_state_dict(self.value_net.state_dict())
+        # exploration uniforms are keyed by (seed, row, time): offset the key by the shard's first GLOBAL env so that the
+        # shards of a multi-GPU run do not draw the same uniforms for the same local row
+        first_env = int(getattr(env, "first_env", 0))
         self.rollout = QNetRollout(self.model_config, self.value_net.state_dict(), self.obs_shape, self.n_actions,
-                                   device=self.device.index or 0, exploration=self.config["exploration"], seed=seed, mode=rollout_mode)
+                                   device=self.device.index or 0, exploration=self.config["exploration"],
+                                   seed=(int(seed) + 0x9E3779B1 * first_env) & 0x7FFFFFFFFFFFFFFF, mode=rollout_mode)
         self.updates_per_step, self.refresh_every = int(updates_per_step), int(refresh_every)
         self.steps = 0          # optimiser steps (update_target_network's counter, abstract.py:91-94)
         self.training = True
@@ -143,23 +161,38 @@ class BatchedDQNAgent:
         self.rollout.eval()
 
     # ---- learning -------------------------------------------------------------------------------------------
-    def record(self, state, action, reward, next_state, terminated, truncated=None) -> None:
-        """``AbstractDQNAgent.record`` (abstract.py:37-63) for a batch of E transitions."""
+    def record(self, state, action, reward, next_state, terminated, truncated=None, info=None) -> None:
+        """``AbstractDQNAgent.record`` (abstract.py:37-63) for a batch of E transitions; ``done`` = ``terminated`` like
+        ``Evaluation.step`` passes it (evaluation.py:181-190).  ``info["final_observation"]`` (the vector env's autoreset)
+        replaces ``next_state`` for the envs that finished; without it, rows that ended by the time limit only cannot be
+        stored (their ``next_state`` is the next episode's first observation) and are dropped."""
         if not self.training:
             return
         torch = self.torch
-        keep = torch.ones(self.num_envs, dtype=torch.bool, device=self.device)
-        if truncated is not None:
-            keep = ~(truncated.bool() & ~terminated.bool())  # next_state of a time-limit end belongs to the next episode
         K = self.K
-        s = state.reshape((self.num_envs, K) + self.obs_shape)[keep].reshape((-1,) + self.obs_shape)
-        ns = next_state.reshape((self.num_envs, K) + self.obs_shape)[keep].reshape((-1,) + self.obs_shape)
-        a = action.reshape(self.num_envs, K)[keep].reshape(-1)
-        r = reward[keep].repeat_interleave(K)               # the aggregated reward is shared by the agents (abstract.py:53-55)
-        t = terminated.bool()[keep].repeat_interleave(K)
-        self.memory.push(s, a, r, ns, t)
+        s = state.reshape((self.num_envs, K) + self.obs_shape)
+        ns = next_state.reshape((self.num_envs, K) + self.obs_shape)
+        a = action.reshape(self.num_envs, K)
+        term = terminated.bool()
+        if info is not None and "final_observation" in info:
+            done = info["_final_observation"].bool().view((self.num_envs,) + (1,) * (ns.dim() - 1))
+            ns = torch.where(done, info["final_observation"].reshape(ns.shape), ns)
+            r, t = reward, term
+        elif truncated is not None:
+            keep = ~(truncated.bool() & ~term)
+            s, ns, a, r, t = s[keep], ns[keep], a[keep], reward[keep], term[keep]
+        else:
+            r, t = reward, term
+        # the aggregated reward is shared by the agents (abstract.py:53-55)
+        self.memory.push(s.reshape((-1,) + self.obs_shape), a.reshape(-1), r.repeat_interleave(K), ns.reshape((-1,) + self.obs_shape),
+                         t.repeat_interleave(K))
+        ready = len(self.memory) >= self.config["batch_size"]
+        if self._world > 1:  # the ranks must agree: the optimiser step holds a collective
+            flag = torch.tensor([1 if ready else 0], dtype=torch.int32, device=self.device)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            ready = bool(flag.item())
         for _ in range(self.updates_per_step):
-            if len(self.memory) < self.config["batch_size"]:
+            if not ready:
                 return
             if self.cuda_graph:
                 self._graph_update()
@@ -201,12 +234,12 @@ class BatchedDQNAgent:
         """Capture one update.  The warm-up iterations that torch needs before a capture (lazy optimiser state, cuBLAS
         workspaces) are undone afterwards: parameters and Adam moments are restored in place, so training is unaffected."""
         torch = self.torch
-        dist = torch.distributed
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            raise NotImplementedError("cuda_graph=True with several ranks: the gradient all-reduce is not captured")
         B = int(self.config["batch_size"])
         self._graph_idx = torch.zeros(B, dtype=torch.int64, device=self.device)
         saved = [p.detach().clone() for p in self.value_net.parameters()]
+        # optimiser state as it is NOW (a checkpoint may have been loaded): restored after the warm-up updates below
+        saved_opt = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                     for p, st in self.optimizer.state.items()}
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -220,10 +253,14 @@ class BatchedDQNAgent:
         with torch.no_grad():
             for p, v in zip(self.value_net.parameters(), saved):
                 p.copy_(v)
-            for state in self.optimizer.state.values():
-                for v in state.values():
+            for p_, state in self.optimizer.state.items():
+                old = saved_opt.get(id(p_))
+                for k, v in state.items():
                     if torch.is_tensor(v):
-                        v.zero_()
+                        if old is not None and torch.is_tensor(old.get(k)):
+                            v.copy_(old[k])   # in place: the captured graph updates THESE tensors
+                        else:
+                            v.zero_()
 
     def _graph_update(self) -> None:
         if self._graph is None:
@@ -267,7 +304,21 @@ class BatchedDQNAgent:
         checkpoint = self.torch.load(filename, map_location=self.device)
         self.value_net.load_state_dict(checkpoint["state_dict"])
         self.target_net.load_state_dict(checkpoint["state_dict"])
-        self.optimizer.load_state_dict(checkpoint["optimizer"])
+        if self._graph is not None:
+            # the captured update reads and writes the optimiser's CURRENT state tensors: copy the checkpoint into them
+            # (load_state_dict would rebind the state to new tensors the graph never sees)
+            loaded = checkpoint["optimizer"]["state"]
+            params = [p for g in self.optimizer.param_groups for p in g["params"]]
+            with self.torch.no_grad():
+                for idx, p in enumerate(params):
+                    src = loaded.get(idx, loaded.get(str(idx)))
+                    if src is None:
+                        continue
+                    for k, v in self.optimizer.state[p].items():
+                        if self.torch.is_tensor(v) and k in src:
+                            v.copy_(self.torch.as_tensor(src[k]).to(v.device, v.dtype))
+        else:
+            self.optimizer.load_state_dict(checkpoint["optimizer"])
         self.rollout.load_parameters(self.value_net, self.model_config)
         return filename
 
@@ -302,7 +353,7 @@ class BatchedEvaluation:
             actions = agent.act(prev)
             obs, reward, terminated, truncated, info = env.step(actions)
             if self.training:
-                agent.record(prev, actions, reward, obs, terminated, truncated)
+                agent.record(prev, actions, reward, obs, terminated, truncated, info)
             if log_every and (step + 1) % log_every == 0:
                 s = env.stats()
                 self.history.append(dict(step=step + 1, episodes=s["episodes"], mean_return=s["total_return"] / max(s["episodes"], 1),

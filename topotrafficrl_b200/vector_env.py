@@ -128,7 +128,11 @@ class TTRLVectorEnv:
         self._reward = torch.zeros(E, dtype=torch.float32, device=self.device)
         self._term = torch.zeros(E, dtype=torch.uint8, device=self.device)
         self._trunc = torch.zeros(E, dtype=torch.uint8, device=self.device)
-        self._shuffle_rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence([self.seed_value, self.first_env, 7])))
+        # batched info dict (AbstractEnv._info abstract.py:169-186) and gymnasium's final_observation, written by the step kernel
+        self._info_buf = torch.zeros((abi.NINFO, E), dtype=torch.float64, device=self.device)
+        self._final_obs = torch.zeros((E,) + self.obs_shape, dtype=torch.float32, device=self.device)
+        self.sim.set_info_outputs_ptr(self._info_buf.data_ptr(), self._final_obs.data_ptr())
+        self._reward_keys = abi.REWARD_KEYS[self.cfg.reward_type]
 
     # ------------------------------------------------------------------------------------------------
     def _stream(self) -> int:
@@ -140,7 +144,6 @@ class TTRLVectorEnv:
         self.sim.seed((self.seed_value << 1) | 1, self.first_env)  # device-side Philox draws (spawns, resets)
         if self.reset_mode == "device":
             self.sim.reset_device(None, self._stream())
-            self._maybe_shuffle()
             self.sim.observe_ptr(self._obs.data_ptr(), self._stream())
             return self._obs, {}
         if self.scene == "highway":
@@ -155,24 +158,14 @@ class TTRLVectorEnv:
             st = pool.slice_envs(0, self.num_envs)
             self.sim.set_state(st)
             self.sim.set_reset_pool(pool)
-            self._maybe_shuffle()
             self.sim.observe_ptr(self._obs.data_ptr(), self._stream())
             return self._obs, {}
         else:
             rngs = [gym_np_random(self.seed_value + self.first_env + e)[0] for e in range(self.num_envs)]
             st = reset_intersection(_SimResetBackend(self.sim), rngs, self.net, self.table, self.config, self.cfg)
         self.sim.set_reset_pool(st)
-        self._maybe_shuffle()
         self.sim.observe_ptr(self._obs.data_ptr(), self._stream())
         return self._obs, {}
-
-    def _maybe_shuffle(self) -> None:
-        if self.cfg.obs_type == abi.OBS_KINEMATICS and self.cfg.order == abi.ORDER_SHUFFLED:
-            m = self.cfg.obs_vehicles - 1
-            perm = np.argsort(self._shuffle_rng.random((self.num_envs * self.num_agents, m)), axis=1)
-            inv = np.empty_like(perm)
-            np.put_along_axis(inv, perm, np.broadcast_to(np.arange(m), perm.shape), axis=1)
-            self.sim.inject_shuffle(inv.astype(np.int32))
 
     def step(self, actions):
         """actions: int tensor [E] (``[E, K]`` with K controlled vehicles) on this device (int32 preferred; int64 is converted)."""
@@ -182,23 +175,40 @@ class TTRLVectorEnv:
         if actions.dtype != torch.int32:
             actions = actions.to(torch.int32)
         actions = actions.contiguous()
-        self._maybe_shuffle()
         self.sim.step_ptr(actions.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr(), self._term.data_ptr(),
                           self._trunc.data_ptr(), self._stream())
         return self._obs, self._reward, self._term.bool(), self._trunc.bool(), self._info()
 
     def _info(self) -> dict:
-        if self.num_agents == 1:
-            return {}
-        return {"agents_rewards": self._agent_reward, "agents_terminated": self._agent_term.bool()}
+        """The reference's ``info`` dict with one device tensor per key (views of buffers the next ``step`` overwrites):
+        ``speed`` / ``crashed`` of ``controlled_vehicles[0]``, ``rewards`` = ``_rewards(action)``, ``agents_rewards`` /
+        ``agents_terminated`` (``[E, K]``), and gymnasium's autoreset pair: ``final_observation`` ``[E, ...]`` holds the
+        terminal observation of the envs flagged in ``_final_observation`` (= terminated | truncated; their row of the
+        returned observation already belongs to the next episode)."""
+        buf = self._info_buf
+        info = {"speed": buf[abi.INFO_SPEED], "crashed": buf[abi.INFO_CRASHED] != 0,
+                "rewards": {k: buf[abi.INFO_REWARDS + i] for i, k in enumerate(self._reward_keys)},
+                "agents_rewards": self._agent_reward, "agents_terminated": self._agent_term.bool()}
+        if self.autoreset:
+            info["final_observation"] = self._final_obs
+            info["_final_observation"] = (self._term | self._trunc).bool()
+        return info
 
-    def step_host(self, actions: np.ndarray, copy: bool = True):
-        """numpy in / numpy out.  ``copy=False``: zero-copy views of the page-locked staging buffers (valid until the next call)."""
+    def step_host(self, actions: np.ndarray, copy: bool = True, with_info: bool = False):
+        """numpy in / numpy out.  ``copy=False``: zero-copy views of the page-locked staging buffers (valid until the next call).
+        ``with_info``: also fetch ``speed`` / ``crashed`` / ``rewards`` / ``final_observation`` (extra D2H copies every step)."""
+        if with_info:
+            self.sim.host_info(copy=False)  # switches the info / final-observation outputs of the host-buffer path on
         obs, reward, term, trunc = self.sim.step_host(actions, copy=copy)
-        info = {}
-        if self.num_agents > 1:
-            ar, at = self.sim.agent_outputs_host(copy=copy)
-            info = {"agents_rewards": ar, "agents_terminated": at.view(np.bool_)}
+        ar, at = self.sim.agent_outputs_host(copy=copy)
+        info = {"agents_rewards": ar, "agents_terminated": at.view(np.bool_)}
+        if with_info:
+            buf, fo = self.sim.host_info(copy=copy)
+            info.update({"speed": buf[abi.INFO_SPEED], "crashed": buf[abi.INFO_CRASHED] != 0,
+                         "rewards": {k: buf[abi.INFO_REWARDS + i] for i, k in enumerate(self._reward_keys)}})
+            if self.autoreset:
+                info["final_observation"] = fo.reshape((self.num_envs,) + self.obs_shape)
+                info["_final_observation"] = (term | trunc).view(np.bool_)
         return obs.reshape((self.num_envs,) + self.obs_shape), reward, term.view(np.bool_), trunc.view(np.bool_), info
 
     def get_state(self) -> SimState:
