@@ -40,7 +40,8 @@ typedef struct ttrl_lane {
     int32_t priority;    /* lane.priority (regulation.py:73-76) */
     int32_t forbidden;   /* lane.forbidden (lane.py:111) */
     int32_t is_exit;     /* "il" in _from and "o" in _to (intersection_env.py:352-353, :366-367) */
-    int32_t pad0, pad1;
+    int32_t cache_col;   /* reserved (pass 0): the library numbers the curved lanes here (column of its per-vehicle cache) */
+    int32_t pad1;
     double ax, ay;       /* straight/sine: start; circular: center */
     double dx, dy;       /* straight/sine: unit direction (lane.py:190); lateral = (-dy, dx) */
     double heading;      /* straight/sine: arctan2 of end-start (lane.py:185) */

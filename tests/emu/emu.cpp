@@ -70,7 +70,7 @@ struct HostEnv {
         obs_s.assign((size_t)(cfg.obs_vehicles * cfg.n_features + 4), 0.f);
         perm_s.assign((size_t)(2 * cfg.obs_vehicles + 4), 0u);
         cell.assign((size_t)(cfg.grid_w * cfg.grid_h + 4 + TTRL_MAX_TTC_CELLS), 0);
-        c.st = &st; c.sc = sc; c.lanes = sc->lanes; c.SR = SR.data(); c.lmask = lmask.data();
+        c.st = &st; c.sc = sc; c.lanes = sc->lanes; c.SR = SR.data(); c.NC = sc->n_curved; c.lmask = lmask.data();
         c.pred = cfg.regulated ? pred.data() : nullptr; c.pbits = cfg.regulated ? pbits.data() : nullptr; c.obs_s = obs_s.data(); c.perm_s = perm_s.data(); c.cell = cell.data();
         c.L = cfg.n_lanes; c.vcap = vcap;
         c.gap_den = 2 * sqrt(-cfg.comfort_acc_max * cfg.comfort_acc_min);
@@ -100,6 +100,7 @@ SceneDev* emu_scene_create(const ttrl_config* cfg, const ttrl_lane* lanes, const
     SceneDev* s = (SceneDev*)calloc(1, sizeof(SceneDev));
     s->cfg = *cfg;
     memcpy(s->lanes, lanes, sizeof(ttrl_lane) * cfg->n_lanes);
+    s->n_curved = assign_cache_columns(s->lanes, cfg->n_lanes);
     memcpy(s->roads, roads, sizeof(ttrl_road) * cfg->n_roads);
     memcpy(s->node_first, node_first, sizeof(int32_t) * (cfg->n_nodes + 1));
     memcpy(s->node_roads, node_roads, sizeof(int32_t) * node_first[cfg->n_nodes]);

@@ -47,7 +47,7 @@ QNET_MLP, QNET_EGO_ATTENTION, QNET_DUELING = 0, 1, 2
 class Lane(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("road", C.c_int32), ("lane_id", C.c_int32), ("priority", C.c_int32),
-        ("forbidden", C.c_int32), ("is_exit", C.c_int32), ("pad0", C.c_int32), ("pad1", C.c_int32),
+        ("forbidden", C.c_int32), ("is_exit", C.c_int32), ("cache_col", C.c_int32), ("pad1", C.c_int32),
         ("ax", C.c_double), ("ay", C.c_double), ("dx", C.c_double), ("dy", C.c_double),
         ("heading", C.c_double), ("length", C.c_double), ("width", C.c_double), ("speed_limit", C.c_double),
         ("radius", C.c_double), ("start_phase", C.c_double), ("end_phase", C.c_double), ("cdir", C.c_double),

@@ -64,7 +64,8 @@ struct SceneDev {
     int32_t spawn_route_len[16];
     int32_t spawn_route_road[16 * TTRL_ROUTE_CAP];
     ttrl_reset_params rp;  // device-side reset parameters (have_rp != 0)
-    int32_t have_rp, pad_rp;
+    int32_t have_rp;
+    int32_t n_curved;    // curved lanes = columns of the per-vehicle coordinate cache (assign_cache_columns)
     int32_t F;           // sub-steps per env-step (abstract.py:254-256)
     int32_t reg_period;  // int(1/dt/REGULATION_FREQUENCY) (regulation.py:30)
     double dt;           // 1/simulation_frequency
@@ -117,7 +118,8 @@ struct EnvCtx {
     EnvState<V_>* st;
     const SceneDev* sc;
     const ttrl_lane* lanes;  // lane table (shared-memory copy)
-    d2* SR;                  // [V][L] (longitudinal, lateral) local coordinates of vehicle v in lane l
+    d2* SR;                  // [V][NC] (longitudinal, lateral) local coordinates of vehicle v in CURVED lane column k (sr_of)
+    int NC;                  // curved lanes of the network (columns of SR)
     uint32_t* lmask;         // [L][W] bit v of lane l: vehicle v is on lane l with margin 1 (road.py:503)
     double* pred;            // [4][V] regulation predictions of one time slice (x, y, cos h, sin h); null if not regulated
     uint32_t* pbits;         // [V (V - 1) / 2 bits] pairs in conflict (regulation); null if not regulated
@@ -289,8 +291,27 @@ template <class C> TT_HD double lane_heading_at_c(const ttrl_lane& l, double s) 
 // ------------------------------------------------------------------------------------------------
 // table access
 // ------------------------------------------------------------------------------------------------
-template <class C> TT_HD double& S_(C& c, int v, int l) { return c.SR[v * c.L + l].x; }
-template <class C> TT_HD double& R_(C& c, int v, int l) { return c.SR[v * c.L + l].y; }
+// (s, r) of vehicle v in lane l.  Straight lanes: 6 flops from the position (the same expression as the closest-lane
+// search: bit-identical); curved lanes: the cached result of that search (one atan2 / sin per vehicle, lane and sub-step).
+// Caching only the curved lanes is what lets an SM hold more envs: the full V x L table was the largest shared-memory
+// array of the intersection scene (24 x 20 x 16 B = 7.7 KB of 15.9 KB per env; 8 curved lanes: 3 KB; highway: none).
+template <class C> TT_HD d2 sr_of(C& c, int v, int l) {
+    const ttrl_lane& ln = c.lanes[l];
+    if (C::kPlain || ln.kind == TTRL_LANE_STRAIGHT) {
+        const d2 p = c.st->pos[v];
+        const double dx = p.x - ln.ax, dy = p.y - ln.ay;
+        return d2{dx * ln.dx + dy * ln.dy, dx * (-ln.dy) + dy * ln.dx};
+    }
+    return c.SR[v * c.NC + ln.cache_col];
+}
+template <class C> TT_HD double S_(C& c, int v, int l) { return sr_of(c, v, l).x; }
+template <class C> TT_HD double R_(C& c, int v, int l) { return sr_of(c, v, l).y; }
+// columns of the curved-lane cache (host side: ttrl_sim_create / the test emulator); returns their number
+inline int assign_cache_columns(ttrl_lane* lanes, int n_lanes) {
+    int nc = 0;
+    for (int l = 0; l < n_lanes; ++l) lanes[l].cache_col = lanes[l].kind == TTRL_LANE_STRAIGHT ? -1 : nc++;
+    return nc;
+}
 
 // Rebuild row v of the table and return the closest lane: RoadNetwork.get_closest_lane_index
 // (road.py:55-71, np.argmin keeps the FIRST minimum) over distance_with_heading (lane.py:132-147).
@@ -306,8 +327,7 @@ TT_HD int table_row_and_closest(C& c, int v, uint64_t& on_mask) {
         const ttrl_lane& ln = c.lanes[l];
         double s, r;
         if (C::kPlain || ln.kind == TTRL_LANE_STRAIGHT) { const double dx = px - ln.ax, dy = py - ln.ay; s = dx * ln.dx + dy * ln.dy; r = dx * (-ln.dy) + dy * ln.dx; }
-        else lane_local_curved_inl(ln, px, py, s, r);
-        c.SR[v * c.L + l] = d2{s, r};
+        else { lane_local_curved_inl(ln, px, py, s, r); c.SR[v * c.NC + ln.cache_col] = d2{s, r}; }
         if (lane_on_lane(ln, s, r, 1.0)) m |= 1ull << l;
         double ang = fabs(wrap_to_pi(hd - lane_heading_at_c<C>(ln, s)));
         double d = lane_distance_sr(ln, s, r) + 1.0 * ang;
@@ -441,7 +461,7 @@ TT_STEER double steering_control(C& c, int i, int target_lane, double& tan_steer
     const double TAU_PURSUIT = 0.5 * 0.2, KP_LATERAL = 1 / 0.6, KP_HEADING = 1 / 0.2;
     const double MAX_STEER = kPi / 3;
     const ttrl_lane& tl = c.lanes[target_lane];
-    const d2 sr = c.SR[i * c.L + target_lane];
+    const d2 sr = sr_of(c, i, target_lane);
     const double speed = c.st->v[i];
     double lane_next = sr.x + speed * TAU_PURSUIT;
     double lane_future_heading = lane_heading_at_c<C>(tl, lane_next);
@@ -521,7 +541,6 @@ TT_HD void neighbours(C& c, int i, int lane, int& front, int& rear) {
     const double s = S_(c, i, lane);
     double sf = 0, sr = 0;
     int f = -1, r = -1;
-    const int L = c.L;
 #pragma unroll 1
     for (int w = 0; w < C::W; ++w) {
         uint32_t m = c.lmask[lane * C::W + w];
@@ -534,7 +553,7 @@ TT_HD void neighbours(C& c, int i, int lane, int& front, int& rear) {
 #endif
             m &= m - 1;
             const int j = w * 32 + b;
-            const double sv = c.SR[j * L + lane].x;
+            const double sv = S_(c, j, lane);
             if (s <= sv) { if (f < 0 || sv <= sf) { sf = sv; f = j; } }
             else if (r < 0 || sv > sr) { sr = sv; r = j; }
         }

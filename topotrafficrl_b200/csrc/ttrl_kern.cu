@@ -144,6 +144,7 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V, P>& c, unsigned char* smem_ct
     c.vcap = vcap;
     c.lanes = lanes_s;
     c.SR = reinterpret_cast<d2*>(smem + lay.off_SR);
+    c.NC = sc->n_curved;
     c.lmask = reinterpret_cast<uint32_t*>(smem + lay.off_lmask);
     c.pred = lay.off_pred >= 0 ? reinterpret_cast<double*>(smem + lay.off_pred) : nullptr;
     c.pbits = lay.off_pred >= 0 ? reinterpret_cast<uint32_t*>(smem + lay.off_pred + sizeof(double) * 4 * V) : nullptr;
@@ -311,7 +312,9 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
     SmemLayout l{};
     l.lanes_bytes = (int)align_up(sizeof(ttrl_lane) * cfg.n_lanes, 128);
     size_t off = align_up(sizeof(EnvState<V>), 16);
-    l.off_SR = (int)off; off += sizeof(d2) * vcap * cfg.n_lanes;
+    int n_curved = 0;
+    for (int k = 0; k < cfg.n_lanes; ++k) n_curved += lanes[k].kind != TTRL_LANE_STRAIGHT ? 1 : 0;
+    l.off_SR = (int)off; off += sizeof(d2) * (size_t)vcap * (n_curved > 0 ? n_curved : 1);  // curved-lane coordinate cache
     l.off_lmask = (int)off; off += align_up(sizeof(uint32_t) * ((V + 31) / 32) * cfg.n_lanes, 16);
     if (cfg.regulated) { l.off_pred = (int)off; off += sizeof(double) * 4 * V + align_up(sizeof(uint32_t) * ((V * (V - 1) / 2 + 31) / 32), 16); } else l.off_pred = -1;
     l.off_obs = (int)off; off += align_up(sizeof(float) * (cfg.obs_type == TTRL_OBS_KINEMATICS ? cfg.obs_vehicles * cfg.n_features : 4), 16);
