@@ -181,7 +181,8 @@ def test_full_size_configs3_vs_oracle_with_qnet_in_the_loop():
         ref = env.get_state()
         draws = (abi.SpawnDraw * E)()
         for e in range(E):
-            counter = int(ref.env_i[abi.EI_STEPS, e]) | (int(ref.env_i[abi.EI_EPISODE, e]) << 32)
+            # the spawn of a step is keyed by env.steps AFTER its 15 sub-steps (ttrl_core.cuh: env_step_finish)
+            counter = (int(ref.env_i[abi.EI_STEPS, e]) + 15) | (int(ref.env_i[abi.EI_EPISODE, e]) << 32)
             L.emu_device_spawn_draw(C.c_uint64(seed), C.c_int64(e), C.c_uint64(counter), C.byref(draws[e]))
         a_host = actions.cpu().numpy().astype(np.int32)
         obs, reward, term, trunc, info = env.step(actions)

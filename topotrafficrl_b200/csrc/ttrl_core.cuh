@@ -43,14 +43,6 @@ constexpr int kPred = 11;            // regulation.py:87: np.arange(0.25, 3, 0.2
 constexpr double kVehLength = 5.0;   // kinematics.py:21
 constexpr double kVehWidth = 2.0;    // kinematics.py:23
 constexpr int kStatFields = 9;       // ttrl_episode_stats
-// CTA-wide phase alignment points of an aligned env_substep (bit k = point k: 0 sub-step start, 1 before C1,
-// 2 before C2, 3 before integrate, 4 before collide); tuned per capacity in ttrl_kern.cu
-#ifndef TT_ALIGN_MASK
-#define TT_ALIGN_MASK 0x01
-#endif
-constexpr int kAlignMask = TT_ALIGN_MASK;
-constexpr int kAlignPerSubstep = ((kAlignMask >> 0) & 1) + ((kAlignMask >> 1) & 1) + ((kAlignMask >> 2) & 1) + ((kAlignMask >> 3) & 1) + ((kAlignMask >> 4) & 1);
-
 struct alignas(16) d2 { double x, y; };  // 16-byte pair (one LDS.128 on the device)
 
 // Read-only scene description, resident in global memory (L1/L2 hot: ~12 KB).
@@ -1110,16 +1102,14 @@ TT_HD void regulate_apply(C& c, int i) {
 // one simulation sub-step (AbstractEnv._simulate body abstract.py:257-273)
 // ------------------------------------------------------------------------------------------------
 template <class C, class Exec>
-TT_HD void env_substep(C& c, Exec& ex, const int32_t* actions, bool aligned = false) {  // inlined on purpose: a call boundary here costs ~30 % (ctx spills)
+TT_HD void env_substep(C& c, Exec& ex, const int32_t* actions) {  // inlined on purpose: a call boundary here costs ~30 % (ctx spills)
     // `actions`: this env's raw action ids (one per controlled vehicle) or null (action=None)
-    // `aligned`: the CTA-wide phase alignment points are active (k_step's main loop only; kAlignPerSubstep of them)
     auto* st = c.st;
     const SceneDev* sc = c.sc;
     using ES = EnvState<C::V>;
     const int n = st->n;
     // ego meta-action on the first sub-step of an env-step: DiscreteMetaAction.act action.py:259-260
     const int32_t* first_actions = (actions && st->steps % sc->F == 0) ? actions : nullptr;
-    if (aligned && (kAlignMask & 1)) ex.align();
     ex.parn(n, [&](int t) {
         if (t == 0) { st->n_chg = 0; st->n_pair = 0; st->n_w = 0; st->overflow = 0; }
         act_phase_a(c, ex, t, first_actions);
@@ -1144,12 +1134,10 @@ TT_HD void env_substep(C& c, Exec& ex, const int32_t* actions, bool aligned = fa
             }
         }
     }
-    if (aligned && (kAlignMask & 2)) ex.align();
     ex.parn(n, [&](int t) {
         if (t == 0) { st->n_mob = 0; for (int w = 0; w < C::W; ++w) st->bmask[w] = 0; }
         act_phase_c1(c, ex, t);
     });
-    if (aligned && (kAlignMask & 4)) ex.align();
     ex.parn(n + st->n_chg, [&](int k) { act_phase_c2(c, k); });
     if (!C::kPlain && sc->cfg.regulated) {  // RegulatedRoad.step regulation.py:28-32
         const int rs = st->road_steps + 1;
@@ -1175,10 +1163,8 @@ TT_HD void env_substep(C& c, Exec& ex, const int32_t* actions, bool aligned = fa
             ex.parn(n, [&](int t) { regulate_apply(c, t); });
         }
     }
-    if (aligned && (kAlignMask & 8)) ex.align();
     ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; });
     ex.parn(n, [&](int t) { integrate(c, ex, t); });
-    if (aligned && (kAlignMask & 16)) ex.align();
     collide_all(c, ex);
     if (ex.first()) { st->steps += 1; if (!C::kPlain && sc->cfg.regulated) st->road_steps += 1; }
     ex.sync();
@@ -1770,6 +1756,11 @@ TT_HD void store_env(C& c, Exec& ex, const GlobalState& g, int e) {
     }
     ex.parn(V, [&](int t) {
         const size_t o = (size_t)e * V + t, fs = (size_t)g.E * V;
+        if (t >= C::V) {  // the buffer has more slots than this kernel's capacity (small size class): dead by construction
+            for (int f = 0; f < TTRL_ND; ++f) g.vd[f * fs + o] = 0;
+            for (int f = 0; f < TTRL_NI; ++f) g.vi[f * fs + o] = 0;
+            return;
+        }
         const bool live = t < st->n;
         const int rlen = live ? st->rlen[t] : 0;
         // canonical form: dead slots zero, unused route bytes zero (keeps get_state comparable bit for bit)
@@ -1906,8 +1897,10 @@ TT_HD void reset_highway(C& c, Exec& ex, uint64_t seed, int64_t genv, int episod
 }
 
 // IntersectionEnv._make_vehicles (intersection_env.py:251-318)
+// In three parts, so that the kernels that reset many envs per CTA can run the warm-up sub-steps of all their envs in
+// lockstep (one CTA-wide alignment per sub-step, k_reset_list / k_regen_list): begin, warm-up loop, end.
 template <class C, class Exec>
-TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode, bool aligned) {
+TT_HD void reset_intersection_begin(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) {
     auto* st = c.st;
     const SceneDev* sc = c.sc;
     const ttrl_reset_params& rp = sc->rp;
@@ -1921,7 +1914,13 @@ TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int e
         spawn_vehicle(c, ex, d, sp);
     }
     rebuild_tables(c, ex);
-    for (int k = 0; k < rp.warmup_substeps; ++k) env_substep(c, ex, nullptr, aligned);  // (:267-274) road.act(); road.step(1/sf)
+}
+template <class C, class Exec>
+TT_HD void reset_intersection_end(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) {
+    auto* st = c.st;
+    const SceneDev* sc = c.sc;
+    const ttrl_reset_params& rp = sc->rp;
+    const ttrl_config& cfg = sc->cfg;
     {   // challenger vehicle (:276-277)
         ttrl_spawn_draw d;
         device_spawn_draw(seed, genv, reset_attempt_counter(episode, rp.n_vehicles - 1), d);
@@ -2047,12 +2046,37 @@ TT_HD void reset_cast(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) 
 }
 
 template <class C, class Exec>
-TT_HDN void env_reset(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode, bool aligned = false) {  // cold path: keep it out of the step loop's code
+TT_HD void reset_intersection(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) {
+    reset_intersection_begin(c, ex, seed, genv, episode);
+    for (int k = 0; k < c.sc->rp.warmup_substeps; ++k) env_substep(c, ex, nullptr);  // (:267-274) road.act(); road.step(1/sf)
+    reset_intersection_end(c, ex, seed, genv, episode);
+}
+
+template <class C, class Exec>
+TT_HDN void env_reset(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) {  // cold path: keep it out of the step loop's code
     // the plain profile only ever resets highways (ttrl_sim_set_reset_params moves a sim with another reset scene to the general
     // profile): the intersection reset would drag a second copy of the whole sub-step into its kernel
-    if (!C::kPlain && c.sc->rp.scene == 1) reset_intersection(c, ex, seed, genv, episode, aligned);
+    if (!C::kPlain && c.sc->rp.scene == 1) reset_intersection(c, ex, seed, genv, episode);
     else if (!C::kPlain && c.sc->rp.scene == 2) reset_cast(c, ex, seed, genv, episode);
     else reset_highway(c, ex, seed, genv, episode);
+}
+
+// env_reset for the teams of a multi-env CTA, `active` = this team has an env to reset.  EVERY team of the CTA calls it: the
+// alignment barrier of the warm-up loop is ONE instruction that active and idle teams reach alike -- a CTA barrier executed
+// from different instructions by two sub-warp teams of the same warp deadlocks (tools/probes/bar_divergence.cu).
+template <class C, class Exec>
+TT_HD void env_reset_lockstep(C& c, Exec& ex, bool active, uint64_t seed, int64_t genv, int episode) {
+    if (C::kPlain || c.sc->rp.scene != 1) {  // uniform over the CTA: no warm-up sub-steps
+        if (active) env_reset(c, ex, seed, genv, episode);
+        return;
+    }
+    if (active) reset_intersection_begin(c, ex, seed, genv, episode);
+    const int warmup = c.sc->rp.warmup_substeps;
+    for (int k = 0; k < warmup; ++k) {
+        ex.align();
+        if (active) env_substep(c, ex, nullptr);
+    }
+    if (active) reset_intersection_end(c, ex, seed, genv, episode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2087,27 +2111,34 @@ struct StepIO {
     uint64_t seed;
     int64_t first_global_env;
     int obs_size;
+    // Env classification of this step (k_classify; null: CTA b, team t steps env b G + t).  The envs are binned by
+    // (size class, regulation phase): cls_list[b * E ..] holds the cls_count[b] envs of bin b, and a launch covers the bins
+    // cls_first .. cls_first + cls_n - 1, every CTA taking G envs of ONE bin.  Phase bins keep the teams of a CTA on the same
+    // regulation ticks (RegulatedRoad.step regulation.py:28-32 fires every 7th road step, at a phase that depends on the env's
+    // episode length so far): the per-sub-step alignment barrier otherwise makes every sub-step wait for the few teams that tick.
+    // Size classes let envs that currently hold few vehicles run in a kernel instantiated for a smaller slot capacity.
+    const int32_t* cls_list;
+    const int32_t* cls_count;
+    int cls_first, cls_n;
 };
+constexpr int kClsPhases = 8;              // regulation phase bins per size class
+constexpr int kClsBins = 2 * kClsPhases;   // size class 0 (small) bins 0..7, class 1 (large) bins 8..15
 
-// number of Exec::align() calls one env_step makes (teams without an env replay them)
-TT_HD int env_step_align_count(const SceneDev* sc) { return sc->F * kAlignPerSubstep; }
-TT_HD int env_reset_align_count(const SceneDev* sc) { return sc->rp.scene == 1 ? sc->rp.warmup_substeps * kAlignPerSubstep : 0; }
-
+// env_step in three parts (load, F sub-steps, finish) so that k_step can run the sub-steps of the envs of a CTA in lockstep,
+// with the alignment barrier as ONE instruction outside the per-team branches (see env_reset_lockstep).
 template <class C, class Exec>
-TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int e) {
+TT_HD void env_step_load(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int e) {
+    load_env(c, ex, g, e);
+    if (ex.first()) c.st->time += 1 / c.sc->cfg.policy_frequency;
+    ex.sync();
+}
+template <class C, class Exec>
+TT_HD void env_step_finish(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int e, double veh_steps) {
     auto* st = c.st;
     const SceneDev* sc = c.sc;
     const ttrl_config& cfg = sc->cfg;
-    load_env(c, ex, g, e);
     const int K = n_agents(c);
     const int32_t* actions = io.actions ? io.actions + (size_t)e * K : nullptr;
-    if (ex.first()) st->time += 1 / cfg.policy_frequency;
-    ex.sync();
-    double veh_steps = 0;
-    for (int f = 0; f < sc->F; ++f) {
-        env_substep(c, ex, actions, true);
-        veh_steps += st->n;
-    }
     float* obs = io.obs ? io.obs + (size_t)e * io.obs_size : nullptr;
     const int32_t* perm = io.inv_perm ? io.inv_perm + (size_t)e * K * (cfg.obs_vehicles - 1) : nullptr;
     if (obs) observe(c, ex, obs, perm, io.seed, io.first_global_env + e);
@@ -2223,6 +2254,17 @@ TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int 
         if (obs) observe(c, ex, obs, perm, io.seed, io.first_global_env + e);
     }
     store_env(c, ex, g, e);
+}
+template <class C, class Exec>
+TT_HD void env_step(C& c, Exec& ex, const GlobalState& g, const StepIO& io, int e) {
+    env_step_load(c, ex, g, io, e);
+    const int32_t* actions = io.actions ? io.actions + (size_t)e * n_agents(c) : nullptr;
+    double veh_steps = 0;
+    for (int f = 0; f < c.sc->F; ++f) {
+        env_substep(c, ex, actions);
+        veh_steps += c.st->n;
+    }
+    env_step_finish(c, ex, g, io, e, veh_steps);
 }
 
 }  // namespace ttrl

@@ -25,15 +25,24 @@ using namespace ttrl;
 // ------------------------------------------------------------------------------------------------
 template <int V, int T>
 struct DevExec {
-    int tid;    // thread within the team
-    int G;      // teams in this CTA (1 unless T == 32)
+    int tid;        // thread within the team
+    int G;          // teams in this CTA (1 unless T <= 32)
+    unsigned mask;  // T <= 32: the team's lanes of its warp (a sub-warp team shares the warp with 32 / T - 1 other envs)
+    int lane;       // lane within the warp
+    __device__ __forceinline__ DevExec(int tid_, int G_) : tid(tid_), G(G_) {
+        lane = (int)(threadIdx.x & 31u);
+        mask = T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (lane & ~(T - 1)));
+    }
     __device__ __forceinline__ bool first() const { return tid == 0; }
     __device__ __forceinline__ void sync() {
-        if (T == 32) __syncwarp(); else __syncthreads();
+        if (T <= 32) __syncwarp(mask); else __syncthreads();
     }
     // CTA-wide phase alignment; every team of the CTA calls it the same number of times
     __device__ __forceinline__ void align() {
-        if (T == 32 && G > 1) __syncthreads();
+#if defined(TT_NO_ALIGN)
+        return;  // experiment: free-running teams
+#endif
+        if (T <= 32 && G > 1) __syncthreads();
     }
     template <class F> __device__ __forceinline__ void par(F f) {
 #pragma unroll 1
@@ -49,7 +58,7 @@ struct DevExec {
         int p = 0;
 #pragma unroll 1
         for (int t = tid; t < n; t += T) p |= f(t) ? 1 : 0;
-        if (T == 32) return __any_sync(0xffffffffu, p) != 0;
+        if (T <= 32) return __ballot_sync(mask, p) != 0;
         return __syncthreads_or(p) != 0;
     }
     template <class F1, class F2> __device__ __forceinline__ void par2(F1 f1, F2 f2) {
@@ -66,6 +75,8 @@ struct DevExec {
     // 8 lanes per candidate pair, one separating axis each; the pair's result is reduced with shuffles:
     // intersecting / will_intersect = no lane reports a separation, translation axis = first axis of minimal absd.
     template <class FA, class FP> __device__ __forceinline__ void sat_pairs(int np, FA fa, FP fp) {
+        static_assert(T % 8 == 0, "a pair's 8 axis lanes must lie inside one team");
+        const unsigned wmask = T <= 32 ? mask : 0xffffffffu;
         const int total = np * 8;
 #pragma unroll 1
         for (int base = 0; base < total; base += T) {
@@ -75,19 +86,19 @@ struct DevExec {
             AxisRes r;
             r.absd = INFINITY; r.nx = 0; r.ny = 0; r.fl = 0;
             if (act) r = fa(q, axis);
-            const unsigned gbase = (unsigned)(tid & 31) & ~7u;
-            const unsigned sep_now = __ballot_sync(0xffffffffu, act && (r.fl & 1));
-            const unsigned sep_after = __ballot_sync(0xffffffffu, act && (r.fl & 2));
+            const unsigned gbase = (unsigned)lane & ~7u;
+            const unsigned sep_now = __ballot_sync(wmask, act && (r.fl & 1));
+            const unsigned sep_after = __ballot_sync(wmask, act && (r.fl & 2));
             const bool inter = ((sep_now >> gbase) & 0xFFu) == 0, will = ((sep_after >> gbase) & 0xFFu) == 0;
             double bd = r.absd;
             int bi = axis;
 #pragma unroll
             for (int off = 1; off < 8; off <<= 1) {
-                const double od = __shfl_xor_sync(0xffffffffu, bd, off);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                const double od = __shfl_xor_sync(wmask, bd, off);
+                const int oi = __shfl_xor_sync(wmask, bi, off);
                 if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
             }
-            const double nx = __shfl_sync(0xffffffffu, r.nx, (int)gbase + bi), ny = __shfl_sync(0xffffffffu, r.ny, (int)gbase + bi);
+            const double nx = __shfl_sync(wmask, r.nx, (int)gbase + bi), ny = __shfl_sync(wmask, r.ny, (int)gbase + bi);
             if (act && axis == 0) fp(q, inter, will, bd, nx, ny);
         }
         sync();
@@ -113,18 +124,18 @@ struct DevExec {
 #error "compile with -DTT_V=<slot capacity>"
 #endif
 #ifndef TT_T
-#define TT_T (TT_V <= 32 ? 32 : TT_V <= 64 ? 64 : TT_V <= 128 ? 128 : 256)
+#define TT_T (TT_V <= 16 ? 16 : TT_V <= 32 ? 32 : TT_V <= 64 ? 64 : TT_V <= 128 ? 128 : 256)
 #endif
 #ifndef TT_MINB
 #define TT_MINB (TT_V <= 32 ? 1 : TT_V <= 64 ? 10 : TT_V <= 128 ? 5 : 3)
 #endif
 // envs per CTA of k_step (1 = one env per CTA, no phase alignment)
 #ifndef TT_G
-#define TT_G (TT_V <= 32 ? 16 : 1)   /* upper bound; the launch uses as many as fit in shared memory */
+#define TT_G (TT_V <= 32 ? 512 / TT_T : 1)   /* upper bound (512 threads); the launch uses as many as fit in shared memory */
 #endif
 template <int V> struct TeamOf {
     static constexpr int T = TT_T, MINB = TT_MINB, G = TT_G;
-    static_assert(G == 1 || T == 32, "several envs per CTA need one-warp teams");
+    static_assert(G == 1 || T <= 32, "several envs per CTA need teams of at most one warp");
 };
 
 template <int V, int P>
@@ -141,7 +152,7 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V, P>& c, unsigned char* smem_ct
     c.st = reinterpret_cast<EnvState<V>*>(smem);
     c.sc = sc;
     c.L = sc->cfg.n_lanes;
-    c.vcap = vcap;
+    c.vcap = vcap < V ? vcap : V;  // a buffer with more slots than this kernel's capacity: the small size class
     c.lanes = lanes_s;
     c.SR = reinterpret_cast<d2*>(smem + lay.off_SR);
     c.NC = sc->n_curved;
@@ -162,7 +173,7 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V, P>& c, unsigned char* smem_ct
     constexpr int T = TeamOf<V>::T;                            \
     EnvCtx<V, 2> c;                                            \
     make_ctx<V, 2>(c, smem, 0, sc, lay, g.V);                  \
-    DevExec<V, T> ex{(int)threadIdx.x, 1};
+    DevExec<V, T> ex((int)threadIdx.x, 1);
 
 template <int V, int P>
 __global__ void __launch_bounds__(TeamOf<V>::T * TeamOf<V>::G, TeamOf<V>::G > 1 ? 1 : TeamOf<V>::MINB)
@@ -172,16 +183,38 @@ k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay
     const int G = (int)blockDim.x / T;
     const int team = threadIdx.x / T;
     EnvCtx<V, P> c;
-    make_ctx<V, P>(c, smem, team, sc, lay, g.V);
-    DevExec<V, T> ex{(int)threadIdx.x % T, G};
-    const int e = (int)blockIdx.x * G + team;
-    if (e < g.E) {
-        env_step(c, ex, g, io, e);
-    } else {
-        // a team without an env (last CTA) still takes part in the phase alignment of its CTA
-        const int n_align = env_step_align_count(sc);
-        for (int k = 0; k < n_align; ++k) ex.align();
+    DevExec<V, T> ex((int)threadIdx.x % T, G);
+    int e = (int)blockIdx.x * G + team;
+    if (io.cls_list) {  // binned launch: this CTA takes G envs of one bin
+        int cta = (int)blockIdx.x, b = io.cls_first, cnt = 0;
+        for (; b < io.cls_first + io.cls_n; ++b) {
+            cnt = io.cls_count[b];
+            const int nct = (cnt + G - 1) / G;
+            if (cta < nct) break;
+            cta -= nct;
+        }
+        if (b == io.cls_first + io.cls_n) return;  // uniform per CTA (before any barrier)
+        const int idx = cta * G + team;
+        e = idx < cnt ? io.cls_list[(size_t)b * g.E + idx] : g.E;
     }
+    make_ctx<V, P>(c, smem, team, sc, lay, g.V);
+    // The teams of the CTA run their sub-steps in lockstep: one alignment barrier per sub-step keeps the warps in the same
+    // code region (shared instruction fetch).  The barrier is ONE instruction outside the per-team branches, reached by teams
+    // with and without an env alike (a team without an env: last CTA of a bin).
+    const bool active = e < g.E;
+    if (active) env_step_load(c, ex, g, io, e);
+    const int32_t* actions = (active && io.actions) ? io.actions + (size_t)e * n_agents(c) : nullptr;
+    double veh_steps = 0;
+    const int F = sc->F;
+#pragma unroll 1
+    for (int f = 0; f < F; ++f) {
+        ex.align();
+        if (active) {
+            env_substep(c, ex, actions);
+            veh_steps += c.st->n;
+        }
+    }
+    if (active) env_step_finish(c, ex, g, io, e, veh_steps);
 }
 
 template <int V>
@@ -246,7 +279,7 @@ k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayo
     if (b >= n_done) return;  // uniform per CTA
     EnvCtx<V, P> c;
     make_ctx<V, P>(c, smem, team, sc, lay, g.V);
-    DevExec<V, T> ex{(int)threadIdx.x % T, G};
+    DevExec<V, T> ex((int)threadIdx.x % T, G);
     // The finished envs are dealt ROUND-ROBIN over the CTAs (one CTA per SM), team by team: a typical step finishes ~1/13 of
     // the envs, and a few teams on every SM run faster than 14 teams on a third of the SMs (a team's speed is set by
     // dependency latency and by its share of the SM's instruction fetch).  With more finished envs than teams the CTA
@@ -254,17 +287,15 @@ k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayo
     const int passes = (n_done + G * nb - 1) / (G * nb);
     for (int pass = 0; pass < passes; ++pass) {
         const int k = (pass * G + team) * nb + b;
-        if (k < n_done) {
-            const int e = io.done_list[k];
-            const int episode = g.ei[TTRL_EI_EPISODE * g.E + e] + 1;
-            env_reset(c, ex, io.seed, io.first_global_env + e, episode, true);
+        const bool active = k < n_done;
+        const int e = active ? io.done_list[k] : 0;
+        const int episode = active ? g.ei[TTRL_EI_EPISODE * g.E + e] + 1 : 0;
+        env_reset_lockstep(c, ex, active, io.seed, io.first_global_env + e, episode);
+        if (active) {
             if (io.obs) observe(c, ex, io.obs + (size_t)e * io.obs_size,
                                 io.inv_perm ? io.inv_perm + (size_t)e * n_agents(c) * (sc->cfg.obs_vehicles - 1) : nullptr,
                                 io.seed, io.first_global_env + e);
             store_env(c, ex, g, e);
-        } else {
-            const int n_align = env_reset_align_count(sc);
-            for (int a = 0; a < n_align; ++a) ex.align();
         }
     }
 }
@@ -284,20 +315,18 @@ k_regen_list(const SceneDev* __restrict__ sc, StepIO io, SmemLayout lay) {
     if (b >= n_regen) return;  // uniform per CTA
     EnvCtx<V, P> c;
     make_ctx<V, P>(c, smem, team, sc, lay, io.shadow.V);
-    DevExec<V, T> ex{(int)threadIdx.x % T, G};
+    DevExec<V, T> ex((int)threadIdx.x % T, G);
     const int passes = (n_regen + G * nb - 1) / (G * nb);
     for (int pass = 0; pass < passes; ++pass) {
         const int k = (pass * G + team) * nb + b;
-        if (k < n_regen) {
-            const int e = io.regen_list[2 * k], episode = io.regen_list[2 * k + 1];
-            env_reset(c, ex, io.seed, io.first_global_env + e, episode, true);
+        const bool active = k < n_regen;
+        const int e = active ? io.regen_list[2 * k] : 0, episode = active ? io.regen_list[2 * k + 1] : 0;
+        env_reset_lockstep(c, ex, active, io.seed, io.first_global_env + e, episode);
+        if (active) {
             store_env(c, ex, io.shadow, e);
             __threadfence();
             ex.sync();
             if (ex.first()) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(io.shadow_ready + e), "r"(episode) : "memory");
-        } else {
-            const int n_align = env_reset_align_count(sc);
-            for (int a = 0; a < n_align; ++a) ex.align();
         }
     }
 }
@@ -324,7 +353,10 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
     l.per_env = (int)align_up(off, 128);
     l.total = l.lanes_bytes + l.per_env;                       // single-team kernels
     int G = TeamOf<V>::G;                                      // k_step: G envs per CTA, as many as fit
+    if (const char* v = getenv("TTRL_G")) { const int cap = atoi(v); if (cap >= 1 && cap < G) G = cap; }  // tuning experiments
     while (G > 1 && l.lanes_bytes + G * l.per_env > 227 * 1024) --G;
+    if (TeamOf<V>::T < 32 && G > 1) G -= G % (32 / TeamOf<V>::T);  // whole warps
+    if (G < 1) G = 1;
     l.G = G;
     l.total_step = l.lanes_bytes + G * l.per_env;
     *out = l;
@@ -358,10 +390,16 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
 template <int V>
 static void launch_step(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io) {
     const int G = lay.G;
-    if (io.done_list) cudaMemsetAsync(io.done_count, 0, sizeof(int32_t), st);
-    if (lay.plain == 1) k_step<V, 1><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
-    else if (lay.plain == 2) k_step<V, 2><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
-    else k_step<V, 0><<<(E + G - 1) / G, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    // binned launch: every bin may leave one partly filled CTA; CTAs beyond the bins' envs exit at once
+    const int nb = (E + G - 1) / G + (io.cls_list ? io.cls_n : 0);
+    if (lay.plain == 1) k_step<V, 1><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    else if (lay.plain == 2) k_step<V, 2><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    else k_step<V, 0><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+}
+// the packed reset of the envs the step found finished (io.done_list)
+template <int V>
+static void launch_reset_list(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io) {
+    const int G = lay.G;
     // one CTA per SM (fewer for tiny batches); CTAs beyond the number of finished envs exit at once
     const int nb_reset = (E + G - 1) / G < lay.n_sms ? (E + G - 1) / G : lay.n_sms;
     if (io.done_list && lay.plain == 2) k_reset_list<V, 2><<<nb_reset, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
@@ -404,7 +442,7 @@ static void launch_reset(int E, const SmemLayout& lay, cudaStream_t st, const Sc
 #define TT_CAT_(a, b) a##b
 #define TT_CAT(a, b) TT_CAT_(a, b)
 extern "C" const KernelSet* TT_CAT(ttrl_kernel_set_, TT_V)(void) {
-    static const KernelSet ks = {TT_V, TeamOf<TT_V>::T, configure<TT_V>, launch_step<TT_V>, launch_substep<TT_V>, launch_observe<TT_V>, launch_spawn<TT_V>, launch_reset<TT_V>,
+    static const KernelSet ks = {TT_V, TeamOf<TT_V>::T, configure<TT_V>, launch_step<TT_V>, launch_reset_list<TT_V>, launch_substep<TT_V>, launch_observe<TT_V>, launch_spawn<TT_V>, launch_reset<TT_V>,
                                  launch_regen<TT_V>};
     return &ks;
 }

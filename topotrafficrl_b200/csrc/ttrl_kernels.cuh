@@ -17,6 +17,7 @@ struct KernelSet {
     int T;        // threads per env
     int (*configure)(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, SmemLayout* lay);  // layout + shared-memory opt-in; cudaError_t as int
     void (*step)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io);
+    void (*reset_list)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io);
     void (*substep)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const int32_t* actions);
     void (*observe)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, float* obs, int obs_size,
                     const int32_t* inv_perm, uint64_t seed, int64_t first_global_env, double* info);
