@@ -70,7 +70,7 @@ struct HostEnv {
         obs_s.assign((size_t)(cfg.obs_vehicles * cfg.n_features + 4), 0.f);
         perm_s.assign((size_t)(2 * cfg.obs_vehicles + 4), 0u);
         cell.assign((size_t)(cfg.grid_w * cfg.grid_h + 4 + TTRL_MAX_TTC_CELLS), 0);
-        c.st = &st; c.sc = sc; c.lanes = sc->lanes; c.SR = SR.data(); c.NC = sc->n_curved; c.lmask = lmask.data();
+        c.st = &st; c.sc = sc; c.lanes = sc->lanes; c.SR = SR.data(); c.NC = P == 1 ? cfg.n_lanes : sc->n_curved; c.lmask = lmask.data();
         c.pred = cfg.regulated ? pred.data() : nullptr; c.pbits = cfg.regulated ? pbits.data() : nullptr; c.obs_s = obs_s.data(); c.perm_s = perm_s.data(); c.cell = cell.data();
         c.L = cfg.n_lanes; c.vcap = vcap;
         c.gap_den = 2 * sqrt(-cfg.comfort_acc_max * cfg.comfort_acc_min);

@@ -66,7 +66,9 @@ struct SceneDev {
 // Per-env state in shared memory (struct of arrays over the V slots) + task scratch.
 template <int V>
 struct alignas(16) EnvState {
-    static constexpr int MB = V < 16 ? V : 16;  // MOBIL batch: vehicles whose lane-change timer fired, per round
+    // MOBIL batch: vehicles whose lane-change timer fired, per round.  Small scenes (a handful of vehicles per env, the
+    // shared-memory footprint of an env decides how many an SM holds) take rounds of 4: 9 x 4 evaluation slots instead of 9 x 16
+    static constexpr int MB = V <= 32 ? 4 : 16;
     static constexpr int PQ = 2 * V;            // collision candidate pair queue
     static constexpr int WQ = V / 2;            // will-intersect pair list
     d2 pos[V];   // x, y
@@ -111,7 +113,7 @@ struct EnvCtx {
     const SceneDev* sc;
     const ttrl_lane* lanes;  // lane table (shared-memory copy)
     d2* SR;                  // [V][NC] (longitudinal, lateral) local coordinates of vehicle v in CURVED lane column k (sr_of)
-    int NC;                  // curved lanes of the network (columns of SR)
+    int NC;                  // columns of SR: the curved lanes of the network (plain profile: every lane)
     uint32_t* lmask;         // [L][W] bit v of lane l: vehicle v is on lane l with margin 1 (road.py:503)
     double* pred;            // [4][V] regulation predictions of one time slice (x, y, cos h, sin h); null if not regulated
     uint32_t* pbits;         // [V (V - 1) / 2 bits] pairs in conflict (regulation); null if not regulated
@@ -287,9 +289,12 @@ template <class C> TT_HD double lane_heading_at_c(const ttrl_lane& l, double s) 
 // search: bit-identical); curved lanes: the cached result of that search (one atan2 / sin per vehicle, lane and sub-step).
 // Caching only the curved lanes is what lets an SM hold more envs: the full V x L table was the largest shared-memory
 // array of the intersection scene (24 x 20 x 16 B = 7.7 KB of 15.9 KB per env; 8 curved lanes: 3 KB; highway: none).
+// The plain profile (highway: 4 lanes, register-limited occupancy) keeps the full table: there it costs no resident env
+// and saves the recomputation (measured: 1.154 -> 1.188 ms/step without it).
 template <class C> TT_HD d2 sr_of(C& c, int v, int l) {
+    if (C::kPlain) return c.SR[v * c.NC + l];
     const ttrl_lane& ln = c.lanes[l];
-    if (C::kPlain || ln.kind == TTRL_LANE_STRAIGHT) {
+    if (ln.kind == TTRL_LANE_STRAIGHT) {
         const d2 p = c.st->pos[v];
         const double dx = p.x - ln.ax, dy = p.y - ln.ay;
         return d2{dx * ln.dx + dy * ln.dy, dx * (-ln.dy) + dy * ln.dx};
@@ -318,7 +323,8 @@ TT_HD int table_row_and_closest(C& c, int v, uint64_t& on_mask) {
     for (int l = 0; l < c.L; ++l) {
         const ttrl_lane& ln = c.lanes[l];
         double s, r;
-        if (C::kPlain || ln.kind == TTRL_LANE_STRAIGHT) { const double dx = px - ln.ax, dy = py - ln.ay; s = dx * ln.dx + dy * ln.dy; r = dx * (-ln.dy) + dy * ln.dx; }
+        if (C::kPlain) { const double dx = px - ln.ax, dy = py - ln.ay; s = dx * ln.dx + dy * ln.dy; r = dx * (-ln.dy) + dy * ln.dx; c.SR[v * c.NC + l] = d2{s, r}; }
+        else if (ln.kind == TTRL_LANE_STRAIGHT) { const double dx = px - ln.ax, dy = py - ln.ay; s = dx * ln.dx + dy * ln.dy; r = dx * (-ln.dy) + dy * ln.dx; }
         else { lane_local_curved_inl(ln, px, py, s, r); c.SR[v * c.NC + ln.cache_col] = d2{s, r}; }
         if (lane_on_lane(ln, s, r, 1.0)) m |= 1ull << l;
         double ang = fabs(wrap_to_pi(hd - lane_heading_at_c<C>(ln, s)));

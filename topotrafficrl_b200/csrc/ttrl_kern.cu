@@ -155,7 +155,7 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V, P>& c, unsigned char* smem_ct
     c.vcap = vcap < V ? vcap : V;  // a buffer with more slots than this kernel's capacity: the small size class
     c.lanes = lanes_s;
     c.SR = reinterpret_cast<d2*>(smem + lay.off_SR);
-    c.NC = sc->n_curved;
+    c.NC = P == 1 ? sc->cfg.n_lanes : sc->n_curved;
     c.lmask = reinterpret_cast<uint32_t*>(smem + lay.off_lmask);
     c.pred = lay.off_pred >= 0 ? reinterpret_cast<double*>(smem + lay.off_pred) : nullptr;
     c.pbits = lay.off_pred >= 0 ? reinterpret_cast<uint32_t*>(smem + lay.off_pred + sizeof(double) * 4 * V) : nullptr;
@@ -202,6 +202,10 @@ k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay
     // code region (shared instruction fetch).  The barrier is ONE instruction outside the per-team branches, reached by teams
     // with and without an env alike (a team without an env: last CTA of a bin).
     const bool active = e < g.E;
+    if (TeamOf<V>::G == 1) {  // one env per CTA: nothing to align
+        if (active) env_step(c, ex, g, io, e);
+        return;
+    }
     if (active) env_step_load(c, ex, g, io, e);
     const int32_t* actions = (active && io.actions) ? io.actions + (size_t)e * n_agents(c) : nullptr;
     double veh_steps = 0;
@@ -343,7 +347,8 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
     size_t off = align_up(sizeof(EnvState<V>), 16);
     int n_curved = 0;
     for (int k = 0; k < cfg.n_lanes; ++k) n_curved += lanes[k].kind != TTRL_LANE_STRAIGHT ? 1 : 0;
-    l.off_SR = (int)off; off += sizeof(d2) * (size_t)vcap * (n_curved > 0 ? n_curved : 1);  // curved-lane coordinate cache
+    // coordinate cache: the curved lanes; scenes without any (they run the plain profile or never read it): every lane
+    l.off_SR = (int)off; off += sizeof(d2) * (size_t)vcap * (n_curved > 0 ? n_curved : cfg.n_lanes);
     l.off_lmask = (int)off; off += align_up(sizeof(uint32_t) * ((V + 31) / 32) * cfg.n_lanes, 16);
     if (cfg.regulated) { l.off_pred = (int)off; off += sizeof(double) * 4 * V + align_up(sizeof(uint32_t) * ((V * (V - 1) / 2 + 31) / 32), 16); } else l.off_pred = -1;
     l.off_obs = (int)off; off += align_up(sizeof(float) * (cfg.obs_type == TTRL_OBS_KINEMATICS ? cfg.obs_vehicles * cfg.n_features : 4), 16);
