@@ -67,6 +67,10 @@ WORKLOADS = {
                                label="training: intersection 8192 envs, DQN MLP [128,128] (baseline.json), act + step + record per iteration",
                                bytes_per_env_step=24 * 128 + 4 + 420 + 8 + 420 + 4, n_actions=3),
     # SURVEY.md section 8 rows A29 / N3 (not BASELINE configs; parity cases with a throughput line)
+    # BASELINE configs[4]: one GPU's shard of 1M envs (1 048 576 / 8), full step + observation + policy
+    "c5_shard": dict(scene="intersection", E=131072, n=24, over=None, qnet="ego_attention_2h",
+                     label="configs[4] shard: 131072 of 1 048 576 intersection envs (1M / 8 GPUs) + DQN ego-attention Q-net rollout in the loop",
+                     bytes_per_env_step=24 * 128 + 4 + 420 + 8 + 420 + 4, n_actions=3),
     "multiagent": dict(scene="intersection", E=8192, n=24, agents=4,
                        over={"controlled_vehicles": 4, "initial_vehicle_count": 5,
                              "action": {"type": "MultiAgentAction", "action_config": {"type": "DiscreteMetaAction", "lateral": False, "longitudinal": True}},
@@ -232,32 +236,77 @@ def build_scene(w):
     return cfgd, net, table, cfg, scenes.intersection_spawn_routes(net, table)
 
 
+SPAWN_DRAW_DTYPE = np.dtype([("u_spawn", "f8"), ("entry", "i4"), ("exit", "i4"), ("n_pos", "f8"), ("n_speed", "f8"), ("delta", "f8")])
+
+
+class _OracleResetBackend:
+    """`reset.reset_intersection` driven by the CPU oracle (spawn attempts + warm-up sub-steps on a host SimState): the CPU
+    arm generates its own initial states with the reference's procedure, without touching the GPU."""
+
+    def __init__(self, orc, num_envs: int, vcap: int):
+        from topotrafficrl_b200.state import SimState
+        self.orc, self.num_envs = orc, num_envs
+        self.st = SimState.zeros(num_envs, vcap)
+
+    def spawn(self, draws, longitudinal, position_deviation, speed_deviation, spawn_probability, go_straight):
+        return self.orc.spawn(self.st, draws, longitudinal, position_deviation, speed_deviation, spawn_probability, go_straight)
+
+    def substep_none(self):
+        self.orc.substep(self.st, None)
+
+    def get_state(self):
+        return self.st.copy()
+
+    def set_state(self, st):
+        self.st = st.copy()
+
+
 def cpu_oracle_throughput(w, seconds: float, seed: int = 0):
     """CPU arm: the oracle port on all host cores, bounded sample of the workload.  Returns (veh-steps/s, env-steps/s, cores, sample)."""
+    import ctypes as C
+
     from oracle import oracle as O
     from topotrafficrl_b200 import scenes
-    if w["scene"] != "highway":
-        raise SystemExit("the CPU arm is implemented for the highway workloads")
+    from topotrafficrl_b200._gym import np_random as gym_np_random
+    from topotrafficrl_b200.reset import reset_intersection
+    if w["scene"] not in ("highway", "intersection") or w.get("agents"):
+        raise SystemExit("the CPU arm is implemented for the highway and the single-agent intersection workloads")
     cfgd, net, table, cfg, routes = build_scene(w)
     cores = os.cpu_count() or 1
     E = max(cores * 8, 64)
-    st = scenes.make_highway_state(E, cfgd, seed=seed)
-    orc = O.Oracle(cfg, table, threads=cores)
+    orc = O.Oracle(cfg, table, routes, threads=cores)
+    if w["scene"] == "highway":
+        st = scenes.make_highway_state(E, cfgd, seed=seed)
+    else:  # IntersectionEnv._make_vehicles for E seeded envs (numpy PCG64 streams like gymnasium's), capacity as on the device
+        backend = _OracleResetBackend(orc, E, w["n"])
+        st = reset_intersection(backend, [gym_np_random(1000 * seed + e)[0] for e in range(E)], net, table, cfgd, cfg)
     orc.set_reset_pool(st.copy())
     orc.set_autoreset(True)
     rng = np.random.default_rng(seed)
     stats = np.zeros(8)
-    orc.step(st, rng.integers(0, w["n_actions"], size=E).astype(np.int32), stats=stats)  # warm-up
+
+    def draws():
+        if w["scene"] != "intersection":
+            return None
+        d = np.zeros(E, SPAWN_DRAW_DTYPE)  # the draws of _spawn_vehicle (intersection_env.py:328-346, behavior.py:66-69)
+        d["u_spawn"] = rng.uniform(size=E)
+        d["entry"] = rng.integers(0, 4, size=E)
+        d["exit"] = (d["entry"] + rng.integers(1, 4, size=E)) % 4
+        d["n_pos"], d["n_speed"], d["delta"] = rng.normal(size=E), rng.normal(size=E), rng.uniform(3.5, 4.5, size=E)
+        draws.keep = d
+        return C.cast(d.ctypes.data, C.c_void_p)
+
+    orc.step(st, rng.integers(0, w["n_actions"], size=E).astype(np.int32), draws(), stats=stats)  # warm-up
     stats[:] = 0
     t0 = time.perf_counter()
     steps = 0
     while True:
-        orc.step(st, rng.integers(0, w["n_actions"], size=E).astype(np.int32), stats=stats)
+        orc.step(st, rng.integers(0, w["n_actions"], size=E).astype(np.int32), draws(), stats=stats)
         steps += 1
         if time.perf_counter() - t0 >= seconds:
             break
     dt = time.perf_counter() - t0
-    return stats[6] / dt, stats[7] / dt, cores, f"{E} envs x {w['n']} vehicles x {steps} env-steps ({dt:.1f} s) of the same scene generator"
+    return stats[6] / dt, stats[7] / dt, cores, f"{E} envs x {stats[6] / max(stats[7], 1) / 15:.1f} vehicles (mean) x {steps} env-steps ({dt:.1f} s) of the same scene generator"
 
 
 def run_reference(args, w):
@@ -283,13 +332,9 @@ def run_reference(args, w):
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args, w):
+def _setup_dist():
     import torch
     import torch.distributed as dist
-
-    from topotrafficrl_b200 import scenes
-    from topotrafficrl_b200.sim import Sim
-
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -297,14 +342,31 @@ def run_ours(args, w):
         raise SystemExit("bench.py needs a CUDA device: the simulator has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
+    return rank, local_rank, world, dev
 
-    cfgd, net, table, cfg, routes = build_scene(w)
-    E = args.envs or w["E"]
-    K, W = args.steps, args.warmup
-    first_env = rank * E
+
+STRONG_TOTAL_ENVS = {"highway": 32768, "intersection": 1048576}  # fixed total E split over the GPUs
+
+
+def measure(args, wname, K, W, with_cpu, self_check_steps=0):
+    """One workload: device-resident arm, end-to-end (host buffer) arm, roofline, clocks -> the JSON line's dict (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+
     from topotrafficrl_b200.vector_env import TTRLVectorEnv
+    w = WORKLOADS[wname]
+    rank, local_rank, world, dev = _setup_dist()
+    cfgd, net, table, cfg, routes = build_scene(w)
+    if args.envs:
+        E = args.envs
+    elif args.scaling == "strong":
+        E = STRONG_TOTAL_ENVS["highway" if w["scene"] == "highway" else "intersection"] // world
+    else:
+        E = w["E"]
+    first_env = rank * E
+    default_vcap = not args.vcap
     venv = TTRLVectorEnv(E, scene=w["scene"], config=w["over"], device=local_rank, seed=0, first_env=first_env,
                          vcap=(args.vcap or w["n"]), reset_mode=args.reset_mode, async_reset=not args.sync_reset)
     venv.reset()
@@ -313,7 +375,8 @@ def run_ours(args, w):
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    actions = torch.randint(0, w["n_actions"], (W + K, E * A), dtype=torch.int32, device=dev, generator=gen)
+    n_extra = max(0, int(self_check_steps))
+    actions = torch.randint(0, w["n_actions"], (W + K + n_extra, E * A), dtype=torch.int32, device=dev, generator=gen)
     obs = torch.zeros(E * sim.obs_size, dtype=torch.float32, device=dev)
     rew = torch.zeros(E, dtype=torch.float32, device=dev)
     term = torch.zeros(E, dtype=torch.uint8, device=dev)
@@ -337,6 +400,8 @@ def run_ours(args, w):
                                                                                "final_temperature": 0.05}}, seed=rank, rollout_mode=args.qnet_mode, cuda_graph=(world == 1))
         sim.observe_ptr(obs.data_ptr(), stream)
         obs_t = obs.view((E,) + venv.obs_shape)
+        final_obs = torch.zeros_like(obs_t)
+        sim.set_info_outputs_ptr(None, final_obs.data_ptr())
 
     def step(k):
         a = actions[k]
@@ -344,7 +409,7 @@ def run_ours(args, w):
             prev = obs_t.clone()
             a = trainer.act(prev)
             sim.step_ptr(a.data_ptr(), obs.data_ptr(), rew.data_ptr(), term.data_ptr(), trunc.data_ptr(), stream)
-            trainer.record(prev, a, rew, obs_t, term, trunc)
+            trainer.record(prev, a, rew, obs_t, term, trunc, {"final_observation": final_obs, "_final_observation": (term | trunc)})
             return
         if qnet is not None:  # agent.act on the observation the previous step left in HBM (no host round trip)
             a = qnet.act(obs3)
@@ -355,6 +420,11 @@ def run_ours(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
+    counted = qnet if qnet is not None else (trainer.rollout if trainer is not None else None)  # OUR kernels only (not torch's)
+
+    def our_launches():
+        return sim.launch_count + (counted._L.ttrl_qnet_launch_count(counted._h) if counted is not None else 0)
+
     # ---- device-resident arm -------------------------------------------------------------------------
     for k in range(W):
         step(k)
@@ -362,8 +432,7 @@ def run_ours(args, w):
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    counted = qnet if qnet is not None else (trainer.rollout if trainer is not None else None)  # OUR kernels only (not torch's)
-    launches0 = sim.launch_count + (counted._L.ttrl_qnet_launch_count(counted._h) if counted is not None else 0)
+    launches0 = our_launches()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     t_wall0 = time.perf_counter()
     for k in range(K):
@@ -373,19 +442,35 @@ def run_ours(args, w):
         ev[k][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = sim.launch_count + (counted._L.ttrl_qnet_launch_count(counted._h) if counted is not None else 0) - launches0
+    launches = our_launches() - launches0
     clocks = sampler.stop()
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(ms))
     s = sim.stats(reset=True)  # one reduction kernel, outside the timed region
     veh_steps, env_steps = s.vehicle_steps, s.env_steps
+    capacity_rejects = s.spawn_capacity_rejects
     red = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([veh_steps, env_steps, s.episodes, s.crashes, s.total_return], dtype=torch.float64, device=dev)
+    tot = torch.tensor([veh_steps, env_steps, s.episodes, s.crashes, s.total_return, capacity_rejects], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)  # episode statistics: the only collective of the workload
     total_ms_max = float(red.item())
-    veh_all, env_all, episodes, crashes, ret = (float(x) for x in tot.tolist())
+    veh_all, env_all, episodes, crashes, ret, rejects_all = (float(x) for x in tot.tolist())
+
+    # ---- longer self-check of the same arm (the contract's K can be a 20 ms region): not part of `value` -------------
+    self_check = None
+    if n_extra:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for k in range(n_extra):
+            step(W + K + k)
+        e1.record()
+        barrier()
+        s3 = sim.stats(reset=True)
+        sc_ms = e0.elapsed_time(e1)
+        self_check = {"steps": n_extra, "ms_per_step": sc_ms / n_extra, "value": s3.vehicle_steps / (sc_ms * 1e-3),
+                      "note": "back-to-back steps, no L2 flush, one event pair around all of them (this rank)"}
 
     # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------------
     acts_host = actions.cpu().numpy()
@@ -411,6 +496,7 @@ def run_ours(args, w):
     h2d = E * A * 4 + (E * sim.obs_size * 4 if qnet is not None else 0)
     d2h = E * (sim.obs_size * 4 + 4 + 2) + E * A * 5  # + per-agent rewards / terminal flags
 
+    line = None
     if rank == 0:
         hbm_peak, peak_kind = _peaks()
         kernel_ms = statistics.mean(ms)
@@ -420,7 +506,7 @@ def run_ours(args, w):
             "metric": "vehicle_steps_per_sec", "value": veh_all / (total_ms_max * 1e-3), "unit": "vehicle-steps/s",
             "env_steps_per_sec": env_all / (total_ms_max * 1e-3),
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["label"], "envs_per_gpu": E, "vehicles_per_env": w["n"], "sub_steps_per_step": 15,
                        "autoreset": ("pool of host-generated initial states" if args.reset_mode == "host" else "device-side fresh reset"), "l2": "flushed between timed steps (256 MB fill)",
                        "target": "1e8 vehicle-steps/s per B200 (BASELINE.json north_star)"},
@@ -429,16 +515,52 @@ def run_ours(args, w):
                     "ms_per_step": float(e2e_t.item()) / K * 1e3},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": _dram_traffic(args.workload) if E == w["E"] else None, "kernel": "k_step", "kernel_ms": kernel_ms, "peak_kind": peak_kind,
+                         "traffic": _dram_traffic(wname) if E == w["E"] else None,
+                         "traffic_source": "profiles/dram_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel, per launch",
+                         "kernel": "k_step", "kernel_ms": kernel_ms, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks,
-            "episode_stats": {"episodes": episodes, "crashes": crashes, "mean_return": ret / episodes if episodes else None},
+            "episode_stats": {"episodes": episodes, "crashes": crashes, "mean_return": ret / episodes if episodes else None,
+                              "spawn_capacity_rejects": rejects_all},
             "wall_s_timed_region": t_wall,
         }
-        if world == 1 and not args.no_cpu_baseline and w["scene"] == "highway":
+        if self_check is not None:
+            line["self_check"] = self_check
+        if with_cpu and w["scene"] in ("highway", "intersection") and not w.get("agents"):
             v, evs, cores, sample = cpu_oracle_throughput(w, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "vehicle-steps/s", "cores": cores, "kind": "port", "sample": sample,
                                     "env_steps_per_sec": evs}
+    if counted is not None:
+        counted.close()
+    venv.close()
+    del flush
+    torch.cuda.empty_cache()
+    if default_vcap and rejects_all > 0:
+        # the reference's vehicle list has no capacity: a rejected spawn makes the episodes differ from the reference's
+        raise SystemExit(f"bench.py: {int(rejects_all)} spawns were rejected for lack of vehicle slots at the default capacity of workload {wname!r}")
+    return line
+
+
+ALSO_WORKLOADS = ("dense200", "intersection", "intersection_qnet")  # BASELINE configs[2], [3] (step only) and [3] proper
+
+
+def run_ours(args, wname):
+    import torch.distributed as dist
+    rank, local_rank, world, dev = _setup_dist()
+    headline = wname == "highway50" and not args.envs and args.scaling == "weak"
+    line = measure(args, wname, args.steps, args.warmup, with_cpu=(world == 1 and not args.no_cpu_baseline),
+                   self_check_steps=(200 if headline and world == 1 else 0))
+    if headline and world == 1 and not args.no_also:
+        # every other BASELINE config on the same box, same contract (>= 50 timed steps each), next to the headline fields
+        also = {}
+        for name in ALSO_WORKLOADS:
+            sub = measure(args, name, max(50, min(args.steps, 100)), max(args.warmup, 5), with_cpu=(not args.no_cpu_baseline and name != "intersection_qnet"))
+            also[name] = {k: sub[k] for k in ("value", "unit", "env_steps_per_sec", "steps", "warmup", "ms_per_step", "config", "e2e", "gpu_launches",
+                                               "roofline", "clocks", "episode_stats") if k in sub}
+            if "cpu_baseline" in sub:
+                also[name]["cpu_baseline"] = sub["cpu_baseline"]
+        line["also"] = also
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -456,6 +578,9 @@ def main():
     ap.add_argument("--vcap", type=int, default=0, help="vehicle slots per env (intersection workloads; default 24)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="headline run only: skip the dense200 / intersection / intersection_qnet block")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's envs on EVERY GPU; strong: a fixed total (32768 highway / 1048576 intersection envs) split over the GPUs")
     ap.add_argument("--sync-reset", action="store_true", help="device resets right after the step that finished the env (no side-stream regeneration)")
     ap.add_argument("--reset-mode", default="device", choices=["device", "host"],
                     help="device = fresh episodes generated on the GPU at every autoreset (the reference's _make_vehicles incl. its 45 warm-up sub-steps); host = replay a pool of host-generated initial states")
@@ -464,11 +589,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    w = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, w)
+        run_reference(args, WORKLOADS[args.workload])
     else:
-        run_ours(args, w)
+        run_ours(args, args.workload)
 
 
 if __name__ == "__main__":

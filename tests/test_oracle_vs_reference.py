@@ -86,3 +86,79 @@ def test_highway_substeps_live(H, n, density):
             H.ref_substep(env, a)
             orc.substep(before, np.array([a], np.int32))
             T.compare_states(before, H.extract_state(env, table, n), T.TOL_SUBSTEP, f"seed {seed} sub-step {k}")
+
+
+class _DeviceHighwayDraws:
+    """numpy-Generator stand-in that feeds the reference's highway reset (Vehicle.create_random kinematics.py:50-104 +
+    IDMVehicle.randomize_behavior behavior.py:66-69) the DEVICE's reset draws, vehicle by vehicle: stream index 2 s -> (lane,
+    speed), 2 s + 1 -> (spacing jitter, DELTA) of slot s (ttrl_core.cuh: reset_highway)."""
+
+    def __init__(self, emu, seed, env, episode, lanes, speed_limit):
+        self.u = lambda idx: emu.reset_uniforms(seed, env, episode, idx)
+        self.lanes, self.speed_limit = lanes, speed_limit
+        self.slot, self.choices = 0, 0
+
+    def choice(self, a, *args, **kw):
+        self.choices += 1
+        if self.choices % 3:  # `_from`, `_to`: one road, a single candidate each
+            return a[0]
+        lid = int(self.u(2 * self.slot)[0] * self.lanes)
+        return min(lid, self.lanes - 1)
+
+    def uniform(self, low=0.0, high=1.0, size=None):
+        if (low, high) == (0.9, 1.1):     # spacing jitter: the last draw of create_random
+            v = 0.9 + 0.2 * self.u(2 * self.slot + 1)[0]
+            self._placed = True
+            return v
+        if (low, high) == (3.5, 4.5):     # randomize_behavior
+            v = 3.5 + self.u(2 * self.slot + 1)[1]
+            self.slot += 1
+            return v
+        assert abs(low - 0.7 * self.speed_limit) < 1e-12 and abs(high - 0.8 * self.speed_limit) < 1e-12, (low, high)
+        return (0.7 + 0.1 * self.u(2 * self.slot)[1]) * self.speed_limit
+
+
+def test_device_highway_reset_is_create_random_with_the_same_draws(H):
+    """Device-side highway reset (the device logic built for the host) == the reference's own procedure --
+    RoadNetwork.straight_road_network + Vehicle.create_random for the ego and every IDMVehicle + randomize_behavior --
+    when the reference is fed the device's draws: positions, lanes, speeds, DELTA, lane-change timers, target speeds."""
+    from tests.emu.emu import Emulator
+    from topotrafficrl_b200.state import SimState
+    n, density = 50, 2.0
+    _, table, cfg, cfgd = T.highway_scene(n, density)
+    emu = Emulator(cfg, table)
+    emu.set_reset_params(scenes.highway_reset_params(cfgd))
+    seed, first, episode, E = 17, 40, 2, 4
+    got = SimState.zeros(E, n)
+    emu.reset(got, seed, first, episode)
+    env = H.SyntheticHighwayEnv(config={"vehicles_count": n, "vehicles_density": density})
+    for e in range(E):
+        env.reset(seed=0)
+        draws = _DeviceHighwayDraws(emu, seed, first + e, episode, int(cfgd["lanes_count"]), float(cfgd["speed_limit"]))
+        env.np_random = draws
+        # the ego's create_random draws no DELTA: advance the slot by hand after it (SyntheticHighwayEnv._reset otherwise)
+
+        def patched():
+            H.restore_idm_class_constants()
+            from ttrl_env.road.road import Road, RoadNetwork
+            from ttrl_env.vehicle.behavior import IDMVehicle
+            from ttrl_env.vehicle.kinematics import Vehicle
+            net = RoadNetwork.straight_road_network(env.config["lanes_count"], length=env.config["road_length"], speed_limit=env.config["speed_limit"])
+            env.road = Road(network=net, np_random=draws, record_history=False)
+            ego = Vehicle.create_random(env.road, speed=25, spacing=env.config["ego_spacing"])
+            ego = env.action_type.vehicle_class(env.road, ego.position, ego.heading, ego.speed)
+            env.controlled_vehicles = [ego]
+            env.road.vehicles.append(ego)
+            draws.slot = 1
+            for _ in range(env.config["vehicles_count"] - 1):
+                v = IDMVehicle.create_random(env.road, spacing=1 / env.config["vehicles_density"])
+                v.randomize_behavior()
+                env.road.vehicles.append(v)
+
+        patched()
+        env.define_spaces()
+        want = H.extract_state(env, table, n)
+        want.env_i[abi.EI_EPISODE] = episode
+        want.env_i[abi.EI_STEPS] = 0
+        want.env_d[abi.ED_TIME] = 0
+        T.compare_states(got.slice_envs(e, e + 1), want, 1e-9, f"highway reset env {e}")

@@ -47,10 +47,11 @@ done_first = False
 for r in rows:
     if r and r[0] == "Kernel Name":
         if done_first:
-            break  # first profiled launch only
+            break  # first MATCHING profiled launch only
         name = r[1]
         func = None
-        if re.sub(r"I?Li\d+.*", "", kern) in name:
+        want_v = re.search(r"ILi(\d+)", kern)  # k_stepILi16 -> launches of k_step<(int)16, ...> only
+        if re.sub(r"I?Li\d+.*", "", kern) in name and (not want_v or f"<(int){want_v.group(1)}," in name):
             cands = [f for f in funcs if kern in f]
             func = cands[0] if cands else None
         k = 0

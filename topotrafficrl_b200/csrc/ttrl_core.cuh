@@ -139,8 +139,15 @@ TT_HD double not_zero(double x) {  // utils.py:48-54
 TT_HD double mod_2pi(double a) {
     const double b = 2 * kPi;
     if (a >= 0 && a < b) return a;
-    double q = floor(a / b);
-    double m = fma(-q, b, a);
+    // one turn below / above: the quotient floor(a / b) is exactly -1 / +1 there (the 1e-6 margins keep clear of the values
+    // where the division could round across an integer), so the general path's fma(-q, b, a) is a + b / a - b rounded once
+    double m;
+    if (a < 0 && a > -(b - 1e-6)) m = a + b;
+    else if (a >= b && a < 2 * b - 1e-6) m = a - b;
+    else {
+        const double q = floor(a / b);
+        m = fma(-q, b, a);
+    }
     if (m < 0) m += b;
     else if (m >= b) m -= b;
     return m;

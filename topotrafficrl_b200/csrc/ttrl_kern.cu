@@ -212,6 +212,9 @@ k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay
     const int F = sc->F;
 #pragma unroll 1
     for (int f = 0; f < F; ++f) {
+#if defined(TT_ALIGN_EVERY)
+        if (f % TT_ALIGN_EVERY == 0)   // experiment: let the teams drift for TT_ALIGN_EVERY - 1 sub-steps
+#endif
         ex.align();
         if (active) {
             env_substep(c, ex, actions);
