@@ -236,7 +236,7 @@ def build_scene(w):
     return cfgd, net, table, cfg, scenes.intersection_spawn_routes(net, table)
 
 
-SPAWN_DRAW_DTYPE = np.dtype([("u_spawn", "f8"), ("entry", "i4"), ("exit", "i4"), ("n_pos", "f8"), ("n_speed", "f8"), ("delta", "f8")])
+SPAWN_DRAW_DTYPE = np.dtype([("u_spawn", "f8"), ("entry", "i4"), ("exit", "i4"), ("n_pos", "f8"), ("n_speed", "f8"), ("delta", "f8"), ("lin_u", "f8", (5,))])
 
 
 class _OracleResetBackend:

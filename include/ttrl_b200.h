@@ -79,6 +79,7 @@ enum { TTRL_ORDER_SORTED = 0, TTRL_ORDER_SHUFFLED = 1 };
 enum { TTRL_ACT_ALL = 0 /* 0 LANE_LEFT 1 IDLE 2 LANE_RIGHT 3 FASTER 4 SLOWER */,
        TTRL_ACT_LONGI = 1 /* 0 SLOWER 1 IDLE 2 FASTER */,
        TTRL_ACT_LAT = 2 /* 0 LANE_LEFT 1 IDLE 2 LANE_RIGHT */ };
+enum { TTRL_VEHICLE_IDM = 0, TTRL_VEHICLE_LINEAR = 1 };
 enum { TTRL_REWARD_INTERSECTION = 0 /* intersection_env.py:61-104 (mean over the controlled vehicles) */,
        TTRL_REWARD_HIGHWAY = 1 /* u_turn_env.py:39-71: UTurnEnv, and the same template on the synthetic highway */,
        TTRL_REWARD_ROUNDABOUT = 2 /* roundabout_env.py:43-64: speed-index and lane-change terms */ };
@@ -109,7 +110,11 @@ typedef struct ttrl_config {
     double grid_xrange[2], grid_yrange[2];
     double grid_min[2], grid_max[2], grid_step[2];
     /* reward / termination */
-    int32_t reward_type, normalize_reward, offroad_terminal, pad4;
+    int32_t reward_type, normalize_reward, offroad_terminal;
+    /* class of the surrounding traffic, config["other_vehicles_type"] (intersection_env.py:257, roundabout_env.py:337):
+     * TTRL_VEHICLE_IDM = IDMVehicle (behavior.py:16-348), TTRL_VEHICLE_LINEAR = LinearVehicle (behavior.py:350-558: acceleration
+     * and steering linear in per-vehicle parameters, TIME_WANTED 2.5 -- the host passes that as time_wanted) */
+    int32_t vehicle_model;
     double collision_reward, high_speed_reward, arrived_reward, lane_reward;
     double reward_speed_lo, reward_speed_hi;
     /* IntersectionEnv spawn / clear (intersection_env.py:320-362) */
@@ -122,6 +127,9 @@ typedef struct ttrl_config {
     /* RoundaboutEnv (roundabout_env.py:43-64): weight of `action in [0, 2]`, and the denominator of the speed-index
      * term, MDPVehicle.DEFAULT_TARGET_SPEEDS.size - 1 (controller.py:259) */
     double lane_change_reward, speed_index_den;
+    /* LinearVehicle.randomize_behavior (behavior.py:402-410): parameter k = lin_lo[k] + u * (lin_hi[k] - lin_lo[k]) with
+     * ACCELERATION_RANGE / STEERING_RANGE (behavior.py:359-371) in TTRL_LIN_* order; lin_default = the class attributes */
+    double lin_lo[5], lin_hi[5], lin_default[5];
 } ttrl_config;
 
 /* ------------------------------------------------------------------------------------------------
@@ -152,8 +160,14 @@ typedef struct ttrl_spawn_draw {
     double u_spawn;      /* np_random.uniform()                      (:328) */
     int32_t entry, exit; /* np_random.choice(range(4), 2, False)      (:331) */
     double n_pos, n_speed; /* np_random.normal() x2                   (:338, :340) */
-    double delta;        /* np_random.uniform(3.5, 4.5)               (behavior.py:67) */
+    double delta;        /* IDMVehicle.randomize_behavior: np_random.uniform(3.5, 4.5)            (behavior.py:67) */
+    double lin_u[5];     /* LinearVehicle.randomize_behavior: np_random.uniform(size=3), then (size=2) (behavior.py:402-410) */
 } ttrl_spawn_draw;
+
+/* LinearVehicle parameters, one block per vehicle slot next to the state arrays (sims with vehicle_model == TTRL_VEHICLE_LINEAR
+ * only): field f of slot s of env e at buf[(f*E + e)*V + s].  ACCELERATION_PARAMETERS[0..2], STEERING_PARAMETERS[0..1]
+ * (behavior.py:353-357; class defaults 0.3, 0.3, 2.0 and KP_HEADING, KP_HEADING * KP_LATERAL). */
+enum { TTRL_LIN_ACC0 = 0, TTRL_LIN_ACC1, TTRL_LIN_ACC2, TTRL_LIN_STEER0, TTRL_LIN_STEER1, TTRL_NLIN = 5 };
 
 /* Episode statistics accumulated on device (maps to Evaluation.after_all_episodes, trainer/evaluation.py:325-333) */
 typedef struct ttrl_episode_stats {
@@ -260,6 +274,11 @@ int ttrl_sim_host_info_buffers(ttrl_sim* sim, double** info, float** final_obs);
 int ttrl_sim_set_state(ttrl_sim* sim, const double* veh_d, const int32_t* veh_i,
                        const int32_t* env_i, const double* env_d);
 int ttrl_sim_get_state(ttrl_sim* sim, double* veh_d, int32_t* veh_i, int32_t* env_i, double* env_d);
+/* The LinearVehicle parameter block of the state / of the reset pool (host double[TTRL_NLIN * E * V] resp. [TTRL_NLIN * pool_size * V]);
+ * fail unless the sim was created with vehicle_model == TTRL_VEHICLE_LINEAR.  Call the pool form after ttrl_sim_set_reset_pool. */
+int ttrl_sim_set_linear_params(ttrl_sim* sim, const double* lin);
+int ttrl_sim_get_linear_params(ttrl_sim* sim, double* lin);
+int ttrl_sim_set_reset_pool_linear_params(ttrl_sim* sim, const double* lin);
 
 /* Store the current state as reset pool entry `slot` (autoreset source; reset itself stays on the host:
  * AbstractEnv.reset, abstract.py:188-214).  Env e restarts from pool entry (e + k*E) mod pool_size at its k-th reset. */

@@ -67,6 +67,11 @@ class Oracle:
         self.obs_size = L.orc_obs_size(self._sc)
         self.K = max(1, int(cfg.controlled_vehicles))
         self.agent_reward = self.agent_terminated = None  # per-agent outputs of the last step()
+        self._pool_lin = None
+
+    def _lin(self, st) -> None:
+        """LinearVehicle parameter blocks (``SimState.lin``) of the state the next call operates on and of the pool."""
+        self._L.orc_scene_set_linear_params(self._sc, _p(getattr(st, "lin", None)), _p(self._pool_lin))
 
     def __del__(self):
         try:
@@ -76,6 +81,7 @@ class Oracle:
 
     def set_reset_pool(self, pool: SimState) -> None:
         pool = pool.contiguous()
+        self._pool_keep, self._pool_lin = pool, pool.lin
         self._L.orc_scene_set_reset_pool(self._sc, C.c_int(pool.num_envs), C.c_int(pool.vcap), _p(pool.veh_d), _p(pool.veh_i),
                                          _p(pool.env_i), _p(pool.env_d))
 
@@ -84,11 +90,13 @@ class Oracle:
 
     def substep(self, st: SimState, actions: Optional[np.ndarray] = None) -> None:
         a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32)
+        self._lin(st)
         self._L.orc_substep(self._sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d),
                             C.c_int(st.num_envs), C.c_int(st.vcap), _p(a), C.c_int(self.threads))
 
     def observe(self, st: SimState) -> np.ndarray:
         obs = np.zeros((st.num_envs, self.obs_size), np.float32)
+        self._lin(st)
         self._L.orc_observe(self._sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d),
                             C.c_int(st.num_envs), C.c_int(st.vcap), _p(obs), C.c_int(self.threads))
         return obs
@@ -103,6 +111,7 @@ class Oracle:
         accepted = np.zeros(E, np.int32)
         self.agent_reward = np.zeros((E, self.K), np.float32)
         self.agent_terminated = np.zeros((E, self.K), np.uint8)
+        self._lin(st)
         self._L.orc_step_agents(self._sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(E), C.c_int(st.vcap),
                                 _p(a), _p(obs), _p(reward), _p(term), _p(trunc),
                                 draws if draws is not None else None, _p(accepted), _p(stats), C.c_int(self.threads),
@@ -112,6 +121,7 @@ class Oracle:
     def spawn(self, st: SimState, draws, longitudinal: float, position_deviation: float = 1.0,
               speed_deviation: float = 1.0, spawn_probability: float = 0.6, go_straight: bool = False) -> np.ndarray:
         accepted = np.zeros(st.num_envs, np.int32)
+        self._lin(st)
         self._L.orc_spawn(self._sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(st.num_envs),
                           C.c_int(st.vcap), draws, C.c_double(longitudinal), C.c_double(position_deviation),
                           C.c_double(speed_deviation), C.c_double(spawn_probability), C.c_int(int(go_straight)), _p(accepted))

@@ -21,7 +21,7 @@ from ttrl_env.envs.intersection_env import IntersectionEnv, MultiAgentIntersecti
 from ttrl_env.envs.roundabout_env import RoundaboutEnv  # noqa: E402
 from ttrl_env.envs.u_turn_env import UTurnEnv  # noqa: E402
 from ttrl_env.road.road import Road, RoadNetwork  # noqa: E402
-from ttrl_env.vehicle.behavior import IDMVehicle  # noqa: E402
+from ttrl_env.vehicle.behavior import IDMVehicle, LinearVehicle  # noqa: E402
 from ttrl_env.vehicle.controller import MDPVehicle  # noqa: E402
 from ttrl_env.vehicle.kinematics import Vehicle  # noqa: E402
 
@@ -34,9 +34,12 @@ IDM_CLASS_DEFAULTS = dict(DISTANCE_WANTED=IDMVehicle.DISTANCE_WANTED, COMFORT_AC
 
 
 def restore_idm_class_constants() -> None:
-    """IntersectionEnv mutates IDMVehicle class attributes process-wide (intersection_env.py:258-261)."""
+    """IntersectionEnv mutates class attributes of ``other_vehicles_type`` process-wide (intersection_env.py:258-261): on
+    IDMVehicle itself, or -- with LinearVehicle traffic -- as new attributes of the subclass, removed again here."""
     for k, v in IDM_CLASS_DEFAULTS.items():
         setattr(IDMVehicle, k, v)
+        if k in LinearVehicle.__dict__:
+            delattr(LinearVehicle, k)
 
 
 class SyntheticHighwayEnv(AbstractEnv):
@@ -103,8 +106,9 @@ class SyntheticHighwayEnv(AbstractEnv):
 # --------------------------------------------------------------------------------------------------
 def extract_state(env, table: NetworkTable, vcap: int) -> SimState:
     """Snapshot ``env.road.vehicles`` (list order) into a 1-env SimState."""
-    st = SimState.zeros(1, vcap)
     vehicles = env.road.vehicles
+    linear = any(isinstance(v, LinearVehicle) for v in vehicles) or "LinearVehicle" in str(env.config.get("other_vehicles_type", ""))
+    st = SimState.zeros(1, vcap, linear=linear)
     assert len(vehicles) <= vcap, (len(vehicles), vcap)
     for s, v in enumerate(vehicles):
         route = getattr(v, "route", None)
@@ -120,7 +124,8 @@ def extract_state(env, table: NetworkTable, vcap: int) -> SimState:
             speed_index=int(getattr(v, "speed_index", 0)), route=route,
             steering=float(v.action["steering"]), accel=float(v.action["acceleration"]),
             impact=None if v.impact is None else (float(v.impact[0]), float(v.impact[1])),
-            yielding=bool(getattr(v, "is_yielding", False)), yield_timer=int(getattr(v, "yield_timer", 0)))
+            yielding=bool(getattr(v, "is_yielding", False)), yield_timer=int(getattr(v, "yield_timer", 0)),
+            linear=(list(v.ACCELERATION_PARAMETERS) + list(v.STEERING_PARAMETERS)) if isinstance(v, LinearVehicle) else None)
     st.env_i[abi.EI_NVEH, 0] = len(vehicles)
     st.env_i[abi.EI_STEPS, 0] = env.steps
     st.env_i[abi.EI_ROAD_STEPS, 0] = getattr(env.road, "steps", 0)
@@ -188,5 +193,11 @@ def draws_from_log(log) -> Optional[abi.SpawnDraw]:
     assert log[1][0] == "choice" and log[2][0] == "normal" and log[3][0] == "normal", log
     d.entry, d.exit = int(log[1][1][0]), int(log[1][1][1])
     d.n_pos, d.n_speed = float(log[2][1]), float(log[3][1])
-    d.delta = float(log[4][1]) if len(log) > 4 else 4.0
+    d.delta = 4.0
+    if len(log) > 5:    # LinearVehicle.randomize_behavior: uniform(size=3), uniform(size=2)
+        u = list(np.ravel(log[4][1])) + list(np.ravel(log[5][1]))
+        for k in range(5):
+            d.lin_u[k] = float(u[k])
+    elif len(log) > 4:  # IDMVehicle.randomize_behavior: uniform(3.5, 4.5)
+        d.delta = float(log[4][1])
     return d

@@ -25,6 +25,7 @@ typedef struct {
     double x, y, heading, speed, steering, accel, target_speed, timer, delta, impact_x, impact_y;
     int lane, target_lane, flags, speed_index, route_len, yield_timer;
     int route_road[TTRL_ROUTE_CAP], route_lane[TTRL_ROUTE_CAP];
+    double lin[TTRL_NLIN]; /* LinearVehicle.ACCELERATION_PARAMETERS[3] + STEERING_PARAMETERS[2] (behavior.py:353-357) */
 } veh_t;
 
 typedef struct {
@@ -48,6 +49,8 @@ typedef struct orc_scene {
     int spawn_lane[4];
     int spawn_route_len[4][4];
     int spawn_route_road[4][4][TTRL_ROUTE_CAP];
+    /* LinearVehicle parameter blocks [TTRL_NLIN][E][V] of the state arrays of the next calls / of the pool (NULL: class defaults) */
+    double* lin; const double* pool_lin;
 } orc_scene;
 
 /* ----------------------------------------------------------------------------------------------
@@ -293,6 +296,12 @@ static double steering_control(const orc_scene* sc, const veh_t* v, int target_l
     double s, r; lane_local(tl, v->x, v->y, &s, &r);
     double lane_next = s + v->speed * TAU_PURSUIT;
     double lane_future_heading = lane_heading_at(tl, lane_next);
+    if (sc->cfg.vehicle_model == TTRL_VEHICLE_LINEAR && !(v->flags & TTRL_FL_MDP)) {
+        /* LinearVehicle.steering_control = np.dot(STEERING_PARAMETERS, steering_features) behavior.py:466-500 */
+        double f0 = wrap_to_pi(lane_future_heading - v->heading) * LENGTH / not_zero(v->speed);
+        double f1 = -r * LENGTH / (not_zero(v->speed) * not_zero(v->speed)); /* not_zero(speed) ** 2 */
+        return v->lin[TTRL_LIN_STEER0] * f0 + v->lin[TTRL_LIN_STEER1] * f1;
+    }
     double lateral_speed_command = -KP_LATERAL * r;
     double heading_command = asin(clipd(lateral_speed_command / not_zero(v->speed), -1, 1));
     double heading_ref = lane_future_heading + clipd(heading_command, -PI / 4, PI / 4);
@@ -383,6 +392,25 @@ static double idm_acceleration(const orc_scene* sc, double self_delta, const veh
     }
     return acc;
 }
+/* LinearVehicle.acceleration behavior.py:416-464: np.dot(self.ACCELERATION_PARAMETERS, acceleration_features(ego, front)) */
+static double linear_acceleration(const orc_scene* sc, const veh_t* self, const veh_t* ego, const veh_t* front) {
+    double vt = 0, dv = 0, dp = 0;
+    if (ego) {
+        vt = ego->target_speed - ego->speed;
+        double d_safe = sc->cfg.distance_wanted + fmax(ego->speed, 0) * sc->cfg.time_wanted;
+        if (front) {
+            double d = lane_distance_to(sc, ego, front);
+            dv = fmin(front->speed - ego->speed, 0);
+            dp = fmin(d - d_safe, 0);
+        }
+    }
+    return self->lin[TTRL_LIN_ACC0] * vt + self->lin[TTRL_LIN_ACC1] * dv + self->lin[TTRL_LIN_ACC2] * dp;
+}
+/* self.acceleration(ego_vehicle, front_vehicle): the class of `self` decides (other_vehicles_type) */
+static double acceleration(const orc_scene* sc, const veh_t* self, const veh_t* ego, const veh_t* front) {
+    if (sc->cfg.vehicle_model == TTRL_VEHICLE_LINEAR) return linear_acceleration(sc, self, ego, front);
+    return idm_acceleration(sc, self->delta, ego, front);
+}
 double orc_idm_acceleration(const orc_scene* sc, double self_delta, const double* ego6, const double* front6) {
     /* ego6/front6 = x, y, heading, speed, target_speed, lane */
     veh_t e, f; memset(&e, 0, sizeof e); memset(&f, 0, sizeof f);
@@ -398,14 +426,14 @@ static int mobil(const orc_scene* sc, const env_t* e, int vi, int cand) {
     neighbour_vehicles(sc, e, vi, cand, &np_, &nf_);
     const veh_t* new_preceding = np_ >= 0 ? &e->v[np_] : 0;
     const veh_t* new_following = nf_ >= 0 ? &e->v[nf_] : 0;
-    double new_following_a = idm_acceleration(sc, self->delta, new_following, new_preceding);
-    double new_following_pred_a = idm_acceleration(sc, self->delta, new_following, self);
+    double new_following_a = acceleration(sc, self, new_following, new_preceding);
+    double new_following_pred_a = acceleration(sc, self, new_following, self);
     if (new_following_pred_a < -sc->cfg.lane_change_max_braking_imposed) return 0;
     int op_, of_;
     neighbour_vehicles(sc, e, vi, self->lane, &op_, &of_);
     const veh_t* old_preceding = op_ >= 0 ? &e->v[op_] : 0;
     const veh_t* old_following = of_ >= 0 ? &e->v[of_] : 0;
-    double self_pred_a = idm_acceleration(sc, self->delta, self, new_preceding);
+    double self_pred_a = acceleration(sc, self, self, new_preceding);
     if (self->route_len > 0 && self->route_lane[0] >= 0) {
         int want = self->route_lane[0] - sc->lanes[self->target_lane].lane_id;
         int dir = sc->lanes[cand].lane_id - sc->lanes[self->target_lane].lane_id;
@@ -413,9 +441,9 @@ static int mobil(const orc_scene* sc, const env_t* e, int vi, int cand) {
         if (sd != sw) return 0;
         else if (self_pred_a < -sc->cfg.lane_change_max_braking_imposed) return 0;
     } else {
-        double self_a = idm_acceleration(sc, self->delta, self, old_preceding);
-        double old_following_a = idm_acceleration(sc, self->delta, old_following, self);
-        double old_following_pred_a = idm_acceleration(sc, self->delta, old_following, old_preceding);
+        double self_a = acceleration(sc, self, self, old_preceding);
+        double old_following_a = acceleration(sc, self, old_following, self);
+        double old_following_pred_a = acceleration(sc, self, old_following, old_preceding);
         double jerk = self_pred_a - self_a +
                       sc->cfg.politeness * (new_following_pred_a - new_following_a + old_following_pred_a - old_following_a);
         if (jerk < sc->cfg.lane_change_min_acc_gain) return 0;
@@ -460,10 +488,10 @@ static void idm_act(const orc_scene* sc, env_t* e, int vi) {
     double steering = clipd(steering_control(sc, self, self->target_lane), -MAX_STEER, MAX_STEER);
     int f, r;
     neighbour_vehicles(sc, e, vi, self->lane, &f, &r);
-    double acc = idm_acceleration(sc, self->delta, self, f >= 0 ? &e->v[f] : 0);
+    double acc = acceleration(sc, self, self, f >= 0 ? &e->v[f] : 0);
     if (self->lane != self->target_lane) {
         neighbour_vehicles(sc, e, vi, self->target_lane, &f, &r);
-        double tacc = idm_acceleration(sc, self->delta, self, f >= 0 ? &e->v[f] : 0);
+        double tacc = acceleration(sc, self, self, f >= 0 ? &e->v[f] : 0);
         acc = fmin(acc, tacc);
     }
     acc = clipd(acc, -sc->cfg.acc_max, sc->cfg.acc_max);
@@ -1004,6 +1032,8 @@ static int spawn_vehicle(const orc_scene* sc, env_t* e, const ttrl_spawn_draw* d
     v.route_road[0] = sc->lanes[v.lane].road; v.route_lane[0] = sc->lanes[v.lane].lane_id;
     for (int k = 0; k < sc->spawn_route_len[entry][exit_]; ++k) { v.route_road[1 + k] = sc->spawn_route_road[entry][exit_][k]; v.route_lane[1 + k] = -1; }
     v.delta = d->delta;                                  /* randomize_behavior behavior.py:66-69 */
+    if (sc->cfg.vehicle_model == TTRL_VEHICLE_LINEAR)    /* LinearVehicle.randomize_behavior behavior.py:402-410 */
+        for (int k = 0; k < TTRL_NLIN; ++k) v.lin[k] = sc->cfg.lin_lo[k] + d->lin_u[k] * (sc->cfg.lin_hi[k] - sc->cfg.lin_lo[k]);
     e->v[e->n++] = v;
     return 1;
 }
@@ -1011,7 +1041,7 @@ static int spawn_vehicle(const orc_scene* sc, env_t* e, const ttrl_spawn_draw* d
 /* ----------------------------------------------------------------------------------------------
  * SoA <-> env_t
  * -------------------------------------------------------------------------------------------- */
-static void load_env(env_t* e, const double* vd, const int32_t* vi, const int32_t* ei, const double* ed, int E, int V, int ie) {
+static void load_env(env_t* e, const double* vd, const int32_t* vi, const int32_t* ei, const double* ed, int E, int V, int ie, const double* lin) {
     e->n = ei[TTRL_EI_NVEH * E + ie]; e->steps = ei[TTRL_EI_STEPS * E + ie]; e->road_steps = ei[TTRL_EI_ROAD_STEPS * E + ie];
     e->ego = ei[TTRL_EI_EGO * E + ie]; e->episode = ei[TTRL_EI_EPISODE * E + ie]; e->done = ei[TTRL_EI_DONE * E + ie];
     e->time = ed[TTRL_ED_TIME * E + ie]; e->ret = ed[TTRL_ED_RETURN * E + ie];
@@ -1024,6 +1054,7 @@ static void load_env(env_t* e, const double* vd, const int32_t* vi, const int32_
         v->timer = D(TTRL_D_TIMER); v->delta = D(TTRL_D_DELTA); v->impact_x = D(TTRL_D_IMPACT_X); v->impact_y = D(TTRL_D_IMPACT_Y);
         v->lane = I(TTRL_I_LANE); v->target_lane = I(TTRL_I_TARGET_LANE); v->flags = I(TTRL_I_FLAGS);
         v->speed_index = I(TTRL_I_SPEED_INDEX); v->route_len = I(TTRL_I_ROUTE_LEN); v->yield_timer = I(TTRL_I_YIELD_TIMER);
+        for (int k = 0; k < TTRL_NLIN; ++k) v->lin[k] = lin ? lin[((size_t)k * E + ie) * V + s] : 0;
         const uint32_t rr[TTRL_ROUTE_WORDS] = {(uint32_t)I(TTRL_I_ROUTE_ROAD), (uint32_t)I(TTRL_I_ROUTE_ROAD1), (uint32_t)I(TTRL_I_ROUTE_ROAD2)};
         const uint32_t rl[TTRL_ROUTE_WORDS] = {(uint32_t)I(TTRL_I_ROUTE_LANE), (uint32_t)I(TTRL_I_ROUTE_LANE1), (uint32_t)I(TTRL_I_ROUTE_LANE2)};
         for (int k = 0; k < TTRL_ROUTE_CAP; ++k) {
@@ -1036,7 +1067,7 @@ static void load_env(env_t* e, const double* vd, const int32_t* vi, const int32_
     for (int k = 0; k < TTRL_MAX_CONTROLLED; ++k) e->egos[k] = e->ego;
     find_agents(e);
 }
-static void store_env(const env_t* e, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int V, int ie) {
+static void store_env(const env_t* e, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int V, int ie, double* lin) {
     ei[TTRL_EI_NVEH * E + ie] = e->n; ei[TTRL_EI_STEPS * E + ie] = e->steps; ei[TTRL_EI_ROAD_STEPS * E + ie] = e->road_steps;
     ei[TTRL_EI_EGO * E + ie] = e->ego; ei[TTRL_EI_EPISODE * E + ie] = e->episode; ei[TTRL_EI_DONE * E + ie] = e->done;
     ed[TTRL_ED_TIME * E + ie] = e->time; ed[TTRL_ED_RETURN * E + ie] = e->ret;
@@ -1059,6 +1090,7 @@ static void store_env(const env_t* e, double* vd, int32_t* vi, int32_t* ei, doub
         I(TTRL_I_ROUTE_ROAD) = (int32_t)rr[0]; I(TTRL_I_ROUTE_LANE) = (int32_t)rl[0];
         I(TTRL_I_ROUTE_ROAD1) = (int32_t)rr[1]; I(TTRL_I_ROUTE_LANE1) = (int32_t)rl[1];
         I(TTRL_I_ROUTE_ROAD2) = (int32_t)rr[2]; I(TTRL_I_ROUTE_LANE2) = (int32_t)rl[2];
+        if (lin) for (int k = 0; k < TTRL_NLIN; ++k) lin[((size_t)k * E + ie) * V + s] = v->lin[k];
 #undef D
 #undef I
     }
@@ -1101,15 +1133,17 @@ void orc_scene_set_reset_pool(orc_scene* sc, int pool_size, int V, const double*
     sc->pool_ed = (double*)malloc(sizeof(double) * TTRL_NED * pool_size); memcpy(sc->pool_ed, ed, sizeof(double) * TTRL_NED * pool_size);
 }
 void orc_scene_set_autoreset(orc_scene* sc, int on) { sc->autoreset = on; }
+/* parameter blocks [TTRL_NLIN][E][V] that go with the state arrays of the following calls / with the reset pool */
+void orc_scene_set_linear_params(orc_scene* sc, double* lin, const double* pool_lin) { sc->lin = lin; sc->pool_lin = pool_lin; }
 int orc_obs_size(const orc_scene* sc) { return obs_size(sc); }
 
 /* F x substep is what _simulate does; this runs ONE substep for E envs (debug / per-substep parity). */
 void orc_substep(const orc_scene* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int V, const int32_t* actions, int threads) {
 #pragma omp parallel for num_threads(threads) schedule(dynamic, 4)
     for (int ie = 0; ie < E; ++ie) {
-        env_t e; load_env(&e, vd, vi, ei, ed, E, V, ie);
+        env_t e; load_env(&e, vd, vi, ei, ed, E, V, ie, sc->lin);
         env_substep(sc, &e, actions ? actions + (size_t)ie * n_agents(sc) : NULL);
-        store_env(&e, vd, vi, ei, ed, E, V, ie);
+        store_env(&e, vd, vi, ei, ed, E, V, ie, sc->lin);
     }
 }
 
@@ -1117,7 +1151,7 @@ void orc_observe(const orc_scene* sc, const double* vd, const int32_t* vi, const
     int osz = obs_size(sc);
 #pragma omp parallel for num_threads(threads) schedule(dynamic, 4)
     for (int ie = 0; ie < E; ++ie) {
-        env_t e; load_env(&e, vd, vi, ei, ed, E, V, ie);
+        env_t e; load_env(&e, vd, vi, ei, ed, E, V, ie, sc->lin);
         observe(sc, &e, obs + (size_t)ie * osz);
     }
 }
@@ -1141,7 +1175,7 @@ void orc_step_agents(const orc_scene* sc, double* vd, int32_t* vi, int32_t* ei, 
     double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma omp parallel for num_threads(threads) schedule(dynamic, 4) reduction(+ : st[:8])
     for (int ie = 0; ie < E; ++ie) {
-        env_t e; load_env(&e, vd, vi, ei, ed, E, V, ie);
+        env_t e; load_env(&e, vd, vi, ei, ed, E, V, ie, sc->lin);
         e.time += 1 / sc->cfg.policy_frequency;
         const int K = n_agents(sc);
         const int32_t* act = actions ? actions + (size_t)ie * K : NULL;
@@ -1174,12 +1208,12 @@ void orc_step_agents(const orc_scene* sc, double* vd, int32_t* vi, int32_t* ei, 
             if (sc->autoreset && sc->pool_size > 0) {
                 int episode = e.episode + 1;
                 int slot = (int)(((long long)ie + (long long)episode * E) % sc->pool_size);
-                load_env(&e, sc->pool_vd, sc->pool_vi, sc->pool_ei, sc->pool_ed, sc->pool_E, sc->pool_V, slot);
+                load_env(&e, sc->pool_vd, sc->pool_vi, sc->pool_ei, sc->pool_ed, sc->pool_E, sc->pool_V, slot, sc->pool_lin);
                 e.episode = episode; e.done = 0;
                 observe(sc, &e, obs + (size_t)ie * osz);
             }
         }
-        store_env(&e, vd, vi, ei, ed, E, V, ie);
+        store_env(&e, vd, vi, ei, ed, E, V, ie, sc->lin);
     }
     if (stats) for (int k = 0; k < 8; ++k) stats[k] += st[k];
 }
@@ -1190,9 +1224,9 @@ void orc_spawn(const orc_scene* sc, double* vd, int32_t* vi, int32_t* ei, double
                double longitudinal, double position_deviation, double speed_deviation, double spawn_probability, int go_straight,
                int32_t* accepted) {
     for (int ie = 0; ie < E; ++ie) {
-        env_t e; load_env(&e, vd, vi, ei, ed, E, V, ie);
+        env_t e; load_env(&e, vd, vi, ei, ed, E, V, ie, sc->lin);
         int acc = spawn_vehicle(sc, &e, &draws[ie], longitudinal, position_deviation, speed_deviation, spawn_probability, go_straight, V);
         if (accepted) accepted[ie] = acc;
-        store_env(&e, vd, vi, ei, ed, E, V, ie);
+        store_env(&e, vd, vi, ei, ed, E, V, ie, sc->lin);
     }
 }

@@ -30,6 +30,7 @@ TOL_STEP = 1e-6
 # (tests/golden/intersection_ep_<name>.npz, written by make_golden.py `episodes`): name -> (config overrides, seeds)
 _KIN_OBS = {"type": "Kinematics", "vehicles_count": 15, "features": ["presence", "x", "y", "vx", "vy", "cos_h", "sin_h"],
             "features_range": {"x": [-100, 100], "y": [-100, 100], "vx": [-20, 20], "vy": [-20, 20]}, "absolute": True}
+LINEAR = {"other_vehicles_type": "ttrl_env.vehicle.behavior.LinearVehicle"}  # RoundaboutEnv/env.json
 EPISODE_CONFIGS = {
     # env.json as shipped: "order": "shuffled" (BASELINE configs[0])
     "envjson": ({"observation": dict(_KIN_OBS, order="shuffled"), "destination": "o1"}, list(range(100, 112))),
@@ -40,6 +41,10 @@ EPISODE_CONFIGS = {
     # episode), un-normalised shuffled observation, 9 initial vehicles, spawn probability 0.3
     "normdest": ({"initial_vehicle_count": 9, "spawn_probability": 0.3, "observation": dict(_KIN_OBS, normalize=False, order="shuffled"),
                   "normalize_reward": True, "destination": None}, list(range(130, 136))),
+    # env_linear.json as shipped: LinearVehicle traffic (behavior.py:350-558)
+    "linear": ({"other_vehicles_type": "ttrl_env.vehicle.behavior.LinearVehicle", "initial_vehicle_count": 9, "spawn_probability": 0.3,
+                "observation": dict(_KIN_OBS, normalize=False, order="shuffled"), "normalize_reward": True, "destination": None},
+               list(range(160, 166))),
     "straight": ({"destination": "o2"}, [140, 141, 142, 143]),   # env_straight.json
     "right": ({"destination": "o3"}, [150, 151, 152, 153]),      # env_right.json
 }
@@ -56,8 +61,12 @@ def batch_state(g, prefix: str, sel=None) -> SimState:
         vd, vi, ei, ed = vd[sel], vi[sel], ei[sel], ed[sel]
     if vi.shape[1] < abi.NI:  # fixtures written before the route grew to 12 entries: words 1, 2 are zero (routes <= 4 entries)
         vi = np.concatenate([vi, np.zeros((vi.shape[0], abi.NI - vi.shape[1], vi.shape[2]), vi.dtype)], axis=1)
+    lin = None
+    if prefix + "_lin" in g.files:  # LinearVehicle parameters
+        lin = g[prefix + "_lin"] if sel is None else g[prefix + "_lin"][sel]
+        lin = np.ascontiguousarray(lin.transpose(1, 0, 2))
     return SimState(np.ascontiguousarray(vd.transpose(1, 0, 2)), np.ascontiguousarray(vi.transpose(1, 0, 2)),
-                    np.ascontiguousarray(ei.T), np.ascontiguousarray(ed.T))
+                    np.ascontiguousarray(ei.T), np.ascontiguousarray(ed.T), lin)
 
 
 def intersection_scene(overrides=None):
@@ -84,6 +93,8 @@ def draws_array(draw_rows):
     for k, row in enumerate(draw_rows):
         arr[k].u_spawn, arr[k].entry, arr[k].exit = float(row[0]), int(row[1]), int(row[2])
         arr[k].n_pos, arr[k].n_speed, arr[k].delta = float(row[3]), float(row[4]), float(row[5])
+        for q in range(5):  # LinearVehicle.randomize_behavior's uniforms (fixtures of IDM traffic carry six columns)
+            arr[k].lin_u[q] = float(row[6 + q]) if len(row) > 6 else 0.0
     return arr
 
 
@@ -100,6 +111,10 @@ def compare_states(got: SimState, want: SimState, tol: float, what: str = "", ch
     for f in (abi.EI_STEPS, abi.EI_ROAD_STEPS, abi.EI_EGO):
         assert (got.env_i[f] == want.env_i[f]).all(), f"{what}: env int field {f} differs"
     worst = 0.0
+    assert (got.lin is None) == (want.lin is None), f"{what}: LinearVehicle parameter block present on one side only"
+    if want.lin is not None:
+        d = np.abs(got.lin - want.lin)[:, live]
+        assert d.size == 0 or d.max() <= 1e-12, f"{what}: LinearVehicle parameters differ by {d.max()}"
     for f in range(abi.ND):
         if not check_action and f in (abi.D_STEERING, abi.D_ACCEL):
             continue

@@ -19,6 +19,7 @@ struct HostExec {
     bool first() const { return true; }  // single-thread sections run once
     void sync() {}
     void align() {}
+    void align2() {}
     template <class F> void par(F f) { for (int t = 0; t < T; ++t) f(t); }
     template <class F> void parn(int n, F f) { for (int t = 0; t < n; ++t) f(t); }
     template <class F> bool any(int n, F f) { bool r = false; for (int t = 0; t < n; ++t) r = f(t) || r; return r; }
@@ -58,6 +59,7 @@ struct HostEnv {
     std::vector<double> pred;
     std::vector<float> obs_s;
     std::vector<uint32_t> perm_s;
+    std::vector<double> lin;
     std::vector<int32_t> cell;
     EnvCtx<V, P> c;
     HostEnv(const SceneDev* sc, int vcap) {
@@ -68,10 +70,11 @@ struct HostEnv {
         pred.assign((size_t)4 * V, 0.0);
         pbits.assign((size_t)(V * (V - 1) / 2 + 31) / 32 + 1, 0u);
         obs_s.assign((size_t)(cfg.obs_vehicles * cfg.n_features + 4), 0.f);
+        lin.assign((size_t)TTRL_NLIN * V, 0.0);
         perm_s.assign((size_t)(2 * cfg.obs_vehicles + 4), 0u);
         cell.assign((size_t)(cfg.grid_w * cfg.grid_h + 4 + TTRL_MAX_TTC_CELLS), 0);
         c.st = &st; c.sc = sc; c.lanes = sc->lanes; c.SR = SR.data(); c.NC = P == 1 ? cfg.n_lanes : sc->n_curved; c.lmask = lmask.data();
-        c.pred = cfg.regulated ? pred.data() : nullptr; c.pbits = cfg.regulated ? pbits.data() : nullptr; c.obs_s = obs_s.data(); c.perm_s = perm_s.data(); c.cell = cell.data();
+        c.pred = cfg.regulated ? pred.data() : nullptr; c.pbits = cfg.regulated ? pbits.data() : nullptr; c.obs_s = obs_s.data(); c.perm_s = perm_s.data(); c.lin = cfg.vehicle_model == TTRL_VEHICLE_LINEAR ? lin.data() : nullptr; c.cell = cell.data();
         c.L = cfg.n_lanes; c.vcap = vcap;
         c.gap_den = 2 * sqrt(-cfg.comfort_acc_max * cfg.comfort_acc_min);
         c.tan_max_steer = tan(kPi / 3);
@@ -110,6 +113,10 @@ SceneDev* emu_scene_create(const ttrl_config* cfg, const ttrl_lane* lanes, const
     return s;
 }
 void emu_scene_destroy(SceneDev* s) { free(s); }
+// LinearVehicle parameter blocks of the state / pool buffers the following calls operate on ([TTRL_NLIN][E][V]; null: class defaults)
+static thread_local double* g_lin = nullptr;
+static thread_local double* g_pool_lin = nullptr;
+void emu_set_linear_params(double* lin, double* pool_lin) { g_lin = lin; g_pool_lin = pool_lin; }
 void emu_scene_set_spawn_routes(SceneDev* s, const int32_t* spawn_lane, const int32_t* route_len, const int32_t* route_road) {
     memcpy(s->spawn_lane, spawn_lane, sizeof(int32_t) * 4);
     memcpy(s->spawn_route_len, route_len, sizeof(int32_t) * 16);
@@ -117,7 +124,7 @@ void emu_scene_set_spawn_routes(SceneDev* s, const int32_t* spawn_lane, const in
 }
 
 void emu_substep(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, const int32_t* actions) {
-    GlobalState g{vd, vi, ei, ed, E, Vs};
+    GlobalState g{vd, vi, ei, ed, E, Vs, g_lin};
     DISPATCH(Vs, {
         HostEnv<V, P> env(sc, Vs);
         HostExec ex{V};
@@ -131,7 +138,7 @@ void emu_substep(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, doubl
 
 void emu_observe(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, float* obs, int obs_size,
                  const int32_t* inv_perm) {
-    GlobalState g{vd, vi, ei, ed, E, Vs};
+    GlobalState g{vd, vi, ei, ed, E, Vs, g_lin};
     DISPATCH(Vs, {
         HostEnv<V, P> env(sc, Vs);
         HostExec ex{V};
@@ -147,13 +154,13 @@ void emu_step(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* 
               int32_t* accepted, const int32_t* inv_perm, double* stats, int pool_size, double* pvd, int32_t* pvi, int32_t* pei,
               double* ped, int autoreset, uint64_t seed, int64_t first_global_env, float* agent_reward, uint8_t* agent_terminated,
               double* info, float* final_obs) {
-    GlobalState g{vd, vi, ei, ed, E, Vs};
+    GlobalState g{vd, vi, ei, ed, E, Vs, g_lin};
     StepIO io{};
     io.agent_reward = agent_reward; io.agent_terminated = agent_terminated;
     io.info = info; io.final_obs = final_obs;
     io.actions = actions; io.obs = obs; io.reward = reward; io.terminated = terminated; io.truncated = truncated;
     io.draws = draws; io.spawn_accepted = accepted; io.inv_perm = inv_perm; io.stats = stats;
-    io.pool = GlobalState{pvd, pvi, pei, ped, pool_size, Vs};
+    io.pool = GlobalState{pvd, pvi, pei, ped, pool_size, Vs, g_pool_lin};
     io.autoreset = autoreset; io.seed = seed; io.first_global_env = first_global_env; io.obs_size = obs_size;
     DISPATCH(Vs, {
         HostEnv<V, P> env(sc, Vs);
@@ -165,7 +172,7 @@ void emu_step(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* 
 void emu_spawn(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, const ttrl_spawn_draw* draws,
                double longitudinal, double position_deviation, double speed_deviation, double spawn_probability, int go_straight,
                int32_t* accepted) {
-    GlobalState g{vd, vi, ei, ed, E, Vs};
+    GlobalState g{vd, vi, ei, ed, E, Vs, g_lin};
     SpawnParams sp{longitudinal, position_deviation, speed_deviation, spawn_probability, go_straight};
     DISPATCH(Vs, {
         HostEnv<V, P> env(sc, Vs);
@@ -181,7 +188,7 @@ void emu_spawn(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double*
 
 void emu_scene_set_reset_params(SceneDev* s, const ttrl_reset_params* rp) { s->rp = *rp; s->have_rp = 1; }
 void emu_reset(const SceneDev* sc, double* vd, int32_t* vi, int32_t* ei, double* ed, int E, int Vs, uint64_t seed, int64_t first_global_env, int episode) {
-    GlobalState g{vd, vi, ei, ed, E, Vs};
+    GlobalState g{vd, vi, ei, ed, E, Vs, g_lin};
     DISPATCH(Vs, {
         HostEnv<V, P> env(sc, Vs);
         HostExec ex{V};

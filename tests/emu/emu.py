@@ -25,6 +25,11 @@ def lib():
     return _lib
 
 
+def _lin(st, pool=None):
+    """Tell the emulator which LinearVehicle parameter blocks the next call operates on (None: class defaults)."""
+    lib().emu_set_linear_params(_p(getattr(st, "lin", None)), _p(getattr(pool, "lin", None)) if pool is not None else None)
+
+
 def _p(a):
     if a is None:
         return None
@@ -49,10 +54,12 @@ class Emulator:
 
     def substep(self, st: SimState, actions=None):
         a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32)
+        _lin(st)
         self.L.emu_substep(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(st.num_envs), C.c_int(st.vcap), _p(a))
 
     def observe(self, st: SimState, inv_perm=None):
         obs = np.zeros((st.num_envs, self.obs_size), np.float32)
+        _lin(st)
         self.L.emu_observe(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(st.num_envs), C.c_int(st.vcap),
                            _p(obs), C.c_int(self.obs_size), _p(inv_perm))
         return obs
@@ -70,6 +77,7 @@ class Emulator:
         self.info = np.zeros((abi.NINFO, E), np.float64)          # ttrl_sim_set_info_outputs
         self.final_obs = np.zeros((E, self.obs_size), np.float32)
         pool = self.pool
+        _lin(st, pool)
         self.L.emu_step(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(E), C.c_int(st.vcap), _p(a),
                         _p(obs), C.c_int(self.obs_size), _p(reward), _p(term), _p(trunc), draws, _p(acc), _p(inv_perm), _p(stats),
                         C.c_int(pool.num_envs if pool is not None else 0),
@@ -83,6 +91,7 @@ class Emulator:
         self.L.emu_scene_set_reset_params(self.sc, C.byref(rp))
 
     def reset(self, st: SimState, seed: int, first_env: int = 0, episode: int = 0):
+        _lin(st)
         self.L.emu_reset(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(st.num_envs), C.c_int(st.vcap),
                          C.c_uint64(seed), C.c_int64(first_env), C.c_int(episode))
 
@@ -98,6 +107,7 @@ class Emulator:
 
     def spawn(self, st, draws, longitudinal, position_deviation=1.0, speed_deviation=1.0, spawn_probability=0.6, go_straight=False):
         acc = np.zeros(st.num_envs, np.int32)
+        _lin(st)
         self.L.emu_spawn(self.sc, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d), C.c_int(st.num_envs), C.c_int(st.vcap), draws,
                          C.c_double(longitudinal), C.c_double(position_deviation), C.c_double(speed_deviation),
                          C.c_double(spawn_probability), C.c_int(int(go_straight)), _p(acc))

@@ -41,6 +41,8 @@ class Rec:
     def add_state(self, prefix, st):
         self.add(**{prefix + "_vd": st.veh_d[:, 0], prefix + "_vi": st.veh_i[:, 0],
                     prefix + "_ei": st.env_i[:, 0], prefix + "_ed": st.env_d[:, 0]})
+        if st.lin is not None:  # LinearVehicle parameters
+            self.add(**{prefix + "_lin": st.lin[:, 0]})
 
     def save(self, name):
         path = os.path.join(OUT, name)
@@ -49,7 +51,7 @@ class Rec:
 
 
 def draw_array(d: abi.SpawnDraw):
-    return np.array([d.u_spawn, d.entry, d.exit, d.n_pos, d.n_speed, d.delta], dtype=np.float64)
+    return np.array([d.u_spawn, d.entry, d.exit, d.n_pos, d.n_speed, d.delta] + [d.lin_u[k] for k in range(5)], dtype=np.float64)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -414,10 +416,16 @@ if __name__ == "__main__":
         intersection_steps(range(100, 112), None, "intersection_steps_kin.npz")
         intersection_steps(range(200, 204), GRID_DENSE, "intersection_steps_grid_dense.npz")
         intersection_steps(range(300, 304), GRID_ROAD, "intersection_steps_grid_road.npz")
-    if "episodes" in which:
+    if "episodes" in which or "linear" in which:
         from tests.common import EPISODE_CONFIGS
         for name, (over, seeds) in EPISODE_CONFIGS.items():
-            intersection_episodes(name, over, seeds)
+            if "episodes" in which or name == "linear":
+                intersection_episodes(name, over, seeds)
+    if "linear" in which:  # RoundaboutEnv/env.json and env_route_0.json as shipped: LinearVehicle traffic
+        from tests.common import LINEAR
+        scripted_scene(H.RoundaboutEnv, scenes.make_roundabout_network(), LINEAR, range(800, 806), "roundabout_linear", 5)
+        scripted_scene(H.RoundaboutEnv, scenes.make_roundabout_network(), dict(LINEAR, incoming_vehicle_destination=0), range(810, 813),
+                       "roundabout_linear_route0", 5, substeps=False)
     if "int_reset" in which:
         intersection_reset(range(8))
     if "hw" in which:

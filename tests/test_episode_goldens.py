@@ -25,8 +25,11 @@ def episode_arrays(name):
     first = np.zeros(n, bool)
     first[g["ep_first"]] = True
     ep_of = np.cumsum(first) - 1
-    before = SimState.zeros(n, after.vcap)
-    for dst, a, b in ((before.veh_d, after.veh_d, reset.veh_d), (before.veh_i, after.veh_i, reset.veh_i)):
+    before = SimState.zeros(n, after.vcap, linear=after.lin is not None)
+    per_vehicle = [(before.veh_d, after.veh_d, reset.veh_d), (before.veh_i, after.veh_i, reset.veh_i)]
+    if after.lin is not None:
+        per_vehicle.append((before.lin, after.lin, reset.lin))
+    for dst, a, b in per_vehicle:
         dst[:, ~first] = a[:, src_after[~first]]
         dst[:, first] = b[:, ep_of[first]]
     for dst, a, b in ((before.env_i, after.env_i, reset.env_i), (before.env_d, after.env_d, reset.env_d)):

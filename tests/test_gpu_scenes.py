@@ -310,3 +310,69 @@ def test_shard_invariance_with_device_resets(scene):
     assert int(sw.env_i[abi.EI_EPISODE].max()) >= 2
     for env in [whole] + halves:
         env.close()
+
+
+@pytest.mark.parametrize("name,over", [("roundabout_linear", T.LINEAR), ("roundabout_linear_route0", dict(T.LINEAR, incoming_vehicle_destination=0))])
+def test_linear_vehicle_traffic_vs_reference_golden(name, over):
+    """RoundaboutEnv/env.json and env_route_0.json as shipped (LinearVehicle traffic, behavior.py:350-558) on the GPU: resynced
+    sub-steps and env-steps against the unmodified reference; the front end's seeded resets (five randomize_behavior uniforms per
+    vehicle from the env's numpy stream) and episodes; the vector env (device reset, LinearVehicle parameters from Philox) against
+    the oracle."""
+    import os
+    torch = _torch()
+    from oracle import oracle as O
+    from topotrafficrl_b200 import TTRLVectorEnv
+    from topotrafficrl_b200._gym import make
+    import topotrafficrl_b200.envs  # noqa: F401
+    _, table, cfg, _ = T.roundabout_scene(over)
+    g = T.golden(f"{name}_steps.npz")
+    if os.path.exists(os.path.join(T.GOLDEN, f"{name}_substeps.npz")):
+        gs = T.golden(f"{name}_substeps.npz")
+        st = T.batch_state(gs, "before")
+        sim = _sim(cfg, table, st.num_envs, st.vcap)
+        sim.set_state(st)
+        a = torch.as_tensor(gs["action"].astype(np.int32), device="cuda")
+        sim.substep_ptr(a.data_ptr(), 0)
+        T.compare_states(sim.get_state(), T.batch_state(gs, "after"), T.TOL_SUBSTEP, f"{name} sub-step")
+        sim.close()
+    st = T.batch_state(g, "before")
+    sim = _sim(cfg, table, st.num_envs, st.vcap)
+    sim.set_state(st)
+    obs, reward, term, trunc = _dev_step(sim, g["action"])
+    T.compare_states(sim.get_state(), T.batch_state(g, "after"), T.TOL_STEP, f"{name} step")
+    np.testing.assert_allclose(obs.reshape(g["obs"].shape), g["obs"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(reward, g["reward"], rtol=0, atol=1e-6)
+    assert (term.astype(bool) == g["terminated"]).all() and (trunc.astype(bool) == g["truncated"]).all()
+    sim.close()
+    # single-env front end: reset(seed) == the reference's, then golden steps from golden states
+    env = make("roundabout-v0", config=over)
+    for r, seed in enumerate(g["reset_seed"]):
+        o, _ = env.reset(seed=int(seed))
+        np.testing.assert_allclose(o, g["reset_obs"][r], rtol=0, atol=2e-6)
+        T.compare_states(env.sim.get_state(), T.batch_state(g, "reset", slice(r, r + 1)), 1e-12, f"{name} reset {seed}")
+    for k in range(min(8, len(g["action"]))):
+        env.sim.set_state(T.batch_state(g, "before", slice(k, k + 1)))
+        o, r, t, u, _ = env.step(int(g["action"][k]))
+        np.testing.assert_allclose(o, g["obs"][k], rtol=0, atol=2e-6)
+        assert abs(r - g["reward"][k]) <= 1e-6 and t == bool(g["terminated"][k])
+    env.close()
+    # vector env, device-side reset: free running against the oracle
+    E = 512
+    venv = TTRLVectorEnv(E, "roundabout", config=over, seed=4)
+    venv.reset()
+    orc = O.Oracle(venv.cfg, venv.table, threads=8)
+    rng = np.random.default_rng(1)
+    first = venv.get_state()
+    assert first.lin is not None and len(np.unique(first.lin[0, :, 1].round(9))) > E // 2  # per-vehicle parameters, randomised per env
+    for step in range(4):
+        act = rng.integers(0, 5, size=E).astype(np.int32)
+        before = venv.get_state()
+        vobs, vrew, vterm, vtrunc, _ = venv.step(torch.as_tensor(act, device="cuda"))
+        oo, orr, ot, ou, _ = orc.step(before, act, None)
+        calm = ((before.veh_i[abi.I_FLAGS] & (abi.FL_CRASHED | abi.FL_HAS_IMPACT)) == 0).all(axis=1)
+        done = ot.astype(bool) | ou.astype(bool)
+        sel = np.nonzero(calm & ~done)[0]
+        T.compare_states(venv.get_state().select_envs(sel), before.select_envs(sel), 1e-7, f"{name} vector step {step}")
+        np.testing.assert_allclose(vrew.cpu().numpy()[calm], orr[calm], rtol=0, atol=1e-6)
+        assert (vterm.cpu().numpy()[calm] == ot.astype(bool)[calm]).all()
+    venv.close()

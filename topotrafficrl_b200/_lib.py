@@ -49,6 +49,9 @@ def lib():
     L.ttrl_sim_set_spawn_routes.argtypes = [vp, vp, vp, vp]
     L.ttrl_sim_set_state.argtypes = [vp, vp, vp, vp, vp]
     L.ttrl_sim_get_state.argtypes = [vp, vp, vp, vp, vp]
+    L.ttrl_sim_set_linear_params.argtypes = [vp, vp]
+    L.ttrl_sim_get_linear_params.argtypes = [vp, vp]
+    L.ttrl_sim_set_reset_pool_linear_params.argtypes = [vp, vp]
     L.ttrl_sim_set_reset_pool.argtypes = [vp, i32, vp, vp, vp, vp]
     L.ttrl_sim_set_autoreset.argtypes = [vp, i32]
     L.ttrl_sim_set_reset_params.argtypes = [vp, C.POINTER(abi.ResetParams)]

@@ -42,6 +42,14 @@ ED_TIME, ED_RETURN = range(2)
 NED = 2
 
 QNET_MLP, QNET_EGO_ATTENTION, QNET_DUELING = 0, 1, 2
+VEHICLE_IDM, VEHICLE_LINEAR = 0, 1
+# LinearVehicle parameter block [NLIN][E][V] (behavior.py:353-367): ACCELERATION_PARAMETERS, STEERING_PARAMETERS
+NLIN = 5
+# class attributes of LinearVehicle: ACCELERATION_PARAMETERS + STEERING_PARAMETERS = [KP_HEADING, KP_HEADING * KP_LATERAL]
+# (controller.py:24-32), ACCELERATION_RANGE = [0.5 p, 1.5 p], STEERING_RANGE = p -+ [0.07, 1.5]
+LINEAR_DEFAULTS = (0.3, 0.3, 2.0, 1 / 0.2, (1 / 0.2) * (1 / 0.6))
+LINEAR_RANGE_LO = (0.5 * 0.3, 0.5 * 0.3, 0.5 * 2.0, 1 / 0.2 - 0.07, (1 / 0.2) * (1 / 0.6) - 1.5)
+LINEAR_RANGE_HI = (1.5 * 0.3, 1.5 * 0.3, 1.5 * 2.0, 1 / 0.2 + 0.07, (1 / 0.2) * (1 / 0.6) + 1.5)
 
 
 class Lane(C.Structure):
@@ -79,18 +87,19 @@ class Config(C.Structure):
         ("align_to_vehicle_axes", C.c_int32), ("as_image", C.c_int32), ("ttc_steps", C.c_int32), ("pad3", C.c_int32),
         ("grid_xrange", C.c_double * 2), ("grid_yrange", C.c_double * 2),
         ("grid_min", C.c_double * 2), ("grid_max", C.c_double * 2), ("grid_step", C.c_double * 2),
-        ("reward_type", C.c_int32), ("normalize_reward", C.c_int32), ("offroad_terminal", C.c_int32), ("pad4", C.c_int32),
+        ("reward_type", C.c_int32), ("normalize_reward", C.c_int32), ("offroad_terminal", C.c_int32), ("vehicle_model", C.c_int32),
         ("collision_reward", C.c_double), ("high_speed_reward", C.c_double), ("arrived_reward", C.c_double),
         ("lane_reward", C.c_double), ("reward_speed_lo", C.c_double), ("reward_speed_hi", C.c_double),
         ("spawn_enabled", C.c_int32), ("controlled_vehicles", C.c_int32),
         ("spawn_probability", C.c_double),
         ("lane_change_reward", C.c_double), ("speed_index_den", C.c_double),
+        ("lin_lo", C.c_double * 5), ("lin_hi", C.c_double * 5), ("lin_default", C.c_double * 5),
     ]
 
 
 class SpawnDraw(C.Structure):
     _fields_ = [("u_spawn", C.c_double), ("entry", C.c_int32), ("exit", C.c_int32),
-                ("n_pos", C.c_double), ("n_speed", C.c_double), ("delta", C.c_double)]
+                ("n_pos", C.c_double), ("n_speed", C.c_double), ("delta", C.c_double), ("lin_u", C.c_double * 5)]
 
 
 MAX_SPAWN_ATTEMPTS = 32

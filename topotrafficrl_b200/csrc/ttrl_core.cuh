@@ -119,6 +119,7 @@ struct EnvCtx {
     uint32_t* pbits;         // [V (V - 1) / 2 bits] pairs in conflict (regulation); null if not regulated
     float* obs_s;            // staging for one Kinematics observation
     uint32_t* perm_s;        // [2 (obs_vehicles - 1)] device-drawn row shuffle: random keys, then their ranks
+    double* lin;             // [TTRL_NLIN][V] LinearVehicle parameters (vehicle_model == TTRL_VEHICLE_LINEAR), else null
     int32_t* cell;           // OccupancyGrid per-cell winner (W*H ints)
     int L;
     int vcap;                // storage capacity (slots per env in HBM), <= V
@@ -470,6 +471,17 @@ TT_STEER double steering_control(C& c, int i, int target_lane, double& tan_steer
     const double speed = c.st->v[i];
     double lane_next = sr.x + speed * TAU_PURSUIT;
     double lane_future_heading = lane_heading_at_c<C>(tl, lane_next);
+    if (!C::kPlain && c.lin && !(c.st->flags[i] & TTRL_FL_MDP)) {
+        // LinearVehicle.steering_control / steering_features (behavior.py:466-500): linear in STEERING_PARAMETERS; clipped to
+        // +-MAX_STEERING_ANGLE by IDMVehicle.act (behavior.py:114-116)
+        const double f0 = wrap_to_pi(lane_future_heading - c.st->h[i]) * kVehLength / not_zero(speed);
+        const double nz = not_zero(speed);
+        const double f1 = -sr.y * kVehLength / (nz * nz);
+        double steering_angle = c.lin[TTRL_LIN_STEER0 * C::V + i] * f0 + c.lin[TTRL_LIN_STEER1 * C::V + i] * f1;
+        steering_angle = clipd(steering_angle, -MAX_STEER, MAX_STEER);
+        tan_steer = tan(steering_angle);
+        return steering_angle;
+    }
     double lateral_speed_command = -KP_LATERAL * sr.y;
     double heading_command = asin(clipd(lateral_speed_command / not_zero(speed), -1.0, 1.0));
     double heading_ref = lane_future_heading + clipd(heading_command, -kPi / 4, kPi / 4);
@@ -577,13 +589,28 @@ TT_HD double desired_gap(C& c, int ego, int front) {
     const double dv = dvx * e.x + dvy * e.y;
     return cfg.distance_wanted + ve * cfg.time_wanted + ve * dv / c.gap_den;
 }
-// IDMVehicle.acceleration behavior.py:150-190 (self_delta = SELF's DELTA, also when ego is another vehicle)
+// IDMVehicle.acceleration behavior.py:150-190 as vehicle `self` evaluates it for `ego` (its own DELTA / parameters, also when
+// ego is another vehicle: MOBIL); LinearVehicle.acceleration behavior.py:416-464 when the traffic is linear
 template <class C>
-TT_IDM double idm_acceleration(C& c, double self_delta, int ego, int front) {
+TT_IDM double idm_acceleration(C& c, int self, int ego, int front) {
     if (ego < 0) return 0.0;
     const ttrl_config& cfg = c.sc->cfg;
     auto* st = c.st;
     const int le = st->lane[ego];
+    if (!C::kPlain && c.lin) {
+        // acceleration_features: vt = target_speed - speed, dv = min(front.speed - speed, 0), dp = min(d - d_safe, 0) with
+        // d_safe = DISTANCE_WANTED + max(speed, 0) TIME_WANTED; np.dot(ACCELERATION_PARAMETERS, [vt, dv, dp])
+        const double vt = st->tspeed[ego] - st->v[ego];
+        double dv = 0, dp = 0;
+        if (front >= 0) {
+            const double d_safe = cfg.distance_wanted + fmax(st->v[ego], 0.0) * cfg.time_wanted;
+            const double d = S_(c, front, le) - S_(c, ego, le);
+            dv = fmin(st->v[front] - st->v[ego], 0.0);
+            dp = fmin(d - d_safe, 0.0);
+        }
+        return (c.lin[TTRL_LIN_ACC0 * C::V + self] * vt + c.lin[TTRL_LIN_ACC1 * C::V + self] * dv) + c.lin[TTRL_LIN_ACC2 * C::V + self] * dp;
+    }
+    const double self_delta = st->delta[self];
     const double ts = clipd(st->tspeed[ego], 0.0, c.lanes[le].speed_limit);
     // np.power(x, delta) for x >= 0, delta in [3.5, 4.5] as exp(delta log x): a few ulp from pow, a third of its cost
     double acc = cfg.comfort_acc_max * (1 - exp(self_delta * log(fmax(st->v[ego], 0.0) / fabs(not_zero(ts)))));
@@ -678,7 +705,7 @@ TT_HD void mobil_batch(C& c, Exec& ex, int base, int nb) {
                 else { ego = i; front = new_prec; }
             }
         }
-        st->mq_a[k] = idm_acceleration(c, st->delta[i], ego, front);
+        st->mq_a[k] = idm_acceleration(c, i, ego, front);
     });
     // M3: decisions, candidates in side_lanes order; a later accepted candidate overwrites (behavior.py:250-263)
     ex.parn(nb, [&](int b) {
@@ -756,7 +783,7 @@ TT_HD void act_phase_c2(C& c, int k) {
         int r;
         neighbours(c, i, st->tlane[i], front, r);
     }
-    const double a = idm_acceleration(c, st->delta[i], i, front);
+    const double a = idm_acceleration(c, i, i, front);
     if (k < n) st->acc[i] = a; else st->acc2[i] = a;
 }
 
@@ -1114,8 +1141,10 @@ TT_HD void regulate_apply(C& c, int i) {
 // ------------------------------------------------------------------------------------------------
 // one simulation sub-step (AbstractEnv._simulate body abstract.py:257-273)
 // ------------------------------------------------------------------------------------------------
+// In two parts -- Road.act (+ regulation), then Road.step -- so that a multi-env CTA can place an alignment barrier between
+// them as well (k_step); env_substep is the two back to back.
 template <class C, class Exec>
-TT_HD void env_substep(C& c, Exec& ex, const int32_t* actions) {  // inlined on purpose: a call boundary here costs ~30 % (ctx spills)
+TT_HD void substep_act(C& c, Exec& ex, const int32_t* actions) {  // inlined on purpose: a call boundary here costs ~30 % (ctx spills)
     // `actions`: this env's raw action ids (one per controlled vehicle) or null (action=None)
     auto* st = c.st;
     const SceneDev* sc = c.sc;
@@ -1176,11 +1205,22 @@ TT_HD void env_substep(C& c, Exec& ex, const int32_t* actions) {  // inlined on 
             ex.parn(n, [&](int t) { regulate_apply(c, t); });
         }
     }
+}
+template <class C, class Exec>
+TT_HD void substep_move(C& c, Exec& ex) {
+    auto* st = c.st;
+    const SceneDev* sc = c.sc;
+    const int n = st->n;
     ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; });
     ex.parn(n, [&](int t) { integrate(c, ex, t); });
     collide_all(c, ex);
     if (ex.first()) { st->steps += 1; if (!C::kPlain && sc->cfg.regulated) st->road_steps += 1; }
     ex.sync();
+}
+template <class C, class Exec>
+TT_HD void env_substep(C& c, Exec& ex, const int32_t* actions) {
+    substep_act(c, ex, actions);
+    substep_move(c, ex);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1549,6 +1589,7 @@ TT_HD void write_info(C& c, double* info, int E, int e, const int32_t* raw_actio
 // ------------------------------------------------------------------------------------------------
 struct SlotRegs {
     double d[13];
+    double lin[TTRL_NLIN];
     int32_t i[6];
     Route rt;
 };
@@ -1560,6 +1601,7 @@ TT_HD void slot_read(C& c, int t, SlotRegs& r) {
     r.d[11] = st->imp[t].x; r.d[12] = st->imp[t].y;
     r.i[0] = st->lane[t]; r.i[1] = st->tlane[t]; r.i[2] = st->flags[t]; r.i[3] = st->sidx[t]; r.i[4] = st->rlen[t]; r.i[5] = st->ytimer[t];
     r.rt = route_of(st, t);
+    if (!C::kPlain && c.lin) for (int k = 0; k < TTRL_NLIN; ++k) r.lin[k] = c.lin[k * C::V + t];
 }
 template <class C>
 TT_HD void slot_write(C& c, int t, const SlotRegs& r) {
@@ -1569,6 +1611,7 @@ TT_HD void slot_write(C& c, int t, const SlotRegs& r) {
     st->imp[t] = d2{r.d[11], r.d[12]};
     st->lane[t] = r.i[0]; st->tlane[t] = r.i[1]; st->flags[t] = r.i[2]; st->sidx[t] = r.i[3]; st->rlen[t] = r.i[4]; st->ytimer[t] = r.i[5];
     route_store(st, t, r.rt);
+    if (!C::kPlain && c.lin) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = r.lin[k];
 }
 
 // slots of the controlled vehicles from their agent bits (after a compaction / reset of a multi-agent env)
@@ -1674,7 +1717,10 @@ TT_HD void spawn_vehicle(C& c, Exec& ex, const ttrl_spawn_draw& d, const SpawnPa
         st->lane[s] = ln; st->tlane[s] = ln;         // controller.py:46
         st->tspeed[s] = speed;                       // controller.py:47
         st->timer[s] = py_mod1((px + py) * kPi);     // behavior.py:64
-        st->delta[s] = d.delta;                      // behavior.py:66-69
+        st->delta[s] = d.delta;                      // IDMVehicle.randomize_behavior behavior.py:66-69
+        if (!C::kPlain && c.lin) st->delta[s] = 4.0; // LinearVehicle.randomize_behavior (behavior.py:402-410) leaves the class DELTA
+        if (!C::kPlain && c.lin)
+            for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + s] = sc->cfg.lin_lo[k] + d.lin_u[k] * (sc->cfg.lin_hi[k] - sc->cfg.lin_lo[k]);
         st->flags[s] = 0; st->sidx[s] = 0; st->ytimer[s] = 0;
         st->rlen[s] = planned_route(c, ln, entry, exit_, s);
         st->n = s + 1;
@@ -1693,6 +1739,7 @@ struct GlobalState {
     double* ed;   // [NED][E]
     int E;
     int V;        // slots per env in this buffer
+    double* lin;  // [TTRL_NLIN][E][V] LinearVehicle parameters, or null (IDM traffic)
 };
 // CG = true: every load bypasses L1 (ld.global.cg).  Used for the shadow buffers of the asynchronous device reset, which
 // another kernel may have written while this one was already running (L1 is not coherent; a neighbouring env's earlier
@@ -1739,6 +1786,7 @@ TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
             st->rroad[1][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_ROAD1 * fs + o]); st->rlanew[1][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_LANE1 * fs + o]);
             st->rroad[2][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_ROAD2 * fs + o]); st->rlanew[2][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_LANE2 * fs + o]);
             st->ytimer[t] = gload<CG>(&g.vi[TTRL_I_YIELD_TIMER * fs + o]);
+            if (!C::kPlain && c.lin) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = g.lin ? gload<CG>(&g.lin[k * fs + o]) : c.sc->cfg.lin_default[k];
             if (C::kMulti && t < st_n && (st->flags[t] & TTRL_FL_CONTROLLED) && (st->flags[t] & TTRL_FL_AGENT_MASK))
                 st->egos[(st->flags[t] & TTRL_FL_AGENT_MASK) >> TTRL_FL_AGENT_SHIFT] = t;  // agents k >= 1 (distinct slots: no race)
         } else {
@@ -1747,6 +1795,7 @@ TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
             st->tspeed[t] = st->timer[t] = st->delta[t] = 0;
             st->lane[t] = st->tlane[t] = st->flags[t] = st->sidx[t] = st->rlen[t] = st->ytimer[t] = 0;
             for (int w = 0; w < TTRL_ROUTE_WORDS; ++w) st->rroad[w][t] = st->rlanew[w][t] = 0;
+            if (!C::kPlain && c.lin) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = 0;
         }
         st->mark[t] = 0; st->tl_old[t] = 0; st->acc2[t] = 0; st->tsteer[t] = 0; st->best[t] = -1; st->fo[t] = -1;
         // pre-check guard from the loaded speed (integrate refreshes it every sub-step)
@@ -1772,6 +1821,7 @@ TT_HD void store_env(C& c, Exec& ex, const GlobalState& g, int e) {
         if (t >= C::V) {  // the buffer has more slots than this kernel's capacity (small size class): dead by construction
             for (int f = 0; f < TTRL_ND; ++f) g.vd[f * fs + o] = 0;
             for (int f = 0; f < TTRL_NI; ++f) g.vi[f * fs + o] = 0;
+            if (g.lin) for (int f = 0; f < TTRL_NLIN; ++f) g.lin[f * fs + o] = 0;
             return;
         }
         const bool live = t < st->n;
@@ -1795,6 +1845,7 @@ TT_HD void store_env(C& c, Exec& ex, const GlobalState& g, int e) {
         g.vi[TTRL_I_ROUTE_ROAD2 * fs + o] = (int32_t)(st->rroad[2][t] & keep2);
         g.vi[TTRL_I_ROUTE_LANE2 * fs + o] = (int32_t)(st->rlanew[2][t] & keep2);
         g.vi[TTRL_I_YIELD_TIMER * fs + o] = live ? st->ytimer[t] : 0;
+        if (!C::kPlain && c.lin && g.lin) for (int k = 0; k < TTRL_NLIN; ++k) g.lin[k * fs + o] = live ? c.lin[k * C::V + t] : 0;
     });
 }
 
@@ -1820,6 +1871,13 @@ TT_HDN void device_spawn_draw(uint64_t seed, int64_t global_env, uint64_t counte
     d.n_pos = rad * cos(2 * kPi * u2);
     d.n_speed = rad * sin(2 * kPi * u2);
     d.delta = 3.5 + u01(e[2], e[3]) * (4.5 - 3.5);       // behavior.py:66-69
+    // LinearVehicle.randomize_behavior's five uniforms (behavior.py:402-410): three more counter blocks
+    for (int k = 0; k < 3; ++k) {
+        uint32_t f[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), ctr, dom | (3u + (uint32_t)k)};
+        philox4x32(f, (uint32_t)seed, (uint32_t)(seed >> 32));
+        d.lin_u[2 * k] = u01(f[0], f[1]);
+        if (2 * k + 1 < 5) d.lin_u[2 * k + 1] = u01(f[2], f[3]);
+    }
 }
 
 
@@ -1852,6 +1910,7 @@ TT_HD void reset_scalars(C& c, Exec& ex, int episode) {
         st->lane[t] = st->tlane[t] = st->flags[t] = st->sidx[t] = st->rlen[t] = st->ytimer[t] = 0;
         for (int w = 0; w < TTRL_ROUTE_WORDS; ++w) st->rroad[w][t] = st->rlanew[w][t] = 0;
         st->mark[t] = 0; st->tl_old[t] = 0; st->best[t] = -1; st->fo[t] = -1;
+        if (!C::kPlain && c.lin) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = 0;
     });
     ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; });
 }
@@ -2037,7 +2096,15 @@ TT_HD void reset_cast(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) 
             st->delta[s] = 4.0;
         } else {
             st->timer[s] = py_mod1((px + py) * kPi);                          // behavior.py:64
-            st->delta[s] = m.randomize ? 3.5 + ue * (4.5 - 3.5) : 4.0;        // behavior.py:66-69
+            st->delta[s] = (m.randomize && !c.lin) ? 3.5 + ue * (4.5 - 3.5) : 4.0;   // behavior.py:66-69
+            if (c.lin) {                                                      // LinearVehicle: class defaults or randomize_behavior
+                double lu[6];
+                reset_uniforms(seed, genv, episode, 0x300u + 4u * s, lu[0], lu[1]);
+                reset_uniforms(seed, genv, episode, 0x301u + 4u * s, lu[2], lu[3]);
+                reset_uniforms(seed, genv, episode, 0x302u + 4u * s, lu[4], lu[5]);
+                for (int k = 0; k < TTRL_NLIN; ++k)
+                    c.lin[k * C::V + s] = m.randomize ? cfg.lin_lo[k] + lu[k] * (cfg.lin_hi[k] - cfg.lin_lo[k]) : cfg.lin_default[k];
+            }
         }
         if (m.n_dest <= 0) { st->rlen[s] = -1; return; }                      // route None
         int k = m.n_dest == 1 ? 0 : (int)(ud * m.n_dest);                     // np_random.choice(destinations)
@@ -2087,7 +2154,9 @@ TT_HD void env_reset_lockstep(C& c, Exec& ex, bool active, uint64_t seed, int64_
     const int warmup = c.sc->rp.warmup_substeps;
     for (int k = 0; k < warmup; ++k) {
         ex.align();
-        if (active) env_substep(c, ex, nullptr);
+        if (active) substep_act(c, ex, nullptr);
+        ex.align2();
+        if (active) substep_move(c, ex);
     }
     if (active) reset_intersection_end(c, ex, seed, genv, episode);
 }

@@ -23,6 +23,9 @@ using namespace ttrl;
 //    vehicles per env, long scalar phases) aligned multi-env CTAs are 23 % faster, for 2-warp and larger teams the
 //    barrier skew costs more than the fetch sharing saves (profiles/r1c_variants.txt).
 // ------------------------------------------------------------------------------------------------
+#ifndef TT_ALIGN_POINTS
+#define TT_ALIGN_POINTS 1   /* CTA-wide alignment points per sub-step: 1 = at its start, 2 = also between Road.act and Road.step */
+#endif
 template <int V, int T>
 struct DevExec {
     int tid;        // thread within the team
@@ -43,6 +46,11 @@ struct DevExec {
         return;  // experiment: free-running teams
 #endif
         if (T <= 32 && G > 1) __syncthreads();
+    }
+    __device__ __forceinline__ void align2() {
+#if TT_ALIGN_POINTS >= 2
+        align();
+#endif
     }
     template <class F> __device__ __forceinline__ void par(F f) {
 #pragma unroll 1
@@ -161,6 +169,7 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V, P>& c, unsigned char* smem_ct
     c.pbits = lay.off_pred >= 0 ? reinterpret_cast<uint32_t*>(smem + lay.off_pred + sizeof(double) * 4 * V) : nullptr;
     c.obs_s = reinterpret_cast<float*>(smem + lay.off_obs);
     c.perm_s = reinterpret_cast<uint32_t*>(smem + lay.off_perm);
+    c.lin = lay.off_lin >= 0 ? reinterpret_cast<double*>(smem + lay.off_lin) : nullptr;
     c.cell = reinterpret_cast<int32_t*>(smem + lay.off_cell);
     c.gap_den = 2 * sqrt(-sc->cfg.comfort_acc_max * sc->cfg.comfort_acc_min);  // behavior.py:214-216
     c.tan_max_steer = tan(kPi / 3);
@@ -216,8 +225,10 @@ k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay
         if (f % TT_ALIGN_EVERY == 0)   // experiment: let the teams drift for TT_ALIGN_EVERY - 1 sub-steps
 #endif
         ex.align();
+        if (active) substep_act(c, ex, actions);
+        ex.align2();  // second alignment point, between Road.act and Road.step (TT_ALIGN_POINTS)
         if (active) {
-            env_substep(c, ex, actions);
+            substep_move(c, ex);
             veh_steps += c.st->n;
         }
     }
@@ -356,6 +367,7 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
     if (cfg.regulated) { l.off_pred = (int)off; off += sizeof(double) * 4 * V + align_up(sizeof(uint32_t) * ((V * (V - 1) / 2 + 31) / 32), 16); } else l.off_pred = -1;
     l.off_obs = (int)off; off += align_up(sizeof(float) * (cfg.obs_type == TTRL_OBS_KINEMATICS ? cfg.obs_vehicles * cfg.n_features : 4), 16);
     l.off_perm = (int)off; off += align_up(sizeof(uint32_t) * 2 * (cfg.obs_type == TTRL_OBS_KINEMATICS && cfg.order == TTRL_ORDER_SHUFFLED && cfg.obs_vehicles > 1 ? cfg.obs_vehicles - 1 : 0), 16);
+    if (cfg.vehicle_model == TTRL_VEHICLE_LINEAR) { l.off_lin = (int)off; off += sizeof(double) * TTRL_NLIN * V; } else l.off_lin = -1;
     l.off_cell = (int)off; off += align_up(sizeof(int32_t) * (cfg.obs_type == TTRL_OBS_GRID ? cfg.grid_w * cfg.grid_h :
                                                                 cfg.obs_type == TTRL_OBS_TTC ? TTRL_MAX_TTC_CELLS : 4), 16);
     l.per_env = (int)align_up(off, 128);

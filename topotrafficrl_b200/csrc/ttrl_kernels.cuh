@@ -8,7 +8,7 @@ namespace ttrl {
 
 struct SmemLayout {
     // offsets inside one env's region; a CTA's dynamic shared memory = lane table (lanes_bytes) + G env regions (per_env)
-    int off_SR, off_lmask, off_pred, off_obs, off_perm, off_cell, lanes_bytes, per_env, total, total_step, G, plain, n_sms;
+    int off_SR, off_lmask, off_pred, off_obs, off_perm, off_lin, off_cell, lanes_bytes, per_env, total, total_step, G, plain, n_sms;
 };
 
 // One set of launchers per compiled slot capacity.

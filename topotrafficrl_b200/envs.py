@@ -150,7 +150,8 @@ class AbstractEnv(Env):
         saved = None
         if self.cfg.spawn_enabled:
             draws = (abi.SpawnDraw * 1)()
-            saved = draw_spawn(self.np_random, float(self.config["spawn_probability"]), draws[0])
+            saved = draw_spawn(self.np_random, float(self.config["spawn_probability"]), draws[0],
+                               linear=self.cfg.vehicle_model == abi.VEHICLE_LINEAR)
             self.sim.inject_spawn(draws)
         obs, reward, term, trunc = self.sim.step_host(acts.reshape(1, K))
         if saved is not None and not self.sim.spawn_accepted()[0]:

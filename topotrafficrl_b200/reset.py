@@ -31,7 +31,21 @@ class ResetBackend(Protocol):
     def set_state(self, st: SimState) -> None: ...
 
 
-def draw_spawn(rng: np.random.Generator, spawn_probability: float, rec: abi.SpawnDraw):
+def draw_behavior(rng: np.random.Generator, linear: bool):
+    """``randomize_behavior()``: IDMVehicle draws DELTA ~ U[3.5, 4.5] (behavior.py:66-69); LinearVehicle draws uniform(size=3)
+    and uniform(size=2) for its acceleration / steering parameters (behavior.py:402-410).  Returns (delta, five uniforms | None)."""
+    if not linear:
+        return float(rng.uniform(low=3.5, high=4.5)), None
+    return 4.0, np.concatenate([rng.uniform(size=3), rng.uniform(size=2)])
+
+
+def linear_parameters(u) -> np.ndarray:
+    """ACCELERATION_RANGE[0] + ua (ACCELERATION_RANGE[1] - ACCELERATION_RANGE[0]), same for the steering pair."""
+    lo, hi = np.array(abi.LINEAR_RANGE_LO), np.array(abi.LINEAR_RANGE_HI)
+    return lo + np.asarray(u) * (hi - lo)
+
+
+def draw_spawn(rng: np.random.Generator, spawn_probability: float, rec: abi.SpawnDraw, linear: bool = False):
     """Consume the draws of one ``_spawn_vehicle`` call up to (and speculatively including) the behaviour
     draw; returns the generator state to restore if the spawn is rejected by the 15 m rule
     (the reference only draws DELTA for accepted vehicles: intersection_env.py:342-346)."""
@@ -46,7 +60,9 @@ def draw_spawn(rng: np.random.Generator, spawn_probability: float, rec: abi.Spaw
     rec.n_pos = rng.normal()
     rec.n_speed = rng.normal()
     saved = rng.bit_generator.state
-    rec.delta = rng.uniform(low=3.5, high=4.5)
+    rec.delta, u = draw_behavior(rng, linear)
+    for k in range(5):
+        rec.lin_u[k] = 0.0 if u is None else float(u[k])
     return saved
 
 
@@ -58,12 +74,13 @@ def reset_intersection(backend: ResetBackend, rngs: Sequence[np.random.Generator
         raise NotImplementedError(f"controlled_vehicles must be in 1..{abi.MAX_CONTROLLED}")
     n_vehicles = int(config["initial_vehicle_count"])
     sim_freq = int(config["simulation_frequency"])
-    st0 = SimState.zeros(E, backend.get_state().vcap)
+    linear = cfg.vehicle_model == abi.VEHICLE_LINEAR
+    st0 = SimState.zeros(E, backend.get_state().vcap, linear=linear)
     backend.set_state(st0)
     draws = (abi.SpawnDraw * E)()
 
     def attempt(longitudinal, position_deviation, speed_deviation, p, go_straight):
-        saved = [draw_spawn(rngs[e], p, draws[e]) for e in range(E)]
+        saved = [draw_spawn(rngs[e], p, draws[e], linear) for e in range(E)]
         accepted = backend.spawn(draws, float(longitudinal), position_deviation, speed_deviation, p, go_straight)
         for e in range(E):
             if saved[e] is not None and not accepted[e]:
@@ -154,13 +171,14 @@ class _Cast:
         self.st.env_i[abi.EI_EGO, self.e] = self.n
         self.n += 1
 
-    def idm_on_lane(self, lane_index, longitudinal: float, speed: float, destination, delta: float = 4.0) -> None:
+    def idm_on_lane(self, lane_index, longitudinal: float, speed: float, destination, delta: float = 4.0, linear=None) -> None:
+        """An ``other_vehicles_type`` vehicle; ``linear``: its LinearVehicle parameters (None with IDM traffic)."""
         lane = self.net.get_lane(lane_index)
         position, heading = lane.position(longitudinal, 0), float(lane.heading_at(longitudinal))
         lane_key = self.net.get_closest_lane_index(position, heading)
         self.st.set_vehicle(self.e, self.n, x=float(position[0]), y=float(position[1]), heading=heading, speed=float(speed),
                             lane=self.table.flat(lane_key), timer=float((np.sum(position) * np.pi) % 1.0), delta=float(delta),
-                            route=self._route(lane_key, destination))
+                            route=self._route(lane_key, destination), linear=linear)
         self.n += 1
 
     def done(self) -> None:
@@ -170,9 +188,15 @@ class _Cast:
 def reset_roundabout(rngs: Sequence[np.random.Generator], net: RoadNetwork, table: NetworkTable, config: dict, cfg: abi.Config,
                      vcap: int) -> SimState:
     """``RoundaboutEnv._make_vehicles`` (roundabout_env.py:326-387) for one Generator per env, draws in the reference's order."""
-    st = SimState.zeros(len(rngs), vcap)
+    linear = cfg.vehicle_model == abi.VEHICLE_LINEAR
+    st = SimState.zeros(len(rngs), vcap, linear=linear)
     position_deviation = speed_deviation = 2
     destinations = ["exr", "sxr", "nxr"]
+
+    def behavior(rng):  # vehicle.randomize_behavior()
+        delta, u = draw_behavior(rng, linear)
+        return dict(delta=delta, linear=None if u is None else linear_parameters(u))
+
     for e, rng in enumerate(rngs):
         cast = _Cast(st, e, net, table, cfg)
         ego_lane = net.get_lane(("ser", "ses", 0))
@@ -184,18 +208,18 @@ def reset_roundabout(rngs: Sequence[np.random.Generator], net: RoadNetwork, tabl
             destination = destinations[config["incoming_vehicle_destination"]]
         else:
             destination = str(rng.choice(destinations))
-        cast.idm_on_lane(("we", "sx", 1), lon, speed, destination, delta=rng.uniform(low=3.5, high=4.5))
+        cast.idm_on_lane(("we", "sx", 1), lon, speed, destination, **behavior(rng))
         # other vehicles
         for i in list(range(1, 2)) + list(range(-1, 0)):
             lon = 20 * i + rng.normal() * position_deviation
             speed = 16 + rng.normal() * speed_deviation
             destination = str(rng.choice(destinations))
-            cast.idm_on_lane(("we", "sx", 0), lon, speed, destination, delta=rng.uniform(low=3.5, high=4.5))
+            cast.idm_on_lane(("we", "sx", 0), lon, speed, destination, **behavior(rng))
         # entering vehicle
         lon = 50 + rng.normal() * position_deviation
         speed = 16 + rng.normal() * speed_deviation
         destination = str(rng.choice(destinations))
-        cast.idm_on_lane(("eer", "ees", 0), lon, speed, destination, delta=rng.uniform(low=3.5, high=4.5))
+        cast.idm_on_lane(("eer", "ees", 0), lon, speed, destination, **behavior(rng))
         cast.done()
     return st
 
@@ -203,7 +227,8 @@ def reset_roundabout(rngs: Sequence[np.random.Generator], net: RoadNetwork, tabl
 def reset_uturn(rngs: Sequence[np.random.Generator], net: RoadNetwork, table: NetworkTable, config: dict, cfg: abi.Config,
                 vcap: int) -> SimState:
     """``UTurnEnv._make_vehicles`` (u_turn_env.py:173-271)."""
-    st = SimState.zeros(len(rngs), vcap)
+    linear = cfg.vehicle_model == abi.VEHICLE_LINEAR
+    st = SimState.zeros(len(rngs), vcap, linear=linear)
     position_deviation = speed_deviation = 2
     for e, rng in enumerate(rngs):
         cast = _Cast(st, e, net, table, cfg)
@@ -214,17 +239,17 @@ def reset_uturn(rngs: Sequence[np.random.Generator], net: RoadNetwork, table: Ne
         for lane_index, lon0, speed0, randomize in script:
             lon = lon0 + rng.normal() * position_deviation
             speed = speed0 + rng.normal() * speed_deviation
-            delta = rng.uniform(low=3.5, high=4.5) if randomize else 4.0  # randomize_behavior (behavior.py:66-69)
-            cast.idm_on_lane(lane_index, lon, speed, "d", delta=delta)
+            delta, u = draw_behavior(rng, linear) if randomize else (4.0, None)  # randomize_behavior (behavior.py:66-69, :402-410)
+            params = None if not linear else (linear_parameters(u) if u is not None else np.array(abi.LINEAR_DEFAULTS))
+            cast.idm_on_lane(lane_index, lon, speed, "d", delta=delta, linear=params)
         cast.done()
     return st
 
 
 def _compact(st: SimState, e: int, order: List[int]) -> None:
-    vd = st.veh_d[:, e, :].copy()
-    vi = st.veh_i[:, e, :].copy()
-    st.veh_d[:, e, :] = 0
-    st.veh_i[:, e, :] = 0
-    for dst, src in enumerate(order):
-        st.veh_d[:, e, dst] = vd[:, src]
-        st.veh_i[:, e, dst] = vi[:, src]
+    arrays = [st.veh_d, st.veh_i] + ([st.lin] if st.lin is not None else [])
+    for a in arrays:
+        old = a[:, e, :].copy()
+        a[:, e, :] = 0
+        for dst, src in enumerate(order):
+            a[:, e, dst] = old[:, src]

@@ -251,9 +251,15 @@ def build_config(table: NetworkTable, config: dict, scene: str, ego_lanes_count:
     cfg.regulated = 1 if scene == "intersection" else 0
     # the class of the surrounding traffic (intersection_env.py:257, roundabout_env.py:337, u_turn_env.py:203)
     ovt = str(config.get("other_vehicles_type", "ttrl_env.vehicle.behavior.IDMVehicle")).rsplit(".", 1)[-1]
-    if ovt != "IDMVehicle":
-        raise NotImplementedError(f"other_vehicles_type {ovt!r}: only IDMVehicle traffic runs on the device "
-                                  "(LinearVehicle / MultipleModelVehicle would silently change the dynamics)")
+    if ovt == "LinearVehicle" and scene != "highway":
+        # behavior.py:350-558: controllers linear in per-vehicle parameters, TIME_WANTED 2.5 (class attribute :373)
+        cfg.vehicle_model = abi.VEHICLE_LINEAR
+        cfg.time_wanted = 2.5
+        for k in range(abi.NLIN):
+            cfg.lin_lo[k], cfg.lin_hi[k], cfg.lin_default[k] = abi.LINEAR_RANGE_LO[k], abi.LINEAR_RANGE_HI[k], abi.LINEAR_DEFAULTS[k]
+    elif ovt != "IDMVehicle":
+        raise NotImplementedError(f"other_vehicles_type {ovt!r}: IDMVehicle and LinearVehicle traffic run on the device "
+                                  "(AggressiveVehicle / DefensiveVehicle / MultipleModelVehicle would silently change the dynamics)")
     cfg.controlled_vehicles = int(config.get("controlled_vehicles", 1))
     if not 1 <= cfg.controlled_vehicles <= abi.MAX_CONTROLLED:
         # ego k starts on arm k % 4 (intersection_env.py:287-289): a fifth ego would be placed onto the first one

@@ -29,6 +29,7 @@ class Sim:
         self._L = lib()
         self.cfg, self.table = cfg, table
         self.num_envs, self.vcap, self.device = int(num_envs), int(vcap), int(device)
+        self.linear = cfg.vehicle_model == abi.VEHICLE_LINEAR  # LinearVehicle traffic: the state carries SimState.lin
         h = C.c_void_p()
         check(self._L.ttrl_sim_create(C.byref(cfg), C.cast(table.lanes, C.c_void_p), C.cast(table.roads, C.c_void_p),
                                       _p(table.node_first), _p(table.node_roads), self.num_envs, self.vcap, self.device,
@@ -56,16 +57,26 @@ class Sim:
         st = st.contiguous()
         assert st.num_envs == self.num_envs and st.vcap == self.vcap, (st.num_envs, st.vcap, self.num_envs, self.vcap)
         check(self._L.ttrl_sim_set_state(self._h, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d)))
+        if self.linear:
+            if st.lin is None:
+                raise ValueError("this sim runs LinearVehicle traffic: the state needs its parameter block (SimState.lin)")
+            check(self._L.ttrl_sim_set_linear_params(self._h, _p(st.lin)))
 
     def get_state(self) -> SimState:
-        st = SimState.zeros(self.num_envs, self.vcap)
+        st = SimState.zeros(self.num_envs, self.vcap, linear=self.linear)
         check(self._L.ttrl_sim_get_state(self._h, _p(st.veh_d), _p(st.veh_i), _p(st.env_i), _p(st.env_d)))
+        if self.linear:
+            check(self._L.ttrl_sim_get_linear_params(self._h, _p(st.lin)))
         return st
 
     def set_reset_pool(self, pool: SimState) -> None:
         pool = pool.contiguous()
         assert pool.vcap == self.vcap
         check(self._L.ttrl_sim_set_reset_pool(self._h, pool.num_envs, _p(pool.veh_d), _p(pool.veh_i), _p(pool.env_i), _p(pool.env_d)))
+        if self.linear:
+            if pool.lin is None:
+                raise ValueError("this sim runs LinearVehicle traffic: the pool needs its parameter block (SimState.lin)")
+            check(self._L.ttrl_sim_set_reset_pool_linear_params(self._h, _p(pool.lin)))
 
     def set_autoreset(self, mode) -> None:
         """``False``/0: off; ``True``/1: restart finished envs from the reset pool; 2 or ``"device"``: device-side reset."""

@@ -54,11 +54,13 @@ class SimState:
     veh_i: np.ndarray  # int32   [NI, E, V]
     env_i: np.ndarray  # int32   [NEI, E]
     env_d: np.ndarray  # float64 [NED, E]
+    lin: Optional[np.ndarray] = None  # float64 [NLIN, E, V]: LinearVehicle parameters (``vehicle_model`` linear), else None
 
     @classmethod
-    def zeros(cls, num_envs: int, vcap: int) -> "SimState":
+    def zeros(cls, num_envs: int, vcap: int, linear: bool = False) -> "SimState":
         return cls(np.zeros((abi.ND, num_envs, vcap), np.float64), np.zeros((abi.NI, num_envs, vcap), np.int32),
-                   np.zeros((abi.NEI, num_envs), np.int32), np.zeros((abi.NED, num_envs), np.float64))
+                   np.zeros((abi.NEI, num_envs), np.int32), np.zeros((abi.NED, num_envs), np.float64),
+                   np.zeros((abi.NLIN, num_envs, vcap), np.float64) if linear else None)
 
     @property
     def num_envs(self) -> int:
@@ -68,19 +70,21 @@ class SimState:
     def vcap(self) -> int:
         return self.veh_d.shape[2]
 
+    def _map(self, f) -> "SimState":
+        return SimState(f(self.veh_d), f(self.veh_i), f(self.env_i), f(self.env_d), None if self.lin is None else f(self.lin))
+
     def copy(self) -> "SimState":
-        return SimState(self.veh_d.copy(), self.veh_i.copy(), self.env_i.copy(), self.env_d.copy())
+        return self._map(lambda a: a.copy())
 
     def contiguous(self) -> "SimState":
-        return SimState(*(np.ascontiguousarray(a) for a in (self.veh_d, self.veh_i, self.env_i, self.env_d)))
+        return self._map(np.ascontiguousarray)
 
     def slice_envs(self, lo: int, hi: int) -> "SimState":
-        return SimState(self.veh_d[:, lo:hi].copy(), self.veh_i[:, lo:hi].copy(),
-                        self.env_i[:, lo:hi].copy(), self.env_d[:, lo:hi].copy())
+        return self._map(lambda a: a[:, lo:hi].copy())
 
     def select_envs(self, idx) -> "SimState":
         idx = np.asarray(idx)
-        return SimState(self.veh_d[:, idx].copy(), self.veh_i[:, idx].copy(), self.env_i[:, idx].copy(), self.env_d[:, idx].copy())
+        return self._map(lambda a: a[:, idx].copy())
 
     def n_vehicles(self) -> np.ndarray:
         return self.env_i[abi.EI_NVEH]
@@ -90,7 +94,8 @@ class SimState:
 
     def set_vehicle(self, e: int, s: int, *, x, y, heading, speed, lane, target_lane=None, target_speed=None,
                     timer=0.0, delta=4.0, mdp=False, controlled=False, crashed=False, speed_index=0,
-                    route=None, steering=0.0, accel=0.0, impact=None, yielding=False, yield_timer=0, agent=0) -> None:
+                    route=None, steering=0.0, accel=0.0, impact=None, yielding=False, yield_timer=0, agent=0,
+                    linear=None) -> None:
         d, i = self.veh_d, self.veh_i
         d[abi.D_X, e, s], d[abi.D_Y, e, s] = x, y
         d[abi.D_HEADING, e, s], d[abi.D_SPEED, e, s] = heading, speed
@@ -114,3 +119,5 @@ class SimState:
         for w in range(abi.ROUTE_WORDS):
             i[abi.I_ROUTE_ROAD_WORDS[w], e, s], i[abi.I_ROUTE_LANE_WORDS[w], e, s] = rr[w], rl[w]
         i[abi.I_YIELD_TIMER, e, s] = yield_timer
+        if self.lin is not None:  # ACCELERATION_PARAMETERS + STEERING_PARAMETERS of a LinearVehicle (zeros for the controlled ones)
+            self.lin[:, e, s] = 0.0 if linear is None else np.asarray(linear, np.float64)
