@@ -391,6 +391,40 @@ int ttrl_qnet_act_injected(ttrl_qnet* q, const float* obs_dev, int num_envs, dou
                            int32_t* actions_dev, float* q_dev, void* stream);
 int64_t ttrl_qnet_launch_count(const ttrl_qnet* q);
 
+/* ------------------------------------------------------------------------------------------------
+ * DQN update (training driver) for the MultiLayerPerceptron model with two hidden layers.
+ * Replaces DQNAgent.compute_bellman_residual (deep_q_network/pytorch.py:41-73: value_net(s), value_net(s'), target_net(s'),
+ * double-DQN target, loss) + DQNAgent.step_optimizer (pytorch.py:32-39: backward, clamp to [-1, 1], Adam) for one minibatch
+ * gathered from a device-resident replay memory.  Parameters are six float32 device tensors in torch's state_dict order and
+ * layout: layers.0.weight [h1][n_in], layers.0.bias, layers.1.weight [h2][h1], layers.1.bias, predict.weight [A][h2], predict.bias.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ttrl_dqn ttrl_dqn;
+enum { TTRL_LOSS_L2 = 0, TTRL_LOSS_L1 = 1, TTRL_LOSS_SMOOTH_L1 = 2 }; /* loss_function_factory: F.mse_loss / l1_loss / smooth_l1_loss */
+typedef struct ttrl_dqn_desc {
+    int32_t n_in, h1, h2, n_actions;  /* flattened observation size, hidden widths (<= 128), actions (<= 7) */
+    int32_t batch;                    /* minibatch size (any; processed 64 rows at a time) */
+    int32_t loss;                     /* TTRL_LOSS_* */
+    int32_t double_q;                 /* config["double"] (pytorch.py:52-60) */
+    float gamma;
+} ttrl_dqn_desc;
+int ttrl_dqn_create(const ttrl_dqn_desc* desc, int device, ttrl_dqn** out);
+int ttrl_dqn_destroy(ttrl_dqn* q);
+int64_t ttrl_dqn_num_params(const ttrl_dqn* q);
+int64_t ttrl_dqn_launch_count(const ttrl_dqn* q);
+/* Flat gradient (parameter order above, float32[num_params]) and mean loss of the minibatch `idx_dev` (int64[batch] rows of the
+ * replay memory: state / next_state float32[capacity][n_in], action int64, reward float32, terminal uint8).  One launch. */
+int ttrl_dqn_grad(ttrl_dqn* q, const float* const* value_params /* 6 device pointers */, const float* const* target_params,
+                  const float* state_dev, const float* next_state_dev, const int64_t* action_dev, const float* reward_dev,
+                  const uint8_t* terminal_dev, const int64_t* idx_dev, float* grad_dev, float* loss_dev, void* stream);
+/* grad * grad_scale (1 / world size after an all-reduce), clamp to +-grad_clamp, torch.optim.Adam's update number `step` (1-based) of
+ * the six tensors and their exp_avg / exp_avg_sq; rollout_blob_dev (or NULL): the weight blob of a ttrl_qnet of the same
+ * architecture, refreshed in the same pass (same layout as ttrl_qnet_set_weights).  One launch. */
+int ttrl_dqn_adam(ttrl_dqn* q, float* const* params, float* const* exp_avg, float* const* exp_avg_sq, const float* grad_dev, int64_t step,
+                  double lr, double beta1, double beta2, double eps, double weight_decay, double grad_clamp, double grad_scale,
+                  float* rollout_blob_dev, void* stream);
+/* device pointer of a ttrl_qnet's float32 weight blob (layout of ttrl_qnet_create) for ttrl_dqn_adam's rollout_blob_dev */
+float* ttrl_qnet_weights_dev(ttrl_qnet* q);
+
 #ifdef __cplusplus
 }
 #endif

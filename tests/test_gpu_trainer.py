@@ -125,7 +125,7 @@ def test_cuda_graph_update_equals_eager_update():
     for graph in (False, True):
         env = factory.load_environment(ENV_JSON, num_envs=128, seed=9)
         envs.append(env)
-        agents.append(factory.load_agent(dict(AGENT, model=CONFIGS["mlp"]), env, seed=4, cuda_graph=graph))
+        agents.append(factory.load_agent(dict(AGENT, model=CONFIGS["mlp"]), env, seed=4, cuda_graph=graph, update_kernel=False))
     obs = [env.reset()[0] for env in envs]
     for step in range(8):
         for k, (env, agent) in enumerate(zip(envs, agents)):
@@ -139,6 +139,64 @@ def test_cuda_graph_update_equals_eager_update():
         d = (p.detach() - q.detach()).abs()
         assert float(d.max()) < 5e-5 and float(d.median()) < 2e-7, (n, float(d.max()), float(d.median()))
     assert abs(float(agents[0].last_loss) - float(agents[1].last_loss)) < 1e-4
+    for a in agents:
+        a.close()
+    for e in envs:
+        e.close()
+
+
+@pytest.mark.parametrize("loss,double", [("l2", True), ("smooth_l1", True), ("l1", False)])
+def test_kernel_update_equals_torch_autograd_update(loss, double):
+    """The library's DQN update kernels (ttrl_dqn_grad + ttrl_dqn_adam: forwards, double-DQN target, loss, backward, clamp, Adam,
+    rollout blob) against the torch autograd update (pytorch.py:32-73) on the same replay memory and the same minibatches:
+    gradients of one minibatch to 1e-6, parameters and loss curve over 40 updates to float32 rounding, rollout weights refreshed."""
+    torch = _torch()
+    from topotrafficrl_b200.trainer import KernelDQNUpdate
+    cfg = dict(AGENT, model=CONFIGS["mlp"], loss_function=loss, double=double, batch_size=96, target_update=8)  # 96 rows: a full + a ragged pass
+    env = factory.load_environment(ENV_JSON, num_envs=128, seed=9)
+    envs = [env]
+    agents = [factory.load_agent(cfg, env, seed=4, update_kernel=kernel) for kernel in (False, True)]
+    assert agents[0].kernel_update is None and isinstance(agents[1].kernel_update, KernelDQNUpdate)
+    obs, _ = env.reset()
+    losses = [[], []]
+    for step in range(40):
+        prev = obs.clone()
+        a = agents[0].act(prev)  # ONE stream of transitions feeds both learners (same replay memory, same minibatch indices)
+        obs, reward, term, trunc, info = env.step(a)
+        for k, agent in enumerate(agents):
+            agent.record(prev, a, reward, obs, term, trunc, info)
+            losses[k].append(float(agent.last_loss))
+        if step == 0:  # one minibatch: the kernel's flat gradient against autograd's, before anything can drift
+            ref, ker = agents
+            idx = torch.arange(96, device="cuda")
+            ker.kernel_update._L.ttrl_dqn_grad(ker.kernel_update._h, ker.kernel_update._pv, ker.kernel_update._pt, ker.memory.state.data_ptr(),
+                                               ker.memory.next_state.data_ptr(), ker.memory.action.data_ptr(), ker.memory.reward.data_ptr(),
+                                               ker.memory.terminal.data_ptr(), idx.data_ptr(), ker.kernel_update.grad.data_ptr(),
+                                               ker.kernel_update.loss.data_ptr(), 0)
+            m = ker.memory
+            l = ker.compute_bellman_residual((m.state[idx], m.action[idx], m.reward[idx], m.next_state[idx], m.terminal[idx]))
+            ker.value_net.zero_grad()
+            l.backward()
+            want = torch.cat([p.grad.reshape(-1) for p in ker.kernel_update.value_params])
+            np.testing.assert_allclose(ker.kernel_update.grad.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=2e-6)
+            assert abs(float(ker.kernel_update.loss[0]) - float(l)) < 1e-5
+            ker.value_net.zero_grad()
+        assert torch.equal(agents[0].memory.state, agents[1].memory.state)
+    assert agents[0].steps == agents[1].steps == 40
+    for (n, p), q in zip(agents[0].value_net.named_parameters(), agents[1].value_net.parameters()):
+        d = (p.detach() - q.detach()).abs()
+        assert float(d.max()) < 2e-3 and float(d.median()) < 2e-5, (n, float(d.max()), float(d.median()))
+    np.testing.assert_allclose(losses[1][:8], losses[0][:8], rtol=1e-4, atol=1e-6)
+    # Adam state in torch's own format (checkpoints), target network copied at multiples of target_update
+    st = agents[1].optimizer.state[agents[1].kernel_update.value_params[0]]
+    assert float(st["step"]) == 40 and float(st["exp_avg_sq"].abs().sum()) > 0
+    assert all(torch.equal(a, b) for a, b in zip(agents[1].target_net.state_dict().values(), agents[1].value_net.state_dict().values()))
+    # the rollout kernels carry the updated network (blob written by ttrl_dqn_adam)
+    agents[1].eval()
+    _, q = agents[1].rollout.act(obs.reshape(-1, 15, 7), step_exploration_time=False, return_q=True)
+    with torch.no_grad():
+        want = agents[1].value_net(obs.reshape(-1, 15, 7))
+    np.testing.assert_allclose(q.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=5e-5)
     for a in agents:
         a.close()
     for e in envs:

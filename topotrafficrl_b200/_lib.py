@@ -81,6 +81,16 @@ def lib():
     L.ttrl_qnet_act_injected.argtypes = [vp, vp, i32, dbl, vp, vp, vp, vp]
     L.ttrl_qnet_launch_count.argtypes = [vp]
     L.ttrl_qnet_launch_count.restype = i64
+    L.ttrl_qnet_weights_dev.argtypes = [vp]
+    L.ttrl_qnet_weights_dev.restype = vp
+    L.ttrl_dqn_create.argtypes = [C.POINTER(abi.DqnDesc), i32, C.POINTER(vp)]
+    L.ttrl_dqn_destroy.argtypes = [vp]
+    L.ttrl_dqn_num_params.argtypes = [vp]
+    L.ttrl_dqn_num_params.restype = i64
+    L.ttrl_dqn_launch_count.argtypes = [vp]
+    L.ttrl_dqn_launch_count.restype = i64
+    L.ttrl_dqn_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ttrl_dqn_adam.argtypes = [vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, dbl, dbl, dbl, vp, vp]
     if L.ttrl_abi_version() != abi.ABI_VERSION:
         raise TTRLError(f"{LIB_PATH} has ABI version {L.ttrl_abi_version()}, this package binds version {abi.ABI_VERSION}: rebuild it")
     _lib = L

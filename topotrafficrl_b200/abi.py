@@ -143,6 +143,14 @@ REWARD_KEYS = {
 }
 
 
+LOSS_L2, LOSS_L1, LOSS_SMOOTH_L1 = 0, 1, 2
+
+
+class DqnDesc(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("h1", C.c_int32), ("h2", C.c_int32), ("n_actions", C.c_int32), ("batch", C.c_int32),
+                ("loss", C.c_int32), ("double_q", C.c_int32), ("gamma", C.c_float)]
+
+
 class QnetDesc(C.Structure):
     _fields_ = [
         ("type", C.c_int32), ("n_entities", C.c_int32), ("n_features", C.c_int32), ("n_actions", C.c_int32),

@@ -933,6 +933,8 @@ int ttrl_qnet_set_weights(ttrl_qnet* q, const float* weights, int64_t n_weights,
     return 0;
 }
 
+float* ttrl_qnet_weights_dev(ttrl_qnet* q) { return q ? q->d_weights : nullptr; }
+
 int ttrl_qnet_destroy(ttrl_qnet* q) {
     if (!q) return 0;
     cudaSetDevice(q->device);

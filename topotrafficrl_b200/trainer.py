@@ -32,9 +32,97 @@ from typing import Optional
 
 import numpy as np
 
+import ctypes as C
+
+from . import abi
+from ._lib import check, lib
 from .agent import QNetRollout
 from .factory import rec_update
 from .models import model_factory, size_model_config
+
+
+class KernelDQNUpdate:
+    """The DQN update as two kernels of the CUDA library (``csrc/ttrl_dqn.cu``: ``ttrl_dqn_grad`` = the three forward passes,
+    the double-DQN target, the loss and the backward pass of one minibatch gathered from the device replay memory, in ONE
+    launch; ``ttrl_dqn_adam`` = gradient clamp + Adam + the refreshed weight blob of the rollout kernels, in one more) instead of
+    ~150 torch / cuBLAS launches.  MultiLayerPerceptron with two hidden layers (baseline.json), ADAM, l2 / l1 / smooth_l1.
+    The torch modules and ``torch.optim.Adam``'s state tensors are updated IN PLACE, so checkpoints, the target-network copy
+    and evaluation keep working unchanged."""
+
+    LOSSES = {"l2": abi.LOSS_L2, "l1": abi.LOSS_L1, "smooth_l1": abi.LOSS_SMOOTH_L1}
+
+    @classmethod
+    def eligible(cls, model_config: dict, config: dict, obs_shape, n_actions: int) -> bool:
+        layers = list(model_config.get("layers", [64, 64]))
+        return (model_config.get("type") == "MultiLayerPerceptron" and len(layers) == 2 and max(layers) <= 128
+                and model_config.get("activation", "RELU") == "RELU" and int(np.prod(obs_shape)) <= 128 and n_actions <= 7
+                and config["optimizer"]["type"] == "ADAM" and config["loss_function"] in cls.LOSSES)
+
+    def __init__(self, agent) -> None:
+        import torch
+
+        self.torch, self.agent = torch, agent
+        self._L = lib()
+        net, cfg = agent.value_net, agent.config
+        d = abi.DqnDesc()
+        d.n_in, d.h1, d.h2 = int(np.prod(agent.obs_shape)), int(net.layers[0].out_features), int(net.layers[1].out_features)
+        d.n_actions, d.batch = int(agent.n_actions), int(cfg["batch_size"])
+        d.loss, d.double_q, d.gamma = self.LOSSES[cfg["loss_function"]], int(bool(cfg["double"])), float(cfg["gamma"])
+        h = C.c_void_p()
+        check(self._L.ttrl_dqn_create(C.byref(d), agent.device.index or 0, C.byref(h)))
+        self._h = h
+        names = ["layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias", "predict.weight", "predict.bias"]
+        self.value_params = [dict(agent.value_net.named_parameters())[n] for n in names]
+        self.target_params = [dict(agent.target_net.named_parameters())[n] for n in names]
+        n = int(self._L.ttrl_dqn_num_params(self._h))
+        assert n == sum(p.numel() for p in self.value_params)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=agent.device)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=agent.device)
+        # torch.optim.Adam creates its state at the first step(): the same tensors, made here, are what the kernel updates
+        for p in self.value_params:
+            st = agent.optimizer.state[p]
+            if "exp_avg" not in st:
+                st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(p), torch.zeros_like(p)
+        self._bind()
+
+    def _ptrs(self, tensors):
+        for t in tensors:
+            assert t.is_contiguous() and t.dtype == self.torch.float32
+        return (C.c_void_p * 6)(*[t.data_ptr() for t in tensors])
+
+    def _bind(self) -> None:
+        """(Re)read the device pointers: after construction and after anything that may have replaced a tensor (load())."""
+        state = self.agent.optimizer.state
+        self._pv, self._pt = self._ptrs([p.data for p in self.value_params]), self._ptrs([p.data for p in self.target_params])
+        self._pm = self._ptrs([state[p]["exp_avg"] for p in self.value_params])
+        self._pq = self._ptrs([state[p]["exp_avg_sq"] for p in self.value_params])
+
+    def update(self, idx, refresh_rollout: bool) -> None:
+        torch, agent, m = self.torch, self.agent, self.agent.memory
+        stream = int(torch.cuda.current_stream(agent.device).cuda_stream)
+        check(self._L.ttrl_dqn_grad(self._h, self._pv, self._pt, m.state.data_ptr(), m.next_state.data_ptr(), m.action.data_ptr(),
+                                    m.reward.data_ptr(), m.terminal.data_ptr(), idx.data_ptr(), self.grad.data_ptr(), self.loss.data_ptr(), stream))
+        scale = 1.0
+        if agent._world > 1:  # gradient averaging over the ranks: the one data-path collective (NCCL)
+            torch.distributed.all_reduce(self.grad)
+            scale = 1.0 / agent._world
+        g = agent.optimizer.param_groups[0]
+        step = int(agent.optimizer.state[self.value_params[0]]["step"].item()) + 1  # Adam's own counter (restored by load())
+        blob = self._L.ttrl_qnet_weights_dev(agent.rollout._h) if refresh_rollout else None
+        check(self._L.ttrl_dqn_adam(self._h, self._pv, self._pm, self._pq, self.grad.data_ptr(), step, float(g["lr"]), float(g["betas"][0]),
+                                    float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), 1.0, scale, blob, stream))
+        for p in self.value_params:  # host-side counters of torch's optimiser state (checkpoint format)
+            agent.optimizer.state[p]["step"] += 1
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.ttrl_dqn_launch_count(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.ttrl_dqn_destroy(self._h)
+            self._h = None
 
 
 class DeviceReplayMemory:
@@ -86,7 +174,8 @@ class BatchedDQNAgent:
                     exploration=dict(method="EpsilonGreedy"), target_update=1, double=True, n_steps=1)
 
     def __init__(self, env, config: Optional[dict] = None, seed: int = 0, rollout_mode: str = "fp32",
-                 updates_per_step: int = 1, refresh_every: int = 1, cuda_graph: bool = False, min_memory_steps: int = 8) -> None:
+                 updates_per_step: int = 1, refresh_every: int = 1, cuda_graph: bool = False, min_memory_steps: int = 8,
+                 update_kernel="auto") -> None:
         import torch
         from torch.nn import functional as F
 
@@ -115,6 +204,15 @@ class BatchedDQNAgent:
         self._world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         # several ranks: the gradient all-reduce sits between backward and the optimiser step, the update runs eagerly
         self.cuda_graph = bool(cuda_graph) and self._world == 1
+        # update_kernel: "auto" = the library's own update kernels when the model / optimiser / loss are ones they implement
+        # (KernelDQNUpdate), torch autograd otherwise; True = require them; False = torch autograd
+        eligible = KernelDQNUpdate.eligible(self.model_config, self.config, self.obs_shape, self.n_actions)
+        if update_kernel is True and not eligible:
+            raise NotImplementedError("update_kernel=True: the update kernels implement MultiLayerPerceptron (two hidden layers <= 128 "
+                                      "wide, RELU), ADAM and the l2 / l1 / smooth_l1 losses")
+        use_kernel = bool(update_kernel) and eligible
+        if use_kernel:
+            self.cuda_graph = False
         if self.cuda_graph and opt["type"] != "ADAM":
             raise NotImplementedError("cuda_graph=True is implemented for the ADAM optimiser")
         if opt["type"] == "ADAM":
@@ -140,6 +238,7 @@ class BatchedDQNAgent:
         self.rollout = QNetRollout(self.model_config, self.value_net.state_dict(), self.obs_shape, self.n_actions,
                                    device=self.device.index or 0, exploration=self.config["exploration"],
                                    seed=(int(seed) + 0x9E3779B1 * first_env) & 0x7FFFFFFFFFFFFFFF, mode=rollout_mode)
+        self.kernel_update = KernelDQNUpdate(self) if use_kernel else None
         self.updates_per_step, self.refresh_every = int(updates_per_step), int(refresh_every)
         self.steps = 0          # optimiser steps (update_target_network's counter, abstract.py:91-94)
         self.training = True
@@ -194,14 +293,20 @@ class BatchedDQNAgent:
         for _ in range(self.updates_per_step):
             if not ready:
                 return
-            if self.cuda_graph:
+            if self.kernel_update is not None:
+                B = int(self.config["batch_size"])
+                idx = torch.randperm(self.memory.size, device=self.device, generator=self.gen)[:B]
+                last = _ == self.updates_per_step - 1
+                self.kernel_update.update(idx, refresh_rollout=last and (self.steps + 1) % self.refresh_every == 0)
+                self.last_loss = self.kernel_update.loss[0]
+            elif self.cuda_graph:
                 self._graph_update()
             else:
                 loss = self.compute_bellman_residual(self.memory.sample(self.config["batch_size"]))
                 self.step_optimizer(loss)
                 self.last_loss = loss.detach()
             self.update_target_network()
-        if self.steps % self.refresh_every == 0:
+        if self.kernel_update is None and self.steps % self.refresh_every == 0:  # (the kernel path refreshes the blob itself)
             self.rollout.load_parameters(self.value_net, self.model_config)
 
     def compute_bellman_residual(self, batch):
@@ -320,9 +425,13 @@ class BatchedDQNAgent:
         else:
             self.optimizer.load_state_dict(checkpoint["optimizer"])
         self.rollout.load_parameters(self.value_net, self.model_config)
+        if self.kernel_update is not None:
+            self.kernel_update._bind()
         return filename
 
     def close(self) -> None:
+        if self.kernel_update is not None:
+            self.kernel_update.close()
         self.rollout.close()
 
 
