@@ -81,7 +81,7 @@ struct HostEnv {
     }
 };
 
-// scene profile like the library's (ttrl_kern.cu configure): 2 = several controlled vehicles, 0 = general single-agent
+// scene profile like the library's (ttrl_kern.cu configure): 3 = LinearVehicle traffic, 2 = several controlled vehicles, 0 = general single-agent
 // (the "plain" profile 1 only removes code paths that plain scenes never take)
 #define DISPATCH_V(vcap, ...)                                        \
     do {                                                             \
@@ -92,7 +92,8 @@ struct HostEnv {
     } while (0)
 #define DISPATCH(vcap, ...)                                                                    \
     do {                                                                                       \
-        if (sc->cfg.controlled_vehicles > 1) { constexpr int P = 2; DISPATCH_V(vcap, __VA_ARGS__); } \
+        if (sc->cfg.vehicle_model == TTRL_VEHICLE_LINEAR) { constexpr int P = 3; DISPATCH_V(vcap, __VA_ARGS__); } \
+        else if (sc->cfg.controlled_vehicles > 1) { constexpr int P = 2; DISPATCH_V(vcap, __VA_ARGS__); } \
         else { constexpr int P = 0; DISPATCH_V(vcap, __VA_ARGS__); }                           \
     } while (0)
 

@@ -48,7 +48,7 @@ struct alignas(16) d2 { double x, y; };  // 16-byte pair (one LDS.128 on the dev
 // Read-only scene description, resident in global memory (L1/L2 hot: ~12 KB).
 struct SceneDev {
     ttrl_config cfg;
-    ttrl_lane lanes[TTRL_MAX_LANES];
+    alignas(16) ttrl_lane lanes[TTRL_MAX_LANES];  // copied to shared memory with 16-byte vector loads (make_ctx)
     ttrl_road roads[TTRL_MAX_ROADS];
     int32_t node_first[TTRL_MAX_NODES + 1];
     int32_t node_roads[TTRL_MAX_ROADS];
@@ -103,11 +103,15 @@ struct alignas(16) EnvState {
 // is bound by instruction-cache miss traffic, so code that is never executed should not sit between code that is.
 // P_ = 2 ("multi"): the number of controlled vehicles is read from the config at run time (MultiAgentIntersectionEnv); the
 // single-agent profiles 0 / 1 compile the per-agent loops and lookups out for the same reason.
+// P_ = 3 ("linear"): general single-agent scenes whose traffic is LinearVehicle -- its controllers are compiled into this
+// profile only, for the same reason.  P_ = 4 ("any"): everything decided at run time (several agents, linear traffic if
+// c.lin is set): the single-team utility kernels (k_substep, k_observe, k_spawn, k_reset), which are not performance critical.
 template <int V_, int P_ = 0>
 struct EnvCtx {
     static constexpr int V = V_;
+    static constexpr int P = P_;
     static constexpr bool kPlain = P_ == 1;
-    static constexpr bool kMulti = P_ == 2;
+    static constexpr bool kMulti = P_ == 2 || P_ == 4;
     static constexpr int W = (V_ + 31) / 32;  // mask words per lane
     EnvState<V_>* st;
     const SceneDev* sc;
@@ -126,6 +130,9 @@ struct EnvCtx {
     double gap_den;          // 2 sqrt(-COMFORT_ACC_MAX COMFORT_ACC_MIN) (behavior.py:214-216)
     double tan_max_steer;    // tan(MAX_STEERING_ANGLE)
 };
+
+// LinearVehicle traffic in this env? (compile-time for the step profiles, run-time for the "any" profile)
+template <class C> TT_HD bool is_linear(const C& c) { return C::P == 3 || (C::P == 4 && c.lin != nullptr); }
 
 // ------------------------------------------------------------------------------------------------
 // scalar helpers: ttrl_env/utils.py
@@ -471,7 +478,7 @@ TT_STEER double steering_control(C& c, int i, int target_lane, double& tan_steer
     const double speed = c.st->v[i];
     double lane_next = sr.x + speed * TAU_PURSUIT;
     double lane_future_heading = lane_heading_at_c<C>(tl, lane_next);
-    if (!C::kPlain && c.lin && !(c.st->flags[i] & TTRL_FL_MDP)) {
+    if (is_linear(c) && !(c.st->flags[i] & TTRL_FL_MDP)) {
         // LinearVehicle.steering_control / steering_features (behavior.py:466-500): linear in STEERING_PARAMETERS; clipped to
         // +-MAX_STEERING_ANGLE by IDMVehicle.act (behavior.py:114-116)
         const double f0 = wrap_to_pi(lane_future_heading - c.st->h[i]) * kVehLength / not_zero(speed);
@@ -597,7 +604,7 @@ TT_IDM double idm_acceleration(C& c, int self, int ego, int front) {
     const ttrl_config& cfg = c.sc->cfg;
     auto* st = c.st;
     const int le = st->lane[ego];
-    if (!C::kPlain && c.lin) {
+    if (is_linear(c)) {
         // acceleration_features: vt = target_speed - speed, dv = min(front.speed - speed, 0), dp = min(d - d_safe, 0) with
         // d_safe = DISTANCE_WANTED + max(speed, 0) TIME_WANTED; np.dot(ACCELERATION_PARAMETERS, [vt, dv, dp])
         const double vt = st->tspeed[ego] - st->v[ego];
@@ -1601,7 +1608,7 @@ TT_HD void slot_read(C& c, int t, SlotRegs& r) {
     r.d[11] = st->imp[t].x; r.d[12] = st->imp[t].y;
     r.i[0] = st->lane[t]; r.i[1] = st->tlane[t]; r.i[2] = st->flags[t]; r.i[3] = st->sidx[t]; r.i[4] = st->rlen[t]; r.i[5] = st->ytimer[t];
     r.rt = route_of(st, t);
-    if (!C::kPlain && c.lin) for (int k = 0; k < TTRL_NLIN; ++k) r.lin[k] = c.lin[k * C::V + t];
+    if (is_linear(c)) for (int k = 0; k < TTRL_NLIN; ++k) r.lin[k] = c.lin[k * C::V + t];
 }
 template <class C>
 TT_HD void slot_write(C& c, int t, const SlotRegs& r) {
@@ -1611,7 +1618,7 @@ TT_HD void slot_write(C& c, int t, const SlotRegs& r) {
     st->imp[t] = d2{r.d[11], r.d[12]};
     st->lane[t] = r.i[0]; st->tlane[t] = r.i[1]; st->flags[t] = r.i[2]; st->sidx[t] = r.i[3]; st->rlen[t] = r.i[4]; st->ytimer[t] = r.i[5];
     route_store(st, t, r.rt);
-    if (!C::kPlain && c.lin) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = r.lin[k];
+    if (is_linear(c)) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = r.lin[k];
 }
 
 // slots of the controlled vehicles from their agent bits (after a compaction / reset of a multi-agent env)
@@ -1718,8 +1725,8 @@ TT_HD void spawn_vehicle(C& c, Exec& ex, const ttrl_spawn_draw& d, const SpawnPa
         st->tspeed[s] = speed;                       // controller.py:47
         st->timer[s] = py_mod1((px + py) * kPi);     // behavior.py:64
         st->delta[s] = d.delta;                      // IDMVehicle.randomize_behavior behavior.py:66-69
-        if (!C::kPlain && c.lin) st->delta[s] = 4.0; // LinearVehicle.randomize_behavior (behavior.py:402-410) leaves the class DELTA
-        if (!C::kPlain && c.lin)
+        if (is_linear(c)) st->delta[s] = 4.0; // LinearVehicle.randomize_behavior (behavior.py:402-410) leaves the class DELTA
+        if (is_linear(c))
             for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + s] = sc->cfg.lin_lo[k] + d.lin_u[k] * (sc->cfg.lin_hi[k] - sc->cfg.lin_lo[k]);
         st->flags[s] = 0; st->sidx[s] = 0; st->ytimer[s] = 0;
         st->rlen[s] = planned_route(c, ln, entry, exit_, s);
@@ -1786,7 +1793,7 @@ TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
             st->rroad[1][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_ROAD1 * fs + o]); st->rlanew[1][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_LANE1 * fs + o]);
             st->rroad[2][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_ROAD2 * fs + o]); st->rlanew[2][t] = (uint32_t)gload<CG>(&g.vi[TTRL_I_ROUTE_LANE2 * fs + o]);
             st->ytimer[t] = gload<CG>(&g.vi[TTRL_I_YIELD_TIMER * fs + o]);
-            if (!C::kPlain && c.lin) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = g.lin ? gload<CG>(&g.lin[k * fs + o]) : c.sc->cfg.lin_default[k];
+            if (is_linear(c)) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = g.lin ? gload<CG>(&g.lin[k * fs + o]) : c.sc->cfg.lin_default[k];
             if (C::kMulti && t < st_n && (st->flags[t] & TTRL_FL_CONTROLLED) && (st->flags[t] & TTRL_FL_AGENT_MASK))
                 st->egos[(st->flags[t] & TTRL_FL_AGENT_MASK) >> TTRL_FL_AGENT_SHIFT] = t;  // agents k >= 1 (distinct slots: no race)
         } else {
@@ -1795,7 +1802,7 @@ TT_HD void load_env(C& c, Exec& ex, const GlobalState& g, int e) {
             st->tspeed[t] = st->timer[t] = st->delta[t] = 0;
             st->lane[t] = st->tlane[t] = st->flags[t] = st->sidx[t] = st->rlen[t] = st->ytimer[t] = 0;
             for (int w = 0; w < TTRL_ROUTE_WORDS; ++w) st->rroad[w][t] = st->rlanew[w][t] = 0;
-            if (!C::kPlain && c.lin) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = 0;
+            if (is_linear(c)) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = 0;
         }
         st->mark[t] = 0; st->tl_old[t] = 0; st->acc2[t] = 0; st->tsteer[t] = 0; st->best[t] = -1; st->fo[t] = -1;
         // pre-check guard from the loaded speed (integrate refreshes it every sub-step)
@@ -1845,7 +1852,7 @@ TT_HD void store_env(C& c, Exec& ex, const GlobalState& g, int e) {
         g.vi[TTRL_I_ROUTE_ROAD2 * fs + o] = (int32_t)(st->rroad[2][t] & keep2);
         g.vi[TTRL_I_ROUTE_LANE2 * fs + o] = (int32_t)(st->rlanew[2][t] & keep2);
         g.vi[TTRL_I_YIELD_TIMER * fs + o] = live ? st->ytimer[t] : 0;
-        if (!C::kPlain && c.lin && g.lin) for (int k = 0; k < TTRL_NLIN; ++k) g.lin[k * fs + o] = live ? c.lin[k * C::V + t] : 0;
+        if (is_linear(c) && g.lin) for (int k = 0; k < TTRL_NLIN; ++k) g.lin[k * fs + o] = live ? c.lin[k * C::V + t] : 0;
     });
 }
 
@@ -1910,7 +1917,7 @@ TT_HD void reset_scalars(C& c, Exec& ex, int episode) {
         st->lane[t] = st->tlane[t] = st->flags[t] = st->sidx[t] = st->rlen[t] = st->ytimer[t] = 0;
         for (int w = 0; w < TTRL_ROUTE_WORDS; ++w) st->rroad[w][t] = st->rlanew[w][t] = 0;
         st->mark[t] = 0; st->tl_old[t] = 0; st->best[t] = -1; st->fo[t] = -1;
-        if (!C::kPlain && c.lin) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = 0;
+        if (is_linear(c)) for (int k = 0; k < TTRL_NLIN; ++k) c.lin[k * C::V + t] = 0;
     });
     ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; });
 }
@@ -2096,8 +2103,8 @@ TT_HD void reset_cast(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) 
             st->delta[s] = 4.0;
         } else {
             st->timer[s] = py_mod1((px + py) * kPi);                          // behavior.py:64
-            st->delta[s] = (m.randomize && !c.lin) ? 3.5 + ue * (4.5 - 3.5) : 4.0;   // behavior.py:66-69
-            if (c.lin) {                                                      // LinearVehicle: class defaults or randomize_behavior
+            st->delta[s] = (m.randomize && !is_linear(c)) ? 3.5 + ue * (4.5 - 3.5) : 4.0;   // behavior.py:66-69
+            if (is_linear(c)) {                                               // LinearVehicle: class defaults or randomize_behavior
                 double lu[6];
                 reset_uniforms(seed, genv, episode, 0x300u + 4u * s, lu[0], lu[1]);
                 reset_uniforms(seed, genv, episode, 0x301u + 4u * s, lu[2], lu[3]);

@@ -164,6 +164,7 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V, P>& c, unsigned char* smem_ct
     c.lanes = lanes_s;
     c.SR = reinterpret_cast<d2*>(smem + lay.off_SR);
     c.NC = P == 1 ? sc->cfg.n_lanes : sc->n_curved;
+    static_assert(P >= 0 && P <= 4, "scene profile");
     c.lmask = reinterpret_cast<uint32_t*>(smem + lay.off_lmask);
     c.pred = lay.off_pred >= 0 ? reinterpret_cast<double*>(smem + lay.off_pred) : nullptr;
     c.pbits = lay.off_pred >= 0 ? reinterpret_cast<uint32_t*>(smem + lay.off_pred + sizeof(double) * 4 * V) : nullptr;
@@ -180,8 +181,8 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V, P>& c, unsigned char* smem_ct
 #define TT_KERNEL_PROLOGUE                                     \
     extern __shared__ __align__(16) unsigned char smem[];      \
     constexpr int T = TeamOf<V>::T;                            \
-    EnvCtx<V, 2> c;                                            \
-    make_ctx<V, 2>(c, smem, 0, sc, lay, g.V);                  \
+    EnvCtx<V, 4> c;                                            \
+    make_ctx<V, 4>(c, smem, 0, sc, lay, g.V);                  \
     DevExec<V, T> ex((int)threadIdx.x, 1);
 
 template <int V, int P>
@@ -354,6 +355,9 @@ k_regen_list(const SceneDev* __restrict__ sc, StepIO io, SmemLayout lay) {
 // ------------------------------------------------------------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// the LinearVehicle profile is instantiated for the small capacities only (its scenes: roundabout, intersection)
+template <int V> constexpr bool kHasLinearProfile = V <= 32;
+
 template <int V>
 static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, SmemLayout* out) {
     SmemLayout l{};
@@ -385,6 +389,12 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
     if ((e = cudaFuncSetAttribute(k_step<V, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_step<V, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_step<V, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
+    if constexpr (kHasLinearProfile<V>) {
+        if ((e = cudaFuncSetAttribute(k_step<V, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
+        if ((e = cudaFuncSetAttribute(k_reset_list<V, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
+        if ((e = cudaFuncSetAttribute(k_regen_list<V, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total_step)) != cudaSuccess) return (int)e;
+        cudaFuncSetAttribute(k_step<V, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
     if ((e = cudaFuncSetAttribute(k_substep<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_observe<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(k_spawn<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total)) != cudaSuccess) return (int)e;
@@ -402,6 +412,10 @@ static int configure(const ttrl_config& cfg, const ttrl_lane* lanes, int vcap, S
                  cfg.obs_type != TTRL_OBS_TTC;
     for (int k = 0; k < cfg.n_lanes; ++k) plain = plain && lanes[k].kind == TTRL_LANE_STRAIGHT;
     out->plain = plain ? 1 : (cfg.controlled_vehicles > 1 ? 2 : 0);  // scene profile: 0 general single-agent, 1 plain, 2 multi-agent
+    if (cfg.vehicle_model == TTRL_VEHICLE_LINEAR) {  // 3: general single-agent with LinearVehicle traffic (capacities <= 32)
+        if (cfg.controlled_vehicles > 1 || !kHasLinearProfile<V>) return (int)cudaErrorNotSupported;
+        out->plain = 3;
+    }
     int dev = 0, n_sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
     out->n_sms = n_sms > 0 ? n_sms : 148;
@@ -412,7 +426,8 @@ static void launch_step(int E, const SmemLayout& lay, cudaStream_t st, const Sce
     const int G = lay.G;
     // binned launch: every bin may leave one partly filled CTA; CTAs beyond the bins' envs exit at once
     const int nb = (E + G - 1) / G + (io.cls_list ? io.cls_n : 0);
-    if (lay.plain == 1) k_step<V, 1><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    if (lay.plain == 3) { if constexpr (kHasLinearProfile<V>) k_step<V, 3><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay); }
+    else if (lay.plain == 1) k_step<V, 1><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
     else if (lay.plain == 2) k_step<V, 2><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
     else k_step<V, 0><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
 }
@@ -422,7 +437,8 @@ static void launch_reset_list(int E, const SmemLayout& lay, cudaStream_t st, con
     const int G = lay.G;
     // one CTA per SM (fewer for tiny batches); CTAs beyond the number of finished envs exit at once
     const int nb_reset = (E + G - 1) / G < lay.n_sms ? (E + G - 1) / G : lay.n_sms;
-    if (io.done_list && lay.plain == 2) k_reset_list<V, 2><<<nb_reset, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
+    if (io.done_list && lay.plain == 3) { if constexpr (kHasLinearProfile<V>) k_reset_list<V, 3><<<nb_reset, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay); }
+    else if (io.done_list && lay.plain == 2) k_reset_list<V, 2><<<nb_reset, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
     else if (io.done_list) k_reset_list<V, 0><<<nb_reset, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
 }
 // the regeneration of the episodes queued by the last step, on the side stream
@@ -435,7 +451,8 @@ static void launch_regen(int E, const SmemLayout& lay, cudaStream_t st, const Sc
     static const int div = [] { const char* v = getenv("TTRL_REGEN_SM_DIV"); const int d = v ? atoi(v) : 1; return d > 0 ? d : 1; }();  // tuning experiments
     const int cap = lay.n_sms / div > 0 ? lay.n_sms / div : 1;
     const int nb = (E + G - 1) / G < cap ? (E + G - 1) / G : cap;
-    if (lay.plain == 2) k_regen_list<V, 2><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay);
+    if (lay.plain == 3) { if constexpr (kHasLinearProfile<V>) k_regen_list<V, 3><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay); }
+    else if (lay.plain == 2) k_regen_list<V, 2><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay);
     else k_regen_list<V, 0><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay);
 }
 template <int V>
