@@ -19,7 +19,7 @@ struct HostExec {
     bool first() const { return true; }  // single-thread sections run once
     void sync() {}
     void align() {}
-    void align2() {}
+    template <int K> void align_at() {}
     template <class F> void par(F f) { for (int t = 0; t < T; ++t) f(t); }
     template <class F> void parn(int n, F f) { for (int t = 0; t < n; ++t) f(t); }
     template <class F> bool any(int n, F f) { bool r = false; for (int t = 0; t < n; ++t) r = f(t) || r; return r; }

@@ -1148,10 +1148,11 @@ TT_HD void regulate_apply(C& c, int i) {
 // ------------------------------------------------------------------------------------------------
 // one simulation sub-step (AbstractEnv._simulate body abstract.py:257-273)
 // ------------------------------------------------------------------------------------------------
-// In two parts -- Road.act (+ regulation), then Road.step -- so that a multi-env CTA can place an alignment barrier between
-// them as well (k_step); env_substep is the two back to back.
+// In four parts -- lane decisions (follow_road, meta-action, MOBIL, abort rule), controls (steering, IDM, regulation), integration
+// (+ closest lane), collisions -- so that a multi-env CTA can place alignment barriers between them (k_step: Exec::align_at<k>);
+// env_substep is the four back to back.
 template <class C, class Exec>
-TT_HD void substep_act(C& c, Exec& ex, const int32_t* actions) {  // inlined on purpose: a call boundary here costs ~30 % (ctx spills)
+TT_HD void substep_lanes(C& c, Exec& ex, const int32_t* actions) {  // inlined on purpose: a call boundary here costs ~30 % (ctx spills)
     // `actions`: this env's raw action ids (one per controlled vehicle) or null (action=None)
     auto* st = c.st;
     const SceneDev* sc = c.sc;
@@ -1183,6 +1184,12 @@ TT_HD void substep_act(C& c, Exec& ex, const int32_t* actions) {  // inlined on 
             }
         }
     }
+}
+template <class C, class Exec>
+TT_HD void substep_controls(C& c, Exec& ex) {
+    auto* st = c.st;
+    const SceneDev* sc = c.sc;
+    const int n = st->n;
     ex.parn(n, [&](int t) {
         if (t == 0) { st->n_mob = 0; for (int w = 0; w < C::W; ++w) st->bmask[w] = 0; }
         act_phase_c1(c, ex, t);
@@ -1214,20 +1221,37 @@ TT_HD void substep_act(C& c, Exec& ex, const int32_t* actions) {  // inlined on 
     }
 }
 template <class C, class Exec>
-TT_HD void substep_move(C& c, Exec& ex) {
-    auto* st = c.st;
-    const SceneDev* sc = c.sc;
-    const int n = st->n;
+TT_HD void substep_integrate(C& c, Exec& ex) {
+    const int n = c.st->n;
     ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; });
     ex.parn(n, [&](int t) { integrate(c, ex, t); });
+}
+template <class C, class Exec>
+TT_HD void substep_collide(C& c, Exec& ex) {
+    auto* st = c.st;
     collide_all(c, ex);
-    if (ex.first()) { st->steps += 1; if (!C::kPlain && sc->cfg.regulated) st->road_steps += 1; }
+    if (ex.first()) { st->steps += 1; if (!C::kPlain && c.sc->cfg.regulated) st->road_steps += 1; }
     ex.sync();
 }
 template <class C, class Exec>
 TT_HD void env_substep(C& c, Exec& ex, const int32_t* actions) {
-    substep_act(c, ex, actions);
-    substep_move(c, ex);
+    substep_lanes(c, ex, actions);
+    substep_controls(c, ex);
+    substep_integrate(c, ex);
+    substep_collide(c, ex);
+}
+// the same for the teams of a multi-env CTA (`active`: this team has an env): every alignment barrier is ONE instruction
+// that active and idle teams reach alike (see env_reset_lockstep)
+template <class C, class Exec>
+TT_HD void env_substep_lockstep(C& c, Exec& ex, bool active, const int32_t* actions) {
+    ex.template align_at<0>();
+    if (active) substep_lanes(c, ex, actions);
+    ex.template align_at<1>();
+    if (active) substep_controls(c, ex);
+    ex.template align_at<2>();
+    if (active) substep_integrate(c, ex);
+    ex.template align_at<3>();
+    if (active) substep_collide(c, ex);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2159,12 +2183,7 @@ TT_HD void env_reset_lockstep(C& c, Exec& ex, bool active, uint64_t seed, int64_
     }
     if (active) reset_intersection_begin(c, ex, seed, genv, episode);
     const int warmup = c.sc->rp.warmup_substeps;
-    for (int k = 0; k < warmup; ++k) {
-        ex.align();
-        if (active) substep_act(c, ex, nullptr);
-        ex.align2();
-        if (active) substep_move(c, ex);
-    }
+    for (int k = 0; k < warmup; ++k) env_substep_lockstep(c, ex, active, nullptr);
     if (active) reset_intersection_end(c, ex, seed, genv, episode);
 }
 
@@ -2209,6 +2228,10 @@ struct StepIO {
     const int32_t* cls_list;
     const int32_t* cls_count;
     int cls_first, cls_n;
+    // a plain (not binned) launch may cover a sub-range of the envs: env_first .. env_first + env_count - 1 (env_count 0: all).
+    // The host-buffer step of scenes with large observations runs the batch as a few such slices on two streams, so that the
+    // device-to-host copy of one slice's observations overlaps the kernel of the next (ttrl_sim_step_pinned).
+    int env_first, env_count;
 };
 constexpr int kClsPhases = 8;              // regulation phase bins per size class
 constexpr int kClsBins = 2 * kClsPhases;   // size class 0 (small) bins 0..7, class 1 (large) bins 8..15

@@ -23,8 +23,10 @@ using namespace ttrl;
 //    vehicles per env, long scalar phases) aligned multi-env CTAs are 23 % faster, for 2-warp and larger teams the
 //    barrier skew costs more than the fetch sharing saves (profiles/r1c_variants.txt).
 // ------------------------------------------------------------------------------------------------
-#ifndef TT_ALIGN_POINTS
-#define TT_ALIGN_POINTS 1   /* CTA-wide alignment points per sub-step: 1 = at its start, 2 = also between Road.act and Road.step */
+// CTA-wide alignment points per sub-step of the multi-env CTAs (bit k = point k of Exec::align_at).  Measured on B200
+// (profiles/r2_alignment.txt): start only 1.88 ms/step (intersection, 8192 envs), start + before the integration 1.67 - 1.78, start + before the controls + before the integration 1.68 - 1.70, all four 1.76.
+#ifndef TT_ALIGN_MASK
+#define TT_ALIGN_MASK 0x7
 #endif
 template <int V, int T>
 struct DevExec {
@@ -47,10 +49,9 @@ struct DevExec {
 #endif
         if (T <= 32 && G > 1) __syncthreads();
     }
-    __device__ __forceinline__ void align2() {
-#if TT_ALIGN_POINTS >= 2
-        align();
-#endif
+    // alignment point k of a sub-step (0 its start, 1 before the controls, 2 before the integration, 3 before the collisions)
+    template <int K> __device__ __forceinline__ void align_at() {
+        if ((TT_ALIGN_MASK >> K) & 1) align();
     }
     template <class F> __device__ __forceinline__ void par(F f) {
 #pragma unroll 1
@@ -194,7 +195,8 @@ k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay
     const int team = threadIdx.x / T;
     EnvCtx<V, P> c;
     DevExec<V, T> ex((int)threadIdx.x % T, G);
-    int e = (int)blockIdx.x * G + team;
+    int e = io.env_first + (int)blockIdx.x * G + team;
+    if (io.env_count > 0 && e >= io.env_first + io.env_count) e = g.E;  // past the slice of this launch
     if (io.cls_list) {  // binned launch: this CTA takes G envs of one bin
         int cta = (int)blockIdx.x, b = io.cls_first, cnt = 0;
         for (; b < io.cls_first + io.cls_n; ++b) {
@@ -222,16 +224,8 @@ k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay
     const int F = sc->F;
 #pragma unroll 1
     for (int f = 0; f < F; ++f) {
-#if defined(TT_ALIGN_EVERY)
-        if (f % TT_ALIGN_EVERY == 0)   // experiment: let the teams drift for TT_ALIGN_EVERY - 1 sub-steps
-#endif
-        ex.align();
-        if (active) substep_act(c, ex, actions);
-        ex.align2();  // second alignment point, between Road.act and Road.step (TT_ALIGN_POINTS)
-        if (active) {
-            substep_move(c, ex);
-            veh_steps += c.st->n;
-        }
+        env_substep_lockstep(c, ex, active, actions);
+        if (active) veh_steps += c.st->n;
     }
     if (active) env_step_finish(c, ex, g, io, e, veh_steps);
 }
@@ -425,7 +419,8 @@ template <int V>
 static void launch_step(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const StepIO& io) {
     const int G = lay.G;
     // binned launch: every bin may leave one partly filled CTA; CTAs beyond the bins' envs exit at once
-    const int nb = (E + G - 1) / G + (io.cls_list ? io.cls_n : 0);
+    const int n_envs = (!io.cls_list && io.env_count > 0) ? io.env_count : E;
+    const int nb = (n_envs + G - 1) / G + (io.cls_list ? io.cls_n : 0);
     if (lay.plain == 3) { if constexpr (kHasLinearProfile<V>) k_step<V, 3><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay); }
     else if (lay.plain == 1) k_step<V, 1><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
     else if (lay.plain == 2) k_step<V, 2><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, g, io, lay);
