@@ -219,3 +219,36 @@ def test_device_highway_reset_properties():
     assert ((d >= 3.5) & (d <= 4.5)).all()
     np.testing.assert_allclose(a.veh_d[abi.D_TIMER][:, 1:], ((x[:, 1:] + y[:, 1:]) * np.pi) % 1.0, atol=1e-9)
     assert len(np.unique(lane[:, 1:])) == 4
+
+
+def test_headless_rasteriser_geometry():
+    """render.render_rgb (env.render() with render_mode="rgb_array"): window centred like EnvViewer.window_position with the
+    config's centering_position / scaling, ego green, IDM traffic blue, crashed red, lane markings white on grey."""
+    from topotrafficrl_b200.render import BLUE, GREEN, GREY, RED, WHITE, render_rgb
+    net, table, cfg, _ = T.intersection_scene()
+    cfgd = scenes.merged_config(scenes.INTERSECTION_CONFIG, None)
+    g = T.golden("intersection_reset.npz")
+    st = T.batch_state(g, "state", slice(0, 1))
+    img = render_rgb(net, st, cfgd)
+    assert img.shape == (600, 600, 3) and img.dtype == np.uint8
+    ego = int(st.env_i[abi.EI_EGO, 0])
+    cx, cy = int(0.5 * 600), int(0.6 * 600)                      # centering_position [0.5, 0.6]: the ego's pixel
+    assert tuple(img[cy, cx]) == GREEN
+    scaling = cfgd["scaling"]
+    n = int(st.env_i[abi.EI_NVEH, 0])
+    seen = 0
+    for s in range(n):
+        if s == ego:
+            continue
+        px = int((st.veh_d[abi.D_X, 0, s] - st.veh_d[abi.D_X, 0, ego]) * scaling) + cx
+        py = int((st.veh_d[abi.D_Y, 0, s] - st.veh_d[abi.D_Y, 0, ego]) * scaling) + cy
+        if 5 < px < 595 and 5 < py < 595:
+            assert tuple(img[py, px]) == BLUE, (s, px, py, img[py, px])
+            seen += 1
+    assert seen >= 2
+    assert (img == np.array(WHITE, np.uint8)).all(axis=2).sum() > 500 and (img == np.array(GREY, np.uint8)).all(axis=2).mean() > 0.5
+    st.veh_i[abi.I_FLAGS, 0, ego] |= abi.FL_CRASHED
+    assert tuple(render_rgb(net, st, cfgd)[cy, cx]) == RED
+    # the continuous right-hand line of the ego's incoming lane (o0 -> ir0: x = 2 +- 2 m): a white column right of the ego
+    col = int((4.0 - st.veh_d[abi.D_X, 0, ego]) * scaling) + cx
+    assert (img[cy - 40:cy + 40, col - 2:col + 3] == np.array(WHITE, np.uint8)).all(axis=2).any(axis=1).mean() > 0.9

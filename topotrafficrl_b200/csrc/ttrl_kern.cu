@@ -34,20 +34,24 @@ struct DevExec {
     int G;          // teams in this CTA (1 unless T <= 32)
     unsigned mask;  // T <= 32: the team's lanes of its warp (a sub-warp team shares the warp with 32 / T - 1 other envs)
     int lane;       // lane within the warp
+    int team;       // team within the CTA (teams of several warps in a multi-env CTA meet at named barrier 1 + team)
     __device__ __forceinline__ DevExec(int tid_, int G_) : tid(tid_), G(G_) {
+        team = (int)threadIdx.x / T;
         lane = (int)(threadIdx.x & 31u);
         mask = T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (lane & ~(T - 1)));
     }
     __device__ __forceinline__ bool first() const { return tid == 0; }
     __device__ __forceinline__ void sync() {
-        if (T <= 32) __syncwarp(mask); else __syncthreads();
+        if (T <= 32) __syncwarp(mask);
+        else if (G > 1) asm volatile("bar.sync %0, %1;" :: "r"(1 + team), "r"(T) : "memory");  // this team's warps only
+        else __syncthreads();
     }
     // CTA-wide phase alignment; every team of the CTA calls it the same number of times
     __device__ __forceinline__ void align() {
 #if defined(TT_NO_ALIGN)
         return;  // experiment: free-running teams
 #endif
-        if (T <= 32 && G > 1) __syncthreads();
+        if (G > 1) __syncthreads();
     }
     // alignment point k of a sub-step (0 its start, 1 before the controls, 2 before the integration, 3 before the collisions)
     template <int K> __device__ __forceinline__ void align_at() {
@@ -68,6 +72,12 @@ struct DevExec {
 #pragma unroll 1
         for (int t = tid; t < n; t += T) p |= f(t) ? 1 : 0;
         if (T <= 32) return __ballot_sync(mask, p) != 0;
+        if (G > 1) {  // OR-reduction over this team's warps at its named barrier
+            int r;
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %3, 0;\n\tbar.red.or.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(r) : "r"(1 + team), "r"(T), "r"(p) : "memory");
+            return r != 0;
+        }
         return __syncthreads_or(p) != 0;
     }
     template <class F1, class F2> __device__ __forceinline__ void par2(F1 f1, F2 f2) {
@@ -144,7 +154,7 @@ struct DevExec {
 #endif
 template <int V> struct TeamOf {
     static constexpr int T = TT_T, MINB = TT_MINB, G = TT_G;
-    static_assert(G == 1 || T <= 32, "several envs per CTA need teams of at most one warp");
+    static_assert(G == 1 || T <= 32 || G <= 15, "multi-warp teams of a multi-env CTA use named barriers 1..15");
 };
 
 template <int V, int P>

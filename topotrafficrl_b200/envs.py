@@ -170,7 +170,14 @@ class AbstractEnv(Env):
         return self._format_obs(obs, perms), float(reward[0]), bool(term[0]), bool(trunc[0]), info
 
     def render(self):
-        raise NotImplementedError("rendering (pygame) is outside the B200 hot path (SURVEY.md section 2 row 20)")
+        """``AbstractEnv.render`` (abstract.py:275-303) for ``render_mode="rgb_array"``: a headless numpy redraw of the reference's
+        picture (``render.py``); there is no window for ``"human"`` (pygame is not a dependency and the GPU box has no display)."""
+        if self.render_mode is None:
+            return None
+        if self.render_mode != "rgb_array":
+            raise NotImplementedError("render_mode 'human' needs pygame and a display: use render_mode='rgb_array'")
+        from .render import render_rgb
+        return render_rgb(self.net, self.sim.get_state(), self.config, 0, linear_traffic=self.cfg.vehicle_model == abi.VEHICLE_LINEAR)
 
     def close(self) -> None:
         self.done = True
