@@ -28,14 +28,15 @@ using namespace ttrl;
 #ifndef TT_ALIGN_MASK
 #define TT_ALIGN_MASK 0x7
 #endif
-template <int V, int T>
+// MULTI: the CTA holds several teams (compile-time, so that single-env CTAs carry none of the multi-team paths)
+template <int V, int T, bool MULTI>
 struct DevExec {
     int tid;        // thread within the team
     int G;          // teams in this CTA (1 unless T <= 32)
     unsigned mask;  // T <= 32: the team's lanes of its warp (a sub-warp team shares the warp with 32 / T - 1 other envs)
     int lane;       // lane within the warp
     int team;       // team within the CTA (teams of several warps in a multi-env CTA meet at named barrier 1 + team)
-    __device__ __forceinline__ DevExec(int tid_, int G_) : tid(tid_), G(G_) {
+    __device__ __forceinline__ DevExec(int tid_, int G_) : tid(tid_), G(MULTI ? G_ : 1) {
         team = (int)threadIdx.x / T;
         lane = (int)(threadIdx.x & 31u);
         mask = T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (lane & ~(T - 1)));
@@ -43,7 +44,7 @@ struct DevExec {
     __device__ __forceinline__ bool first() const { return tid == 0; }
     __device__ __forceinline__ void sync() {
         if (T <= 32) __syncwarp(mask);
-        else if (G > 1) asm volatile("bar.sync %0, %1;" :: "r"(1 + team), "r"(T) : "memory");  // this team's warps only
+        else if (MULTI) asm volatile("bar.sync %0, %1;" :: "r"(1 + team), "r"(T) : "memory");  // this team's warps only
         else __syncthreads();
     }
     // CTA-wide phase alignment; every team of the CTA calls it the same number of times
@@ -51,7 +52,7 @@ struct DevExec {
 #if defined(TT_NO_ALIGN)
         return;  // experiment: free-running teams
 #endif
-        if (G > 1) __syncthreads();
+        if (MULTI && G > 1) __syncthreads();
     }
     // alignment point k of a sub-step (0 its start, 1 before the controls, 2 before the integration, 3 before the collisions)
     template <int K> __device__ __forceinline__ void align_at() {
@@ -72,7 +73,7 @@ struct DevExec {
 #pragma unroll 1
         for (int t = tid; t < n; t += T) p |= f(t) ? 1 : 0;
         if (T <= 32) return __ballot_sync(mask, p) != 0;
-        if (G > 1) {  // OR-reduction over this team's warps at its named barrier
+        if (MULTI) {  // OR-reduction over this team's warps at its named barrier
             int r;
             asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %3, 0;\n\tbar.red.or.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                          : "=r"(r) : "r"(1 + team), "r"(T), "r"(p) : "memory");
@@ -194,7 +195,7 @@ __device__ __forceinline__ void make_ctx(EnvCtx<V, P>& c, unsigned char* smem_ct
     constexpr int T = TeamOf<V>::T;                            \
     EnvCtx<V, 4> c;                                            \
     make_ctx<V, 4>(c, smem, 0, sc, lay, g.V);                  \
-    DevExec<V, T> ex((int)threadIdx.x, 1);
+    DevExec<V, T, false> ex((int)threadIdx.x, 1);
 
 template <int V, int P>
 __global__ void __launch_bounds__(TeamOf<V>::T * TeamOf<V>::G, TeamOf<V>::G > 1 ? 1 : TeamOf<V>::MINB)
@@ -204,7 +205,7 @@ k_step(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayout lay
     const int G = (int)blockDim.x / T;
     const int team = threadIdx.x / T;
     EnvCtx<V, P> c;
-    DevExec<V, T> ex((int)threadIdx.x % T, G);
+    DevExec<V, T, (TeamOf<V>::G > 1)> ex((int)threadIdx.x % T, G);
     int e = io.env_first + (int)blockIdx.x * G + team;
     if (io.env_count > 0 && e >= io.env_first + io.env_count) e = g.E;  // past the slice of this launch
     if (io.cls_list) {  // binned launch: this CTA takes G envs of one bin
@@ -302,7 +303,7 @@ k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayo
     if (b >= n_done) return;  // uniform per CTA
     EnvCtx<V, P> c;
     make_ctx<V, P>(c, smem, team, sc, lay, g.V);
-    DevExec<V, T> ex((int)threadIdx.x % T, G);
+    DevExec<V, T, (TeamOf<V>::G > 1)> ex((int)threadIdx.x % T, G);
     // The finished envs are dealt ROUND-ROBIN over the CTAs (one CTA per SM), team by team: a typical step finishes ~1/13 of
     // the envs, and a few teams on every SM run faster than 14 teams on a third of the SMs (a team's speed is set by
     // dependency latency and by its share of the SM's instruction fetch).  With more finished envs than teams the CTA
@@ -338,7 +339,7 @@ k_regen_list(const SceneDev* __restrict__ sc, StepIO io, SmemLayout lay) {
     if (b >= n_regen) return;  // uniform per CTA
     EnvCtx<V, P> c;
     make_ctx<V, P>(c, smem, team, sc, lay, io.shadow.V);
-    DevExec<V, T> ex((int)threadIdx.x % T, G);
+    DevExec<V, T, (TeamOf<V>::G > 1)> ex((int)threadIdx.x % T, G);
     const int passes = (n_regen + G * nb - 1) / (G * nb);
     for (int pass = 0; pass < passes; ++pass) {
         const int k = (pass * G + team) * nb + b;
