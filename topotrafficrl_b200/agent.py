@@ -158,9 +158,9 @@ class QNetRollout:
         self.training = True
 
     def set_mode(self, mode: str) -> None:
-        """``"fp32"``: CUDA-core fp32 forward, the parity path (default).  ``"tensor"``: hidden GEMMs on the tcgen05
-        tensor cores (BF16x3 split, FP32 accumulation in TMEM); MultiLayerPerceptron with two hidden layers only --
-        raises :class:`TTRLError` otherwise (no silent fallback)."""
+        """``"fp32"``: CUDA-core fp32 forward, the parity path (default).  ``"tensor"``: the GEMMs on the tcgen05 tensor
+        cores (BF16x3 split, FP32 accumulation in TMEM): MultiLayerPerceptron with two hidden layers and the
+        EgoAttentionNetwork shapes of the shipped configs; any other network raises :class:`TTRLError` (no silent fallback)."""
         if mode not in self.MODES:
             raise ValueError(f"unknown mode {mode!r}")
         check(self._L.ttrl_qnet_set_mode(self._h, self.MODES[mode]))

@@ -25,8 +25,10 @@ using namespace ttrl;
 // ------------------------------------------------------------------------------------------------
 // CTA-wide alignment points per sub-step of the multi-env CTAs (bit k = point k of Exec::align_at).  Measured on B200
 // (profiles/r2_alignment.txt): start only 1.88 ms/step (intersection, 8192 envs), start + before the integration 1.67 - 1.78, start + before the controls + before the integration 1.68 - 1.70, all four 1.76.
+// Two-warp highway teams (10 per CTA, named team barriers): the start-of-sub-step point only -- 1.048 ms/step against 1.14 with
+// none (0x0) or two (0x5), 1.16 with three, and 1.175 for one env per CTA (profiles/r2_step_scheduling.txt item 12).
 #ifndef TT_ALIGN_MASK
-#define TT_ALIGN_MASK 0x7
+#define TT_ALIGN_MASK (TT_V <= 32 ? 0x7 : 0x1)
 #endif
 // MULTI: the CTA holds several teams (compile-time, so that single-env CTAs carry none of the multi-team paths)
 template <int V, int T, bool MULTI>
@@ -151,7 +153,9 @@ struct DevExec {
 #endif
 // envs per CTA of k_step (1 = one env per CTA, no phase alignment)
 #ifndef TT_G
-#define TT_G (TT_V <= 32 ? 512 / TT_T : 1)   /* upper bound (512 threads); the launch uses as many as fit in shared memory */
+/* upper bound; the launch uses as many as fit in shared memory.  V <= 32: 512 threads.  V <= 64 (two-warp teams): 10 envs =
+ * 640 threads at ~100 registers, the same 20 warps per SM as one env per CTA had, but fetching in step (G = 8: 1.22, 10: 1.05, 12: 1.11 ms) */
+#define TT_G (TT_V <= 32 ? 512 / TT_T : TT_V <= 64 ? 10 : 1)
 #endif
 template <int V> struct TeamOf {
     static constexpr int T = TT_T, MINB = TT_MINB, G = TT_G;
