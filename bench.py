@@ -448,14 +448,14 @@ def measure(args, wname, K, W, with_cpu, self_check_steps=0):
     total_ms = float(sum(ms))
     s = sim.stats(reset=True)  # one reduction kernel, outside the timed region
     veh_steps, env_steps = s.vehicle_steps, s.env_steps
-    capacity_rejects = s.spawn_capacity_rejects
+    capacity_rejects, sync_resets = s.spawn_capacity_rejects, s.sync_resets
     red = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([veh_steps, env_steps, s.episodes, s.crashes, s.total_return, capacity_rejects], dtype=torch.float64, device=dev)
+    tot = torch.tensor([veh_steps, env_steps, s.episodes, s.crashes, s.total_return, capacity_rejects, sync_resets], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)  # episode statistics: the only collective of the workload
     total_ms_max = float(red.item())
-    veh_all, env_all, episodes, crashes, ret, rejects_all = (float(x) for x in tot.tolist())
+    veh_all, env_all, episodes, crashes, ret, rejects_all, sync_resets_all = (float(x) for x in tot.tolist())
 
     # ---- longer self-check of the same arm (the contract's K can be a 20 ms region): not part of `value` -------------
     self_check = None
@@ -521,7 +521,7 @@ def measure(args, wname, K, W, with_cpu, self_check_steps=0):
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks,
             "episode_stats": {"episodes": episodes, "crashes": crashes, "mean_return": ret / episodes if episodes else None,
-                              "spawn_capacity_rejects": rejects_all},
+                              "spawn_capacity_rejects": rejects_all, "sync_resets": sync_resets_all},
             "wall_s_timed_region": t_wall,
         }
         if self_check is not None:

@@ -176,6 +176,9 @@ typedef struct ttrl_episode_stats {
      * capacity): non-zero means the slot capacity `vcap` is too small for the workload and the episodes DIFFER from the
      * reference's from that point on */
     double spawn_capacity_rejects;
+    /* TTRL_AUTORESET_DEVICE_ASYNC: finished envs whose next episode was not ready in the shadow ring and that were reset by
+     * the packed second launch on the step's critical path instead (same episode, only slower) */
+    double sync_resets;
 } ttrl_episode_stats;
 
 /* Device-side reset: fresh episodes generated on the GPU with counter-based (Philox) draws

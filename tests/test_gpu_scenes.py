@@ -277,7 +277,9 @@ def test_async_device_reset_equals_synchronous_device_reset(K):
     np.testing.assert_array_equal(sa.veh_d, sb.veh_d)
     np.testing.assert_array_equal(sa.env_i, sb.env_i)
     s0, s1 = envs[0].stats(), envs[1].stats()
-    assert s0 == s1 and s0["episodes"] > 3 * E
+    # same episodes; the asynchronous mode only resets fewer envs through the packed second launch (the ring was generated at reset)
+    assert {k: v for k, v in s0.items() if k != "sync_resets"} == {k: v for k, v in s1.items() if k != "sync_resets"} and s0["episodes"] > 3 * E
+    assert s0["sync_resets"] < 0.5 * s1["sync_resets"] and s1["sync_resets"] == s1["episodes"]
     assert int(sa.env_i[abi.EI_EPISODE].max()) >= 5
     for env in envs:
         env.close()

@@ -51,7 +51,7 @@ for r in rows:
         name = r[1]
         func = None
         want_v = re.search(r"ILi(\d+)", kern)  # k_stepILi16 -> launches of k_step<(int)16, ...> only
-        if re.sub(r"I?Li\d+.*", "", kern) in name and (not want_v or f"<(int){want_v.group(1)}," in name):
+        if re.sub(r"I?Li\d+.*", "", kern) in name and (not want_v or (f"<(int){want_v.group(1)}," in name or f"<{want_v.group(1)}," in name)):
             cands = [f for f in funcs if kern in f]
             func = cands[0] if cands else None
         k = 0

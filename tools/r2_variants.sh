@@ -15,3 +15,14 @@ except Exception as e:
 PY
 }
 "$@"
+runx() {  # like run, also prints the episode statistics that tell how often the synchronous reset fallback fired
+  tag=$1; run "$@"
+  python - "$tag" <<'PY'
+import json,sys
+try:
+    d=json.load(open(f"gpurun_out/{sys.argv[1]}.json")); s=d["episode_stats"]
+    print(f"    episodes {s['episodes']:.0f}  sync_resets {s.get('sync_resets')}  per step {s.get('sync_resets',0)/d['steps']:.1f}")
+except Exception as e:
+    print("   ", e)
+PY
+}

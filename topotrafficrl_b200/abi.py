@@ -129,7 +129,8 @@ class ResetParams(C.Structure):
 class EpisodeStats(C.Structure):
     _fields_ = [("episodes", C.c_double), ("total_return", C.c_double), ("total_length", C.c_double),
                 ("crashes", C.c_double), ("arrivals", C.c_double), ("total_speed", C.c_double),
-                ("vehicle_steps", C.c_double), ("env_steps", C.c_double), ("spawn_capacity_rejects", C.c_double)]
+                ("vehicle_steps", C.c_double), ("env_steps", C.c_double), ("spawn_capacity_rejects", C.c_double),
+                ("sync_resets", C.c_double)]
 
 
 ABI_VERSION = 2

@@ -42,7 +42,7 @@ constexpr double kPi = 3.141592653589793;
 constexpr int kPred = 11;            // regulation.py:87: np.arange(0.25, 3, 0.25)
 constexpr double kVehLength = 5.0;   // kinematics.py:21
 constexpr double kVehWidth = 2.0;    // kinematics.py:23
-constexpr int kStatFields = 9;       // ttrl_episode_stats
+constexpr int kStatFields = 10;      // ttrl_episode_stats
 struct alignas(16) d2 { double x, y; };  // 16-byte pair (one LDS.128 on the device)
 
 // Read-only scene description, resident in global memory (L1/L2 hot: ~12 KB).
@@ -2211,8 +2211,14 @@ struct StepIO {
     // `shadow` by k_regen_list on a side stream; shadow_ready[e] = episode number held by the shadow of env e (-1: none),
     // written after the record (release) and read before it (acquire).  A finished env whose shadow holds episode + 1
     // restarts from it inside the step; otherwise it takes the done_list path.  Either way (e, episode + 2) is queued.
-    GlobalState shadow;            // shadow.E == 0: off
-    int32_t* shadow_ready;         // [E]
+    // The shadows form a ring of `shadow_depth` episodes per env: episode p of env e lives in record (p % depth) * E + e, so an
+    // env whose episodes end in quick succession still finds the next one ready (the synchronous fallback costs the latency of
+    // a whole reset -- 45 sub-steps -- on the step's critical path even for a single env).  shadow_queued[record] = the episode
+    // that record holds or is queued for (-1: none).
+    GlobalState shadow;            // shadow.E == 0: off; else shadow_depth * E records
+    int32_t* shadow_ready;         // [shadow_depth * E]
+    int32_t* shadow_queued;        // [shadow_depth * E]
+    int shadow_depth;
     int32_t* regen_list;           // [2 E]: (env, episode to generate) pairs
     int32_t* regen_count;
     int autoreset;
@@ -2331,23 +2337,35 @@ TT_HD void env_step_finish(C& c, Exec& ex, const GlobalState& g, const StepIO& i
         // resets with warm-up sub-steps are batched: a lone resetting team would keep its whole CTA (and SM) waiting
         const int next_episode = st->episode + 1;
         bool from_shadow = false;
+        const int D = io.shadow_depth > 0 ? io.shadow_depth : 1;
+        const int rec = (next_episode % D) * g.E + e;
         if (io.shadow.E > 0) {
-            if (ex.first()) st->flag0 = ex.load_acquire(&io.shadow_ready[e]) == next_episode ? 1 : 0;
+            if (ex.first()) st->flag0 = ex.load_acquire(&io.shadow_ready[rec]) == next_episode ? 1 : 0;
             ex.sync();
             from_shadow = st->flag0 != 0;  // uniform: shared memory
             ex.sync();
         }
         if (from_shadow) {
-            load_env<true>(c, ex, io.shadow, e);  // episode, time, counters come with the record (env_reset wrote them)
+            load_env<true>(c, ex, io.shadow, rec);  // episode, time, counters come with the record (env_reset wrote them)
             if (obs) observe(c, ex, obs, perm, io.seed, io.first_global_env + e);
         }
         if (ex.first()) {
-            if (!from_shadow) io.done_list[ex.atomic_add_global(io.done_count, 1)] = e;
+            if (!from_shadow) {
+                io.done_list[ex.atomic_add_global(io.done_count, 1)] = e;
+                if (io.stats) io.stats[(size_t)9 * g.E + e] += 1;  // sync_resets
+            }
             if (io.shadow.E > 0) {
-                io.shadow_ready[e] = -1;  // consumed, or stale: invalid until the queued regeneration has finished
-                const int k = ex.atomic_add_global(io.regen_count, 1);
-                io.regen_list[2 * k] = e;
-                io.regen_list[2 * k + 1] = next_episode + 1;
+                // queue every episode of the ring's horizon that no record holds or waits for yet: next_episode + 1 .. + D
+                // (the last one reuses the record of next_episode, consumed above or stale)
+                for (int k = 1; k <= D; ++k) {
+                    const int ep = next_episode + k, r = (ep % D) * g.E + e;
+                    if (io.shadow_queued[r] == ep) continue;
+                    io.shadow_queued[r] = ep;
+                    io.shadow_ready[r] = -1;  // invalid until the queued regeneration has finished
+                    const int q = ex.atomic_add_global(io.regen_count, 1);
+                    io.regen_list[2 * q] = e;
+                    io.regen_list[2 * q + 1] = ep;
+                }
             }
         }
         ex.sync();

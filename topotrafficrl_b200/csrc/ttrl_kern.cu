@@ -351,10 +351,12 @@ k_regen_list(const SceneDev* __restrict__ sc, StepIO io, SmemLayout lay) {
         const int e = active ? io.regen_list[2 * k] : 0, episode = active ? io.regen_list[2 * k + 1] : 0;
         env_reset_lockstep(c, ex, active, io.seed, io.first_global_env + e, episode);
         if (active) {
-            store_env(c, ex, io.shadow, e);
+            const int D = io.shadow_depth > 0 ? io.shadow_depth : 1;
+            const int rec = (episode % D) * (io.shadow.E / D) + e;  // the ring record of this episode
+            store_env(c, ex, io.shadow, rec);
             __threadfence();
             ex.sync();
-            if (ex.first()) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(io.shadow_ready + e), "r"(episode) : "memory");
+            if (ex.first()) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(io.shadow_ready + rec), "r"(episode) : "memory");
         }
     }
 }

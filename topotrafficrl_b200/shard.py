@@ -7,7 +7,7 @@ from __future__ import annotations
 from typing import Dict, Tuple
 
 STAT_FIELDS = ("episodes", "total_return", "total_length", "crashes", "arrivals", "total_speed", "vehicle_steps", "env_steps",
-               "spawn_capacity_rejects")
+               "spawn_capacity_rejects", "sync_resets")
 
 
 def shard_range(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
