@@ -274,7 +274,7 @@ def test_missing_device_arguments_fail_loudly():
         _sim(cfg, table, 4, 1000)
 
 
-@pytest.mark.parametrize("n,density", [(20, 2.0), (50, 3.0), (200, 4.0)])
+@pytest.mark.parametrize("n,density", [(12, 2.0), (20, 2.0), (50, 3.0), (60, 3.0), (100, 3.0), (200, 4.0)])  # kernel sets 16, 24, 50, 64, 100, 200
 def test_task_queue_stress_vs_oracle(n, density):
     """Pair-queue overflow (serial fallback), several MOBIL batches in one sub-step, many ongoing lane changes and
     ragged vehicle counts (1..n): device == oracle per resynced-free sub-step and per env-step."""

@@ -78,7 +78,8 @@ struct alignas(16) EnvState {
     double h[V], v[V];
     double steer[V], acc[V], tspeed[V], timer[V], delta[V];
     double thr2[V];      // collision pre-check guard: (diag + v dt)^2 (1 + 1e-12), or -1 when diag + v dt < 0
-    double acc2[V];      // IDM acceleration w.r.t. the target lane (vehicles changing lane)
+    double acc2[V];      // IDM acceleration w.r.t. the target lane (vehicles changing lane); dead after the integration: its
+                         // storage then holds the collision scan's float pre-filter (x and guard radius per vehicle)
     double tsteer[V];    // tan(steering command) of this sub-step (by-product of steering_control, used by integrate)
     double mq_a[9 * MB];  // MOBIL IDM evaluations of the batch
     int32_t lane[V], tlane[V], flags[V], sidx[V], rlen[V], ytimer[V];
@@ -968,13 +969,23 @@ template <class C, class Exec>
 TT_HD void collide_all(C& c, Exec& ex) {
     auto* st = c.st;
     const int n = st->n;
+    // K0: float copies for the pre-filter.  |x_hi - x_lo| > radius_lo + 1 cm in float implies the exact squared-distance guard
+    // rejects the pair (float rounding of positions up to 1e4 m is < 1 mm): the filter can only skip pairs the guard would skip.
+    float* xf = reinterpret_cast<float*>(st->acc2);  // [V] x, [V] radius: acc2 is rewritten by phase C2 before its next read
+    float* rf = xf + C::V;
+    ex.parn(n, [&](int k) {
+        xf[k] = (float)st->pos[k].x;
+        rf[k] = st->thr2[k] < 0 ? -1.0f : (float)sqrt(st->thr2[k]) * 1.000001f + 0.01f;
+    });
     // K1
     ex.parn(n, [&](int k) {
         const int half = n / 2;
+        const float xk = xf[k], rk = rf[k];
         for (int m = 1; m <= half; ++m) {
             int p = k + m;
             if (p >= n) p -= n;
             if (2 * m == n && k >= half) break;  // even n: the diametral pair is visited once
+            if (fabsf(xf[p] - xk) > (k < p ? rk : rf[p])) continue;
             const int lo = k < p ? k : p, hi = k < p ? p : k;
             if (!collide_candidate(c, lo, hi)) continue;
             const int slot = ex.atomic_add(&st->n_pair, 1);
