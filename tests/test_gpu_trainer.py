@@ -201,3 +201,56 @@ def test_kernel_update_equals_torch_autograd_update(loss, double):
         a.close()
     for e in envs:
         e.close()
+
+
+@pytest.mark.parametrize("path", ["graph", "kernel"])
+def test_checkpoint_resume_keeps_optimizer_state(path, tmp_path):
+    """save() -> load() into a fresh agent -> one more update == continuing the original agent: the Adam moments and step counter
+    survive the resume on the CUDA-graph path (whose warm-up updates before the capture must not wipe a loaded state, and whose
+    captured graph must see a state loaded after the capture) and on the kernel path (which updates torch's state tensors in place)."""
+    torch = _torch()
+    kw = dict(cuda_graph=True, update_kernel=False) if path == "graph" else dict(update_kernel=True)
+    env = factory.load_environment(ENV_JSON, num_envs=128, seed=9)
+    cfg = dict(AGENT, model=CONFIGS["mlp"], batch_size=64, target_update=4)
+    a = factory.load_agent(cfg, env, seed=4, **kw)
+    obs, _ = env.reset()
+    for step in range(12):
+        prev = obs.clone()
+        act = a.act(prev)
+        obs, reward, term, trunc, info = env.step(act)
+        a.record(prev, act, reward, obs, term, trunc, info)
+    ck = a.save(str(tmp_path / "ck.tar"))
+    # resume BEFORE the first update of the new agent (graph path: the capture happens after the load) ...
+    b = factory.load_agent(cfg, env, seed=99, **kw)
+    b.load(ck)
+    # ... and AFTER it (graph path: the capture already happened)
+    c = factory.load_agent(cfg, env, seed=98, **kw)
+    for name in ("state", "next_state", "action", "reward", "terminal"):
+        for other in (b, c):
+            getattr(other.memory, name).copy_(getattr(a.memory, name))
+    for other in (b, c):
+        other.memory.size, other.memory.position = a.memory.size, a.memory.position
+    prev = obs.clone()
+    act = a.act(prev)
+    obs2, reward, term, trunc, info = env.step(act)
+    c.gen.set_state(a.gen.get_state())
+    c.record(prev, act, reward, obs2, term, trunc, info)   # one update with fresh moments, then the load
+    c.load(ck)
+    for name in ("state", "next_state", "action", "reward", "terminal"):
+        getattr(c.memory, name).copy_(getattr(a.memory, name))
+    c.memory.size, c.memory.position = a.memory.size, a.memory.position
+    state = a.gen.get_state()
+    for other in (b, c):
+        other.gen.set_state(state)
+    a.gen.set_state(state)
+    for agent in (a, b, c):
+        agent.record(prev, act, reward, obs2, term, trunc, info)
+    for (n, p), q, r in zip(a.value_net.named_parameters(), b.value_net.parameters(), c.value_net.parameters()):
+        assert float((p - q).abs().max()) < 1e-6, (path, "load before the first update", n)
+        assert float((p - r).abs().max()) < 1e-6, (path, "load after the first update", n)
+    pa = next(iter(a.value_net.parameters()))
+    sa, sb = a.optimizer.state[pa], b.optimizer.state[next(iter(b.value_net.parameters()))]
+    assert float(sa["step"]) == float(sb["step"]) == 13
+    for agent in (a, b, c):
+        agent.close()
+    env.close()
