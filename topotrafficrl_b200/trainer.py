@@ -286,10 +286,13 @@ class BatchedDQNAgent:
         self.memory.push(s.reshape((-1,) + self.obs_shape), a.reshape(-1), r.repeat_interleave(K), ns.reshape((-1,) + self.obs_shape),
                          t.repeat_interleave(K))
         ready = len(self.memory) >= self.config["batch_size"]
-        if self._world > 1:  # the ranks must agree: the optimiser step holds a collective
+        if self._world > 1 and not getattr(self, "_ready_everywhere", False):
+            # the ranks must agree: the optimiser step holds a collective.  The memory only grows, so once every rank is ready the
+            # question (a host synchronisation) is not asked again
             flag = torch.tensor([1 if ready else 0], dtype=torch.int32, device=self.device)
             torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
             ready = bool(flag.item())
+            self._ready_everywhere = ready
         for _ in range(self.updates_per_step):
             if not ready:
                 return
