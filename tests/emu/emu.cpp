@@ -104,7 +104,8 @@ SceneDev* emu_scene_create(const ttrl_config* cfg, const ttrl_lane* lanes, const
     SceneDev* s = (SceneDev*)calloc(1, sizeof(SceneDev));
     s->cfg = *cfg;
     memcpy(s->lanes, lanes, sizeof(ttrl_lane) * cfg->n_lanes);
-    s->n_curved = assign_cache_columns(s->lanes, cfg->n_lanes);
+    s->n_curved = assign_cache_columns(s->lanes, cfg->n_lanes, s->curved_lane);
+    s->arc_tasks = getenv("TTRL_EMU_ARC_TASKS") ? atoi(getenv("TTRL_EMU_ARC_TASKS")) : use_arc_tasks(s->lanes, cfg->n_lanes, s->n_curved);
     memcpy(s->roads, roads, sizeof(ttrl_road) * cfg->n_roads);
     memcpy(s->node_first, node_first, sizeof(int32_t) * (cfg->n_nodes + 1));
     memcpy(s->node_roads, node_roads, sizeof(int32_t) * node_first[cfg->n_nodes]);

@@ -93,3 +93,22 @@ def test_task_queue_stress_vs_oracle(n, density):
         T.compare_states(a, b, 1e-7, f"stress step {k}")
         np.testing.assert_allclose(oa[0], ob[0], rtol=0, atol=2e-6)
         assert (oa[2] == ob[2]).all() and (oa[3] == ob[3]).all()
+
+
+@pytest.mark.parametrize("scene", ["roundabout", "uturn"])
+def test_curved_lane_task_list_on_scenes_that_do_not_use_it_by_default(scene, monkeypatch):
+    """closest_lane_tasks (straight pass + curved-lane task list + merge; sine-lane bounds, NaN cache entries read on demand) is
+    only enabled where it pays (use_arc_tasks: the intersection); forced on here, it must reproduce the reference on the ring and the
+    sine lanes of the roundabout and on the u-turn just the same."""
+    from tests.emu.emu import Emulator
+    monkeypatch.setenv("TTRL_EMU_ARC_TASKS", "1")
+    _, table, cfg, _ = T.roundabout_scene() if scene == "roundabout" else T.uturn_scene()
+    emu = Emulator(cfg, table)
+    gs, g = T.golden(f"{scene}_substeps.npz"), T.golden(f"{scene}_steps.npz")
+    st = T.batch_state(gs, "before")
+    emu.substep(st, gs["action"].astype(np.int32))
+    T.compare_states(st, T.batch_state(gs, "after"), T.TOL_SUBSTEP, f"{scene} sub-step, task form")
+    st = T.batch_state(g, "before")
+    obs, reward, term, trunc, _ = emu.step(st, g["action"].astype(np.int32))
+    T.compare_states(st, T.batch_state(g, "after"), T.TOL_STEP, f"{scene} step, task form")
+    np.testing.assert_allclose(obs.reshape(g["obs"].shape), g["obs"], rtol=0, atol=2e-6)

@@ -58,6 +58,9 @@ struct SceneDev {
     ttrl_reset_params rp;  // device-side reset parameters (have_rp != 0)
     int32_t have_rp;
     int32_t n_curved;    // curved lanes = columns of the per-vehicle coordinate cache (assign_cache_columns)
+    int8_t curved_lane[TTRL_MAX_LANES];  // cache column -> lane index
+    int32_t arc_tasks;   // closest-lane search through the curved-lane task list (use_arc_tasks), else one loop per vehicle
+    int32_t pad_arc;
     int32_t F;           // sub-steps per env-step (abstract.py:254-256)
     int32_t reg_period;  // int(1/dt/REGULATION_FREQUENCY) (regulation.py:30)
     double dt;           // 1/simulation_frequency
@@ -95,7 +98,7 @@ struct alignas(16) EnvState {
     int16_t mq_f[3 * MB], mq_r[3 * MB];  // MOBIL neighbour queries: own lane, left candidate, right candidate
     int32_t n, steps, road_steps, ego, episode, done, flag0, flag1;
     int32_t egos[TTRL_MAX_CONTROLLED];  // slots of env.controlled_vehicles (egos[0] == ego)
-    int32_t n_chg, n_mob, n_pair, n_w, overflow, pad0;
+    int32_t n_chg, n_mob, n_pair, n_w, overflow, n_arc;  // n_arc: queued (vehicle, curved lane) projection tasks of this sub-step
     double time, ret;
 };
 
@@ -301,6 +304,11 @@ template <class C> TT_HD double lane_heading_at_c(const ttrl_lane& l, double s) 
 // ------------------------------------------------------------------------------------------------
 // table access
 // ------------------------------------------------------------------------------------------------
+TT_HDN d2 sr_curved_slow(const ttrl_lane& ln, d2 p) {
+    double s, r;
+    lane_local_curved_inl(ln, p.x, p.y, s, r);
+    return d2{s, r};
+}
 // (s, r) of vehicle v in lane l.  Straight lanes: 6 flops from the position (the same expression as the closest-lane
 // search: bit-identical); curved lanes: the cached result of that search (one atan2 / sin per vehicle, lane and sub-step).
 // Caching only the curved lanes is what lets an SM hold more envs: the full V x L table was the largest shared-memory
@@ -315,14 +323,22 @@ template <class C> TT_HD d2 sr_of(C& c, int v, int l) {
         const double dx = p.x - ln.ax, dy = p.y - ln.ay;
         return d2{dx * ln.dx + dy * ln.dy, dx * (-ln.dy) + dy * ln.dx};
     }
-    return c.SR[v * c.NC + ln.cache_col];
+    const d2 cached = c.SR[v * c.NC + ln.cache_col];
+    // a NaN lateral marks an entry the closest-lane search skipped (the vehicle is nowhere near that lane: closest_lane_tasks);
+    // the rare reader of such an entry projects on demand
+    if (cached.y != cached.y) return sr_curved_slow(ln, c.st->pos[v]);
+    return cached;
 }
 template <class C> TT_HD double S_(C& c, int v, int l) { return sr_of(c, v, l).x; }
 template <class C> TT_HD double R_(C& c, int v, int l) { return sr_of(c, v, l).y; }
 // columns of the curved-lane cache (host side: ttrl_sim_create / the test emulator); returns their number
-inline int assign_cache_columns(ttrl_lane* lanes, int n_lanes) {
+inline int assign_cache_columns(ttrl_lane* lanes, int n_lanes, int8_t* curved_lane) {
     int nc = 0;
-    for (int l = 0; l < n_lanes; ++l) lanes[l].cache_col = lanes[l].kind == TTRL_LANE_STRAIGHT ? -1 : nc++;
+    for (int l = 0; l < n_lanes; ++l) {
+        if (lanes[l].kind == TTRL_LANE_STRAIGHT) { lanes[l].cache_col = -1; continue; }
+        curved_lane[nc] = (int8_t)l;
+        lanes[l].cache_col = nc++;
+    }
     return nc;
 }
 
@@ -362,6 +378,117 @@ TT_HD void publish_on_mask(C& c, Exec& ex, int v, uint64_t m) {
         ex.atomic_or(&c.lmask[l * C::W + (v >> 5)], 1u << (v & 31));
     }
 }
+// ------------------------------------------------------------------------------------------------
+// The closest-lane search of the sub-step, as three phases (non-plain profiles).  The curved-lane projection (atan2 / sin) is the
+// most expensive part of a sub-step and is only needed for the few (vehicle, lane) pairs where the vehicle can be ON the lane
+// (|r| <= width / 2 + 1) or the lane can be the argmin (|r| <= the best straight-lane distance; d >= |r| exactly, every other term
+// of lane.py:127-147 being non-negative).  |r| costs one sqrt for an arc (|radius - rad|), a bound for a sine lane (|lat| - amplitude):
+//   S  per vehicle: all straight lanes (argmin candidate, on-lane bits); curved lanes: the bound -> task queue, or NaN into the cache
+//   T  per task:    the projection -> cache, on-lane bit                      (full lanes: ~1 trip instead of one iteration per arc)
+//   M  per vehicle: distance of its queued lanes from the cache, merged into the argmin as (distance, lane index) pairs --
+//                   np.argmin's first minimum (road.py:55-71) whatever the evaluation order.
+// Scratch: candidate bits in mark[], straight-lane best distance / lane in acc2[] / tl_old[], the queue in mq_a (all idle here).
+// ------------------------------------------------------------------------------------------------
+template <class C> TT_HD uint16_t* arc_queue(C& c) { return reinterpret_cast<uint16_t*>(c.st->mq_a); }
+template <class C> constexpr int arc_queue_cap() { return 9 * EnvState<C::V>::MB * (int)(sizeof(double) / sizeof(uint16_t)); }
+
+template <class C, class Exec>
+TT_HD void arc_project(C& c, Exec& ex, int v, int col) {
+    const int l = c.sc->curved_lane[col];
+    const ttrl_lane& ln = c.lanes[l];
+    double s, r;
+    lane_local_curved_inl(ln, c.st->pos[v].x, c.st->pos[v].y, s, r);
+    c.SR[v * c.NC + col] = d2{s, r};
+    if (lane_on_lane(ln, s, r, 1.0)) ex.atomic_or(&c.lmask[l * C::W + (v >> 5)], 1u << (v & 31));
+}
+template <class C, class Exec>
+TT_HD void closest_lane_straight(C& c, Exec& ex, int v) {
+    auto* st = c.st;
+    const double px = st->pos[v].x, py = st->pos[v].y, hd = st->h[v];
+    int best = -1;
+    double bd = 0;
+    uint64_t m = 0;
+    for (int l = 0; l < c.L; ++l) {
+        const ttrl_lane& ln = c.lanes[l];
+        if (ln.kind != TTRL_LANE_STRAIGHT) continue;
+        const double dx = px - ln.ax, dy = py - ln.ay;
+        const double s = dx * ln.dx + dy * ln.dy, r = dx * (-ln.dy) + dy * ln.dx;
+        if (lane_on_lane(ln, s, r, 1.0)) m |= 1ull << l;
+        const double d = lane_distance_sr(ln, s, r) + 1.0 * fabs(wrap_to_pi(hd - ln.heading));
+        if (best < 0 || d < bd) { bd = d; best = l; }
+    }
+    publish_on_mask(c, ex, v, m);
+    uint32_t cand = 0;
+    for (int col = 0; col < c.NC; ++col) {
+        const ttrl_lane& ln = c.lanes[c.sc->curved_lane[col]];
+        const double dx = px - ln.ax, dy = py - ln.ay;
+        double lb;  // lower bound of |r|
+        if (ln.kind == TTRL_LANE_CIRCULAR) lb = fabs(ln.radius - sqrt(dx * dx + dy * dy));
+        else lb = fmax(fabs(dx * (-ln.dy) + dy * ln.dx) - fabs(ln.amplitude), 0.0);
+        if (best < 0 || lb <= bd || lb <= ln.width / 2 + 1.0) {
+            cand |= 1u << col;
+            const int q = ex.atomic_add(&st->n_arc, 1);
+            if (q < arc_queue_cap<C>()) arc_queue(c)[q] = (uint16_t)(v | (col << 8));
+            else arc_project(c, ex, v, col);  // queue full: project right here
+        } else {
+            c.SR[v * c.NC + col] = d2{0.0, NAN};
+        }
+    }
+    st->mark[v] = (int32_t)cand;
+    st->acc2[v] = bd;
+    st->tl_old[v] = best;
+}
+template <class C>
+TT_HD void closest_lane_merge(C& c, int v) {
+    auto* st = c.st;
+    const double hd = st->h[v];
+    double bd = st->acc2[v];
+    int best = st->tl_old[v];
+    uint32_t cand = (uint32_t)st->mark[v];
+    while (cand) {
+#if defined(__CUDA_ARCH__)
+        const int col = __ffs((int)cand) - 1;
+#else
+        const int col = __builtin_ctz(cand);
+#endif
+        cand &= cand - 1;
+        const int l = c.sc->curved_lane[col];
+        const ttrl_lane& ln = c.lanes[l];
+        const d2 sr = c.SR[v * c.NC + col];
+        const double d = lane_distance_sr(ln, sr.x, sr.y) + 1.0 * fabs(wrap_to_pi(hd - lane_heading_at(ln, sr.x)));
+        if (best < 0 || d < bd || (d == bd && l < best)) { bd = d; best = l; }
+    }
+    st->lane[v] = best;
+    st->mark[v] = 0;
+}
+// the search for every vehicle of the env (after positions changed): replaces table_row_and_closest per vehicle
+template <class C, class Exec>
+TT_HD void closest_lane_tasks(C& c, Exec& ex) {
+    auto* st = c.st;
+    const int n = st->n;
+    ex.parn(n, [&](int t) { closest_lane_straight(c, ex, t); });
+    const int nq = st->n_arc < arc_queue_cap<C>() ? st->n_arc : arc_queue_cap<C>();
+    ex.parn(nq, [&](int q) { const int rec = arc_queue(c)[q]; arc_project(c, ex, rec & 0xFF, rec >> 8); });
+    ex.parn(n, [&](int t) { closest_lane_merge(c, t); });
+}
+
+// When the task form pays (measured, profiles/r2_step_scheduling.txt item 14): several curved lanes whose |r| bounds separate
+// them -- the intersection's eight turn arcs (1.53 -> 1.47 ms/step).  Not for a ring (the roundabout's arcs share centre and radius, so
+// a vehicle on the ring is a candidate of all of them: 2.01 -> 3.08 ms) nor for two arcs (u-turn: 0.71 -> 0.81, the extra phases cost
+// more than they save).  Host side (ttrl_sim_create / the test emulator).
+inline int use_arc_tasks(const ttrl_lane* lanes, int n_lanes, int n_curved) {
+    if (n_curved < 4 || n_curved > 32) return 0;  // (candidate sets are 32-bit)
+    for (int a = 0; a < n_lanes; ++a) {
+        if (lanes[a].kind == TTRL_LANE_STRAIGHT) continue;
+        if (lanes[a].kind != TTRL_LANE_CIRCULAR) return 0;  // sine lanes: the amplitude bound is too weak to separate them
+        for (int b = a + 1; b < n_lanes; ++b)
+            if (lanes[b].kind == TTRL_LANE_CIRCULAR && fabs(lanes[a].ax - lanes[b].ax) < 1e-9 && fabs(lanes[a].ay - lanes[b].ay) < 1e-9 &&
+                fabs(lanes[a].radius - lanes[b].radius) < 0.5 * (lanes[a].width + lanes[b].width))
+                return 0;                                    // two arcs of one circle
+    }
+    return 1;
+}
+
 // Rebuild the whole table + lane masks from positions (after load / compaction).
 template <class C, class Exec>
 TT_HD void rebuild_tables(C& c, Exec& ex) {
@@ -840,9 +967,11 @@ TT_HD void integrate(C& c, Exec& ex, int i) {
     sincos(nh, &sn, &cn);
     st->cs[i] = d2{cn, sn};
     st->flags[i] = fl;
-    uint64_t m;
-    st->lane[i] = table_row_and_closest(c, i, m);
-    publish_on_mask(c, ex, i, m);
+    if (C::kPlain || !c.sc->arc_tasks) {  // (else: closest_lane_tasks, after every vehicle has moved)
+        uint64_t m;
+        st->lane[i] = table_row_and_closest(c, i, m);
+        publish_on_mask(c, ex, i, m);
+    }
     // collision pre-check guard (objects.py:123-126): radius (diag_i + diag_j)/2 + speed dt of the LOWER index
     const double diag = sqrt(kVehLength * kVehLength + kVehWidth * kVehWidth);
     const double thr = (diag + diag) / 2 + nv * dt;
@@ -1234,8 +1363,9 @@ TT_HD void substep_controls(C& c, Exec& ex) {
 template <class C, class Exec>
 TT_HD void substep_integrate(C& c, Exec& ex) {
     const int n = c.st->n;
-    ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; });
+    ex.parn(c.L * C::W, [&](int k) { c.lmask[k] = 0; if (k == 0) c.st->n_arc = 0; });
     ex.parn(n, [&](int t) { integrate(c, ex, t); });
+    if (!C::kPlain && c.sc->arc_tasks) closest_lane_tasks(c, ex);
 }
 template <class C, class Exec>
 TT_HD void substep_collide(C& c, Exec& ex) {
