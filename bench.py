@@ -20,6 +20,11 @@ Numbers on the JSON line
   cpu_baseline  the CPU oracle (C restatement of the reference algorithm, oracle/) on the host cores of this
              box, bounded sample of the same workload.  Rank 0, N=1 only.
 
+The default run (headline workload, N = 1) adds an `also` block -- BASELINE configs[2] (dense200), configs[3] without and with the
+DQN Q-network rollout (intersection, intersection_qnet), each >= 50 timed steps with its own roofline / e2e / clocks / CPU baseline --
+and a 200-step `self_check` of the headline.  `--scaling strong` splits a fixed total (32 768 highway / 1 048 576 intersection
+envs) over the GPUs instead of giving every GPU the workload's envs.  A workload whose slot capacity rejected a spawn fails the run.
+
 `--impl reference` times the CPU oracle port alone (the Python reference itself cannot travel to the GPU box and
 runs at ~1.8e3 vehicle-steps/s/core; the C port is the faster, fairer CPU arm).
 """
