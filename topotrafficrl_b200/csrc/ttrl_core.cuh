@@ -2316,16 +2316,24 @@ TT_HDN void env_reset(C& c, Exec& ex, uint64_t seed, int64_t genv, int episode) 
 // env_reset for the teams of a multi-env CTA, `active` = this team has an env to reset.  EVERY team of the CTA calls it: the
 // alignment barrier of the warm-up loop is ONE instruction that active and idle teams reach alike -- a CTA barrier executed
 // from different instructions by two sub-warp teams of the same warp deadlocks (tools/probes/bar_divergence.cu).
+// `part` of `parts`: the reset may be spread over several launches (k_regen_list: short kernels that the next step does not have
+// to wait long for); the state between two parts lives in the record `rec` of `g` -- a sub-step is a pure function of the stored
+// state (what the resynced parity tests rely on), so the split changes nothing.  The caller stores the state after each part.
 template <class C, class Exec>
-TT_HD void env_reset_lockstep(C& c, Exec& ex, bool active, uint64_t seed, int64_t genv, int episode) {
-    if (C::kPlain || c.sc->rp.scene != 1) {  // uniform over the CTA: no warm-up sub-steps
-        if (active) env_reset(c, ex, seed, genv, episode);
+TT_HD void env_reset_lockstep(C& c, Exec& ex, bool active, uint64_t seed, int64_t genv, int episode, int part = 0, int parts = 1,
+                              const GlobalState* g = nullptr, int rec = 0) {
+    if (C::kPlain || c.sc->rp.scene != 1) {  // uniform over the CTA: no warm-up sub-steps, everything in the last part
+        if (active && part == parts - 1) env_reset(c, ex, seed, genv, episode);
         return;
     }
-    if (active) reset_intersection_begin(c, ex, seed, genv, episode);
+    if (active) {
+        if (part == 0) reset_intersection_begin(c, ex, seed, genv, episode);
+        else load_env(c, ex, *g, rec);
+    }
     const int warmup = c.sc->rp.warmup_substeps;
-    for (int k = 0; k < warmup; ++k) env_substep_lockstep(c, ex, active, nullptr);
-    if (active) reset_intersection_end(c, ex, seed, genv, episode);
+    const int k0 = (int)((long long)warmup * part / parts), k1 = (int)((long long)warmup * (part + 1) / parts);
+    for (int k = k0; k < k1; ++k) env_substep_lockstep(c, ex, active, nullptr);
+    if (active && part == parts - 1) reset_intersection_end(c, ex, seed, genv, episode);
 }
 
 // ------------------------------------------------------------------------------------------------

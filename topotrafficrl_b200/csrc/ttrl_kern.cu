@@ -333,7 +333,7 @@ k_reset_list(const SceneDev* __restrict__ sc, GlobalState g, StepIO io, SmemLayo
 // a release store of its episode number after every thread's writes have been fenced.
 template <int V, int P>
 __global__ void __launch_bounds__(TeamOf<V>::T * TeamOf<V>::G, TeamOf<V>::G > 1 ? 1 : TeamOf<V>::MINB)
-k_regen_list(const SceneDev* __restrict__ sc, StepIO io, SmemLayout lay) {
+k_regen_list(const SceneDev* __restrict__ sc, StepIO io, SmemLayout lay, int part, int parts) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int T = TeamOf<V>::T;
     const int G = (int)blockDim.x / T;
@@ -349,14 +349,16 @@ k_regen_list(const SceneDev* __restrict__ sc, StepIO io, SmemLayout lay) {
         const int k = (pass * G + team) * nb + b;
         const bool active = k < n_regen;
         const int e = active ? io.regen_list[2 * k] : 0, episode = active ? io.regen_list[2 * k + 1] : 0;
-        env_reset_lockstep(c, ex, active, io.seed, io.first_global_env + e, episode);
+        const int D = io.shadow_depth > 0 ? io.shadow_depth : 1;
+        const int rec = (episode % D) * (io.shadow.E / D) + e;  // the ring record of this episode
+        env_reset_lockstep(c, ex, active, io.seed, io.first_global_env + e, episode, part, parts, &io.shadow, rec);
         if (active) {
-            const int D = io.shadow_depth > 0 ? io.shadow_depth : 1;
-            const int rec = (episode % D) * (io.shadow.E / D) + e;  // the ring record of this episode
-            store_env(c, ex, io.shadow, rec);
-            __threadfence();
-            ex.sync();
-            if (ex.first()) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(io.shadow_ready + rec), "r"(episode) : "memory");
+            store_env(c, ex, io.shadow, rec);  // (an unfinished reset parks its state in the record: ready stays -1)
+            if (part == parts - 1) {
+                __threadfence();
+                ex.sync();
+                if (ex.first()) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(io.shadow_ready + rec), "r"(episode) : "memory");
+            }
         }
     }
 }
@@ -455,7 +457,7 @@ static void launch_reset_list(int E, const SmemLayout& lay, cudaStream_t st, con
 }
 // the regeneration of the episodes queued by the last step, on the side stream
 template <int V>
-static void launch_regen(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const StepIO& io) {
+static void launch_regen(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const StepIO& io, int parts) {
     const int G = lay.G;
     // One CTA per SM, default stream priority: the regeneration CTAs (4-5 busy teams each) slot into the ragged tail of the
     // step kernel's last wave and the next step's CTAs follow as they drain.  Measured alternatives (profiles/r1k_async_reset.txt):
@@ -463,9 +465,11 @@ static void launch_regen(int E, const SmemLayout& lay, cudaStream_t st, const Sc
     static const int div = [] { const char* v = getenv("TTRL_REGEN_SM_DIV"); const int d = v ? atoi(v) : 1; return d > 0 ? d : 1; }();  // tuning experiments
     const int cap = lay.n_sms / div > 0 ? lay.n_sms / div : 1;
     const int nb = (E + G - 1) / G < cap ? (E + G - 1) / G : cap;
-    if (lay.plain == 3) { if constexpr (kHasLinearProfile<V>) k_regen_list<V, 3><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay); }
-    else if (lay.plain == 2) k_regen_list<V, 2><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay);
-    else k_regen_list<V, 0><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay);
+    for (int part = 0; part < parts; ++part) {  // consecutive launches on the same stream: part k + 1 continues from the records of part k
+        if (lay.plain == 3) { if constexpr (kHasLinearProfile<V>) k_regen_list<V, 3><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay, part, parts); }
+        else if (lay.plain == 2) k_regen_list<V, 2><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay, part, parts);
+        else k_regen_list<V, 0><<<nb, TeamOf<V>::T * G, lay.total_step, st>>>(sc, io, lay, part, parts);
+    }
 }
 template <int V>
 static void launch_substep(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const int32_t* actions) {

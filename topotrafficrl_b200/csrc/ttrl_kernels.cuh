@@ -25,7 +25,7 @@ struct KernelSet {
                   SpawnParams sp, int32_t* accepted);
     void (*reset)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const GlobalState& g, const uint8_t* mask, uint64_t seed,
                   int64_t first_global_env);
-    void (*regen)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const StepIO& io);
+    void (*regen)(int E, const SmemLayout& lay, cudaStream_t st, const SceneDev* sc, const StepIO& io, int parts);
 };
 
 }  // namespace ttrl
