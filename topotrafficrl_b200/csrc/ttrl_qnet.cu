@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(128, 1) k_qnet_mlp_tc(TcMlp d, const float* __
 struct TcEgo {
     int NE, Fe, Fs, H, A, pidx;
     int ego_w1, ego_b1, ego_w2, ego_b2, oth_w1, oth_b1, oth_w2, oth_b2, wk, wv, wq, wc, o_w1, o_b1, o_w2, o_b2, p_w, p_b;  // blob offsets
-    int off_b1hi, off_b1lo, off_b2hi, off_b2lo, off_b3hi, off_b3lo, off_ahi, off_alo, off_f32, off_x, off_small, off_bar, total;
+    int off_b1hi, off_b1lo, off_b2hi, off_b2lo, off_b3hi, off_b3lo, off_ahi, off_f32, off_x, x_stride, off_small, small_stride, off_bar, total;
 };
 
 #define TT_TMEM_LD32(v, addr)                                                                                              \
@@ -500,6 +500,16 @@ __device__ __forceinline__ void tc_sync_before_mma() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// The ego kernel runs TWO tiles per CTA, one per group of 4 warps (threads 0..127 / 128..255), each with its own A operand,
+// accumulators (256 TMEM columns), mbarrier and named barrier (ids 1 and 2): while one group waits for its MMA or runs an
+// epilogue, the other one stages, issues or reads back -- the tensor pipe and the CUDA cores of the SM overlap across the two tiles.
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory"); }
+__device__ __forceinline__ void tc_group_sync_before_mma(int grp) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    group_sync(grp);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 // out[env][n] = act(bias[n] + sum_k in[env][k] * Wt[k][n]) for the 8 observations of a tile; thread = (env, 4 columns)
@@ -521,26 +531,29 @@ __device__ __forceinline__ void tile_dense8(const float* in, const float* Wt, co
     }
 }
 
-__global__ void __launch_bounds__(128, 1) k_qnet_ego_tc(TcEgo d, const float* __restrict__ weights, const float* __restrict__ obs, int E,
+__global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __restrict__ weights, const float* __restrict__ obs, int E,
                                                          double eps, uint64_t seed, uint64_t step, const double* __restrict__ u_inj,
                                                          int32_t* __restrict__ actions, float* __restrict__ qout) {
     extern __shared__ __align__(1024) unsigned char sm[];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int env = tid >> 4, ent = tid & 15;     // row tid of the tile = entity `ent` of observation `env`
+    const int tid = threadIdx.x, grp = tid >> 7, t = tid & 127, warp = t >> 5;   // group of 4 warps; warp w reads TMEM lanes 32 (w % 4) ..
+    const int env = t >> 4, ent = t & 15;         // row t of the group's tile = entity `ent` of observation `env`
     const int Fs = d.Fs, nin = d.NE * d.Fe;
     float* f32 = reinterpret_cast<float*>(sm + d.off_f32);
     float* s_wc = f32; float* s_ow1 = s_wc + Fs * Fs; float* s_ow2 = s_ow1 + Fs * Fs; float* s_pw = s_ow2 + Fs * Fs;
     float* s_b1o = s_pw + Fs * 4; float* s_b1e = s_b1o + Fs; float* s_b2o = s_b1e + Fs; float* s_b2e = s_b2o + Fs;
     float* s_ob1 = s_b2e + Fs; float* s_ob2 = s_ob1 + Fs; float* s_pb = s_ob2 + Fs;
-    float* s_x = reinterpret_cast<float*>(sm + d.off_x);          // [8][nin]
-    float* s_q = reinterpret_cast<float*>(sm + d.off_small);      // [8][64] query of the ego
-    float* s_ego = s_q + 8 * 64; float* s_val = s_ego + 8 * 64; float* s_t0 = s_val + 8 * 64; float* s_t1 = s_t0 + 8 * 64;
-    float* scratch = reinterpret_cast<float*>(sm + d.off_ahi);    // [128][64] fp32, aliases the A operand (hi + lo)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + d.off_bar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + d.off_bar + 8);
+    float* s_x = reinterpret_cast<float*>(sm + d.off_x + grp * d.x_stride);          // [8][nin]
+    float* s_q = reinterpret_cast<float*>(sm + d.off_small + grp * d.small_stride);  // [8][64] query of the ego
+    // s_val and s_t1 reuse the query's storage: the query is dead after the scores, s_val after the combine layer
+    float* s_ego = s_q + 8 * 64; float* s_val = s_q; float* s_t0 = s_ego + 8 * 64; float* s_t1 = s_q;
+    unsigned char* a_hi_p = sm + d.off_ahi + grp * (2 * 128 * 64 * 2);               // this group's A operand: hi then lo
+    unsigned char* a_lo_p = a_hi_p + 128 * 64 * 2;
+    float* scratch = reinterpret_cast<float*>(a_hi_p);            // [128][64] fp32, aliases the A operand (hi + lo)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + d.off_bar + grp * 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + d.off_bar + 16);
 
     // ---- one-time setup: stacked B operands (split BF16, canonical layout) and the fp32 tail weights ----
-    for (int i = tid; i < 128 * 16; i += 128) {            // B1[n][k], K = 16: n < 64 others layer 1, n >= 64 ego layer 1
+    for (int i = tid; i < 128 * 16; i += 256) {            // B1[n][k], K = 16: n < 64 others layer 1, n >= 64 ego layer 1
         const int n = i >> 4, k = i & 15;
         float w = 0.f;
         if (k < d.Fe) w = __ldg(weights + (n < 64 ? d.oth_w1 : d.ego_w1) + k * Fs + (n & 63));
@@ -548,51 +561,52 @@ __global__ void __launch_bounds__(128, 1) k_qnet_ego_tc(TcEgo d, const float* __
         const uint32_t o = canon_off(n, k, 16);
         *reinterpret_cast<unsigned short*>(sm + d.off_b1hi + o) = hi; *reinterpret_cast<unsigned short*>(sm + d.off_b1lo + o) = lo;
     }
-    for (int i = tid; i < 128 * 64; i += 128) {            // B2[n][k], K = 64
+    for (int i = tid; i < 128 * 64; i += 256) {            // B2[n][k], K = 64
         const int n = i >> 6, k = i & 63;
         unsigned short hi, lo; split_bf16(__ldg(weights + (n < 64 ? d.oth_w2 : d.ego_w2) + k * Fs + (n & 63)), hi, lo);
         const uint32_t o = canon_off(n, k, 64);
         *reinterpret_cast<unsigned short*>(sm + d.off_b2hi + o) = hi; *reinterpret_cast<unsigned short*>(sm + d.off_b2lo + o) = lo;
     }
-    for (int i = tid; i < 192 * 64; i += 128) {            // B3[n][k] = [W_k ; W_v ; W_q]
+    for (int i = tid; i < 192 * 64; i += 256) {            // B3[n][k] = [W_k ; W_v ; W_q]
         const int n = i >> 6, k = i & 63;
         const int base = n < 64 ? d.wk : n < 128 ? d.wv : d.wq;
         unsigned short hi, lo; split_bf16(__ldg(weights + base + k * Fs + (n & 63)), hi, lo);
         const uint32_t o = canon_off(n, k, 64);
         *reinterpret_cast<unsigned short*>(sm + d.off_b3hi + o) = hi; *reinterpret_cast<unsigned short*>(sm + d.off_b3lo + o) = lo;
     }
-    for (int i = tid; i < Fs * Fs; i += 128) { s_wc[i] = __ldg(weights + d.wc + i); s_ow1[i] = __ldg(weights + d.o_w1 + i); s_ow2[i] = __ldg(weights + d.o_w2 + i); }
-    for (int i = tid; i < Fs * d.A; i += 128) s_pw[i] = __ldg(weights + d.p_w + i);
-    for (int i = tid; i < Fs; i += 128) {
+    for (int i = tid; i < Fs * Fs; i += 256) { s_wc[i] = __ldg(weights + d.wc + i); s_ow1[i] = __ldg(weights + d.o_w1 + i); s_ow2[i] = __ldg(weights + d.o_w2 + i); }
+    for (int i = tid; i < Fs * d.A; i += 256) s_pw[i] = __ldg(weights + d.p_w + i);
+    for (int i = tid; i < Fs; i += 256) {
         s_b1o[i] = __ldg(weights + d.oth_b1 + i); s_b1e[i] = __ldg(weights + d.ego_b1 + i);
         s_b2o[i] = __ldg(weights + d.oth_b2 + i); s_b2e[i] = __ldg(weights + d.ego_b2 + i);
         s_ob1[i] = __ldg(weights + d.o_b1 + i); s_ob2[i] = __ldg(weights + d.o_b2 + i);
     }
-    for (int i = tid; i < d.A; i += 128) s_pb[i] = __ldg(weights + d.p_b + i);
-    if (tid == 0) {
+    for (int i = tid; i < d.A; i += 256) s_pb[i] = __ldg(weights + d.p_b + i);
+    if (t == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    if (tid < 32) {   // 512 columns: 256 per group (one CTA per SM: the shared-memory footprint excludes a second one)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_sync_before_mma();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem = tmem_base + (uint32_t)grp * 256u;
     const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t idesc192 = (1u << 4) | (1u << 7) | (1u << 10) | ((192u >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t a_hi = smem_u32(sm + d.off_ahi), a_lo = smem_u32(sm + d.off_alo);
+    const uint32_t a_hi = smem_u32(a_hi_p), a_lo = smem_u32(a_lo_p);
     uint32_t parity = 0;
     const int dk = Fs / d.H;
     const float inv = 1.0f / sqrtf((float)dk);
 
     const int tiles = (E + 7) / 8;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int tile = 2 * blockIdx.x + grp; tile < tiles; tile += 2 * gridDim.x) {
         const int e0 = tile * 8, nenv = min(8, E - e0);
         // ---- observations of the tile (contiguous in HBM) ----
-        for (int i = tid; i < 8 * nin; i += 128) s_x[i] = i < nenv * nin ? __ldg(obs + (size_t)e0 * nin + i) : 0.f;
-        __syncthreads();
+        for (int i = t; i < 8 * nin; i += 128) s_x[i] = i < nenv * nin ? __ldg(obs + (size_t)e0 * nin + i) : 0.f;
+        group_sync(grp);
         // ---- A1[r][k] (K = 16): features of entity `ent` of observation `env`, zero padded ----
         {
             uint32_t ph[8], pl[8];
@@ -605,16 +619,16 @@ __global__ void __launch_bounds__(128, 1) k_qnet_ego_tc(TcEgo d, const float* __
                 ph[q2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
                 pl[q2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
             }
-            const uint32_t o0 = canon_off(tid, 0, 16), o1 = canon_off(tid, 8, 16);
-            *reinterpret_cast<uint4*>(sm + d.off_ahi + o0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            *reinterpret_cast<uint4*>(sm + d.off_ahi + o1) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-            *reinterpret_cast<uint4*>(sm + d.off_alo + o0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-            *reinterpret_cast<uint4*>(sm + d.off_alo + o1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            const uint32_t o0 = canon_off(t, 0, 16), o1 = canon_off(t, 8, 16);
+            *reinterpret_cast<uint4*>(a_hi_p + o0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4*>(a_hi_p + o1) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+            *reinterpret_cast<uint4*>(a_lo_p + o0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            *reinterpret_cast<uint4*>(a_lo_p + o1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
         }
         // ---- two embedding layers: MMA (N = 128: others | ego) + epilogue selecting the row's half ----
         for (int layer = 0; layer < 2; ++layer) {
-            tc_sync_before_mma();
-            if (tid == 0) {
+            tc_group_sync_before_mma(grp);
+            if (t == 0) {
                 if (layer == 0) issue_layer(tmem, a_hi, a_lo, smem_u32(sm + d.off_b1hi), smem_u32(sm + d.off_b1lo), 16, idesc128);
                 else issue_layer(tmem, a_hi, a_lo, smem_u32(sm + d.off_b2hi), smem_u32(sm + d.off_b2lo), 64, idesc128);
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -646,9 +660,9 @@ __global__ void __launch_bounds__(128, 1) k_qnet_ego_tc(TcEgo d, const float* __
                         ph[q2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
                         pl[q2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
                     }
-                    const uint32_t o = canon_off(tid, c0 + g * 8, 64);
-                    *reinterpret_cast<uint4*>(sm + d.off_ahi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                    *reinterpret_cast<uint4*>(sm + d.off_alo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    const uint32_t o = canon_off(t, c0 + g * 8, 64);
+                    *reinterpret_cast<uint4*>(a_hi_p + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                    *reinterpret_cast<uint4*>(a_lo_p + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     if (layer == 1 && ent == 0) {   // the ego's embedding: residual of the attention block
 #pragma unroll
                         for (int q2 = 0; q2 < 8; ++q2) s_ego[env * 64 + c0 + g * 8 + q2] = hv[q2];
@@ -657,8 +671,8 @@ __global__ void __launch_bounds__(128, 1) k_qnet_ego_tc(TcEgo d, const float* __
             }
         }
         // ---- K | V | Q = input_all x [W_k ; W_v ; W_q]^T ----
-        tc_sync_before_mma();
-        if (tid == 0) {
+        tc_group_sync_before_mma(grp);
+        if (t == 0) {
             issue_layer(tmem, a_hi, a_lo, smem_u32(sm + d.off_b3hi), smem_u32(sm + d.off_b3lo), 64, idesc192);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
         }
@@ -674,7 +688,7 @@ __global__ void __launch_bounds__(128, 1) k_qnet_ego_tc(TcEgo d, const float* __
                 for (int j = 0; j < 32; ++j) { s_q[env * 64 + j] = __uint_as_float(v0[j]); s_q[env * 64 + 32 + j] = __uint_as_float(v1[j]); }
             }
         }
-        __syncthreads();
+        group_sync(grp);
         // ---- attention (models.py:370-388): scores / sqrt(d_k), masked_fill(-1e9), softmax over the entities ----
         float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;  // per head probability of this row (H <= 4, d_k = 64 >> hshift... a power of two)
         const int hshift = d.H == 1 ? 6 : d.H == 2 ? 5 : 4;
@@ -716,7 +730,7 @@ __global__ void __launch_bounds__(128, 1) k_qnet_ego_tc(TcEgo d, const float* __
             uint32_t v0[32], v1[32];
             TT_TMEM_LD32(v0, tmem_row + 64u);
             TT_TMEM_LD32(v1, tmem_row + 96u);
-            float* row = scratch + tid * 64;
+            float* row = scratch + t * 64;
 #pragma unroll
             for (int c = 0; c < 64; c += 4) {
                 float o[4];
@@ -729,7 +743,7 @@ __global__ void __launch_bounds__(128, 1) k_qnet_ego_tc(TcEgo d, const float* __
                 *reinterpret_cast<float4*>(row + c) = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
-        __syncthreads();
+        group_sync(grp);
         {   // value[env][c] = sum over the entities; thread = (env, 4 columns)
             const int j = ent;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -739,18 +753,18 @@ __global__ void __launch_bounds__(128, 1) k_qnet_ego_tc(TcEgo d, const float* __
             }
             *reinterpret_cast<float4*>(s_val + env * 64 + 4 * j) = a;
         }
-        __syncthreads();
+        group_sync(grp);
         // ---- (attention_combine(value) + ego) / 2 (models.py:193), output MLP (models.py:69-76), action ----
-        tile_dense8(s_val, s_wc, nullptr, Fs, Fs, false, s_t0, tid);
-        __syncthreads();
+        tile_dense8(s_val, s_wc, nullptr, Fs, Fs, false, s_t0, t);
+        group_sync(grp);
         for (int c = ent * 4; c < ent * 4 + 4; ++c) s_t0[env * 64 + c] = (s_t0[env * 64 + c] + s_ego[env * 64 + c]) / 2.f;
-        __syncthreads();
-        tile_dense8(s_t0, s_ow1, s_ob1, Fs, Fs, true, s_t1, tid);
-        __syncthreads();
-        tile_dense8(s_t1, s_ow2, s_ob2, Fs, Fs, true, s_t0, tid);
-        __syncthreads();
-        tile_dense8(s_t0, s_pw, s_pb, Fs, d.A, false, s_t1, tid);
-        __syncthreads();
+        group_sync(grp);
+        tile_dense8(s_t0, s_ow1, s_ob1, Fs, Fs, true, s_t1, t);
+        group_sync(grp);
+        tile_dense8(s_t1, s_ow2, s_ob2, Fs, Fs, true, s_t0, t);
+        group_sync(grp);
+        tile_dense8(s_t0, s_pw, s_pb, Fs, d.A, false, s_t1, t);
+        group_sync(grp);
         if (ent == 0 && env < nenv) {
             const int e = e0 + env;
             const float* qv = s_t1 + env * 64;
@@ -758,9 +772,11 @@ __global__ void __launch_bounds__(128, 1) k_qnet_ego_tc(TcEgo d, const float* __
             actions[e] = select_action(qv, d.A, eps, u_inj ? u_inj[e] : uniform_for(seed, step, e));
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        group_sync(grp);
     }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256u) : "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();   // both groups are done with their accumulators
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
 }
 
 }  // namespace
@@ -897,12 +913,14 @@ int ttrl_qnet_create(const ttrl_qnet_desc* desc, const float* weights_host, int6
         t.off_b2lo = o; o += up(128 * 64 * 2);
         t.off_b3hi = o; o += up(192 * 64 * 2);
         t.off_b3lo = o; o += up(192 * 64 * 2);
-        t.off_ahi = o; o += 128 * 64 * 2;   // hi and lo contiguous: together they are the [128][64] fp32 scratch
-        t.off_alo = o; o += 128 * 64 * 2;
-        t.off_f32 = o; o += up((int)sizeof(float) * (3 * 64 * 64 + 64 * 4 + 6 * 64 + 16));
-        t.off_x = o; o += up((int)sizeof(float) * 8 * nin);
-        t.off_small = o; o += up((int)sizeof(float) * 5 * 8 * 64);
-        t.off_bar = o; o += 16;
+        auto up16 = [](int x) { return (x + 15) / 16 * 16; };
+        t.off_ahi = o; o += 2 * (2 * 128 * 64 * 2);   // per group: hi and lo contiguous, together the [128][64] fp32 scratch
+        t.off_f32 = o; o += up16((int)sizeof(float) * (3 * 64 * 64 + 64 * 4 + 6 * 64 + 16));
+        t.x_stride = up16((int)sizeof(float) * 8 * nin);
+        t.off_x = o; o += 2 * t.x_stride;
+        t.small_stride = (int)sizeof(float) * 3 * 8 * 64;
+        t.off_small = o; o += 2 * t.small_stride;
+        t.off_bar = o; o += 32;                        // two mbarriers + the TMEM address
         t.total = o;
         if (t.total <= 227 * 1024 &&
             cudaFuncSetAttribute(k_qnet_ego_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, t.total) == cudaSuccess)
@@ -947,10 +965,10 @@ static int qnet_launch(ttrl_qnet* q, const float* obs_dev, int E, double eps, ui
                        int32_t* actions_dev, float* q_dev, void* stream) {
     QCK(cudaSetDevice(q->device));
     if (q->mode == TTRL_QNET_MODE_TENSOR && q->net.d.type == TTRL_QNET_EGO_ATTENTION) {
-        int grid = (E + 7) / 8;
+        int grid = (E + 15) / 16;   // two tiles of 8 observations in flight per CTA
         if (grid > q->n_sms) grid = q->n_sms;
         if (grid < 1) grid = 1;
-        k_qnet_ego_tc<<<grid, 128, q->tce.total, (cudaStream_t)stream>>>(q->tce, q->d_weights, obs_dev, E, eps, seed, step, u_dev, actions_dev, q_dev);
+        k_qnet_ego_tc<<<grid, 256, q->tce.total, (cudaStream_t)stream>>>(q->tce, q->d_weights, obs_dev, E, eps, seed, step, u_dev, actions_dev, q_dev);
         q->launches++;
         QCK(cudaGetLastError());
         return 0;
