@@ -278,9 +278,14 @@ __global__ void __launch_bounds__(kWarps * 32) k_qnet_fp32(QnetDev net, const fl
 struct TcMlp {
     int nin, K1, H1, H2, A;                              // K1 = nin rounded up to 16
     int w1, b1, w2, b2, w3, b3;                          // offsets into the fp32 blob ([in][out] matrices)
-    int off_w1hi, off_w1lo, off_w2hi, off_w2lo, off_ahi, off_alo, off_f32, off_bar, total;  // shared-memory bytes
+    // shared-memory bytes.  [0, img_bytes) is the WEIGHT IMAGE: split BF16 canonical B operands + the fp32 tail, prepared once
+    // per weight update in HBM (k_qnet_mlp_prep) and brought in by every CTA with bulk (TMA) copies
+    int off_w1hi, off_w1lo, off_w2hi, off_w2lo, off_f32, img_bytes, off_ahi, off_alo, off_raw, slot_bytes, n_slots, off_bar, total;
     int tmem_cols;
 };
+constexpr int kMlpSlotRows = 32;   // observations per slot of the raw-observation ring (a quarter of a 128-row tile)
+constexpr int kMlpMaxSlots = 4;
+constexpr int kMlpThreads = 512, kMlpColGroups = kMlpThreads / 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
@@ -299,11 +304,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy HBM -> shared memory on the TMA unit (SASS UBLKCP); completion counts `bytes` on the mbarrier.  16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
     const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
     hi = __bfloat16_as_ushort(h);
     lo = __bfloat16_as_ushort(l);
+}
+// two values -> packed BF16x2 (hi pair, lo pair), the first value in the low half: one packed conversion per pair
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // canonical K-major no-swizzle offset (bytes) of element (row, k) in an operand with K columns
 __device__ __forceinline__ uint32_t canon_off(int row, int k, int K) {
@@ -323,69 +346,133 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint
     }
 }
 
-__global__ void __launch_bounds__(128, 1) k_qnet_mlp_tc(TcMlp d, const float* __restrict__ weights, const float* __restrict__ obs, int E,
+#define TT_TMEM_LD32(v, addr)                                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                    \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), \
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),  \
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),  \
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                          \
+                 : "r"(addr) : "memory");                                                                                    \
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+
+// The weight image of the tensor-core MLP: what k_qnet_mlp_tc keeps in shared memory bytes [0, img_bytes), laid out in HBM.
+__global__ void k_qnet_mlp_prep(TcMlp d, const float* __restrict__ weights, unsigned char* __restrict__ img) {
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = t0; i < d.K1 * d.H1; i += stride) {   // B1[n][k] = W1t[k][n]; coalesced reads along n
+        const int k = i / d.H1, n = i - k * d.H1;
+        unsigned short hi, lo;
+        split_bf16(k < d.nin ? weights[d.w1 + k * d.H1 + n] : 0.f, hi, lo);
+        const uint32_t o = canon_off(n, k, d.K1);
+        *reinterpret_cast<unsigned short*>(img + d.off_w1hi + o) = hi;
+        *reinterpret_cast<unsigned short*>(img + d.off_w1lo + o) = lo;
+    }
+    for (int i = t0; i < d.H1 * d.H2; i += stride) {   // B2[n][k] = W2t[k][n]
+        const int k = i / d.H2, n = i - k * d.H2;
+        unsigned short hi, lo;
+        split_bf16(weights[d.w2 + k * d.H2 + n], hi, lo);
+        const uint32_t o = canon_off(n, k, d.H1);
+        *reinterpret_cast<unsigned short*>(img + d.off_w2hi + o) = hi;
+        *reinterpret_cast<unsigned short*>(img + d.off_w2lo + o) = lo;
+    }
+    float* f32 = reinterpret_cast<float*>(img + d.off_f32);   // b1[H1] b2[H2] W3[A][H2] b3[A]
+    for (int i = t0; i < d.H1; i += stride) f32[i] = weights[d.b1 + i];
+    for (int i = t0; i < d.H2; i += stride) f32[d.H1 + i] = weights[d.b2 + i];
+    for (int i = t0; i < d.A * d.H2; i += stride) { const int a = i / d.H2, k = i - a * d.H2; f32[d.H1 + d.H2 + i] = weights[d.w3 + k * d.A + a]; }
+    for (int i = t0; i < d.A; i += stride) f32[d.H1 + d.H2 + d.A * d.H2 + i] = weights[d.b3 + i];
+}
+
+// Staging is a TMA pipeline: thread 0 streams the raw fp32 observations of the CTA's tiles, a quarter tile (32 rows, contiguous in
+// HBM) per bulk copy, through a ring of n_slots shared-memory slots, one mbarrier each; the 128 threads turn a landed slot into the
+// split-BF16 canonical A operand from shared memory (conflict-free reads: a warp reads 32 rows at one column, row stride nin is odd for
+// the shipped 105) and the slot is refilled with the quarter n_slots ahead -- so the loads of the next tile run under the MMAs and
+// epilogues of this one.  A ragged last quarter (or an unaligned observation pointer) takes guarded global loads instead.
+__global__ void __launch_bounds__(kMlpThreads, 1) k_qnet_mlp_tc(TcMlp d, const unsigned char* __restrict__ img, const float* __restrict__ obs, int E,
                                                          double eps, uint64_t seed, uint64_t step, const double* __restrict__ u_inj,
                                                          int32_t* __restrict__ actions, float* __restrict__ qout) {
     extern __shared__ __align__(1024) unsigned char sm[];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    // 16 warps: warp w owns TMEM lanes (= tile rows) 32 (w % 4) .. + 32 and, in the epilogues, the 32-column chunks cg, cg + 4, ..
+    // (cg = w / 4): the four warps of a lane quadrant split the columns of a row, four warps per scheduler hide the TMEM / shared
+    // memory latencies one warp per scheduler could not (profiles/r2_qnet_mlp_raw.txt: 10 % issue slots with 4 warps)
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, cg = tid >> 7;
     float* f32 = reinterpret_cast<float*>(sm + d.off_f32);   // b1[H1] b2[H2] W3[A][H2] b3[A]
     float* sb1 = f32; float* sb2 = sb1 + d.H1; float* sw3 = sb2 + d.H2; float* sb3 = sw3 + d.A * d.H2;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + d.off_bar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + d.off_bar + 8);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + d.off_bar);               // MMA completion
+    const uint32_t bar_w = smem_u32(bar) + 8, bar_full = smem_u32(bar) + 16;   // weight image; ring slots
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + d.off_bar + 16 + 8 * kMlpMaxSlots);
+    const int NS = d.n_slots, tiles = (E + 127) / 128;
+    const bool tma = NS >= 2 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
+    // quarter g of this CTA: tile blockIdx.x + (g / 4) gridDim.x, rows 32 (g % 4) .. + 32; only whole quarters go through the ring
+    auto quarter_full = [&](int g) { const int tl = blockIdx.x + (g >> 2) * gridDim.x; return tl < tiles && tl * 128 + (g & 3) * kMlpSlotRows + kMlpSlotRows <= E; };
+    auto issue_quarter = [&](int g) {
+        const int slot = g % NS, tl = blockIdx.x + (g >> 2) * gridDim.x;
+        mbar_expect_tx(bar_full + 8 * slot, (uint32_t)d.slot_bytes);
+        bulk_g2s(smem_u32(sm + d.off_raw + slot * d.slot_bytes), obs + (size_t)(tl * 128 + (g & 3) * kMlpSlotRows) * d.nin, (uint32_t)d.slot_bytes, bar_full + 8 * slot);
+    };
 
-    // ---- one-time setup: weights -> split BF16 canonical B operands; biases / head -> fp32 ----
-    for (int i = tid; i < d.H1 * d.K1; i += 128) {   // B1[n][k] = W1t[k][n]
-        const int n = i / d.K1, k = i - n * d.K1;
-        unsigned short hi, lo;
-        split_bf16(k < d.nin ? __ldg(weights + d.w1 + k * d.H1 + n) : 0.f, hi, lo);
-        const uint32_t o = canon_off(n, k, d.K1);
-        *reinterpret_cast<unsigned short*>(sm + d.off_w1hi + o) = hi;
-        *reinterpret_cast<unsigned short*>(sm + d.off_w1lo + o) = lo;
-    }
-    for (int i = tid; i < d.H2 * d.H1; i += 128) {   // B2[n][k] = W2t[k][n]
-        const int n = i / d.H1, k = i - n * d.H1;
-        unsigned short hi, lo;
-        split_bf16(__ldg(weights + d.w2 + k * d.H2 + n), hi, lo);
-        const uint32_t o = canon_off(n, k, d.H1);
-        *reinterpret_cast<unsigned short*>(sm + d.off_w2hi + o) = hi;
-        *reinterpret_cast<unsigned short*>(sm + d.off_w2lo + o) = lo;
-    }
-    for (int i = tid; i < d.H1; i += 128) sb1[i] = __ldg(weights + d.b1 + i);
-    for (int i = tid; i < d.H2; i += 128) sb2[i] = __ldg(weights + d.b2 + i);
-    for (int i = tid; i < d.A * d.H2; i += 128) { const int a = i / d.H2, k = i - a * d.H2; sw3[i] = __ldg(weights + d.w3 + k * d.A + a); }
-    for (int i = tid; i < d.A; i += 128) sb3[i] = __ldg(weights + d.b3 + i);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
+        mbar_init(smem_u32(bar), 1);
+        mbar_init(bar_w, 1);
+        for (int k = 0; k < kMlpMaxSlots; ++k) mbar_init(bar_full + 8 * k, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // ---- one-time setup: the weight image (split BF16 canonical B operands, biases, head) by bulk copies ----
+        mbar_expect_tx(bar_w, (uint32_t)d.img_bytes);
+        for (int o = 0; o < d.img_bytes; o += 32768) bulk_g2s(smem_u32(sm + o), img + o, (uint32_t)min(32768, d.img_bytes - o), bar_w);
+        if (tma) for (int g = 0; g < NS; ++g) if (quarter_full(g)) issue_quarter(g);
     }
     if (warp == 0) {  // TMEM allocation by one warp; the address lands in shared memory
+        __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)d.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mbar_wait(bar_w, 0);
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+    const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 TMEM lanes
     // instruction descriptor: D = F32 [4,6), A = B = BF16 [7,10) [10,13), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
     const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d.H1 >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d.H2 >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_hi = smem_u32(sm + d.off_ahi), a_lo = smem_u32(sm + d.off_alo);
-    uint32_t parity = 0;
+    uint32_t parity = 0, slot_phase = 0;
+    int gq = 0;   // running quarter index of this CTA
 
-    const int tiles = (E + 127) / 128;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int e0 = tile * 128, rows = min(128, E - e0);
-        // ---- A1 = split(obs tile) in the K1 layout; coalesced reads of the contiguous rows ----
-        const float* src = obs + (size_t)e0 * d.nin;
-        for (int i = tid; i < 128 * d.K1; i += 128) {
-            const int r = i / d.K1, k = i - r * d.K1;
-            unsigned short hi, lo;
-            split_bf16((r < rows && k < d.nin) ? __ldg(src + r * d.nin + k) : 0.f, hi, lo);
-            const uint32_t o = canon_off(r, k, d.K1);
-            *reinterpret_cast<unsigned short*>(sm + d.off_ahi + o) = hi;
-            *reinterpret_cast<unsigned short*>(sm + d.off_alo + o) = lo;
+        // ---- A1 = split(obs tile) in the K1 layout, a quarter at a time; task = (8 columns, row), row fastest ----
+        for (int q = 0; q < 128 / kMlpSlotRows; ++q, ++gq) {
+            const int slot = tma ? gq % NS : 0;
+            const bool landed = tma && e0 + q * kMlpSlotRows + kMlpSlotRows <= E;
+            const float* raw = reinterpret_cast<const float*>(sm + d.off_raw + slot * d.slot_bytes);
+            if (landed) { mbar_wait(bar_full + 8 * slot, (slot_phase >> slot) & 1u); slot_phase ^= 1u << slot; }
+            for (int i = tid; i < kMlpSlotRows * (d.K1 >> 3); i += kMlpThreads) {
+                const int r = i & (kMlpSlotRows - 1), k0 = (i / kMlpSlotRows) * 8, arow = q * kMlpSlotRows + r;
+                float x[8];
+                if (landed) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = k0 + j < d.nin ? raw[r * d.nin + k0 + j] : 0.f;
+                } else {
+                    const float* src = obs + (size_t)(e0 + arow) * d.nin;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = (arow < rows && k0 + j < d.nin) ? __ldg(src + k0 + j) : 0.f;
+                }
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    split_bf16x2(x[2 * j], x[2 * j + 1], ph[j], pl[j]);
+                }
+                const uint32_t o = canon_off(arow, k0, d.K1);
+                *reinterpret_cast<uint4*>(sm + d.off_ahi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4*>(sm + d.off_alo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
+            if (tma) {
+                __syncthreads();   // every thread has read the slot: refill it with the quarter n_slots ahead
+                if (tid == 0 && quarter_full(gq + NS)) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue_quarter(gq + NS);
+                }
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -398,8 +485,8 @@ __global__ void __launch_bounds__(128, 1) k_qnet_mlp_tc(TcMlp d, const float* __
         mbar_wait(smem_u32(bar), parity);
         parity ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue 1: h1 = relu(acc + b1) -> split -> A2 (K = H1 layout); thread t = row t ----
-        for (int c0 = 0; c0 < d.H1; c0 += 32) {
+        // ---- epilogue 1: h1 = relu(acc + b1) -> split -> A2 (K = H1 layout); thread = (row, column group) ----
+        for (int c0 = cg * 32; c0 < d.H1; c0 += 32 * kMlpColGroups) {
             uint32_t v[32];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -411,16 +498,13 @@ __global__ void __launch_bounds__(128, 1) k_qnet_mlp_tc(TcMlp d, const float* __
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int g = 0; g < 4; ++g) {  // 8 columns = one 16-byte row of a core matrix
+                if (c0 + g * 8 >= d.H1) break;   // widths are multiples of 16, chunks of 32
                 uint32_t ph[4], pl[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    unsigned short h0, l0, h1, l1;
-                    split_bf16(fmaxf(__uint_as_float(v[g * 8 + 2 * q]) + sb1[c0 + g * 8 + 2 * q], 0.f), h0, l0);
-                    split_bf16(fmaxf(__uint_as_float(v[g * 8 + 2 * q + 1]) + sb1[c0 + g * 8 + 2 * q + 1], 0.f), h1, l1);
-                    ph[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                    pl[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                    split_bf16x2(fmaxf(__uint_as_float(v[g * 8 + 2 * q]) + sb1[c0 + g * 8 + 2 * q], 0.f), fmaxf(__uint_as_float(v[g * 8 + 2 * q + 1]) + sb1[c0 + g * 8 + 2 * q + 1], 0.f), ph[q], pl[q]);
                 }
-                const uint32_t o = canon_off(tid, c0 + g * 8, d.H1);
+                const uint32_t o = canon_off(row, c0 + g * 8, d.H1);
                 *reinterpret_cast<uint4*>(sm + d.off_ahi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                 *reinterpret_cast<uint4*>(sm + d.off_alo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
@@ -436,27 +520,37 @@ __global__ void __launch_bounds__(128, 1) k_qnet_mlp_tc(TcMlp d, const float* __
         mbar_wait(smem_u32(bar), parity);
         parity ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue 2: h2 = relu(acc + b2); head (A outputs) and action selection on the CUDA cores ----
-        float q[16];
-        for (int a = 0; a < d.A; ++a) q[a] = sb3[a];
-        for (int c0 = 0; c0 < d.H2; c0 += 32) {
-            uint32_t v[32];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                         : "r"(tmem_row + (uint32_t)c0) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // ---- epilogue 2: h2 = relu(acc + b2); head (A outputs, 4 at a time in registers) per column group, summed through the
+        // free A operand; action selection on the CUDA cores ----
+        float* part = reinterpret_cast<float*>(sm + d.off_ahi);   // [column group][row][A rounded up to 4]
+        const int A4 = (d.A + 3) & ~3;
+        for (int a0 = 0; a0 < d.A; a0 += 4) {
+            float q4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c0 = cg * 32; c0 < d.H2; c0 += 32 * kMlpColGroups) {
+                uint32_t v[32];
+                TT_TMEM_LD32(v, tmem_row + (uint32_t)c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float h = fmaxf(__uint_as_float(v[j]) + sb2[c0 + j], 0.f);
-                for (int a = 0; a < d.A; ++a) q[a] = fmaf(h, sw3[a * d.H2 + c0 + j], q[a]);
+                for (int j = 0; j < 32; ++j) {
+                    if (c0 + j >= d.H2) break;
+                    const float h = fmaxf(__uint_as_float(v[j]) + sb2[c0 + j], 0.f);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (a0 + u < d.A) q4[u] = fmaf(h, sw3[(a0 + u) * d.H2 + c0 + j], q4[u]);
+                }
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (a0 + u < d.A) part[(cg * 128 + row) * A4 + a0 + u] = q4[u];
         }
-        if (tid < rows) {
-            const int e = e0 + tid;
+        __syncthreads();
+        if (cg == 0 && row < rows) {
+            const int e = e0 + row;
+            float q[16];
+            for (int a = 0; a < d.A; ++a) {
+                float sum = sb3[a];
+                for (int g = 0; g < kMlpColGroups; ++g) sum += part[(g * 128 + row) * A4 + a];
+                q[a] = sum;
+            }
             if (qout) for (int a = 0; a < d.A; ++a) qout[(size_t)e * d.A + a] = q[a];
             actions[e] = select_action(q, d.A, eps, u_inj ? u_inj[e] : uniform_for(seed, step, e));
         }
@@ -486,15 +580,6 @@ struct TcEgo {
     int off_b1hi, off_b1lo, off_b2hi, off_b2lo, off_b3hi, off_b3lo, off_ahi, off_f32, off_x, x_stride, off_small, small_stride, off_bar, total;
 };
 
-#define TT_TMEM_LD32(v, addr)                                                                                              \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                    \
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), \
-                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),  \
-                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),  \
-                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                          \
-                 : "r"(addr) : "memory");                                                                                    \
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 
 __device__ __forceinline__ void tc_sync_before_mma() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -602,22 +687,33 @@ __global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __
     const float inv = 1.0f / sqrtf((float)dk);
 
     const int tiles = (E + 7) / 8;
+    constexpr int kEgoPre = 15;   // 8 observations x (15 entities x 16 features) / 128 threads
+    float pre[kEgoPre];
+    auto fetch_obs = [&](int tl) {
+        const int valid = tl < tiles ? min(8, E - tl * 8) * nin : 0;
+#pragma unroll
+        for (int u = 0; u < kEgoPre; ++u) {
+            const int i = t + 128 * u;
+            pre[u] = i < valid ? __ldg(obs + (size_t)tl * 8 * nin + i) : 0.f;
+        }
+    };
+    fetch_obs(2 * blockIdx.x + grp);
     for (int tile = 2 * blockIdx.x + grp; tile < tiles; tile += 2 * gridDim.x) {
         const int e0 = tile * 8, nenv = min(8, E - e0);
-        // ---- observations of the tile (contiguous in HBM) ----
-        for (int i = t; i < 8 * nin; i += 128) s_x[i] = i < nenv * nin ? __ldg(obs + (size_t)e0 * nin + i) : 0.f;
+        // ---- observations of the tile (contiguous in HBM): fetched into registers one tile ahead, so that the load latency
+        // runs under the previous tile's work ----
+#pragma unroll
+        for (int u = 0; u < kEgoPre; ++u)
+            if (t + 128 * u < 8 * nin) s_x[t + 128 * u] = pre[u];
         group_sync(grp);
+        fetch_obs(tile + 2 * gridDim.x);
         // ---- A1[r][k] (K = 16): features of entity `ent` of observation `env`, zero padded ----
         {
             uint32_t ph[8], pl[8];
 #pragma unroll
             for (int q2 = 0; q2 < 8; ++q2) {
-                unsigned short h0, l0, h1, l1;
                 const int k0 = 2 * q2, k1 = 2 * q2 + 1;
-                split_bf16((ent < d.NE && k0 < d.Fe) ? s_x[env * nin + ent * d.Fe + k0] : 0.f, h0, l0);
-                split_bf16((ent < d.NE && k1 < d.Fe) ? s_x[env * nin + ent * d.Fe + k1] : 0.f, h1, l1);
-                ph[q2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                pl[q2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                split_bf16x2((ent < d.NE && k0 < d.Fe) ? s_x[env * nin + ent * d.Fe + k0] : 0.f, (ent < d.NE && k1 < d.Fe) ? s_x[env * nin + ent * d.Fe + k1] : 0.f, ph[q2], pl[q2]);
             }
             const uint32_t o0 = canon_off(t, 0, 16), o1 = canon_off(t, 8, 16);
             *reinterpret_cast<uint4*>(a_hi_p + o0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -654,11 +750,7 @@ __global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __
                     }
 #pragma unroll
                     for (int q2 = 0; q2 < 4; ++q2) {
-                        unsigned short h0, l0, h1, l1;
-                        split_bf16(hv[2 * q2], h0, l0);
-                        split_bf16(hv[2 * q2 + 1], h1, l1);
-                        ph[q2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                        pl[q2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                        split_bf16x2(hv[2 * q2], hv[2 * q2 + 1], ph[q2], pl[q2]);
                     }
                     const uint32_t o = canon_off(t, c0 + g * 8, 64);
                     *reinterpret_cast<uint4*>(a_hi_p + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -784,6 +876,9 @@ __global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __
 struct ttrl_qnet {
     QnetDev net;
     float* d_weights = nullptr;
+    unsigned char* d_img = nullptr;   // tensor-core MLP: the weight image (TcMlp), rebuilt when the weights change
+    bool img_dirty = true;            // set by set_weights; stays set once the blob pointer has been handed out (ttrl_qnet_weights_dev)
+    bool external_writer = false;
     int device = 0;
     int smem_bytes = 0;
     int n_sms = 0;
@@ -874,22 +969,31 @@ int ttrl_qnet_create(const ttrl_qnet_desc* desc, const float* weights_host, int6
         TcMlp& t = q->tc;
         t.nin = nin; t.K1 = (nin + 15) / 16 * 16; t.H1 = desc->hidden[0]; t.H2 = desc->hidden[1]; t.A = desc->n_actions;
         t.w1 = n.out[0].w_off; t.b1 = n.out[0].b_off; t.w2 = n.out[1].w_off; t.b2 = n.out[1].b_off; t.w3 = n.out[2].w_off; t.b3 = n.out[2].b_off;
-        auto up = [](int x) { return (x + 1023) / 1024 * 1024; };
+        auto up = [](int x) { return (x + 127) / 128 * 128; };
         int o = 0;
         t.off_w1hi = o; o += up(t.H1 * t.K1 * 2);
         t.off_w1lo = o; o += up(t.H1 * t.K1 * 2);
         t.off_w2hi = o; o += up(t.H2 * t.H1 * 2);
         t.off_w2lo = o; o += up(t.H2 * t.H1 * 2);
+        t.off_f32 = o; o += up((int)sizeof(float) * (t.H1 + t.H2 + t.A * t.H2 + t.A));
+        t.img_bytes = o;
         const int ka = t.K1 > t.H1 ? t.K1 : t.H1;
         t.off_ahi = o; o += up(128 * ka * 2);
         t.off_alo = o; o += up(128 * ka * 2);
-        t.off_f32 = o; o += up((int)sizeof(float) * (t.H1 + t.H2 + t.A * t.H2 + t.A));
-        t.off_bar = o; o += 16;
+        const int part_bytes = kMlpColGroups * 128 * ((t.A + 3) & ~3) * (int)sizeof(float);   // epilogue 2 reuses the A operand
+        if (o - t.off_ahi < part_bytes) o = t.off_ahi + up(part_bytes);
+        t.slot_bytes = kMlpSlotRows * nin * (int)sizeof(float);   // a multiple of 128
+        t.off_raw = o;
+        const int room = 227 * 1024 - 64 - o;
+        t.n_slots = room < 2 * t.slot_bytes ? 0 : room / t.slot_bytes > kMlpMaxSlots ? kMlpMaxSlots : room / t.slot_bytes;
+        o += t.n_slots * t.slot_bytes;
+        t.off_bar = o; o += 64;                                   // MMA, weight-image and slot mbarriers, the TMEM address
         t.total = o;
         const int mx = t.H1 > t.H2 ? t.H1 : t.H2;
         t.tmem_cols = mx <= 32 ? 32 : mx <= 64 ? 64 : mx <= 128 ? 128 : 256;
         if (t.total <= 227 * 1024 &&
-            cudaFuncSetAttribute(k_qnet_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, t.total) == cudaSuccess)
+            cudaFuncSetAttribute(k_qnet_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, t.total) == cudaSuccess &&
+            cudaMalloc(&q->d_img, t.img_bytes) == cudaSuccess && cudaMemset(q->d_img, 0, t.img_bytes) == cudaSuccess)
             q->tc_ok = true;
         (void)cudaGetLastError();
     }
@@ -948,15 +1052,20 @@ int ttrl_qnet_set_weights(ttrl_qnet* q, const float* weights, int64_t n_weights,
     QCK(cudaMemcpyAsync(q->d_weights, weights, sizeof(float) * n_weights, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                         (cudaStream_t)stream));
     if (!on_device) QCK(cudaStreamSynchronize((cudaStream_t)stream));  // the host buffer may be reused by the caller
+    q->img_dirty = true;
     return 0;
 }
 
-float* ttrl_qnet_weights_dev(ttrl_qnet* q) { return q ? q->d_weights : nullptr; }
+float* ttrl_qnet_weights_dev(ttrl_qnet* q) {
+    if (q) q->external_writer = true;   // the caller's kernels update the blob in place: derived images are rebuilt on every launch
+    return q ? q->d_weights : nullptr;
+}
 
 int ttrl_qnet_destroy(ttrl_qnet* q) {
     if (!q) return 0;
     cudaSetDevice(q->device);
     cudaFree(q->d_weights);
+    cudaFree(q->d_img);
     delete q;
     return 0;
 }
@@ -977,7 +1086,14 @@ static int qnet_launch(ttrl_qnet* q, const float* obs_dev, int E, double eps, ui
         int grid = (E + 127) / 128;
         if (grid > q->n_sms) grid = q->n_sms;
         if (grid < 1) grid = 1;
-        k_qnet_mlp_tc<<<grid, 128, q->tc.total, (cudaStream_t)stream>>>(q->tc, q->d_weights, obs_dev, E, eps, seed, step, u_dev, actions_dev, q_dev);
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        QCK(cudaStreamIsCapturing((cudaStream_t)stream, &cap));   // a captured launch is replayed after later weight updates
+        if (q->img_dirty || q->external_writer || cap != cudaStreamCaptureStatusNone) {
+            k_qnet_mlp_prep<<<32, 256, 0, (cudaStream_t)stream>>>(q->tc, q->d_weights, q->d_img);
+            q->launches++;
+            if (cap == cudaStreamCaptureStatusNone) q->img_dirty = false;
+        }
+        k_qnet_mlp_tc<<<grid, kMlpThreads, q->tc.total, (cudaStream_t)stream>>>(q->tc, q->d_img, obs_dev, E, eps, seed, step, u_dev, actions_dev, q_dev);
         q->launches++;
         QCK(cudaGetLastError());
         return 0;
