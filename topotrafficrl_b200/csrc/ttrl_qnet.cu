@@ -587,41 +587,63 @@ __device__ __forceinline__ void tc_sync_before_mma() {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// The ego kernel runs TWO tiles per CTA, one per group of 4 warps (threads 0..127 / 128..255), each with its own A operand,
+// The ego kernel runs TWO tiles per CTA, one per group of 8 warps (threads 0..255 / 256..511), each with its own A operand,
 // accumulators (256 TMEM columns), mbarrier and named barrier (ids 1 and 2): while one group waits for its MMA or runs an
 // epilogue, the other one stages, issues or reads back -- the tensor pipe and the CUDA cores of the SM overlap across the two tiles.
-__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory"); }
+// Inside a group, thread (row, cg) owns tile row `row` (= TMEM lane) and the 32-column half `cg` of every 64-wide quantity, so
+// 16 warps (four per scheduler) share the epilogues (profiles/r2_qnet_ego_raw.txt: 28 % issue slots with 8 warps).
+constexpr int kEgoGT = 256;
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "n"(kEgoGT) : "memory"); }
 __device__ __forceinline__ void tc_group_sync_before_mma(int grp) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     group_sync(grp);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// out[env][n] = act(bias[n] + sum_k in[env][k] * Wt[k][n]) for the 8 observations of a tile; thread = (env, 4 columns)
-__device__ __forceinline__ void tile_dense8(const float* in, const float* Wt, const float* bias, int K, int N, bool relu, float* out, int tid) {
-    const int env = tid >> 4, j = tid & 15;
+// out[env][n] = act(bias[n] + sum_k in[env][k] * Wt[k][n]) for the 8 observations of a tile; thread = (env, 2 columns); K % 4 == 0
+__device__ __forceinline__ void tile_dense8(const float* in, const float* Wt, const float* bias, int K, int N, bool relu, float* out, int t) {
+    const int env = t >> 5, j = t & 31;
     if (N >= 64) {
-        float a0 = bias ? bias[4 * j] : 0.f, a1 = bias ? bias[4 * j + 1] : 0.f, a2 = bias ? bias[4 * j + 2] : 0.f, a3 = bias ? bias[4 * j + 3] : 0.f;
-        for (int k = 0; k < K; ++k) {
-            const float x = in[env * 64 + k];
-            const float4 w = *reinterpret_cast<const float4*>(Wt + k * N + 4 * j);
-            a0 = fmaf(x, w.x, a0); a1 = fmaf(x, w.y, a1); a2 = fmaf(x, w.z, a2); a3 = fmaf(x, w.w, a3);
+        float a0 = bias ? bias[2 * j] : 0.f, a1 = bias ? bias[2 * j + 1] : 0.f;
+        for (int k = 0; k < K; k += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(in + env * 64 + k);
+            const float2 w0 = *reinterpret_cast<const float2*>(Wt + k * N + 2 * j), w1 = *reinterpret_cast<const float2*>(Wt + (k + 1) * N + 2 * j);
+            const float2 w2 = *reinterpret_cast<const float2*>(Wt + (k + 2) * N + 2 * j), w3 = *reinterpret_cast<const float2*>(Wt + (k + 3) * N + 2 * j);
+            a0 = fmaf(x.x, w0.x, a0); a1 = fmaf(x.x, w0.y, a1);
+            a0 = fmaf(x.y, w1.x, a0); a1 = fmaf(x.y, w1.y, a1);
+            a0 = fmaf(x.z, w2.x, a0); a1 = fmaf(x.z, w2.y, a1);
+            a0 = fmaf(x.w, w3.x, a0); a1 = fmaf(x.w, w3.y, a1);
         }
-        if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
-        *reinterpret_cast<float4*>(out + env * 64 + 4 * j) = make_float4(a0, a1, a2, a3);
-    } else if (j < N) {
-        float a = bias ? bias[j] : 0.f;
-        for (int k = 0; k < K; ++k) a = fmaf(in[env * 64 + k], Wt[k * N + j], a);
-        out[env * 64 + j] = relu ? fmaxf(a, 0.f) : a;
+        if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+        *reinterpret_cast<float2*>(out + env * 64 + 2 * j) = make_float2(a0, a1);
+    } else {   // N <= 4 (the action head): lane = slice of k, butterfly sum over the warp
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = j; k < K; k += 32) {
+            const float x = in[env * 64 + k];
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+                if (n < N) acc[n] = fmaf(x, Wt[k * N + n], acc[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], off);
+        }
+        if (j < N) {
+            const float a = (j == 0 ? acc[0] : j == 1 ? acc[1] : j == 2 ? acc[2] : acc[3]) + (bias ? bias[j] : 0.f);
+            out[env * 64 + j] = relu ? fmaxf(a, 0.f) : a;
+        }
     }
 }
 
-__global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __restrict__ weights, const float* __restrict__ obs, int E,
-                                                         double eps, uint64_t seed, uint64_t step, const double* __restrict__ u_inj,
-                                                         int32_t* __restrict__ actions, float* __restrict__ qout) {
+__global__ void __launch_bounds__(2 * kEgoGT, 1) k_qnet_ego_tc(TcEgo d, const float* __restrict__ weights, const float* __restrict__ obs, int E,
+                                                                double eps, uint64_t seed, uint64_t step, const double* __restrict__ u_inj,
+                                                                int32_t* __restrict__ actions, float* __restrict__ qout) {
     extern __shared__ __align__(1024) unsigned char sm[];
-    const int tid = threadIdx.x, grp = tid >> 7, t = tid & 127, warp = t >> 5;   // group of 4 warps; warp w reads TMEM lanes 32 (w % 4) ..
-    const int env = t >> 4, ent = t & 15;         // row t of the group's tile = entity `ent` of observation `env`
+    const int tid = threadIdx.x, grp = tid / kEgoGT, t = tid % kEgoGT;
+    const int row = t & 127, cg = t >> 7, warp = t >> 5;   // warp w of the group reads TMEM lanes 32 (w % 4) ..
+    const int env = row >> 4, ent = row & 15;              // row of the group's tile = entity `ent` of observation `env`
+    const int denv = t >> 5, dj = t & 31;                  // (observation, column pair) mapping of the per-observation tail
     const int Fs = d.Fs, nin = d.NE * d.Fe;
     float* f32 = reinterpret_cast<float*>(sm + d.off_f32);
     float* s_wc = f32; float* s_ow1 = s_wc + Fs * Fs; float* s_ow2 = s_ow1 + Fs * Fs; float* s_pw = s_ow2 + Fs * Fs;
@@ -638,7 +660,7 @@ __global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + d.off_bar + 16);
 
     // ---- one-time setup: stacked B operands (split BF16, canonical layout) and the fp32 tail weights ----
-    for (int i = tid; i < 128 * 16; i += 256) {            // B1[n][k], K = 16: n < 64 others layer 1, n >= 64 ego layer 1
+    for (int i = tid; i < 128 * 16; i += 2 * kEgoGT) {            // B1[n][k], K = 16: n < 64 others layer 1, n >= 64 ego layer 1
         const int n = i >> 4, k = i & 15;
         float w = 0.f;
         if (k < d.Fe) w = __ldg(weights + (n < 64 ? d.oth_w1 : d.ego_w1) + k * Fs + (n & 63));
@@ -646,27 +668,27 @@ __global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __
         const uint32_t o = canon_off(n, k, 16);
         *reinterpret_cast<unsigned short*>(sm + d.off_b1hi + o) = hi; *reinterpret_cast<unsigned short*>(sm + d.off_b1lo + o) = lo;
     }
-    for (int i = tid; i < 128 * 64; i += 256) {            // B2[n][k], K = 64
+    for (int i = tid; i < 128 * 64; i += 2 * kEgoGT) {            // B2[n][k], K = 64
         const int n = i >> 6, k = i & 63;
         unsigned short hi, lo; split_bf16(__ldg(weights + (n < 64 ? d.oth_w2 : d.ego_w2) + k * Fs + (n & 63)), hi, lo);
         const uint32_t o = canon_off(n, k, 64);
         *reinterpret_cast<unsigned short*>(sm + d.off_b2hi + o) = hi; *reinterpret_cast<unsigned short*>(sm + d.off_b2lo + o) = lo;
     }
-    for (int i = tid; i < 192 * 64; i += 256) {            // B3[n][k] = [W_k ; W_v ; W_q]
+    for (int i = tid; i < 192 * 64; i += 2 * kEgoGT) {            // B3[n][k] = [W_k ; W_v ; W_q]
         const int n = i >> 6, k = i & 63;
         const int base = n < 64 ? d.wk : n < 128 ? d.wv : d.wq;
         unsigned short hi, lo; split_bf16(__ldg(weights + base + k * Fs + (n & 63)), hi, lo);
         const uint32_t o = canon_off(n, k, 64);
         *reinterpret_cast<unsigned short*>(sm + d.off_b3hi + o) = hi; *reinterpret_cast<unsigned short*>(sm + d.off_b3lo + o) = lo;
     }
-    for (int i = tid; i < Fs * Fs; i += 256) { s_wc[i] = __ldg(weights + d.wc + i); s_ow1[i] = __ldg(weights + d.o_w1 + i); s_ow2[i] = __ldg(weights + d.o_w2 + i); }
-    for (int i = tid; i < Fs * d.A; i += 256) s_pw[i] = __ldg(weights + d.p_w + i);
-    for (int i = tid; i < Fs; i += 256) {
+    for (int i = tid; i < Fs * Fs; i += 2 * kEgoGT) { s_wc[i] = __ldg(weights + d.wc + i); s_ow1[i] = __ldg(weights + d.o_w1 + i); s_ow2[i] = __ldg(weights + d.o_w2 + i); }
+    for (int i = tid; i < Fs * d.A; i += 2 * kEgoGT) s_pw[i] = __ldg(weights + d.p_w + i);
+    for (int i = tid; i < Fs; i += 2 * kEgoGT) {
         s_b1o[i] = __ldg(weights + d.oth_b1 + i); s_b1e[i] = __ldg(weights + d.ego_b1 + i);
         s_b2o[i] = __ldg(weights + d.oth_b2 + i); s_b2e[i] = __ldg(weights + d.ego_b2 + i);
         s_ob1[i] = __ldg(weights + d.o_b1 + i); s_ob2[i] = __ldg(weights + d.o_b2 + i);
     }
-    for (int i = tid; i < d.A; i += 256) s_pb[i] = __ldg(weights + d.p_b + i);
+    for (int i = tid; i < d.A; i += 2 * kEgoGT) s_pb[i] = __ldg(weights + d.p_b + i);
     if (t == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -678,22 +700,23 @@ __global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __
     tc_sync_before_mma();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem = tmem_base + (uint32_t)grp * 256u;
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t idesc192 = (1u << 4) | (1u << 7) | (1u << 10) | ((192u >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_hi = smem_u32(a_hi_p), a_lo = smem_u32(a_lo_p);
     uint32_t parity = 0;
     const int dk = Fs / d.H;
     const float inv = 1.0f / sqrtf((float)dk);
+    const uint32_t c0 = (uint32_t)cg * 32u;   // this thread's half of every 64-wide quantity
 
     const int tiles = (E + 7) / 8;
-    constexpr int kEgoPre = 15;   // 8 observations x (15 entities x 16 features) / 128 threads
+    constexpr int kEgoPre = 8;   // 8 observations x (15 entities x 16 features) / 256 threads, rounded up
     float pre[kEgoPre];
     auto fetch_obs = [&](int tl) {
         const int valid = tl < tiles ? min(8, E - tl * 8) * nin : 0;
 #pragma unroll
         for (int u = 0; u < kEgoPre; ++u) {
-            const int i = t + 128 * u;
+            const int i = t + kEgoGT * u;
             pre[u] = i < valid ? __ldg(obs + (size_t)tl * 8 * nin + i) : 0.f;
         }
     };
@@ -704,22 +727,21 @@ __global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __
         // runs under the previous tile's work ----
 #pragma unroll
         for (int u = 0; u < kEgoPre; ++u)
-            if (t + 128 * u < 8 * nin) s_x[t + 128 * u] = pre[u];
+            if (t + kEgoGT * u < 8 * nin) s_x[t + kEgoGT * u] = pre[u];
         group_sync(grp);
         fetch_obs(tile + 2 * gridDim.x);
-        // ---- A1[r][k] (K = 16): features of entity `ent` of observation `env`, zero padded ----
+        // ---- A1[r][k] (K = 16): features 8 cg .. 8 cg + 7 of entity `ent` of observation `env`, zero padded ----
         {
-            uint32_t ph[8], pl[8];
+            uint32_t ph[4], pl[4];
 #pragma unroll
-            for (int q2 = 0; q2 < 8; ++q2) {
-                const int k0 = 2 * q2, k1 = 2 * q2 + 1;
-                split_bf16x2((ent < d.NE && k0 < d.Fe) ? s_x[env * nin + ent * d.Fe + k0] : 0.f, (ent < d.NE && k1 < d.Fe) ? s_x[env * nin + ent * d.Fe + k1] : 0.f, ph[q2], pl[q2]);
+            for (int q2 = 0; q2 < 4; ++q2) {
+                const int k0 = 8 * cg + 2 * q2, k1 = k0 + 1;
+                split_bf16x2((ent < d.NE && k0 < d.Fe) ? s_x[env * nin + ent * d.Fe + k0] : 0.f,
+                             (ent < d.NE && k1 < d.Fe) ? s_x[env * nin + ent * d.Fe + k1] : 0.f, ph[q2], pl[q2]);
             }
-            const uint32_t o0 = canon_off(t, 0, 16), o1 = canon_off(t, 8, 16);
-            *reinterpret_cast<uint4*>(a_hi_p + o0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            *reinterpret_cast<uint4*>(a_hi_p + o1) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-            *reinterpret_cast<uint4*>(a_lo_p + o0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-            *reinterpret_cast<uint4*>(a_lo_p + o1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            const uint32_t o = canon_off(row, 8 * cg, 16);
+            *reinterpret_cast<uint4*>(a_hi_p + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4*>(a_lo_p + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
         // ---- two embedding layers: MMA (N = 128: others | ego) + epilogue selecting the row's half ----
         for (int layer = 0; layer < 2; ++layer) {
@@ -732,32 +754,29 @@ __global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __
             mbar_wait(smem_u32(bar), parity);
             parity ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const float* bo = layer == 0 ? s_b1o : s_b2o;
-            const float* be = layer == 0 ? s_b1e : s_b2e;
-            for (int c0 = 0; c0 < 64; c0 += 32) {
+            const float* bb = ent == 0 ? (layer == 0 ? s_b1e : s_b2e) : (layer == 0 ? s_b1o : s_b2o);   // ego | others bias
+            {
                 uint32_t vo[32], ve[32];
-                TT_TMEM_LD32(vo, tmem_row + (uint32_t)c0);
-                TT_TMEM_LD32(ve, tmem_row + (uint32_t)(64 + c0));
+                TT_TMEM_LD32(vo, tmem_row + c0);
+                TT_TMEM_LD32(ve, tmem_row + 64u + c0);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint32_t ph[4], pl[4];
                     float hv[8];
 #pragma unroll
                     for (int q2 = 0; q2 < 8; ++q2) {
-                        const int c = c0 + g * 8 + q2;
-                        const float acc = ent == 0 ? __uint_as_float(ve[g * 8 + q2]) + be[c] : __uint_as_float(vo[g * 8 + q2]) + bo[c];
-                        hv[q2] = fmaxf(acc, 0.f);
+                        const int c = (int)c0 + g * 8 + q2;
+                        hv[q2] = fmaxf(__uint_as_float(ent == 0 ? ve[g * 8 + q2] : vo[g * 8 + q2]) + bb[c], 0.f);
                     }
 #pragma unroll
-                    for (int q2 = 0; q2 < 4; ++q2) {
-                        split_bf16x2(hv[2 * q2], hv[2 * q2 + 1], ph[q2], pl[q2]);
-                    }
-                    const uint32_t o = canon_off(t, c0 + g * 8, 64);
+                    for (int q2 = 0; q2 < 4; ++q2) split_bf16x2(hv[2 * q2], hv[2 * q2 + 1], ph[q2], pl[q2]);
+                    const uint32_t o = canon_off(row, (int)c0 + g * 8, 64);
                     *reinterpret_cast<uint4*>(a_hi_p + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                     *reinterpret_cast<uint4*>(a_lo_p + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     if (layer == 1 && ent == 0) {   // the ego's embedding: residual of the attention block
-#pragma unroll
-                        for (int q2 = 0; q2 < 8; ++q2) s_ego[env * 64 + c0 + g * 8 + q2] = hv[q2];
+                        float4* eg = reinterpret_cast<float4*>(s_ego + env * 64 + (int)c0 + g * 8);
+                        eg[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                        eg[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
                     }
                 }
             }
@@ -772,39 +791,42 @@ __global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __
         parity ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {   // the ego rows publish their query
-            uint32_t v0[32], v1[32];
-            TT_TMEM_LD32(v0, tmem_row + 128u);
-            TT_TMEM_LD32(v1, tmem_row + 160u);
+            uint32_t v0[32];
+            TT_TMEM_LD32(v0, tmem_row + 128u + c0);
             if (ent == 0) {
+                float4* qd = reinterpret_cast<float4*>(s_q + env * 64 + (int)c0);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { s_q[env * 64 + j] = __uint_as_float(v0[j]); s_q[env * 64 + 32 + j] = __uint_as_float(v1[j]); }
+                for (int j = 0; j < 8; ++j)
+                    qd[j] = make_float4(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1]), __uint_as_float(v0[4 * j + 2]), __uint_as_float(v0[4 * j + 3]));
             }
         }
         group_sync(grp);
-        // ---- attention (models.py:370-388): scores / sqrt(d_k), masked_fill(-1e9), softmax over the entities ----
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;  // per head probability of this row (H <= 4, d_k = 64 >> hshift... a power of two)
-        const int hshift = d.H == 1 ? 6 : d.H == 2 ? 5 : 4;
+        // ---- attention (models.py:370-388): scores / sqrt(d_k), masked_fill(-1e9), softmax over the entities.  The thread's 32
+        // key columns hold two heads (H = 4: heads 2 cg, 2 cg + 1), one head (H = 2: head cg) or half a head (H = 1) ----
+        float p_lo, p_hi;   // probability of this row for the head of its columns 0..15 / 16..31
         {
-            uint32_t k0[32], k1[32];
-            TT_TMEM_LD32(k0, tmem_row + 0u);
-            TT_TMEM_LD32(k1, tmem_row + 32u);
+            uint32_t kk[32];
+            TT_TMEM_LD32(kk, tmem_row + c0);
             const bool masked = ent < d.NE ? s_x[env * nin + ent * d.Fe + d.pidx] < 0.5f : true;
-            float sc[4] = {0.f, 0.f, 0.f, 0.f};
-            const float* qrow = s_q + env * 64;
+            const float4* qrow = reinterpret_cast<const float4*>(s_q + env * 64 + c0);
+            float sc_lo = 0.f, sc_hi = 0.f;
 #pragma unroll
-            for (int c = 0; c < 64; ++c) {   // static register indices; the head of column c is c >> hshift
-                const float kv = __uint_as_float(c < 32 ? k0[c & 31] : k1[c & 31]);
-                const int h = c >> hshift;
-                const float qc = qrow[c];
-                sc[0] = h == 0 ? fmaf(qc, kv, sc[0]) : sc[0];
-                sc[1] = h == 1 ? fmaf(qc, kv, sc[1]) : sc[1];
-                sc[2] = h == 2 ? fmaf(qc, kv, sc[2]) : sc[2];
-                sc[3] = h == 3 ? fmaf(qc, kv, sc[3]) : sc[3];
+            for (int c = 0; c < 4; ++c) {
+                const float4 ql = qrow[c], qh = qrow[4 + c];
+                sc_lo = fmaf(ql.x, __uint_as_float(kk[4 * c]), sc_lo); sc_lo = fmaf(ql.y, __uint_as_float(kk[4 * c + 1]), sc_lo);
+                sc_lo = fmaf(ql.z, __uint_as_float(kk[4 * c + 2]), sc_lo); sc_lo = fmaf(ql.w, __uint_as_float(kk[4 * c + 3]), sc_lo);
+                sc_hi = fmaf(qh.x, __uint_as_float(kk[16 + 4 * c]), sc_hi); sc_hi = fmaf(qh.y, __uint_as_float(kk[16 + 4 * c + 1]), sc_hi);
+                sc_hi = fmaf(qh.z, __uint_as_float(kk[16 + 4 * c + 2]), sc_hi); sc_hi = fmaf(qh.w, __uint_as_float(kk[16 + 4 * c + 3]), sc_hi);
             }
-            float pr[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                float v = sc[h] * inv;
+            if (d.H != 4) { sc_lo += sc_hi; sc_hi = sc_lo; }
+            if (d.H == 1) {   // the two halves of the single head meet through shared memory (s_t0 is free here)
+                s_t0[cg * 128 + row] = sc_lo;
+                group_sync(grp);
+                sc_lo = s_t0[row] + s_t0[128 + row];
+                sc_hi = sc_lo;
+            }
+            auto softmax16 = [&](float sc) {
+                float v = sc * inv;
                 if (masked) v = -1e9f;
                 if (ent >= d.NE) v = -INFINITY;  // pad row: not an entity
                 float m = v;
@@ -814,42 +836,36 @@ __global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __
                 float sum = ev;
 #pragma unroll
                 for (int off = 1; off < 16; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-                pr[h] = ev / sum;
-            }
-            p0 = pr[0]; p1 = pr[1]; p2 = pr[2]; p3 = pr[3];
+                return ev / sum;
+            };
+            p_lo = softmax16(sc_lo);
+            p_hi = d.H == 4 ? softmax16(sc_hi) : p_lo;
         }
         {   // p-weighted value rows -> scratch (the A operand is free: its MMA has completed)
-            uint32_t v0[32], v1[32];
-            TT_TMEM_LD32(v0, tmem_row + 64u);
-            TT_TMEM_LD32(v1, tmem_row + 96u);
-            float* row = scratch + t * 64;
+            uint32_t vv[32];
+            TT_TMEM_LD32(vv, tmem_row + 64u + c0);
+            float* orow = scratch + row * 64 + c0;
 #pragma unroll
-            for (int c = 0; c < 64; c += 4) {
-                float o[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int h = (c + u) >> hshift;
-                    const float pw = h == 0 ? p0 : h == 1 ? p1 : h == 2 ? p2 : p3;
-                    o[u] = pw * __uint_as_float(c + u < 32 ? v0[(c + u) & 31] : v1[(c + u) & 31]);
-                }
-                *reinterpret_cast<float4*>(row + c) = make_float4(o[0], o[1], o[2], o[3]);
+            for (int c = 0; c < 32; c += 4) {
+                const float pw = c < 16 ? p_lo : p_hi;
+                *reinterpret_cast<float4*>(orow + c) = make_float4(pw * __uint_as_float(vv[c]), pw * __uint_as_float(vv[c + 1]),
+                                                                   pw * __uint_as_float(vv[c + 2]), pw * __uint_as_float(vv[c + 3]));
             }
         }
         group_sync(grp);
-        {   // value[env][c] = sum over the entities; thread = (env, 4 columns)
-            const int j = ent;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        {   // value[env][c] = sum over the entities; thread = (env, 2 columns)
+            float2 a = make_float2(0.f, 0.f);
             for (int n = 0; n < d.NE; ++n) {
-                const float4 t = *reinterpret_cast<const float4*>(scratch + (env * 16 + n) * 64 + 4 * j);
-                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                const float2 v = *reinterpret_cast<const float2*>(scratch + (denv * 16 + n) * 64 + 2 * dj);
+                a.x += v.x; a.y += v.y;
             }
-            *reinterpret_cast<float4*>(s_val + env * 64 + 4 * j) = a;
+            *reinterpret_cast<float2*>(s_val + denv * 64 + 2 * dj) = a;
         }
         group_sync(grp);
         // ---- (attention_combine(value) + ego) / 2 (models.py:193), output MLP (models.py:69-76), action ----
         tile_dense8(s_val, s_wc, nullptr, Fs, Fs, false, s_t0, t);
         group_sync(grp);
-        for (int c = ent * 4; c < ent * 4 + 4; ++c) s_t0[env * 64 + c] = (s_t0[env * 64 + c] + s_ego[env * 64 + c]) / 2.f;
+        for (int c = 2 * dj; c < 2 * dj + 2; ++c) s_t0[denv * 64 + c] = (s_t0[denv * 64 + c] + s_ego[denv * 64 + c]) / 2.f;
         group_sync(grp);
         tile_dense8(s_t0, s_ow1, s_ob1, Fs, Fs, true, s_t1, t);
         group_sync(grp);
@@ -857,7 +873,7 @@ __global__ void __launch_bounds__(256, 1) k_qnet_ego_tc(TcEgo d, const float* __
         group_sync(grp);
         tile_dense8(s_t0, s_pw, s_pb, Fs, d.A, false, s_t1, t);
         group_sync(grp);
-        if (ent == 0 && env < nenv) {
+        if (cg == 0 && ent == 0 && env < nenv) {
             const int e = e0 + env;
             const float* qv = s_t1 + env * 64;
             if (qout) for (int a = 0; a < d.A; ++a) qout[(size_t)e * d.A + a] = qv[a];
@@ -1077,7 +1093,7 @@ static int qnet_launch(ttrl_qnet* q, const float* obs_dev, int E, double eps, ui
         int grid = (E + 15) / 16;   // two tiles of 8 observations in flight per CTA
         if (grid > q->n_sms) grid = q->n_sms;
         if (grid < 1) grid = 1;
-        k_qnet_ego_tc<<<grid, 256, q->tce.total, (cudaStream_t)stream>>>(q->tce, q->d_weights, obs_dev, E, eps, seed, step, u_dev, actions_dev, q_dev);
+        k_qnet_ego_tc<<<grid, 2 * kEgoGT, q->tce.total, (cudaStream_t)stream>>>(q->tce, q->d_weights, obs_dev, E, eps, seed, step, u_dev, actions_dev, q_dev);
         q->launches++;
         QCK(cudaGetLastError());
         return 0;
