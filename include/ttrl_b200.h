@@ -425,7 +425,10 @@ int ttrl_dqn_grad(ttrl_dqn* q, const float* const* value_params /* 6 device poin
 int ttrl_dqn_adam(ttrl_dqn* q, float* const* params, float* const* exp_avg, float* const* exp_avg_sq, const float* grad_dev, int64_t step,
                   double lr, double beta1, double beta2, double eps, double weight_decay, double grad_clamp, double grad_scale,
                   float* rollout_blob_dev, void* stream);
-/* device pointer of a ttrl_qnet's float32 weight blob (layout of ttrl_qnet_create) for ttrl_dqn_adam's rollout_blob_dev */
+/* device pointer of a ttrl_qnet's float32 weight blob (layout of ttrl_qnet_create) for ttrl_dqn_adam's rollout_blob_dev.
+ * Once it has been handed out the library assumes the caller's kernels write the blob in place: the tensor-core MLP path
+ * then rebuilds its derived weight image (one small extra launch) on every ttrl_qnet_act instead of only after
+ * ttrl_qnet_set_weights. */
 float* ttrl_qnet_weights_dev(ttrl_qnet* q);
 
 #ifdef __cplusplus
