@@ -44,6 +44,7 @@ constexpr double kVehLength = 5.0;   // kinematics.py:21
 constexpr double kVehWidth = 2.0;    // kinematics.py:23
 constexpr int kStatFields = 10;      // ttrl_episode_stats
 struct alignas(16) d2 { double x, y; };  // 16-byte pair (one LDS.128 on the device)
+struct alignas(8) f2 { float x, y; };     // 8-byte pair (one LDS.64)
 
 // Read-only scene description, resident in global memory (L1/L2 hot: ~12 KB).
 struct SceneDev {
@@ -1100,21 +1101,20 @@ TT_HD void collide_all(C& c, Exec& ex) {
     const int n = st->n;
     // K0: float copies for the pre-filter.  |x_hi - x_lo| > radius_lo + 1 cm in float implies the exact squared-distance guard
     // rejects the pair (float rounding of positions up to 1e4 m is < 1 mm): the filter can only skip pairs the guard would skip.
-    float* xf = reinterpret_cast<float*>(st->acc2);  // [V] x, [V] radius: acc2 is rewritten by phase C2 before its next read
-    float* rf = xf + C::V;
+    f2* xr = reinterpret_cast<f2*>(st->acc2);  // [V] (x, radius): acc2 is rewritten by phase C2 before its next read
     ex.parn(n, [&](int k) {
-        xf[k] = (float)st->pos[k].x;
-        rf[k] = st->thr2[k] < 0 ? -1.0f : (float)sqrt(st->thr2[k]) * 1.000001f + 0.01f;
+        xr[k] = f2{(float)st->pos[k].x, st->thr2[k] < 0 ? -1.0f : (float)sqrt(st->thr2[k]) * 1.000001f + 0.01f};
     });
     // K1
     ex.parn(n, [&](int k) {
         const int half = n / 2;
-        const float xk = xf[k], rk = rf[k];
-        for (int m = 1; m <= half; ++m) {
+        const int mmax = (2 * half == n && k >= half) ? half - 1 : half;  // even n: the diametral pair is visited once
+        const f2 me = xr[k];
+        for (int m = 1; m <= mmax; ++m) {
             int p = k + m;
             if (p >= n) p -= n;
-            if (2 * m == n && k >= half) break;  // even n: the diametral pair is visited once
-            if (fabsf(xf[p] - xk) > (k < p ? rk : rf[p])) continue;
+            const f2 other = xr[p];
+            if (fabsf(other.x - me.x) > (k < p ? me.y : other.y)) continue;
             const int lo = k < p ? k : p, hi = k < p ? p : k;
             if (!collide_candidate(c, lo, hi)) continue;
             const int slot = ex.atomic_add(&st->n_pair, 1);
