@@ -112,3 +112,30 @@ def test_curved_lane_task_list_on_scenes_that_do_not_use_it_by_default(scene, mo
     obs, reward, term, trunc, _ = emu.step(st, g["action"].astype(np.int32))
     T.compare_states(st, T.batch_state(g, "after"), T.TOL_STEP, f"{scene} step, task form")
     np.testing.assert_allclose(obs.reshape(g["obs"].shape), g["obs"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("n", [50, 200])
+def test_collision_candidate_scan_vs_oracle(n):
+    """The collision candidate scan (collide_all: float pre-filter on x with the lower index's guard radius, half-ring over a
+    doubled list) on adversarial layouts: clusters far apart, negative x, x on round values +- 1e-9, very fast vehicles (guard
+    radius > 10 m), one long pile-up, distant clusters interleaved in index order -- emulated device logic == oracle per sub-step,
+    and the collisions did happen.  (Written for a cell-list form of the scan, which was measured slower and dropped.)"""
+    _, table, cfg, cfgd = T.highway_scene(n, 3.0)
+    emu, orc = Emulator(cfg, table), O.Oracle(cfg, table)
+    a = scenes.make_highway_state(6, cfgd, seed=11)
+    rng = np.random.default_rng(5)
+    x = a.veh_d[abi.D_X]
+    x[0, : n // 2] += 640.0                                   # two clusters exactly one bucket span apart
+    x[1, :n] -= x[1, :n].mean() + 3.0                          # negative x, cluster across 0
+    x[2, :n] = np.round(x[2, :n] / 10.0) * 10.0 + rng.choice([-1e-9, 0.0, 1e-9], size=n)  # on cell boundaries
+    a.veh_d[abi.D_SPEED, 3, : n // 3] = 75.0                   # guard radius 5.39 + 75 / 15 > cell width
+    x[4, :n] = 200.0 + np.arange(n) * 2.6                      # one long pile-up across many cells
+    x[5, : n // 2] += 1280.0
+    x[5, n // 2: n] = x[5, : n - n // 2] - 1280.0 + rng.uniform(-3, 3, size=n - n // 2)  # aliased buckets that DO hold real neighbours two spans away
+    b = a.copy()
+    for k in range(6):
+        emu.substep(a, None)
+        orc.substep(b, None)
+        T.compare_states(a, b, 1e-9, f"scan sub-step {k}")
+    crashed = (a.veh_i[abi.I_FLAGS] & abi.FL_CRASHED) != 0
+    assert crashed[4].sum() > n // 2 and crashed[2].sum() > 0

@@ -25,6 +25,7 @@
 // Reference citations are relative to /root/reference.
 #pragma once
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 #include "../../include/ttrl_b200.h"
 
@@ -83,8 +84,8 @@ struct alignas(16) EnvState {
     double steer[V], acc[V], tspeed[V], timer[V], delta[V];
     double thr2[V];      // collision pre-check guard: (diag + v dt)^2 (1 + 1e-12), or -1 when diag + v dt < 0
     double acc2[V];      // IDM acceleration w.r.t. the target lane (vehicles changing lane); dead after the integration: its
-                         // storage then holds the collision scan's float pre-filter (x and guard radius per vehicle)
-    double tsteer[V];    // tan(steering command) of this sub-step (by-product of steering_control, used by integrate)
+                         // storage and tsteer's then hold the collision scan's float pre-filter (collide_all)
+    double tsteer[V];    // tan(steering command) of this sub-step (by-product of steering_control, used by integrate); follows acc2
     double mq_a[9 * MB];  // MOBIL IDM evaluations of the batch
     int32_t lane[V], tlane[V], flags[V], sidx[V], rlen[V], ytimer[V];
     uint32_t rroad[TTRL_ROUTE_WORDS][V], rlanew[TTRL_ROUTE_WORDS][V];  // route entry k: byte k % 4 of word k / 4 (road index / lane id)
@@ -1101,20 +1102,24 @@ TT_HD void collide_all(C& c, Exec& ex) {
     const int n = st->n;
     // K0: float copies for the pre-filter.  |x_hi - x_lo| > radius_lo + 1 cm in float implies the exact squared-distance guard
     // rejects the pair (float rounding of positions up to 1e4 m is < 1 mm): the filter can only skip pairs the guard would skip.
-    f2* xr = reinterpret_cast<f2*>(st->acc2);  // [V] (x, radius): acc2 is rewritten by phase C2 before its next read
+    // (x, guard radius) per vehicle as float pairs, the list written twice back to back (entries k and n + k) so that the half-ring
+    // scan indexes k + m without wrapping.  Storage: acc2 and tsteer, both dead between the integration and the next controls.
+    static_assert(offsetof(EnvState<C::V>, tsteer) == offsetof(EnvState<C::V>, acc2) + sizeof(double) * C::V, "acc2 and tsteer must be adjacent");
+    f2* xr = reinterpret_cast<f2*>(st->acc2);
     ex.parn(n, [&](int k) {
-        xr[k] = f2{(float)st->pos[k].x, st->thr2[k] < 0 ? -1.0f : (float)sqrt(st->thr2[k]) * 1.000001f + 0.01f};
+        const f2 v = f2{(float)st->pos[k].x, st->thr2[k] < 0 ? -1.0f : (float)sqrt(st->thr2[k]) * 1.000001f + 0.01f};
+        xr[k] = v;
+        xr[n + k] = v;
     });
     // K1
     ex.parn(n, [&](int k) {
         const int half = n / 2;
         const int mmax = (2 * half == n && k >= half) ? half - 1 : half;  // even n: the diametral pair is visited once
         const f2 me = xr[k];
-        for (int m = 1; m <= mmax; ++m) {
-            int p = k + m;
-            if (p >= n) p -= n;
-            const f2 other = xr[p];
-            if (fabsf(other.x - me.x) > (k < p ? me.y : other.y)) continue;
+        for (int q = k + 1; q <= k + mmax; ++q) {
+            const f2 other = xr[q];
+            if (fabsf(other.x - me.x) > (q < n ? me.y : other.y)) continue;  // the guard radius is the lower index's
+            const int p = q < n ? q : q - n;
             const int lo = k < p ? k : p, hi = k < p ? p : k;
             if (!collide_candidate(c, lo, hi)) continue;
             const int slot = ex.atomic_add(&st->n_pair, 1);
