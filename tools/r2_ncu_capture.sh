@@ -3,9 +3,10 @@
 # exceed what gpurun copies back): <tag> <kernel mangled substring, e.g. k_stepILi50ELi1> <launch-skip> <bench args...>
 tag=$1; kern=$2; skip=$3; shift 3
 rep=/tmp/$tag.ncu-rep
-timeout 500 ncu --set full --import-source on --clock-control none -k regex:k_step --launch-skip $skip --launch-count 2 -f -o /tmp/$tag python bench.py "$@" --no-cpu-baseline > gpurun_out/${tag}_ncu.log 2>&1
+timeout 500 ncu --set full --import-source on --clock-control none -k regex:k_step --launch-skip $skip --launch-count ${NCU_COUNT:-2} -f -o /tmp/$tag python bench.py "$@" --no-cpu-baseline > gpurun_out/${tag}_ncu.log 2>&1
 python tools/ncu_summary.py $rep > gpurun_out/${tag}_raw.txt 2>&1
-python tools/ncu_lines.py $rep topotrafficrl_b200/csrc/build $kern 60 > gpurun_out/${tag}_lines.txt 2>&1
+src=topotrafficrl_b200/csrc/build; [ -d $src ] || src=topotrafficrl_b200/csrc/libttrl_b200.so   # the build directory does not travel to the GPU box
+python tools/ncu_lines.py $rep $src $kern 60 > gpurun_out/${tag}_lines.txt 2>&1
 ncu -i $rep --page raw --csv 2>/dev/null | python -c "
 import csv,sys
 rows=list(csv.reader(sys.stdin))
