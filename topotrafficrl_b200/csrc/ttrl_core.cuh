@@ -1101,6 +1101,11 @@ TT_HDN void collide_serial(C& c, int k) {
     if (has_imp) { st->imp[k] = d2{ix, iy}; st->flags[k] |= TTRL_FL_HAS_IMPACT; }
     if (crashed) st->flags[k] |= TTRL_FL_CRASHED;
 }
+template <class C>
+TT_HD void advance_substep_counters(C& c) {
+    c.st->steps += 1;
+    if (!C::kPlain && c.sc->cfg.regulated) c.st->road_steps += 1;
+}
 template <class C, class Exec>
 TT_HD void collide_all(C& c, Exec& ex) {
     auto* st = c.st;
@@ -1116,8 +1121,11 @@ TT_HD void collide_all(C& c, Exec& ex) {
         xr[k] = v;
         xr[n + k] = v;
     });
-    // K1
+    // K1 (vehicle 0's thread also advances the sub-step counters: nothing below reads them, and the barrier that ends this loop
+    // publishes them -- one team barrier per sub-step less than a separate update)
+    if (n == 0) { if (ex.first()) advance_substep_counters(c); ex.sync(); return; }
     ex.parn(n, [&](int k) {
+        if (k == 0) advance_substep_counters(c);
         const int half = n / 2;
         const int mmax = (2 * half == n && k >= half) ? half - 1 : half;  // even n: the diametral pair is visited once
         const f2 me = xr[k];
@@ -1380,9 +1388,8 @@ TT_HD void substep_integrate(C& c, Exec& ex) {
 template <class C, class Exec>
 TT_HD void substep_collide(C& c, Exec& ex) {
     auto* st = c.st;
-    collide_all(c, ex);
-    if (ex.first()) { st->steps += 1; if (!C::kPlain && c.sc->cfg.regulated) st->road_steps += 1; }
-    ex.sync();
+    collide_all(c, ex);  // advances st->steps / st->road_steps; ends on a team barrier on every path
+    (void)st;
 }
 template <class C, class Exec>
 TT_HD void env_substep(C& c, Exec& ex, const int32_t* actions) {
