@@ -600,22 +600,27 @@ __device__ __forceinline__ void tc_group_sync_before_mma(int grp) {
     group_sync(grp);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// out[env][n] = act(bias[n] + sum_k in[env][k] * Wt[k][n]) for the 8 observations of a tile; thread = (env, 2 columns); K % 4 == 0
+// out[env][n] = act(bias[n] + sum_k in[env][k] * Wt[k][n]) for the 8 observations of a tile; K % 4 == 0.  Wide layers: thread =
+// (pair of observations, one column) -- a warp reads 32 consecutive weights (one shared-memory wavefront per k) and two broadcast
+// input vectors per four k, 6 wavefronts per 8 FMAs instead of 9 for (observation, column pair)
 __device__ __forceinline__ void tile_dense8(const float* in, const float* Wt, const float* bias, int K, int N, bool relu, float* out, int t) {
     const int env = t >> 5, j = t & 31;
     if (N >= 64) {
-        float a0 = bias ? bias[2 * j] : 0.f, a1 = bias ? bias[2 * j + 1] : 0.f;
+        const int col = t & 63, e0 = (t >> 6) * 2;
+        float a0 = bias ? bias[col] : 0.f, a1 = a0;
+        const float* in0 = in + e0 * 64;
+        const float* in1 = in0 + 64;
         for (int k = 0; k < K; k += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(in + env * 64 + k);
-            const float2 w0 = *reinterpret_cast<const float2*>(Wt + k * N + 2 * j), w1 = *reinterpret_cast<const float2*>(Wt + (k + 1) * N + 2 * j);
-            const float2 w2 = *reinterpret_cast<const float2*>(Wt + (k + 2) * N + 2 * j), w3 = *reinterpret_cast<const float2*>(Wt + (k + 3) * N + 2 * j);
-            a0 = fmaf(x.x, w0.x, a0); a1 = fmaf(x.x, w0.y, a1);
-            a0 = fmaf(x.y, w1.x, a0); a1 = fmaf(x.y, w1.y, a1);
-            a0 = fmaf(x.z, w2.x, a0); a1 = fmaf(x.z, w2.y, a1);
-            a0 = fmaf(x.w, w3.x, a0); a1 = fmaf(x.w, w3.y, a1);
+            const float4 x0 = *reinterpret_cast<const float4*>(in0 + k), x1 = *reinterpret_cast<const float4*>(in1 + k);
+            const float w0 = Wt[k * N + col], w1 = Wt[(k + 1) * N + col], w2 = Wt[(k + 2) * N + col], w3 = Wt[(k + 3) * N + col];
+            a0 = fmaf(x0.x, w0, a0); a1 = fmaf(x1.x, w0, a1);
+            a0 = fmaf(x0.y, w1, a0); a1 = fmaf(x1.y, w1, a1);
+            a0 = fmaf(x0.z, w2, a0); a1 = fmaf(x1.z, w2, a1);
+            a0 = fmaf(x0.w, w3, a0); a1 = fmaf(x1.w, w3, a1);
         }
         if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-        *reinterpret_cast<float2*>(out + env * 64 + 2 * j) = make_float2(a0, a1);
+        out[e0 * 64 + col] = a0;
+        out[(e0 + 1) * 64 + col] = a1;
     } else {   // N <= 4 (the action head): lane = slice of k, butterfly sum over the warp
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         for (int k = j; k < K; k += 32) {
