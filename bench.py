@@ -318,7 +318,9 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step_seconds = 2.0
+    # a "step" of this arm is a bounded sample of the workload on the host cores: 2 s each, less when many steps are asked for, so
+    # that the whole run stays within ~2.5 minutes
+    per_step_seconds = min(2.0, max(0.25, 150.0 / max(args.warmup + args.steps, 1)))
     vals, evals = [], []
     cores = sample = None
     for k in range(args.warmup + args.steps):
